@@ -1,0 +1,156 @@
+/* pk_b200.h — C ABI of the B200-native acoustic-model hot path (libpk_b200.so).
+ *
+ * Boundary: the reference (mravanelli/pytorch-kaldi) has no native code; its hot path is the
+ * stock-PyTorch forward/backward of the `neural_networks.py` module zoo called from
+ * `utils.forward_model` (utils.py:2330/2339) inside `core.run_nn`'s minibatch loop
+ * (core.py:577-699).  These entry points are what the `torch.autograd.Function` shims of the
+ * drop-in `neural_networks.py` bind (through ctypes); each comment names the reference code
+ * the call replaces.  See INTEGRATION.md for the reference-side binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated otherwise; no torch types cross the ABI;
+ *   - `stream` is a cudaStream_t passed as void* (the caller's current stream);
+ *   - return value 0 = ok; non-zero = error, message via pk_last_error() (thread-local);
+ *     nothing aborts or exits;
+ *   - "row-major"      [rows][ld]  : rows = frames n = t*B + b (utils.py:2323 t-major order);
+ *     "channel-major"  [chan][ld]  : one row per feature/unit, ld >= T*B, column = t*B + b;
+ *   - fp16 operand buffers need ld % 8 == 0 and 16-byte aligned bases (TMA requirement),
+ *     fp32 (tf32) operand buffers need ld % 4 == 0.
+ */
+#ifndef PK_B200_H_
+#define PK_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PK_ABI_VERSION 1
+
+/* operand types for pk_gemm_tn */
+#define PK_F16 0
+#define PK_TF32 2
+
+/* activation ids == neural_networks.act_fun (neural_networks.py:36-57) */
+#define PK_ACT_RELU 0
+#define PK_ACT_TANH 1
+#define PK_ACT_SIGMOID 2
+#define PK_ACT_LEAKY_RELU 3
+#define PK_ACT_ELU 4
+#define PK_ACT_LINEAR 5
+
+/* recurrent cell kinds (neural_networks.py classes liGRU :997, RNN :1319, GRU :486,
+ * minimalGRU :1158, LSTM :300) */
+#define PK_CELL_LIGRU 0
+#define PK_CELL_RNN 1
+#define PK_CELL_GRU 2
+#define PK_CELL_MGRU 3
+#define PK_CELL_LSTM 4
+/* optional tuning flags OR-ed into `cell`: CTAs per cluster of the persistent kernel
+ * (default: chosen from H) */
+#define PK_REC_CLUSTER8 0x800
+#define PK_REC_CLUSTER16 0x1000
+#define PK_CELL_MASK 0xff
+
+const char* pk_last_error(void);
+int pk_version(void);
+
+/* C[M][ldc] (fp32) = alpha * (*alpha_dev) * A[M][lda] . B[N][ldb]^T  (+ bias) ; both operands
+ * K-major.  tcgen05 / TMEM / TMA kernel.  bias_mode 1: bias[n], 2: bias[m].  rowstats: optional
+ * [2][M] doubles accumulating per-row sum and sum of squares of the OUTPUT (BatchNorm batch
+ * statistics of a channel-major projection).  accumulate: C += ...; split_k > 1 partitions K
+ * over gridDim.z with fp32 atomics.
+ * Replaces: nn.Linear forward/backward GEMMs (neural_networks.py:1114-1115, :432-435,
+ * :609-611, :138-148 and their autograd transposes). */
+int pk_gemm_tn(int dtype, int M, int N, int K, const void* A, int64_t lda, const void* B,
+               int64_t ldb, float* C, int64_t ldc, const float* bias, int bias_mode,
+               double* rowstats, float alpha, const float* alpha_dev, int accumulate, int split_k,
+               void* stream);
+
+/* outT[c][r] = in[r][c] (fp32, optional) plus optional fp16 copies scaled by *scale_dev:
+ * outT16 (channel-major) and in16 (row-major).  Replaces flip/cat/view shuffles
+ * (neural_networks.py:1095-1097, :1144-1150) and feeds the K-major GEMM operands. */
+int pk_transpose_f32(const float* in, int64_t ldi, int R, int C, float* outT, int64_t ldo,
+                     void* outT16, int64_t ldo16, void* in16, int64_t ldi16,
+                     const float* scale_dev, void* stream);
+int pk_convert_f16(const float* in, int64_t ldi, int R, int C, void* out, int64_t ldo,
+                   const float* scale_dev, void* stream);
+
+/* *scale_out = 2^k with amax(x) * 2^k in [2^(target_log2-1), 2^target_log2): the loss scale
+ * that keeps fp16 gradient operands in range.  amax_scratch: 1 float. */
+int pk_amax_scale(const float* x, int64_t ld, int R, int C, float target_log2,
+                  float* amax_scratch, float* scale_out, void* stream);
+
+/* nn.BatchNorm1d(C, momentum) over the projection rows (neural_networks.py:1070-1071,
+ * :1118-1124): stats = [2][C] doubles (sum, sumsq over the n_unique = T*B de-duplicated rows);
+ * n_ref = number of rows the reference normalised (T*2B when bidirectional) for the unbiased
+ * running_var.  Writes folded scale = gamma*rstd, shift = beta - mean*scale, and
+ * mean/rstd for the backward.  training=0 uses running stats. */
+int pk_bn_finalize(const double* stats, int C, int64_t n_unique, int64_t n_ref,
+                   const float* gamma, const float* beta, float eps, float momentum,
+                   int training, float* running_mean, float* running_var, int64_t* num_batches,
+                   float* scale, float* shift, float* mean_out, float* rstd_out, void* stream);
+/* no normalisation: scale = 1, shift = bias (or 0) */
+int pk_fill_scale_shift(const float* bias, int C, float* scale, float* shift, void* stream);
+
+/* Backward of the (optional) BatchNorm on the de-duplicated projection.  GT = [ndir][C][ldt]
+ * gradients w.r.t. the normalised pre-activations in natural time (both directions are
+ * summed), PT = [C][ldp] raw projections.  Outputs dgamma/dbeta [C] (dbeta = bias grad when
+ * use_bn=0) and dP as fp16 * (*gscale) in channel-major (dPT16) and row-major (dP16) form.
+ * sums_scratch: 2*C doubles. */
+int pk_bn_bwd(int C, int ndir, int64_t n, const float* GT, int64_t ldt, const float* PT,
+              int64_t ldp, int use_bn, int training, const float* mean, const float* rstd,
+              const float* gamma, const float* gscale, float* dgamma, float* dbeta, void* dPT16,
+              int64_t ld16t, void* dP16, int64_t ld16r, double* sums_scratch, void* stream);
+
+/* One recurrent layer, all T steps in ONE persistent cluster kernel.
+ *   PT    [G*H][ldp]  channel-major projections W x (G gates: liGRU h,z), shared by both
+ *                     directions (direction 1 reads time T-1-k);
+ *   scale/shift [G*H] folded BatchNorm (or 1 / bias);   U [G*H][H] recurrent weights (fp32);
+ *   mask  [ndir*B][H] dropout mask of the candidate (neural_networks.py:1102-1111) or NULL
+ *                     with mask_scalar = 1-p (eval);
+ * outputs (any may be NULL): Y32 [T*B][ldy32] row-major [t,b,d*H+u] (= module output),
+ * Y16 fp16 copy (next layer's GEMM operand), HT/HT16/ZT/HCT channel-major [ndir*H][ldt]
+ * (state, update gate, masked candidate — saved for the backward).
+ * Replaces: the `for k in range(x.shape[0])` loops (liGRU neural_networks.py:1130-1141). */
+int pk_rnn_layer_fwd(int cell, int T, int B, int H, int ndir, int act, const float* PT,
+                     int64_t ldp, const float* scale, const float* shift, const float* U,
+                     const float* mask, float mask_scalar, float* Y32, int64_t ldy32, void* Y16,
+                     int64_t ldy16, float* HT, void* HT16, float* ZT, float* HCT, int64_t ldt,
+                     void* stream);
+
+/* Reverse-time persistent kernel: dYT [ndir*H][ldt] channel-major gradient w.r.t. the layer
+ * output -> GT [ndir][G*H][ldt] fp32 gradients w.r.t. the normalised pre-activations
+ * (+ GT16 = fp16 * (*gscale), the operand of dU = sum_t G_t^T h_{t-1}).
+ * Replaces: autograd through the per-step graph (core.py:634 loss.backward()). */
+int pk_rnn_layer_bwd(int cell, int T, int B, int H, int ndir, int act, const float* dYT,
+                     const float* HT, const float* ZT, const float* HCT, int64_t ldt,
+                     const float* U, const float* mask, float mask_scalar, const float* gscale,
+                     float* GT, void* GT16, void* stream);
+
+/* In place: logits [N][ld] -> log-posteriors (act_fun("softmax") = LogSoftmax(dim=1),
+ * neural_networks.py:53-54).  With labels (int64, utils.py:2348-2352): acc[0] = sum_n
+ * -logp[n,lab[n]] (nn.NLLLoss numerator, utils.py:2361), acc[1] = #(argmax != lab)
+ * (cost_err, utils.py:2379-2380).  acc: 2 doubles, zeroed by the callee. */
+int pk_logsoftmax_nll(int N, int S, float* logits, int64_t ld, const int64_t* labels,
+                      double* acc, void* stream);
+
+/* Gradient w.r.t. the logits as scaled fp16 GEMM operands (row-major d16, channel-major dT16)
+ * and dbias [S].  Fused-NLL mode (dlogp NULL): (exp(logp) - onehot(lab)) * gcoef.  General mode:
+ * dlogp - exp(logp) * rowsum(dlogp) (rowsum_scratch: N floats). */
+int pk_logsoftmax_bwd(int N, int S, const float* logp, int64_t ld, const int64_t* labels,
+                      const float* dlogp, int64_t lddl, float gcoef, float out_scale, void* d16,
+                      int64_t ld16, void* dT16, int64_t ld16t, float* dbias,
+                      float* rowsum_scratch, void* stream);
+
+/* torch.optim.RMSprop (momentum 0, not centered) / SGD steps over a flat buffer
+ * (utils.py:2121-2162, core.py:640-642); gscale multiplies the gradient (1/world_size). */
+int pk_rmsprop_step(float* p, const float* g, float* v, int64_t n, float lr, float alpha,
+                    float eps, float gscale, void* stream);
+int pk_sgd_step(float* p, const float* g, int64_t n, float lr, float gscale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PK_B200_H_ */

@@ -1,0 +1,157 @@
+// pk_api.cu — extern "C" shim: validates arguments, forwards to the kernels, never throws.
+#include "../../include/pk_b200.h"
+
+#include "pk_common.cuh"
+#include "pk_kernels.h"
+
+#include <cstdarg>
+#include <cstdio>
+
+namespace pk {
+namespace {
+thread_local char g_err[1024] = "";
+}
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace pk
+
+using namespace pk;
+
+extern "C" {
+
+const char* pk_last_error(void) { return pk::g_err; }
+int pk_version(void) { return PK_ABI_VERSION; }
+
+int pk_gemm_tn(int dtype, int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb,
+               float* C, int64_t ldc, const float* bias, int bias_mode, double* rowstats, float alpha,
+               const float* alpha_dev, int accumulate, int split_k, void* stream) {
+  PK_REQUIRE(A && B && C, "pk_gemm_tn: null operand");
+  GemmArgs a;
+  a.dtype = dtype; a.M = M; a.N = N; a.K = K;
+  a.A = A; a.lda = lda; a.B = B; a.ldb = ldb; a.C = C; a.ldc = ldc;
+  a.bias = bias; a.bias_mode = bias_mode; a.rowstats = rowstats;
+  a.alpha = alpha; a.alpha_dev = alpha_dev; a.accumulate = accumulate; a.split_k = split_k;
+  return gemm_tn(a, static_cast<cudaStream_t>(stream));
+}
+
+int pk_transpose_f32(const float* in, int64_t ldi, int R, int C, float* outT, int64_t ldo, void* outT16,
+                     int64_t ldo16, void* in16, int64_t ldi16, const float* scale_dev, void* stream) {
+  PK_REQUIRE(in != nullptr, "pk_transpose_f32: null input");
+  return transpose_f32(in, ldi, R, C, outT, ldo, static_cast<__half*>(outT16), ldo16,
+                       static_cast<__half*>(in16), ldi16, scale_dev, static_cast<cudaStream_t>(stream));
+}
+
+int pk_convert_f16(const float* in, int64_t ldi, int R, int C, void* out, int64_t ldo, const float* scale_dev,
+                   void* stream) {
+  PK_REQUIRE(in && out, "pk_convert_f16: null pointer");
+  return convert_f16(in, ldi, R, C, static_cast<__half*>(out), ldo, scale_dev,
+                     static_cast<cudaStream_t>(stream));
+}
+
+int pk_amax_scale(const float* x, int64_t ld, int R, int C, float target_log2, float* amax_scratch,
+                  float* scale_out, void* stream) {
+  PK_REQUIRE(x && amax_scratch && scale_out, "pk_amax_scale: null pointer");
+  return amax_scale(x, ld, R, C, target_log2, amax_scratch, scale_out, static_cast<cudaStream_t>(stream));
+}
+
+int pk_bn_finalize(const double* stats, int C, int64_t n_unique, int64_t n_ref, const float* gamma,
+                   const float* beta, float eps, float momentum, int training, float* running_mean,
+                   float* running_var, int64_t* num_batches, float* scale, float* shift, float* mean_out,
+                   float* rstd_out, void* stream) {
+  PK_REQUIRE(scale && shift, "pk_bn_finalize: null output");
+  PK_REQUIRE(!training || stats, "pk_bn_finalize: training mode needs stats");
+  return bn_finalize(stats, C, n_unique, n_ref, gamma, beta, eps, momentum, training, running_mean,
+                     running_var, reinterpret_cast<long long*>(num_batches), scale, shift, mean_out, rstd_out,
+                     static_cast<cudaStream_t>(stream));
+}
+
+int pk_fill_scale_shift(const float* bias, int C, float* scale, float* shift, void* stream) {
+  PK_REQUIRE(scale && shift, "pk_fill_scale_shift: null output");
+  return fill_scale_shift(bias, C, scale, shift, static_cast<cudaStream_t>(stream));
+}
+
+int pk_bn_bwd(int C, int ndir, int64_t n, const float* GT, int64_t ldt, const float* PT, int64_t ldp, int use_bn,
+              int training, const float* mean, const float* rstd, const float* gamma, const float* gscale,
+              float* dgamma, float* dbeta, void* dPT16, int64_t ld16t, void* dP16, int64_t ld16r,
+              double* sums_scratch, void* stream) {
+  PK_REQUIRE(GT != nullptr, "pk_bn_bwd: null GT");
+  PK_REQUIRE(!use_bn || (rstd && (!training || (PT && mean))), "pk_bn_bwd: BatchNorm mode needs PT/mean/rstd");
+  BnBwdArgs a;
+  a.C = C; a.ndir = ndir; a.n = n; a.GT = GT; a.ldt = ldt; a.PT = PT; a.ldp = ldp;
+  a.use_bn = use_bn; a.training = training; a.mean = mean; a.rstd = rstd; a.gamma = gamma; a.gscale = gscale;
+  a.dgamma = dgamma; a.dbeta = dbeta;
+  a.dPT16 = static_cast<__half*>(dPT16); a.ld16t = ld16t;
+  a.dP16 = static_cast<__half*>(dP16); a.ld16r = ld16r;
+  a.sums_scratch = sums_scratch;
+  return bn_bwd(a, static_cast<cudaStream_t>(stream));
+}
+
+int pk_rnn_layer_fwd(int cell, int T, int B, int H, int ndir, int act, const float* PT, int64_t ldp,
+                     const float* scale, const float* shift, const float* U, const float* mask,
+                     float mask_scalar, float* Y32, int64_t ldy32, void* Y16, int64_t ldy16, float* HT,
+                     void* HT16, float* ZT, float* HCT, int64_t ldt, void* stream) {
+  const int cluster = (cell & PK_REC_CLUSTER16) ? 16 : (cell & PK_REC_CLUSTER8) ? 8 : 0;
+  cell &= PK_CELL_MASK;
+  PK_REQUIRE(cell == PK_CELL_LIGRU, "pk_rnn_layer_fwd: cell kind %d not implemented", cell);
+  PK_REQUIRE(PT && scale && shift && U, "pk_rnn_layer_fwd: null input");
+  PK_REQUIRE(act >= PK_ACT_RELU && act <= PK_ACT_LINEAR, "pk_rnn_layer_fwd: bad activation %d", act);
+  RecFwdArgs a;
+  a.T = T; a.B = B; a.H = H; a.ndir = ndir; a.act = act;
+  a.PT = PT; a.ldp = ldp; a.scale = scale; a.shift = shift; a.U = U; a.mask = mask; a.mask_scalar = mask_scalar;
+  a.Y32 = Y32; a.ldy32 = ldy32; a.Y16 = static_cast<__half*>(Y16); a.ldy16 = ldy16;
+  a.HT = HT; a.HT16 = static_cast<__half*>(HT16); a.ZT = ZT; a.HCT = HCT; a.ldt = ldt;
+  a.cluster = cluster;
+  return ligru_fwd(a, static_cast<cudaStream_t>(stream));
+}
+
+int pk_rnn_layer_bwd(int cell, int T, int B, int H, int ndir, int act, const float* dYT, const float* HT,
+                     const float* ZT, const float* HCT, int64_t ldt, const float* U, const float* mask,
+                     float mask_scalar, const float* gscale, float* GT, void* GT16, void* stream) {
+  const int cluster = (cell & PK_REC_CLUSTER16) ? 16 : (cell & PK_REC_CLUSTER8) ? 8 : 0;
+  cell &= PK_CELL_MASK;
+  PK_REQUIRE(cell == PK_CELL_LIGRU, "pk_rnn_layer_bwd: cell kind %d not implemented", cell);
+  PK_REQUIRE(dYT && HT && ZT && HCT && U && GT, "pk_rnn_layer_bwd: null input");
+  RecBwdArgs a;
+  a.T = T; a.B = B; a.H = H; a.ndir = ndir; a.act = act;
+  a.dYT = dYT; a.HT = HT; a.ZT = ZT; a.HCT = HCT; a.ldt = ldt; a.U = U; a.mask = mask;
+  a.mask_scalar = mask_scalar; a.gscale = gscale; a.GT = GT; a.GT16 = static_cast<__half*>(GT16);
+  a.cluster = cluster;
+  return ligru_bwd(a, static_cast<cudaStream_t>(stream));
+}
+
+int pk_logsoftmax_nll(int N, int S, float* logits, int64_t ld, const int64_t* labels, double* acc,
+                      void* stream) {
+  PK_REQUIRE(logits != nullptr, "pk_logsoftmax_nll: null logits");
+  HeadFwdArgs a;
+  a.N = N; a.S = S; a.logits = logits; a.ld = ld;
+  a.labels = reinterpret_cast<const long long*>(labels); a.acc = acc;
+  return logsoftmax_nll(a, static_cast<cudaStream_t>(stream));
+}
+
+int pk_logsoftmax_bwd(int N, int S, const float* logp, int64_t ld, const int64_t* labels, const float* dlogp,
+                      int64_t lddl, float gcoef, float out_scale, void* d16, int64_t ld16, void* dT16,
+                      int64_t ld16t, float* dbias, float* rowsum_scratch, void* stream) {
+  PK_REQUIRE(logp != nullptr, "pk_logsoftmax_bwd: null logp");
+  HeadBwdArgs a;
+  a.N = N; a.S = S; a.logp = logp; a.ld = ld; a.labels = reinterpret_cast<const long long*>(labels);
+  a.dlogp = dlogp; a.lddl = lddl; a.gcoef = gcoef; a.out_scale = out_scale;
+  a.d16 = static_cast<__half*>(d16); a.ld16 = ld16; a.dT16 = static_cast<__half*>(dT16); a.ld16t = ld16t;
+  a.dbias = dbias; a.rowsum_scratch = rowsum_scratch;
+  return logsoftmax_bwd(a, static_cast<cudaStream_t>(stream));
+}
+
+int pk_rmsprop_step(float* p, const float* g, float* v, int64_t n, float lr, float alpha, float eps,
+                    float gscale, void* stream) {
+  PK_REQUIRE(n <= 0 || (p && g && v), "pk_rmsprop_step: null pointer");
+  return rmsprop_step(p, g, v, n, lr, alpha, eps, gscale, static_cast<cudaStream_t>(stream));
+}
+int pk_sgd_step(float* p, const float* g, int64_t n, float lr, float gscale, void* stream) {
+  PK_REQUIRE(n <= 0 || (p && g), "pk_sgd_step: null pointer");
+  return sgd_step(p, g, n, lr, gscale, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

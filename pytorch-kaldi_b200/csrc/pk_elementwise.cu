@@ -1,0 +1,483 @@
+// pk_elementwise.cu — HBM-bound companions of the GEMM / recurrent kernels.
+//
+// All of these are streaming kernels (coalesced, vectorised where the layout allows, grids
+// sized in multiples of the SM count); none of them is reshaped into a GEMM.
+//   transpose / convert : fp32 -> fp16 operand staging (row-major and channel-major copies)
+//   amax_scale          : power-of-two loss scale for fp16 gradient operands
+//   bn_finalize         : BatchNorm1d statistics -> folded scale/shift + running stats
+//                         (reference neural_networks.py:1118-1124, nn.BatchNorm1d(momentum=0.05))
+//   bn_bwd              : BatchNorm backward on the de-duplicated projection
+//   logsoftmax_nll      : LogSoftmax(dim=1) + NLLLoss + argmax error in one pass
+//                         (neural_networks.py:53-54, utils.py:2344-2381)
+//   logsoftmax_bwd      : gradient of the above, emitted directly as fp16 GEMM operands
+//   rmsprop / sgd       : fused optimizer steps over a flat parameter buffer (utils.py:2121-2162)
+#include "pk_common.cuh"
+#include "pk_kernels.h"
+
+namespace pk {
+
+namespace {
+
+constexpr int kSMs = 148;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------
+// transpose (+ optional fp16 copies).  32x32 tiles through padded shared memory.
+// ------------------------------------------------------------------------------------
+__global__ void transpose_kernel(const float* __restrict__ in, long long ldi, int R, int C,
+                                 float* __restrict__ outT, long long ldo, __half* __restrict__ outT16,
+                                 long long ldo16, __half* __restrict__ in16, long long ldi16,
+                                 const float* __restrict__ scale_dev) {
+  __shared__ float tile[32][33];
+  const float s = scale_dev ? __ldg(scale_dev) : 1.f;
+  const int tiles_c = (C + 31) / 32;
+  const long long ntiles = static_cast<long long>((R + 31) / 32) * tiles_c;
+  for (long long tidx = blockIdx.x; tidx < ntiles; tidx += gridDim.x) {
+    const int r0 = static_cast<int>(tidx / tiles_c) * 32;
+    const int c0 = static_cast<int>(tidx % tiles_c) * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int r = r0 + i, c = c0 + threadIdx.x;
+      float v = 0.f;
+      if (r < R && c < C) {
+        v = in[static_cast<long long>(r) * ldi + c];
+        if (in16) in16[static_cast<long long>(r) * ldi16 + c] = f16_sat(v * s);
+      }
+      tile[i][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int c = c0 + i, r = r0 + threadIdx.x;
+      if (r < R && c < C) {
+        const float v = tile[threadIdx.x][i];
+        if (outT) outT[static_cast<long long>(c) * ldo + r] = v;
+        if (outT16) outT16[static_cast<long long>(c) * ldo16 + r] = f16_sat(v * s);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void convert_kernel(const float* __restrict__ in, long long ldi, int R, int C,
+                               __half* __restrict__ out, long long ldo, const float* __restrict__ scale_dev) {
+  const float s = scale_dev ? __ldg(scale_dev) : 1.f;
+  const long long total = static_cast<long long>(R) * C;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / C;
+    const int c = static_cast<int>(i - r * C);
+    out[r * ldo + c] = f16_sat(in[r * ldi + c] * s);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// amax -> power-of-two scale
+// ------------------------------------------------------------------------------------
+__global__ void amax_kernel(const float* __restrict__ x, long long ld, int R, int C, unsigned int* amax_bits) {
+  float m = 0.f;
+  const long long total = static_cast<long long>(R) * C;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / C;
+    const int c = static_cast<int>(i - r * C);
+    const float v = fabsf(x[r * ld + c]);
+    if (v == v) m = fmaxf(m, v);  // ignore NaN
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) atomicMax(amax_bits, __float_as_uint(fminf(m, 3.0e38f)));
+}
+__global__ void scale_from_amax_kernel(const unsigned int* amax_bits, float target_log2, float* scale_out) {
+  const float amax = __uint_as_float(*amax_bits);
+  float s = 1.f;
+  if (amax > 0.f) {
+    int e;
+    frexpf(amax, &e);  // amax = f * 2^e, f in [0.5, 1)  => amax < 2^e
+    float ex = target_log2 - static_cast<float>(e);
+    ex = fminf(fmaxf(ex, -100.f), 100.f);
+    s = exp2f(ex);  // amax * s in [2^(target-1), 2^target)
+  }
+  *scale_out = s;
+}
+
+// ------------------------------------------------------------------------------------
+// BatchNorm finalize
+// ------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, int C, long long n_unique,
+                                   long long n_ref, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum, int training,
+                                   float* running_mean, float* running_var, long long* num_batches,
+                                   float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && training && num_batches) *num_batches += 1;
+  if (c >= C) return;
+  float mean, rstd;
+  if (training) {
+    const double m = stats[c] / static_cast<double>(n_unique);
+    double var = stats[C + c] / static_cast<double>(n_unique) - m * m;
+    if (var < 0.0) var = 0.0;
+    mean = static_cast<float>(m);
+    rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    if (running_mean) {
+      // torch updates running_var with the unbiased estimate over the rows the reference
+      // actually normalised (T*2B duplicated rows for a bidirectional layer)
+      const double unbiased = (n_ref > 1) ? var * static_cast<double>(n_ref) / static_cast<double>(n_ref - 1) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+    }
+  } else {
+    mean = running_mean[c];
+    rstd = 1.f / sqrtf(running_var[c] + eps);
+  }
+  const float gmm = gamma ? gamma[c] : 1.f;
+  const float bt = beta ? beta[c] : 0.f;
+  const float sc = gmm * rstd;
+  scale[c] = sc;
+  shift[c] = bt - mean * sc;
+  if (mean_out) mean_out[c] = mean;
+  if (rstd_out) rstd_out[c] = rstd;
+}
+
+__global__ void fill_scale_shift_kernel(const float* __restrict__ bias, int C, float* scale, float* shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    scale[c] = 1.f;
+    shift[c] = bias ? bias[c] : 0.f;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// BatchNorm backward, pass 1: per-channel sums over the T*B unique rows (one CTA per channel)
+// ------------------------------------------------------------------------------------
+__global__ void bn_bwd_sums_kernel(const BnBwdArgs a, double* __restrict__ sums /* [2][C] */) {
+  const int c = blockIdx.x;
+  const float* g0 = a.GT + static_cast<long long>(c) * a.ldt;
+  const float* g1 = (a.ndir == 2) ? g0 + static_cast<long long>(a.C) * a.ldt : nullptr;
+  const float* p = a.PT ? a.PT + static_cast<long long>(c) * a.ldp : nullptr;
+  const float mean = (a.use_bn && a.mean) ? a.mean[c] : 0.f;
+  const float rstd = (a.use_bn && a.rstd) ? a.rstd[c] : 1.f;
+  double s1 = 0.0, s2 = 0.0;
+  for (long long i = threadIdx.x; i < a.n; i += blockDim.x) {
+    float g = g0[i];
+    if (g1) g += g1[i];
+    s1 += g;
+    if (a.use_bn) s2 += static_cast<double>(g) * ((p[i] - mean) * rstd);
+  }
+  __shared__ double red[2][32];
+  s1 = warp_sum_d(s1);
+  s2 = warp_sum_d(s2);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { red[0][w] = s1; red[1][w] = s2; }
+  __syncthreads();
+  if (w == 0) {
+    const int nw = blockDim.x >> 5;
+    s1 = l < nw ? red[0][l] : 0.0;
+    s2 = l < nw ? red[1][l] : 0.0;
+    s1 = warp_sum_d(s1);
+    s2 = warp_sum_d(s2);
+    if (l == 0) {
+      sums[c] = s1;
+      sums[a.C + c] = s2;
+      if (a.dbeta) a.dbeta[c] = static_cast<float>(s1);
+      if (a.dgamma && a.use_bn) a.dgamma[c] = static_cast<float>(s2);
+    }
+  }
+}
+
+// pass 2: dP = gamma*rstd*(g - mean(g) - p_hat*mean(g*p_hat)), written as scaled fp16 in both
+// layouts (channel-major for dW = dP^T X, row-major for dX = dP W) through a 32x32 smem transpose
+__global__ void bn_bwd_apply_kernel(const BnBwdArgs a, const double* __restrict__ sums) {
+  __shared__ float tile[32][33];
+  const float s = a.gscale ? __ldg(a.gscale) : 1.f;
+  const int tiles_i = static_cast<int>((a.n + 31) / 32);
+  const long long ntiles = static_cast<long long>((a.C + 31) / 32) * tiles_i;
+  const double inv_n = 1.0 / static_cast<double>(a.n);
+  for (long long tidx = blockIdx.x; tidx < ntiles; tidx += gridDim.x) {
+    const int c0 = static_cast<int>(tidx / tiles_i) * 32;
+    const long long i0 = static_cast<long long>(tidx % tiles_i) * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+      const int c = c0 + j;
+      const long long i = i0 + threadIdx.x;
+      float v = 0.f;
+      if (c < a.C && i < a.n) {
+        float g = a.GT[static_cast<long long>(c) * a.ldt + i];
+        if (a.ndir == 2) g += a.GT[static_cast<long long>(a.C + c) * a.ldt + i];
+        if (a.use_bn) {
+          const float rstd = a.rstd[c];
+          const float gam = a.gamma ? a.gamma[c] : 1.f;
+          if (a.training) {
+            const float ph = (a.PT[static_cast<long long>(c) * a.ldp + i] - a.mean[c]) * rstd;
+            const float mg = static_cast<float>(sums[c] * inv_n);
+            const float mgp = static_cast<float>(sums[a.C + c] * inv_n);
+            v = gam * rstd * (g - mg - ph * mgp);
+          } else {
+            v = gam * rstd * g;
+          }
+        } else {
+          v = g;
+        }
+        v *= s;
+        if (a.dPT16) a.dPT16[static_cast<long long>(c) * a.ld16t + i] = f16_sat(v);
+      }
+      tile[j][threadIdx.x] = v;
+    }
+    __syncthreads();
+    if (a.dP16) {
+      for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const long long i = i0 + j;
+        const int c = c0 + threadIdx.x;
+        if (c < a.C && i < a.n) a.dP16[i * a.ld16r + c] = f16_sat(tile[threadIdx.x][j]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// LogSoftmax + NLL + argmax error, one warp per row (row stays L1-resident across passes)
+// ------------------------------------------------------------------------------------
+__global__ void logsoftmax_nll_kernel(const HeadFwdArgs a, double* __restrict__ acc /* [2] */) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  double loss_local = 0.0, err_local = 0.0;
+  for (long long row = static_cast<long long>(blockIdx.x) * warps_per_block + w; row < a.N;
+       row += static_cast<long long>(gridDim.x) * warps_per_block) {
+    float* x = a.logits + row * a.ld;
+    float m = -INFINITY;
+    int mi = 0x7fffffff;
+    for (int j = l; j < a.S; j += 32) {
+      const float v = x[j];
+      if (v > m) { m = v; mi = j; }
+    }
+    // warp arg-max with first-index tie break (torch.max(dim=1) on CPU returns the first maximum)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, m, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+      if (om > m || (om == m && oi < mi)) { m = om; mi = oi; }
+    }
+    float ssum = 0.f;
+    for (int j = l; j < a.S; j += 32) ssum += expf(x[j] - m);
+    ssum = warp_sum(ssum);
+    const float lse = m + logf(ssum);
+    float xlab = 0.f;
+    long long lab = -1;
+    if (a.labels) {
+      lab = a.labels[row];
+      if (lab >= 0 && lab < a.S) xlab = x[lab];  // read the raw logit before the in-place update
+    }
+    __syncwarp();
+    for (int j = l; j < a.S; j += 32) x[j] = x[j] - lse;
+    if (a.labels && l == 0) {
+      if (lab >= 0 && lab < a.S) loss_local += static_cast<double>(lse - xlab);
+      err_local += (static_cast<long long>(mi) != lab) ? 1.0 : 0.0;
+    }
+  }
+  if (a.labels) {
+    __shared__ double red[2][32];
+    if (l == 0) { red[0][w] = loss_local; red[1][w] = err_local; }
+    __syncthreads();
+    if (w == 0) {
+      double s1 = l < warps_per_block ? red[0][l] : 0.0;
+      double s2 = l < warps_per_block ? red[1][l] : 0.0;
+      s1 = warp_sum_d(s1);
+      s2 = warp_sum_d(s2);
+      if (l == 0) {
+        atomicAdd(acc, s1);
+        atomicAdd(acc + 1, s2);
+      }
+    }
+  }
+}
+
+// rowsum of dlogp (general log-softmax backward)
+__global__ void rowsum_kernel(const float* __restrict__ d, long long ld, int N, int S, float* __restrict__ out) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  for (long long row = static_cast<long long>(blockIdx.x) * warps_per_block + w; row < N;
+       row += static_cast<long long>(gridDim.x) * warps_per_block) {
+    float s = 0.f;
+    for (int j = l; j < S; j += 32) s += d[row * ld + j];
+    s = warp_sum(s);
+    if (l == 0) out[row] = s;
+  }
+}
+
+__global__ void logsoftmax_bwd_kernel(const HeadBwdArgs a, const float* __restrict__ rowsum) {
+  __shared__ float tile[32][33];
+  __shared__ float colsum[32];
+  const int tiles_c = (a.S + 31) / 32;
+  const long long ntiles = static_cast<long long>((a.N + 31) / 32) * tiles_c;
+  for (long long tidx = blockIdx.x; tidx < ntiles; tidx += gridDim.x) {
+    const long long r0 = (tidx / tiles_c) * 32;
+    const int c0 = static_cast<int>(tidx % tiles_c) * 32;
+    if (threadIdx.y == 0) colsum[threadIdx.x] = 0.f;
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const long long r = r0 + i;
+      const int c = c0 + threadIdx.x;
+      float d = 0.f;
+      if (r < a.N && c < a.S) {
+        const float p = expf(a.logp[r * a.ld + c]);
+        if (a.dlogp) {
+          d = a.dlogp[r * a.lddl + c] - p * rowsum[r];
+        } else {
+          d = (p - ((a.labels[r] == c) ? 1.f : 0.f)) * a.gcoef;
+        }
+        if (a.d16) a.d16[r * a.ld16 + c] = f16_sat(d * a.out_scale);
+      }
+      tile[i][threadIdx.x] = d;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int c = c0 + i;
+      const long long r = r0 + threadIdx.x;
+      const float d = tile[threadIdx.x][i];
+      if (a.dT16 && c < a.S && r < a.N) a.dT16[static_cast<long long>(c) * a.ld16t + r] = f16_sat(d * a.out_scale);
+      if (a.dbias) {
+        const float cs = warp_sum(d);  // threadIdx.x spans the 32 rows of column c (zero padded)
+        if (threadIdx.x == 0 && c < a.S) atomicAdd(a.dbias + c, cs);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void rmsprop_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ v,
+                               long long n, float lr, float alpha, float eps, float gscale) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float gi = g[i] * gscale;
+    const float vi = alpha * v[i] + (1.f - alpha) * gi * gi;
+    v[i] = vi;
+    p[i] -= lr * gi / (sqrtf(vi) + eps);
+  }
+}
+__global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, long long n, float lr, float gscale) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    p[i] -= lr * g[i] * gscale;
+}
+
+inline int grid_for(long long work_items, int per_block) {
+  long long b = (work_items + per_block - 1) / per_block;
+  const long long cap = static_cast<long long>(kSMs) * 8;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+}  // namespace
+
+int transpose_f32(const float* in, long long ldi, int R, int C, float* outT, long long ldo, __half* outT16,
+                  long long ldo16, __half* in16, long long ldi16, const float* scale_dev, cudaStream_t stream) {
+  PK_REQUIRE(R > 0 && C > 0, "transpose: empty");
+  const long long ntiles = static_cast<long long>((R + 31) / 32) * ((C + 31) / 32);
+  transpose_kernel<<<grid_for(ntiles, 1), dim3(32, 8), 0, stream>>>(in, ldi, R, C, outT, ldo, outT16, ldo16,
+                                                                     in16, ldi16, scale_dev);
+  PK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int convert_f16(const float* in, long long ldi, int R, int C, __half* out, long long ldo,
+                const float* scale_dev, cudaStream_t stream) {
+  PK_REQUIRE(R > 0 && C > 0, "convert: empty");
+  convert_kernel<<<grid_for(static_cast<long long>(R) * C, 1024), 256, 0, stream>>>(in, ldi, R, C, out, ldo,
+                                                                                     scale_dev);
+  PK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int amax_scale(const float* x, long long ld, int R, int C, float target_log2, float* amax_scratch,
+               float* scale_out, cudaStream_t stream) {
+  PK_CHECK_CUDA(cudaMemsetAsync(amax_scratch, 0, sizeof(float), stream));
+  amax_kernel<<<grid_for(static_cast<long long>(R) * C, 2048), 256, 0, stream>>>(
+      x, ld, R, C, reinterpret_cast<unsigned int*>(amax_scratch));
+  scale_from_amax_kernel<<<1, 1, 0, stream>>>(reinterpret_cast<unsigned int*>(amax_scratch), target_log2,
+                                              scale_out);
+  PK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int bn_finalize(const double* stats, int C, long long n_unique, long long n_ref, const float* gamma,
+                const float* beta, float eps, float momentum, int training, float* running_mean,
+                float* running_var, long long* num_batches, float* scale, float* shift, float* mean_out,
+                float* rstd_out, cudaStream_t stream) {
+  PK_REQUIRE(training || (running_mean && running_var), "bn_finalize: eval mode needs running stats");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(stats, C, n_unique, n_ref, gamma, beta, eps,
+                                                          momentum, training, running_mean, running_var,
+                                                          num_batches, scale, shift, mean_out, rstd_out);
+  PK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int fill_scale_shift(const float* bias, int C, float* scale, float* shift, cudaStream_t stream) {
+  fill_scale_shift_kernel<<<(C + 127) / 128, 128, 0, stream>>>(bias, C, scale, shift);
+  PK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int bn_bwd(const BnBwdArgs& a, cudaStream_t stream) {
+  PK_REQUIRE(a.C > 0 && a.n > 0, "bn_bwd: empty");
+  PK_REQUIRE(a.sums_scratch != nullptr, "bn_bwd: sums_scratch (2*C doubles) required");
+  double* sums = a.sums_scratch;
+  bn_bwd_sums_kernel<<<a.C, 256, 0, stream>>>(a, sums);
+  const long long ntiles = static_cast<long long>((a.C + 31) / 32) * ((a.n + 31) / 32);
+  bn_bwd_apply_kernel<<<grid_for(ntiles, 1), dim3(32, 8), 0, stream>>>(a, sums);
+  PK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int logsoftmax_nll(const HeadFwdArgs& a, cudaStream_t stream) {
+  PK_REQUIRE(a.N > 0 && a.S > 0, "logsoftmax_nll: empty");
+  PK_REQUIRE(!a.labels || a.acc, "logsoftmax_nll: acc (2 doubles: loss sum, error count) required with labels");
+  if (a.acc) PK_CHECK_CUDA(cudaMemsetAsync(a.acc, 0, 2 * sizeof(double), stream));
+  logsoftmax_nll_kernel<<<grid_for(a.N, 8), 256, 0, stream>>>(a, a.acc);
+  PK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int logsoftmax_bwd(const HeadBwdArgs& a, cudaStream_t stream) {
+  PK_REQUIRE(a.N > 0 && a.S > 0, "logsoftmax_bwd: empty");
+  PK_REQUIRE(a.dlogp || a.labels, "logsoftmax_bwd: need labels (fused NLL) or dlogp (general)");
+  float* rowsum = a.rowsum_scratch;
+  if (a.dlogp) {
+    PK_REQUIRE(rowsum != nullptr, "logsoftmax_bwd: rowsum_scratch (N floats) required in general mode");
+    rowsum_kernel<<<grid_for(a.N, 8), 256, 0, stream>>>(a.dlogp, a.lddl, a.N, a.S, rowsum);
+  }
+  if (a.dbias) PK_CHECK_CUDA(cudaMemsetAsync(a.dbias, 0, sizeof(float) * a.S, stream));
+  const long long ntiles = static_cast<long long>((a.N + 31) / 32) * ((a.S + 31) / 32);
+  logsoftmax_bwd_kernel<<<grid_for(ntiles, 1), dim3(32, 8), 0, stream>>>(a, rowsum);
+  PK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int rmsprop_step(float* p, const float* g, float* v, long long n, float lr, float alpha, float eps,
+                 float gscale, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  rmsprop_kernel<<<grid_for(n, 1024), 256, 0, stream>>>(p, g, v, n, lr, alpha, eps, gscale);
+  PK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int sgd_step(float* p, const float* g, long long n, float lr, float gscale, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  sgd_kernel<<<grid_for(n, 1024), 256, 0, stream>>>(p, g, n, lr, gscale);
+  PK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace pk

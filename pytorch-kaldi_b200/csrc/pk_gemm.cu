@@ -1,0 +1,280 @@
+// pk_gemm.cu — C[M,N] = alpha * A[M,K] * B[N,K]^T (+bias) on tcgen05 tensor cores.
+//
+// Both operands are K-major ("TN"): every projection of the acoustic-model path is laid out
+// so that the contraction index is contiguous ("Data layout in HBM").
+//   * TMA (cp.async.bulk.tensor.2d, 128-byte swizzle) stages 128x{64 f16 | 32 tf32} operand
+//     tiles through a 6-deep shared-memory ring guarded by full/empty mbarriers;
+//   * one elected thread issues tcgen05.mma.cta_group::1 (128x128xK16/K8) with the fp32
+//     accumulator tile living in tensor memory (128 lanes x 128 columns);
+//   * four epilogue warps pull the accumulator back with tcgen05.ld (32 lanes x 32 columns per
+//     instruction) and fuse: alpha / device-side scale, bias along N or along M, per-row
+//     sum / sum-of-squares (BatchNorm batch statistics of a channel-major projection), plain
+//     or atomic (split-K / accumulate) stores.
+//
+// Replaces: every `nn.Linear` call of the reference module zoo (neural_networks.py:1114-1115
+// liGRU input projections, :432-435 LSTM, :609-611 GRU, MLP :138-148) and the autograd GEMMs
+// behind them.
+#include "pk_common.cuh"
+#include "pk_kernels.h"
+
+#include <mutex>
+
+namespace pk {
+
+namespace {
+
+constexpr int kBM = 128;
+constexpr int kBN = 128;
+constexpr int kStages = 6;
+constexpr int kTileBytes = kBM * 128;  // 128 rows x 128 bytes
+constexpr int kGemmThreads = 192;
+constexpr int kSmemBytes = 2 * kStages * kTileBytes + 256 + 1024;  // + barriers + align slack
+
+struct GemmDev {
+  int M, N, K;
+  float* C;
+  long long ldc;
+  const float* bias;
+  int bias_mode;  // 0 none, 1 along N (C[m][n] += bias[n]), 2 along M (C[m][n] += bias[m])
+  double* rowstats;  // [2][M] or null
+  float alpha;
+  const float* alpha_dev;  // optional device multiplier (e.g. 1/loss_scale)
+  int atomic;              // 1: atomicAdd into C
+  int kb_per_split;
+  int bk_elems;
+};
+
+template <int DT>  // 0 = f16 operands, 2 = tf32 (fp32 operands)
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const GemmDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kStages * kTileBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + 2 * kStages * kTileBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* acc_bar = empty_bar + kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_blk = blockIdx.x;
+  const int n_blk = blockIdx.y;
+  const int kb_total = (p.K + p.bk_elems - 1) / p.bk_elems;
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int kb_end = min(kb_total, kb_begin + p.kb_per_split);
+  const int nkb = kb_end - kb_begin;
+  if (nkb <= 0) return;  // uniform across the CTA (only possible for trailing splits)
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(acc_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<128>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % kStages;
+        const uint32_t ph = (i / kStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full_bar[s], 2 * kTileBytes);
+        const int kc = (kb_begin + i) * p.bk_elems;
+        tma_load_2d(sA + s * kTileBytes, &tmA, &full_bar[s], kc, m_blk * kBM);
+        tma_load_2d(sB + s * kTileBytes, &tmB, &full_bar[s], kc, n_blk * kBN);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc(DT, kBM, kBN);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % kStages;
+        const uint32_t ph = (i / kStages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(sA + s * kTileBytes);
+        const uint32_t b_base = smem_u32(sB + s * kTileBytes);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // 4 x 32 bytes = one 128-byte swizzle row
+          const uint64_t ad = umma_desc_k_sw128(a_base + k * 32);
+          const uint64_t bd = umma_desc_k_sw128(b_base + k * 32);
+          if (DT == 0)
+            umma_f16(tmem_base, ad, bd, idesc, (i | k) != 0);
+          else
+            umma_tf32(tmem_base, ad, bd, idesc, (i | k) != 0);
+        }
+        umma_commit(&empty_bar[s]);  // frees the stage once these MMAs retire
+      }
+      umma_commit(acc_bar);
+    }
+    __syncwarp();
+  } else {
+    // ---- epilogue: warps 2..5 own TMEM lane groups (warp % 4) ----
+    const int lg = warp & 3;
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    const int row = lg * 32 + lane;
+    const long long gm = static_cast<long long>(m_blk) * kBM + row;
+    float alpha = p.alpha;
+    if (p.alpha_dev) alpha *= __ldg(p.alpha_dev);
+    const bool add_bias = (p.bias != nullptr) && (blockIdx.z == 0);
+    float bias_m = 0.f;
+    if (add_bias && p.bias_mode == 2 && gm < p.M) bias_m = __ldg(p.bias + gm);
+    double s1 = 0.0, s2 = 0.0;
+    float* crow = p.C + gm * p.ldc;
+    const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+#pragma unroll 1
+    for (int c0 = 0; c0 < kBN; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + c0, v);
+      tmem_ld_wait();
+      const int gn0 = n_blk * kBN + c0;
+      if (gm < p.M && gn0 < p.N) {
+        float o[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = alpha * __uint_as_float(v[j]);
+          if (add_bias) x += (p.bias_mode == 1) ? ((gn0 + j < p.N) ? __ldg(p.bias + gn0 + j) : 0.f)
+                                                : bias_m;
+          o[j] = x;
+        }
+        if (p.rowstats) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (gn0 + j < p.N) {
+              s1 += o[j];
+              s2 += static_cast<double>(o[j]) * o[j];
+            }
+        }
+        if (p.atomic) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (gn0 + j < p.N) atomicAdd(crow + gn0 + j, o[j]);
+        } else if (vec_ok && gn0 + 32 <= p.N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(crow + gn0 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (gn0 + j < p.N) crow[gn0 + j] = o[j];
+        }
+      }
+    }
+    if (p.rowstats && gm < p.M) {
+      atomicAdd(p.rowstats + gm, s1);
+      atomicAdd(p.rowstats + p.M + gm, s2);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<128>(tmem_base);
+}
+
+// ---- host side: tensor-map encoding through the driver entry point (no -lcuda needed) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+int make_operand_map(CUtensorMap* map, const void* base, int dtype, long long rows, long long k,
+                     long long ld_elems) {
+  EncodeTiledFn enc = get_encode_fn();
+  PK_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  const int esz = (dtype == PK_DT_F16) ? 2 : 4;
+  PK_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "GEMM operand base not 16-byte aligned");
+  PK_REQUIRE((ld_elems * esz) % 16 == 0, "GEMM operand row pitch (%lld elems) not 16-byte multiple",
+             ld_elems);
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld_elems) * esz};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / esz), static_cast<cuuint32_t>(kBM)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, dtype == PK_DT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                   2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PK_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%lld k=%lld ld=%lld", (int)r,
+             rows, k, ld_elems);
+  return 0;
+}
+
+}  // namespace
+
+int gemm_tn(const GemmArgs& a, cudaStream_t stream) {
+  PK_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "gemm_tn: empty problem M=%d N=%d K=%d", a.M, a.N, a.K);
+  PK_REQUIRE(a.dtype == PK_DT_F16 || a.dtype == PK_DT_TF32, "gemm_tn: bad dtype %d", a.dtype);
+  PK_REQUIRE(a.bias_mode >= 0 && a.bias_mode <= 2, "gemm_tn: bad bias mode");
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(gemm_tn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kSmemBytes);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(gemm_tn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      kSmemBytes);
+  });
+  PK_CHECK_CUDA(attr_err);
+
+  CUtensorMap tmA, tmB;
+  if (int rc = make_operand_map(&tmA, a.A, a.dtype, a.M, a.K, a.lda)) return rc;
+  if (int rc = make_operand_map(&tmB, a.B, a.dtype, a.N, a.K, a.ldb)) return rc;
+
+  GemmDev p;
+  p.M = a.M; p.N = a.N; p.K = a.K;
+  p.C = a.C; p.ldc = a.ldc;
+  p.bias = a.bias; p.bias_mode = a.bias ? a.bias_mode : 0;
+  p.rowstats = a.rowstats;
+  p.alpha = a.alpha;
+  p.alpha_dev = a.alpha_dev;
+  p.bk_elems = (a.dtype == PK_DT_F16) ? 64 : 32;
+  const int kb_total = (a.K + p.bk_elems - 1) / p.bk_elems;
+  int splits = a.split_k > 0 ? a.split_k : 1;
+  if (splits > kb_total) splits = kb_total;
+  p.kb_per_split = (kb_total + splits - 1) / splits;
+  splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  PK_REQUIRE(!(a.rowstats && splits > 1), "gemm_tn: rowstats with split-K unsupported");
+  p.atomic = (splits > 1 || a.accumulate) ? 1 : 0;
+  if (splits > 1 && !a.accumulate) {
+    if (a.ldc == a.N) {
+      PK_CHECK_CUDA(cudaMemsetAsync(a.C, 0, sizeof(float) * (size_t)a.M * a.N, stream));
+    } else {
+      PK_CHECK_CUDA(cudaMemset2DAsync(a.C, sizeof(float) * a.ldc, 0, sizeof(float) * a.N, a.M, stream));
+    }
+  }
+  dim3 grid((a.M + kBM - 1) / kBM, (a.N + kBN - 1) / kBN, splits);
+  if (a.dtype == PK_DT_F16)
+    gemm_tn_kernel<0><<<grid, kGemmThreads, kSmemBytes, stream>>>(tmA, tmB, p);
+  else
+    gemm_tn_kernel<2><<<grid, kGemmThreads, kSmemBytes, stream>>>(tmA, tmB, p);
+  PK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace pk

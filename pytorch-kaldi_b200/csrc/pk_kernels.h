@@ -1,0 +1,140 @@
+// pk_kernels.h — internal (C++) launch interfaces shared by the .cu files and the C-ABI shim.
+#pragma once
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define PK_DT_F16 0
+#define PK_DT_TF32 2
+
+namespace pk {
+
+struct GemmArgs {
+  int dtype = PK_DT_F16;  // operand type of A and B
+  int M = 0, N = 0, K = 0;
+  const void* A = nullptr;  // [M][lda] K-major
+  long long lda = 0;
+  const void* B = nullptr;  // [N][ldb] K-major
+  long long ldb = 0;
+  float* C = nullptr;  // [M][ldc] fp32
+  long long ldc = 0;
+  const float* bias = nullptr;
+  int bias_mode = 0;  // 1: along N, 2: along M
+  double* rowstats = nullptr;  // [2][M] (sum, sumsq) accumulated with atomics, or null
+  float alpha = 1.f;
+  const float* alpha_dev = nullptr;
+  int accumulate = 0;  // C += result
+  int split_k = 1;
+};
+int gemm_tn(const GemmArgs& a, cudaStream_t stream);
+
+// gate families of the recurrent kernels (reference neural_networks.py classes)
+enum Cell : int { CELL_LIGRU = 0, CELL_RNN = 1, CELL_GRU = 2, CELL_MGRU = 3, CELL_LSTM = 4 };
+
+struct RecFwdArgs {
+  int T = 0, B = 0, H = 0, ndir = 1, act = 0;
+  const float* PT = nullptr;  // [G*H][ldp] channel-major pre-activations, col = t*B + b
+  long long ldp = 0;
+  const float* scale = nullptr;  // [G*H]
+  const float* shift = nullptr;  // [G*H]
+  const float* U = nullptr;      // [G*H][H] fp32
+  const float* mask = nullptr;   // [ndir*B][H] or null
+  float mask_scalar = 1.f;
+  float* Y32 = nullptr;  // [T*B][ldy32] row-major, col = d*H + u
+  long long ldy32 = 0;
+  __half* Y16 = nullptr;  // [T*B][ldy16]
+  long long ldy16 = 0;
+  float* HT = nullptr;     // [ndir*H][ldt] channel-major, natural time
+  __half* HT16 = nullptr;  // same, fp16
+  float* ZT = nullptr;
+  float* HCT = nullptr;
+  long long ldt = 0;
+  int cluster = 0;  // 0 = auto, 8 or 16 CTAs per cluster
+};
+int ligru_fwd(const RecFwdArgs& a, cudaStream_t stream);
+
+struct RecBwdArgs {
+  int T = 0, B = 0, H = 0, ndir = 1, act = 0;
+  const float* dYT = nullptr;  // [ndir*H][ldt]
+  const float* HT = nullptr;
+  const float* ZT = nullptr;
+  const float* HCT = nullptr;
+  long long ldt = 0;
+  const float* U = nullptr;
+  const float* mask = nullptr;
+  float mask_scalar = 1.f;
+  const float* gscale = nullptr;  // device scalar: power-of-two loss scale for fp16 operands
+  float* GT = nullptr;            // [ndir][2H][ldt] fp32
+  __half* GT16 = nullptr;         // [ndir][2H][ldt] fp16, scaled by *gscale
+  int cluster = 0;
+};
+int ligru_bwd(const RecBwdArgs& a, cudaStream_t stream);
+
+// ---- memory-bound helpers (pk_elementwise.cu) ----
+// out[c][r] = in[r][c]; optional fp16 copies. in is [R][ldi] fp32.
+int transpose_f32(const float* in, long long ldi, int R, int C, float* outT, long long ldo,
+                  __half* outT16, long long ldo16, __half* in16, long long ldi16, const float* scale_dev,
+                  cudaStream_t stream);
+int convert_f16(const float* in, long long ldi, int R, int C, __half* out, long long ldo,
+                const float* scale_dev, cudaStream_t stream);
+int amax_scale(const float* x, long long ld, int R, int C, float target_log2, float* amax_scratch,
+               float* scale_out, cudaStream_t stream);
+int bn_finalize(const double* stats, int C, long long n_unique, long long n_ref, const float* gamma,
+                const float* beta, float eps, float momentum, int training, float* running_mean,
+                float* running_var, long long* num_batches, float* scale, float* shift, float* mean_out,
+                float* rstd_out, cudaStream_t stream);
+int fill_scale_shift(const float* bias, int C, float* scale, float* shift, cudaStream_t stream);
+struct BnBwdArgs {
+  int C = 0;          // channels (G*H)
+  int ndir = 1;
+  long long n = 0;    // unique rows T*B
+  const float* GT = nullptr;   // [ndir][C][ldt] fp32 (unscaled)
+  const float* PT = nullptr;   // [C][ldp] pre-BN projections
+  long long ldt = 0, ldp = 0;
+  int use_bn = 1;
+  int training = 1;
+  const float* mean = nullptr;   // [C] batch (training) or running (eval)
+  const float* rstd = nullptr;   // [C]
+  const float* gamma = nullptr;  // [C]
+  const float* gscale = nullptr; // device loss scale applied to the fp16 outputs
+  float* dgamma = nullptr;       // [C]  (or dbias when !use_bn, written to dbeta)
+  float* dbeta = nullptr;        // [C]
+  __half* dPT16 = nullptr;       // [C][ld16t]    channel-major, scaled
+  long long ld16t = 0;
+  __half* dP16 = nullptr;        // [n][ld16r]    row-major, scaled
+  long long ld16r = 0;
+  double* sums_scratch = nullptr; // [2][C]
+};
+int bn_bwd(const BnBwdArgs& a, cudaStream_t stream);
+
+struct HeadFwdArgs {
+  int N = 0, S = 0;
+  float* logits = nullptr;  // [N][ld] in: logits, out: log-posteriors (in place)
+  long long ld = 0;
+  const long long* labels = nullptr;  // [N] or null
+  double* acc = nullptr;              // [2] device accumulators: NLL sum, error count (zeroed by callee)
+};
+int logsoftmax_nll(const HeadFwdArgs& a, cudaStream_t stream);
+struct HeadBwdArgs {
+  int N = 0, S = 0;
+  const float* logp = nullptr;  // [N][ld]
+  long long ld = 0;
+  const long long* labels = nullptr;  // fused-NLL mode (dlogp == null): d = (exp(logp) - onehot) * gcoef
+  const float* dlogp = nullptr;       // general mode: d = dlogp - exp(logp) * rowsum(dlogp)
+  long long lddl = 0;
+  float gcoef = 1.f;                  // upstream grad / N for fused mode
+  float out_scale = 1.f;              // fp16 loss scale (host value, power of two)
+  __half* d16 = nullptr;              // [N][ld16] row-major scaled
+  long long ld16 = 0;
+  __half* dT16 = nullptr;             // [S][ld16t] channel-major scaled
+  long long ld16t = 0;
+  float* dbias = nullptr;             // [S] column sums (unscaled)
+  float* rowsum_scratch = nullptr;    // [N] (general mode only)
+};
+int logsoftmax_bwd(const HeadBwdArgs& a, cudaStream_t stream);
+int rmsprop_step(float* p, const float* g, float* v, long long n, float lr, float alpha, float eps,
+                 float gscale, cudaStream_t stream);
+int sgd_step(float* p, const float* g, long long n, float lr, float gscale, cudaStream_t stream);
+
+}  // namespace pk

@@ -1,0 +1,487 @@
+// pk_rnn.cu — persistent, weight-stationary recurrent kernels (liGRU) for sm_100a.
+//
+// The reference runs `for k in range(T)` in Python with ~11 launches per step
+// (neural_networks.py:1130-1141).  Here one launch covers the whole sequence:
+//
+//   * a thread-block CLUSTER of 8 CTAs owns 8 rows of the (direction-stacked) batch; the
+//     bidirectional layer is just 2B independent rows (reference :1095-1097 stacks x and
+//     flip(x) on the batch axis and shares the weights), so 2B/8 clusters run concurrently;
+//   * inside a cluster the hidden units are sliced across the 8 CTAs; every warp keeps its
+//     [16 x H] slice of the recurrent matrix U in REGISTERS as mma.sync A-fragments (fp16,
+//     loaded once), so the only per-step operand traffic is the hidden state itself;
+//   * each step: h_{t-1} (fp16 copy, 8 rows x H) is read from shared memory with ldmatrix,
+//     the [gates x 8 rows] products run on the tensor cores with fp32 accumulation, the gate
+//     non-linearities / dropout mask / BatchNorm affine are applied in registers on the fp32
+//     state, and the new fp16 slice is pushed to the other 7 CTAs through distributed shared
+//     memory (st.shared::cluster, 16-byte vectors) followed by ONE cluster barrier per step;
+//   * flip / stack / cat of the reference (:1144-1150, :1962-1970) disappear into indexing:
+//     direction-1 rows read time T-1-k and write their outputs at natural time.
+//
+// The backward kernel walks the same recurrence in reverse with U^T stationary in registers.
+#include "pk_common.cuh"
+#include "pk_kernels.h"
+
+#include <cstdlib>
+#include <mutex>
+
+namespace pk {
+
+namespace {
+
+constexpr int kRows = 8;  // batch rows per cluster (the n8 of m16n8k16)
+
+// =====================================================================================
+// forward
+// =====================================================================================
+template <int KT, int MT, int CL>
+__global__ void __launch_bounds__(MT * 32, 1) ligru_fwd_kernel(const RecFwdArgs a) {
+  constexpr int kCluster = CL;
+  constexpr int HS = CL * 8 * MT + 8;  // halves per row of the staged state (pad keeps ldmatrix conflict-free)
+  static_assert((CL * MT) % 8 == 0, "row pitch must be 16 (mod 128) bytes");
+  static_assert(CL * 8 * MT >= 16 * KT, "unit slots must cover the K range");
+  __shared__ __align__(16) __half h16[2][kRows][HS];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2;
+  const int q = lane & 3;
+  const uint32_t crank = cluster_ctarank();
+  const int cl = blockIdx.x / kCluster;
+  const int H = a.H, B = a.B, T = a.T;
+  const int nrows = a.ndir * B;
+  const int ubase = crank * (8 * MT) + warp * 8;  // first unit of this warp's 8-unit tile
+  const int u = ubase + g;
+  const bool u_ok = u < H;
+
+  // ---- recurrent weights -> A fragments (row g = candidate gate "h", row g+8 = update gate "z")
+  uint32_t A[KT][4];
+  {
+    const float* Uh = a.U + static_cast<long long>(u) * H;
+    const float* Uz = a.U + static_cast<long long>(H + u) * H;
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt) {
+      const int k0 = kt * 16 + 2 * q;
+      float h00 = 0.f, h01 = 0.f, h10 = 0.f, h11 = 0.f, z00 = 0.f, z01 = 0.f, z10 = 0.f, z11 = 0.f;
+      if (u_ok) {
+        if (k0 < H) { h00 = __ldg(Uh + k0); z00 = __ldg(Uz + k0); }
+        if (k0 + 1 < H) { h01 = __ldg(Uh + k0 + 1); z01 = __ldg(Uz + k0 + 1); }
+        if (k0 + 8 < H) { h10 = __ldg(Uh + k0 + 8); z10 = __ldg(Uz + k0 + 8); }
+        if (k0 + 9 < H) { h11 = __ldg(Uh + k0 + 9); z11 = __ldg(Uz + k0 + 9); }
+      }
+      A[kt][0] = pack_f16x2_sat(h00, h01);
+      A[kt][1] = pack_f16x2_sat(z00, z01);
+      A[kt][2] = pack_f16x2_sat(h10, h11);
+      A[kt][3] = pack_f16x2_sat(z10, z11);
+    }
+  }
+
+  // ---- zero both state buffers (h_0 = 0, reference :1096), then make sure every CTA did
+  for (int i = threadIdx.x; i < 2 * kRows * HS / 2; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(&h16[0][0][0])[i] = 0u;
+  cluster_sync_all();
+
+  // ---- per-thread row bookkeeping: this thread owns (unit u, rows 2q and 2q+1)
+  int rb[2], rd[2];
+  bool rok[2];
+  float msk[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int r = cl * kRows + 2 * q + i;
+    rok[i] = (r < nrows) && u_ok;
+    const int rr = r < nrows ? r : 0;
+    rd[i] = (rr >= B) ? 1 : 0;
+    rb[i] = rr - rd[i] * B;
+    msk[i] = a.mask ? ((rok[i]) ? __ldg(a.mask + static_cast<long long>(rr) * H + u) : 0.f)
+                    : a.mask_scalar;
+  }
+  float sc_h = 0.f, sh_h = 0.f, sc_z = 0.f, sh_z = 0.f;
+  if (u_ok) {
+    sc_h = __ldg(a.scale + u);
+    sh_h = __ldg(a.shift + u);
+    sc_z = __ldg(a.scale + H + u);
+    sh_z = __ldg(a.shift + H + u);
+  }
+  const float* Ph = a.PT + static_cast<long long>(u_ok ? u : 0) * a.ldp;
+  const float* Pz = a.PT + static_cast<long long>(u_ok ? H + u : 0) * a.ldp;
+
+  float hprev[2] = {0.f, 0.f};
+  float ph[2] = {0.f, 0.f}, pz[2] = {0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+    if (rok[i]) {
+      const long long col = static_cast<long long>(rd[i] ? T - 1 : 0) * B + rb[i];
+      ph[i] = __ldg(Ph + col);
+      pz[i] = __ldg(Pz + col);
+    }
+
+  // ldmatrix lane addressing: matrix (lane>>3) row (lane&7): &h16[buf][lane&7][k0 + 8*(lane>>3)]
+  const uint32_t ldm_off = static_cast<uint32_t>(((lane & 7) * HS + 8 * (lane >> 3)) * 2);
+  const uint32_t ldm_off2 = static_cast<uint32_t>(((lane & 7) * HS + 8 * ((lane >> 3) & 1)) * 2);
+  const uint32_t h16_base = smem_u32(&h16[0][0][0]);
+  constexpr uint32_t kBufBytes = kRows * HS * 2;
+
+  for (int k = 0; k < T; ++k) {
+    const int cur = k & 1, nxt = cur ^ 1;
+    // ---------------- U * h_{k-1} on the tensor cores ----------------
+    float acc[4][4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f; }
+    const uint32_t bufa = h16_base + cur * kBufBytes;
+#pragma unroll
+    for (int kt = 0; kt + 1 < KT; kt += 2) {
+      uint32_t b0, b1, b2, b3;
+      ldmatrix_x4(bufa + ldm_off + kt * 32, b0, b1, b2, b3);
+      mma_m16n8k16_f16(acc[kt & 3], A[kt], b0, b1);
+      mma_m16n8k16_f16(acc[(kt + 1) & 3], A[kt + 1], b2, b3);
+    }
+    if (KT & 1) {
+      uint32_t b0, b1;
+      ldmatrix_x2(bufa + ldm_off2 + (KT - 1) * 32, b0, b1);
+      mma_m16n8k16_f16(acc[(KT - 1) & 3], A[KT - 1], b0, b1);
+    }
+    float ch[2], cz[2];
+    ch[0] = (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]);
+    ch[1] = (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]);
+    cz[0] = (acc[0][2] + acc[1][2]) + (acc[2][2] + acc[3][2]);
+    cz[1] = (acc[0][3] + acc[1][3]) + (acc[2][3] + acc[3][3]);
+
+    // ---------------- gates (reference :1133-1136) ----------------
+    float hn[2], zz[2], hcv[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float zt = sigmoidf_(fmaf(sc_z, pz[i], sh_z) + cz[i]);
+      const float at = fmaf(sc_h, ph[i], sh_h) + ch[i];
+      const float hc = act_fwd(a.act, at) * msk[i];
+      float h = zt * hprev[i] + (1.f - zt) * hc;
+      if (!rok[i]) h = 0.f;
+      hn[i] = h; zz[i] = zt; hcv[i] = hc;
+      hprev[i] = h;
+      h16[nxt][2 * q + i][u] = f16_sat(h);
+    }
+    __syncwarp();
+    // ---------------- broadcast the warp's 8x8 fp16 tile to the 7 peer CTAs ----------------
+    {
+      const int n = lane & 7;
+      const __half* src = &h16[nxt][n][ubase];
+      const uint4 val = *reinterpret_cast<const uint4*>(src);
+      const uint32_t laddr = smem_u32(src);
+#pragma unroll
+      for (int j = 0; j < kCluster / 4; ++j) {
+        const uint32_t dst = (lane >> 3) + 4 * j;
+        if (dst != crank) st_cluster_v4(mapa_shared(laddr, dst), val);
+      }
+    }
+    cluster_arrive_release();
+
+    // ---------------- off the critical path: global stores + next step's projections ----------
+    float nph[2] = {0.f, 0.f}, npz[2] = {0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      if (rok[i]) {
+        const int t = rd[i] ? (T - 1 - k) : k;
+        const long long col = static_cast<long long>(t) * B + rb[i];
+        if (k + 1 < T) {
+          const long long ncol = col + (rd[i] ? -B : B);
+          nph[i] = __ldg(Ph + ncol);
+          npz[i] = __ldg(Pz + ncol);
+        }
+        const long long ch_idx = static_cast<long long>(rd[i] * H + u) * a.ldt + col;
+        if (a.HT) a.HT[ch_idx] = hn[i];
+        if (a.HT16) a.HT16[ch_idx] = f16_sat(hn[i]);
+        if (a.ZT) a.ZT[ch_idx] = zz[i];
+        if (a.HCT) a.HCT[ch_idx] = hcv[i];
+        if (a.Y32) a.Y32[col * a.ldy32 + rd[i] * H + u] = hn[i];
+        if (a.Y16) a.Y16[col * a.ldy16 + rd[i] * H + u] = f16_sat(hn[i]);
+      }
+    }
+    ph[0] = nph[0]; ph[1] = nph[1]; pz[0] = npz[0]; pz[1] = npz[1];
+    cluster_wait_acquire();
+  }
+  // no CTA may exit while peers can still write into its shared memory
+  cluster_sync_all();
+}
+
+// =====================================================================================
+// backward
+// =====================================================================================
+// One step k (time running backwards):
+//   dh   = dY_k + z_{k+1} . dh_{k+1} + U^T [da_{k+1}; dpz_{k+1}]            (carry)
+//   dz   = dh . (h_{k-1} - hc_k);   dhc = dh . (1 - z_k)
+//   da   = dhc . mask . act'(.)      dpz = dz . z_k (1 - z_k)
+// Thread ownership: warp (mt, half) keeps the 16-unit x (half-gate K range) slice of U^T in
+// registers; after the MMA the two warps of a pair exchange partial sums through smem so that
+// warp (mt,0) finishes units g and warp (mt,1) units g+8 of the tile.
+template <int KT, int MT, int CL>
+__global__ void __launch_bounds__(((MT + 1) / 2) * 64, 1) ligru_bwd_kernel(const RecBwdArgs a) {
+  constexpr int kCluster = CL;
+  constexpr int MT16 = (MT + 1) / 2;     // 16-unit tiles per CTA
+  constexpr int KP = CL * 8 * MT;        // unit-slot stride between the two gates in the staged vector
+  static_assert((CL * MT) % 8 == 0, "row pitch must be 16 (mod 128) bytes");
+  static_assert(KP >= 16 * KT, "unit slots must cover the K range");
+  constexpr int GS = 2 * KP + 8;         // halves per staged row
+  constexpr int UPC = 8 * MT;            // units owned per CTA
+  __shared__ __align__(16) __half g16[2][kRows][GS];
+  __shared__ float xbuf[MT16][2][32][2];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2;
+  const int q = lane & 3;
+  const int mt = warp >> 1;
+  const int half = warp & 1;
+  const uint32_t crank = cluster_ctarank();
+  const int cl = blockIdx.x / kCluster;
+  const int H = a.H, B = a.B, T = a.T;
+  const int nrows = a.ndir * B;
+  const int cta_ubase = crank * UPC;
+
+  // ---- U^T slice -> A fragments.  A[row = unit][col = j] = Ug[j][unit], Ug = Uh (half 0) / Uz (half 1)
+  uint32_t A[KT][4];
+  {
+    const int slot_lo = mt * 16 + g, slot_hi = slot_lo + 8;
+    const int u_lo = cta_ubase + slot_lo, u_hi = cta_ubase + slot_hi;
+    const bool ok_lo = (slot_lo < UPC) && (u_lo < H);
+    const bool ok_hi = (slot_hi < UPC) && (u_hi < H);
+    const float* Ug = a.U + static_cast<long long>(half) * H * H;
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt) {
+      const int j0 = kt * 16 + 2 * q;
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = 0.f;
+      // v layout: {lo[j0], lo[j0+1], hi[j0], hi[j0+1], lo[j0+8], lo[j0+9], hi[j0+8], hi[j0+9]}
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = j0 + (e & 1) + ((e >> 1) ? 8 : 0);
+        if (j < H) {
+          if (ok_lo) v[(e >> 1) * 4 + (e & 1)] = __ldg(Ug + static_cast<long long>(j) * H + u_lo);
+          if (ok_hi) v[(e >> 1) * 4 + 2 + (e & 1)] = __ldg(Ug + static_cast<long long>(j) * H + u_hi);
+        }
+      }
+      A[kt][0] = pack_f16x2_sat(v[0], v[1]);
+      A[kt][1] = pack_f16x2_sat(v[2], v[3]);
+      A[kt][2] = pack_f16x2_sat(v[4], v[5]);
+      A[kt][3] = pack_f16x2_sat(v[6], v[7]);
+    }
+  }
+
+  for (int i = threadIdx.x; i < 2 * kRows * GS / 2; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(&g16[0][0][0])[i] = 0u;
+  cluster_sync_all();
+
+  // ---- element ownership of this thread: unit = tile unit (8*half + g), rows 2q, 2q+1
+  const int slot = mt * 16 + 8 * half + g;
+  const int u = cta_ubase + slot;
+  const bool u_ok = (slot < UPC) && (u < H);
+  const int wslot0 = mt * 16 + 8 * half;  // first slot of this warp's 8-unit group
+  const bool warp_ok = wslot0 < UPC;      // the last tile may be half empty (MT odd)
+  int rb[2], rd[2];
+  bool rok[2];
+  float msk[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int r = cl * kRows + 2 * q + i;
+    rok[i] = (r < nrows) && u_ok;
+    const int rr = r < nrows ? r : 0;
+    rd[i] = (rr >= B) ? 1 : 0;
+    rb[i] = rr - rd[i] * B;
+    msk[i] = a.mask ? (rok[i] ? __ldg(a.mask + static_cast<long long>(rr) * H + u) : 0.f)
+                    : a.mask_scalar;
+  }
+  const float s = a.gscale ? __ldg(a.gscale) : 1.f;
+  const float inv_s = 1.f / s;
+
+  float carry[2] = {0.f, 0.f};
+  // prefetched operands of the step
+  float dy[2] = {0.f, 0.f}, zz[2] = {0.f, 0.f}, hc[2] = {0.f, 0.f}, hp[2] = {0.f, 0.f};
+  auto load_step = [&](int k, float (&ody)[2], float (&oz)[2], float (&ohc)[2], float (&ohp)[2]) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      ody[i] = oz[i] = ohc[i] = ohp[i] = 0.f;
+      if (rok[i]) {
+        const int t = rd[i] ? (T - 1 - k) : k;
+        const long long col = static_cast<long long>(t) * B + rb[i];
+        const long long idx = static_cast<long long>(rd[i] * H + u) * a.ldt + col;
+        ody[i] = __ldg(a.dYT + idx);
+        oz[i] = __ldg(a.ZT + idx);
+        ohc[i] = __ldg(a.HCT + idx);
+        if (k > 0) ohp[i] = __ldg(a.HT + idx + (rd[i] ? B : -B));
+      }
+    }
+  };
+  load_step(T - 1, dy, zz, hc, hp);
+
+  const uint32_t ldm_off = static_cast<uint32_t>(((lane & 7) * GS + 8 * (lane >> 3)) * 2);
+  const uint32_t ldm_off2 = static_cast<uint32_t>(((lane & 7) * GS + 8 * ((lane >> 3) & 1)) * 2);
+  const uint32_t g16_base = smem_u32(&g16[0][0][0]);
+  constexpr uint32_t kBufBytes = kRows * GS * 2;
+  const long long gate_stride = static_cast<long long>(H) * a.ldt;         // da -> dpz rows
+  const long long dir_stride = 2 * gate_stride;                            // direction blocks of GT
+
+  for (int k = T - 1; k >= 0; --k) {
+    const int buf = k & 1;
+    // ---------------- phase A: pointwise backward of step k ----------------
+    float da[2], dpz[2], keep[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float dh = dy[i] + carry[i];
+      const float dzv = dh * (hp[i] - hc[i]);
+      const float dhc = dh * (1.f - zz[i]);
+      const float m = msk[i];
+      const float y = (m != 0.f) ? hc[i] / m : 0.f;
+      float dav = dhc * m * act_bwd_from_out(a.act, y);
+      float dpzv = dzv * zz[i] * (1.f - zz[i]);
+      if (!rok[i]) { dav = 0.f; dpzv = 0.f; }
+      da[i] = dav; dpz[i] = dpzv;
+      keep[i] = dh * zz[i];
+      if (warp_ok) {
+        g16[buf][2 * q + i][slot + cta_ubase] = f16_sat(dav * s);
+        g16[buf][2 * q + i][KP + slot + cta_ubase] = f16_sat(dpzv * s);
+      }
+    }
+    __syncwarp();
+    if (warp_ok) {
+      // 16 chunks (8 rows x 2 gates) of 16 bytes, each to every peer: lane -> chunk (lane&15), peer half (lane>>4)
+      const int n = lane & 7;
+      const int gate = (lane >> 3) & 1;
+      const __half* src = &g16[buf][n][gate * KP + cta_ubase + wslot0];
+      const uint4 val = *reinterpret_cast<const uint4*>(src);
+      const uint32_t laddr = smem_u32(src);
+#pragma unroll
+      for (int j = 0; j < kCluster / 2; ++j) {
+        const uint32_t dst = (lane >> 4) * (kCluster / 2) + j;
+        if (dst != crank) st_cluster_v4(mapa_shared(laddr, dst), val);
+      }
+    }
+    cluster_arrive_release();
+    // global stores of this step + prefetch of step k-1 while the barrier completes
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      if (rok[i]) {
+        const int t = rd[i] ? (T - 1 - k) : k;
+        const long long col = static_cast<long long>(t) * B + rb[i];
+        const long long idx = rd[i] * dir_stride + static_cast<long long>(u) * a.ldt + col;
+        a.GT[idx] = da[i];
+        a.GT[idx + gate_stride] = dpz[i];
+        if (a.GT16) {
+          a.GT16[idx] = f16_sat(da[i] * s);
+          a.GT16[idx + gate_stride] = f16_sat(dpz[i] * s);
+        }
+      }
+    }
+    float ndy[2], nz[2], nhc[2], nhp[2];
+    if (k > 0) load_step(k - 1, ndy, nz, nhc, nhp);
+    cluster_wait_acquire();
+
+    // ---------------- phase B: U^T [da; dpz] for the carry into step k-1 ----------------
+    if (k > 0) {
+      float acc[4][4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f; }
+      const uint32_t bufa = g16_base + buf * kBufBytes + half * (KP * 2);
+#pragma unroll
+      for (int kt = 0; kt + 1 < KT; kt += 2) {
+        uint32_t b0, b1, b2, b3;
+        ldmatrix_x4(bufa + ldm_off + kt * 32, b0, b1, b2, b3);
+        mma_m16n8k16_f16(acc[kt & 3], A[kt], b0, b1);
+        mma_m16n8k16_f16(acc[(kt + 1) & 3], A[kt + 1], b2, b3);
+      }
+      if (KT & 1) {
+        uint32_t b0, b1;
+        ldmatrix_x2(bufa + ldm_off2 + (KT - 1) * 32, b0, b1);
+        mma_m16n8k16_f16(acc[(KT - 1) & 3], A[KT - 1], b0, b1);
+      }
+      float c4[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) c4[e] = (acc[0][e] + acc[1][e]) + (acc[2][e] + acc[3][e]);
+      // warp half 0 keeps units g (c4[0..1]) and ships c4[2..3]; half 1 keeps g+8 and ships c4[0..1]
+      xbuf[mt][half][lane][0] = half ? c4[0] : c4[2];
+      xbuf[mt][half][lane][1] = half ? c4[1] : c4[3];
+      asm volatile("bar.sync %0, 64;" ::"r"(mt + 1) : "memory");
+      const float o0 = xbuf[mt][half ^ 1][lane][0];
+      const float o1 = xbuf[mt][half ^ 1][lane][1];
+      const float m0 = half ? c4[2] : c4[0];
+      const float m1 = half ? c4[3] : c4[1];
+      carry[0] = keep[0] + (m0 + o0) * inv_s;
+      carry[1] = keep[1] + (m1 + o1) * inv_s;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) { dy[i] = ndy[i]; zz[i] = nz[i]; hc[i] = nhc[i]; hp[i] = nhp[i]; }
+    }
+  }
+  cluster_sync_all();
+}
+
+template <typename Args, void (*Kern)(const Args)>
+int launch_rec(const Args& a, int cluster, int nclusters, int threads, cudaStream_t stream) {
+  if (cluster > 8) {
+    static std::once_flag once;
+    static cudaError_t err = cudaSuccess;
+    std::call_once(once, [] { err = cudaFuncSetAttribute(Kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1); });
+    PK_CHECK_CUDA(err);
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nclusters * cluster, 1, 1);
+  cfg.blockDim = dim3(threads, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, Kern, a));
+  return 0;
+}
+
+int pick_cluster(int requested, int H) {
+  if (requested == 8 || requested == 16) return requested;
+  // tuning knob for bring-up: PK_REC_CLUSTER=8|16
+  static int env = [] {
+    const char* e = getenv("PK_REC_CLUSTER");
+    return e ? atoi(e) : 0;
+  }();
+  if (env == 8 || env == 16) return env;
+  return (H > 512) ? 16 : 8;  // 16-CTA clusters keep the 35 k-tile weight slice spill-free
+}
+
+}  // namespace
+
+int ligru_fwd(const RecFwdArgs& a, cudaStream_t stream) {
+  PK_REQUIRE(a.T > 0 && a.B > 0 && a.H > 0, "ligru_fwd: empty problem");
+  PK_REQUIRE(a.ndir == 1 || a.ndir == 2, "ligru_fwd: ndir must be 1 or 2");
+  PK_REQUIRE(a.H <= 560, "ligru_fwd: hidden size %d > 560 not supported by the register-resident kernel", a.H);
+  const int nclusters = (a.ndir * a.B + kRows - 1) / kRows;
+  const int cl = pick_cluster(a.cluster, a.H);
+  if (cl == 8) {
+    if (a.H <= 256) return launch_rec<RecFwdArgs, ligru_fwd_kernel<16, 4, 8>>(a, 8, nclusters, 4 * 32, stream);
+    if (a.H <= 384) return launch_rec<RecFwdArgs, ligru_fwd_kernel<24, 6, 8>>(a, 8, nclusters, 6 * 32, stream);
+    if (a.H <= 512) return launch_rec<RecFwdArgs, ligru_fwd_kernel<32, 8, 8>>(a, 8, nclusters, 8 * 32, stream);
+    return launch_rec<RecFwdArgs, ligru_fwd_kernel<35, 9, 8>>(a, 8, nclusters, 9 * 32, stream);
+  }
+  if (a.H <= 256) return launch_rec<RecFwdArgs, ligru_fwd_kernel<16, 2, 16>>(a, 16, nclusters, 2 * 32, stream);
+  if (a.H <= 384) return launch_rec<RecFwdArgs, ligru_fwd_kernel<24, 3, 16>>(a, 16, nclusters, 3 * 32, stream);
+  if (a.H <= 512) return launch_rec<RecFwdArgs, ligru_fwd_kernel<32, 4, 16>>(a, 16, nclusters, 4 * 32, stream);
+  return launch_rec<RecFwdArgs, ligru_fwd_kernel<35, 5, 16>>(a, 16, nclusters, 5 * 32, stream);
+}
+
+int ligru_bwd(const RecBwdArgs& a, cudaStream_t stream) {
+  PK_REQUIRE(a.T > 0 && a.B > 0 && a.H > 0, "ligru_bwd: empty problem");
+  PK_REQUIRE(a.ndir == 1 || a.ndir == 2, "ligru_bwd: ndir must be 1 or 2");
+  PK_REQUIRE(a.H <= 560, "ligru_bwd: hidden size %d > 560 not supported by the register-resident kernel", a.H);
+  const int nclusters = (a.ndir * a.B + kRows - 1) / kRows;
+  const int cl = pick_cluster(a.cluster, a.H);
+  if (cl == 8) {
+    if (a.H <= 256) return launch_rec<RecBwdArgs, ligru_bwd_kernel<16, 4, 8>>(a, 8, nclusters, 2 * 64, stream);
+    if (a.H <= 384) return launch_rec<RecBwdArgs, ligru_bwd_kernel<24, 6, 8>>(a, 8, nclusters, 3 * 64, stream);
+    if (a.H <= 512) return launch_rec<RecBwdArgs, ligru_bwd_kernel<32, 8, 8>>(a, 8, nclusters, 4 * 64, stream);
+    return launch_rec<RecBwdArgs, ligru_bwd_kernel<35, 9, 8>>(a, 8, nclusters, 5 * 64, stream);
+  }
+  if (a.H <= 256) return launch_rec<RecBwdArgs, ligru_bwd_kernel<16, 2, 16>>(a, 16, nclusters, 1 * 64, stream);
+  if (a.H <= 384) return launch_rec<RecBwdArgs, ligru_bwd_kernel<24, 3, 16>>(a, 16, nclusters, 2 * 64, stream);
+  if (a.H <= 512) return launch_rec<RecBwdArgs, ligru_bwd_kernel<32, 4, 16>>(a, 16, nclusters, 2 * 64, stream);
+  return launch_rec<RecBwdArgs, ligru_bwd_kernel<35, 5, 16>>(a, 16, nclusters, 3 * 64, stream);
+}
+
+}  // namespace pk
