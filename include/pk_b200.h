@@ -51,6 +51,12 @@ extern "C" {
  * (default: chosen from H) */
 #define PK_REC_CLUSTER8 0x800
 #define PK_REC_CLUSTER16 0x1000
+/* step synchronisation: default = st.async + mbarrier; this flag selects the
+ * barrier.cluster variant (kept for A/B timing) */
+#define PK_REC_SYNC_BARRIER 0x2000
+/* timing experiments only (results are incomplete): skip the global stores / loads */
+#define PK_REC_DBG_NOSTORE 0x10000
+#define PK_REC_DBG_NOLOAD 0x20000
 #define PK_CELL_MASK 0xff
 
 const char* pk_last_error(void);

@@ -1,0 +1,375 @@
+"""CPU oracle for the acoustic-model hot path  --  TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+A plain-numpy restatement of the reference algorithm (mravanelli/pytorch-kaldi) for the path
+BASELINE.json names: module zoo forward/backward (neural_networks.py) + the cost ops of
+utils.forward_model + the optimizer step of core.run_nn.  Every function cites the reference
+file:line it follows.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this file; the product (pytorch-kaldi_b200/) never does.
+
+Pinning: the reference ships no golden vectors or tests for this path, so this
+restatement is pinned against outputs of the reference itself: tests/golden/make_golden.py
+imports /root/reference/neural_networks.py in the build container, runs it on seeded inputs and
+commits the vectors under tests/golden/*.npz; tests/test_oracle.py checks this file against
+them (forward, loss, error rate, every parameter gradient, one optimizer step).
+
+The restatement is deliberately literal (it concatenates x and flip(x) on the batch axis and
+normalises the duplicated rows exactly like the reference does) so that the de-duplicated,
+fused CUDA path is checked against the reference's own formulation, not against itself.
+Backward passes are derived by hand (no autograd) -> an independent check of the kernels' math.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# --------------------------------------------------------------------------------------
+# activations  (neural_networks.py:36-57 act_fun)
+# --------------------------------------------------------------------------------------
+
+
+def act_fwd(name: str, x: np.ndarray) -> np.ndarray:
+    if name == "relu":
+        return np.maximum(x, 0)
+    if name == "tanh":
+        return np.tanh(x)
+    if name == "sigmoid":
+        return 1.0 / (1.0 + np.exp(-x))
+    if name == "leaky_relu":  # nn.LeakyReLU(0.2), neural_networks.py:47-48
+        return np.where(x > 0, x, 0.2 * x)
+    if name == "elu":
+        return np.where(x > 0, x, np.expm1(np.minimum(x, 0)))
+    if name == "linear":  # nn.LeakyReLU(1) == identity, neural_networks.py:56-57
+        return x
+    raise ValueError(f"unknown activation {name}")
+
+
+def act_bwd(name: str, x: np.ndarray, y: np.ndarray) -> np.ndarray:
+    """d act / d x given pre-activation x and output y."""
+    if name == "relu":
+        return (x > 0).astype(x.dtype)
+    if name == "tanh":
+        return 1.0 - y * y
+    if name == "sigmoid":
+        return y * (1.0 - y)
+    if name == "leaky_relu":
+        return np.where(x > 0, 1.0, 0.2).astype(x.dtype)
+    if name == "elu":
+        return np.where(x > 0, 1.0, y + 1.0).astype(x.dtype)
+    if name == "linear":
+        return np.ones_like(x)
+    raise ValueError(f"unknown activation {name}")
+
+
+def sigmoid(x):
+    return 1.0 / (1.0 + np.exp(-x))
+
+
+def flip0(x: np.ndarray) -> np.ndarray:
+    """neural_networks.py:1962-1970 flip(x, 0): time reversal."""
+    return x[::-1].copy()
+
+
+# --------------------------------------------------------------------------------------
+# normalisation layers
+# --------------------------------------------------------------------------------------
+
+
+def layernorm_fwd(x, gamma, beta, eps=1e-6):
+    """neural_networks.py:23-33 custom LayerNorm: UNBIASED std, eps added to the std."""
+    n = x.shape[-1]
+    mean = x.mean(-1, keepdims=True)
+    xc = x - mean
+    std = np.sqrt((xc * xc).sum(-1, keepdims=True) / (n - 1))
+    y = gamma * xc / (std + eps) + beta
+    return y, (xc, std, gamma, eps)
+
+
+def layernorm_bwd(dy, cache):
+    xc, std, gamma, eps = cache
+    n = xc.shape[-1]
+    dgamma = (dy * xc / (std + eps)).reshape(-1, n).sum(0)
+    dbeta = dy.reshape(-1, n).sum(0)
+    g = dy * gamma
+    # y = g * xc / (std+eps); std = sqrt(sum xc^2/(n-1)); xc = x - mean
+    dxc = g / (std + eps)
+    dstd = -(g * xc).sum(-1, keepdims=True) / (std + eps) ** 2
+    dxc = dxc + dstd * xc / ((n - 1) * np.maximum(std, 1e-30))
+    dx = dxc - dxc.mean(-1, keepdims=True)
+    return dx, dgamma, dbeta
+
+
+def batchnorm_fwd(x2d, bn, training):
+    """nn.BatchNorm1d(C, momentum=0.05) on [N, C] rows (neural_networks.py:1070-1071, :1118-1124).
+    `bn` is a dict(weight, bias, running_mean, running_var, num_batches_tracked, eps, momentum);
+    running stats are updated in place when training (biased var for normalisation, unbiased for
+    the running estimate — torch semantics)."""
+    eps = bn.get("eps", 1e-5)
+    if training:
+        n = x2d.shape[0]
+        mean = x2d.mean(0)
+        var = ((x2d - mean) ** 2).mean(0)
+        m = bn.get("momentum", 0.05)
+        bn["running_mean"] = (1 - m) * bn["running_mean"] + m * mean
+        bn["running_var"] = (1 - m) * bn["running_var"] + m * var * n / max(n - 1, 1)
+        bn["num_batches_tracked"] = bn.get("num_batches_tracked", 0) + 1
+    else:
+        mean, var = bn["running_mean"], bn["running_var"]
+    rstd = 1.0 / np.sqrt(var + eps)
+    xhat = (x2d - mean) * rstd
+    y = xhat * bn["weight"] + bn["bias"]
+    return y, (xhat, rstd, bn["weight"], training)
+
+
+def batchnorm_bwd(dy, cache):
+    xhat, rstd, gamma, training = cache
+    dgamma = (dy * xhat).sum(0)
+    dbeta = dy.sum(0)
+    if training:
+        n = dy.shape[0]
+        dx = gamma * rstd * (dy - dbeta / n - xhat * dgamma / n)
+    else:
+        dx = gamma * rstd * dy
+    return dx, dgamma, dbeta
+
+
+# --------------------------------------------------------------------------------------
+# liGRU  (neural_networks.py:997-1155)
+# --------------------------------------------------------------------------------------
+
+
+def ligru_forward(x, layers, *, bidir=True, training=True, masks=None):
+    """x [T,B,D] -> [T,B,(2)H_last].
+
+    layers: list of dicts with keys
+        wh, wz   [H,D]   (nn.Linear weights, :1054-1059)      bh, bz [H] or None (bias only when no BN/LN)
+        uh, uz   [H,H]   (:1061-1063)
+        bn_wh, bn_wz     BatchNorm dicts or None (:1070-1071)
+        act      activation name, drop  dropout probability
+    masks: per-layer [rows,H] Bernoulli(1-p) masks (training; reference draws them on the CPU
+           generator, :1102-1105) or None -> eval scalar (1-p) (:1107).
+    Returns (out, caches).
+    """
+    caches = []
+    for li, L in enumerate(layers):
+        T, B, D = x.shape
+        H = L["uh"].shape[0]
+        xin = x
+        if bidir:  # :1095-1097
+            x2 = np.concatenate([x, flip0(x)], axis=1)
+        else:
+            x2 = x
+        R = x2.shape[1]
+        if training and masks is not None:
+            mask = masks[li].astype(x.dtype)
+        else:
+            mask = np.asarray(1.0 - L["drop"], dtype=x.dtype)  # :1107
+        wh_out = x2 @ L["wh"].T  # :1114
+        wz_out = x2 @ L["wz"].T  # :1115
+        if L.get("bh") is not None:
+            wh_out = wh_out + L["bh"]
+            wz_out = wz_out + L["bz"]
+        bn_cache_h = bn_cache_z = None
+        if L.get("bn_wh") is not None:  # :1118-1124
+            yh, bn_cache_h = batchnorm_fwd(wh_out.reshape(T * R, H), L["bn_wh"], training)
+            yz, bn_cache_z = batchnorm_fwd(wz_out.reshape(T * R, H), L["bn_wz"], training)
+            wh_out = yh.reshape(T, R, H)
+            wz_out = yz.reshape(T, R, H)
+        ht = np.zeros((R, H), dtype=x.dtype)  # :1096
+        hs = np.zeros((T, R, H), dtype=x.dtype)
+        zs = np.zeros_like(hs)
+        ats = np.zeros_like(hs)
+        for k in range(T):  # :1130-1141
+            zt = sigmoid(wz_out[k] + ht @ L["uz"].T)
+            at = wh_out[k] + ht @ L["uh"].T
+            hcand = act_fwd(L["act"], at) * mask
+            ht = zt * ht + (1 - zt) * hcand
+            hs[k], zs[k], ats[k] = ht, zt, at
+        if bidir:  # :1147-1150
+            h_f = hs[:, :B]
+            h_b = flip0(hs[:, B:])
+            out = np.concatenate([h_f, h_b], axis=2)
+        else:
+            out = hs
+        caches.append(dict(x2=x2, hs=hs, zs=zs, ats=ats, mask=mask, bn_h=bn_cache_h, bn_z=bn_cache_z, B=B,
+                           xin_shape=xin.shape))
+        x = out
+    return x, caches
+
+
+def ligru_backward(dout, layers, caches, *, bidir=True):
+    """Hand-derived BPTT of ligru_forward.  Returns (dx, grads) with grads[i] = dict(wh, wz, uh,
+    uz, bh, bz, bn_wh_weight, bn_wh_bias, bn_wz_weight, bn_wz_bias)."""
+    grads = [None] * len(layers)
+    for li in reversed(range(len(layers))):
+        L, c = layers[li], caches[li]
+        x2, hs, zs, ats, mask, B = c["x2"], c["hs"], c["zs"], c["ats"], c["mask"], c["B"]
+        T, R, H = hs.shape
+        if bidir:
+            dH = np.concatenate([dout[:, :, :H], flip0(dout[:, :, H:])], axis=1)
+        else:
+            dH = dout
+        carry = np.zeros((R, H), dtype=dout.dtype)
+        da_all = np.zeros_like(hs)
+        dz_all = np.zeros_like(hs)
+        duh = np.zeros_like(L["uh"])
+        duz = np.zeros_like(L["uz"])
+        for k in reversed(range(T)):
+            hprev = hs[k - 1] if k > 0 else np.zeros((R, H), dtype=dout.dtype)
+            zt, at = zs[k], ats[k]
+            y = act_fwd(L["act"], at)
+            hcand = y * mask
+            dh = dH[k] + carry
+            dzt = dh * (hprev - hcand)
+            dhc = dh * (1 - zt)
+            da = dhc * mask * act_bwd(L["act"], at, y)
+            dzp = dzt * zt * (1 - zt)
+            carry = dh * zt + da @ L["uh"] + dzp @ L["uz"]
+            duh += da.T @ hprev
+            duz += dzp.T @ hprev
+            da_all[k], dz_all[k] = da, dzp
+        g = dict(uh=duh, uz=duz)
+        dwh_pre = da_all.reshape(T * R, H)
+        dwz_pre = dz_all.reshape(T * R, H)
+        if c["bn_h"] is not None:
+            dwh_pre, g["bn_wh_weight"], g["bn_wh_bias"] = batchnorm_bwd(dwh_pre, c["bn_h"])
+            dwz_pre, g["bn_wz_weight"], g["bn_wz_bias"] = batchnorm_bwd(dwz_pre, c["bn_z"])
+        if L.get("bh") is not None:
+            g["bh"] = dwh_pre.sum(0)
+            g["bz"] = dwz_pre.sum(0)
+        x2f = x2.reshape(T * R, -1)
+        g["wh"] = dwh_pre.T @ x2f
+        g["wz"] = dwz_pre.T @ x2f
+        dx2 = (dwh_pre @ L["wh"] + dwz_pre @ L["wz"]).reshape(T, R, -1)
+        if bidir:
+            dout = dx2[:, :B] + flip0(dx2[:, B:])
+        else:
+            dout = dx2
+        grads[li] = g
+    return dout, grads
+
+
+# --------------------------------------------------------------------------------------
+# MLP  (neural_networks.py:60-150) — also the senone head (dnn_act = softmax)
+# --------------------------------------------------------------------------------------
+
+
+def log_softmax(x):
+    """act_fun("softmax") = nn.LogSoftmax(dim=1), neural_networks.py:53-54."""
+    m = x.max(axis=1, keepdims=True)
+    e = np.exp(x - m)
+    return x - m - np.log(e.sum(axis=1, keepdims=True))
+
+
+def mlp_forward(x, layers, *, training=True, drop_masks=None):
+    """x [N,D].  layers: dicts(w [O,I], b [O], bn (dict|None), ln (dict(gamma,beta)|None), act, drop).
+    Order per layer: drop(act(bn(ln(w x + b))))  (neural_networks.py:138-148).
+    drop_masks: per-layer keep masks (nn.Dropout inverted scaling applied here) or None."""
+    caches = []
+    for li, L in enumerate(layers):
+        lin = x @ L["w"].T + L["b"]
+        pre = lin
+        ln_cache = bn_cache = None
+        if L.get("ln") is not None:
+            pre, ln_cache = layernorm_fwd(pre, L["ln"]["gamma"], L["ln"]["beta"])
+        if L.get("bn") is not None:
+            pre, bn_cache = batchnorm_fwd(pre, L["bn"], training)
+        if L["act"] == "softmax":
+            y = log_softmax(pre)
+        else:
+            y = act_fwd(L["act"], pre)
+        keep = None
+        if training and L.get("drop", 0.0) > 0 and drop_masks is not None and drop_masks[li] is not None:
+            keep = drop_masks[li].astype(x.dtype) / (1.0 - L["drop"])
+            out = y * keep
+        else:
+            out = y
+        caches.append(dict(x=x, pre=pre, y=y, keep=keep, ln=ln_cache, bn=bn_cache))
+        x = out
+    return x, caches
+
+
+def mlp_backward(dout, layers, caches):
+    grads = [None] * len(layers)
+    for li in reversed(range(len(layers))):
+        L, c = layers[li], caches[li]
+        d = dout if c["keep"] is None else dout * c["keep"]
+        if L["act"] == "softmax":
+            d = d - np.exp(c["y"]) * d.sum(axis=1, keepdims=True)
+        else:
+            d = d * act_bwd(L["act"], c["pre"], c["y"])
+        g = {}
+        if c["bn"] is not None:
+            d, g["bn_weight"], g["bn_bias"] = batchnorm_bwd(d, c["bn"])
+        if c["ln"] is not None:
+            d, g["ln_gamma"], g["ln_beta"] = layernorm_bwd(d, c["ln"])
+        g["w"] = d.T @ c["x"]
+        g["b"] = d.sum(0)
+        dout = d @ L["w"]
+        grads[li] = g
+    return dout, grads
+
+
+# --------------------------------------------------------------------------------------
+# cost ops of utils.forward_model
+# --------------------------------------------------------------------------------------
+
+
+def nll_loss(logp, labels):
+    """nn.NLLLoss() mean over ALL rows incl. padding (utils.py:2087, :2344-2361)."""
+    n = logp.shape[0]
+    return -logp[np.arange(n), labels].mean()
+
+
+def nll_loss_bwd(logp, labels, gout=1.0):
+    d = np.zeros_like(logp)
+    n = logp.shape[0]
+    d[np.arange(n), labels] = -gout / n
+    return d
+
+
+def cost_err(logp, labels):
+    """utils.py:2379-2380: mean(argmax != lab); argmax = first maximum."""
+    return float((np.argmax(logp, axis=1) != labels).mean())
+
+
+# --------------------------------------------------------------------------------------
+# optimizers (torch.optim semantics as configured by utils.optimizer_init, utils.py:2106-2164)
+# --------------------------------------------------------------------------------------
+
+
+def rmsprop_step(p, g, v, lr=0.0004, alpha=0.95, eps=1e-8):
+    v = alpha * v + (1 - alpha) * g * g
+    p = p - lr * g / (np.sqrt(v) + eps)
+    return p, v
+
+
+def sgd_step(p, g, lr=0.08):
+    return p - lr * g
+
+
+# --------------------------------------------------------------------------------------
+# whole training step of the headline recipe: liGRU stack -> softmax head(s) -> NLL (+ err)
+# (cfg/TIMIT_baselines/TIMIT_liGRU_fmllr.cfg [model]; core.py:616-642)
+# --------------------------------------------------------------------------------------
+
+
+def ligru_model_step(x, labels, ligru_layers, heads, *, masks, bidir=True, loss_weights=None):
+    """x [T,B,D], labels: list of [T*B] int arrays (one per head, t-major rows utils.py:2323).
+    heads: list of single-layer softmax MLP layer dicts.  Returns dict(loss, losses, err, logp, grads)."""
+    out, caches = ligru_forward(x, ligru_layers, bidir=bidir, training=True, masks=masks)
+    T, B, F = out.shape
+    flat = out.reshape(T * B, F)
+    dflat = np.zeros_like(flat)
+    losses, logps, hgrads = [], [], []
+    lw = loss_weights or [1.0] * len(heads)
+    for hd, lab, w in zip(heads, labels, lw):
+        logp, hc = mlp_forward(flat, [hd], training=True)
+        losses.append(nll_loss(logp, lab))
+        logps.append(logp)
+        dlogp = nll_loss_bwd(logp, lab, w)
+        dx, hg = mlp_backward(dlogp, [hd], hc)
+        dflat += dx
+        hgrads.append(hg[0])
+    _, lgrads = ligru_backward(dflat.reshape(T, B, F), ligru_layers, caches, bidir=bidir)
+    loss = sum(w * l for w, l in zip(lw, losses))
+    return dict(loss=loss, losses=losses, err=cost_err(logps[0], labels[0]), logp=logps, out=out, ligru_grads=lgrads,
+                head_grads=hgrads)

@@ -95,6 +95,8 @@ int pk_rnn_layer_fwd(int cell, int T, int B, int H, int ndir, int act, const flo
                      float mask_scalar, float* Y32, int64_t ldy32, void* Y16, int64_t ldy16, float* HT,
                      void* HT16, float* ZT, float* HCT, int64_t ldt, void* stream) {
   const int cluster = (cell & PK_REC_CLUSTER16) ? 16 : (cell & PK_REC_CLUSTER8) ? 8 : 0;
+  const int sync = (cell & PK_REC_SYNC_BARRIER) ? 0 : -1;
+  const int dbg = ((cell & PK_REC_DBG_NOSTORE) ? 1 : 0) | ((cell & PK_REC_DBG_NOLOAD) ? 2 : 0);
   cell &= PK_CELL_MASK;
   PK_REQUIRE(cell == PK_CELL_LIGRU, "pk_rnn_layer_fwd: cell kind %d not implemented", cell);
   PK_REQUIRE(PT && scale && shift && U, "pk_rnn_layer_fwd: null input");
@@ -105,6 +107,8 @@ int pk_rnn_layer_fwd(int cell, int T, int B, int H, int ndir, int act, const flo
   a.Y32 = Y32; a.ldy32 = ldy32; a.Y16 = static_cast<__half*>(Y16); a.ldy16 = ldy16;
   a.HT = HT; a.HT16 = static_cast<__half*>(HT16); a.ZT = ZT; a.HCT = HCT; a.ldt = ldt;
   a.cluster = cluster;
+  a.sync = sync;
+  a.dbg = dbg;
   return ligru_fwd(a, static_cast<cudaStream_t>(stream));
 }
 
@@ -112,6 +116,8 @@ int pk_rnn_layer_bwd(int cell, int T, int B, int H, int ndir, int act, const flo
                      const float* ZT, const float* HCT, int64_t ldt, const float* U, const float* mask,
                      float mask_scalar, const float* gscale, float* GT, void* GT16, void* stream) {
   const int cluster = (cell & PK_REC_CLUSTER16) ? 16 : (cell & PK_REC_CLUSTER8) ? 8 : 0;
+  const int sync = (cell & PK_REC_SYNC_BARRIER) ? 0 : -1;
+  const int dbg = ((cell & PK_REC_DBG_NOSTORE) ? 1 : 0) | ((cell & PK_REC_DBG_NOLOAD) ? 2 : 0);
   cell &= PK_CELL_MASK;
   PK_REQUIRE(cell == PK_CELL_LIGRU, "pk_rnn_layer_bwd: cell kind %d not implemented", cell);
   PK_REQUIRE(dYT && HT && ZT && HCT && U && GT, "pk_rnn_layer_bwd: null input");
@@ -120,6 +126,8 @@ int pk_rnn_layer_bwd(int cell, int T, int B, int H, int ndir, int act, const flo
   a.dYT = dYT; a.HT = HT; a.ZT = ZT; a.HCT = HCT; a.ldt = ldt; a.U = U; a.mask = mask;
   a.mask_scalar = mask_scalar; a.gscale = gscale; a.GT = GT; a.GT16 = static_cast<__half*>(GT16);
   a.cluster = cluster;
+  a.sync = sync;
+  a.dbg = dbg;
   return ligru_bwd(a, static_cast<cudaStream_t>(stream));
 }
 

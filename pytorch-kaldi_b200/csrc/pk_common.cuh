@@ -253,6 +253,31 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, uint4 v) {
                : "memory");
 }
 
+// remote (or local) 16-byte store that signals `bytes` on an mbarrier living in the SAME target
+// CTA: data and completion travel together, so the consumer needs no fence and no barrier.
+__device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, uint4 v, uint32_t cluster_mbar) {
+  asm volatile(
+      "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+          cluster_addr),
+      "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(cluster_mbar)
+      : "memory");
+}
+// wait on a local mbarrier whose transaction bytes are produced by peer CTAs of the cluster
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
 // ----------------------------------------------------------------------------
 // warp-level tensor-core MMA (fp16 operands, fp32 accumulate) + ldmatrix
 // ----------------------------------------------------------------------------

@@ -51,6 +51,8 @@ struct RecFwdArgs {
   float* HCT = nullptr;
   long long ldt = 0;
   int cluster = 0;  // 0 = auto, 8 or 16 CTAs per cluster
+  int sync = -1;    // -1 = default (st.async + mbarrier), 0 = barrier.cluster, 1 = st.async
+  int dbg = 0;      // timing experiments only: bit0 skip global stores, bit1 skip global loads
 };
 int ligru_fwd(const RecFwdArgs& a, cudaStream_t stream);
 
@@ -68,6 +70,8 @@ struct RecBwdArgs {
   float* GT = nullptr;            // [ndir][2H][ldt] fp32
   __half* GT16 = nullptr;         // [ndir][2H][ldt] fp16, scaled by *gscale
   int cluster = 0;
+  int sync = -1;
+  int dbg = 0;
 };
 int ligru_bwd(const RecBwdArgs& a, cudaStream_t stream);
 

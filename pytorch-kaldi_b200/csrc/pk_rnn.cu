@@ -3,17 +3,24 @@
 // The reference runs `for k in range(T)` in Python with ~11 launches per step
 // (neural_networks.py:1130-1141).  Here one launch covers the whole sequence:
 //
-//   * a thread-block CLUSTER of 8 CTAs owns 8 rows of the (direction-stacked) batch; the
+//   * a thread-block CLUSTER of 8 (or 16) CTAs owns 8 rows of the direction-stacked batch; the
 //     bidirectional layer is just 2B independent rows (reference :1095-1097 stacks x and
 //     flip(x) on the batch axis and shares the weights), so 2B/8 clusters run concurrently;
-//   * inside a cluster the hidden units are sliced across the 8 CTAs; every warp keeps its
+//   * inside a cluster the hidden units are sliced across the CTAs; every warp keeps its
 //     [16 x H] slice of the recurrent matrix U in REGISTERS as mma.sync A-fragments (fp16,
 //     loaded once), so the only per-step operand traffic is the hidden state itself;
 //   * each step: h_{t-1} (fp16 copy, 8 rows x H) is read from shared memory with ldmatrix,
 //     the [gates x 8 rows] products run on the tensor cores with fp32 accumulation, the gate
 //     non-linearities / dropout mask / BatchNorm affine are applied in registers on the fp32
-//     state, and the new fp16 slice is pushed to the other 7 CTAs through distributed shared
-//     memory (st.shared::cluster, 16-byte vectors) followed by ONE cluster barrier per step;
+//     state, and the new fp16 slice is pushed to every CTA of the cluster through distributed
+//     shared memory;
+//   * step synchronisation (SY=1, default): the push is `st.async` — each 16-byte store carries
+//     its own completion (complete_tx on the TARGET CTA's mbarrier), consumers just wait on
+//     their local mbarrier: no fence, no cluster barrier, so the global-memory traffic of the
+//     step (saved activations out, next projections in) is never waited for.
+//     (SY=0 keeps the first implementation — plain st.shared::cluster + one
+//     barrier.cluster per step — whose release fence compiles to MEMBAR.ALL.GPU and stalls on
+//     the outstanding global stores; kept for A/B measurement.)
 //   * flip / stack / cat of the reference (:1144-1150, :1962-1970) disappear into indexing:
 //     direction-1 rows read time T-1-k and write their outputs at natural time.
 //
@@ -33,25 +40,29 @@ constexpr int kRows = 8;  // batch rows per cluster (the n8 of m16n8k16)
 // =====================================================================================
 // forward
 // =====================================================================================
-template <int KT, int MT, int CL>
+template <int KT, int MT, int CL, int SY>
 __global__ void __launch_bounds__(MT * 32, 1) ligru_fwd_kernel(const RecFwdArgs a) {
-  constexpr int kCluster = CL;
-  constexpr int HS = CL * 8 * MT + 8;  // halves per row of the staged state (pad keeps ldmatrix conflict-free)
+  constexpr int HS = CL * 8 * MT + 8;  // halves per staged state row (pad keeps ldmatrix conflict-free)
   static_assert((CL * MT) % 8 == 0, "row pitch must be 16 (mod 128) bytes");
   static_assert(CL * 8 * MT >= 16 * KT, "unit slots must cover the K range");
+  constexpr uint32_t kTxBytes = CL * MT * 128;  // bytes every CTA receives per step
   __shared__ __align__(16) __half h16[2][kRows][HS];
+  __shared__ __align__(16) __half stage[MT][kRows][8];
+  __shared__ __align__(8) uint64_t mbar[2];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int g = lane >> 2;
   const int q = lane & 3;
   const uint32_t crank = cluster_ctarank();
-  const int cl = blockIdx.x / kCluster;
+  const int cl = blockIdx.x / CL;
   const int H = a.H, B = a.B, T = a.T;
   const int nrows = a.ndir * B;
   const int ubase = crank * (8 * MT) + warp * 8;  // first unit of this warp's 8-unit tile
   const int u = ubase + g;
   const bool u_ok = u < H;
+  const bool do_store = !(a.dbg & 1);
+  const bool do_load = !(a.dbg & 2);
 
   // ---- recurrent weights -> A fragments (row g = candidate gate "h", row g+8 = update gate "z")
   uint32_t A[KT][4];
@@ -75,9 +86,14 @@ __global__ void __launch_bounds__(MT * 32, 1) ligru_fwd_kernel(const RecFwdArgs 
     }
   }
 
-  // ---- zero both state buffers (h_0 = 0, reference :1096), then make sure every CTA did
+  // ---- zero both state buffers (h_0 = 0, reference :1096), init barriers, then cluster-wide sync
   for (int i = threadIdx.x; i < 2 * kRows * HS / 2; i += blockDim.x)
     reinterpret_cast<uint32_t*>(&h16[0][0][0])[i] = 0u;
+  if (SY && threadIdx.x == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    fence_mbar_init();
+  }
   cluster_sync_all();
 
   // ---- per-thread row bookkeeping: this thread owns (unit u, rows 2q and 2q+1)
@@ -122,6 +138,10 @@ __global__ void __launch_bounds__(MT * 32, 1) ligru_fwd_kernel(const RecFwdArgs 
 
   for (int k = 0; k < T; ++k) {
     const int cur = k & 1, nxt = cur ^ 1;
+    if (SY) {
+      if (k > 0) mbar_wait_cluster(&mbar[cur], ((k - 1) >> 1) & 1);  // h_{k-1} has landed from all peers
+      if (threadIdx.x == 0) mbar_arrive_expect_tx(&mbar[nxt], kTxBytes);  // arm the fill of this step
+    }
     // ---------------- U * h_{k-1} on the tensor cores ----------------
     float acc[4][4];
 #pragma unroll
@@ -156,22 +176,32 @@ __global__ void __launch_bounds__(MT * 32, 1) ligru_fwd_kernel(const RecFwdArgs 
       if (!rok[i]) h = 0.f;
       hn[i] = h; zz[i] = zt; hcv[i] = hc;
       hprev[i] = h;
-      h16[nxt][2 * q + i][u] = f16_sat(h);
+      if (SY) stage[warp][2 * q + i][g] = f16_sat(h);
+      else h16[nxt][2 * q + i][u] = f16_sat(h);
     }
     __syncwarp();
-    // ---------------- broadcast the warp's 8x8 fp16 tile to the 7 peer CTAs ----------------
+    // ---------------- push the warp's 8x8 fp16 tile to the CTAs of the cluster ----------------
     {
       const int n = lane & 7;
-      const __half* src = &h16[nxt][n][ubase];
-      const uint4 val = *reinterpret_cast<const uint4*>(src);
-      const uint32_t laddr = smem_u32(src);
+      const uint32_t laddr = smem_u32(&h16[nxt][n][ubase]);
+      if (SY) {
+        const uint4 val = *reinterpret_cast<const uint4*>(&stage[warp][n][0]);
+        const uint32_t lbar = smem_u32(&mbar[nxt]);
 #pragma unroll
-      for (int j = 0; j < kCluster / 4; ++j) {
-        const uint32_t dst = (lane >> 3) + 4 * j;
-        if (dst != crank) st_cluster_v4(mapa_shared(laddr, dst), val);
+        for (int j = 0; j < CL / 4; ++j) {
+          const uint32_t dst = (lane >> 3) + 4 * j;
+          st_async_v4(mapa_shared(laddr, dst), val, mapa_shared(lbar, dst));
+        }
+      } else {
+        const uint4 val = *reinterpret_cast<const uint4*>(&h16[nxt][n][ubase]);
+#pragma unroll
+        for (int j = 0; j < CL / 4; ++j) {
+          const uint32_t dst = (lane >> 3) + 4 * j;
+          if (dst != crank) st_cluster_v4(mapa_shared(laddr, dst), val);
+        }
       }
     }
-    cluster_arrive_release();
+    if (!SY) cluster_arrive_release();
 
     // ---------------- off the critical path: global stores + next step's projections ----------
     float nph[2] = {0.f, 0.f}, npz[2] = {0.f, 0.f};
@@ -180,24 +210,28 @@ __global__ void __launch_bounds__(MT * 32, 1) ligru_fwd_kernel(const RecFwdArgs 
       if (rok[i]) {
         const int t = rd[i] ? (T - 1 - k) : k;
         const long long col = static_cast<long long>(t) * B + rb[i];
-        if (k + 1 < T) {
+        if (k + 1 < T && do_load) {
           const long long ncol = col + (rd[i] ? -B : B);
           nph[i] = __ldg(Ph + ncol);
           npz[i] = __ldg(Pz + ncol);
         }
-        const long long ch_idx = static_cast<long long>(rd[i] * H + u) * a.ldt + col;
-        if (a.HT) a.HT[ch_idx] = hn[i];
-        if (a.HT16) a.HT16[ch_idx] = f16_sat(hn[i]);
-        if (a.ZT) a.ZT[ch_idx] = zz[i];
-        if (a.HCT) a.HCT[ch_idx] = hcv[i];
-        if (a.Y32) a.Y32[col * a.ldy32 + rd[i] * H + u] = hn[i];
-        if (a.Y16) a.Y16[col * a.ldy16 + rd[i] * H + u] = f16_sat(hn[i]);
+        if (do_store) {
+          const long long ch_idx = static_cast<long long>(rd[i] * H + u) * a.ldt + col;
+          if (a.HT) a.HT[ch_idx] = hn[i];
+          if (a.HT16) a.HT16[ch_idx] = f16_sat(hn[i]);
+          if (a.ZT) a.ZT[ch_idx] = zz[i];
+          if (a.HCT) a.HCT[ch_idx] = hcv[i];
+          if (a.Y32) a.Y32[col * a.ldy32 + rd[i] * H + u] = hn[i];
+          if (a.Y16) a.Y16[col * a.ldy16 + rd[i] * H + u] = f16_sat(hn[i]);
+        }
       }
     }
     ph[0] = nph[0]; ph[1] = nph[1]; pz[0] = npz[0]; pz[1] = npz[1];
-    cluster_wait_acquire();
+    if (!SY) cluster_wait_acquire();
+    else __syncwarp();
   }
-  // no CTA may exit while peers can still write into its shared memory
+  // drain the last incoming fill, then: no CTA may exit while peers can still write into it
+  if (SY) mbar_wait_cluster(&mbar[T & 1], ((T - 1) >> 1) & 1);
   cluster_sync_all();
 }
 
@@ -211,17 +245,20 @@ __global__ void __launch_bounds__(MT * 32, 1) ligru_fwd_kernel(const RecFwdArgs 
 // Thread ownership: warp (mt, half) keeps the 16-unit x (half-gate K range) slice of U^T in
 // registers; after the MMA the two warps of a pair exchange partial sums through smem so that
 // warp (mt,0) finishes units g and warp (mt,1) units g+8 of the tile.
-template <int KT, int MT, int CL>
+template <int KT, int MT, int CL, int SY>
 __global__ void __launch_bounds__(((MT + 1) / 2) * 64, 1) ligru_bwd_kernel(const RecBwdArgs a) {
-  constexpr int kCluster = CL;
   constexpr int MT16 = (MT + 1) / 2;     // 16-unit tiles per CTA
+  constexpr int NW = MT16 * 2;           // warps
   constexpr int KP = CL * 8 * MT;        // unit-slot stride between the two gates in the staged vector
   static_assert((CL * MT) % 8 == 0, "row pitch must be 16 (mod 128) bytes");
   static_assert(KP >= 16 * KT, "unit slots must cover the K range");
   constexpr int GS = 2 * KP + 8;         // halves per staged row
   constexpr int UPC = 8 * MT;            // units owned per CTA
+  constexpr uint32_t kTxBytes = CL * MT * 256;
   __shared__ __align__(16) __half g16[2][kRows][GS];
-  __shared__ float xbuf[MT16][2][32][2];
+  __shared__ __align__(16) __half stage[NW][2][kRows][8];
+  __shared__ float xbuf[2][MT16][2][32][2];  // double-buffered by step parity
+  __shared__ __align__(8) uint64_t mbar[2];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -230,10 +267,12 @@ __global__ void __launch_bounds__(((MT + 1) / 2) * 64, 1) ligru_bwd_kernel(const
   const int mt = warp >> 1;
   const int half = warp & 1;
   const uint32_t crank = cluster_ctarank();
-  const int cl = blockIdx.x / kCluster;
+  const int cl = blockIdx.x / CL;
   const int H = a.H, B = a.B, T = a.T;
   const int nrows = a.ndir * B;
   const int cta_ubase = crank * UPC;
+  const bool do_store = !(a.dbg & 1);
+  const bool do_load = !(a.dbg & 2);
 
   // ---- U^T slice -> A fragments.  A[row = unit][col = j] = Ug[j][unit], Ug = Uh (half 0) / Uz (half 1)
   uint32_t A[KT][4];
@@ -267,6 +306,11 @@ __global__ void __launch_bounds__(((MT + 1) / 2) * 64, 1) ligru_bwd_kernel(const
 
   for (int i = threadIdx.x; i < 2 * kRows * GS / 2; i += blockDim.x)
     reinterpret_cast<uint32_t*>(&g16[0][0][0])[i] = 0u;
+  if (SY && threadIdx.x == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    fence_mbar_init();
+  }
   cluster_sync_all();
 
   // ---- element ownership of this thread: unit = tile unit (8*half + g), rows 2q, 2q+1
@@ -320,6 +364,7 @@ __global__ void __launch_bounds__(((MT + 1) / 2) * 64, 1) ligru_bwd_kernel(const
 
   for (int k = T - 1; k >= 0; --k) {
     const int buf = k & 1;
+    if (SY && threadIdx.x == 0) mbar_arrive_expect_tx(&mbar[buf], kTxBytes);
     // ---------------- phase A: pointwise backward of step k ----------------
     float da[2], dpz[2], keep[2];
 #pragma unroll
@@ -335,8 +380,13 @@ __global__ void __launch_bounds__(((MT + 1) / 2) * 64, 1) ligru_bwd_kernel(const
       da[i] = dav; dpz[i] = dpzv;
       keep[i] = dh * zz[i];
       if (warp_ok) {
-        g16[buf][2 * q + i][slot + cta_ubase] = f16_sat(dav * s);
-        g16[buf][2 * q + i][KP + slot + cta_ubase] = f16_sat(dpzv * s);
+        if (SY) {
+          stage[warp][0][2 * q + i][g] = f16_sat(dav * s);
+          stage[warp][1][2 * q + i][g] = f16_sat(dpzv * s);
+        } else {
+          g16[buf][2 * q + i][slot + cta_ubase] = f16_sat(dav * s);
+          g16[buf][2 * q + i][KP + slot + cta_ubase] = f16_sat(dpzv * s);
+        }
       }
     }
     __syncwarp();
@@ -344,34 +394,46 @@ __global__ void __launch_bounds__(((MT + 1) / 2) * 64, 1) ligru_bwd_kernel(const
       // 16 chunks (8 rows x 2 gates) of 16 bytes, each to every peer: lane -> chunk (lane&15), peer half (lane>>4)
       const int n = lane & 7;
       const int gate = (lane >> 3) & 1;
-      const __half* src = &g16[buf][n][gate * KP + cta_ubase + wslot0];
-      const uint4 val = *reinterpret_cast<const uint4*>(src);
-      const uint32_t laddr = smem_u32(src);
+      const uint32_t laddr = smem_u32(&g16[buf][n][gate * KP + cta_ubase + wslot0]);
+      if (SY) {
+        const uint4 val = *reinterpret_cast<const uint4*>(&stage[warp][gate][n][0]);
+        const uint32_t lbar = smem_u32(&mbar[buf]);
 #pragma unroll
-      for (int j = 0; j < kCluster / 2; ++j) {
-        const uint32_t dst = (lane >> 4) * (kCluster / 2) + j;
-        if (dst != crank) st_cluster_v4(mapa_shared(laddr, dst), val);
-      }
-    }
-    cluster_arrive_release();
-    // global stores of this step + prefetch of step k-1 while the barrier completes
+        for (int j = 0; j < CL / 2; ++j) {
+          const uint32_t dst = (lane >> 4) * (CL / 2) + j;
+          st_async_v4(mapa_shared(laddr, dst), val, mapa_shared(lbar, dst));
+        }
+      } else {
+        const uint4 val = *reinterpret_cast<const uint4*>(&g16[buf][n][gate * KP + cta_ubase + wslot0]);
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      if (rok[i]) {
-        const int t = rd[i] ? (T - 1 - k) : k;
-        const long long col = static_cast<long long>(t) * B + rb[i];
-        const long long idx = rd[i] * dir_stride + static_cast<long long>(u) * a.ldt + col;
-        a.GT[idx] = da[i];
-        a.GT[idx + gate_stride] = dpz[i];
-        if (a.GT16) {
-          a.GT16[idx] = f16_sat(da[i] * s);
-          a.GT16[idx + gate_stride] = f16_sat(dpz[i] * s);
+        for (int j = 0; j < CL / 2; ++j) {
+          const uint32_t dst = (lane >> 4) * (CL / 2) + j;
+          if (dst != crank) st_cluster_v4(mapa_shared(laddr, dst), val);
         }
       }
     }
-    float ndy[2], nz[2], nhc[2], nhp[2];
-    if (k > 0) load_step(k - 1, ndy, nz, nhc, nhp);
-    cluster_wait_acquire();
+    if (!SY) cluster_arrive_release();
+    // global stores of this step + prefetch of step k-1 while the exchange completes
+    if (do_store) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        if (rok[i]) {
+          const int t = rd[i] ? (T - 1 - k) : k;
+          const long long col = static_cast<long long>(t) * B + rb[i];
+          const long long idx = rd[i] * dir_stride + static_cast<long long>(u) * a.ldt + col;
+          a.GT[idx] = da[i];
+          a.GT[idx + gate_stride] = dpz[i];
+          if (a.GT16) {
+            a.GT16[idx] = f16_sat(da[i] * s);
+            a.GT16[idx + gate_stride] = f16_sat(dpz[i] * s);
+          }
+        }
+      }
+    }
+    float ndy[2] = {0.f, 0.f}, nz[2] = {0.f, 0.f}, nhc[2] = {0.f, 0.f}, nhp[2] = {0.f, 0.f};
+    if (k > 0 && do_load) load_step(k - 1, ndy, nz, nhc, nhp);
+    if (SY) mbar_wait_cluster(&mbar[buf], ((T - 1 - k) >> 1) & 1);
+    else cluster_wait_acquire();
 
     // ---------------- phase B: U^T [da; dpz] for the carry into step k-1 ----------------
     if (k > 0) {
@@ -395,11 +457,11 @@ __global__ void __launch_bounds__(((MT + 1) / 2) * 64, 1) ligru_bwd_kernel(const
 #pragma unroll
       for (int e = 0; e < 4; ++e) c4[e] = (acc[0][e] + acc[1][e]) + (acc[2][e] + acc[3][e]);
       // warp half 0 keeps units g (c4[0..1]) and ships c4[2..3]; half 1 keeps g+8 and ships c4[0..1]
-      xbuf[mt][half][lane][0] = half ? c4[0] : c4[2];
-      xbuf[mt][half][lane][1] = half ? c4[1] : c4[3];
+      xbuf[buf][mt][half][lane][0] = half ? c4[0] : c4[2];
+      xbuf[buf][mt][half][lane][1] = half ? c4[1] : c4[3];
       asm volatile("bar.sync %0, 64;" ::"r"(mt + 1) : "memory");
-      const float o0 = xbuf[mt][half ^ 1][lane][0];
-      const float o1 = xbuf[mt][half ^ 1][lane][1];
+      const float o0 = xbuf[buf][mt][half ^ 1][lane][0];
+      const float o1 = xbuf[buf][mt][half ^ 1][lane][1];
       const float m0 = half ? c4[2] : c4[0];
       const float m1 = half ? c4[3] : c4[1];
       carry[0] = keep[0] + (m0 + o0) * inv_s;
@@ -437,13 +499,45 @@ int launch_rec(const Args& a, int cluster, int nclusters, int threads, cudaStrea
 
 int pick_cluster(int requested, int H) {
   if (requested == 8 || requested == 16) return requested;
-  // tuning knob for bring-up: PK_REC_CLUSTER=8|16
-  static int env = [] {
+  static int env = [] {  // tuning knob for bring-up: PK_REC_CLUSTER=8|16
     const char* e = getenv("PK_REC_CLUSTER");
     return e ? atoi(e) : 0;
   }();
   if (env == 8 || env == 16) return env;
-  return (H > 512) ? 16 : 8;  // 16-CTA clusters keep the 35 k-tile weight slice spill-free
+  (void)H;
+  return 8;
+}
+int pick_sync(int requested) {  // 1 = st.async + mbarrier (default), 0 = barrier.cluster
+  if (requested == 0 || requested == 1) return requested;
+  static int env = [] {
+    const char* e = getenv("PK_REC_SYNC");
+    return e ? atoi(e) : 1;
+  }();
+  return env ? 1 : 0;
+}
+
+#define PK_DISPATCH_REC(KERN, ARGS, THREADS_OF_MT)                                                            \
+  if (cl == 8) {                                                                                             \
+    if (a.H <= 256) return launch_rec<ARGS, KERN<16, 4, 8, SYNC>>(a, 8, nclusters, THREADS_OF_MT(4), stream);   \
+    if (a.H <= 384) return launch_rec<ARGS, KERN<24, 6, 8, SYNC>>(a, 8, nclusters, THREADS_OF_MT(6), stream);   \
+    if (a.H <= 512) return launch_rec<ARGS, KERN<32, 8, 8, SYNC>>(a, 8, nclusters, THREADS_OF_MT(8), stream);   \
+    return launch_rec<ARGS, KERN<35, 9, 8, SYNC>>(a, 8, nclusters, THREADS_OF_MT(9), stream);                   \
+  }                                                                                                           \
+  if (a.H <= 256) return launch_rec<ARGS, KERN<16, 2, 16, SYNC>>(a, 16, nclusters, THREADS_OF_MT(2), stream);   \
+  if (a.H <= 384) return launch_rec<ARGS, KERN<24, 3, 16, SYNC>>(a, 16, nclusters, THREADS_OF_MT(3), stream);   \
+  if (a.H <= 512) return launch_rec<ARGS, KERN<32, 4, 16, SYNC>>(a, 16, nclusters, THREADS_OF_MT(4), stream);   \
+  return launch_rec<ARGS, KERN<35, 5, 16, SYNC>>(a, 16, nclusters, THREADS_OF_MT(5), stream);
+
+#define PK_FWD_THREADS(mt) ((mt) * 32)
+#define PK_BWD_THREADS(mt) ((((mt) + 1) / 2) * 64)
+
+template <int SYNC>
+int ligru_fwd_t(const RecFwdArgs& a, int cl, int nclusters, cudaStream_t stream) {
+  PK_DISPATCH_REC(ligru_fwd_kernel, RecFwdArgs, PK_FWD_THREADS)
+}
+template <int SYNC>
+int ligru_bwd_t(const RecBwdArgs& a, int cl, int nclusters, cudaStream_t stream) {
+  PK_DISPATCH_REC(ligru_bwd_kernel, RecBwdArgs, PK_BWD_THREADS)
 }
 
 }  // namespace
@@ -454,16 +548,7 @@ int ligru_fwd(const RecFwdArgs& a, cudaStream_t stream) {
   PK_REQUIRE(a.H <= 560, "ligru_fwd: hidden size %d > 560 not supported by the register-resident kernel", a.H);
   const int nclusters = (a.ndir * a.B + kRows - 1) / kRows;
   const int cl = pick_cluster(a.cluster, a.H);
-  if (cl == 8) {
-    if (a.H <= 256) return launch_rec<RecFwdArgs, ligru_fwd_kernel<16, 4, 8>>(a, 8, nclusters, 4 * 32, stream);
-    if (a.H <= 384) return launch_rec<RecFwdArgs, ligru_fwd_kernel<24, 6, 8>>(a, 8, nclusters, 6 * 32, stream);
-    if (a.H <= 512) return launch_rec<RecFwdArgs, ligru_fwd_kernel<32, 8, 8>>(a, 8, nclusters, 8 * 32, stream);
-    return launch_rec<RecFwdArgs, ligru_fwd_kernel<35, 9, 8>>(a, 8, nclusters, 9 * 32, stream);
-  }
-  if (a.H <= 256) return launch_rec<RecFwdArgs, ligru_fwd_kernel<16, 2, 16>>(a, 16, nclusters, 2 * 32, stream);
-  if (a.H <= 384) return launch_rec<RecFwdArgs, ligru_fwd_kernel<24, 3, 16>>(a, 16, nclusters, 3 * 32, stream);
-  if (a.H <= 512) return launch_rec<RecFwdArgs, ligru_fwd_kernel<32, 4, 16>>(a, 16, nclusters, 4 * 32, stream);
-  return launch_rec<RecFwdArgs, ligru_fwd_kernel<35, 5, 16>>(a, 16, nclusters, 5 * 32, stream);
+  return pick_sync(a.sync) ? ligru_fwd_t<1>(a, cl, nclusters, stream) : ligru_fwd_t<0>(a, cl, nclusters, stream);
 }
 
 int ligru_bwd(const RecBwdArgs& a, cudaStream_t stream) {
@@ -472,16 +557,7 @@ int ligru_bwd(const RecBwdArgs& a, cudaStream_t stream) {
   PK_REQUIRE(a.H <= 560, "ligru_bwd: hidden size %d > 560 not supported by the register-resident kernel", a.H);
   const int nclusters = (a.ndir * a.B + kRows - 1) / kRows;
   const int cl = pick_cluster(a.cluster, a.H);
-  if (cl == 8) {
-    if (a.H <= 256) return launch_rec<RecBwdArgs, ligru_bwd_kernel<16, 4, 8>>(a, 8, nclusters, 2 * 64, stream);
-    if (a.H <= 384) return launch_rec<RecBwdArgs, ligru_bwd_kernel<24, 6, 8>>(a, 8, nclusters, 3 * 64, stream);
-    if (a.H <= 512) return launch_rec<RecBwdArgs, ligru_bwd_kernel<32, 8, 8>>(a, 8, nclusters, 4 * 64, stream);
-    return launch_rec<RecBwdArgs, ligru_bwd_kernel<35, 9, 8>>(a, 8, nclusters, 5 * 64, stream);
-  }
-  if (a.H <= 256) return launch_rec<RecBwdArgs, ligru_bwd_kernel<16, 2, 16>>(a, 16, nclusters, 1 * 64, stream);
-  if (a.H <= 384) return launch_rec<RecBwdArgs, ligru_bwd_kernel<24, 3, 16>>(a, 16, nclusters, 2 * 64, stream);
-  if (a.H <= 512) return launch_rec<RecBwdArgs, ligru_bwd_kernel<32, 4, 16>>(a, 16, nclusters, 2 * 64, stream);
-  return launch_rec<RecBwdArgs, ligru_bwd_kernel<35, 5, 16>>(a, 16, nclusters, 3 * 64, stream);
+  return pick_sync(a.sync) ? ligru_bwd_t<1>(a, cl, nclusters, stream) : ligru_bwd_t<0>(a, cl, nclusters, stream);
 }
 
 }  // namespace pk

@@ -271,11 +271,12 @@ static void test_ligru(int T, int B, int H, int ndir, int act) {
   dPT.up(c.PT); dsc.up(c.scale); dsh.up(c.shift); dU.up(c.U); dmask.up(c.mask);
   const long long ldy = (long long)ndir * H + 2;
   const long long ldy16 = ((long long)ndir * H + 7) / 8 * 8;
-  for (int pass = 0; pass < 2; ++pass) {
-    const char* cl = pass == 0 ? "8" : "16";
+  for (int pass = 0; pass < 3; ++pass) {
+    const char* cl = pass == 0 ? "8" : pass == 1 ? "16" : "8b";
+    const int vflag = pass == 0 ? PK_REC_CLUSTER8 : pass == 1 ? PK_REC_CLUSTER16 : (PK_REC_CLUSTER8 | PK_REC_SYNC_BARRIER);
     Dev<float> dHT(nch), dZT(nch), dHCT(nch), dY((size_t)T * B * ldy);
     Dev<__half> dY16((size_t)T * B * ldy16), dHT16(nch);
-    PKC(pk_rnn_layer_fwd(PK_CELL_LIGRU | (pass == 0 ? PK_REC_CLUSTER8 : PK_REC_CLUSTER16), T, B, H, ndir, act, dPT.p, c.ld, dsc.p, dsh.p, dU.p, dmask.p, 1.f, dY.p, ldy,
+    PKC(pk_rnn_layer_fwd(PK_CELL_LIGRU | vflag, T, B, H, ndir, act, dPT.p, c.ld, dsc.p, dsh.p, dU.p, dmask.p, 1.f, dY.p, ldy,
                          dY16.p, ldy16, dHT.p, dHT16.p, dZT.p, dHCT.p, c.ld, nullptr));
     CK(cudaDeviceSynchronize());
     auto gHT = dHT.down(), gZT = dZT.down(), gHCT = dHCT.down(), gY = dY.down();
@@ -303,7 +304,7 @@ static void test_ligru(int T, int B, int H, int ndir, int act) {
     Dev<__half> dGT16(GT.size());
     ddYT.up(dYT);
     dscale.up({s});
-    PKC(pk_rnn_layer_bwd(PK_CELL_LIGRU | (pass == 0 ? PK_REC_CLUSTER8 : PK_REC_CLUSTER16), T, B, H, ndir, act, ddYT.p, dHT.p, dZT.p, dHCT.p, c.ld, dU.p, dmask.p, 1.f,
+    PKC(pk_rnn_layer_bwd(PK_CELL_LIGRU | vflag, T, B, H, ndir, act, ddYT.p, dHT.p, dZT.p, dHCT.p, c.ld, dU.p, dmask.p, 1.f,
                          dscale.p, dGT.p, dGT16.p, nullptr));
     CK(cudaDeviceSynchronize());
     auto gGT = dGT.down();
@@ -518,20 +519,29 @@ static void bench_all() {
     Dev<__half> dY16((size_t)T * B * 1104), dHT16(nch), dGT16(2 * nch);
     dgs.up({1024.f});
     ddY.up(randn(nch, 1e-3f));
-    for (int cl : {8, 16}) {
-      const int flag = cl == 8 ? PK_REC_CLUSTER8 : PK_REC_CLUSTER16;
+    struct V { const char* name; int flags; };
+    const V vs[] = {{"cl8  st.async            ", PK_REC_CLUSTER8},
+                    {"cl16 st.async            ", PK_REC_CLUSTER16},
+                    {"cl8  barrier             ", PK_REC_CLUSTER8 | PK_REC_SYNC_BARRIER},
+                    {"cl16 barrier             ", PK_REC_CLUSTER16 | PK_REC_SYNC_BARRIER},
+                    {"cl8  st.async nostore    ", PK_REC_CLUSTER8 | PK_REC_DBG_NOSTORE},
+                    {"cl8  st.async noload/st  ", PK_REC_CLUSTER8 | PK_REC_DBG_NOSTORE | PK_REC_DBG_NOLOAD},
+                    {"cl16 st.async noload/st  ", PK_REC_CLUSTER16 | PK_REC_DBG_NOSTORE | PK_REC_DBG_NOLOAD},
+                    {"cl8  barrier  noload/st  ", PK_REC_CLUSTER8 | PK_REC_SYNC_BARRIER | PK_REC_DBG_NOSTORE | PK_REC_DBG_NOLOAD}};
+    for (const V& v : vs) {
+      const int flag = v.flags;
       int rc = 0;
       float ms = time_ms(3, [&] {
         rc |= pk_rnn_layer_fwd(PK_CELL_LIGRU | flag, T, B, H, ndir, PK_ACT_RELU, dPT.p, ld, dsc.p, dsh.p, dU.p, dmask.p, 1.f, dY.p, 1100,
                                dY16.p, 1104, dHT.p, dHT16.p, dZT.p, dHCT.p, ld, nullptr);
       });
-      printf("ligru_fwd cluster=%2d : %.3f ms/layer  (%.3f us/step) rc=%d %s\n", cl, ms, ms * 1000.f / T, rc,
+      printf("ligru_fwd %s: %.3f ms/layer  (%.3f us/step) rc=%d %s\n", v.name, ms, ms * 1000.f / T, rc,
              rc ? pk_last_error() : "");
       ms = time_ms(3, [&] {
         rc |= pk_rnn_layer_bwd(PK_CELL_LIGRU | flag, T, B, H, ndir, PK_ACT_RELU, ddY.p, dHT.p, dZT.p, dHCT.p, ld, dU.p, dmask.p, 1.f,
                                dgs.p, dGT.p, dGT16.p, nullptr);
       });
-      printf("ligru_bwd cluster=%2d : %.3f ms/layer  (%.3f us/step) rc=%d %s\n", cl, ms, ms * 1000.f / T, rc,
+      printf("ligru_bwd %s: %.3f ms/layer  (%.3f us/step) rc=%d %s\n", v.name, ms, ms * 1000.f / T, rc,
              rc ? pk_last_error() : "");
     }
   }

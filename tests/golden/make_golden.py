@@ -1,0 +1,237 @@
+"""Generate golden vectors from the UNMODIFIED reference (mravanelli/pytorch-kaldi).
+
+Run in the build container only (needs /root/reference; the GPU box does not have it):
+
+    python tests/golden/make_golden.py
+
+It imports /root/reference/neural_networks.py, builds the reference modules from cfg-style
+option dicts (the same strings utils.model_init hands to the constructors, utils.py:2047-2057),
+runs forward / NLLLoss / backward / one optimizer step on seeded synthetic chunks on the CPU in
+fp32, and writes small .npz fixtures next to this file.  The oracle (oracle/pk_oracle.py) and the
+CUDA path are both checked against these files.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+REF = os.environ.get("PK_REFERENCE", "/root/reference")
+sys.path.insert(0, REF)
+import neural_networks as ref_nn  # noqa: E402  (the reference's module zoo)
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class MaskRecorder:
+    """Records the CPU-generator dropout masks the reference draws inside forward()
+    (torch.bernoulli(...), neural_networks.py:1103-1105)."""
+
+    def __init__(self):
+        self.masks = []
+        self._orig = torch.bernoulli
+
+    def __enter__(self):
+        def rec(*a, **k):
+            m = self._orig(*a, **k)
+            self.masks.append(m.clone().numpy())
+            return m
+
+        torch.bernoulli = rec
+        return self
+
+    def __exit__(self, *exc):
+        torch.bernoulli = self._orig
+
+
+def ligru_opts(lay, drop, bn, act, bidir, orth=True):
+    n = len(lay)
+    return {
+        "ligru_lay": ",".join(map(str, lay)),
+        "ligru_drop": ",".join([str(drop)] * n),
+        "ligru_use_laynorm_inp": "False",
+        "ligru_use_batchnorm_inp": "False",
+        "ligru_use_laynorm": ",".join(["False"] * n),
+        "ligru_use_batchnorm": ",".join([str(bn)] * n),
+        "ligru_bidir": str(bidir),
+        "ligru_act": ",".join([act] * n),
+        "ligru_orthinit": str(orth),
+        "use_cuda": "False",
+        "to_do": "train",
+    }
+
+
+def mlp_opts(lay, drop, bn, ln, act):
+    n = len(lay)
+    as_list = lambda v: ",".join(map(str, v if isinstance(v, (list, tuple)) else [v] * n))
+    return {
+        "dnn_lay": ",".join(map(str, lay)),
+        "dnn_drop": as_list(drop),
+        "dnn_use_laynorm_inp": "False",
+        "dnn_use_batchnorm_inp": "False",
+        "dnn_use_batchnorm": as_list(bn),
+        "dnn_use_laynorm": as_list(ln),
+        "dnn_act": as_list(act),
+        "use_cuda": "False",
+        "to_do": "train",
+    }
+
+
+def sd_np(module, prefix):
+    return {prefix + k: v.detach().numpy().copy() for k, v in module.state_dict().items()}
+
+
+def grads_np(module, prefix):
+    out = {}
+    for k, p in module.named_parameters():
+        if p.grad is not None:
+            out[prefix + k] = p.grad.detach().numpy().copy()
+    return out
+
+
+def ligru_case(name, *, T, B, D, lay, S, S2, drop, bn, act, bidir, seed, head_scale=20.0, full=True):
+    torch.manual_seed(seed)
+    net = ref_nn.liGRU(ligru_opts(lay, drop, bn, act, bidir), D)
+    head = ref_nn.MLP(mlp_opts([S], 0.0, False, False, "softmax"), net.out_dim)
+    head2 = ref_nn.MLP(mlp_opts([S2], 0.0, False, False, "softmax"), net.out_dim) if S2 else None
+    with torch.no_grad():  # give the posteriors real margins
+        head.wx[0].weight.mul_(head_scale)
+        head.wx[0].bias.normal_(0, 0.1)
+        if head2 is not None:
+            head2.wx[0].weight.mul_(head_scale)
+        for i in range(len(lay)):
+            if bn:
+                net.bn_wh[i].weight.uniform_(0.5, 1.5)
+                net.bn_wh[i].bias.normal_(0, 0.2)
+                net.bn_wz[i].weight.uniform_(0.5, 1.5)
+                net.bn_wz[i].bias.normal_(0, 0.2)
+            else:
+                net.wh[i].bias.normal_(0, 0.2)
+                net.wz[i].bias.normal_(0, 0.2)
+    mods = [("ligru.", net), ("head.", head)] + ([("head2.", head2)] if head2 is not None else [])
+    out = {}
+    for pfx, m in mods:
+        out.update({"init." + k: v for k, v in sd_np(m, pfx).items()})
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(T, B, D, generator=g)
+    lab = torch.randint(0, S, (T * B,), generator=g)
+    lab2 = torch.randint(0, S2, (T * B,), generator=g) if S2 else None
+    for m in (net, head, head2):
+        if m is not None:
+            m.train()
+    opts = [torch.optim.RMSprop(m.parameters(), lr=0.0004, alpha=0.95, eps=1e-8) for _, m in mods]
+    torch.manual_seed(seed + 2)
+    with MaskRecorder() as rec:
+        h = net(x)
+    flat = h.view(T * B, -1)
+    logp = head(flat)
+    loss_cd = torch.nn.NLLLoss()(logp, lab)
+    loss = loss_cd
+    if head2 is not None:
+        logp2 = head2(flat)
+        loss_mono = torch.nn.NLLLoss()(logp2, lab2)
+        loss = loss_cd + loss_mono * 1.0  # loss_final=sum(loss_cd, mult_constant(loss_mono,1.0))
+    pred = torch.max(logp, dim=1)[1]
+    err = torch.mean((pred != lab).float())
+    h.retain_grad()
+    for o in opts:
+        o.zero_grad()
+    loss.backward()
+    out.update(x=x.numpy(), lab=lab.numpy(), out=h.detach().numpy(), logp=logp.detach().numpy(),
+               loss=np.float64(loss.item()), loss_cd=np.float64(loss_cd.item()), err=np.float64(err.item()),
+               dout=h.grad.numpy())
+    if head2 is not None:
+        out.update(lab2=lab2.numpy(), logp2=logp2.detach().numpy())
+    for i, m in enumerate(rec.masks):
+        out[f"mask{i}"] = m
+    for pfx, m in mods:
+        out.update({"grad." + k: v for k, v in grads_np(m, pfx).items()})
+        out.update({"bnstat." + k: v for k, v in sd_np(m, pfx).items() if "running" in k or "num_batches" in k})
+    for o in opts:
+        o.step()
+    for pfx, m in mods:
+        out.update({"step1." + k: v for k, v in sd_np(m, pfx).items() if "running" not in k and "num_batches" not in k})
+    # eval-mode forward (to_do=valid: test_flag True -> scalar (1-p) mask, BN running stats)
+    net.eval(); head.eval()
+    net.test_flag = True
+    with torch.no_grad():
+        out["eval_logp"] = head(net(x).view(T * B, -1)).numpy()
+    meta = dict(T=T, B=B, D=D, lay=lay, S=S, S2=S2 or 0, drop=drop, bn=bn, act=act, bidir=bidir)
+    out["meta"] = np.array(repr(meta))
+    if not full:  # keep the fixture small: drop the big square matrices' gradients down to samples
+        rng = np.random.default_rng(0)
+        for k in list(out.keys()):
+            v = out[k]
+            if isinstance(v, np.ndarray) and v.size > 200_000 and (k.startswith("grad.") or k.startswith("step1.")):
+                idx = rng.integers(0, v.size, 4096)
+                out[k + ".idx"] = idx
+                out[k + ".val"] = v.reshape(-1)[idx]
+                out[k + ".sum"] = np.float64(v.astype(np.float64).sum())
+                out[k + ".sumsq"] = np.float64((v.astype(np.float64) ** 2).sum())
+                del out[k]
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: loss={loss.item():.6f} err={err.item():.4f} -> {path} ({os.path.getsize(path)/1e6:.2f} MB)")
+
+
+def mlp_case(name, *, N, D, lay, drop, bn, ln, act, seed):
+    torch.manual_seed(seed)
+    net = ref_nn.MLP(mlp_opts(lay, drop, bn, ln, act), D)
+    with torch.no_grad():
+        net.wx[-1].weight.mul_(20.0)
+        for i in range(len(lay)):
+            net.bn[i].weight.uniform_(0.5, 1.5)
+            net.bn[i].bias.normal_(0, 0.2)
+            net.ln[i].gamma.uniform_(0.5, 1.5)
+            net.ln[i].beta.normal_(0, 0.2)
+    out = {"init." + k: v for k, v in sd_np(net, "mlp.").items()}
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(N, D, generator=g)
+    lab = torch.randint(0, lay[-1], (N,), generator=g)
+    net.train()
+    keeps = []
+    hooks = [m.register_forward_hook(lambda mod, inp, o: keeps.append(((o != 0) | (inp[0] == 0)).numpy().copy()))
+             for m in net.drop]
+    opt = torch.optim.SGD(net.parameters(), lr=0.08)
+    torch.manual_seed(seed + 2)
+    logp = net(x)
+    for h in hooks:
+        h.remove()
+    loss = torch.nn.NLLLoss()(logp, lab)
+    err = torch.mean((torch.max(logp, dim=1)[1] != lab).float())
+    opt.zero_grad()
+    loss.backward()
+    out.update(x=x.numpy(), lab=lab.numpy(), logp=logp.detach().numpy(), loss=np.float64(loss.item()),
+               err=np.float64(err.item()))
+    for i, k in enumerate(keeps):
+        out[f"keep{i}"] = k
+    out.update({"grad." + k: v for k, v in grads_np(net, "mlp.").items()})
+    out.update({"bnstat." + k: v for k, v in sd_np(net, "mlp.").items() if "running" in k or "num_batches" in k})
+    opt.step()
+    out.update({"step1." + k: v for k, v in sd_np(net, "mlp.").items() if "running" not in k and "num_batches" not in k})
+    meta = dict(N=N, D=D, lay=lay, drop=drop, bn=bn, ln=ln, act=act)
+    out["meta"] = np.array(repr(meta))
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: loss={loss.item():.6f} err={err.item():.4f} -> {path} ({os.path.getsize(path)/1e6:.2f} MB)")
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(4)
+    # A: the headline recipe in miniature (2 heads like cfg/TIMIT_baselines/TIMIT_liGRU_fmllr.cfg)
+    ligru_case("ligru_small", T=12, B=4, D=10, lay=[24, 24], S=30, S2=7, drop=0.2, bn=True, act="relu", bidir=True,
+               seed=11)
+    # B: no BatchNorm (biases), tanh, unidirectional, odd sizes
+    ligru_case("ligru_uni_tanh_nobn", T=9, B=3, D=7, lay=[20], S=13, S2=0, drop=0.3, bn=False, act="tanh",
+               bidir=False, seed=12)
+    # C: ragged sizes that do not divide any tile: B not multiple of 8, H not multiple of 8
+    ligru_case("ligru_ragged", T=17, B=5, D=13, lay=[37, 29, 37], S=41, S2=0, drop=0.2, bn=True, act="leaky_relu",
+               bidir=True, seed=13)
+    # D: the real hidden size of config 2 (one layer, short chunk) — sampled gradients only
+    ligru_case("ligru_h550", T=10, B=8, D=40, lay=[550], S=100, S2=0, drop=0.2, bn=True, act="relu", bidir=True,
+               seed=14, full=False)
+    # E: config-1 family: MLP with BatchNorm + ReLU + dropout + softmax output
+    mlp_case("mlp_bn_relu", N=64, D=23, lay=[48, 48, 19], drop=[0.15, 0.15, 0.0], bn=[True, True, False],
+             ln=[False, False, False], act=["relu", "relu", "softmax"], seed=21)
+    mlp_case("mlp_ln_tanh", N=33, D=11, lay=[20, 16, 9], drop=[0.0, 0.1, 0.0], bn=[False, True, False],
+             ln=[True, True, False], act=["tanh", "sigmoid", "softmax"], seed=22)
