@@ -93,7 +93,9 @@ def check_tensor(d, key, got, tol):
     got = np.asarray(got, dtype=np.float64)
     if kind == "full":
         assert got.shape == ref.shape, (key, got.shape, ref.shape)
-        e = relerr(got, ref)
+        # floor: gradients that are mathematically zero (a bias in front of BatchNorm) are
+        # pure rounding noise in the fp32 reference
+        e = relerr(got, ref, floor=1e-5)
         assert e <= tol, f"{key}: rel err {e:.3e} > {tol}"
     else:
         idx, val, s, ss = ref

@@ -1,0 +1,130 @@
+"""Pin the oracle (oracle/pk_oracle.py) against the golden vectors produced by the unmodified
+reference (tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+import golden_util as gu
+import pk_oracle as orc
+
+LIGRU_CASES = ["ligru_small", "ligru_uni_tanh_nobn", "ligru_ragged", "ligru_h550"]
+MLP_CASES = ["mlp_bn_relu", "mlp_ln_tanh"]
+TOL = 2e-4  # oracle runs in float64, the reference in float32
+
+
+def run_ligru(name, dtype=np.float64):
+    d = gu.load(name)
+    m = d["meta"]
+    layers = gu.ligru_layers(d, dtype)
+    heads = [gu.head_layer(d, "head", dtype)]
+    labels = [d["lab"].astype(np.int64)]
+    if m["S2"]:
+        heads.append(gu.head_layer(d, "head2", dtype))
+        labels.append(d["lab2"].astype(np.int64))
+    res = orc.ligru_model_step(d["x"].astype(dtype), labels, layers, heads, masks=gu.masks(d), bidir=m["bidir"])
+    return d, layers, heads, res
+
+
+@pytest.mark.parametrize("name", LIGRU_CASES)
+def test_ligru_forward_loss_err(name):
+    d, layers, heads, res = run_ligru(name)
+    assert gu.relerr(res["out"], d["out"]) < TOL
+    assert gu.relerr(res["logp"][0], d["logp"]) < TOL
+    assert abs(res["loss"] - float(d["loss"])) / abs(float(d["loss"])) < 1e-5
+    assert abs(res["losses"][0] - float(d["loss_cd"])) / abs(float(d["loss_cd"])) < 1e-5
+    # integer path: argmax -> != -> mean is exact given the log-posteriors
+    assert res["err"] == pytest.approx(float(d["err"]), abs=1e-7)
+    if d["meta"]["S2"]:
+        assert gu.relerr(res["logp"][1], d["logp2"]) < TOL
+
+
+@pytest.mark.parametrize("name", LIGRU_CASES)
+def test_ligru_gradients(name):
+    d, layers, heads, res = run_ligru(name)
+    m = d["meta"]
+    for i, g in enumerate(res["ligru_grads"]):
+        for k in ("wh", "wz", "uh", "uz"):
+            gu.check_tensor(d, f"grad.ligru.{k}.{i}.weight", g[k], 5e-4)
+        if m["bn"]:
+            for gate in ("wh", "wz"):
+                gu.check_tensor(d, f"grad.ligru.bn_{gate}.{i}.weight", g[f"bn_{gate}_weight"], 5e-4)
+                gu.check_tensor(d, f"grad.ligru.bn_{gate}.{i}.bias", g[f"bn_{gate}_bias"], 5e-4)
+        else:
+            gu.check_tensor(d, f"grad.ligru.wh.{i}.bias", g["bh"], 5e-4)
+            gu.check_tensor(d, f"grad.ligru.wz.{i}.bias", g["bz"], 5e-4)
+    gu.check_tensor(d, "grad.head.wx.0.weight", res["head_grads"][0]["w"], 5e-4)
+    gu.check_tensor(d, "grad.head.wx.0.bias", res["head_grads"][0]["b"], 5e-4)
+
+
+@pytest.mark.parametrize("name", ["ligru_small", "ligru_ragged"])
+def test_ligru_bn_running_stats_and_rmsprop(name):
+    d, layers, heads, res = run_ligru(name)
+    for i, L in enumerate(layers):
+        for gate in ("wh", "wz"):
+            bn = L[f"bn_{gate}"]
+            assert gu.relerr(bn["running_mean"], d[f"bnstat.ligru.bn_{gate}.{i}.running_mean"]) < TOL
+            assert gu.relerr(bn["running_var"], d[f"bnstat.ligru.bn_{gate}.{i}.running_var"]) < TOL
+            assert bn["num_batches_tracked"] == int(d[f"bnstat.ligru.bn_{gate}.{i}.num_batches_tracked"])
+    # first RMSprop step (v0 = 0): p1 = p0 - lr * g / (sqrt((1-alpha) g^2) + eps)
+    for i, g in enumerate(res["ligru_grads"]):
+        for k in ("wh", "uh"):
+            p0 = d[f"init.ligru.{k}.{i}.weight"].astype(np.float64)
+            p1, _ = orc.rmsprop_step(p0, g[k], np.zeros_like(p0), lr=0.0004, alpha=0.95, eps=1e-8)
+            # the sign-like first step amplifies tiny gradient differences where |g| ~ eps; compare
+            # only where the reference gradient is clearly non-zero
+            gref = d[f"grad.ligru.{k}.{i}.weight"]
+            sel = np.abs(gref) > 1e-6 * np.abs(gref).max()
+            ref = d[f"step1.ligru.{k}.{i}.weight"]
+            assert np.max(np.abs(p1[sel] - ref[sel])) < 1e-6
+
+
+def test_ligru_eval_mode():
+    d = gu.load("ligru_small")
+    m = d["meta"]
+    # eval uses the running stats AFTER the training step recorded in the fixture
+    layers = gu.ligru_layers(d)
+    for i, L in enumerate(layers):
+        for gate in ("wh", "wz"):
+            L[f"bn_{gate}"]["running_mean"] = d[f"bnstat.ligru.bn_{gate}.{i}.running_mean"].astype(np.float64)
+            L[f"bn_{gate}"]["running_var"] = d[f"bnstat.ligru.bn_{gate}.{i}.running_var"].astype(np.float64)
+    stage = "step1."
+    for i, L in enumerate(layers):
+        for k in ("wh", "wz", "uh", "uz"):
+            L[k] = d[f"{stage}ligru.{k}.{i}.weight"].astype(np.float64)
+        for gate in ("wh", "wz"):
+            L[f"bn_{gate}"]["weight"] = d[f"{stage}ligru.bn_{gate}.{i}.weight"].astype(np.float64)
+            L[f"bn_{gate}"]["bias"] = d[f"{stage}ligru.bn_{gate}.{i}.bias"].astype(np.float64)
+    head = gu.head_layer(d, "head", stage=stage)
+    out, _ = orc.ligru_forward(d["x"].astype(np.float64), layers, bidir=m["bidir"], training=False, masks=None)
+    T, B, F = out.shape
+    logp, _ = orc.mlp_forward(out.reshape(T * B, F), [head], training=False)
+    assert gu.relerr(logp, d["eval_logp"]) < TOL
+
+
+@pytest.mark.parametrize("name", MLP_CASES)
+def test_mlp(name):
+    d = gu.load(name)
+    m = d["meta"]
+    layers = gu.mlp_layers(d)
+    keeps = [d[f"keep{i}"] if m["drop"][i] > 0 else None for i in range(len(m["lay"]))]
+    logp, caches = orc.mlp_forward(d["x"].astype(np.float64), layers, training=True, drop_masks=keeps)
+    lab = d["lab"].astype(np.int64)
+    assert gu.relerr(logp, d["logp"]) < TOL
+    assert abs(orc.nll_loss(logp, lab) - float(d["loss"])) / float(d["loss"]) < 1e-5
+    assert orc.cost_err(logp, lab) == pytest.approx(float(d["err"]), abs=1e-7)
+    _, grads = orc.mlp_backward(orc.nll_loss_bwd(logp, lab), layers, caches)
+    for i, g in enumerate(grads):
+        gu.check_tensor(d, f"grad.mlp.wx.{i}.weight", g["w"], 5e-4)
+        if m["bn"][i] and not m["ln"][i]:
+            # a bias in front of BatchNorm has a mathematically zero gradient: rounding noise only
+            assert np.abs(g["b"]).max() < 1e-9 and np.abs(d[f"grad.mlp.wx.{i}.bias"]).max() < 1e-5
+        else:
+            gu.check_tensor(d, f"grad.mlp.wx.{i}.bias", g["b"], 5e-4)
+        if m["bn"][i]:
+            gu.check_tensor(d, f"grad.mlp.bn.{i}.weight", g["bn_weight"], 5e-4)
+            gu.check_tensor(d, f"grad.mlp.bn.{i}.bias", g["bn_bias"], 5e-4)
+        if m["ln"][i]:
+            gu.check_tensor(d, f"grad.mlp.ln.{i}.gamma", g["ln_gamma"], 5e-4)
+            gu.check_tensor(d, f"grad.mlp.ln.{i}.beta", g["ln_beta"], 5e-4)
+    # SGD step (utils.py:2129-2137, lr 0.08)
+    p1 = orc.sgd_step(d["init.mlp.wx.0.weight"].astype(np.float64), grads[0]["w"], lr=0.08)
+    assert gu.relerr(p1, d["step1.mlp.wx.0.weight"]) < 1e-5
