@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PK_ABI_VERSION 1
+#define PK_ABI_VERSION 2
 
 /* operand types for pk_gemm_tn */
 #define PK_F16 0
@@ -47,32 +47,35 @@ extern "C" {
 #define PK_CELL_GRU 2
 #define PK_CELL_MGRU 3
 #define PK_CELL_LSTM 4
+#define PK_CELL_MASK 0xff
 /* optional tuning flags OR-ed into `cell`: CTAs per cluster of the persistent kernel
  * (default: chosen from H) */
-#define PK_REC_CLUSTER8 0x800
-#define PK_REC_CLUSTER16 0x1000
+#define PK_REC_CLUSTER(n) ((n) << 8) /* n in {8, 9, 10, 12, 16}; bits 8..12 */
+#define PK_REC_CLUSTER8 PK_REC_CLUSTER(8)
+#define PK_REC_CLUSTER16 PK_REC_CLUSTER(16)
 /* step synchronisation: default = st.async + mbarrier; this flag selects the
  * barrier.cluster variant (kept for A/B timing) */
 #define PK_REC_SYNC_BARRIER 0x2000
 /* timing experiments only (results are incomplete): skip the global stores / loads */
 #define PK_REC_DBG_NOSTORE 0x10000
 #define PK_REC_DBG_NOLOAD 0x20000
-#define PK_CELL_MASK 0xff
 
 const char* pk_last_error(void);
 int pk_version(void);
 
-/* C[M][ldc] (fp32) = alpha * (*alpha_dev) * A[M][lda] . B[N][ldb]^T  (+ bias) ; both operands
- * K-major.  tcgen05 / TMEM / TMA kernel.  bias_mode 1: bias[n], 2: bias[m].  rowstats: optional
- * [2][M] doubles accumulating per-row sum and sum of squares of the OUTPUT (BatchNorm batch
- * statistics of a channel-major projection).  accumulate: C += ...; split_k > 1 partitions K
- * over gridDim.z with fp32 atomics.
+/* C[M][ldc] (fp32) = alpha * (*alpha_dev) * A[M][a_k0 : a_k0+K] . B[N][b_k0 : b_k0+K]^T (+ bias);
+ * both operands K-major ([rows][ld]).  tcgen05 / TMEM / TMA kernel.
+ *   bias_mode 1: bias[n], 2: bias[m];  rowstats: optional [2][M] doubles accumulating per-row
+ *   sum and sum of squares of the OUTPUT (BatchNorm batch statistics of a channel-major
+ *   projection);  accumulate: C += ...;  split_k > 1 partitions K over gridDim.z with fp32
+ *   atomics;  a_kext / b_kext: valid extent of each operand's K axis (0 -> k0 + K), reads past
+ *   it return zeros (this is how the time-shifted product sum_t G_t^T h_{t-1} is expressed).
  * Replaces: nn.Linear forward/backward GEMMs (neural_networks.py:1114-1115, :432-435,
  * :609-611, :138-148 and their autograd transposes). */
-int pk_gemm_tn(int dtype, int M, int N, int K, const void* A, int64_t lda, const void* B,
-               int64_t ldb, float* C, int64_t ldc, const float* bias, int bias_mode,
-               double* rowstats, float alpha, const float* alpha_dev, int accumulate, int split_k,
-               void* stream);
+int pk_gemm_tn(int dtype, int M, int N, int K, const void* A, int64_t lda, int64_t a_k0,
+               int64_t a_kext, const void* B, int64_t ldb, int64_t b_k0, int64_t b_kext, float* C,
+               int64_t ldc, const float* bias, int bias_mode, double* rowstats, float alpha,
+               const float* alpha_dev, int accumulate, int split_k, void* stream);
 
 /* outT[c][r] = in[r][c] (fp32, optional) plus optional fp16 copies scaled by *scale_dev:
  * outT16 (channel-major) and in16 (row-major).  Replaces flip/cat/view shuffles
@@ -83,8 +86,8 @@ int pk_transpose_f32(const float* in, int64_t ldi, int R, int C, float* outT, in
 int pk_convert_f16(const float* in, int64_t ldi, int R, int C, void* out, int64_t ldo,
                    const float* scale_dev, void* stream);
 
-/* *scale_out = 2^k with amax(x) * 2^k in [2^(target_log2-1), 2^target_log2): the loss scale
- * that keeps fp16 gradient operands in range.  amax_scratch: 1 float. */
+/* scale_out[0] = 2^k with amax(x) * 2^k in [2^(target_log2-1), 2^target_log2): the loss scale
+ * that keeps fp16 gradient operands in range; scale_out[1] = 2^-k.  amax_scratch: 1 float. */
 int pk_amax_scale(const float* x, int64_t ld, int R, int C, float target_log2,
                   float* amax_scratch, float* scale_out, void* stream);
 
@@ -142,13 +145,14 @@ int pk_rnn_layer_bwd(int cell, int T, int B, int H, int ndir, int act, const flo
 int pk_logsoftmax_nll(int N, int S, float* logits, int64_t ld, const int64_t* labels,
                       double* acc, void* stream);
 
-/* Gradient w.r.t. the logits as scaled fp16 GEMM operands (row-major d16, channel-major dT16)
- * and dbias [S].  Fused-NLL mode (dlogp NULL): (exp(logp) - onehot(lab)) * gcoef.  General mode:
- * dlogp - exp(logp) * rowsum(dlogp) (rowsum_scratch: N floats). */
+/* Gradient w.r.t. the logits as fp16 GEMM operands scaled by out_scale * (*scale_dev)
+ * (row-major d16, channel-major dT16) and dbias [S] (unscaled).  Fused-NLL mode (dlogp NULL):
+ * (exp(logp) - onehot(lab)) * gcoef.  General mode: dlogp - exp(logp) * rowsum(dlogp)
+ * (rowsum_scratch: N floats). */
 int pk_logsoftmax_bwd(int N, int S, const float* logp, int64_t ld, const int64_t* labels,
-                      const float* dlogp, int64_t lddl, float gcoef, float out_scale, void* d16,
-                      int64_t ld16, void* dT16, int64_t ld16t, float* dbias,
-                      float* rowsum_scratch, void* stream);
+                      const float* dlogp, int64_t lddl, float gcoef, float out_scale,
+                      const float* scale_dev, void* d16, int64_t ld16, void* dT16, int64_t ld16t,
+                      float* dbias, float* rowsum_scratch, void* stream);
 
 /* torch.optim.RMSprop (momentum 0, not centered) / SGD steps over a flat buffer
  * (utils.py:2121-2162, core.py:640-642); gscale multiplies the gradient (1/world_size). */

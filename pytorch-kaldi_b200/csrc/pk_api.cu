@@ -21,18 +21,34 @@ void set_last_error(const char* fmt, ...) {
 
 using namespace pk;
 
+namespace {
+struct RecFlags {
+  int cell, cluster, sync, dbg;
+};
+RecFlags parse_cell(int cell) {
+  RecFlags f;
+  f.cluster = (cell >> 8) & 0x1f;  // PK_REC_CLUSTER(n)
+  f.sync = (cell & PK_REC_SYNC_BARRIER) ? 0 : -1;
+  f.dbg = ((cell & PK_REC_DBG_NOSTORE) ? 1 : 0) | ((cell & PK_REC_DBG_NOLOAD) ? 2 : 0);
+  f.cell = cell & PK_CELL_MASK;
+  return f;
+}
+}  // namespace
+
 extern "C" {
 
 const char* pk_last_error(void) { return pk::g_err; }
 int pk_version(void) { return PK_ABI_VERSION; }
 
-int pk_gemm_tn(int dtype, int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb,
-               float* C, int64_t ldc, const float* bias, int bias_mode, double* rowstats, float alpha,
-               const float* alpha_dev, int accumulate, int split_k, void* stream) {
+int pk_gemm_tn(int dtype, int M, int N, int K, const void* A, int64_t lda, int64_t a_k0, int64_t a_kext,
+               const void* B, int64_t ldb, int64_t b_k0, int64_t b_kext, float* C, int64_t ldc,
+               const float* bias, int bias_mode, double* rowstats, float alpha, const float* alpha_dev,
+               int accumulate, int split_k, void* stream) {
   PK_REQUIRE(A && B && C, "pk_gemm_tn: null operand");
   GemmArgs a;
   a.dtype = dtype; a.M = M; a.N = N; a.K = K;
   a.A = A; a.lda = lda; a.B = B; a.ldb = ldb; a.C = C; a.ldc = ldc;
+  a.a_k0 = a_k0; a.a_kext = a_kext; a.b_k0 = b_k0; a.b_kext = b_kext;
   a.bias = bias; a.bias_mode = bias_mode; a.rowstats = rowstats;
   a.alpha = alpha; a.alpha_dev = alpha_dev; a.accumulate = accumulate; a.split_k = split_k;
   return gemm_tn(a, static_cast<cudaStream_t>(stream));
@@ -94,11 +110,8 @@ int pk_rnn_layer_fwd(int cell, int T, int B, int H, int ndir, int act, const flo
                      const float* scale, const float* shift, const float* U, const float* mask,
                      float mask_scalar, float* Y32, int64_t ldy32, void* Y16, int64_t ldy16, float* HT,
                      void* HT16, float* ZT, float* HCT, int64_t ldt, void* stream) {
-  const int cluster = (cell & PK_REC_CLUSTER16) ? 16 : (cell & PK_REC_CLUSTER8) ? 8 : 0;
-  const int sync = (cell & PK_REC_SYNC_BARRIER) ? 0 : -1;
-  const int dbg = ((cell & PK_REC_DBG_NOSTORE) ? 1 : 0) | ((cell & PK_REC_DBG_NOLOAD) ? 2 : 0);
-  cell &= PK_CELL_MASK;
-  PK_REQUIRE(cell == PK_CELL_LIGRU, "pk_rnn_layer_fwd: cell kind %d not implemented", cell);
+  const RecFlags f = parse_cell(cell);
+  PK_REQUIRE(f.cell == PK_CELL_LIGRU, "pk_rnn_layer_fwd: cell kind %d not implemented", f.cell);
   PK_REQUIRE(PT && scale && shift && U, "pk_rnn_layer_fwd: null input");
   PK_REQUIRE(act >= PK_ACT_RELU && act <= PK_ACT_LINEAR, "pk_rnn_layer_fwd: bad activation %d", act);
   RecFwdArgs a;
@@ -106,28 +119,21 @@ int pk_rnn_layer_fwd(int cell, int T, int B, int H, int ndir, int act, const flo
   a.PT = PT; a.ldp = ldp; a.scale = scale; a.shift = shift; a.U = U; a.mask = mask; a.mask_scalar = mask_scalar;
   a.Y32 = Y32; a.ldy32 = ldy32; a.Y16 = static_cast<__half*>(Y16); a.ldy16 = ldy16;
   a.HT = HT; a.HT16 = static_cast<__half*>(HT16); a.ZT = ZT; a.HCT = HCT; a.ldt = ldt;
-  a.cluster = cluster;
-  a.sync = sync;
-  a.dbg = dbg;
+  a.cluster = f.cluster; a.sync = f.sync; a.dbg = f.dbg;
   return ligru_fwd(a, static_cast<cudaStream_t>(stream));
 }
 
 int pk_rnn_layer_bwd(int cell, int T, int B, int H, int ndir, int act, const float* dYT, const float* HT,
                      const float* ZT, const float* HCT, int64_t ldt, const float* U, const float* mask,
                      float mask_scalar, const float* gscale, float* GT, void* GT16, void* stream) {
-  const int cluster = (cell & PK_REC_CLUSTER16) ? 16 : (cell & PK_REC_CLUSTER8) ? 8 : 0;
-  const int sync = (cell & PK_REC_SYNC_BARRIER) ? 0 : -1;
-  const int dbg = ((cell & PK_REC_DBG_NOSTORE) ? 1 : 0) | ((cell & PK_REC_DBG_NOLOAD) ? 2 : 0);
-  cell &= PK_CELL_MASK;
-  PK_REQUIRE(cell == PK_CELL_LIGRU, "pk_rnn_layer_bwd: cell kind %d not implemented", cell);
+  const RecFlags f = parse_cell(cell);
+  PK_REQUIRE(f.cell == PK_CELL_LIGRU, "pk_rnn_layer_bwd: cell kind %d not implemented", f.cell);
   PK_REQUIRE(dYT && HT && ZT && HCT && U && GT, "pk_rnn_layer_bwd: null input");
   RecBwdArgs a;
   a.T = T; a.B = B; a.H = H; a.ndir = ndir; a.act = act;
   a.dYT = dYT; a.HT = HT; a.ZT = ZT; a.HCT = HCT; a.ldt = ldt; a.U = U; a.mask = mask;
   a.mask_scalar = mask_scalar; a.gscale = gscale; a.GT = GT; a.GT16 = static_cast<__half*>(GT16);
-  a.cluster = cluster;
-  a.sync = sync;
-  a.dbg = dbg;
+  a.cluster = f.cluster; a.sync = f.sync; a.dbg = f.dbg;
   return ligru_bwd(a, static_cast<cudaStream_t>(stream));
 }
 
@@ -141,12 +147,13 @@ int pk_logsoftmax_nll(int N, int S, float* logits, int64_t ld, const int64_t* la
 }
 
 int pk_logsoftmax_bwd(int N, int S, const float* logp, int64_t ld, const int64_t* labels, const float* dlogp,
-                      int64_t lddl, float gcoef, float out_scale, void* d16, int64_t ld16, void* dT16,
-                      int64_t ld16t, float* dbias, float* rowsum_scratch, void* stream) {
+                      int64_t lddl, float gcoef, float out_scale, const float* scale_dev, void* d16,
+                      int64_t ld16, void* dT16, int64_t ld16t, float* dbias, float* rowsum_scratch,
+                      void* stream) {
   PK_REQUIRE(logp != nullptr, "pk_logsoftmax_bwd: null logp");
   HeadBwdArgs a;
   a.N = N; a.S = S; a.logp = logp; a.ld = ld; a.labels = reinterpret_cast<const long long*>(labels);
-  a.dlogp = dlogp; a.lddl = lddl; a.gcoef = gcoef; a.out_scale = out_scale;
+  a.dlogp = dlogp; a.lddl = lddl; a.gcoef = gcoef; a.out_scale = out_scale; a.scale_dev = scale_dev;
   a.d16 = static_cast<__half*>(d16); a.ld16 = ld16; a.dT16 = static_cast<__half*>(dT16); a.ld16t = ld16t;
   a.dbias = dbias; a.rowsum_scratch = rowsum_scratch;
   return logsoftmax_bwd(a, static_cast<cudaStream_t>(stream));

@@ -110,7 +110,8 @@ __global__ void scale_from_amax_kernel(const unsigned int* amax_bits, float targ
     ex = fminf(fmaxf(ex, -100.f), 100.f);
     s = exp2f(ex);  // amax * s in [2^(target-1), 2^target)
   }
-  *scale_out = s;
+  scale_out[0] = s;
+  scale_out[1] = 1.f / s;
 }
 
 // ------------------------------------------------------------------------------------
@@ -319,14 +320,12 @@ __global__ void rowsum_kernel(const float* __restrict__ d, long long ld, int N, 
 
 __global__ void logsoftmax_bwd_kernel(const HeadBwdArgs a, const float* __restrict__ rowsum) {
   __shared__ float tile[32][33];
-  __shared__ float colsum[32];
+  const float oscale = a.out_scale * (a.scale_dev ? __ldg(a.scale_dev) : 1.f);
   const int tiles_c = (a.S + 31) / 32;
   const long long ntiles = static_cast<long long>((a.N + 31) / 32) * tiles_c;
   for (long long tidx = blockIdx.x; tidx < ntiles; tidx += gridDim.x) {
     const long long r0 = (tidx / tiles_c) * 32;
     const int c0 = static_cast<int>(tidx % tiles_c) * 32;
-    if (threadIdx.y == 0) colsum[threadIdx.x] = 0.f;
-    __syncthreads();
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
       const long long r = r0 + i;
       const int c = c0 + threadIdx.x;
@@ -338,7 +337,7 @@ __global__ void logsoftmax_bwd_kernel(const HeadBwdArgs a, const float* __restri
         } else {
           d = (p - ((a.labels[r] == c) ? 1.f : 0.f)) * a.gcoef;
         }
-        if (a.d16) a.d16[r * a.ld16 + c] = f16_sat(d * a.out_scale);
+        if (a.d16) a.d16[r * a.ld16 + c] = f16_sat(d * oscale);
       }
       tile[i][threadIdx.x] = d;
     }
@@ -347,7 +346,7 @@ __global__ void logsoftmax_bwd_kernel(const HeadBwdArgs a, const float* __restri
       const int c = c0 + i;
       const long long r = r0 + threadIdx.x;
       const float d = tile[threadIdx.x][i];
-      if (a.dT16 && c < a.S && r < a.N) a.dT16[static_cast<long long>(c) * a.ld16t + r] = f16_sat(d * a.out_scale);
+      if (a.dT16 && c < a.S && r < a.N) a.dT16[static_cast<long long>(c) * a.ld16t + r] = f16_sat(d * oscale);
       if (a.dbias) {
         const float cs = warp_sum(d);  // threadIdx.x spans the 32 rows of column c (zero padded)
         if (threadIdx.x == 0 && c < a.S) atomicAdd(a.dbias + c, cs);

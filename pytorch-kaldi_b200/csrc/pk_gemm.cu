@@ -42,6 +42,7 @@ struct GemmDev {
   int atomic;              // 1: atomicAdd into C
   int kb_per_split;
   int bk_elems;
+  int a_k0, b_k0;  // element offsets of the contraction range inside each operand's rows
 };
 
 template <int DT>  // 0 = f16 operands, 2 = tf32 (fp32 operands)
@@ -92,8 +93,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(&empty_bar[s], ph ^ 1);
         mbar_arrive_expect_tx(&full_bar[s], 2 * kTileBytes);
         const int kc = (kb_begin + i) * p.bk_elems;
-        tma_load_2d(sA + s * kTileBytes, &tmA, &full_bar[s], kc, m_blk * kBM);
-        tma_load_2d(sB + s * kTileBytes, &tmB, &full_bar[s], kc, n_blk * kBN);
+        tma_load_2d(sA + s * kTileBytes, &tmA, &full_bar[s], kc + p.a_k0, m_blk * kBM);
+        tma_load_2d(sB + s * kTileBytes, &tmB, &full_bar[s], kc + p.b_k0, n_blk * kBN);
       }
     }
   } else if (warp == 1) {
@@ -243,8 +244,13 @@ int gemm_tn(const GemmArgs& a, cudaStream_t stream) {
   PK_CHECK_CUDA(attr_err);
 
   CUtensorMap tmA, tmB;
-  if (int rc = make_operand_map(&tmA, a.A, a.dtype, a.M, a.K, a.lda)) return rc;
-  if (int rc = make_operand_map(&tmB, a.B, a.dtype, a.N, a.K, a.ldb)) return rc;
+  // the K extent of each map bounds what TMA may read; everything beyond is zero-filled, so a
+  // shifted contraction (a_k0 != b_k0) stays exact as long as one side runs out of bounds
+  PK_REQUIRE(a.a_k0 >= 0 && a.b_k0 >= 0, "gemm_tn: negative k offset");
+  const long long a_ext = a.a_kext > 0 ? a.a_kext : a.a_k0 + a.K;
+  const long long b_ext = a.b_kext > 0 ? a.b_kext : a.b_k0 + a.K;
+  if (int rc = make_operand_map(&tmA, a.A, a.dtype, a.M, a_ext, a.lda)) return rc;
+  if (int rc = make_operand_map(&tmB, a.B, a.dtype, a.N, b_ext, a.ldb)) return rc;
 
   GemmDev p;
   p.M = a.M; p.N = a.N; p.K = a.K;
@@ -254,6 +260,8 @@ int gemm_tn(const GemmArgs& a, cudaStream_t stream) {
   p.alpha = a.alpha;
   p.alpha_dev = a.alpha_dev;
   p.bk_elems = (a.dtype == PK_DT_F16) ? 64 : 32;
+  p.a_k0 = static_cast<int>(a.a_k0);
+  p.b_k0 = static_cast<int>(a.b_k0);
   const int kb_total = (a.K + p.bk_elems - 1) / p.bk_elems;
   int splits = a.split_k > 0 ? a.split_k : 1;
   if (splits > kb_total) splits = kb_total;

@@ -26,11 +26,11 @@ struct GemmArgs {
   const float* alpha_dev = nullptr;
   int accumulate = 0;  // C += result
   int split_k = 1;
+  // contraction range: A[:, a_k0 : a_k0+K] . B[:, b_k0 : b_k0+K]^T; *_kext = valid extent of the
+  // operand's K axis (0 -> k0 + K); reads past it return zeros
+  long long a_k0 = 0, b_k0 = 0, a_kext = 0, b_kext = 0;
 };
 int gemm_tn(const GemmArgs& a, cudaStream_t stream);
-
-// gate families of the recurrent kernels (reference neural_networks.py classes)
-enum Cell : int { CELL_LIGRU = 0, CELL_RNN = 1, CELL_GRU = 2, CELL_MGRU = 3, CELL_LSTM = 4 };
 
 struct RecFwdArgs {
   int T = 0, B = 0, H = 0, ndir = 1, act = 0;
@@ -82,6 +82,7 @@ int transpose_f32(const float* in, long long ldi, int R, int C, float* outT, lon
                   cudaStream_t stream);
 int convert_f16(const float* in, long long ldi, int R, int C, __half* out, long long ldo,
                 const float* scale_dev, cudaStream_t stream);
+// scale_out[0] = 2^k, scale_out[1] = 2^-k
 int amax_scale(const float* x, long long ld, int R, int C, float target_log2, float* amax_scratch,
                float* scale_out, cudaStream_t stream);
 int bn_finalize(const double* stats, int C, long long n_unique, long long n_ref, const float* gamma,
@@ -102,8 +103,8 @@ struct BnBwdArgs {
   const float* rstd = nullptr;   // [C]
   const float* gamma = nullptr;  // [C]
   const float* gscale = nullptr; // device loss scale applied to the fp16 outputs
-  float* dgamma = nullptr;       // [C]  (or dbias when !use_bn, written to dbeta)
-  float* dbeta = nullptr;        // [C]
+  float* dgamma = nullptr;       // [C]
+  float* dbeta = nullptr;        // [C]  (= bias gradient when !use_bn)
   __half* dPT16 = nullptr;       // [C][ld16t]    channel-major, scaled
   long long ld16t = 0;
   __half* dP16 = nullptr;        // [n][ld16r]    row-major, scaled
@@ -129,6 +130,7 @@ struct HeadBwdArgs {
   long long lddl = 0;
   float gcoef = 1.f;                  // upstream grad / N for fused mode
   float out_scale = 1.f;              // fp16 loss scale (host value, power of two)
+  const float* scale_dev = nullptr;   // optional extra device-side scale factor
   __half* d16 = nullptr;              // [N][ld16] row-major scaled
   long long ld16 = 0;
   __half* dT16 = nullptr;             // [S][ld16t] channel-major scaled

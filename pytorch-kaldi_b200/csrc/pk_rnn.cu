@@ -3,7 +3,7 @@
 // The reference runs `for k in range(T)` in Python with ~11 launches per step
 // (neural_networks.py:1130-1141).  Here one launch covers the whole sequence:
 //
-//   * a thread-block CLUSTER of 8 (or 16) CTAs owns 8 rows of the direction-stacked batch; the
+//   * a thread-block CLUSTER of CL CTAs (8..16) owns 8 rows of the direction-stacked batch; the
 //     bidirectional layer is just 2B independent rows (reference :1095-1097 stacks x and
 //     flip(x) on the batch axis and shares the weights), so 2B/8 clusters run concurrently;
 //   * inside a cluster the hidden units are sliced across the CTAs; every warp keeps its
@@ -21,6 +21,9 @@
 //     (SY=0 keeps the first implementation — plain st.shared::cluster + one
 //     barrier.cluster per step — whose release fence compiles to MEMBAR.ALL.GPU and stalls on
 //     the outstanding global stores; kept for A/B measurement.)
+//   * the per-step global inputs (projections / saved activations) are prefetched one step ahead
+//     with cp.async straight into shared memory: no registers held across the MMA phase and no
+//     scoreboard stall on L2 latency;
 //   * flip / stack / cat of the reference (:1144-1150, :1962-1970) disappear into indexing:
 //     direction-1 rows read time T-1-k and write their outputs at natural time.
 //
@@ -37,18 +40,40 @@ namespace {
 
 constexpr int kRows = 8;  // batch rows per cluster (the n8 of m16n8k16)
 
+__device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int SY>
+__device__ __forceinline__ void step_wait(uint64_t* bar, uint32_t parity) {
+  // the payload is shared memory written by st.async and published by complete_tx on this very
+  // barrier: a CTA-scope acquire suffices (and avoids the CCTL.IVALL a cluster-scope acquire emits)
+  mbar_wait(bar, parity);
+}
+
 // =====================================================================================
 // forward
 // =====================================================================================
+template <int KT, int MT, int CL>
+struct FwdSmem {
+  static constexpr int HS = CL * 8 * MT + 8;  // halves per staged state row
+  __half h16[2][kRows][HS];
+  __half stage[MT][kRows][8];
+  float pre[2][MT * 32][4];  // cp.async landing zone: {ph0, ph1, pz0, pz1} per thread, double buffered
+  uint64_t mbar[2];
+};
+
 template <int KT, int MT, int CL, int SY>
 __global__ void __launch_bounds__(MT * 32, 1) ligru_fwd_kernel(const RecFwdArgs a) {
-  constexpr int HS = CL * 8 * MT + 8;  // halves per staged state row (pad keeps ldmatrix conflict-free)
-  static_assert((CL * MT) % 8 == 0, "row pitch must be 16 (mod 128) bytes");
+  using S = FwdSmem<KT, MT, CL>;
+  constexpr int HS = S::HS;
+  static_assert((CL * MT) % 2 == 0, "row pitch must be an odd multiple of 16 bytes (ldmatrix conflict-free)");
   static_assert(CL * 8 * MT >= 16 * KT, "unit slots must cover the K range");
   constexpr uint32_t kTxBytes = CL * MT * 128;  // bytes every CTA receives per step
-  __shared__ __align__(16) __half h16[2][kRows][HS];
-  __shared__ __align__(16) __half stage[MT][kRows][8];
-  __shared__ __align__(8) uint64_t mbar[2];
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  S& sm = *reinterpret_cast<S*>(smem_raw);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -88,12 +113,14 @@ __global__ void __launch_bounds__(MT * 32, 1) ligru_fwd_kernel(const RecFwdArgs 
 
   // ---- zero both state buffers (h_0 = 0, reference :1096), init barriers, then cluster-wide sync
   for (int i = threadIdx.x; i < 2 * kRows * HS / 2; i += blockDim.x)
-    reinterpret_cast<uint32_t*>(&h16[0][0][0])[i] = 0u;
+    reinterpret_cast<uint32_t*>(&sm.h16[0][0][0])[i] = 0u;
+  for (int i = threadIdx.x; i < 2 * MT * 32 * 4; i += blockDim.x) (&sm.pre[0][0][0])[i] = 0.f;
   if (SY && threadIdx.x == 0) {
-    mbar_init(&mbar[0], 1);
-    mbar_init(&mbar[1], 1);
+    mbar_init(&sm.mbar[0], 1);
+    mbar_init(&sm.mbar[1], 1);
     fence_mbar_init();
   }
+  __syncthreads();
   cluster_sync_all();
 
   // ---- per-thread row bookkeeping: this thread owns (unit u, rows 2q and 2q+1)
@@ -119,28 +146,32 @@ __global__ void __launch_bounds__(MT * 32, 1) ligru_fwd_kernel(const RecFwdArgs 
   }
   const float* Ph = a.PT + static_cast<long long>(u_ok ? u : 0) * a.ldp;
   const float* Pz = a.PT + static_cast<long long>(u_ok ? H + u : 0) * a.ldp;
+  float* mypre0 = &sm.pre[0][threadIdx.x][0];
+  float* mypre1 = &sm.pre[1][threadIdx.x][0];
 
-  float hprev[2] = {0.f, 0.f};
-  float ph[2] = {0.f, 0.f}, pz[2] = {0.f, 0.f};
+  // prefetch step 0's projections
 #pragma unroll
   for (int i = 0; i < 2; ++i)
-    if (rok[i]) {
+    if (rok[i] && do_load) {
       const long long col = static_cast<long long>(rd[i] ? T - 1 : 0) * B + rb[i];
-      ph[i] = __ldg(Ph + col);
-      pz[i] = __ldg(Pz + col);
+      cp_async_f32(mypre0 + i, Ph + col);
+      cp_async_f32(mypre0 + 2 + i, Pz + col);
     }
+  cp_async_commit();
+
+  float hprev[2] = {0.f, 0.f};
 
   // ldmatrix lane addressing: matrix (lane>>3) row (lane&7): &h16[buf][lane&7][k0 + 8*(lane>>3)]
   const uint32_t ldm_off = static_cast<uint32_t>(((lane & 7) * HS + 8 * (lane >> 3)) * 2);
   const uint32_t ldm_off2 = static_cast<uint32_t>(((lane & 7) * HS + 8 * ((lane >> 3) & 1)) * 2);
-  const uint32_t h16_base = smem_u32(&h16[0][0][0]);
+  const uint32_t h16_base = smem_u32(&sm.h16[0][0][0]);
   constexpr uint32_t kBufBytes = kRows * HS * 2;
 
   for (int k = 0; k < T; ++k) {
     const int cur = k & 1, nxt = cur ^ 1;
     if (SY) {
-      if (k > 0) mbar_wait_cluster(&mbar[cur], ((k - 1) >> 1) & 1);  // h_{k-1} has landed from all peers
-      if (threadIdx.x == 0) mbar_arrive_expect_tx(&mbar[nxt], kTxBytes);  // arm the fill of this step
+      if (k > 0) step_wait<SY>(&sm.mbar[cur], ((k - 1) >> 1) & 1);  // h_{k-1} has landed from all peers
+      if (threadIdx.x == 0) mbar_arrive_expect_tx(&sm.mbar[nxt], kTxBytes);  // arm the fill of this step
     }
     // ---------------- U * h_{k-1} on the tensor cores ----------------
     float acc[4][4];
@@ -166,72 +197,73 @@ __global__ void __launch_bounds__(MT * 32, 1) ligru_fwd_kernel(const RecFwdArgs 
     cz[1] = (acc[0][3] + acc[1][3]) + (acc[2][3] + acc[3][3]);
 
     // ---------------- gates (reference :1133-1136) ----------------
+    cp_async_wait_all();  // this step's projections (issued one step ago) are in smem
+    const float* pre = cur ? mypre1 : mypre0;
     float hn[2], zz[2], hcv[2];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      const float zt = sigmoidf_(fmaf(sc_z, pz[i], sh_z) + cz[i]);
-      const float at = fmaf(sc_h, ph[i], sh_h) + ch[i];
+      const float zt = sigmoidf_(fmaf(sc_z, pre[2 + i], sh_z) + cz[i]);
+      const float at = fmaf(sc_h, pre[i], sh_h) + ch[i];
       const float hc = act_fwd(a.act, at) * msk[i];
       float h = zt * hprev[i] + (1.f - zt) * hc;
       if (!rok[i]) h = 0.f;
       hn[i] = h; zz[i] = zt; hcv[i] = hc;
       hprev[i] = h;
-      if (SY) stage[warp][2 * q + i][g] = f16_sat(h);
-      else h16[nxt][2 * q + i][u] = f16_sat(h);
+      if (SY) sm.stage[warp][2 * q + i][g] = f16_sat(h);
+      else sm.h16[nxt][2 * q + i][u] = f16_sat(h);
     }
     __syncwarp();
     // ---------------- push the warp's 8x8 fp16 tile to the CTAs of the cluster ----------------
     {
       const int n = lane & 7;
-      const uint32_t laddr = smem_u32(&h16[nxt][n][ubase]);
+      const uint32_t laddr = smem_u32(&sm.h16[nxt][n][ubase]);
       if (SY) {
-        const uint4 val = *reinterpret_cast<const uint4*>(&stage[warp][n][0]);
-        const uint32_t lbar = smem_u32(&mbar[nxt]);
+        const uint4 val = *reinterpret_cast<const uint4*>(&sm.stage[warp][n][0]);
+        const uint32_t lbar = smem_u32(&sm.mbar[nxt]);
 #pragma unroll
-        for (int j = 0; j < CL / 4; ++j) {
-          const uint32_t dst = (lane >> 3) + 4 * j;
+        for (int dst = (lane >> 3); dst < CL; dst += 4)
           st_async_v4(mapa_shared(laddr, dst), val, mapa_shared(lbar, dst));
-        }
       } else {
-        const uint4 val = *reinterpret_cast<const uint4*>(&h16[nxt][n][ubase]);
+        const uint4 val = *reinterpret_cast<const uint4*>(&sm.h16[nxt][n][ubase]);
 #pragma unroll
-        for (int j = 0; j < CL / 4; ++j) {
-          const uint32_t dst = (lane >> 3) + 4 * j;
-          if (dst != crank) st_cluster_v4(mapa_shared(laddr, dst), val);
-        }
+        for (int dst = (lane >> 3); dst < CL; dst += 4)
+          if (dst != static_cast<int>(crank)) st_cluster_v4(mapa_shared(laddr, dst), val);
       }
     }
     if (!SY) cluster_arrive_release();
 
-    // ---------------- off the critical path: global stores + next step's projections ----------
-    float nph[2] = {0.f, 0.f}, npz[2] = {0.f, 0.f};
+    // ---------------- off the critical path: next step's projections + global stores ----------
+    {
+      float* npre = nxt ? mypre1 : mypre0;
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      if (rok[i]) {
-        const int t = rd[i] ? (T - 1 - k) : k;
-        const long long col = static_cast<long long>(t) * B + rb[i];
-        if (k + 1 < T && do_load) {
-          const long long ncol = col + (rd[i] ? -B : B);
-          nph[i] = __ldg(Ph + ncol);
-          npz[i] = __ldg(Pz + ncol);
-        }
-        if (do_store) {
-          const long long ch_idx = static_cast<long long>(rd[i] * H + u) * a.ldt + col;
-          if (a.HT) a.HT[ch_idx] = hn[i];
-          if (a.HT16) a.HT16[ch_idx] = f16_sat(hn[i]);
-          if (a.ZT) a.ZT[ch_idx] = zz[i];
-          if (a.HCT) a.HCT[ch_idx] = hcv[i];
-          if (a.Y32) a.Y32[col * a.ldy32 + rd[i] * H + u] = hn[i];
-          if (a.Y16) a.Y16[col * a.ldy16 + rd[i] * H + u] = f16_sat(hn[i]);
+      for (int i = 0; i < 2; ++i) {
+        if (rok[i]) {
+          const int t = rd[i] ? (T - 1 - k) : k;
+          const long long col = static_cast<long long>(t) * B + rb[i];
+          if (k + 1 < T && do_load) {
+            const long long ncol = col + (rd[i] ? -B : B);
+            cp_async_f32(npre + i, Ph + ncol);
+            cp_async_f32(npre + 2 + i, Pz + ncol);
+          }
+          if (do_store) {
+            const long long ch_idx = static_cast<long long>(rd[i] * H + u) * a.ldt + col;
+            if (a.HT) a.HT[ch_idx] = hn[i];
+            if (a.HT16) a.HT16[ch_idx] = f16_sat(hn[i]);
+            if (a.ZT) a.ZT[ch_idx] = zz[i];
+            if (a.HCT) a.HCT[ch_idx] = hcv[i];
+            if (a.Y32) a.Y32[col * a.ldy32 + rd[i] * H + u] = hn[i];
+            if (a.Y16) a.Y16[col * a.ldy16 + rd[i] * H + u] = f16_sat(hn[i]);
+          }
         }
       }
+      cp_async_commit();
     }
-    ph[0] = nph[0]; ph[1] = nph[1]; pz[0] = npz[0]; pz[1] = npz[1];
     if (!SY) cluster_wait_acquire();
     else __syncwarp();
   }
+  cp_async_wait_all();
   // drain the last incoming fill, then: no CTA may exit while peers can still write into it
-  if (SY) mbar_wait_cluster(&mbar[T & 1], ((T - 1) >> 1) & 1);
+  if (SY) step_wait<SY>(&sm.mbar[T & 1], ((T - 1) >> 1) & 1);
   cluster_sync_all();
 }
 
@@ -245,20 +277,30 @@ __global__ void __launch_bounds__(MT * 32, 1) ligru_fwd_kernel(const RecFwdArgs 
 // Thread ownership: warp (mt, half) keeps the 16-unit x (half-gate K range) slice of U^T in
 // registers; after the MMA the two warps of a pair exchange partial sums through smem so that
 // warp (mt,0) finishes units g and warp (mt,1) units g+8 of the tile.
+template <int KT, int MT, int CL>
+struct BwdSmem {
+  static constexpr int MT16 = (MT + 1) / 2;
+  static constexpr int NW = MT16 * 2;
+  static constexpr int KP = CL * 8 * MT;
+  static constexpr int GS = 2 * KP + 8;
+  __half g16[2][kRows][GS];
+  __half stage[NW][2][kRows][8];
+  float xbuf[2][MT16][2][32][2];  // pair exchange, double-buffered by step parity
+  float pre[2][NW * 32][8];       // cp.async landing zone: {dy0,dy1,z0,z1,hc0,hc1,hp0,hp1}
+  uint64_t mbar[2];
+};
+
 template <int KT, int MT, int CL, int SY>
 __global__ void __launch_bounds__(((MT + 1) / 2) * 64, 1) ligru_bwd_kernel(const RecBwdArgs a) {
-  constexpr int MT16 = (MT + 1) / 2;     // 16-unit tiles per CTA
-  constexpr int NW = MT16 * 2;           // warps
-  constexpr int KP = CL * 8 * MT;        // unit-slot stride between the two gates in the staged vector
-  static_assert((CL * MT) % 8 == 0, "row pitch must be 16 (mod 128) bytes");
+  using S = BwdSmem<KT, MT, CL>;
+  constexpr int KP = S::KP;   // unit-slot stride between the two gates in the staged vector
+  constexpr int GS = S::GS;   // halves per staged row
+  static_assert((2 * CL * MT) % 2 == 0, "row pitch");
   static_assert(KP >= 16 * KT, "unit slots must cover the K range");
-  constexpr int GS = 2 * KP + 8;         // halves per staged row
-  constexpr int UPC = 8 * MT;            // units owned per CTA
+  constexpr int UPC = 8 * MT;  // units owned per CTA
   constexpr uint32_t kTxBytes = CL * MT * 256;
-  __shared__ __align__(16) __half g16[2][kRows][GS];
-  __shared__ __align__(16) __half stage[NW][2][kRows][8];
-  __shared__ float xbuf[2][MT16][2][32][2];  // double-buffered by step parity
-  __shared__ __align__(8) uint64_t mbar[2];
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  S& sm = *reinterpret_cast<S*>(smem_raw);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -305,12 +347,14 @@ __global__ void __launch_bounds__(((MT + 1) / 2) * 64, 1) ligru_bwd_kernel(const
   }
 
   for (int i = threadIdx.x; i < 2 * kRows * GS / 2; i += blockDim.x)
-    reinterpret_cast<uint32_t*>(&g16[0][0][0])[i] = 0u;
+    reinterpret_cast<uint32_t*>(&sm.g16[0][0][0])[i] = 0u;
+  for (int i = threadIdx.x; i < 2 * S::NW * 32 * 8; i += blockDim.x) (&sm.pre[0][0][0])[i] = 0.f;
   if (SY && threadIdx.x == 0) {
-    mbar_init(&mbar[0], 1);
-    mbar_init(&mbar[1], 1);
+    mbar_init(&sm.mbar[0], 1);
+    mbar_init(&sm.mbar[1], 1);
     fence_mbar_init();
   }
+  __syncthreads();
   cluster_sync_all();
 
   // ---- element ownership of this thread: unit = tile unit (8*half + g), rows 2q, 2q+1
@@ -336,84 +380,87 @@ __global__ void __launch_bounds__(((MT + 1) / 2) * 64, 1) ligru_bwd_kernel(const
   const float inv_s = 1.f / s;
 
   float carry[2] = {0.f, 0.f};
-  // prefetched operands of the step
-  float dy[2] = {0.f, 0.f}, zz[2] = {0.f, 0.f}, hc[2] = {0.f, 0.f}, hp[2] = {0.f, 0.f};
-  auto load_step = [&](int k, float (&ody)[2], float (&oz)[2], float (&ohc)[2], float (&ohp)[2]) {
+  float* mypre0 = &sm.pre[0][threadIdx.x][0];
+  float* mypre1 = &sm.pre[1][threadIdx.x][0];
+  // prefetch of step k's operands into pre[k & 1]
+  auto prefetch_step = [&](int k) {
+    float* dst = (k & 1) ? mypre1 : mypre0;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      ody[i] = oz[i] = ohc[i] = ohp[i] = 0.f;
-      if (rok[i]) {
+      if (rok[i] && do_load) {
         const int t = rd[i] ? (T - 1 - k) : k;
         const long long col = static_cast<long long>(t) * B + rb[i];
         const long long idx = static_cast<long long>(rd[i] * H + u) * a.ldt + col;
-        ody[i] = __ldg(a.dYT + idx);
-        oz[i] = __ldg(a.ZT + idx);
-        ohc[i] = __ldg(a.HCT + idx);
-        if (k > 0) ohp[i] = __ldg(a.HT + idx + (rd[i] ? B : -B));
+        cp_async_f32(dst + i, a.dYT + idx);
+        cp_async_f32(dst + 2 + i, a.ZT + idx);
+        cp_async_f32(dst + 4 + i, a.HCT + idx);
+        if (k > 0) cp_async_f32(dst + 6 + i, a.HT + idx + (rd[i] ? B : -B));
       }
     }
+    cp_async_commit();
   };
-  load_step(T - 1, dy, zz, hc, hp);
+  prefetch_step(T - 1);
 
   const uint32_t ldm_off = static_cast<uint32_t>(((lane & 7) * GS + 8 * (lane >> 3)) * 2);
   const uint32_t ldm_off2 = static_cast<uint32_t>(((lane & 7) * GS + 8 * ((lane >> 3) & 1)) * 2);
-  const uint32_t g16_base = smem_u32(&g16[0][0][0]);
+  const uint32_t g16_base = smem_u32(&sm.g16[0][0][0]);
   constexpr uint32_t kBufBytes = kRows * GS * 2;
   const long long gate_stride = static_cast<long long>(H) * a.ldt;         // da -> dpz rows
   const long long dir_stride = 2 * gate_stride;                            // direction blocks of GT
 
   for (int k = T - 1; k >= 0; --k) {
     const int buf = k & 1;
-    if (SY && threadIdx.x == 0) mbar_arrive_expect_tx(&mbar[buf], kTxBytes);
+    if (SY && threadIdx.x == 0) mbar_arrive_expect_tx(&sm.mbar[buf], kTxBytes);
     // ---------------- phase A: pointwise backward of step k ----------------
+    cp_async_wait_all();
+    const float* pre = buf ? mypre1 : mypre0;
     float da[2], dpz[2], keep[2];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      const float dh = dy[i] + carry[i];
-      const float dzv = dh * (hp[i] - hc[i]);
-      const float dhc = dh * (1.f - zz[i]);
+      const float zz = pre[2 + i], hc = pre[4 + i];
+      const float hp = (k > 0) ? pre[6 + i] : 0.f;
+      const float dh = pre[i] + carry[i];
+      const float dzv = dh * (hp - hc);
+      const float dhc = dh * (1.f - zz);
       const float m = msk[i];
-      const float y = (m != 0.f) ? hc[i] / m : 0.f;
+      const float y = (m != 0.f) ? hc / m : 0.f;
       float dav = dhc * m * act_bwd_from_out(a.act, y);
-      float dpzv = dzv * zz[i] * (1.f - zz[i]);
+      float dpzv = dzv * zz * (1.f - zz);
       if (!rok[i]) { dav = 0.f; dpzv = 0.f; }
       da[i] = dav; dpz[i] = dpzv;
-      keep[i] = dh * zz[i];
+      keep[i] = dh * zz;
       if (warp_ok) {
         if (SY) {
-          stage[warp][0][2 * q + i][g] = f16_sat(dav * s);
-          stage[warp][1][2 * q + i][g] = f16_sat(dpzv * s);
+          sm.stage[warp][0][2 * q + i][g] = f16_sat(dav * s);
+          sm.stage[warp][1][2 * q + i][g] = f16_sat(dpzv * s);
         } else {
-          g16[buf][2 * q + i][slot + cta_ubase] = f16_sat(dav * s);
-          g16[buf][2 * q + i][KP + slot + cta_ubase] = f16_sat(dpzv * s);
+          sm.g16[buf][2 * q + i][slot + cta_ubase] = f16_sat(dav * s);
+          sm.g16[buf][2 * q + i][KP + slot + cta_ubase] = f16_sat(dpzv * s);
         }
       }
     }
     __syncwarp();
     if (warp_ok) {
-      // 16 chunks (8 rows x 2 gates) of 16 bytes, each to every peer: lane -> chunk (lane&15), peer half (lane>>4)
+      // 16 chunks (8 rows x 2 gates) of 16 bytes, each to every peer: lane -> chunk (lane&15), peer parity (lane>>4)
       const int n = lane & 7;
       const int gate = (lane >> 3) & 1;
-      const uint32_t laddr = smem_u32(&g16[buf][n][gate * KP + cta_ubase + wslot0]);
+      const uint32_t laddr = smem_u32(&sm.g16[buf][n][gate * KP + cta_ubase + wslot0]);
       if (SY) {
-        const uint4 val = *reinterpret_cast<const uint4*>(&stage[warp][gate][n][0]);
-        const uint32_t lbar = smem_u32(&mbar[buf]);
+        const uint4 val = *reinterpret_cast<const uint4*>(&sm.stage[warp][gate][n][0]);
+        const uint32_t lbar = smem_u32(&sm.mbar[buf]);
 #pragma unroll
-        for (int j = 0; j < CL / 2; ++j) {
-          const uint32_t dst = (lane >> 4) * (CL / 2) + j;
+        for (int dst = (lane >> 4); dst < CL; dst += 2)
           st_async_v4(mapa_shared(laddr, dst), val, mapa_shared(lbar, dst));
-        }
       } else {
-        const uint4 val = *reinterpret_cast<const uint4*>(&g16[buf][n][gate * KP + cta_ubase + wslot0]);
+        const uint4 val = *reinterpret_cast<const uint4*>(&sm.g16[buf][n][gate * KP + cta_ubase + wslot0]);
 #pragma unroll
-        for (int j = 0; j < CL / 2; ++j) {
-          const uint32_t dst = (lane >> 4) * (CL / 2) + j;
-          if (dst != crank) st_cluster_v4(mapa_shared(laddr, dst), val);
-        }
+        for (int dst = (lane >> 4); dst < CL; dst += 2)
+          if (dst != static_cast<int>(crank)) st_cluster_v4(mapa_shared(laddr, dst), val);
       }
     }
     if (!SY) cluster_arrive_release();
-    // global stores of this step + prefetch of step k-1 while the exchange completes
+    // prefetch of step k-1 + global stores of this step while the exchange completes
+    if (k > 0) prefetch_step(k - 1);
     if (do_store) {
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
@@ -430,9 +477,7 @@ __global__ void __launch_bounds__(((MT + 1) / 2) * 64, 1) ligru_bwd_kernel(const
         }
       }
     }
-    float ndy[2] = {0.f, 0.f}, nz[2] = {0.f, 0.f}, nhc[2] = {0.f, 0.f}, nhp[2] = {0.f, 0.f};
-    if (k > 0 && do_load) load_step(k - 1, ndy, nz, nhc, nhp);
-    if (SY) mbar_wait_cluster(&mbar[buf], ((T - 1 - k) >> 1) & 1);
+    if (SY) step_wait<SY>(&sm.mbar[buf], ((T - 1 - k) >> 1) & 1);
     else cluster_wait_acquire();
 
     // ---------------- phase B: U^T [da; dpz] for the carry into step k-1 ----------------
@@ -457,34 +502,35 @@ __global__ void __launch_bounds__(((MT + 1) / 2) * 64, 1) ligru_bwd_kernel(const
 #pragma unroll
       for (int e = 0; e < 4; ++e) c4[e] = (acc[0][e] + acc[1][e]) + (acc[2][e] + acc[3][e]);
       // warp half 0 keeps units g (c4[0..1]) and ships c4[2..3]; half 1 keeps g+8 and ships c4[0..1]
-      xbuf[buf][mt][half][lane][0] = half ? c4[0] : c4[2];
-      xbuf[buf][mt][half][lane][1] = half ? c4[1] : c4[3];
+      sm.xbuf[buf][mt][half][lane][0] = half ? c4[0] : c4[2];
+      sm.xbuf[buf][mt][half][lane][1] = half ? c4[1] : c4[3];
       asm volatile("bar.sync %0, 64;" ::"r"(mt + 1) : "memory");
-      const float o0 = xbuf[buf][mt][half ^ 1][lane][0];
-      const float o1 = xbuf[buf][mt][half ^ 1][lane][1];
+      const float o0 = sm.xbuf[buf][mt][half ^ 1][lane][0];
+      const float o1 = sm.xbuf[buf][mt][half ^ 1][lane][1];
       const float m0 = half ? c4[2] : c4[0];
       const float m1 = half ? c4[3] : c4[1];
       carry[0] = keep[0] + (m0 + o0) * inv_s;
       carry[1] = keep[1] + (m1 + o1) * inv_s;
-#pragma unroll
-      for (int i = 0; i < 2; ++i) { dy[i] = ndy[i]; zz[i] = nz[i]; hc[i] = nhc[i]; hp[i] = nhp[i]; }
     }
   }
+  cp_async_wait_all();
   cluster_sync_all();
 }
 
 template <typename Args, void (*Kern)(const Args)>
-int launch_rec(const Args& a, int cluster, int nclusters, int threads, cudaStream_t stream) {
-  if (cluster > 8) {
-    static std::once_flag once;
-    static cudaError_t err = cudaSuccess;
-    std::call_once(once, [] { err = cudaFuncSetAttribute(Kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1); });
-    PK_CHECK_CUDA(err);
-  }
+int launch_rec(const Args& a, int cluster, int nclusters, int threads, size_t smem, cudaStream_t stream) {
+  static std::once_flag once;
+  static cudaError_t err = cudaSuccess;
+  std::call_once(once, [&] {
+    err = cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (err == cudaSuccess && cluster > 8)
+      err = cudaFuncSetAttribute(Kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  });
+  PK_CHECK_CUDA(err);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(nclusters * cluster, 1, 1);
   cfg.blockDim = dim3(threads, 1, 1);
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -497,47 +543,52 @@ int launch_rec(const Args& a, int cluster, int nclusters, int threads, cudaStrea
   return 0;
 }
 
-int pick_cluster(int requested, int H) {
-  if (requested == 8 || requested == 16) return requested;
-  static int env = [] {  // tuning knob for bring-up: PK_REC_CLUSTER=8|16
-    const char* e = getenv("PK_REC_CLUSTER");
-    return e ? atoi(e) : 0;
-  }();
-  if (env == 8 || env == 16) return env;
-  (void)H;
-  return 8;
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+int pick_cluster(int requested) {
+  if (requested > 0) return requested;
+  static int env = env_int("PK_REC_CLUSTER", 0);  // tuning knob for bring-up
+  return env > 0 ? env : 8;
 }
 int pick_sync(int requested) {  // 1 = st.async + mbarrier (default), 0 = barrier.cluster
   if (requested == 0 || requested == 1) return requested;
-  static int env = [] {
-    const char* e = getenv("PK_REC_SYNC");
-    return e ? atoi(e) : 1;
-  }();
+  static int env = env_int("PK_REC_SYNC", 1);
   return env ? 1 : 0;
 }
 
-#define PK_DISPATCH_REC(KERN, ARGS, THREADS_OF_MT)                                                            \
-  if (cl == 8) {                                                                                             \
-    if (a.H <= 256) return launch_rec<ARGS, KERN<16, 4, 8, SYNC>>(a, 8, nclusters, THREADS_OF_MT(4), stream);   \
-    if (a.H <= 384) return launch_rec<ARGS, KERN<24, 6, 8, SYNC>>(a, 8, nclusters, THREADS_OF_MT(6), stream);   \
-    if (a.H <= 512) return launch_rec<ARGS, KERN<32, 8, 8, SYNC>>(a, 8, nclusters, THREADS_OF_MT(8), stream);   \
-    return launch_rec<ARGS, KERN<35, 9, 8, SYNC>>(a, 8, nclusters, THREADS_OF_MT(9), stream);                   \
-  }                                                                                                           \
-  if (a.H <= 256) return launch_rec<ARGS, KERN<16, 2, 16, SYNC>>(a, 16, nclusters, THREADS_OF_MT(2), stream);   \
-  if (a.H <= 384) return launch_rec<ARGS, KERN<24, 3, 16, SYNC>>(a, 16, nclusters, THREADS_OF_MT(3), stream);   \
-  if (a.H <= 512) return launch_rec<ARGS, KERN<32, 4, 16, SYNC>>(a, 16, nclusters, THREADS_OF_MT(4), stream);   \
-  return launch_rec<ARGS, KERN<35, 5, 16, SYNC>>(a, 16, nclusters, THREADS_OF_MT(5), stream);
+#define PK_FWD(KT, MT, CL, SY)                                                                             \
+  return launch_rec<RecFwdArgs, ligru_fwd_kernel<KT, MT, CL, SY>>(a, CL, nclusters, (MT) * 32,               \
+                                                                  sizeof(FwdSmem<KT, MT, CL>), stream)
+#define PK_BWD(KT, MT, CL, SY)                                                                             \
+  return launch_rec<RecBwdArgs, ligru_bwd_kernel<KT, MT, CL, SY>>(a, CL, nclusters, (((MT) + 1) / 2) * 64,   \
+                                                                  sizeof(BwdSmem<KT, MT, CL>), stream)
 
-#define PK_FWD_THREADS(mt) ((mt) * 32)
-#define PK_BWD_THREADS(mt) ((((mt) + 1) / 2) * 64)
+// (k-tiles, 8-unit tiles per CTA, cluster size) per hidden-size class; CL * 8 * MT >= H
+#define PK_DISPATCH(MACRO)                                                                     \
+  if (sy == 0) { /* barrier.cluster variants: cluster of 8 only */                             \
+    if (H <= 256) { MACRO(16, 4, 8, 0); }                                                      \
+    if (H <= 384) { MACRO(24, 6, 8, 0); }                                                      \
+    if (H <= 512) { MACRO(32, 8, 8, 0); }                                                      \
+    MACRO(35, 9, 8, 0);                                                                        \
+  }                                                                                            \
+  if (H <= 256) { MACRO(16, 4, 8, 1); }                                                        \
+  if (H <= 384) { MACRO(24, 6, 8, 1); }                                                        \
+  if (H <= 512) { MACRO(32, 8, 8, 1); }                                                        \
+  if (cl == 9) { MACRO(35, 8, 9, 1); }                                                         \
+  if (cl == 10) { MACRO(35, 7, 10, 1); }                                                       \
+  if (cl == 12) { MACRO(35, 6, 12, 1); }                                                       \
+  if (cl == 16) { MACRO(35, 5, 16, 1); }                                                       \
+  MACRO(35, 9, 8, 1);
 
-template <int SYNC>
-int ligru_fwd_t(const RecFwdArgs& a, int cl, int nclusters, cudaStream_t stream) {
-  PK_DISPATCH_REC(ligru_fwd_kernel, RecFwdArgs, PK_FWD_THREADS)
+int fwd_dispatch(const RecFwdArgs& a, int cl, int sy, int nclusters, cudaStream_t stream) {
+  const int H = a.H;
+  PK_DISPATCH(PK_FWD)
 }
-template <int SYNC>
-int ligru_bwd_t(const RecBwdArgs& a, int cl, int nclusters, cudaStream_t stream) {
-  PK_DISPATCH_REC(ligru_bwd_kernel, RecBwdArgs, PK_BWD_THREADS)
+int bwd_dispatch(const RecBwdArgs& a, int cl, int sy, int nclusters, cudaStream_t stream) {
+  const int H = a.H;
+  PK_DISPATCH(PK_BWD)
 }
 
 }  // namespace
@@ -547,8 +598,7 @@ int ligru_fwd(const RecFwdArgs& a, cudaStream_t stream) {
   PK_REQUIRE(a.ndir == 1 || a.ndir == 2, "ligru_fwd: ndir must be 1 or 2");
   PK_REQUIRE(a.H <= 560, "ligru_fwd: hidden size %d > 560 not supported by the register-resident kernel", a.H);
   const int nclusters = (a.ndir * a.B + kRows - 1) / kRows;
-  const int cl = pick_cluster(a.cluster, a.H);
-  return pick_sync(a.sync) ? ligru_fwd_t<1>(a, cl, nclusters, stream) : ligru_fwd_t<0>(a, cl, nclusters, stream);
+  return fwd_dispatch(a, pick_cluster(a.cluster), pick_sync(a.sync), nclusters, stream);
 }
 
 int ligru_bwd(const RecBwdArgs& a, cudaStream_t stream) {
@@ -556,8 +606,7 @@ int ligru_bwd(const RecBwdArgs& a, cudaStream_t stream) {
   PK_REQUIRE(a.ndir == 1 || a.ndir == 2, "ligru_bwd: ndir must be 1 or 2");
   PK_REQUIRE(a.H <= 560, "ligru_bwd: hidden size %d > 560 not supported by the register-resident kernel", a.H);
   const int nclusters = (a.ndir * a.B + kRows - 1) / kRows;
-  const int cl = pick_cluster(a.cluster, a.H);
-  return pick_sync(a.sync) ? ligru_bwd_t<1>(a, cl, nclusters, stream) : ligru_bwd_t<0>(a, cl, nclusters, stream);
+  return bwd_dispatch(a, pick_cluster(a.cluster), pick_sync(a.sync), nclusters, stream);
 }
 
 }  // namespace pk

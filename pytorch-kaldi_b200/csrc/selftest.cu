@@ -104,7 +104,7 @@ static void test_gemm(int dtype, int M, int N, int K, int bias_mode, bool stats,
     CK(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
   }
   const float alpha = 0.5f;
-  PKC(pk_gemm_tn(dtype, M, N, K, dA, lda, dB, ldb, dC.p, ldc, bias_mode ? dbias.p : nullptr, bias_mode,
+  PKC(pk_gemm_tn(dtype, M, N, K, dA, lda, 0, 0, dB, ldb, 0, 0, dC.p, ldc, bias_mode ? dbias.p : nullptr, bias_mode,
                  stats ? dstats.p : nullptr, alpha, nullptr, accumulate, splitk, nullptr));
   CK(cudaDeviceSynchronize());
   auto C = dC.down();
@@ -136,6 +136,36 @@ static void test_gemm(int dtype, int M, int N, int K, int bias_mode, bool stats,
   report(name, std::max(maxerr, maxst), 2e-4);
   cudaFree(dA);
   cudaFree(dB);
+}
+
+// C = A[:, a0:a0+K] . B[:, b0:b0+K]^T with operand extents KX (the time-shifted dU product)
+static void test_gemm_shift(int M, int N, int KX, int a0, int b0) {
+  const int K = KX - std::max(a0, b0);
+  const long long ld = (KX + 7) / 8 * 8 + 8;
+  std::vector<float> A = randn((size_t)M * ld), B = randn((size_t)N * ld);
+  for (auto& x : A) x = h2f(x);
+  for (auto& x : B) x = h2f(x);
+  std::vector<__half> hA(A.size()), hB(B.size());
+  for (size_t i = 0; i < A.size(); ++i) hA[i] = __float2half_rn(A[i]);
+  for (size_t i = 0; i < B.size(); ++i) hB[i] = __float2half_rn(B[i]);
+  Dev<__half> dA(hA.size()), dB(hB.size());
+  Dev<float> dC((size_t)M * N);
+  dA.up(hA);
+  dB.up(hB);
+  PKC(pk_gemm_tn(PK_F16, M, N, K, dA.p, ld, a0, KX, dB.p, ld, b0, KX, dC.p, N, nullptr, 0, nullptr, 1.f, nullptr, 0, 3,
+                 nullptr));
+  CK(cudaDeviceSynchronize());
+  auto C = dC.down();
+  double e = 0;
+  for (int m = 0; m < M; ++m)
+    for (int n = 0; n < N; ++n) {
+      double acc = 0;
+      for (int k = 0; k < K; ++k) acc += (double)A[(size_t)m * ld + a0 + k] * B[(size_t)n * ld + b0 + k];
+      e = std::max(e, std::fabs(acc - C[(size_t)m * N + n]) / (1.0 + std::fabs(acc)));
+    }
+  char name[128];
+  snprintf(name, sizeof(name), "gemm f16 shifted M%d N%d KX%d a0=%d b0=%d", M, N, KX, a0, b0);
+  report(name, e, 2e-4);
 }
 
 // ---------------------------------------------------------------------------------
@@ -271,9 +301,13 @@ static void test_ligru(int T, int B, int H, int ndir, int act) {
   dPT.up(c.PT); dsc.up(c.scale); dsh.up(c.shift); dU.up(c.U); dmask.up(c.mask);
   const long long ldy = (long long)ndir * H + 2;
   const long long ldy16 = ((long long)ndir * H + 7) / 8 * 8;
-  for (int pass = 0; pass < 3; ++pass) {
-    const char* cl = pass == 0 ? "8" : pass == 1 ? "16" : "8b";
-    const int vflag = pass == 0 ? PK_REC_CLUSTER8 : pass == 1 ? PK_REC_CLUSTER16 : (PK_REC_CLUSTER8 | PK_REC_SYNC_BARRIER);
+  const char* names[] = {"8", "8b", "9", "10", "12", "16"};
+  const int vflags[] = {PK_REC_CLUSTER(8), PK_REC_CLUSTER(8) | PK_REC_SYNC_BARRIER, PK_REC_CLUSTER(9), PK_REC_CLUSTER(10),
+                        PK_REC_CLUSTER(12), PK_REC_CLUSTER(16)};
+  const int npass = H > 512 ? 6 : 2;
+  for (int pass = 0; pass < npass; ++pass) {
+    const char* cl = names[pass];
+    const int vflag = vflags[pass];
     Dev<float> dHT(nch), dZT(nch), dHCT(nch), dY((size_t)T * B * ldy);
     Dev<__half> dY16((size_t)T * B * ldy16), dHT16(nch);
     PKC(pk_rnn_layer_fwd(PK_CELL_LIGRU | vflag, T, B, H, ndir, act, dPT.p, c.ld, dsc.p, dsh.p, dU.p, dmask.p, 1.f, dY.p, ldy,
@@ -349,12 +383,13 @@ static void test_elementwise() {
     auto x = randn(10000, 3e-5f);
     float amax = 0;
     for (auto v : x) amax = std::max(amax, std::fabs(v));
-    Dev<float> dx(x.size()), dscr(1), dsc(1);
+    Dev<float> dx(x.size()), dscr(1), dsc(2);
     dx.up(x);
     PKC(pk_amax_scale(dx.p, 100, 100, 100, 8.f, dscr.p, dsc.p, nullptr));
     CK(cudaDeviceSynchronize());
     const float s = dsc.down()[0];
-    const bool ok = amax * s >= 128.f && amax * s < 256.f && std::exp2(std::round(std::log2(s))) == s;
+    const bool ok = amax * s >= 128.f && amax * s < 256.f && std::exp2(std::round(std::log2(s))) == s &&
+                    dsc.down()[1] == 1.f / s;
     report("amax_scale", ok ? 0 : 1, 0, "scale=" + std::to_string(s));
   }
   // log-softmax + NLL + err, and its backward (fused mode)
@@ -395,7 +430,7 @@ static void test_elementwise() {
     report("logsoftmax_nll", e, 2e-5);
     Dev<__half> d16((size_t)N * ld16), dT16((size_t)S * ld16t);
     const float gcoef = 1.f / N, oscale = 1024.f;
-    PKC(pk_logsoftmax_bwd(N, S, dx.p, ld, (const int64_t*)dlab.p, nullptr, 0, gcoef, oscale, d16.p, ld16, dT16.p,
+    PKC(pk_logsoftmax_bwd(N, S, dx.p, ld, (const int64_t*)dlab.p, nullptr, 0, gcoef, oscale, nullptr, d16.p, ld16, dT16.p,
                           ld16t, dbias.p, nullptr, nullptr));
     CK(cudaDeviceSynchronize());
     auto g16 = d16.down();
@@ -520,14 +555,16 @@ static void bench_all() {
     dgs.up({1024.f});
     ddY.up(randn(nch, 1e-3f));
     struct V { const char* name; int flags; };
-    const V vs[] = {{"cl8  st.async            ", PK_REC_CLUSTER8},
-                    {"cl16 st.async            ", PK_REC_CLUSTER16},
-                    {"cl8  barrier             ", PK_REC_CLUSTER8 | PK_REC_SYNC_BARRIER},
-                    {"cl16 barrier             ", PK_REC_CLUSTER16 | PK_REC_SYNC_BARRIER},
-                    {"cl8  st.async nostore    ", PK_REC_CLUSTER8 | PK_REC_DBG_NOSTORE},
-                    {"cl8  st.async noload/st  ", PK_REC_CLUSTER8 | PK_REC_DBG_NOSTORE | PK_REC_DBG_NOLOAD},
-                    {"cl16 st.async noload/st  ", PK_REC_CLUSTER16 | PK_REC_DBG_NOSTORE | PK_REC_DBG_NOLOAD},
-                    {"cl8  barrier  noload/st  ", PK_REC_CLUSTER8 | PK_REC_SYNC_BARRIER | PK_REC_DBG_NOSTORE | PK_REC_DBG_NOLOAD}};
+    const V vs[] = {{"cl8  st.async            ", PK_REC_CLUSTER(8)},
+                    {"cl9  st.async            ", PK_REC_CLUSTER(9)},
+                    {"cl10 st.async            ", PK_REC_CLUSTER(10)},
+                    {"cl12 st.async            ", PK_REC_CLUSTER(12)},
+                    {"cl16 st.async            ", PK_REC_CLUSTER(16)},
+                    {"cl8  barrier             ", PK_REC_CLUSTER(8) | PK_REC_SYNC_BARRIER},
+                    {"cl8  st.async nostore    ", PK_REC_CLUSTER(8) | PK_REC_DBG_NOSTORE},
+                    {"cl10 st.async nostore    ", PK_REC_CLUSTER(10) | PK_REC_DBG_NOSTORE},
+                    {"cl8  st.async noload/st  ", PK_REC_CLUSTER(8) | PK_REC_DBG_NOSTORE | PK_REC_DBG_NOLOAD},
+                    {"cl10 st.async noload/st  ", PK_REC_CLUSTER(10) | PK_REC_DBG_NOSTORE | PK_REC_DBG_NOLOAD}};
     for (const V& v : vs) {
       const int flag = v.flags;
       int rc = 0;
@@ -561,7 +598,7 @@ static void bench_all() {
       Dev<float> dC((size_t)g.M * g.N);
       int rc = 0;
       float ms = time_ms(5, [&] {
-        rc |= pk_gemm_tn(dtype, g.M, g.N, g.K, dA, lda, dB, lda, dC.p, g.N, nullptr, 0, nullptr, 1.f, nullptr, 0, g.sk,
+        rc |= pk_gemm_tn(dtype, g.M, g.N, g.K, dA, lda, 0, 0, dB, lda, 0, 0, dC.p, g.N, nullptr, 0, nullptr, 1.f, nullptr, 0, g.sk,
                          nullptr);
       });
       printf("gemm %s %-4s M=%5d N=%5d K=%5d sk=%2d : %.3f ms  %.1f TFLOP/s rc=%d\n", g.name,
@@ -593,6 +630,9 @@ int main(int argc, char** argv) {
   test_gemm(PK_F16, 256, 130, 2000, 0, false, 4, 0);
   test_gemm(PK_F16, 256, 130, 2000, 2, false, 3, 1);
   test_gemm(PK_TF32, 100, 60, 900, 0, false, 1, 1);
+  test_gemm_shift(150, 70, 1000, 5, 0);
+  test_gemm_shift(150, 70, 1000, 0, 5);
+  test_gemm_shift(64, 200, 333, 32, 0);
   test_elementwise();
   test_ligru(3, 2, 20, 1, PK_ACT_RELU);
   test_ligru(7, 5, 70, 2, PK_ACT_TANH);

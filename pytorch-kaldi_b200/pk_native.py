@@ -1,0 +1,168 @@
+"""ctypes binding of libpk_b200.so (the C ABI declared in include/pk_b200.h).
+
+PyTorch is used only for device memory and streams: every wrapper takes torch tensors, checks
+device / dtype / contiguity, and passes raw device pointers + the current CUDA stream to the
+library.  There is NO fallback: if the shared library is missing or a call fails, a
+RuntimeError is raised (the product path must fail loudly, never silently run on the CPU).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpk_b200.so")
+
+F16, TF32 = 0, 2
+ACT_IDS = {"relu": 0, "tanh": 1, "sigmoid": 2, "leaky_relu": 3, "elu": 4, "linear": 5}
+CELL_LIGRU, CELL_RNN, CELL_GRU, CELL_MGRU, CELL_LSTM = 0, 1, 2, 3, 4
+REC_CLUSTER8, REC_CLUSTER16, REC_SYNC_BARRIER = 0x800, 0x1000, 0x2000
+
+_c_int, _c_i64, _c_f, _c_p = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
+
+# name -> argtypes (mirrors include/pk_b200.h; tests check that every symbol resolves)
+SIGNATURES = {
+    "pk_gemm_tn": [_c_int, _c_int, _c_int, _c_int, _c_p, _c_i64, _c_i64, _c_i64, _c_p, _c_i64, _c_i64, _c_i64, _c_p,
+                   _c_i64, _c_p, _c_int, _c_p, _c_f, _c_p, _c_int, _c_int, _c_p],
+    "pk_transpose_f32": [_c_p, _c_i64, _c_int, _c_int, _c_p, _c_i64, _c_p, _c_i64, _c_p, _c_i64, _c_p, _c_p],
+    "pk_convert_f16": [_c_p, _c_i64, _c_int, _c_int, _c_p, _c_i64, _c_p, _c_p],
+    "pk_amax_scale": [_c_p, _c_i64, _c_int, _c_int, _c_f, _c_p, _c_p, _c_p],
+    "pk_bn_finalize": [_c_p, _c_int, _c_i64, _c_i64, _c_p, _c_p, _c_f, _c_f, _c_int, _c_p, _c_p, _c_p, _c_p, _c_p,
+                       _c_p, _c_p, _c_p],
+    "pk_fill_scale_shift": [_c_p, _c_int, _c_p, _c_p, _c_p],
+    "pk_bn_bwd": [_c_int, _c_int, _c_i64, _c_p, _c_i64, _c_p, _c_i64, _c_int, _c_int, _c_p, _c_p, _c_p, _c_p, _c_p,
+                  _c_p, _c_p, _c_i64, _c_p, _c_i64, _c_p, _c_p],
+    "pk_rnn_layer_fwd": [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_p, _c_i64, _c_p, _c_p, _c_p, _c_p, _c_f,
+                         _c_p, _c_i64, _c_p, _c_i64, _c_p, _c_p, _c_p, _c_p, _c_i64, _c_p],
+    "pk_rnn_layer_bwd": [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_p, _c_p, _c_p, _c_p, _c_i64, _c_p, _c_p,
+                         _c_f, _c_p, _c_p, _c_p, _c_p],
+    "pk_logsoftmax_nll": [_c_int, _c_int, _c_p, _c_i64, _c_p, _c_p, _c_p],
+    "pk_logsoftmax_bwd": [_c_int, _c_int, _c_p, _c_i64, _c_p, _c_p, _c_i64, _c_f, _c_f, _c_p, _c_p, _c_i64, _c_p,
+                          _c_i64, _c_p, _c_p, _c_p],
+    "pk_rmsprop_step": [_c_p, _c_p, _c_p, _c_i64, _c_f, _c_f, _c_f, _c_f, _c_p],
+    "pk_sgd_step": [_c_p, _c_p, _c_i64, _c_f, _c_f, _c_p],
+}
+
+_lib = None
+
+
+def lib():
+    """Load the shared library once.  Raises if it has not been built (python __graft_entry__.py)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback for the B200 path)")
+        L = ctypes.CDLL(LIB_PATH)
+        L.pk_last_error.restype = ctypes.c_char_p
+        L.pk_last_error.argtypes = []
+        L.pk_version.restype = _c_int
+        L.pk_version.argtypes = []
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = _c_int
+            fn.argtypes = argtypes
+        _lib = L
+    return _lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (rc={rc}): {lib().pk_last_error().decode()}")
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("pk_native: tensor is not on a CUDA device (no CPU fallback)")
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def pad8(n: int) -> int:
+    return (int(n) + 7) // 8 * 8
+
+
+# ---------------------------------------------------------------------------------------------
+# thin wrappers (shapes/strides spelled out by the caller; see include/pk_b200.h)
+# ---------------------------------------------------------------------------------------------
+
+
+def gemm_tn(A, B, C, M, N, K, *, lda, ldb, ldc, dtype=F16, a_k0=0, a_kext=0, b_k0=0, b_kext=0, bias=None,
+            bias_mode=0, rowstats=None, alpha=1.0, alpha_dev=None, accumulate=False, split_k=1):
+    _check(lib().pk_gemm_tn(dtype, M, N, K, _ptr(A), lda, a_k0, a_kext, _ptr(B), ldb, b_k0, b_kext, _ptr(C), ldc,
+                            _ptr(bias), bias_mode if bias is not None else 0, _ptr(rowstats), float(alpha),
+                            _ptr(alpha_dev), int(accumulate), int(split_k), _stream()), "pk_gemm_tn")
+
+
+def transpose_f32(inp, ldi, R, C, *, outT=None, ldo=0, outT16=None, ldo16=0, in16=None, ldi16=0, scale_dev=None):
+    _check(lib().pk_transpose_f32(_ptr(inp), ldi, R, C, _ptr(outT), ldo, _ptr(outT16), ldo16, _ptr(in16), ldi16,
+                                  _ptr(scale_dev), _stream()), "pk_transpose_f32")
+
+
+def convert_f16(inp, ldi, R, C, out, ldo, scale_dev=None):
+    _check(lib().pk_convert_f16(_ptr(inp), ldi, R, C, _ptr(out), ldo, _ptr(scale_dev), _stream()), "pk_convert_f16")
+
+
+def amax_scale(x, ld, R, C, target_log2, scratch, scale_out):
+    _check(lib().pk_amax_scale(_ptr(x), ld, R, C, float(target_log2), _ptr(scratch), _ptr(scale_out), _stream()),
+           "pk_amax_scale")
+
+
+def bn_finalize(stats, C, n_unique, n_ref, gamma, beta, eps, momentum, training, running_mean, running_var,
+                num_batches, scale, shift, mean_out, rstd_out):
+    _check(lib().pk_bn_finalize(_ptr(stats), C, n_unique, n_ref, _ptr(gamma), _ptr(beta), float(eps),
+                                float(momentum), int(training), _ptr(running_mean), _ptr(running_var),
+                                _ptr(num_batches), _ptr(scale), _ptr(shift), _ptr(mean_out), _ptr(rstd_out),
+                                _stream()), "pk_bn_finalize")
+
+
+def fill_scale_shift(bias, C, scale, shift):
+    _check(lib().pk_fill_scale_shift(_ptr(bias), C, _ptr(scale), _ptr(shift), _stream()), "pk_fill_scale_shift")
+
+
+def bn_bwd(C, ndir, n, GT, ldt, PT, ldp, use_bn, training, mean, rstd, gamma, gscale, dgamma, dbeta, dPT16, ld16t,
+           dP16, ld16r, sums_scratch):
+    _check(lib().pk_bn_bwd(C, ndir, n, _ptr(GT), ldt, _ptr(PT), ldp, int(use_bn), int(training), _ptr(mean),
+                           _ptr(rstd), _ptr(gamma), _ptr(gscale), _ptr(dgamma), _ptr(dbeta), _ptr(dPT16), ld16t,
+                           _ptr(dP16), ld16r, _ptr(sums_scratch), _stream()), "pk_bn_bwd")
+
+
+def rnn_layer_fwd(cell, T, B, H, ndir, act, PT, ldp, scale, shift, U, mask, mask_scalar, Y32, ldy32, Y16, ldy16, HT,
+                  HT16, ZT, HCT, ldt):
+    _check(lib().pk_rnn_layer_fwd(cell, T, B, H, ndir, act, _ptr(PT), ldp, _ptr(scale), _ptr(shift), _ptr(U),
+                                  _ptr(mask), float(mask_scalar), _ptr(Y32), ldy32, _ptr(Y16), ldy16, _ptr(HT),
+                                  _ptr(HT16), _ptr(ZT), _ptr(HCT), ldt, _stream()), "pk_rnn_layer_fwd")
+
+
+def rnn_layer_bwd(cell, T, B, H, ndir, act, dYT, HT, ZT, HCT, ldt, U, mask, mask_scalar, gscale, GT, GT16):
+    _check(lib().pk_rnn_layer_bwd(cell, T, B, H, ndir, act, _ptr(dYT), _ptr(HT), _ptr(ZT), _ptr(HCT), ldt, _ptr(U),
+                                  _ptr(mask), float(mask_scalar), _ptr(gscale), _ptr(GT), _ptr(GT16), _stream()),
+           "pk_rnn_layer_bwd")
+
+
+def logsoftmax_nll(N, S, logits, ld, labels, acc):
+    _check(lib().pk_logsoftmax_nll(N, S, _ptr(logits), ld, _ptr(labels), _ptr(acc), _stream()), "pk_logsoftmax_nll")
+
+
+def logsoftmax_bwd(N, S, logp, ld, labels, dlogp, lddl, gcoef, out_scale, scale_dev, d16, ld16, dT16, ld16t, dbias,
+                   rowsum_scratch):
+    _check(lib().pk_logsoftmax_bwd(N, S, _ptr(logp), ld, _ptr(labels), _ptr(dlogp), lddl, float(gcoef),
+                                   float(out_scale), _ptr(scale_dev), _ptr(d16), ld16, _ptr(dT16), ld16t,
+                                   _ptr(dbias), _ptr(rowsum_scratch), _stream()), "pk_logsoftmax_bwd")
+
+
+def rmsprop_step(p, g, v, lr, alpha, eps, gscale=1.0):
+    _check(lib().pk_rmsprop_step(_ptr(p), _ptr(g), _ptr(v), p.numel(), float(lr), float(alpha), float(eps),
+                                 float(gscale), _stream()), "pk_rmsprop_step")
+
+
+def sgd_step(p, g, lr, gscale=1.0):
+    _check(lib().pk_sgd_step(_ptr(p), _ptr(g), p.numel(), float(lr), float(gscale), _stream()), "pk_sgd_step")
