@@ -68,8 +68,8 @@ int pk_version(void);
  *   bias_mode 1: bias[n], 2: bias[m];  rowstats: optional [2][M] doubles accumulating per-row
  *   sum and sum of squares of the OUTPUT (BatchNorm batch statistics of a channel-major
  *   projection);  accumulate: C += ...;  split_k > 1 partitions K over gridDim.z with fp32
- *   atomics;  a_kext / b_kext: valid extent of each operand's K axis (0 -> k0 + K), reads past
- *   it return zeros (this is how the time-shifted product sum_t G_t^T h_{t-1} is expressed).
+ *   atomics;  a_k0 / b_k0 (multiples of 16 bytes) select a sub-range of each operand's K axis;
+ *   a_kext / b_kext: valid extent of that axis (0 -> k0 + K), reads past it return zeros.
  * Replaces: nn.Linear forward/backward GEMMs (neural_networks.py:1114-1115, :432-435,
  * :609-611, :138-148 and their autograd transposes). */
 int pk_gemm_tn(int dtype, int M, int N, int K, const void* A, int64_t lda, int64_t a_k0,
@@ -121,13 +121,15 @@ int pk_bn_bwd(int C, int ndir, int64_t n, const float* GT, int64_t ldt, const fl
  *                     with mask_scalar = 1-p (eval);
  * outputs (any may be NULL): Y32 [T*B][ldy32] row-major [t,b,d*H+u] (= module output),
  * Y16 fp16 copy (next layer's GEMM operand), HT/HT16/ZT/HCT channel-major [ndir*H][ldt]
- * (state, update gate, masked candidate — saved for the backward).
+ * (state, update gate, masked candidate — saved for the backward), HP16 = fp16 copy of the
+ * PREVIOUS state h_{k-1} stored at the column of step k (zeros at k=0): the K-major operand
+ * of dU = sum_t G_t^T h_{t-1}, so that product needs no time shift.
  * Replaces: the `for k in range(x.shape[0])` loops (liGRU neural_networks.py:1130-1141). */
 int pk_rnn_layer_fwd(int cell, int T, int B, int H, int ndir, int act, const float* PT,
                      int64_t ldp, const float* scale, const float* shift, const float* U,
                      const float* mask, float mask_scalar, float* Y32, int64_t ldy32, void* Y16,
-                     int64_t ldy16, float* HT, void* HT16, float* ZT, float* HCT, int64_t ldt,
-                     void* stream);
+                     int64_t ldy16, float* HT, void* HT16, void* HP16, float* ZT, float* HCT,
+                     int64_t ldt, void* stream);
 
 /* Reverse-time persistent kernel: dYT [ndir*H][ldt] channel-major gradient w.r.t. the layer
  * output -> GT [ndir][G*H][ldt] fp32 gradients w.r.t. the normalised pre-activations

@@ -109,7 +109,7 @@ int pk_bn_bwd(int C, int ndir, int64_t n, const float* GT, int64_t ldt, const fl
 int pk_rnn_layer_fwd(int cell, int T, int B, int H, int ndir, int act, const float* PT, int64_t ldp,
                      const float* scale, const float* shift, const float* U, const float* mask,
                      float mask_scalar, float* Y32, int64_t ldy32, void* Y16, int64_t ldy16, float* HT,
-                     void* HT16, float* ZT, float* HCT, int64_t ldt, void* stream) {
+                     void* HT16, void* HP16, float* ZT, float* HCT, int64_t ldt, void* stream) {
   const RecFlags f = parse_cell(cell);
   PK_REQUIRE(f.cell == PK_CELL_LIGRU, "pk_rnn_layer_fwd: cell kind %d not implemented", f.cell);
   PK_REQUIRE(PT && scale && shift && U, "pk_rnn_layer_fwd: null input");
@@ -118,7 +118,8 @@ int pk_rnn_layer_fwd(int cell, int T, int B, int H, int ndir, int act, const flo
   a.T = T; a.B = B; a.H = H; a.ndir = ndir; a.act = act;
   a.PT = PT; a.ldp = ldp; a.scale = scale; a.shift = shift; a.U = U; a.mask = mask; a.mask_scalar = mask_scalar;
   a.Y32 = Y32; a.ldy32 = ldy32; a.Y16 = static_cast<__half*>(Y16); a.ldy16 = ldy16;
-  a.HT = HT; a.HT16 = static_cast<__half*>(HT16); a.ZT = ZT; a.HCT = HCT; a.ldt = ldt;
+  a.HT = HT; a.HT16 = static_cast<__half*>(HT16); a.HP16 = static_cast<__half*>(HP16);
+  a.ZT = ZT; a.HCT = HCT; a.ldt = ldt;
   a.cluster = f.cluster; a.sync = f.sync; a.dbg = f.dbg;
   return ligru_fwd(a, static_cast<cudaStream_t>(stream));
 }

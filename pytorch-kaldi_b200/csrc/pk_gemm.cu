@@ -247,6 +247,11 @@ int gemm_tn(const GemmArgs& a, cudaStream_t stream) {
   // the K extent of each map bounds what TMA may read; everything beyond is zero-filled, so a
   // shifted contraction (a_k0 != b_k0) stays exact as long as one side runs out of bounds
   PK_REQUIRE(a.a_k0 >= 0 && a.b_k0 >= 0, "gemm_tn: negative k offset");
+  {
+    const int esz = (a.dtype == PK_DT_F16) ? 2 : 4;
+    PK_REQUIRE((a.a_k0 * esz) % 16 == 0 && (a.b_k0 * esz) % 16 == 0,
+               "gemm_tn: k offsets must be multiples of 16 bytes (TMA box start alignment)");
+  }
   const long long a_ext = a.a_kext > 0 ? a.a_kext : a.a_k0 + a.K;
   const long long b_ext = a.b_kext > 0 ? a.b_kext : a.b_k0 + a.K;
   if (int rc = make_operand_map(&tmA, a.A, a.dtype, a.M, a_ext, a.lda)) return rc;

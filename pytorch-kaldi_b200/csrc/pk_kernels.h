@@ -47,6 +47,7 @@ struct RecFwdArgs {
   long long ldy16 = 0;
   float* HT = nullptr;     // [ndir*H][ldt] channel-major, natural time
   __half* HT16 = nullptr;  // same, fp16
+  __half* HP16 = nullptr;  // fp16 PREVIOUS state h_{k-1} at the same column (operand of dU), zeros at k=0
   float* ZT = nullptr;
   float* HCT = nullptr;
   long long ldt = 0;

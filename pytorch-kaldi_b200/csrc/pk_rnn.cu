@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(MT * 32, 1) ligru_fwd_kernel(const RecFwdArgs 
     // ---------------- gates (reference :1133-1136) ----------------
     cp_async_wait_all();  // this step's projections (issued one step ago) are in smem
     const float* pre = cur ? mypre1 : mypre0;
-    float hn[2], zz[2], hcv[2];
+    float hn[2], zz[2], hcv[2], hold[2];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const float zt = sigmoidf_(fmaf(sc_z, pre[2 + i], sh_z) + cz[i]);
@@ -208,6 +208,7 @@ __global__ void __launch_bounds__(MT * 32, 1) ligru_fwd_kernel(const RecFwdArgs 
       float h = zt * hprev[i] + (1.f - zt) * hc;
       if (!rok[i]) h = 0.f;
       hn[i] = h; zz[i] = zt; hcv[i] = hc;
+      hold[i] = hprev[i];
       hprev[i] = h;
       if (SY) sm.stage[warp][2 * q + i][g] = f16_sat(h);
       else sm.h16[nxt][2 * q + i][u] = f16_sat(h);
@@ -249,6 +250,7 @@ __global__ void __launch_bounds__(MT * 32, 1) ligru_fwd_kernel(const RecFwdArgs 
             const long long ch_idx = static_cast<long long>(rd[i] * H + u) * a.ldt + col;
             if (a.HT) a.HT[ch_idx] = hn[i];
             if (a.HT16) a.HT16[ch_idx] = f16_sat(hn[i]);
+            if (a.HP16) a.HP16[ch_idx] = f16_sat(hold[i]);
             if (a.ZT) a.ZT[ch_idx] = zz[i];
             if (a.HCT) a.HCT[ch_idx] = hcv[i];
             if (a.Y32) a.Y32[col * a.ldy32 + rd[i] * H + u] = hn[i];
@@ -547,10 +549,13 @@ int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
 }
-int pick_cluster(int requested) {
+int pick_cluster(int requested, int H) {
   if (requested > 0) return requested;
   static int env = env_int("PK_REC_CLUSTER", 0);  // tuning knob for bring-up
-  return env > 0 ? env : 8;
+  if (env > 0) return env;
+  // measured on B200 (profiles/): 10 CTAs x 7 warps keeps the 35 k-tile weight slice in registers
+  // without spills (<= 8 warps/CTA -> 255 regs) and gave the shortest step
+  return H > 512 ? 10 : 8;
 }
 int pick_sync(int requested) {  // 1 = st.async + mbarrier (default), 0 = barrier.cluster
   if (requested == 0 || requested == 1) return requested;
@@ -598,7 +603,7 @@ int ligru_fwd(const RecFwdArgs& a, cudaStream_t stream) {
   PK_REQUIRE(a.ndir == 1 || a.ndir == 2, "ligru_fwd: ndir must be 1 or 2");
   PK_REQUIRE(a.H <= 560, "ligru_fwd: hidden size %d > 560 not supported by the register-resident kernel", a.H);
   const int nclusters = (a.ndir * a.B + kRows - 1) / kRows;
-  return fwd_dispatch(a, pick_cluster(a.cluster), pick_sync(a.sync), nclusters, stream);
+  return fwd_dispatch(a, pick_cluster(a.cluster, a.H), pick_sync(a.sync), nclusters, stream);
 }
 
 int ligru_bwd(const RecBwdArgs& a, cudaStream_t stream) {
@@ -606,7 +611,7 @@ int ligru_bwd(const RecBwdArgs& a, cudaStream_t stream) {
   PK_REQUIRE(a.ndir == 1 || a.ndir == 2, "ligru_bwd: ndir must be 1 or 2");
   PK_REQUIRE(a.H <= 560, "ligru_bwd: hidden size %d > 560 not supported by the register-resident kernel", a.H);
   const int nclusters = (a.ndir * a.B + kRows - 1) / kRows;
-  return bwd_dispatch(a, pick_cluster(a.cluster), pick_sync(a.sync), nclusters, stream);
+  return bwd_dispatch(a, pick_cluster(a.cluster, a.H), pick_sync(a.sync), nclusters, stream);
 }
 
 }  // namespace pk

@@ -309,9 +309,9 @@ static void test_ligru(int T, int B, int H, int ndir, int act) {
     const char* cl = names[pass];
     const int vflag = vflags[pass];
     Dev<float> dHT(nch), dZT(nch), dHCT(nch), dY((size_t)T * B * ldy);
-    Dev<__half> dY16((size_t)T * B * ldy16), dHT16(nch);
+    Dev<__half> dY16((size_t)T * B * ldy16), dHT16(nch), dHP16(nch);
     PKC(pk_rnn_layer_fwd(PK_CELL_LIGRU | vflag, T, B, H, ndir, act, dPT.p, c.ld, dsc.p, dsh.p, dU.p, dmask.p, 1.f, dY.p, ldy,
-                         dY16.p, ldy16, dHT.p, dHT16.p, dZT.p, dHCT.p, c.ld, nullptr));
+                         dY16.p, ldy16, dHT.p, dHT16.p, dHP16.p, dZT.p, dHCT.p, c.ld, nullptr));
     CK(cudaDeviceSynchronize());
     auto gHT = dHT.down(), gZT = dZT.down(), gHCT = dHCT.down(), gY = dY.down();
     auto gY16 = dY16.down();
@@ -327,6 +327,20 @@ static void test_ligru(int T, int B, int H, int ndir, int act) {
           ey = std::max(ey, (double)std::fabs(gY[((size_t)t * B + b) * ldy + ch] - ref));
           ey = std::max(ey, (double)std::fabs(__half2float(gY16[((size_t)t * B + b) * ldy16 + ch]) - h2f(ref)));
         }
+    {  // HP16 must be the fp16 state of the previous step at the same column
+      auto gHP = dHP16.down();
+      for (int r = 0; r < ndir * B; ++r) {
+        const int d = r >= B, b = r - d * B;
+        for (int k = 0; k < T; ++k) {
+          const int t = d ? T - 1 - k : k;
+          for (int uu = 0; uu < H; ++uu) {
+            const size_t idx = (size_t)(d * H + uu) * c.ld + (size_t)t * B + b;
+            const float ref = k > 0 ? h2f(gHT[idx + (d ? B : -B)]) : 0.f;
+            ey = std::max(ey, (double)std::fabs(__half2float(gHP[idx]) - ref));
+          }
+        }
+      }
+    }
     report(name, std::max(e, ey), 2e-3);
 
     // backward
@@ -551,7 +565,7 @@ static void bench_all() {
     dU.up(randn((size_t)2 * H * H, 1.f / sqrtf(550.f)));
     dmask.up(std::vector<float>((size_t)ndir * B * H, 1.f));
     Dev<float> dHT(nch), dZT(nch), dHCT(nch), dY((size_t)T * B * 1100), dGT(2 * nch), dgs(1), ddY(nch);
-    Dev<__half> dY16((size_t)T * B * 1104), dHT16(nch), dGT16(2 * nch);
+    Dev<__half> dY16((size_t)T * B * 1104), dHT16(nch), dHP16(nch), dGT16(2 * nch);
     dgs.up({1024.f});
     ddY.up(randn(nch, 1e-3f));
     struct V { const char* name; int flags; };
@@ -570,7 +584,7 @@ static void bench_all() {
       int rc = 0;
       float ms = time_ms(3, [&] {
         rc |= pk_rnn_layer_fwd(PK_CELL_LIGRU | flag, T, B, H, ndir, PK_ACT_RELU, dPT.p, ld, dsc.p, dsh.p, dU.p, dmask.p, 1.f, dY.p, 1100,
-                               dY16.p, 1104, dHT.p, dHT16.p, dZT.p, dHCT.p, ld, nullptr);
+                               dY16.p, 1104, dHT.p, dHT16.p, dHP16.p, dZT.p, dHCT.p, ld, nullptr);
       });
       printf("ligru_fwd %s: %.3f ms/layer  (%.3f us/step) rc=%d %s\n", v.name, ms, ms * 1000.f / T, rc,
              rc ? pk_last_error() : "");
@@ -630,8 +644,8 @@ int main(int argc, char** argv) {
   test_gemm(PK_F16, 256, 130, 2000, 0, false, 4, 0);
   test_gemm(PK_F16, 256, 130, 2000, 2, false, 3, 1);
   test_gemm(PK_TF32, 100, 60, 900, 0, false, 1, 1);
-  test_gemm_shift(150, 70, 1000, 5, 0);
-  test_gemm_shift(150, 70, 1000, 0, 5);
+  test_gemm_shift(150, 70, 1000, 8, 0);
+  test_gemm_shift(150, 70, 1000, 0, 40);
   test_gemm_shift(64, 200, 333, 32, 0);
   test_elementwise();
   test_ligru(3, 2, 20, 1, PK_ACT_RELU);

@@ -35,7 +35,7 @@ SIGNATURES = {
     "pk_bn_bwd": [_c_int, _c_int, _c_i64, _c_p, _c_i64, _c_p, _c_i64, _c_int, _c_int, _c_p, _c_p, _c_p, _c_p, _c_p,
                   _c_p, _c_p, _c_i64, _c_p, _c_i64, _c_p, _c_p],
     "pk_rnn_layer_fwd": [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_p, _c_i64, _c_p, _c_p, _c_p, _c_p, _c_f,
-                         _c_p, _c_i64, _c_p, _c_i64, _c_p, _c_p, _c_p, _c_p, _c_i64, _c_p],
+                         _c_p, _c_i64, _c_p, _c_i64, _c_p, _c_p, _c_p, _c_p, _c_p, _c_i64, _c_p],
     "pk_rnn_layer_bwd": [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_p, _c_p, _c_p, _c_p, _c_i64, _c_p, _c_p,
                          _c_f, _c_p, _c_p, _c_p, _c_p],
     "pk_logsoftmax_nll": [_c_int, _c_int, _c_p, _c_i64, _c_p, _c_p, _c_p],
@@ -136,10 +136,10 @@ def bn_bwd(C, ndir, n, GT, ldt, PT, ldp, use_bn, training, mean, rstd, gamma, gs
 
 
 def rnn_layer_fwd(cell, T, B, H, ndir, act, PT, ldp, scale, shift, U, mask, mask_scalar, Y32, ldy32, Y16, ldy16, HT,
-                  HT16, ZT, HCT, ldt):
+                  HT16, HP16, ZT, HCT, ldt):
     _check(lib().pk_rnn_layer_fwd(cell, T, B, H, ndir, act, _ptr(PT), ldp, _ptr(scale), _ptr(shift), _ptr(U),
                                   _ptr(mask), float(mask_scalar), _ptr(Y32), ldy32, _ptr(Y16), ldy16, _ptr(HT),
-                                  _ptr(HT16), _ptr(ZT), _ptr(HCT), ldt, _stream()), "pk_rnn_layer_fwd")
+                                  _ptr(HT16), _ptr(HP16), _ptr(ZT), _ptr(HCT), ldt, _stream()), "pk_rnn_layer_fwd")
 
 
 def rnn_layer_bwd(cell, T, B, H, ndir, act, dYT, HT, ZT, HCT, ldt, U, mask, mask_scalar, gscale, GT, GT16):
