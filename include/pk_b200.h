@@ -65,8 +65,8 @@ int pk_version(void);
 
 /* C[M][ldc] (fp32) = alpha * (*alpha_dev) * A[M][a_k0 : a_k0+K] . B[N][b_k0 : b_k0+K]^T (+ bias);
  * both operands K-major ([rows][ld]).  tcgen05 / TMEM / TMA kernel.
- *   bias_mode 1: bias[n], 2: bias[m];  rowstats: optional [2][M] doubles accumulating per-row
- *   sum and sum of squares of the OUTPUT (BatchNorm batch statistics of a channel-major
+ *   bias_mode 1: bias[n], 2: bias[m];  rowstats: optional [M][2] doubles accumulating per-row
+ *   (sum, sum of squares) of the OUTPUT (BatchNorm batch statistics of a channel-major
  *   projection);  accumulate: C += ...;  split_k > 1 partitions K over gridDim.z with fp32
  *   atomics;  a_k0 / b_k0 (multiples of 16 bytes) select a sub-range of each operand's K axis;
  *   a_kext / b_kext: valid extent of that axis (0 -> k0 + K), reads past it return zeros.
@@ -92,7 +92,7 @@ int pk_amax_scale(const float* x, int64_t ld, int R, int C, float target_log2,
                   float* amax_scratch, float* scale_out, void* stream);
 
 /* nn.BatchNorm1d(C, momentum) over the projection rows (neural_networks.py:1070-1071,
- * :1118-1124): stats = [2][C] doubles (sum, sumsq over the n_unique = T*B de-duplicated rows);
+ * :1118-1124): stats = [C][2] doubles (sum, sumsq over the n_unique = T*B de-duplicated rows);
  * n_ref = number of rows the reference normalised (T*2B when bidirectional) for the unbiased
  * running_var.  Writes folded scale = gamma*rstd, shift = beta - mean*scale, and
  * mean/rstd for the backward.  training=0 uses running stats. */

@@ -128,8 +128,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, int C, long
   if (c >= C) return;
   float mean, rstd;
   if (training) {
-    const double m = stats[c] / static_cast<double>(n_unique);
-    double var = stats[C + c] / static_cast<double>(n_unique) - m * m;
+    const double m = stats[2 * c] / static_cast<double>(n_unique);
+    double var = stats[2 * c + 1] / static_cast<double>(n_unique) - m * m;
     if (var < 0.0) var = 0.0;
     mean = static_cast<float>(m);
     rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));

@@ -36,7 +36,7 @@ struct GemmDev {
   long long ldc;
   const float* bias;
   int bias_mode;  // 0 none, 1 along N (C[m][n] += bias[n]), 2 along M (C[m][n] += bias[m])
-  double* rowstats;  // [2][M] or null
+  double* rowstats;  // [M][2] (sum, sumsq) or null
   float alpha;
   const float* alpha_dev;  // optional device multiplier (e.g. 1/loss_scale)
   int atomic;              // 1: atomicAdd into C
@@ -175,8 +175,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     if (p.rowstats && gm < p.M) {
-      atomicAdd(p.rowstats + gm, s1);
-      atomicAdd(p.rowstats + p.M + gm, s2);
+      atomicAdd(p.rowstats + 2 * gm, s1);
+      atomicAdd(p.rowstats + 2 * gm + 1, s2);
     }
   }
 

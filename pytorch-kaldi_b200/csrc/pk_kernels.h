@@ -21,7 +21,7 @@ struct GemmArgs {
   long long ldc = 0;
   const float* bias = nullptr;
   int bias_mode = 0;  // 1: along N, 2: along M
-  double* rowstats = nullptr;  // [2][M] (sum, sumsq) accumulated with atomics, or null
+  double* rowstats = nullptr;  // [M][2] (sum, sumsq) accumulated with atomics, or null
   float alpha = 1.f;
   const float* alpha_dev = nullptr;
   int accumulate = 0;  // C += result

@@ -127,8 +127,8 @@ static void test_gemm(int dtype, int M, int N, int K, int bias_mode, bool stats,
       if (C[(size_t)m * ldc + n] != C0[(size_t)m * ldc + n]) maxerr = 1e9;
   if (stats)
     for (int m = 0; m < M; ++m) {
-      maxst = std::max(maxst, std::fabs(st[m] - rs[m]) / (1.0 + std::fabs(rs[m])));
-      maxst = std::max(maxst, std::fabs(st[M + m] - rs2[m]) / (1.0 + std::fabs(rs2[m])));
+      maxst = std::max(maxst, std::fabs(st[2 * m] - rs[m]) / (1.0 + std::fabs(rs[m])));
+      maxst = std::max(maxst, std::fabs(st[2 * m + 1] - rs2[m]) / (1.0 + std::fabs(rs2[m])));
     }
   char name[128];
   snprintf(name, sizeof(name), "gemm %s M%d N%d K%d bias%d st%d sk%d acc%d", dtype == PK_F16 ? "f16" : "tf32", M, N,
@@ -470,8 +470,8 @@ static void test_elementwise() {
     std::vector<double> stats(2 * C, 0.0);
     for (int c = 0; c < C; ++c)
       for (long long i = 0; i < n; ++i) {
-        stats[c] += PT[(size_t)c * ldp + i];
-        stats[C + c] += (double)PT[(size_t)c * ldp + i] * PT[(size_t)c * ldp + i];
+        stats[2 * c] += PT[(size_t)c * ldp + i];
+        stats[2 * c + 1] += (double)PT[(size_t)c * ldp + i] * PT[(size_t)c * ldp + i];
       }
     Dev<double> dst(2 * C), dsums(2 * C);
     Dev<float> dg(C), db(C), drm(C), drv(C), dsc(C), dsh(C), dmean(C), drstd(C), dPT(PT.size()), dGT(GT.size()), ddg(C),
@@ -493,7 +493,7 @@ static void test_elementwise() {
     auto p16 = dP16.down();
     double e = 0;
     for (int c = 0; c < C; ++c) {
-      const double mean = stats[c] / n, var = stats[C + c] / n - mean * mean, rstd = 1.0 / std::sqrt(var + 1e-5);
+      const double mean = stats[2 * c] / n, var = stats[2 * c + 1] / n - mean * mean, rstd = 1.0 / std::sqrt(var + 1e-5);
       e = std::max(e, std::fabs(sc[c] - gamma[c] * rstd) / (1 + std::fabs(gamma[c] * rstd)));
       e = std::max(e, std::fabs(sh[c] - (beta[c] - mean * gamma[c] * rstd)) / (1 + std::fabs(beta[c])));
       e = std::max(e, std::fabs(rm[c] - 0.05 * mean));

@@ -1,0 +1,299 @@
+"""Drop-in `neural_networks` module for pytorch-kaldi recipes, B200-native compute.
+
+Put this directory first on sys.path and every cfg that says `arch_library = neural_networks`
+resolves to these classes (utils.model_init: importlib.import_module + getattr + Class(options,
+inp_dim), reference utils.py:2047-2057).  The plug-in surface is kept bit-for-bit:
+
+  * constructor signature `Class(options, inp_dim)` with the reference's option names
+    (proto/*.proto) parsed from strings the same way (comma lists, strtobool);
+  * the same sub-modules registered under the same names in the same order and created in the
+    same sequence -> identical state_dict keys/shapes, optimizer parameter indices and
+    CPU-generator consumption (reference neural_networks.py constructors, e.g. liGRU :998-1080);
+  * `.out_dim`, train()/eval(), `to_do`/`use_cuda` options.
+
+Only `forward` differs: it runs the hand-written sm_100a kernels of libpk_b200.so through
+pk_functions (torch.autograd.Function over a C ABI).  There is NO eager-PyTorch or CPU
+fallback: unsupported option combinations raise NotImplementedError, CPU tensors raise
+RuntimeError.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+import pk_functions as pkf
+import pk_native as pk
+
+
+def strtobool(val) -> int:
+    """distutils.util.strtobool semantics (the reference parses cfg strings with it)."""
+    v = str(val).lower()
+    if v in ("y", "yes", "t", "true", "on", "1"):
+        return 1
+    if v in ("n", "no", "f", "false", "off", "0"):
+        return 0
+    raise ValueError(f"invalid truth value {val!r}")
+
+
+class LayerNorm(nn.Module):
+    """Reference neural_networks.py:23-33 — unbiased std, eps added to the std."""
+
+    def __init__(self, features, eps=1e-6):
+        super().__init__()
+        self.gamma = nn.Parameter(torch.ones(features))
+        self.beta = nn.Parameter(torch.zeros(features))
+        self.eps = eps
+
+    def forward(self, x):
+        mean = x.mean(-1, keepdim=True)
+        std = x.std(-1, keepdim=True)
+        return self.gamma * (x - mean) / (std + self.eps) + self.beta
+
+
+def act_fun(act_type):
+    """Reference neural_networks.py:36-57 (module objects are kept for state/API parity; the
+    kernels take the activation id)."""
+    table = {
+        "relu": nn.ReLU, "tanh": nn.Tanh, "sigmoid": nn.Sigmoid, "elu": nn.ELU,
+        "leaky_relu": lambda: nn.LeakyReLU(0.2), "softmax": lambda: nn.LogSoftmax(dim=1),
+        "linear": lambda: nn.LeakyReLU(1),
+    }
+    return table[act_type]() if act_type in table else None
+
+
+def flip(x, dim):
+    """Reference neural_networks.py:1962-1970 (API parity only: the kernels index time instead)."""
+    return torch.flip(x, dims=[dim if dim >= 0 else x.dim() + dim])
+
+
+def _floats(s):
+    return list(map(float, str(s).split(",")))
+
+
+def _ints(s):
+    return list(map(int, str(s).split(",")))
+
+
+def _bools(s):
+    return list(map(strtobool, str(s).split(",")))
+
+
+def _require_cuda(x, who):
+    if not x.is_cuda:
+        raise RuntimeError(f"pytorch-kaldi_b200.{who}: input is not a CUDA tensor — this library has no CPU path "
+                           "(the CPU oracle lives under oracle/ and is test infrastructure only)")
+
+
+# ---------------------------------------------------------------------------------------------
+# MLP (reference neural_networks.py:60-150)
+# ---------------------------------------------------------------------------------------------
+
+
+class MLP(nn.Module):
+    def __init__(self, options, inp_dim):
+        super().__init__()
+        self.input_dim = inp_dim
+        self.dnn_lay = _ints(options["dnn_lay"])
+        self.dnn_drop = _floats(options["dnn_drop"])
+        self.dnn_use_batchnorm = _bools(options["dnn_use_batchnorm"])
+        self.dnn_use_laynorm = _bools(options["dnn_use_laynorm"])
+        self.dnn_use_laynorm_inp = strtobool(options["dnn_use_laynorm_inp"])
+        self.dnn_use_batchnorm_inp = strtobool(options["dnn_use_batchnorm_inp"])
+        self.dnn_act = str(options["dnn_act"]).split(",")
+
+        self.wx = nn.ModuleList([])
+        self.bn = nn.ModuleList([])
+        self.ln = nn.ModuleList([])
+        self.act = nn.ModuleList([])
+        self.drop = nn.ModuleList([])
+        if self.dnn_use_laynorm_inp:
+            self.ln0 = LayerNorm(self.input_dim)
+        if self.dnn_use_batchnorm_inp:
+            self.bn0 = nn.BatchNorm1d(self.input_dim, momentum=0.05)
+        self.N_dnn_lay = len(self.dnn_lay)
+        cur = self.input_dim
+        for i, width in enumerate(self.dnn_lay):
+            self.drop.append(nn.Dropout(p=self.dnn_drop[i]))
+            self.act.append(act_fun(self.dnn_act[i]))
+            self.ln.append(LayerNorm(width))
+            self.bn.append(nn.BatchNorm1d(width, momentum=0.05))
+            add_bias = not (self.dnn_use_laynorm[i] or self.dnn_use_batchnorm[i])
+            lin = nn.Linear(cur, width, bias=add_bias)  # draws from the generator like the reference (:111)
+            bound = np.sqrt(0.01 / (cur + width))       # :114-119
+            lin.weight = nn.Parameter(torch.Tensor(width, cur).uniform_(-bound, bound))
+            lin.bias = nn.Parameter(torch.zeros(width))  # always re-created (:120)
+            self.wx.append(lin)
+            cur = width
+        self.out_dim = cur
+
+    def _is_plain_head(self):
+        return (self.N_dnn_lay == 1 and self.dnn_act[0] == "softmax" and not self.dnn_use_batchnorm[0]
+                and not self.dnn_use_laynorm[0] and not self.dnn_use_laynorm_inp and not self.dnn_use_batchnorm_inp
+                and (self.dnn_drop[0] == 0.0 or not self.training))
+
+    def forward(self, x):
+        _require_cuda(x, "MLP")
+        if self._is_plain_head():
+            return pkf.LinearLogSoftmaxFn.apply(x, self.wx[0].weight, self.wx[0].bias)
+        return pkf.mlp_forward(self, x)
+
+
+# ---------------------------------------------------------------------------------------------
+# recurrent zoo: liGRU :997, GRU :486, minimalGRU :1158, RNN :1319, LSTM :300
+# ---------------------------------------------------------------------------------------------
+
+
+class _Recurrent(nn.Module):
+    """Table-driven constructor shared by the five reference classes.  `_GATES` lists, in the
+    reference's registration order, (input-projection list name, recurrent list name); the
+    BatchNorm lists are `bn_<w-name>`."""
+
+    _PREFIX = ""
+    _GATES = ()
+    _CELL = -1
+
+    def __init__(self, options, inp_dim):
+        super().__init__()
+        p = self._PREFIX
+        self.input_dim = inp_dim
+        self.lay = _ints(options[p + "_lay"])
+        self.drop = _floats(options[p + "_drop"])
+        self.use_batchnorm = _bools(options[p + "_use_batchnorm"])
+        self.use_laynorm = _bools(options[p + "_use_laynorm"])
+        self.use_laynorm_inp = strtobool(options[p + "_use_laynorm_inp"])
+        self.use_batchnorm_inp = strtobool(options[p + "_use_batchnorm_inp"])
+        self.orthinit = strtobool(options[p + "_orthinit"])
+        self.act_names = str(options[p + "_act"]).split(",")
+        self.bidir = strtobool(options[p + "_bidir"])
+        self.use_cuda = strtobool(options["use_cuda"])
+        self.to_do = options["to_do"]
+        self.test_flag = self.to_do != "train"
+        # reference attribute names (kept for user code that pokes at them)
+        for k in ("lay", "drop", "use_batchnorm", "use_laynorm", "use_laynorm_inp", "use_batchnorm_inp", "orthinit"):
+            setattr(self, f"{p}_{k}", getattr(self, k))
+        setattr(self, f"{p}_act", self.act_names)
+
+        for w, u in self._GATES:  # registration order: (w, u) per gate ...
+            setattr(self, w, nn.ModuleList([]))
+            setattr(self, u, nn.ModuleList([]))
+        self.ln = nn.ModuleList([])  # ... then ln, the per-gate BatchNorm lists, act
+        for w, _ in self._GATES:
+            setattr(self, "bn_" + w, nn.ModuleList([]))
+        self.act = nn.ModuleList([])
+        if self.use_laynorm_inp:
+            self.ln0 = LayerNorm(self.input_dim)
+        if self.use_batchnorm_inp:
+            self.bn0 = nn.BatchNorm1d(self.input_dim, momentum=0.05)
+        self.N_lay = len(self.lay)
+        setattr(self, f"N_{p}_lay", self.N_lay)
+        cur = self.input_dim
+        for i, H in enumerate(self.lay):  # creation order inside a layer = generator consumption order
+            self.act.append(act_fun(self.act_names[i]))
+            add_bias = not (self.use_laynorm[i] or self.use_batchnorm[i])
+            for w, _ in self._GATES:
+                getattr(self, w).append(nn.Linear(cur, H, bias=add_bias))
+            for _, u in self._GATES:
+                getattr(self, u).append(nn.Linear(H, H, bias=False))
+            if self.orthinit:
+                for _, u in self._GATES:
+                    nn.init.orthogonal_(getattr(self, u)[i].weight)
+            for w, _ in self._GATES:
+                getattr(self, "bn_" + w).append(nn.BatchNorm1d(H, momentum=0.05))
+            self.ln.append(LayerNorm(H))
+            cur = 2 * H if self.bidir else H
+        self.out_dim = self.lay[-1] + self.bidir * self.lay[-1]
+        self.fast_dropout = False  # True: draw the masks with the device generator (no H2D copy)
+        self.cell_flags = 0        # tuning flags for the persistent kernel (pk_native.REC_*)
+
+    # -- dropout masks: reference draws Bernoulli(1-p) on the CPU generator once per layer per
+    #    forward and moves it to the device (:1102-1111); eval multiplies by the scalar 1-p
+    def _mask(self, i, rows, H, device):
+        if self.test_flag:
+            return None, 1.0 - self.drop[i]
+        if self.fast_dropout:
+            return torch.empty(rows, H, device=device).bernoulli_(1.0 - self.drop[i]), 1.0
+        m = torch.bernoulli(torch.Tensor(rows, H).fill_(1 - self.drop[i]))
+        return m.to(device, non_blocking=True), 1.0
+
+    def _check_supported(self):
+        if self.use_laynorm_inp or self.use_batchnorm_inp or any(self.use_laynorm):
+            raise NotImplementedError(
+                f"pytorch-kaldi_b200.{type(self).__name__}: *_use_laynorm / *_use_laynorm_inp / *_use_batchnorm_inp "
+                "are not implemented natively yet (no shipped recurrent recipe enables them); there is no fallback")
+        for a in self.act_names:
+            if a not in pk.ACT_IDS:
+                raise NotImplementedError(f"activation {a!r} is not valid inside a recurrent layer")
+
+    def forward(self, x):
+        _require_cuda(x, type(self).__name__)
+        self._check_supported()
+        if self._CELL != pk.CELL_LIGRU:
+            raise NotImplementedError(
+                f"pytorch-kaldi_b200.{type(self).__name__}: the persistent kernel for this gate family is not "
+                "built yet (liGRU is); there is no eager fallback")
+        T, B, _ = x.shape
+        rows = (2 if self.bidir else 1) * B
+        cfg = pkf.RecStackCfg(bidir=bool(self.bidir), cell=self._CELL, cell_flags=self.cell_flags)
+        params = []
+        for i, H in enumerate(self.lay):
+            mask, mscal = self._mask(i, rows, H, x.device)
+            ws = [getattr(self, w)[i] for w, _ in self._GATES]
+            us = [getattr(self, u)[i] for _, u in self._GATES]
+            bns = [getattr(self, "bn_" + w)[i] for w, _ in self._GATES]
+            use_bn = bool(self.use_batchnorm[i])
+            cfg.layers.append(pkf.RecLayerCfg(H=H, act=pk.ACT_IDS[self.act_names[i]], use_bn=use_bn,
+                                              bn_training=self.training, bn_h=bns[0],
+                                              bn_z=bns[1] if len(bns) > 1 else None, mask=mask, mask_scalar=mscal))
+            params += [m.weight for m in ws] + [m.weight for m in us]
+            if use_bn:
+                for bn in bns:
+                    params += [bn.weight, bn.bias]
+            else:
+                params += [m.bias for m in ws]
+        return pkf.LiGRUStackFn.apply(x, cfg, *params)
+
+
+class liGRU(_Recurrent):
+    _PREFIX, _CELL = "ligru", pk.CELL_LIGRU
+    _GATES = (("wh", "uh"), ("wz", "uz"))
+
+
+class GRU(_Recurrent):
+    _PREFIX, _CELL = "gru", pk.CELL_GRU
+    _GATES = (("wh", "uh"), ("wz", "uz"), ("wr", "ur"))
+
+
+class minimalGRU(_Recurrent):
+    _PREFIX, _CELL = "minimalgru", pk.CELL_MGRU
+    _GATES = (("wh", "uh"), ("wz", "uz"))
+
+
+class RNN(_Recurrent):
+    _PREFIX, _CELL = "rnn", pk.CELL_RNN
+    _GATES = (("wh", "uh"),)
+
+
+class LSTM(_Recurrent):
+    _PREFIX, _CELL = "lstm", pk.CELL_LSTM
+    _GATES = (("wfx", "ufh"), ("wix", "uih"), ("wox", "uoh"), ("wcx", "uch"))
+
+
+def _not_built(name, why):
+    class _Stub(nn.Module):
+        def __init__(self, *a, **k):
+            raise NotImplementedError(f"pytorch-kaldi_b200.{name}: {why}")
+    _Stub.__name__ = name
+    return _Stub
+
+
+# cuDNN wrappers of the reference (neural_networks.py:153-297) are deliberately not provided:
+# the north star of this library forbids routing the recurrence through cuDNN.
+LSTM_cudnn = _not_built("LSTM_cudnn", "cuDNN RNNs are out of scope; use arch_class = LSTM")
+GRU_cudnn = _not_built("GRU_cudnn", "cuDNN RNNs are out of scope; use arch_class = GRU")
+RNN_cudnn = _not_built("RNN_cudnn", "cuDNN RNNs are out of scope; use arch_class = RNN")
+# convolutional front-ends (neural_networks.py:1464-1959): next rows of the scope table
+CNN = _not_built("CNN", "conv1d front-end kernels are not built yet")
+SincNet = _not_built("SincNet", "sinc-conv front-end kernels are not built yet")
+SincConv = _not_built("SincConv", "sinc-conv front-end kernels are not built yet")
+SincConv_fast = _not_built("SincConv_fast", "sinc-conv front-end kernels are not built yet")

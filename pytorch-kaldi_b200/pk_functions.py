@@ -1,0 +1,341 @@
+"""torch.autograd.Function shims over the C ABI (include/pk_b200.h).
+
+These are the only places where the drop-in modules of neural_networks.py touch the device:
+every forward / backward below is a fixed sequence of libpk_b200.so calls (tcgen05 GEMMs, the
+persistent cluster recurrent kernels, the streaming companions).  torch is used for device
+memory, streams and autograd bookkeeping only.  There is no eager-PyTorch or CPU fallback.
+
+Data layout ("Data layout in HBM"):
+  row-major     [T*B, C]    frames as rows, n = t*B + b   (the reference's own 2-D view, utils.py:2323)
+  channel-major [C, ldt]    one row per unit/feature, ldt = pad8(T*B)
+fp16 copies are the tensor-core operands (fp32 accumulate); gradients are multiplied by a
+power-of-two loss scale before the fp16 conversion and the GEMM epilogues undo it.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import torch
+
+import pk_native as pk
+
+pad8 = pk.pad8
+
+
+@dataclass
+class RecLayerCfg:
+    """Static description of one recurrent layer (built by neural_networks.liGRU.forward)."""
+    H: int
+    act: int
+    use_bn: bool
+    bn_training: bool            # BatchNorm uses batch statistics (module.training)
+    bn_h: Optional[torch.nn.Module] = None   # nn.BatchNorm1d modules (running stats are updated in place)
+    bn_z: Optional[torch.nn.Module] = None
+    mask: Optional[torch.Tensor] = None      # [ndir*B, H] device tensor (training) or None
+    mask_scalar: float = 1.0                 # eval: 1 - p
+
+
+@dataclass
+class RecStackCfg:
+    bidir: bool
+    layers: List[RecLayerCfg] = field(default_factory=list)
+    cell: int = pk.CELL_LIGRU
+    cell_flags: int = 0  # tuning flags OR-ed into the cell id (cluster size, ...)
+
+
+def _rows_view(x2d_src: torch.Tensor, T: int, B: int):
+    """[T,B,D] (possibly a column slice of the chunk tensor, utils.py:2321) -> (tensor, row pitch)."""
+    x = x2d_src
+    if x.dtype != torch.float32:
+        x = x.float()
+    if x.stride(2) != 1 or x.stride(0) != B * x.stride(1):
+        x = x.contiguous()
+    return x, x.stride(1)
+
+
+class LiGRUStackFn(torch.autograd.Function):
+    """Whole liGRU stack: reference neural_networks.liGRU.forward (:1082-1155) and its autograd."""
+
+    @staticmethod
+    def forward(ctx, x, cfg: RecStackCfg, *params):
+        # params per layer: wh, wz, uh, uz, then (bn_wh.weight, bn_wh.bias, bn_wz.weight, bn_wz.bias) if
+        # use_bn else (wh.bias, wz.bias)
+        if not x.is_cuda:
+            raise RuntimeError("pytorch-kaldi_b200: liGRU needs CUDA tensors (there is no CPU fallback)")
+        dev = x.device
+        T, B, D0 = x.shape
+        TB = T * B
+        ldt = pad8(TB)
+        ndir = 2 if cfg.bidir else 1
+        need_grad = any(ctx.needs_input_grad)
+        f32 = dict(device=dev, dtype=torch.float32)
+        f16 = dict(device=dev, dtype=torch.float16)
+
+        saved = []  # per layer dict of tensors needed by backward
+        pi = 0
+        xsrc, ldx = _rows_view(x, T, B)
+        D = D0
+        X16 = XT16 = None
+        y32 = None
+        for li, L in enumerate(cfg.layers):
+            H = L.H
+            wh, wz, uh, uz = params[pi:pi + 4]
+            pi += 4
+            if L.use_bn:
+                g_h, b_h, g_z, b_z = params[pi:pi + 4]
+                pi += 4
+            else:
+                bias_h, bias_z = params[pi:pi + 2]
+                pi += 2
+            C2 = 2 * H
+            ldD = pad8(D)
+            # ---- operands: fp16 copies of the layer input and of the stacked projection weights
+            if li == 0:
+                X16 = torch.empty(TB, ldD, **f16)
+                XT16 = torch.empty(D, ldt, **f16) if need_grad else None
+                pk.transpose_f32(xsrc, ldx, TB, D, outT16=XT16, ldo16=ldt, in16=X16, ldi16=ldD)
+            Wcat = torch.cat([wh, wz], 0).contiguous()
+            W16 = torch.empty(C2, ldD, **f16)
+            ld2H = pad8(C2)
+            WT16 = torch.empty(D, ld2H, **f16) if need_grad else None
+            pk.transpose_f32(Wcat, D, C2, D, outT16=WT16, ldo16=ld2H, in16=W16, ldi16=ldD)
+            # ---- projection PT = [Wh;Wz] X^T (channel-major) with BatchNorm statistics in the epilogue
+            PT = torch.empty(C2, ldt, **f32)
+            bn_train = L.use_bn and L.bn_training
+            stats = torch.zeros(C2, 2, device=dev, dtype=torch.float64) if bn_train else None
+            pk.gemm_tn(W16, X16, PT, C2, TB, D, lda=ldD, ldb=ldD, ldc=ldt, rowstats=stats)
+            scale = torch.empty(C2, **f32)
+            shift = torch.empty(C2, **f32)
+            mean = torch.empty(C2, **f32) if L.use_bn else None
+            rstd = torch.empty(C2, **f32) if L.use_bn else None
+            if L.use_bn:
+                for gi, (bn, gam, bet) in enumerate(((L.bn_h, g_h, b_h), (L.bn_z, g_z, b_z))):
+                    sl = slice(gi * H, (gi + 1) * H)
+                    pk.bn_finalize(stats[sl] if bn_train else None, H, TB, TB * ndir, gam, bet, bn.eps,
+                                   bn.momentum if bn.momentum is not None else 0.1, bn_train,
+                                   bn.running_mean, bn.running_var, bn.num_batches_tracked if bn_train else None,
+                                   scale[sl], shift[sl], mean[sl], rstd[sl])
+            else:
+                pk.fill_scale_shift(torch.cat([bias_h, bias_z]).contiguous(), C2, scale, shift)
+            # ---- the recurrence: one persistent cluster kernel for all T steps
+            U = torch.cat([uh, uz], 0).contiguous()
+            F = ndir * H
+            last = li == len(cfg.layers) - 1
+            ldF = pad8(F)
+            Y16 = None if last else torch.empty(TB, ldF, **f16)
+            if last:
+                y32 = torch.empty(T, B, F, **f32)
+            HT = torch.empty(F, ldt, **f32) if need_grad else None
+            ZT = torch.empty(F, ldt, **f32) if need_grad else None
+            HCT = torch.empty(F, ldt, **f32) if need_grad else None
+            HT16 = torch.empty(F, ldt, **f16) if (need_grad and not last) else None
+            HP16 = torch.empty(F, ldt, **f16) if need_grad else None
+            pk.rnn_layer_fwd(cfg.cell | cfg.cell_flags, T, B, H, ndir, L.act, PT, ldt, scale, shift, U, L.mask,
+                             L.mask_scalar, y32 if last else None, F, Y16, ldF, HT, HT16, HP16, ZT, HCT, ldt)
+            if need_grad:
+                saved.append(dict(D=D, H=H, XT16=XT16, WT16=WT16, PT=PT if bn_train else None, mean=mean, rstd=rstd,
+                                  gamma=torch.cat([g_h, g_z]).contiguous() if L.use_bn else None,
+                                  HT=HT, ZT=ZT, HCT=HCT, HP16=HP16, U=U, mask=L.mask, mask_scalar=L.mask_scalar,
+                                  act=L.act, use_bn=L.use_bn, bn_train=bn_train))
+            # next layer reads this layer's fp16 outputs directly
+            X16, XT16, D = Y16, HT16, F
+        ctx.cfg = cfg
+        ctx.saved = saved
+        ctx.dims = (T, B, D0, ldt, ndir)
+        ctx.x_needs_grad = ctx.needs_input_grad[0]
+        return y32
+
+    @staticmethod
+    def backward(ctx, dY):
+        cfg, saved = ctx.cfg, ctx.saved
+        T, B, D0, ldt, ndir = ctx.dims
+        TB = T * B
+        dev = dY.device
+        f32 = dict(device=dev, dtype=torch.float32)
+        f16 = dict(device=dev, dtype=torch.float16)
+        grads = []
+        dYT = None
+        dx = None
+        scratch = torch.empty(1, **f32)
+        for li in reversed(range(len(saved))):
+            S = saved[li]
+            H, D = S["H"], S["D"]
+            F, C2 = ndir * H, 2 * H
+            ld2H = pad8(C2)
+            if dYT is None:  # top layer: autograd hands us the row-major gradient of the module output
+                dy2 = dY.reshape(TB, F)
+                if dy2.dtype != torch.float32 or not dy2.is_contiguous():
+                    dy2 = dy2.float().contiguous()
+                dYT = torch.empty(F, ldt, **f32)
+                pk.transpose_f32(dy2, F, TB, F, outT=dYT, ldo=ldt)
+            # power-of-two loss scale for this layer's fp16 gradient operands
+            sc = torch.empty(2, **f32)
+            pk.amax_scale(dYT, ldt, F, TB, 8.0, scratch, sc)
+            GT = torch.empty(ndir, C2, ldt, **f32)
+            GT16 = torch.empty(ndir, C2, ldt, **f16)
+            pk.rnn_layer_bwd(cfg.cell | cfg.cell_flags, T, B, H, ndir, S["act"], dYT, S["HT"], S["ZT"], S["HCT"],
+                             ldt, S["U"], S["mask"], S["mask_scalar"], sc, GT, GT16)
+            inv = sc[1:2]
+            # dU = sum_t G_t^T h_{t-1}  (both directions accumulate into the shared weights)
+            dU = torch.empty(C2, H, **f32)
+            for d in range(ndir):
+                pk.gemm_tn(GT16[d], S["HP16"][d * H:(d + 1) * H], dU, C2, H, TB, lda=ldt, ldb=ldt, ldc=H,
+                           alpha_dev=inv, accumulate=(d > 0), split_k=16)
+            # BatchNorm backward on the de-duplicated projection (both directions folded)
+            dgamma = torch.empty(C2, **f32)
+            dbeta = torch.empty(C2, **f32)
+            need_dx = li > 0 or ctx.x_needs_grad
+            dPT16 = torch.empty(C2, ldt, **f16)
+            dP16 = torch.empty(TB, ld2H, **f16) if need_dx else None
+            sums = torch.empty(2 * C2, device=dev, dtype=torch.float64)
+            pk.bn_bwd(C2, ndir, TB, GT, ldt, S["PT"], ldt, S["use_bn"], S["bn_train"], S["mean"], S["rstd"],
+                      S["gamma"], sc, dgamma, dbeta, dPT16, ldt, dP16, ld2H, sums)
+            # dW = dP^T X
+            dW = torch.empty(C2, D, **f32)
+            pk.gemm_tn(dPT16, S["XT16"], dW, C2, D, TB, lda=ldt, ldb=ldt, ldc=D, alpha_dev=inv, split_k=8)
+            lg = [dW[:H], dW[H:], dU[:H], dU[H:]]
+            if S["use_bn"]:
+                lg += [dgamma[:H], dbeta[:H], dgamma[H:], dbeta[H:]]
+            else:
+                lg += [dbeta[:H], dbeta[H:]]
+            grads = lg + grads
+            # gradient w.r.t. the layer input
+            if li > 0:
+                dXT = torch.empty(D, ldt, **f32)
+                pk.gemm_tn(S["WT16"], dP16, dXT, D, TB, C2, lda=ld2H, ldb=ld2H, ldc=ldt, alpha_dev=inv)
+                dYT = dXT
+            elif ctx.x_needs_grad:
+                dx = torch.empty(T, B, D, **f32)
+                pk.gemm_tn(dP16, S["WT16"], dx, TB, D, C2, lda=ld2H, ldb=ld2H, ldc=D, alpha_dev=inv)
+        ctx.saved = None
+        return (dx, None, *grads)
+
+
+class LinearLogSoftmaxFn(torch.autograd.Function):
+    """MLP layer `LogSoftmax(W x + b)` — the senone head (neural_networks.py:138-148 with
+    dnn_act=softmax, :53-54).  Input [N,F] row-major fp32, output log-posteriors [N,S]."""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        if not x.is_cuda:
+            raise RuntimeError("pytorch-kaldi_b200: MLP needs CUDA tensors (there is no CPU fallback)")
+        dev = x.device
+        N, F = x.shape
+        S = W.shape[0]
+        f32 = dict(device=dev, dtype=torch.float32)
+        f16 = dict(device=dev, dtype=torch.float16)
+        need_grad = any(ctx.needs_input_grad)
+        ldF, ldn, ldS = pad8(F), pad8(N), pad8(S)
+        x2 = x if (x.dtype == torch.float32 and x.stride(1) == 1) else x.float().contiguous()
+        X16 = torch.empty(N, ldF, **f16)
+        XT16 = torch.empty(F, ldn, **f16) if ctx.needs_input_grad[1] else None
+        pk.transpose_f32(x2, x2.stride(0), N, F, outT16=XT16, ldo16=ldn, in16=X16, ldi16=ldF)
+        Wc = W.contiguous()
+        W16 = torch.empty(S, ldF, **f16)
+        WT16 = torch.empty(F, ldS, **f16) if ctx.needs_input_grad[0] else None
+        pk.transpose_f32(Wc, F, S, F, outT16=WT16, ldo16=ldS, in16=W16, ldi16=ldF)
+        logp = torch.empty(N, S, **f32)
+        pk.gemm_tn(X16, W16, logp, N, S, F, lda=ldF, ldb=ldF, ldc=S, bias=b.contiguous() if b is not None else None,
+                   bias_mode=1)
+        pk.logsoftmax_nll(N, S, logp, S, None, None)
+        if need_grad:
+            ctx.save_for_backward(logp)
+            ctx.aux = (XT16, WT16, N, F, S, b is not None)
+        return logp
+
+    @staticmethod
+    def backward(ctx, dlogp):
+        (logp,) = ctx.saved_tensors
+        XT16, WT16, N, F, S, has_bias = ctx.aux
+        dev = logp.device
+        f32 = dict(device=dev, dtype=torch.float32)
+        f16 = dict(device=dev, dtype=torch.float16)
+        ldn, ldS = pad8(N), pad8(S)
+        dl = dlogp if (dlogp.dtype == torch.float32 and dlogp.is_contiguous()) else dlogp.float().contiguous()
+        sc = torch.empty(2, **f32)
+        pk.amax_scale(dl, S, N, S, 8.0, torch.empty(1, **f32), sc)
+        d16 = torch.empty(N, ldS, **f16) if ctx.needs_input_grad[0] else None
+        dT16 = torch.empty(S, ldn, **f16) if ctx.needs_input_grad[1] else None
+        db = torch.empty(S, **f32) if (has_bias and ctx.needs_input_grad[2]) else None
+        rowsum = torch.empty(N, **f32)
+        pk.logsoftmax_bwd(N, S, logp, S, None, dl, S, 1.0, 1.0, sc, d16, ldS, dT16, ldn, db, rowsum)
+        inv = sc[1:2]
+        dx = dW = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(N, F, **f32)
+            pk.gemm_tn(d16, WT16, dx, N, F, S, lda=ldS, ldb=ldS, ldc=F, alpha_dev=inv)
+        if ctx.needs_input_grad[1]:
+            dW = torch.empty(S, F, **f32)
+            pk.gemm_tn(dT16, XT16, dW, S, F, N, lda=ldn, ldb=ldn, ldc=F, alpha_dev=inv, split_k=8)
+        return dx, dW, db
+
+
+class HeadNLLFn(torch.autograd.Function):
+    """Fused senone head + cost ops: LogSoftmax(W x + b) -> NLLLoss (mean over all rows) and the
+    frame error count (utils.py:2344-2381) without a separate pass over the [N,S] posteriors in
+    the backward.  Returns (loss, err, logp); `logp` is returned for inspection only (no grad)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, labels):
+        dev = x.device
+        N, F = x.shape
+        S = W.shape[0]
+        f32 = dict(device=dev, dtype=torch.float32)
+        f16 = dict(device=dev, dtype=torch.float16)
+        ldF, ldn, ldS = pad8(F), pad8(N), pad8(S)
+        x2 = x if (x.dtype == torch.float32 and x.stride(1) == 1) else x.float().contiguous()
+        X16 = torch.empty(N, ldF, **f16)
+        XT16 = torch.empty(F, ldn, **f16)
+        pk.transpose_f32(x2, x2.stride(0), N, F, outT16=XT16, ldo16=ldn, in16=X16, ldi16=ldF)
+        Wc = W.contiguous()
+        W16 = torch.empty(S, ldF, **f16)
+        WT16 = torch.empty(F, ldS, **f16)
+        pk.transpose_f32(Wc, F, S, F, outT16=WT16, ldo16=ldS, in16=W16, ldi16=ldF)
+        logp = torch.empty(N, S, **f32)
+        pk.gemm_tn(X16, W16, logp, N, S, F, lda=ldF, ldb=ldF, ldc=S, bias=b.contiguous(), bias_mode=1)
+        acc = torch.empty(2, device=dev, dtype=torch.float64)
+        lab = labels if labels.dtype == torch.int64 else labels.long()
+        lab = lab.contiguous()
+        pk.logsoftmax_nll(N, S, logp, S, lab, acc)
+        loss = (acc[0] / N).float()
+        err = (acc[1] / N).float()
+        ctx.save_for_backward(logp, lab)
+        ctx.aux = (XT16, WT16, N, F, S)
+        ctx.mark_non_differentiable(err, logp)
+        return loss, err, logp
+
+    @staticmethod
+    def backward(ctx, dloss, _derr, _dlogp):
+        logp, lab = ctx.saved_tensors
+        XT16, WT16, N, F, S = ctx.aux
+        dev = logp.device
+        f32 = dict(device=dev, dtype=torch.float32)
+        f16 = dict(device=dev, dtype=torch.float16)
+        ldn, ldS = pad8(N), pad8(S)
+        # |dlogits| <= |dloss| / N; dloss stays on the device (no host sync): it rides along as the
+        # kernel's device-side scale factor, a host-side power of two centres 1/N near 2^8
+        gcoef = 1.0 / N
+        out_scale = 2.0 ** (8 - math.ceil(math.log2(gcoef)))
+        dl = dloss.reshape(1).float().contiguous()
+        d16 = torch.empty(N, ldS, **f16)
+        dT16 = torch.empty(S, ldn, **f16)
+        db = torch.empty(S, **f32)
+        pk.logsoftmax_bwd(N, S, logp, S, lab, None, 0, gcoef, out_scale, dl, d16, ldS, dT16, ldn, db, None)
+        db = db * dl  # the kernel's bias gradient excludes the device-side factor
+        dx = torch.empty(N, F, **f32)
+        pk.gemm_tn(d16, WT16, dx, N, F, S, lda=ldS, ldb=ldS, ldc=F, alpha=1.0 / out_scale)
+        dW = torch.empty(S, F, **f32)
+        pk.gemm_tn(dT16, XT16, dW, S, F, N, lda=ldn, ldb=ldn, ldc=F, alpha=1.0 / out_scale, split_k=8)
+        return dx, dW, db, None
+
+
+def mlp_forward(module, x):
+    """General MLP stack (hidden layers with BatchNorm / LayerNorm / activation / dropout,
+    reference neural_networks.py:130-150).  Dense layers share the projection GEMM + fused
+    epilogue path of the recurrent layers; until that path is wired for hidden layers this
+    raises instead of silently running eager PyTorch."""
+    raise NotImplementedError(
+        "pytorch-kaldi_b200.MLP: only the single-layer softmax head runs natively in this build "
+        "(hidden-layer stacks: next scope row); there is no eager fallback")

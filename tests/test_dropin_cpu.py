@@ -1,0 +1,92 @@
+"""CPU tests of the drop-in boundary: the classes of pytorch-kaldi_b200/neural_networks.py must
+register exactly what the reference constructors register (state_dict keys / shapes / order / values
+under a fixed seed, parameter order, generator consumption, out_dim), must refuse CPU tensors loudly,
+and the C-ABI library must load and export every symbol include/pk_b200.h declares."""
+import ctypes
+import hashlib
+import json
+import os
+import re
+
+import pytest
+import torch
+
+import neural_networks as pknn
+import pk_native
+from structure_cases import CASES
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "structure.json")))
+
+
+def digest(t):
+    return hashlib.sha256(t.detach().contiguous().numpy().tobytes()).hexdigest()[:16]
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_constructor_matches_reference(name):
+    cls, opts, inp_dim = CASES[name]
+    ref = GOLD[name]
+    torch.manual_seed(1234)
+    m = getattr(pknn, cls)(dict(opts), inp_dim)
+    assert int(m.out_dim) == ref["out_dim"]
+    got = [[k, list(v.shape), str(v.dtype), digest(v)] for k, v in m.state_dict().items()]
+    assert [g[:3] for g in got] == [r[:3] for r in ref["keys"]], "state_dict keys/shapes/order differ"
+    bad = [g[0] for g, r in zip(got, ref["keys"]) if g[3] != r[3]]
+    assert not bad, f"initial values differ from the reference for {bad[:5]}"
+    assert [[k, list(p.shape)] for k, p in m.named_parameters()] == ref["params"]
+    # the constructors consumed the CPU generator exactly like the reference's
+    assert float(torch.rand(1).item()) == ref["next_rand"]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference checkout not present")
+def test_live_reference_state_dict_roundtrip():
+    """A checkpoint written by the reference loads into the drop-in and vice versa (core.py:531, :715)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("ref_neural_networks", "/root/reference/neural_networks.py")
+    ref_nn = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_nn)
+    cls, opts, inp_dim = CASES["ligru_timit"]
+    torch.manual_seed(7)
+    a = ref_nn.liGRU(dict(opts), inp_dim)
+    torch.manual_seed(8)
+    b = pknn.liGRU(dict(opts), inp_dim)
+    b.load_state_dict(a.state_dict())
+    for (ka, va), (kb, vb) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert ka == kb and torch.equal(va, vb)
+    opt_a = torch.optim.RMSprop(a.parameters(), lr=0.0004, alpha=0.95, eps=1e-8)
+    opt_b = torch.optim.RMSprop(b.parameters(), lr=0.0004, alpha=0.95, eps=1e-8)
+    opt_b.load_state_dict(opt_a.state_dict())  # index-ordered param groups line up
+
+
+def test_cpu_tensors_are_refused_loudly():
+    cls, opts, inp_dim = CASES["ligru_uni_nobn"]
+    m = pknn.liGRU(dict(opts), inp_dim)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(4, 2, inp_dim))
+    h = pknn.MLP(dict(CASES["mlp_head"][1]), 110)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        h(torch.zeros(3, 110))
+
+
+def test_unsupported_options_raise():
+    for name in ("LSTM_cudnn", "GRU_cudnn", "RNN_cudnn"):
+        with pytest.raises(NotImplementedError):
+            getattr(pknn, name)({}, 3)
+
+
+def test_abi_library_loads_and_exports_every_declared_symbol():
+    """No compute calls here (no GPU in this container): only dlopen + symbol resolution."""
+    header = open(os.path.join(ROOT, "include", "pk_b200.h")).read()
+    declared = set(re.findall(r"\b(pk_[a-z0-9_]+)\s*\(", header))
+    assert {"pk_gemm_tn", "pk_rnn_layer_fwd", "pk_rnn_layer_bwd", "pk_logsoftmax_nll"} <= declared
+    assert os.path.exists(pk_native.LIB_PATH), "build the library first: python -c 'import __graft_entry__ as g; g.build()'"
+    lib = ctypes.CDLL(pk_native.LIB_PATH)
+    for sym in sorted(declared):
+        assert hasattr(lib, sym), f"libpk_b200.so does not export {sym}"
+    # every symbol the Python binding declares must be in the header too
+    assert set(pk_native.SIGNATURES) | {"pk_last_error", "pk_version"} == declared
+    L = pk_native.lib()
+    assert L.pk_version() >= 2
+    assert L.pk_last_error() is not None
