@@ -63,6 +63,12 @@ def sigmoid(x):
     return 1.0 / (1.0 + np.exp(-x))
 
 
+def q16(a: np.ndarray) -> np.ndarray:
+    """Round to fp16 and back: emulates the tensor-core OPERAND rounding of the CUDA path (fp32
+    accumulation is kept).  Only used when `quant=True` (see ligru_forward)."""
+    return a.astype(np.float16).astype(a.dtype)
+
+
 def flip0(x: np.ndarray) -> np.ndarray:
     """neural_networks.py:1962-1970 flip(x, 0): time reversal."""
     return x[::-1].copy()
@@ -136,8 +142,12 @@ def batchnorm_bwd(dy, cache):
 # --------------------------------------------------------------------------------------
 
 
-def ligru_forward(x, layers, *, bidir=True, training=True, masks=None):
+def ligru_forward(x, layers, *, bidir=True, training=True, masks=None, quant=False):
     """x [T,B,D] -> [T,B,(2)H_last].
+
+    quant=False is the reference's fp32 algorithm.  quant=True rounds every GEMM operand (inputs,
+    weights, recurrent state) to fp16 exactly where the CUDA path does, so that non-smooth points
+    (ReLU kinks) fall on the same side in both and gradients can be compared tightly.
 
     layers: list of dicts with keys
         wh, wz   [H,D]   (nn.Linear weights, :1054-1059)      bh, bz [H] or None (bias only when no BN/LN)
@@ -162,8 +172,11 @@ def ligru_forward(x, layers, *, bidir=True, training=True, masks=None):
             mask = masks[li].astype(x.dtype)
         else:
             mask = np.asarray(1.0 - L["drop"], dtype=x.dtype)  # :1107
-        wh_out = x2 @ L["wh"].T  # :1114
-        wz_out = x2 @ L["wz"].T  # :1115
+        Q = q16 if quant else (lambda a: a)
+        x2q = Q(x2)
+        wh_q, wz_q, uh_q, uz_q = Q(L["wh"]), Q(L["wz"]), Q(L["uh"]), Q(L["uz"])
+        wh_out = x2q @ wh_q.T  # :1114
+        wz_out = x2q @ wz_q.T  # :1115
         if L.get("bh") is not None:
             wh_out = wh_out + L["bh"]
             wz_out = wz_out + L["bz"]
@@ -178,8 +191,9 @@ def ligru_forward(x, layers, *, bidir=True, training=True, masks=None):
         zs = np.zeros_like(hs)
         ats = np.zeros_like(hs)
         for k in range(T):  # :1130-1141
-            zt = sigmoid(wz_out[k] + ht @ L["uz"].T)
-            at = wh_out[k] + ht @ L["uh"].T
+            htq = Q(ht)
+            zt = sigmoid(wz_out[k] + htq @ uz_q.T)
+            at = wh_out[k] + htq @ uh_q.T
             hcand = act_fwd(L["act"], at) * mask
             ht = zt * ht + (1 - zt) * hcand
             hs[k], zs[k], ats[k] = ht, zt, at
@@ -189,8 +203,8 @@ def ligru_forward(x, layers, *, bidir=True, training=True, masks=None):
             out = np.concatenate([h_f, h_b], axis=2)
         else:
             out = hs
-        caches.append(dict(x2=x2, hs=hs, zs=zs, ats=ats, mask=mask, bn_h=bn_cache_h, bn_z=bn_cache_z, B=B,
-                           xin_shape=xin.shape))
+        caches.append(dict(x2=x2q, hs=hs, zs=zs, ats=ats, mask=mask, bn_h=bn_cache_h, bn_z=bn_cache_z, B=B,
+                           xin_shape=xin.shape, wq=(wh_q, wz_q, uh_q, uz_q), Q=Q))
         x = out
     return x, caches
 
@@ -203,6 +217,8 @@ def ligru_backward(dout, layers, caches, *, bidir=True):
         L, c = layers[li], caches[li]
         x2, hs, zs, ats, mask, B = c["x2"], c["hs"], c["zs"], c["ats"], c["mask"], c["B"]
         T, R, H = hs.shape
+        wh_q, wz_q, uh_q, uz_q = c["wq"]
+        Q = c["Q"]
         if bidir:
             dH = np.concatenate([dout[:, :, :H], flip0(dout[:, :, H:])], axis=1)
         else:
@@ -222,9 +238,9 @@ def ligru_backward(dout, layers, caches, *, bidir=True):
             dhc = dh * (1 - zt)
             da = dhc * mask * act_bwd(L["act"], at, y)
             dzp = dzt * zt * (1 - zt)
-            carry = dh * zt + da @ L["uh"] + dzp @ L["uz"]
-            duh += da.T @ hprev
-            duz += dzp.T @ hprev
+            carry = dh * zt + da @ uh_q + dzp @ uz_q
+            duh += da.T @ Q(hprev)
+            duz += dzp.T @ Q(hprev)
             da_all[k], dz_all[k] = da, dzp
         g = dict(uh=duh, uz=duz)
         dwh_pre = da_all.reshape(T * R, H)
@@ -238,7 +254,7 @@ def ligru_backward(dout, layers, caches, *, bidir=True):
         x2f = x2.reshape(T * R, -1)
         g["wh"] = dwh_pre.T @ x2f
         g["wz"] = dwz_pre.T @ x2f
-        dx2 = (dwh_pre @ L["wh"] + dwz_pre @ L["wz"]).reshape(T, R, -1)
+        dx2 = (dwh_pre @ wh_q + dwz_pre @ wz_q).reshape(T, R, -1)
         if bidir:
             dout = dx2[:, :B] + flip0(dx2[:, B:])
         else:
@@ -259,13 +275,15 @@ def log_softmax(x):
     return x - m - np.log(e.sum(axis=1, keepdims=True))
 
 
-def mlp_forward(x, layers, *, training=True, drop_masks=None):
+def mlp_forward(x, layers, *, training=True, drop_masks=None, quant=False):
     """x [N,D].  layers: dicts(w [O,I], b [O], bn (dict|None), ln (dict(gamma,beta)|None), act, drop).
     Order per layer: drop(act(bn(ln(w x + b))))  (neural_networks.py:138-148).
     drop_masks: per-layer keep masks (nn.Dropout inverted scaling applied here) or None."""
     caches = []
     for li, L in enumerate(layers):
-        lin = x @ L["w"].T + L["b"]
+        Q = q16 if quant else (lambda a: a)
+        xq, wq = Q(x), Q(L["w"])
+        lin = xq @ wq.T + L["b"]
         pre = lin
         ln_cache = bn_cache = None
         if L.get("ln") is not None:
@@ -282,7 +300,7 @@ def mlp_forward(x, layers, *, training=True, drop_masks=None):
             out = y * keep
         else:
             out = y
-        caches.append(dict(x=x, pre=pre, y=y, keep=keep, ln=ln_cache, bn=bn_cache))
+        caches.append(dict(x=xq, wq=wq, pre=pre, y=y, keep=keep, ln=ln_cache, bn=bn_cache))
         x = out
     return x, caches
 
@@ -303,7 +321,7 @@ def mlp_backward(dout, layers, caches):
             d, g["ln_gamma"], g["ln_beta"] = layernorm_bwd(d, c["ln"])
         g["w"] = d.T @ c["x"]
         g["b"] = d.sum(0)
-        dout = d @ L["w"]
+        dout = d @ c["wq"]
         grads[li] = g
     return dout, grads
 
@@ -352,17 +370,17 @@ def sgd_step(p, g, lr=0.08):
 # --------------------------------------------------------------------------------------
 
 
-def ligru_model_step(x, labels, ligru_layers, heads, *, masks, bidir=True, loss_weights=None):
+def ligru_model_step(x, labels, ligru_layers, heads, *, masks, bidir=True, loss_weights=None, quant=False):
     """x [T,B,D], labels: list of [T*B] int arrays (one per head, t-major rows utils.py:2323).
     heads: list of single-layer softmax MLP layer dicts.  Returns dict(loss, losses, err, logp, grads)."""
-    out, caches = ligru_forward(x, ligru_layers, bidir=bidir, training=True, masks=masks)
+    out, caches = ligru_forward(x, ligru_layers, bidir=bidir, training=True, masks=masks, quant=quant)
     T, B, F = out.shape
     flat = out.reshape(T * B, F)
     dflat = np.zeros_like(flat)
     losses, logps, hgrads = [], [], []
     lw = loss_weights or [1.0] * len(heads)
     for hd, lab, w in zip(heads, labels, lw):
-        logp, hc = mlp_forward(flat, [hd], training=True)
+        logp, hc = mlp_forward(flat, [hd], training=True, quant=quant)
         losses.append(nll_loss(logp, lab))
         logps.append(logp)
         dlogp = nll_loss_bwd(logp, lab, w)

@@ -20,6 +20,19 @@ pytestmark = pytest.mark.gpu
 
 TOL_FWD = 1e-3
 TOL_GRAD = 5e-3
+# Gradients through a ReLU-family recurrence are only piecewise smooth: the fp16-operand recurrent GEMM
+# perturbs pre-activations by ~1e-3 relative, which flips act'(a) for the ~0.1 % of (unit, step) entries with
+# a ~ 0, and each flip changes that entry's gradient by O(1).  Against the fp32 reference such fixtures are
+# therefore held to an L2 bound; the exact backward math is pinned by the quantisation-matched oracle tests
+# below (same operand rounding -> same side of every kink -> TOL_GRAD).
+TOL_GRAD_KINK_L2 = 0.10
+KINK_ACTS = ("relu", "leaky_relu")
+
+
+def rel_l2(got, ref):
+    got = np.asarray(got, dtype=np.float64).reshape(-1)
+    ref = np.asarray(ref, dtype=np.float64).reshape(-1)
+    return float(np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-30))
 
 
 def _mods():
@@ -128,7 +141,15 @@ def test_gradients_match_reference(name):
             if p.grad is None:
                 assert key not in d and key + ".idx" not in d, f"{key}: reference has a gradient, we do not"
                 continue
-            gu.check_tensor(d, key, p.grad.detach().cpu().numpy(), TOL_GRAD)
+            g = p.grad.detach().cpu().numpy()
+            if prefix == "ligru" and d["meta"]["act"] in KINK_ACTS and max(d["meta"]["lay"]) > 32:
+                kind, ref = gu.grad_entry(d, key)
+                if kind == "full":
+                    assert rel_l2(g, ref) < TOL_GRAD_KINK_L2, key
+                else:
+                    assert rel_l2(g.reshape(-1)[ref[0]], ref[1]) < TOL_GRAD_KINK_L2, key
+            else:
+                gu.check_tensor(d, key, g, TOL_GRAD)
     # BatchNorm running statistics (unbiased variance over the T*2B rows the reference normalised)
     if d["meta"]["bn"]:
         sd = net.state_dict()
@@ -178,12 +199,15 @@ def test_fused_head_nll_matches_reference():
         assert gu.relerr(g.cpu().numpy(), r.cpu().numpy()) < TOL_GRAD
 
 
-def test_against_oracle_medium():
-    """Seeded random problem at a size the numpy oracle finishes in seconds: 2 x 550 bidirectional."""
+@pytest.mark.parametrize("act,quant", [("relu", True), ("tanh", False), ("tanh", True)])
+def test_against_oracle_medium(act, quant):
+    """Seeded random problem at a size the numpy oracle finishes in seconds: 2 x 550 bidirectional.
+    relu: against the oracle with the SAME fp16 operand rounding (pins the backward math exactly);
+    tanh (smooth): also against the plain fp32 algorithm."""
     import pk_oracle as orc
     pknn = _mods()
     T, B, D, H, S = 24, 8, 40, 550, 200
-    meta = dict(lay=[H, H], drop=0.2, bn=True, bidir=True, act="relu", D=D)
+    meta = dict(lay=[H, H], drop=0.2, bn=True, bidir=True, act=act, D=D)
     torch.manual_seed(5)
     net = pknn.liGRU(ligru_opts(meta), D)
     head = pknn.MLP(head_opts(S), net.out_dim)
@@ -198,7 +222,7 @@ def test_against_oracle_medium():
     for i in range(2):
         layers.append(dict(
             wh=sd[f"wh.{i}.weight"], wz=sd[f"wz.{i}.weight"], uh=sd[f"uh.{i}.weight"], uz=sd[f"uz.{i}.weight"],
-            bh=None, bz=None, act="relu", drop=0.2,
+            bh=None, bz=None, act=act, drop=0.2,
             bn_wh=dict(weight=sd[f"bn_wh.{i}.weight"], bias=sd[f"bn_wh.{i}.bias"], running_mean=np.zeros(H),
                        running_var=np.ones(H), eps=1e-5, momentum=0.05),
             bn_wz=dict(weight=sd[f"bn_wz.{i}.weight"], bias=sd[f"bn_wz.{i}.bias"], running_mean=np.zeros(H),
@@ -206,7 +230,7 @@ def test_against_oracle_medium():
     hd = dict(w=head.wx[0].weight.detach().numpy().astype(np.float64),
               b=head.wx[0].bias.detach().numpy().astype(np.float64), bn=None, ln=None, act="softmax", drop=0.0)
     ref = orc.ligru_model_step(x.numpy().astype(np.float64), [lab.numpy()], layers, [hd],
-                               masks=[mk.numpy() for mk in masks], bidir=True)
+                               masks=[mk.numpy() for mk in masks], bidir=True, quant=quant)
     net.cuda().train()
     head.cuda().train()
     net._mask = lambda i, rows, Hh, dev: (masks[i].to(dev), 1.0)
@@ -220,6 +244,10 @@ def test_against_oracle_medium():
         for k in ("wh", "wz", "uh", "uz"):
             got = getattr(net, k)[i].weight.grad.cpu().numpy()
             assert gu.relerr(got, ref["ligru_grads"][i][k]) < TOL_GRAD, (i, k)
+        for gate in ("wh", "wz"):
+            bn = getattr(net, "bn_" + gate)[i]
+            assert gu.relerr(bn.weight.grad.cpu().numpy(), ref["ligru_grads"][i][f"bn_{gate}_weight"]) < TOL_GRAD
+            assert gu.relerr(bn.bias.grad.cpu().numpy(), ref["ligru_grads"][i][f"bn_{gate}_bias"]) < TOL_GRAD
     assert gu.relerr(head.wx[0].weight.grad.cpu().numpy(), ref["head_grads"][0]["w"]) < TOL_GRAD
 
 
