@@ -240,38 +240,56 @@ def test_against_oracle_medium(act, quant):
     loss.backward()
     assert gu.relerr(logp.detach().cpu().numpy(), ref["logp"][0]) < TOL_FWD
     assert abs(loss.item() - ref["loss"]) / ref["loss"] < TOL_FWD
+    # relu: accumulation-order differences (~1e-6) can still flip an isolated kink, which moves ONE row of a
+    # weight gradient by percents; the L2 metric is robust to that, the max metric gets a wider bound
+    tol_max = 10 * TOL_GRAD if act in KINK_ACTS else TOL_GRAD
+
+    def close(got, want, what):
+        assert rel_l2(got, want) < TOL_GRAD, what
+        assert gu.relerr(got, want) < tol_max, what
+
     for i in range(2):
         for k in ("wh", "wz", "uh", "uz"):
-            got = getattr(net, k)[i].weight.grad.cpu().numpy()
-            assert gu.relerr(got, ref["ligru_grads"][i][k]) < TOL_GRAD, (i, k)
+            close(getattr(net, k)[i].weight.grad.cpu().numpy(), ref["ligru_grads"][i][k], (i, k))
         for gate in ("wh", "wz"):
             bn = getattr(net, "bn_" + gate)[i]
-            assert gu.relerr(bn.weight.grad.cpu().numpy(), ref["ligru_grads"][i][f"bn_{gate}_weight"]) < TOL_GRAD
-            assert gu.relerr(bn.bias.grad.cpu().numpy(), ref["ligru_grads"][i][f"bn_{gate}_bias"]) < TOL_GRAD
-    assert gu.relerr(head.wx[0].weight.grad.cpu().numpy(), ref["head_grads"][0]["w"]) < TOL_GRAD
+            close(bn.weight.grad.cpu().numpy(), ref["ligru_grads"][i][f"bn_{gate}_weight"], (i, gate, "gamma"))
+            close(bn.bias.grad.cpu().numpy(), ref["ligru_grads"][i][f"bn_{gate}_bias"], (i, gate, "beta"))
+    close(head.wx[0].weight.grad.cpu().numpy(), ref["head_grads"][0]["w"], "head")
 
 
 def test_full_size_time_reversal_property():
-    """BASELINE config 2 shape (500 x 32 x 40 -> 5 x 550 bidirectional).  Both directions share the
-    weights (reference :1095-1097), so in eval mode  y(flip(x))[..., :H] == flip(y(x)[..., H:])  bit for bit,
-    and the forward pass is deterministic."""
+    """BASELINE config 2 shape (500 x 32 x 40 -> 550 bidirectional).  Both directions share the weights
+    (reference :1095-1097), so in eval mode a time-flipped chunk must give the time-flipped output with the
+    direction halves swapped.  One layer: bit for bit (and the forward pass is deterministic).  Five layers: the
+    same holds once the next layers' input columns for the two halves are swapped as well (then only the fp32
+    accumulation order differs)."""
+    import copy
     pknn = _mods()
     T, B, D, H = 500, 32, 40, 550
-    meta = dict(lay=[H] * 5, drop=0.2, bn=True, bidir=True, act="relu", D=D)
-    torch.manual_seed(1)
-    opts = ligru_opts(meta)
-    opts["to_do"] = "valid"
-    net = pknn.liGRU(opts, D).cuda().eval()
-    x = torch.randn(T, B, D, device="cuda")
-    with torch.no_grad():
-        y1 = net(x)
-        y1b = net(x)
-        y2 = net(torch.flip(x, dims=[0]))
-    assert y1.shape == (T, B, 2 * H)
-    assert torch.isfinite(y1).all()
-    assert torch.equal(y1, y1b)
-    assert torch.equal(y2[:, :, :H], torch.flip(y1[:, :, H:], dims=[0]))
-    assert torch.equal(y2[:, :, H:], torch.flip(y1[:, :, :H], dims=[0]))
+    x = torch.randn(T, B, D, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
+    for nlay in (1, 5):
+        meta = dict(lay=[H] * nlay, drop=0.2, bn=True, bidir=True, act="relu", D=D)
+        torch.manual_seed(1)
+        opts = ligru_opts(meta)
+        opts["to_do"] = "valid"
+        net = pknn.liGRU(opts, D).cuda().eval()
+        net2 = copy.deepcopy(net)
+        with torch.no_grad():
+            for i in range(1, nlay):
+                for w in (net2.wh[i].weight, net2.wz[i].weight):
+                    w.copy_(torch.cat([w[:, H:], w[:, :H]], dim=1))
+            y1 = net(x)
+            y1b = net(x)
+            y2 = net2(torch.flip(x, dims=[0]))
+        assert y1.shape == (T, B, 2 * H)
+        assert torch.isfinite(y1).all()
+        assert torch.equal(y1, y1b)
+        want = torch.flip(torch.cat([y1[:, :, H:], y1[:, :, :H]], dim=2), dims=[0])
+        if nlay == 1:
+            assert torch.equal(y2, want)
+        else:
+            assert (y2 - want).abs().max().item() <= 1e-3 * want.abs().max().item()
 
 
 def test_full_size_training_step_runs_and_learns():
