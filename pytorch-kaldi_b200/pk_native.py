@@ -69,9 +69,20 @@ def lib():
     return _lib
 
 
-def _check(rc, what):
+# kernels launched by this library since import (bench.py reports it as gpu_launches); the
+# numbers are the __global__ launches each C entry point performs (memsets are not counted)
+launch_count = 0
+KERNELS_PER_CALL = {"pk_gemm_tn": 1, "pk_transpose_f32": 1, "pk_convert_f16": 1, "pk_amax_scale": 2,
+                    "pk_bn_finalize": 1, "pk_fill_scale_shift": 1, "pk_bn_bwd": 2, "pk_rnn_layer_fwd": 1,
+                    "pk_rnn_layer_bwd": 1, "pk_logsoftmax_nll": 1, "pk_logsoftmax_bwd": 1, "pk_rmsprop_step": 1,
+                    "pk_sgd_step": 1}
+
+
+def _check(rc, what, extra_kernels=0):
+    global launch_count
     if rc != 0:
         raise RuntimeError(f"{what} failed (rc={rc}): {lib().pk_last_error().decode()}")
+    launch_count += KERNELS_PER_CALL[what] + extra_kernels
 
 
 def _ptr(t):
@@ -156,7 +167,8 @@ def logsoftmax_bwd(N, S, logp, ld, labels, dlogp, lddl, gcoef, out_scale, scale_
                    rowsum_scratch):
     _check(lib().pk_logsoftmax_bwd(N, S, _ptr(logp), ld, _ptr(labels), _ptr(dlogp), lddl, float(gcoef),
                                    float(out_scale), _ptr(scale_dev), _ptr(d16), ld16, _ptr(dT16), ld16t,
-                                   _ptr(dbias), _ptr(rowsum_scratch), _stream()), "pk_logsoftmax_bwd")
+                                   _ptr(dbias), _ptr(rowsum_scratch), _stream()), "pk_logsoftmax_bwd",
+           1 if dlogp is not None else 0)
 
 
 def rmsprop_step(p, g, v, lr, alpha, eps, gscale=1.0):

@@ -1,0 +1,79 @@
+"""Training-step glue for the drop-in modules: flat parameter / gradient buffers, ONE gradient
+allreduce per step (NCCL over NVLink when world_size > 1) and ONE fused optimizer kernel.
+
+Mirrors what core.run_nn does per minibatch (reference core.py:616-642): forward_model ->
+zero_grad -> loss.backward() -> optimizer.step(), and replaces torch.nn.DataParallel
+(core.py:537-538) by one process per GPU with utterance columns sharded across ranks
+(SURVEY.md 8e).  The optimizer math is torch.optim.RMSprop / SGD as configured by
+utils.optimizer_init (utils.py:2106-2164).
+"""
+from __future__ import annotations
+
+from typing import Iterable, List
+
+import torch
+import torch.distributed as dist
+
+import pk_native as pk
+
+
+class FlatTrainer:
+    """Re-homes the parameters of `modules` into one contiguous fp32 buffer (and their gradients
+    into another), so that a step is: backward -> (allreduce of the flat gradient) -> one
+    rmsprop/sgd kernel over the flat buffers.  state_dict()/load_state_dict() of the modules keep
+    working (parameters stay nn.Parameters, only their storage moves)."""
+
+    def __init__(self, modules: Iterable[torch.nn.Module], opt: str = "rmsprop", lr: float = 0.0004,
+                 alpha: float = 0.95, eps: float = 1e-8):
+        self.modules: List[torch.nn.Module] = list(modules)
+        self.params = [p for m in self.modules for p in m.parameters()]
+        if not self.params or not self.params[0].is_cuda:
+            raise RuntimeError("FlatTrainer needs CUDA modules (no CPU path)")
+        dev = self.params[0].device
+        n = sum(p.numel() for p in self.params)
+        self.flat_p = torch.empty(n, device=dev, dtype=torch.float32)
+        self.flat_g = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.flat_v = torch.zeros(n, device=dev, dtype=torch.float32) if opt == "rmsprop" else None
+        off = 0
+        for p in self.params:
+            k = p.numel()
+            self.flat_p[off:off + k].copy_(p.data.reshape(-1))
+            p.data = self.flat_p[off:off + k].view_as(p)
+            p.grad = self.flat_g[off:off + k].view_as(p)
+            off += k
+        self.n = n
+        self.opt, self.lr, self.alpha, self.eps = opt, lr, alpha, eps
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    def zero_grad(self):
+        self.flat_g.zero_()
+
+    def step(self):
+        """(allreduce) + optimizer.  Gradients are summed across ranks and scaled by 1/world inside the
+        optimizer kernel, i.e. the loss is the mean over the global batch (equal shard sizes)."""
+        if self.world > 1:
+            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)
+        gscale = 1.0 / self.world
+        if self.opt == "rmsprop":
+            pk.rmsprop_step(self.flat_p, self.flat_g, self.flat_v, self.lr, self.alpha, self.eps, gscale)
+        elif self.opt == "sgd":
+            pk.sgd_step(self.flat_p, self.flat_g, self.lr, gscale)
+        else:
+            raise NotImplementedError(self.opt)
+
+
+def chunk_step(net, head, trainer: FlatTrainer, inp: torch.Tensor, n_fea: int):
+    """One minibatch as core.run_nn + utils.forward_model run it: `inp` is the reference's chunk
+    layout [T, B, n_fea + 1] with the label in the last column stored as float (data_io.py:272,
+    utils.py:2305-2352).  Returns (loss, err) as device scalars."""
+    T, B, _ = inp.shape
+    lab = inp[:, :, n_fea].reshape(-1).long()          # utils.py:2348-2352
+    x = inp[:, :, :n_fea]                              # utils.py:2321 (a strided view; no copy)
+    trainer.zero_grad()
+    out = net(x)                                       # out_dnn1 = compute(liGRU_layers, fea)
+    logp = head(out.view(T * B, -1))                   # out_dnn2 = compute(MLP_layers, out_dnn1)
+    loss = torch.nn.functional.nll_loss(logp, lab)     # loss_final = cost_nll(out_dnn2, lab_cd)
+    err = (logp.detach().max(dim=1)[1] != lab).float().mean()  # err_final = cost_err(out_dnn2, lab_cd)
+    loss.backward()
+    trainer.step()
+    return loss.detach(), err
