@@ -24,10 +24,14 @@ class FlatTrainer:
     working (parameters stay nn.Parameters, only their storage moves)."""
 
     def __init__(self, modules: Iterable[torch.nn.Module], opt: str = "rmsprop", lr: float = 0.0004,
-                 alpha: float = 0.95, eps: float = 1e-8):
+                 alpha: float = 0.95, eps: float = 1e-8, optimizer_fn=None):
+        """optimizer_fn(flat_p, flat_g, flat_v, gscale): test hook that replaces the CUDA optimizer kernel
+        (tests/test_dp_gloo.py runs the buffer / allreduce plumbing on CPU with the oracle's update rule);
+        without it CPU modules are refused."""
         self.modules: List[torch.nn.Module] = list(modules)
         self.params = [p for m in self.modules for p in m.parameters()]
-        if not self.params or not self.params[0].is_cuda:
+        self.optimizer_fn = optimizer_fn
+        if not self.params or (not self.params[0].is_cuda and optimizer_fn is None):
             raise RuntimeError("FlatTrainer needs CUDA modules (no CPU path)")
         dev = self.params[0].device
         n = sum(p.numel() for p in self.params)
@@ -54,7 +58,9 @@ class FlatTrainer:
         if self.world > 1:
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)
         gscale = 1.0 / self.world
-        if self.opt == "rmsprop":
+        if self.optimizer_fn is not None:
+            self.optimizer_fn(self.flat_p, self.flat_g, self.flat_v, gscale)
+        elif self.opt == "rmsprop":
             pk.rmsprop_step(self.flat_p, self.flat_g, self.flat_v, self.lr, self.alpha, self.eps, gscale)
         elif self.opt == "sgd":
             pk.sgd_step(self.flat_p, self.flat_g, self.lr, gscale)
