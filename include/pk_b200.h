@@ -56,6 +56,8 @@ extern "C" {
 /* step synchronisation: default = st.async + mbarrier; this flag selects the
  * barrier.cluster variant (kept for A/B timing) */
 #define PK_REC_SYNC_BARRIER 0x2000
+/* use the non-warp-specialised kernels (A/B timing; they also write the fp32 GT buffer) */
+#define PK_REC_LEGACY 0x4000
 /* timing experiments only (results are incomplete): skip the global stores / loads */
 #define PK_REC_DBG_NOSTORE 0x10000
 #define PK_REC_DBG_NOLOAD 0x20000
@@ -105,10 +107,10 @@ int pk_fill_scale_shift(const float* bias, int C, float* scale, float* shift, vo
 
 /* Backward of the (optional) BatchNorm on the de-duplicated projection.  GT = [ndir][C][ldt]
  * gradients w.r.t. the normalised pre-activations in natural time (both directions are
- * summed), PT = [C][ldp] raw projections.  Outputs dgamma/dbeta [C] (dbeta = bias grad when
+ * summed; pass GT = NULL and GT16 = the fp16 copy scaled by *gscale to read that instead), PT = [C][ldp] raw projections.  Outputs dgamma/dbeta [C] (dbeta = bias grad when
  * use_bn=0) and dP as fp16 * (*gscale) in channel-major (dPT16) and row-major (dP16) form.
  * sums_scratch: 2*C doubles. */
-int pk_bn_bwd(int C, int ndir, int64_t n, const float* GT, int64_t ldt, const float* PT,
+int pk_bn_bwd(int C, int ndir, int64_t n, const float* GT, const void* GT16, int64_t ldt, const float* PT,
               int64_t ldp, int use_bn, int training, const float* mean, const float* rstd,
               const float* gamma, const float* gscale, float* dgamma, float* dbeta, void* dPT16,
               int64_t ld16t, void* dP16, int64_t ld16r, double* sums_scratch, void* stream);
@@ -132,8 +134,9 @@ int pk_rnn_layer_fwd(int cell, int T, int B, int H, int ndir, int act, const flo
                      int64_t ldt, void* stream);
 
 /* Reverse-time persistent kernel: dYT [ndir*H][ldt] channel-major gradient w.r.t. the layer
- * output -> GT [ndir][G*H][ldt] fp32 gradients w.r.t. the normalised pre-activations
- * (+ GT16 = fp16 * (*gscale), the operand of dU = sum_t G_t^T h_{t-1}).
+ * output -> GT16 [ndir][G*H][ldt] = fp16 gradients w.r.t. the normalised pre-activations scaled by
+ * *gscale (operand of dU = sum_t G_t^T h_{t-1} and input of pk_bn_bwd).  GT (fp32, unscaled) is
+ * optional: only the legacy kernels write it.
  * Replaces: autograd through the per-step graph (core.py:634 loss.backward()). */
 int pk_rnn_layer_bwd(int cell, int T, int B, int H, int ndir, int act, const float* dYT,
                      const float* HT, const float* ZT, const float* HCT, int64_t ldt,

@@ -23,13 +23,14 @@ using namespace pk;
 
 namespace {
 struct RecFlags {
-  int cell, cluster, sync, dbg;
+  int cell, cluster, sync, dbg, legacy;
 };
 RecFlags parse_cell(int cell) {
   RecFlags f;
   f.cluster = (cell >> 8) & 0x1f;  // PK_REC_CLUSTER(n)
   f.sync = (cell & PK_REC_SYNC_BARRIER) ? 0 : -1;
   f.dbg = ((cell & PK_REC_DBG_NOSTORE) ? 1 : 0) | ((cell & PK_REC_DBG_NOLOAD) ? 2 : 0);
+  f.legacy = (cell & PK_REC_LEGACY) ? 1 : 0;
   f.cell = cell & PK_CELL_MASK;
   return f;
 }
@@ -90,14 +91,14 @@ int pk_fill_scale_shift(const float* bias, int C, float* scale, float* shift, vo
   return fill_scale_shift(bias, C, scale, shift, static_cast<cudaStream_t>(stream));
 }
 
-int pk_bn_bwd(int C, int ndir, int64_t n, const float* GT, int64_t ldt, const float* PT, int64_t ldp, int use_bn,
+int pk_bn_bwd(int C, int ndir, int64_t n, const float* GT, const void* GT16, int64_t ldt, const float* PT, int64_t ldp, int use_bn,
               int training, const float* mean, const float* rstd, const float* gamma, const float* gscale,
               float* dgamma, float* dbeta, void* dPT16, int64_t ld16t, void* dP16, int64_t ld16r,
               double* sums_scratch, void* stream) {
-  PK_REQUIRE(GT != nullptr, "pk_bn_bwd: null GT");
+  PK_REQUIRE(GT != nullptr || GT16 != nullptr, "pk_bn_bwd: need GT or GT16");
   PK_REQUIRE(!use_bn || (rstd && (!training || (PT && mean))), "pk_bn_bwd: BatchNorm mode needs PT/mean/rstd");
   BnBwdArgs a;
-  a.C = C; a.ndir = ndir; a.n = n; a.GT = GT; a.ldt = ldt; a.PT = PT; a.ldp = ldp;
+  a.C = C; a.ndir = ndir; a.n = n; a.GT = GT; a.GT16 = static_cast<const __half*>(GT16); a.ldt = ldt; a.PT = PT; a.ldp = ldp;
   a.use_bn = use_bn; a.training = training; a.mean = mean; a.rstd = rstd; a.gamma = gamma; a.gscale = gscale;
   a.dgamma = dgamma; a.dbeta = dbeta;
   a.dPT16 = static_cast<__half*>(dPT16); a.ld16t = ld16t;
@@ -120,7 +121,7 @@ int pk_rnn_layer_fwd(int cell, int T, int B, int H, int ndir, int act, const flo
   a.Y32 = Y32; a.ldy32 = ldy32; a.Y16 = static_cast<__half*>(Y16); a.ldy16 = ldy16;
   a.HT = HT; a.HT16 = static_cast<__half*>(HT16); a.HP16 = static_cast<__half*>(HP16);
   a.ZT = ZT; a.HCT = HCT; a.ldt = ldt;
-  a.cluster = f.cluster; a.sync = f.sync; a.dbg = f.dbg;
+  a.cluster = f.cluster; a.sync = f.sync; a.dbg = f.dbg; a.legacy = f.legacy;
   return ligru_fwd(a, static_cast<cudaStream_t>(stream));
 }
 
@@ -129,12 +130,12 @@ int pk_rnn_layer_bwd(int cell, int T, int B, int H, int ndir, int act, const flo
                      float mask_scalar, const float* gscale, float* GT, void* GT16, void* stream) {
   const RecFlags f = parse_cell(cell);
   PK_REQUIRE(f.cell == PK_CELL_LIGRU, "pk_rnn_layer_bwd: cell kind %d not implemented", f.cell);
-  PK_REQUIRE(dYT && HT && ZT && HCT && U && GT, "pk_rnn_layer_bwd: null input");
+  PK_REQUIRE(dYT && HT && ZT && HCT && U && (GT || GT16), "pk_rnn_layer_bwd: null input");
   RecBwdArgs a;
   a.T = T; a.B = B; a.H = H; a.ndir = ndir; a.act = act;
   a.dYT = dYT; a.HT = HT; a.ZT = ZT; a.HCT = HCT; a.ldt = ldt; a.U = U; a.mask = mask;
   a.mask_scalar = mask_scalar; a.gscale = gscale; a.GT = GT; a.GT16 = static_cast<__half*>(GT16);
-  a.cluster = f.cluster; a.sync = f.sync; a.dbg = f.dbg;
+  a.cluster = f.cluster; a.sync = f.sync; a.dbg = f.dbg; a.legacy = f.legacy;
   return ligru_bwd(a, static_cast<cudaStream_t>(stream));
 }
 

@@ -166,15 +166,16 @@ __global__ void fill_scale_shift_kernel(const float* __restrict__ bias, int C, f
 // ------------------------------------------------------------------------------------
 __global__ void bn_bwd_sums_kernel(const BnBwdArgs a, double* __restrict__ sums /* [2][C] */) {
   const int c = blockIdx.x;
-  const float* g0 = a.GT + static_cast<long long>(c) * a.ldt;
-  const float* g1 = (a.ndir == 2) ? g0 + static_cast<long long>(a.C) * a.ldt : nullptr;
+  const long long o0 = static_cast<long long>(c) * a.ldt;
+  const long long o1 = o0 + static_cast<long long>(a.C) * a.ldt;
+  const float inv_s = (a.GT16 && a.gscale) ? 1.f / __ldg(a.gscale) : 1.f;
   const float* p = a.PT ? a.PT + static_cast<long long>(c) * a.ldp : nullptr;
   const float mean = (a.use_bn && a.mean) ? a.mean[c] : 0.f;
   const float rstd = (a.use_bn && a.rstd) ? a.rstd[c] : 1.f;
   double s1 = 0.0, s2 = 0.0;
   for (long long i = threadIdx.x; i < a.n; i += blockDim.x) {
-    float g = g0[i];
-    if (g1) g += g1[i];
+    float g = a.GT ? a.GT[o0 + i] : __half2float(a.GT16[o0 + i]) * inv_s;
+    if (a.ndir == 2) g += a.GT ? a.GT[o1 + i] : __half2float(a.GT16[o1 + i]) * inv_s;
     s1 += g;
     if (a.use_bn) s2 += static_cast<double>(g) * ((p[i] - mean) * rstd);
   }
@@ -204,6 +205,7 @@ __global__ void bn_bwd_sums_kernel(const BnBwdArgs a, double* __restrict__ sums 
 __global__ void bn_bwd_apply_kernel(const BnBwdArgs a, const double* __restrict__ sums) {
   __shared__ float tile[32][33];
   const float s = a.gscale ? __ldg(a.gscale) : 1.f;
+  const float inv_s = (a.GT16 && a.gscale) ? 1.f / s : 1.f;
   const int tiles_i = static_cast<int>((a.n + 31) / 32);
   const long long ntiles = static_cast<long long>((a.C + 31) / 32) * tiles_i;
   const double inv_n = 1.0 / static_cast<double>(a.n);
@@ -215,8 +217,10 @@ __global__ void bn_bwd_apply_kernel(const BnBwdArgs a, const double* __restrict_
       const long long i = i0 + threadIdx.x;
       float v = 0.f;
       if (c < a.C && i < a.n) {
-        float g = a.GT[static_cast<long long>(c) * a.ldt + i];
-        if (a.ndir == 2) g += a.GT[static_cast<long long>(a.C + c) * a.ldt + i];
+        const long long o0 = static_cast<long long>(c) * a.ldt + i;
+        const long long o1 = static_cast<long long>(a.C + c) * a.ldt + i;
+        float g = a.GT ? a.GT[o0] : __half2float(a.GT16[o0]) * inv_s;
+        if (a.ndir == 2) g += a.GT ? a.GT[o1] : __half2float(a.GT16[o1]) * inv_s;
         if (a.use_bn) {
           const float rstd = a.rstd[c];
           const float gam = a.gamma ? a.gamma[c] : 1.f;

@@ -51,7 +51,8 @@ struct RecFwdArgs {
   float* ZT = nullptr;
   float* HCT = nullptr;
   long long ldt = 0;
-  int cluster = 0;  // 0 = auto, 8 or 16 CTAs per cluster
+  int cluster = 0;  // 0 = auto; > 0 selects a legacy (non-specialised) kernel with that cluster size
+  int legacy = 0;   // 1 = non-specialised kernels of pk_rnn.cu
   int sync = -1;    // -1 = default (st.async + mbarrier), 0 = barrier.cluster, 1 = st.async
   int dbg = 0;      // timing experiments only: bit0 skip global stores, bit1 skip global loads
 };
@@ -71,10 +72,14 @@ struct RecBwdArgs {
   float* GT = nullptr;            // [ndir][2H][ldt] fp32
   __half* GT16 = nullptr;         // [ndir][2H][ldt] fp16, scaled by *gscale
   int cluster = 0;
+  int legacy = 0;
   int sync = -1;
   int dbg = 0;
 };
 int ligru_bwd(const RecBwdArgs& a, cudaStream_t stream);
+// warp-specialised variants (pk_rnn_ws.cu); the bwd one writes GT16 only
+int ligru_fwd_ws(const RecFwdArgs& a, cudaStream_t stream);
+int ligru_bwd_ws(const RecBwdArgs& a, cudaStream_t stream);
 
 // ---- memory-bound helpers (pk_elementwise.cu) ----
 // out[c][r] = in[r][c]; optional fp16 copies. in is [R][ldi] fp32.
@@ -95,7 +100,8 @@ struct BnBwdArgs {
   int C = 0;          // channels (G*H)
   int ndir = 1;
   long long n = 0;    // unique rows T*B
-  const float* GT = nullptr;   // [ndir][C][ldt] fp32 (unscaled)
+  const float* GT = nullptr;   // [ndir][C][ldt] fp32 (unscaled), or null -> GT16
+  const __half* GT16 = nullptr; // [ndir][C][ldt] fp16 scaled by *gscale
   const float* PT = nullptr;   // [C][ldp] pre-BN projections
   long long ldt = 0, ldp = 0;
   int use_bn = 1;

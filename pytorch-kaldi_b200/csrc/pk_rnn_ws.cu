@@ -1,0 +1,629 @@
+// pk_rnn_ws.cu — warp-specialised persistent liGRU kernels (round-1 default).
+//
+// Same decomposition as pk_rnn.cu (cluster of CL CTAs x 8 batch rows, recurrent weights stationary in
+// registers as mma.sync fragments, st.async + mbarrier step exchange), but the per-step global-memory
+// work no longer runs on the warps that sit on the serial critical path:
+//
+//   compute warps : wait(step mbarrier) -> ldmatrix + HMMA -> gates -> st.async push
+//                   inputs of the step are read from / outputs written to small shared-memory RINGS
+//   I/O warps     : stream the rings:  global --cp.async--> in-ring   (RI-1 steps ahead)
+//                                      out-ring --> global            (coalesced along units/rows)
+//
+// ncu on the non-specialised kernels (profiles/r1_*): HMMA ~21 % and peer-wait ~9 % of the warp's step;
+// the rest was 64-bit address arithmetic, 12 scattered stores and prefetch issue per thread per step.
+#include "pk_common.cuh"
+#include "pk_kernels.h"
+
+#include <cstdlib>
+#include <mutex>
+
+namespace pk {
+
+namespace {
+
+constexpr int kRows = 8;
+constexpr int RI = 4;  // input ring depth (steps of prefetch distance + 1)
+constexpr int RO = 4;  // output ring depth
+
+__device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+// the mbarrier receives one arrival when all cp.async issued so far by this thread have landed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// =====================================================================================
+// forward
+// =====================================================================================
+template <int KT, int MT, int CL>
+struct FwdWs {
+  static constexpr int HS = CL * 8 * MT + 8;
+  static constexpr int UPC = 8 * MT;
+  __half h16[2][kRows][HS];
+  __half stage[MT][kRows][8];
+  float inr[RI][2][UPC][kRows];   // [slot][gate h,z][unit][row]
+  float outr[RO][3][UPC][kRows];  // [slot][h, z, hc][unit][row]
+  uint64_t step_bar[2];
+  uint64_t in_full[RI], in_empty[RI], out_full[RO], out_empty[RO];
+};
+
+template <int KT, int MT, int CL>
+__global__ void __launch_bounds__((MT + 1) * 32, 1) ligru_fwd_ws_kernel(const RecFwdArgs a) {
+  using S = FwdWs<KT, MT, CL>;
+  constexpr int HS = S::HS;
+  constexpr int UPC = S::UPC;
+  static_assert((CL * MT) % 2 == 0, "row pitch must be an odd multiple of 16 bytes (ldmatrix conflict-free)");
+  static_assert(CL * 8 * MT >= 16 * KT, "unit slots must cover the K range");
+  static_assert(MT + 1 <= 8, "at most 8 warps keep the 255-register budget");
+  constexpr uint32_t kTxBytes = CL * MT * 128;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  S& sm = *reinterpret_cast<S*>(smem_raw);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const int cl = blockIdx.x / CL;
+  const int H = a.H, B = a.B, T = a.T;
+  const int nrows = a.ndir * B;
+  const int cta_ubase = crank * UPC;
+
+  // ---- one-time setup ----
+  for (int i = threadIdx.x; i < 2 * kRows * HS / 2; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(&sm.h16[0][0][0])[i] = 0u;
+  for (int i = threadIdx.x; i < RI * 2 * UPC * kRows; i += blockDim.x) (&sm.inr[0][0][0][0])[i] = 0.f;
+  if (threadIdx.x == 0) {
+    mbar_init(&sm.step_bar[0], 1);
+    mbar_init(&sm.step_bar[1], 1);
+    for (int s = 0; s < RI; ++s) { mbar_init(&sm.in_full[s], 32); mbar_init(&sm.in_empty[s], MT); }
+    for (int s = 0; s < RO; ++s) { mbar_init(&sm.out_full[s], MT); mbar_init(&sm.out_empty[s], 1); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  cluster_sync_all();
+
+  if (warp < MT) {
+    // ================= compute warps =================
+    const int g = lane >> 2, q = lane & 3;
+    const int ul = warp * 8 + g;         // local unit
+    const int u = cta_ubase + ul;
+    const bool u_ok = u < H;
+    uint32_t A[KT][4];
+    {
+      const float* Uh = a.U + static_cast<long long>(u) * H;
+      const float* Uz = a.U + static_cast<long long>(H + u) * H;
+#pragma unroll
+      for (int kt = 0; kt < KT; ++kt) {
+        const int k0 = kt * 16 + 2 * q;
+        float h00 = 0.f, h01 = 0.f, h10 = 0.f, h11 = 0.f, z00 = 0.f, z01 = 0.f, z10 = 0.f, z11 = 0.f;
+        if (u_ok) {
+          if (k0 < H) { h00 = __ldg(Uh + k0); z00 = __ldg(Uz + k0); }
+          if (k0 + 1 < H) { h01 = __ldg(Uh + k0 + 1); z01 = __ldg(Uz + k0 + 1); }
+          if (k0 + 8 < H) { h10 = __ldg(Uh + k0 + 8); z10 = __ldg(Uz + k0 + 8); }
+          if (k0 + 9 < H) { h11 = __ldg(Uh + k0 + 9); z11 = __ldg(Uz + k0 + 9); }
+        }
+        A[kt][0] = pack_f16x2_sat(h00, h01);
+        A[kt][1] = pack_f16x2_sat(z00, z01);
+        A[kt][2] = pack_f16x2_sat(h10, h11);
+        A[kt][3] = pack_f16x2_sat(z10, z11);
+      }
+    }
+    bool rok[2];
+    float msk[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int r = cl * kRows + 2 * q + i;
+      rok[i] = (r < nrows) && u_ok;
+      msk[i] = a.mask ? (rok[i] ? __ldg(a.mask + static_cast<long long>(r) * H + u) : 0.f) : a.mask_scalar;
+    }
+    float sc_h = 0.f, sh_h = 0.f, sc_z = 0.f, sh_z = 0.f;
+    if (u_ok) {
+      sc_h = __ldg(a.scale + u); sh_h = __ldg(a.shift + u);
+      sc_z = __ldg(a.scale + H + u); sh_z = __ldg(a.shift + H + u);
+    }
+    float hprev[2] = {0.f, 0.f};
+    const uint32_t ldm_off = static_cast<uint32_t>(((lane & 7) * HS + 8 * (lane >> 3)) * 2);
+    const uint32_t ldm_off2 = static_cast<uint32_t>(((lane & 7) * HS + 8 * ((lane >> 3) & 1)) * 2);
+    const uint32_t h16_base = smem_u32(&sm.h16[0][0][0]);
+    constexpr uint32_t kBufBytes = kRows * HS * 2;
+    const int act = a.act;
+
+    for (int k = 0; k < T; ++k) {
+      const int cur = k & 1, nxt = cur ^ 1;
+      if (k > 0) mbar_wait(&sm.step_bar[cur], ((k - 1) >> 1) & 1);
+      if (threadIdx.x == 0) mbar_arrive_expect_tx(&sm.step_bar[nxt], kTxBytes);
+      float acc[4][4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f; }
+      const uint32_t bufa = h16_base + cur * kBufBytes;
+#pragma unroll
+      for (int kt = 0; kt + 1 < KT; kt += 2) {
+        uint32_t b0, b1, b2, b3;
+        ldmatrix_x4(bufa + ldm_off + kt * 32, b0, b1, b2, b3);
+        mma_m16n8k16_f16(acc[kt & 3], A[kt], b0, b1);
+        mma_m16n8k16_f16(acc[(kt + 1) & 3], A[kt + 1], b2, b3);
+      }
+      if (KT & 1) {
+        uint32_t b0, b1;
+        ldmatrix_x2(bufa + ldm_off2 + (KT - 1) * 32, b0, b1);
+        mma_m16n8k16_f16(acc[(KT - 1) & 3], A[KT - 1], b0, b1);
+      }
+      const float ch0 = (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]);
+      const float ch1 = (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]);
+      const float cz0 = (acc[0][2] + acc[1][2]) + (acc[2][2] + acc[3][2]);
+      const float cz1 = (acc[0][3] + acc[1][3]) + (acc[2][3] + acc[3][3]);
+
+      // ---- this step's projections from the input ring
+      const int si = k % RI;
+      mbar_wait(&sm.in_full[si], (k / RI) & 1);
+      const float2 ph = *reinterpret_cast<const float2*>(&sm.inr[si][0][ul][2 * q]);
+      const float2 pz = *reinterpret_cast<const float2*>(&sm.inr[si][1][ul][2 * q]);
+      // ---- gates (reference :1133-1136)
+      float hn[2], zz[2], hcv[2];
+      {
+        const float zt = sigmoidf_(fmaf(sc_z, pz.x, sh_z) + cz0);
+        const float hc = act_fwd(act, fmaf(sc_h, ph.x, sh_h) + ch0) * msk[0];
+        float h = zt * hprev[0] + (1.f - zt) * hc;
+        if (!rok[0]) h = 0.f;
+        hn[0] = h; zz[0] = zt; hcv[0] = hc; hprev[0] = h;
+      }
+      {
+        const float zt = sigmoidf_(fmaf(sc_z, pz.y, sh_z) + cz1);
+        const float hc = act_fwd(act, fmaf(sc_h, ph.y, sh_h) + ch1) * msk[1];
+        float h = zt * hprev[1] + (1.f - zt) * hc;
+        if (!rok[1]) h = 0.f;
+        hn[1] = h; zz[1] = zt; hcv[1] = hc; hprev[1] = h;
+      }
+      sm.stage[warp][2 * q][g] = f16_sat(hn[0]);
+      sm.stage[warp][2 * q + 1][g] = f16_sat(hn[1]);
+      __syncwarp();
+      {  // push the warp's 8x8 fp16 tile to every CTA of the cluster (data + completion in one message)
+        const int n = lane & 7;
+        const uint32_t laddr = smem_u32(&sm.h16[nxt][n][cta_ubase + warp * 8]);
+        const uint4 val = *reinterpret_cast<const uint4*>(&sm.stage[warp][n][0]);
+        const uint32_t lbar = smem_u32(&sm.step_bar[nxt]);
+#pragma unroll
+        for (int dst = (lane >> 3); dst < CL; dst += 4)
+          st_async_v4(mapa_shared(laddr, dst), val, mapa_shared(lbar, dst));
+      }
+      // ---- hand the step's outputs to the I/O warp
+      const int so = k % RO;
+      if (k >= RO) mbar_wait(&sm.out_empty[so], ((k / RO) - 1) & 1);
+      *reinterpret_cast<float2*>(&sm.outr[so][0][ul][2 * q]) = make_float2(hn[0], hn[1]);
+      *reinterpret_cast<float2*>(&sm.outr[so][1][ul][2 * q]) = make_float2(zz[0], zz[1]);
+      *reinterpret_cast<float2*>(&sm.outr[so][2][ul][2 * q]) = make_float2(hcv[0], hcv[1]);
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&sm.in_empty[si]);
+        mbar_arrive(&sm.out_full[so]);
+      }
+    }
+    mbar_wait(&sm.step_bar[T & 1], ((T - 1) >> 1) & 1);  // drain the last incoming fill
+  } else {
+    // ================= I/O warp =================
+    // element e = lane + 32*j  ->  (unit = e / 8, row = e % 8); all per-element bookkeeping is fixed over time
+    constexpr int NE = (UPC * kRows + 31) / 32;
+    int colv[NE];        // current column (t*B + b) of the element's row, -1 when invalid
+    int cstep[NE];       // +B / -B per step
+    long long chan[NE];  // (d*H + u) * ldt
+    long long pch[NE];   // u * ldp
+    int yoff[NE];        // d*H + u
+    float hp[NE];        // previous state (for HP16)
+#pragma unroll
+    for (int j = 0; j < NE; ++j) {
+      const int e = lane + 32 * j;
+      const int ul = e >> 3, r = e & 7;
+      const int u = cta_ubase + ul;
+      const int rr = cl * kRows + r;
+      const bool ok = (e < UPC * kRows) && (u < H) && (rr < nrows);
+      const int d = (ok && rr >= B) ? 1 : 0;
+      const int b = rr - d * B;
+      colv[j] = ok ? (d ? (T - 1) * B + b : b) : -1;
+      cstep[j] = d ? -B : B;
+      chan[j] = static_cast<long long>(d * H + u) * a.ldt;
+      pch[j] = static_cast<long long>(u) * a.ldp;
+      yoff[j] = d * H + u;
+      hp[j] = 0.f;
+    }
+    const long long gate_z = static_cast<long long>(H) * a.ldp;
+    const bool do_store = !(a.dbg & 1);
+    const bool do_load = !(a.dbg & 2);
+
+    auto issue_load = [&](int kl) {  // projections of step kl -> in-ring
+      const int s = kl % RI;
+      if (kl >= RI) mbar_wait(&sm.in_empty[s], ((kl / RI) - 1) & 1);
+      if (do_load) {
+#pragma unroll
+        for (int j = 0; j < NE; ++j) {
+          if (colv[j] >= 0) {
+            const int e = lane + 32 * j;
+            const long long col = colv[j] + static_cast<long long>(kl) * cstep[j];
+            cp_async_f32(&sm.inr[s][0][e >> 3][e & 7], a.PT + pch[j] + col);
+            cp_async_f32(&sm.inr[s][1][e >> 3][e & 7], a.PT + pch[j] + gate_z + col);
+          }
+        }
+      }
+      cp_async_arrive_noinc(&sm.in_full[s]);
+    };
+    for (int kl = 0; kl < RI - 1 && kl < T; ++kl) issue_load(kl);
+    for (int k = 0; k < T; ++k) {
+      if (k + RI - 1 < T) issue_load(k + RI - 1);
+      const int s = k % RO;
+      mbar_wait(&sm.out_full[s], (k / RO) & 1);
+      if (do_store) {
+#pragma unroll
+        for (int j = 0; j < NE; ++j) {
+          if (colv[j] >= 0) {
+            const int e = lane + 32 * j;
+            const float h = sm.outr[s][0][e >> 3][e & 7];
+            const long long col = colv[j] + static_cast<long long>(k) * cstep[j];
+            const long long idx = chan[j] + col;
+            if (a.HT) a.HT[idx] = h;
+            if (a.ZT) a.ZT[idx] = sm.outr[s][1][e >> 3][e & 7];
+            if (a.HCT) a.HCT[idx] = sm.outr[s][2][e >> 3][e & 7];
+            if (a.HT16) a.HT16[idx] = f16_sat(h);
+            if (a.HP16) a.HP16[idx] = f16_sat(hp[j]);
+            hp[j] = h;
+          }
+        }
+        // row-major module output: for a fixed row the CTA's units are contiguous -> lanes run along units
+        if (a.Y32 || a.Y16) {
+#pragma unroll 1
+          for (int r = 0; r < kRows; ++r) {
+            const int rr = cl * kRows + r;
+            if (rr >= nrows) break;
+            const int d = rr >= B ? 1 : 0;
+            const int b = rr - d * B;
+            const long long col = static_cast<long long>(d ? T - 1 - k : k) * B + b;
+            for (int ul = lane; ul < UPC; ul += 32) {
+              const int u = cta_ubase + ul;
+              if (u < H) {
+                const float h = sm.outr[s][0][ul][r];
+                if (a.Y32) a.Y32[col * a.ldy32 + d * H + u] = h;
+                if (a.Y16) a.Y16[col * a.ldy16 + d * H + u] = f16_sat(h);
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.out_empty[s]);
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  }
+  // no CTA may exit while peers can still write into its shared memory
+  cluster_sync_all();
+}
+
+// =====================================================================================
+// backward
+// =====================================================================================
+template <int KT, int MT, int CL>
+struct BwdWs {
+  static constexpr int MT16 = (MT + 1) / 2;
+  static constexpr int NWC = MT16 * 2;  // active compute warps
+  static constexpr int KP = CL * 8 * MT;
+  static constexpr int GS = 2 * KP + 8;
+  static constexpr int UPC = 8 * MT;
+  __half g16[2][kRows][GS];
+  __half stage[NWC][2][kRows][8];
+  float xbuf[2][MT16][2][32][2];
+  float inr[RI][4][UPC][kRows];    // [slot][dy, z, hc, hprev][unit][row]
+  __half outr[RO][2][UPC][kRows];  // [slot][da, dpz][unit][row]  (already scaled fp16)
+  uint64_t step_bar[2];
+  uint64_t in_full[RI], in_empty[RI], out_full[RO], out_empty[RO];
+};
+
+constexpr int kBwdComputeWarps = 8;  // two warpgroups (register budget raised with setmaxnreg)
+constexpr int kBwdIoWarps = 4;       // one warpgroup (register budget lowered)
+
+template <int KT, int MT, int CL>
+__global__ void __launch_bounds__((kBwdComputeWarps + kBwdIoWarps) * 32, 1) ligru_bwd_ws_kernel(const RecBwdArgs a) {
+  using S = BwdWs<KT, MT, CL>;
+  constexpr int MT16 = S::MT16, NWC = S::NWC, KP = S::KP, GS = S::GS, UPC = S::UPC;
+  static_assert(KP >= 16 * KT, "unit slots must cover the K range");
+  static_assert(NWC <= kBwdComputeWarps, "too many unit tiles per CTA");
+  constexpr uint32_t kTxBytes = CL * MT * 256;
+  constexpr int NIO = kBwdIoWarps * 32;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  S& sm = *reinterpret_cast<S*>(smem_raw);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const int cl = blockIdx.x / CL;
+  const int H = a.H, B = a.B, T = a.T;
+  const int nrows = a.ndir * B;
+  const int cta_ubase = crank * UPC;
+
+  for (int i = threadIdx.x; i < 2 * kRows * GS / 2; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(&sm.g16[0][0][0])[i] = 0u;
+  for (int i = threadIdx.x; i < RI * 4 * UPC * kRows; i += blockDim.x) (&sm.inr[0][0][0][0])[i] = 0.f;
+  if (threadIdx.x == 0) {
+    mbar_init(&sm.step_bar[0], 1);
+    mbar_init(&sm.step_bar[1], 1);
+    for (int s = 0; s < RI; ++s) { mbar_init(&sm.in_full[s], NIO); mbar_init(&sm.in_empty[s], NWC); }
+    for (int s = 0; s < RO; ++s) { mbar_init(&sm.out_full[s], NWC); mbar_init(&sm.out_empty[s], kBwdIoWarps); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  cluster_sync_all();
+
+  if (warp < kBwdComputeWarps) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;" ::: "memory");
+    if (warp < NWC) {
+      // ================= compute warps =================
+      const int g = lane >> 2, q = lane & 3;
+      const int mt = warp >> 1, half = warp & 1;
+      uint32_t A[KT][4];
+      {
+        const int slot_lo = mt * 16 + g, slot_hi = slot_lo + 8;
+        const int u_lo = cta_ubase + slot_lo, u_hi = cta_ubase + slot_hi;
+        const bool ok_lo = (slot_lo < UPC) && (u_lo < H);
+        const bool ok_hi = (slot_hi < UPC) && (u_hi < H);
+        const float* Ug = a.U + static_cast<long long>(half) * H * H;
+#pragma unroll
+        for (int kt = 0; kt < KT; ++kt) {
+          const int j0 = kt * 16 + 2 * q;
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = 0.f;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = j0 + (e & 1) + ((e >> 1) ? 8 : 0);
+            if (j < H) {
+              if (ok_lo) v[(e >> 1) * 4 + (e & 1)] = __ldg(Ug + static_cast<long long>(j) * H + u_lo);
+              if (ok_hi) v[(e >> 1) * 4 + 2 + (e & 1)] = __ldg(Ug + static_cast<long long>(j) * H + u_hi);
+            }
+          }
+          A[kt][0] = pack_f16x2_sat(v[0], v[1]);
+          A[kt][1] = pack_f16x2_sat(v[2], v[3]);
+          A[kt][2] = pack_f16x2_sat(v[4], v[5]);
+          A[kt][3] = pack_f16x2_sat(v[6], v[7]);
+        }
+      }
+      const int slot = mt * 16 + 8 * half + g;  // element ownership: unit slot, rows 2q, 2q+1
+      const int u = cta_ubase + slot;
+      const bool u_ok = (slot < UPC) && (u < H);
+      const int wslot0 = mt * 16 + 8 * half;
+      const bool warp_ok = wslot0 < UPC;
+      const int sl = warp_ok ? slot : 0;  // ring index (idle half-tiles read slot 0, results unused)
+      bool rok[2];
+      float msk[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int r = cl * kRows + 2 * q + i;
+        rok[i] = (r < nrows) && u_ok;
+        msk[i] = a.mask ? (rok[i] ? __ldg(a.mask + static_cast<long long>(r) * H + u) : 0.f) : a.mask_scalar;
+      }
+      const float s = a.gscale ? __ldg(a.gscale) : 1.f;
+      const float inv_s = 1.f / s;
+      float carry[2] = {0.f, 0.f};
+      const uint32_t ldm_off = static_cast<uint32_t>(((lane & 7) * GS + 8 * (lane >> 3)) * 2);
+      const uint32_t ldm_off2 = static_cast<uint32_t>(((lane & 7) * GS + 8 * ((lane >> 3) & 1)) * 2);
+      const uint32_t g16_base = smem_u32(&sm.g16[0][0][0]);
+      constexpr uint32_t kBufBytes = kRows * GS * 2;
+      const int act = a.act;
+
+      for (int k = T - 1; k >= 0; --k) {
+        const int it = T - 1 - k;  // iteration counter (rings advance with it)
+        const int buf = k & 1;
+        if (threadIdx.x == 0) mbar_arrive_expect_tx(&sm.step_bar[buf], kTxBytes);
+        // ---------------- phase A: pointwise backward of step k ----------------
+        const int si = it % RI;
+        mbar_wait(&sm.in_full[si], (it / RI) & 1);
+        const float2 dy = *reinterpret_cast<const float2*>(&sm.inr[si][0][sl][2 * q]);
+        const float2 zz = *reinterpret_cast<const float2*>(&sm.inr[si][1][sl][2 * q]);
+        const float2 hc = *reinterpret_cast<const float2*>(&sm.inr[si][2][sl][2 * q]);
+        float2 hp = *reinterpret_cast<const float2*>(&sm.inr[si][3][sl][2 * q]);
+        if (k == 0) hp = make_float2(0.f, 0.f);
+        float da[2], dpz[2], keep[2];
+        {
+          const float dh = dy.x + carry[0];
+          const float m = msk[0];
+          const float y = (m != 0.f) ? hc.x / m : 0.f;
+          float dav = dh * (1.f - zz.x) * m * act_bwd_from_out(act, y);
+          float dpzv = dh * (hp.x - hc.x) * zz.x * (1.f - zz.x);
+          if (!rok[0]) { dav = 0.f; dpzv = 0.f; }
+          da[0] = dav; dpz[0] = dpzv; keep[0] = dh * zz.x;
+        }
+        {
+          const float dh = dy.y + carry[1];
+          const float m = msk[1];
+          const float y = (m != 0.f) ? hc.y / m : 0.f;
+          float dav = dh * (1.f - zz.y) * m * act_bwd_from_out(act, y);
+          float dpzv = dh * (hp.y - hc.y) * zz.y * (1.f - zz.y);
+          if (!rok[1]) { dav = 0.f; dpzv = 0.f; }
+          da[1] = dav; dpz[1] = dpzv; keep[1] = dh * zz.y;
+        }
+        const __half2 da16 = __halves2half2(f16_sat(da[0] * s), f16_sat(da[1] * s));
+        const __half2 dz16 = __halves2half2(f16_sat(dpz[0] * s), f16_sat(dpz[1] * s));
+        if (warp_ok) {
+          sm.stage[warp][0][2 * q][g] = __low2half(da16);
+          sm.stage[warp][0][2 * q + 1][g] = __high2half(da16);
+          sm.stage[warp][1][2 * q][g] = __low2half(dz16);
+          sm.stage[warp][1][2 * q + 1][g] = __high2half(dz16);
+        }
+        __syncwarp();
+        if (warp_ok) {
+          const int n = lane & 7;
+          const int gate = (lane >> 3) & 1;
+          const uint32_t laddr = smem_u32(&sm.g16[buf][n][gate * KP + cta_ubase + wslot0]);
+          const uint4 val = *reinterpret_cast<const uint4*>(&sm.stage[warp][gate][n][0]);
+          const uint32_t lbar = smem_u32(&sm.step_bar[buf]);
+#pragma unroll
+          for (int dst = (lane >> 4); dst < CL; dst += 2)
+            st_async_v4(mapa_shared(laddr, dst), val, mapa_shared(lbar, dst));
+        }
+        // ---- outputs of the step (scaled fp16) to the I/O warps
+        const int so = it % RO;
+        if (it >= RO) mbar_wait(&sm.out_empty[so], ((it / RO) - 1) & 1);
+        if (warp_ok) {
+          *reinterpret_cast<__half2*>(&sm.outr[so][0][slot][2 * q]) = da16;
+          *reinterpret_cast<__half2*>(&sm.outr[so][1][slot][2 * q]) = dz16;
+        }
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&sm.in_empty[si]);
+          mbar_arrive(&sm.out_full[so]);
+        }
+        mbar_wait(&sm.step_bar[buf], (it >> 1) & 1);
+
+        // ---------------- phase B: U^T [da; dpz] for the carry into step k-1 ----------------
+        if (k > 0) {
+          float acc[4][4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f; }
+          const uint32_t bufa = g16_base + buf * kBufBytes + half * (KP * 2);
+#pragma unroll
+          for (int kt = 0; kt + 1 < KT; kt += 2) {
+            uint32_t b0, b1, b2, b3;
+            ldmatrix_x4(bufa + ldm_off + kt * 32, b0, b1, b2, b3);
+            mma_m16n8k16_f16(acc[kt & 3], A[kt], b0, b1);
+            mma_m16n8k16_f16(acc[(kt + 1) & 3], A[kt + 1], b2, b3);
+          }
+          if (KT & 1) {
+            uint32_t b0, b1;
+            ldmatrix_x2(bufa + ldm_off2 + (KT - 1) * 32, b0, b1);
+            mma_m16n8k16_f16(acc[(KT - 1) & 3], A[KT - 1], b0, b1);
+          }
+          float c4[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) c4[e] = (acc[0][e] + acc[1][e]) + (acc[2][e] + acc[3][e]);
+          sm.xbuf[buf][mt][half][lane][0] = half ? c4[0] : c4[2];
+          sm.xbuf[buf][mt][half][lane][1] = half ? c4[1] : c4[3];
+          asm volatile("bar.sync %0, 64;" ::"r"(mt + 1) : "memory");
+          const float o0 = sm.xbuf[buf][mt][half ^ 1][lane][0];
+          const float o1 = sm.xbuf[buf][mt][half ^ 1][lane][1];
+          carry[0] = keep[0] + ((half ? c4[2] : c4[0]) + o0) * inv_s;
+          carry[1] = keep[1] + ((half ? c4[3] : c4[1]) + o1) * inv_s;
+        }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
+    // ================= I/O warps (128 threads) =================
+    const int tid = threadIdx.x - kBwdComputeWarps * 32;
+    constexpr int NE = (UPC * kRows + NIO - 1) / NIO;
+    int colv[NE], cstep[NE];
+    long long chan[NE];
+#pragma unroll
+    for (int j = 0; j < NE; ++j) {
+      const int e = tid + NIO * j;
+      const int ul = e >> 3, r = e & 7;
+      const int u = cta_ubase + ul;
+      const int rr = cl * kRows + r;
+      const bool ok = (e < UPC * kRows) && (u < H) && (rr < nrows);
+      const int d = (ok && rr >= B) ? 1 : 0;
+      const int b = rr - d * B;
+      colv[j] = ok ? (d ? (T - 1) * B + b : b) : -1;  // column at step index 0
+      cstep[j] = d ? -B : B;
+      chan[j] = static_cast<long long>(d * H + u) * a.ldt;
+    }
+    const long long gate_stride = static_cast<long long>(H) * a.ldt;
+    const long long dir_stride = 2 * gate_stride;
+    const bool do_store = !(a.dbg & 1);
+    const bool do_load = !(a.dbg & 2);
+
+    auto issue_load = [&](int it) {  // operands of step k = T-1-it -> in-ring slot it % RI
+      const int k = T - 1 - it;
+      const int s = it % RI;
+      if (it >= RI) mbar_wait(&sm.in_empty[s], ((it / RI) - 1) & 1);
+      if (do_load) {
+#pragma unroll
+        for (int j = 0; j < NE; ++j) {
+          if (colv[j] >= 0) {
+            const int e = tid + NIO * j;
+            const long long idx = chan[j] + colv[j] + static_cast<long long>(k) * cstep[j];
+            cp_async_f32(&sm.inr[s][0][e >> 3][e & 7], a.dYT + idx);
+            cp_async_f32(&sm.inr[s][1][e >> 3][e & 7], a.ZT + idx);
+            cp_async_f32(&sm.inr[s][2][e >> 3][e & 7], a.HCT + idx);
+            if (k > 0) cp_async_f32(&sm.inr[s][3][e >> 3][e & 7], a.HT + idx - cstep[j]);
+          }
+        }
+      }
+      cp_async_arrive_noinc(&sm.in_full[s]);
+    };
+    for (int it = 0; it < RI - 1 && it < T; ++it) issue_load(it);
+    for (int it = 0; it < T; ++it) {
+      if (it + RI - 1 < T) issue_load(it + RI - 1);
+      const int k = T - 1 - it;
+      const int s = it % RO;
+      mbar_wait(&sm.out_full[s], (it / RO) & 1);
+      if (do_store) {
+#pragma unroll
+        for (int j = 0; j < NE; ++j) {
+          if (colv[j] >= 0) {
+            const int e = tid + NIO * j;
+            const int ul = e >> 3, r = e & 7;
+            const int u = cta_ubase + ul;
+            const int d = cstep[j] < 0 ? 1 : 0;
+            const long long col = colv[j] + static_cast<long long>(k) * cstep[j];
+            const long long idx = d * dir_stride + static_cast<long long>(u) * a.ldt + col;
+            a.GT16[idx] = sm.outr[s][0][ul][r];
+            a.GT16[idx + gate_stride] = sm.outr[s][1][ul][r];
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.out_empty[s]);
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  }
+  cluster_sync_all();
+}
+
+template <typename Args, void (*Kern)(const Args)>
+int launch_ws(const Args& a, int cluster, int nclusters, int threads, size_t smem, cudaStream_t stream) {
+  static std::once_flag once;
+  static cudaError_t err = cudaSuccess;
+  std::call_once(once, [&] {
+    err = cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (err == cudaSuccess && cluster > 8)
+      err = cudaFuncSetAttribute(Kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  });
+  PK_CHECK_CUDA(err);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nclusters * cluster, 1, 1);
+  cfg.blockDim = dim3(threads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, Kern, a));
+  return 0;
+}
+
+#define PK_FWD_WS(KT, MT, CL)                                                                           \
+  return launch_ws<RecFwdArgs, ligru_fwd_ws_kernel<KT, MT, CL>>(a, CL, nclusters, ((MT) + 1) * 32,        \
+                                                               sizeof(FwdWs<KT, MT, CL>), stream)
+#define PK_BWD_WS(KT, MT, CL)                                                                           \
+  return launch_ws<RecBwdArgs, ligru_bwd_ws_kernel<KT, MT, CL>>(                                        \
+      a, CL, nclusters, (kBwdComputeWarps + kBwdIoWarps) * 32, sizeof(BwdWs<KT, MT, CL>), stream)
+
+}  // namespace
+
+// (k-tiles, 8-unit tiles per CTA, cluster size): CL * 8 * MT >= H and 16 * KT >= H
+int ligru_fwd_ws(const RecFwdArgs& a, cudaStream_t stream) {
+  const int nclusters = (a.ndir * a.B + kRows - 1) / kRows;
+  const int H = a.H;
+  if (H <= 256) { PK_FWD_WS(16, 4, 8); }
+  if (H <= 384) { PK_FWD_WS(24, 6, 8); }
+  if (H <= 512) { PK_FWD_WS(32, 7, 10); }
+  PK_FWD_WS(35, 7, 10);
+}
+int ligru_bwd_ws(const RecBwdArgs& a, cudaStream_t stream) {
+  const int nclusters = (a.ndir * a.B + kRows - 1) / kRows;
+  const int H = a.H;
+  if (H <= 256) { PK_BWD_WS(16, 4, 8); }
+  if (H <= 384) { PK_BWD_WS(24, 6, 8); }
+  if (H <= 512) { PK_BWD_WS(32, 7, 10); }
+  PK_BWD_WS(35, 7, 10);
+}
+
+}  // namespace pk

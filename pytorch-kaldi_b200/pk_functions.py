@@ -173,7 +173,8 @@ class LiGRUStackFn(torch.autograd.Function):
             # power-of-two loss scale for this layer's fp16 gradient operands
             sc = torch.empty(2, **f32)
             pk.amax_scale(dYT, ldt, F, TB, 8.0, scratch, sc)
-            GT = torch.empty(ndir, C2, ldt, **f32)
+            legacy = bool(cfg.cell_flags & pk.REC_LEGACY)
+            GT = torch.empty(ndir, C2, ldt, **f32) if legacy else None
             GT16 = torch.empty(ndir, C2, ldt, **f16)
             pk.rnn_layer_bwd(cfg.cell | cfg.cell_flags, T, B, H, ndir, S["act"], dYT, S["HT"], S["ZT"], S["HCT"],
                              ldt, S["U"], S["mask"], S["mask_scalar"], sc, GT, GT16)
@@ -190,7 +191,7 @@ class LiGRUStackFn(torch.autograd.Function):
             dPT16 = torch.empty(C2, ldt, **f16)
             dP16 = torch.empty(TB, ld2H, **f16) if need_dx else None
             sums = torch.empty(2 * C2, device=dev, dtype=torch.float64)
-            pk.bn_bwd(C2, ndir, TB, GT, ldt, S["PT"], ldt, S["use_bn"], S["bn_train"], S["mean"], S["rstd"],
+            pk.bn_bwd(C2, ndir, TB, GT, GT16, ldt, S["PT"], ldt, S["use_bn"], S["bn_train"], S["mean"], S["rstd"],
                       S["gamma"], sc, dgamma, dbeta, dPT16, ldt, dP16, ld2H, sums)
             # dW = dP^T X
             dW = torch.empty(C2, D, **f32)

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libpk_b200.so")
 F16, TF32 = 0, 2
 ACT_IDS = {"relu": 0, "tanh": 1, "sigmoid": 2, "leaky_relu": 3, "elu": 4, "linear": 5}
 CELL_LIGRU, CELL_RNN, CELL_GRU, CELL_MGRU, CELL_LSTM = 0, 1, 2, 3, 4
-REC_CLUSTER8, REC_CLUSTER16, REC_SYNC_BARRIER = 0x800, 0x1000, 0x2000
+REC_CLUSTER8, REC_CLUSTER16, REC_SYNC_BARRIER, REC_LEGACY = 0x800, 0x1000, 0x2000, 0x4000
 
 _c_int, _c_i64, _c_f, _c_p = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
 
@@ -32,7 +32,7 @@ SIGNATURES = {
     "pk_bn_finalize": [_c_p, _c_int, _c_i64, _c_i64, _c_p, _c_p, _c_f, _c_f, _c_int, _c_p, _c_p, _c_p, _c_p, _c_p,
                        _c_p, _c_p, _c_p],
     "pk_fill_scale_shift": [_c_p, _c_int, _c_p, _c_p, _c_p],
-    "pk_bn_bwd": [_c_int, _c_int, _c_i64, _c_p, _c_i64, _c_p, _c_i64, _c_int, _c_int, _c_p, _c_p, _c_p, _c_p, _c_p,
+    "pk_bn_bwd": [_c_int, _c_int, _c_i64, _c_p, _c_p, _c_i64, _c_p, _c_i64, _c_int, _c_int, _c_p, _c_p, _c_p, _c_p, _c_p,
                   _c_p, _c_p, _c_i64, _c_p, _c_i64, _c_p, _c_p],
     "pk_rnn_layer_fwd": [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_p, _c_i64, _c_p, _c_p, _c_p, _c_p, _c_f,
                          _c_p, _c_i64, _c_p, _c_i64, _c_p, _c_p, _c_p, _c_p, _c_p, _c_i64, _c_p],
@@ -139,9 +139,9 @@ def fill_scale_shift(bias, C, scale, shift):
     _check(lib().pk_fill_scale_shift(_ptr(bias), C, _ptr(scale), _ptr(shift), _stream()), "pk_fill_scale_shift")
 
 
-def bn_bwd(C, ndir, n, GT, ldt, PT, ldp, use_bn, training, mean, rstd, gamma, gscale, dgamma, dbeta, dPT16, ld16t,
+def bn_bwd(C, ndir, n, GT, GT16, ldt, PT, ldp, use_bn, training, mean, rstd, gamma, gscale, dgamma, dbeta, dPT16, ld16t,
            dP16, ld16r, sums_scratch):
-    _check(lib().pk_bn_bwd(C, ndir, n, _ptr(GT), ldt, _ptr(PT), ldp, int(use_bn), int(training), _ptr(mean),
+    _check(lib().pk_bn_bwd(C, ndir, n, _ptr(GT), _ptr(GT16), ldt, _ptr(PT), ldp, int(use_bn), int(training), _ptr(mean),
                            _ptr(rstd), _ptr(gamma), _ptr(gscale), _ptr(dgamma), _ptr(dbeta), _ptr(dPT16), ld16t,
                            _ptr(dP16), ld16r, _ptr(sums_scratch), _stream()), "pk_bn_bwd")
 
