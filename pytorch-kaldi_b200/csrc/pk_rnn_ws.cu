@@ -1,16 +1,22 @@
 // pk_rnn_ws.cu — warp-specialised persistent liGRU kernels (round-1 default).
 //
 // Same decomposition as pk_rnn.cu (cluster of CL CTAs x 8 batch rows, recurrent weights stationary in
-// registers as mma.sync fragments, st.async + mbarrier step exchange), but the per-step global-memory
-// work no longer runs on the warps that sit on the serial critical path:
+// registers as mma.sync fragments, asynchronous DSMEM exchange completed on the receiver's mbarrier), with
+// two changes driven by the ncu profiles under profiles/:
 //
-//   compute warps : wait(step mbarrier) -> ldmatrix + HMMA -> gates -> st.async push
-//                   inputs of the step are read from / outputs written to small shared-memory RINGS
-//   I/O warps     : stream the rings:  global --cp.async--> in-ring   (RI-1 steps ahead)
-//                                      out-ring --> global            (coalesced along units/rows)
-//
-// ncu on the non-specialised kernels (profiles/r1_*): HMMA ~21 % and peer-wait ~9 % of the warp's step;
-// the rest was 64-bit address arithmetic, 12 scattered stores and prefetch issue per thread per step.
+//  1. WARP SPECIALISATION.  The per-step global-memory work no longer runs on the warps that sit on the
+//     serial critical path:
+//       compute warps (2 warpgroups, setmaxnreg.inc 224): wait -> ldmatrix + HMMA -> gates -> push;
+//                     step inputs are read from / outputs written to small shared-memory RINGS
+//       I/O warps (1 warpgroup, setmaxnreg.dec 56): global --cp.async--> in-ring (RI-1 steps ahead),
+//                     out-ring --> global
+//     (before: HMMA ~21 % and peer-wait ~9 % of a warp's step; the rest was address arithmetic, 12 scattered
+//      stores and prefetch issue per thread per step)
+//  2. TILE-MAJOR STAGING + BULK PUSH.  The staged fp16 vector is stored as [8-unit tile][row][8 units], so
+//     (a) the 8x8 tile a warp produces is ONE contiguous 128-byte block that travels to each peer as a single
+//     cp.async.bulk (shared::cta -> shared::cluster, complete_tx on the receiver's mbarrier): 8x fewer
+//     messages / mbarrier updates than 16-byte st.async; (b) every ldmatrix 8x8 matrix is 128 contiguous
+//     bytes: conflict-free without padding.
 #include "pk_common.cuh"
 #include "pk_kernels.h"
 
@@ -22,8 +28,12 @@ namespace pk {
 namespace {
 
 constexpr int kRows = 8;
-constexpr int RI = 4;  // input ring depth (steps of prefetch distance + 1)
+constexpr int RI = 4;  // input ring depth (prefetch distance + 1)
 constexpr int RO = 4;  // output ring depth
+constexpr int kComputeWarps = 8;  // two warpgroups
+constexpr int kIoWarps = 4;       // one warpgroup
+constexpr int kThreads = (kComputeWarps + kIoWarps) * 32;
+constexpr int NIO = kIoWarps * 32;
 
 __device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
@@ -32,32 +42,39 @@ __device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gsrc)
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// 128-byte tile: local shared memory -> shared memory of CTA `dst` (+ complete_tx on ITS mbarrier)
+__device__ __forceinline__ void bulk_push_128(uint32_t dst_cluster_addr, uint32_t src_local_addr,
+                                              uint32_t dst_cluster_mbar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], 128, [%2];" ::"r"(
+          dst_cluster_addr),
+      "r"(src_local_addr), "r"(dst_cluster_mbar)
+      : "memory");
+}
 
 // =====================================================================================
 // forward
 // =====================================================================================
 template <int KT, int MT, int CL>
 struct FwdWs {
-  static constexpr int HS = CL * 8 * MT + 8;
+  static constexpr int NT = CL * MT;  // 8-unit tiles of the whole layer
   static constexpr int UPC = 8 * MT;
-  __half h16[2][kRows][HS];
-  __half stage[MT][kRows][8];
-  float inr[RI][2][UPC][kRows];   // [slot][gate h,z][unit][row]
-  float outr[RO][3][UPC][kRows];  // [slot][h, z, hc][unit][row]
+  __half h16[2][NT][kRows][8];          // tile-major staged state, double buffered by step parity
+  __half stage[2][MT][kRows][8];        // per-warp source tiles of the bulk pushes
+  float inr[RI][2][UPC][kRows];         // [slot][gate h,z][unit][row]
+  float outr[RO][3][UPC][kRows];        // [slot][h, z, hc][unit][row]
   uint64_t step_bar[2];
   uint64_t in_full[RI], in_empty[RI], out_full[RO], out_empty[RO];
 };
 
 template <int KT, int MT, int CL>
-__global__ void __launch_bounds__((MT + 1) * 32, 1) ligru_fwd_ws_kernel(const RecFwdArgs a) {
+__global__ void __launch_bounds__(kThreads, 1) ligru_fwd_ws_kernel(const RecFwdArgs a) {
   using S = FwdWs<KT, MT, CL>;
-  constexpr int HS = S::HS;
-  constexpr int UPC = S::UPC;
-  static_assert((CL * MT) % 2 == 0, "row pitch must be an odd multiple of 16 bytes (ldmatrix conflict-free)");
-  static_assert(CL * 8 * MT >= 16 * KT, "unit slots must cover the K range");
-  static_assert(MT + 1 <= 8, "at most 8 warps keep the 255-register budget");
-  constexpr uint32_t kTxBytes = CL * MT * 128;
-  extern __shared__ __align__(16) uint8_t smem_raw[];
+  constexpr int NT = S::NT, UPC = S::UPC;
+  static_assert(8 * NT >= 16 * KT, "unit tiles must cover the K range");
+  static_assert(MT <= kComputeWarps, "one compute warp per 8-unit tile");
+  constexpr uint32_t kTxBytes = NT * 128;  // every CTA receives the whole staged vector each step
+  extern __shared__ __align__(128) uint8_t smem_raw[];
   S& sm = *reinterpret_cast<S*>(smem_raw);
 
   const int warp = threadIdx.x >> 5;
@@ -68,161 +85,159 @@ __global__ void __launch_bounds__((MT + 1) * 32, 1) ligru_fwd_ws_kernel(const Re
   const int nrows = a.ndir * B;
   const int cta_ubase = crank * UPC;
 
-  // ---- one-time setup ----
-  for (int i = threadIdx.x; i < 2 * kRows * HS / 2; i += blockDim.x)
-    reinterpret_cast<uint32_t*>(&sm.h16[0][0][0])[i] = 0u;
+  for (int i = threadIdx.x; i < 2 * NT * kRows * 8 / 2; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(&sm.h16[0][0][0][0])[i] = 0u;
   for (int i = threadIdx.x; i < RI * 2 * UPC * kRows; i += blockDim.x) (&sm.inr[0][0][0][0])[i] = 0.f;
   if (threadIdx.x == 0) {
     mbar_init(&sm.step_bar[0], 1);
     mbar_init(&sm.step_bar[1], 1);
-    for (int s = 0; s < RI; ++s) { mbar_init(&sm.in_full[s], 32); mbar_init(&sm.in_empty[s], MT); }
-    for (int s = 0; s < RO; ++s) { mbar_init(&sm.out_full[s], MT); mbar_init(&sm.out_empty[s], 1); }
+    for (int s = 0; s < RI; ++s) { mbar_init(&sm.in_full[s], NIO); mbar_init(&sm.in_empty[s], MT); }
+    for (int s = 0; s < RO; ++s) { mbar_init(&sm.out_full[s], MT); mbar_init(&sm.out_empty[s], kIoWarps); }
     fence_mbar_init();
   }
   __syncthreads();
   cluster_sync_all();
 
-  if (warp < MT) {
-    // ================= compute warps =================
-    const int g = lane >> 2, q = lane & 3;
-    const int ul = warp * 8 + g;         // local unit
-    const int u = cta_ubase + ul;
-    const bool u_ok = u < H;
-    uint32_t A[KT][4];
-    {
-      const float* Uh = a.U + static_cast<long long>(u) * H;
-      const float* Uz = a.U + static_cast<long long>(H + u) * H;
+  if (warp < kComputeWarps) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;" ::: "memory");
+    if (warp < MT) {
+      // ================= compute warps =================
+      const int g = lane >> 2, q = lane & 3;
+      const int ul = warp * 8 + g;  // local unit
+      const int u = cta_ubase + ul;
+      const bool u_ok = u < H;
+      uint32_t A[KT][4];
+      {
+        const float* Uh = a.U + static_cast<long long>(u) * H;
+        const float* Uz = a.U + static_cast<long long>(H + u) * H;
 #pragma unroll
-      for (int kt = 0; kt < KT; ++kt) {
-        const int k0 = kt * 16 + 2 * q;
-        float h00 = 0.f, h01 = 0.f, h10 = 0.f, h11 = 0.f, z00 = 0.f, z01 = 0.f, z10 = 0.f, z11 = 0.f;
-        if (u_ok) {
-          if (k0 < H) { h00 = __ldg(Uh + k0); z00 = __ldg(Uz + k0); }
-          if (k0 + 1 < H) { h01 = __ldg(Uh + k0 + 1); z01 = __ldg(Uz + k0 + 1); }
-          if (k0 + 8 < H) { h10 = __ldg(Uh + k0 + 8); z10 = __ldg(Uz + k0 + 8); }
-          if (k0 + 9 < H) { h11 = __ldg(Uh + k0 + 9); z11 = __ldg(Uz + k0 + 9); }
+        for (int kt = 0; kt < KT; ++kt) {
+          const int k0 = kt * 16 + 2 * q;
+          float h00 = 0.f, h01 = 0.f, h10 = 0.f, h11 = 0.f, z00 = 0.f, z01 = 0.f, z10 = 0.f, z11 = 0.f;
+          if (u_ok) {
+            if (k0 < H) { h00 = __ldg(Uh + k0); z00 = __ldg(Uz + k0); }
+            if (k0 + 1 < H) { h01 = __ldg(Uh + k0 + 1); z01 = __ldg(Uz + k0 + 1); }
+            if (k0 + 8 < H) { h10 = __ldg(Uh + k0 + 8); z10 = __ldg(Uz + k0 + 8); }
+            if (k0 + 9 < H) { h11 = __ldg(Uh + k0 + 9); z11 = __ldg(Uz + k0 + 9); }
+          }
+          A[kt][0] = pack_f16x2_sat(h00, h01);
+          A[kt][1] = pack_f16x2_sat(z00, z01);
+          A[kt][2] = pack_f16x2_sat(h10, h11);
+          A[kt][3] = pack_f16x2_sat(z10, z11);
         }
-        A[kt][0] = pack_f16x2_sat(h00, h01);
-        A[kt][1] = pack_f16x2_sat(z00, z01);
-        A[kt][2] = pack_f16x2_sat(h10, h11);
-        A[kt][3] = pack_f16x2_sat(z10, z11);
       }
-    }
-    bool rok[2];
-    float msk[2];
+      bool rok[2];
+      float msk[2];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int r = cl * kRows + 2 * q + i;
-      rok[i] = (r < nrows) && u_ok;
-      msk[i] = a.mask ? (rok[i] ? __ldg(a.mask + static_cast<long long>(r) * H + u) : 0.f) : a.mask_scalar;
-    }
-    float sc_h = 0.f, sh_h = 0.f, sc_z = 0.f, sh_z = 0.f;
-    if (u_ok) {
-      sc_h = __ldg(a.scale + u); sh_h = __ldg(a.shift + u);
-      sc_z = __ldg(a.scale + H + u); sh_z = __ldg(a.shift + H + u);
-    }
-    float hprev[2] = {0.f, 0.f};
-    const uint32_t ldm_off = static_cast<uint32_t>(((lane & 7) * HS + 8 * (lane >> 3)) * 2);
-    const uint32_t ldm_off2 = static_cast<uint32_t>(((lane & 7) * HS + 8 * ((lane >> 3) & 1)) * 2);
-    const uint32_t h16_base = smem_u32(&sm.h16[0][0][0]);
-    constexpr uint32_t kBufBytes = kRows * HS * 2;
-    const int act = a.act;
+      for (int i = 0; i < 2; ++i) {
+        const int r = cl * kRows + 2 * q + i;
+        rok[i] = (r < nrows) && u_ok;
+        msk[i] = a.mask ? (rok[i] ? __ldg(a.mask + static_cast<long long>(r) * H + u) : 0.f) : a.mask_scalar;
+      }
+      float sc_h = 0.f, sh_h = 0.f, sc_z = 0.f, sh_z = 0.f;
+      if (u_ok) {
+        sc_h = __ldg(a.scale + u); sh_h = __ldg(a.shift + u);
+        sc_z = __ldg(a.scale + H + u); sh_z = __ldg(a.shift + H + u);
+      }
+      float hprev[2] = {0.f, 0.f};
+      // ldmatrix: matrix m (lane>>3) = tile 2*kt + m, row lane&7, 16 bytes per row
+      const uint32_t ldm_off = static_cast<uint32_t>(((lane >> 3) * 8 + (lane & 7)) * 16);
+      const uint32_t ldm_off2 = static_cast<uint32_t>((((lane >> 3) & 1) * 8 + (lane & 7)) * 16);
+      const uint32_t h16_base = smem_u32(&sm.h16[0][0][0][0]);
+      constexpr uint32_t kBufBytes = NT * kRows * 16;
+      const int tg = crank * MT + warp;  // global tile id of this warp's 8 units
+      const int act = a.act;
 
-    for (int k = 0; k < T; ++k) {
-      const int cur = k & 1, nxt = cur ^ 1;
-      if (k > 0) mbar_wait(&sm.step_bar[cur], ((k - 1) >> 1) & 1);
-      if (threadIdx.x == 0) mbar_arrive_expect_tx(&sm.step_bar[nxt], kTxBytes);
-      float acc[4][4];
+      for (int k = 0; k < T; ++k) {
+        const int cur = k & 1, nxt = cur ^ 1;
+        if (k > 0) mbar_wait(&sm.step_bar[cur], ((k - 1) >> 1) & 1);
+        if (threadIdx.x == 0) mbar_arrive_expect_tx(&sm.step_bar[nxt], kTxBytes);
+        float acc[4][4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) { acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f; }
-      const uint32_t bufa = h16_base + cur * kBufBytes;
+        for (int c = 0; c < 4; ++c) { acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f; }
+        const uint32_t bufa = h16_base + cur * kBufBytes;
 #pragma unroll
-      for (int kt = 0; kt + 1 < KT; kt += 2) {
-        uint32_t b0, b1, b2, b3;
-        ldmatrix_x4(bufa + ldm_off + kt * 32, b0, b1, b2, b3);
-        mma_m16n8k16_f16(acc[kt & 3], A[kt], b0, b1);
-        mma_m16n8k16_f16(acc[(kt + 1) & 3], A[kt + 1], b2, b3);
-      }
-      if (KT & 1) {
-        uint32_t b0, b1;
-        ldmatrix_x2(bufa + ldm_off2 + (KT - 1) * 32, b0, b1);
-        mma_m16n8k16_f16(acc[(KT - 1) & 3], A[KT - 1], b0, b1);
-      }
-      const float ch0 = (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]);
-      const float ch1 = (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]);
-      const float cz0 = (acc[0][2] + acc[1][2]) + (acc[2][2] + acc[3][2]);
-      const float cz1 = (acc[0][3] + acc[1][3]) + (acc[2][3] + acc[3][3]);
+        for (int kt = 0; kt + 1 < KT; kt += 2) {
+          uint32_t b0, b1, b2, b3;
+          ldmatrix_x4(bufa + ldm_off + kt * 256, b0, b1, b2, b3);  // 2 tiles (256 bytes) per k-tile
+          mma_m16n8k16_f16(acc[kt & 3], A[kt], b0, b1);
+          mma_m16n8k16_f16(acc[(kt + 1) & 3], A[kt + 1], b2, b3);
+        }
+        if (KT & 1) {
+          uint32_t b0, b1;
+          ldmatrix_x2(bufa + ldm_off2 + (KT - 1) * 256, b0, b1);
+          mma_m16n8k16_f16(acc[(KT - 1) & 3], A[KT - 1], b0, b1);
+        }
+        const float ch0 = (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]);
+        const float ch1 = (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]);
+        const float cz0 = (acc[0][2] + acc[1][2]) + (acc[2][2] + acc[3][2]);
+        const float cz1 = (acc[0][3] + acc[1][3]) + (acc[2][3] + acc[3][3]);
 
-      // ---- this step's projections from the input ring
-      const int si = k % RI;
-      mbar_wait(&sm.in_full[si], (k / RI) & 1);
-      const float2 ph = *reinterpret_cast<const float2*>(&sm.inr[si][0][ul][2 * q]);
-      const float2 pz = *reinterpret_cast<const float2*>(&sm.inr[si][1][ul][2 * q]);
-      // ---- gates (reference :1133-1136)
-      float hn[2], zz[2], hcv[2];
-      {
-        const float zt = sigmoidf_(fmaf(sc_z, pz.x, sh_z) + cz0);
-        const float hc = act_fwd(act, fmaf(sc_h, ph.x, sh_h) + ch0) * msk[0];
-        float h = zt * hprev[0] + (1.f - zt) * hc;
-        if (!rok[0]) h = 0.f;
-        hn[0] = h; zz[0] = zt; hcv[0] = hc; hprev[0] = h;
+        const int si = k % RI;
+        mbar_wait(&sm.in_full[si], (k / RI) & 1);
+        const float2 ph = *reinterpret_cast<const float2*>(&sm.inr[si][0][ul][2 * q]);
+        const float2 pz = *reinterpret_cast<const float2*>(&sm.inr[si][1][ul][2 * q]);
+        float hn[2], zz[2], hcv[2];
+        {
+          const float zt = sigmoidf_(fmaf(sc_z, pz.x, sh_z) + cz0);
+          const float hc = act_fwd(act, fmaf(sc_h, ph.x, sh_h) + ch0) * msk[0];
+          float h = zt * hprev[0] + (1.f - zt) * hc;
+          if (!rok[0]) h = 0.f;
+          hn[0] = h; zz[0] = zt; hcv[0] = hc; hprev[0] = h;
+        }
+        {
+          const float zt = sigmoidf_(fmaf(sc_z, pz.y, sh_z) + cz1);
+          const float hc = act_fwd(act, fmaf(sc_h, ph.y, sh_h) + ch1) * msk[1];
+          float h = zt * hprev[1] + (1.f - zt) * hc;
+          if (!rok[1]) h = 0.f;
+          hn[1] = h; zz[1] = zt; hcv[1] = hc; hprev[1] = h;
+        }
+        // ---- stage the warp's 8x8 fp16 tile (128 contiguous bytes) and push it to every CTA
+        sm.stage[nxt][warp][2 * q][g] = f16_sat(hn[0]);
+        sm.stage[nxt][warp][2 * q + 1][g] = f16_sat(hn[1]);
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the bulk-copy (async) proxy
+        __syncwarp();
+        if (lane < CL) {
+          const uint32_t dst = smem_u32(&sm.h16[nxt][tg][0][0]);
+          bulk_push_128(mapa_shared(dst, lane), smem_u32(&sm.stage[nxt][warp][0][0]),
+                        mapa_shared(smem_u32(&sm.step_bar[nxt]), lane));
+        }
+        // ---- hand the step's outputs to the I/O warps
+        const int so = k % RO;
+        if (k >= RO) mbar_wait(&sm.out_empty[so], ((k / RO) - 1) & 1);
+        *reinterpret_cast<float2*>(&sm.outr[so][0][ul][2 * q]) = make_float2(hn[0], hn[1]);
+        *reinterpret_cast<float2*>(&sm.outr[so][1][ul][2 * q]) = make_float2(zz[0], zz[1]);
+        *reinterpret_cast<float2*>(&sm.outr[so][2][ul][2 * q]) = make_float2(hcv[0], hcv[1]);
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&sm.in_empty[si]);
+          mbar_arrive(&sm.out_full[so]);
+        }
       }
-      {
-        const float zt = sigmoidf_(fmaf(sc_z, pz.y, sh_z) + cz1);
-        const float hc = act_fwd(act, fmaf(sc_h, ph.y, sh_h) + ch1) * msk[1];
-        float h = zt * hprev[1] + (1.f - zt) * hc;
-        if (!rok[1]) h = 0.f;
-        hn[1] = h; zz[1] = zt; hcv[1] = hc; hprev[1] = h;
-      }
-      sm.stage[warp][2 * q][g] = f16_sat(hn[0]);
-      sm.stage[warp][2 * q + 1][g] = f16_sat(hn[1]);
-      __syncwarp();
-      {  // push the warp's 8x8 fp16 tile to every CTA of the cluster (data + completion in one message)
-        const int n = lane & 7;
-        const uint32_t laddr = smem_u32(&sm.h16[nxt][n][cta_ubase + warp * 8]);
-        const uint4 val = *reinterpret_cast<const uint4*>(&sm.stage[warp][n][0]);
-        const uint32_t lbar = smem_u32(&sm.step_bar[nxt]);
-#pragma unroll
-        for (int dst = (lane >> 3); dst < CL; dst += 4)
-          st_async_v4(mapa_shared(laddr, dst), val, mapa_shared(lbar, dst));
-      }
-      // ---- hand the step's outputs to the I/O warp
-      const int so = k % RO;
-      if (k >= RO) mbar_wait(&sm.out_empty[so], ((k / RO) - 1) & 1);
-      *reinterpret_cast<float2*>(&sm.outr[so][0][ul][2 * q]) = make_float2(hn[0], hn[1]);
-      *reinterpret_cast<float2*>(&sm.outr[so][1][ul][2 * q]) = make_float2(zz[0], zz[1]);
-      *reinterpret_cast<float2*>(&sm.outr[so][2][ul][2 * q]) = make_float2(hcv[0], hcv[1]);
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&sm.in_empty[si]);
-        mbar_arrive(&sm.out_full[so]);
-      }
+      mbar_wait(&sm.step_bar[T & 1], ((T - 1) >> 1) & 1);  // drain the last incoming fill
     }
-    mbar_wait(&sm.step_bar[T & 1], ((T - 1) >> 1) & 1);  // drain the last incoming fill
   } else {
-    // ================= I/O warp =================
-    // element e = lane + 32*j  ->  (unit = e / 8, row = e % 8); all per-element bookkeeping is fixed over time
-    constexpr int NE = (UPC * kRows + 31) / 32;
-    int colv[NE];        // current column (t*B + b) of the element's row, -1 when invalid
-    int cstep[NE];       // +B / -B per step
-    long long chan[NE];  // (d*H + u) * ldt
-    long long pch[NE];   // u * ldp
-    int yoff[NE];        // d*H + u
-    float hp[NE];        // previous state (for HP16)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
+    // ================= I/O warps (128 threads) =================
+    // element e = tid + 128*j -> (unit = e / 8, row = e % 8); per-element bookkeeping is fixed over time
+    const int tid = threadIdx.x - kComputeWarps * 32;
+    constexpr int NE = (UPC * kRows + NIO - 1) / NIO;
+    int colv[NE], cstep[NE];
+    long long chan[NE], pch[NE];
+    float hp[NE];
 #pragma unroll
     for (int j = 0; j < NE; ++j) {
-      const int e = lane + 32 * j;
+      const int e = tid + NIO * j;
       const int ul = e >> 3, r = e & 7;
       const int u = cta_ubase + ul;
       const int rr = cl * kRows + r;
       const bool ok = (e < UPC * kRows) && (u < H) && (rr < nrows);
       const int d = (ok && rr >= B) ? 1 : 0;
       const int b = rr - d * B;
-      colv[j] = ok ? (d ? (T - 1) * B + b : b) : -1;
+      colv[j] = ok ? (d ? (T - 1) * B + b : b) : -1;  // column at step 0
       cstep[j] = d ? -B : B;
       chan[j] = static_cast<long long>(d * H + u) * a.ldt;
       pch[j] = static_cast<long long>(u) * a.ldp;
-      yoff[j] = d * H + u;
       hp[j] = 0.f;
     }
     const long long gate_z = static_cast<long long>(H) * a.ldp;
@@ -236,7 +251,7 @@ __global__ void __launch_bounds__((MT + 1) * 32, 1) ligru_fwd_ws_kernel(const Re
 #pragma unroll
         for (int j = 0; j < NE; ++j) {
           if (colv[j] >= 0) {
-            const int e = lane + 32 * j;
+            const int e = tid + NIO * j;
             const long long col = colv[j] + static_cast<long long>(kl) * cstep[j];
             cp_async_f32(&sm.inr[s][0][e >> 3][e & 7], a.PT + pch[j] + col);
             cp_async_f32(&sm.inr[s][1][e >> 3][e & 7], a.PT + pch[j] + gate_z + col);
@@ -254,10 +269,9 @@ __global__ void __launch_bounds__((MT + 1) * 32, 1) ligru_fwd_ws_kernel(const Re
 #pragma unroll
         for (int j = 0; j < NE; ++j) {
           if (colv[j] >= 0) {
-            const int e = lane + 32 * j;
+            const int e = tid + NIO * j;
             const float h = sm.outr[s][0][e >> 3][e & 7];
-            const long long col = colv[j] + static_cast<long long>(k) * cstep[j];
-            const long long idx = chan[j] + col;
+            const long long idx = chan[j] + colv[j] + static_cast<long long>(k) * cstep[j];
             if (a.HT) a.HT[idx] = h;
             if (a.ZT) a.ZT[idx] = sm.outr[s][1][e >> 3][e & 7];
             if (a.HCT) a.HCT[idx] = sm.outr[s][2][e >> 3][e & 7];
@@ -266,22 +280,19 @@ __global__ void __launch_bounds__((MT + 1) * 32, 1) ligru_fwd_ws_kernel(const Re
             hp[j] = h;
           }
         }
-        // row-major module output: for a fixed row the CTA's units are contiguous -> lanes run along units
+        // row-major module output: for a fixed row the CTA's units are contiguous -> threads run along units
         if (a.Y32 || a.Y16) {
-#pragma unroll 1
-          for (int r = 0; r < kRows; ++r) {
+          for (int f = tid; f < UPC * kRows; f += NIO) {
+            const int r = f / UPC, ul = f - r * UPC;
             const int rr = cl * kRows + r;
-            if (rr >= nrows) break;
-            const int d = rr >= B ? 1 : 0;
-            const int b = rr - d * B;
-            const long long col = static_cast<long long>(d ? T - 1 - k : k) * B + b;
-            for (int ul = lane; ul < UPC; ul += 32) {
-              const int u = cta_ubase + ul;
-              if (u < H) {
-                const float h = sm.outr[s][0][ul][r];
-                if (a.Y32) a.Y32[col * a.ldy32 + d * H + u] = h;
-                if (a.Y16) a.Y16[col * a.ldy16 + d * H + u] = f16_sat(h);
-              }
+            const int u = cta_ubase + ul;
+            if (rr < nrows && u < H) {
+              const int d = rr >= B ? 1 : 0;
+              const int b = rr - d * B;
+              const long long col = static_cast<long long>(d ? T - 1 - k : k) * B + b;
+              const float h = sm.outr[s][0][ul][r];
+              if (a.Y32) a.Y32[col * a.ldy32 + d * H + u] = h;
+              if (a.Y16) a.Y16[col * a.ldy16 + d * H + u] = f16_sat(h);
             }
           }
         }
@@ -302,30 +313,25 @@ template <int KT, int MT, int CL>
 struct BwdWs {
   static constexpr int MT16 = (MT + 1) / 2;
   static constexpr int NWC = MT16 * 2;  // active compute warps
-  static constexpr int KP = CL * 8 * MT;
-  static constexpr int GS = 2 * KP + 8;
+  static constexpr int NT = CL * MT;
   static constexpr int UPC = 8 * MT;
-  __half g16[2][kRows][GS];
-  __half stage[NWC][2][kRows][8];
+  __half g16[2][2][NT][kRows][8];          // [buffer][gate da,dpz][tile][row][8 units]
+  __half stage[2][NWC][2][kRows][8];
   float xbuf[2][MT16][2][32][2];
-  float inr[RI][4][UPC][kRows];    // [slot][dy, z, hc, hprev][unit][row]
-  __half outr[RO][2][UPC][kRows];  // [slot][da, dpz][unit][row]  (already scaled fp16)
+  float inr[RI][4][UPC][kRows];            // [slot][dy, z, hc, hprev][unit][row]
+  __half outr[RO][2][UPC][kRows];          // [slot][da, dpz][unit][row]  (scaled fp16)
   uint64_t step_bar[2];
   uint64_t in_full[RI], in_empty[RI], out_full[RO], out_empty[RO];
 };
 
-constexpr int kBwdComputeWarps = 8;  // two warpgroups (register budget raised with setmaxnreg)
-constexpr int kBwdIoWarps = 4;       // one warpgroup (register budget lowered)
-
 template <int KT, int MT, int CL>
-__global__ void __launch_bounds__((kBwdComputeWarps + kBwdIoWarps) * 32, 1) ligru_bwd_ws_kernel(const RecBwdArgs a) {
+__global__ void __launch_bounds__(kThreads, 1) ligru_bwd_ws_kernel(const RecBwdArgs a) {
   using S = BwdWs<KT, MT, CL>;
-  constexpr int MT16 = S::MT16, NWC = S::NWC, KP = S::KP, GS = S::GS, UPC = S::UPC;
-  static_assert(KP >= 16 * KT, "unit slots must cover the K range");
-  static_assert(NWC <= kBwdComputeWarps, "too many unit tiles per CTA");
-  constexpr uint32_t kTxBytes = CL * MT * 256;
-  constexpr int NIO = kBwdIoWarps * 32;
-  extern __shared__ __align__(16) uint8_t smem_raw[];
+  constexpr int MT16 = S::MT16, NWC = S::NWC, NT = S::NT, UPC = S::UPC;
+  static_assert(8 * NT >= 16 * KT, "unit tiles must cover the K range");
+  static_assert(NWC <= kComputeWarps, "too many unit tiles per CTA");
+  constexpr uint32_t kTxBytes = 2 * NT * 128;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
   S& sm = *reinterpret_cast<S*>(smem_raw);
 
   const int warp = threadIdx.x >> 5;
@@ -336,20 +342,20 @@ __global__ void __launch_bounds__((kBwdComputeWarps + kBwdIoWarps) * 32, 1) ligr
   const int nrows = a.ndir * B;
   const int cta_ubase = crank * UPC;
 
-  for (int i = threadIdx.x; i < 2 * kRows * GS / 2; i += blockDim.x)
-    reinterpret_cast<uint32_t*>(&sm.g16[0][0][0])[i] = 0u;
+  for (int i = threadIdx.x; i < 2 * 2 * NT * kRows * 8 / 2; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(&sm.g16[0][0][0][0][0])[i] = 0u;
   for (int i = threadIdx.x; i < RI * 4 * UPC * kRows; i += blockDim.x) (&sm.inr[0][0][0][0])[i] = 0.f;
   if (threadIdx.x == 0) {
     mbar_init(&sm.step_bar[0], 1);
     mbar_init(&sm.step_bar[1], 1);
     for (int s = 0; s < RI; ++s) { mbar_init(&sm.in_full[s], NIO); mbar_init(&sm.in_empty[s], NWC); }
-    for (int s = 0; s < RO; ++s) { mbar_init(&sm.out_full[s], NWC); mbar_init(&sm.out_empty[s], kBwdIoWarps); }
+    for (int s = 0; s < RO; ++s) { mbar_init(&sm.out_full[s], NWC); mbar_init(&sm.out_empty[s], kIoWarps); }
     fence_mbar_init();
   }
   __syncthreads();
   cluster_sync_all();
 
-  if (warp < kBwdComputeWarps) {
+  if (warp < kComputeWarps) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 224;" ::: "memory");
     if (warp < NWC) {
       // ================= compute warps =================
@@ -385,9 +391,10 @@ __global__ void __launch_bounds__((kBwdComputeWarps + kBwdIoWarps) * 32, 1) ligr
       const int slot = mt * 16 + 8 * half + g;  // element ownership: unit slot, rows 2q, 2q+1
       const int u = cta_ubase + slot;
       const bool u_ok = (slot < UPC) && (u < H);
-      const int wslot0 = mt * 16 + 8 * half;
-      const bool warp_ok = wslot0 < UPC;
-      const int sl = warp_ok ? slot : 0;  // ring index (idle half-tiles read slot 0, results unused)
+      const int wtile = 2 * mt + half;          // local 8-unit tile of this warp's elements
+      const bool warp_ok = wtile < MT;          // the last 16-unit tile may be half empty (MT odd)
+      const int sl = warp_ok ? slot : 0;
+      const int tg = crank * MT + wtile;        // global tile id
       bool rok[2];
       float msk[2];
 #pragma unroll
@@ -399,14 +406,15 @@ __global__ void __launch_bounds__((kBwdComputeWarps + kBwdIoWarps) * 32, 1) ligr
       const float s = a.gscale ? __ldg(a.gscale) : 1.f;
       const float inv_s = 1.f / s;
       float carry[2] = {0.f, 0.f};
-      const uint32_t ldm_off = static_cast<uint32_t>(((lane & 7) * GS + 8 * (lane >> 3)) * 2);
-      const uint32_t ldm_off2 = static_cast<uint32_t>(((lane & 7) * GS + 8 * ((lane >> 3) & 1)) * 2);
-      const uint32_t g16_base = smem_u32(&sm.g16[0][0][0]);
-      constexpr uint32_t kBufBytes = kRows * GS * 2;
+      const uint32_t ldm_off = static_cast<uint32_t>(((lane >> 3) * 8 + (lane & 7)) * 16);
+      const uint32_t ldm_off2 = static_cast<uint32_t>((((lane >> 3) & 1) * 8 + (lane & 7)) * 16);
+      const uint32_t g16_base = smem_u32(&sm.g16[0][0][0][0][0]);
+      constexpr uint32_t kGateBytes = NT * kRows * 16;
+      constexpr uint32_t kBufBytes = 2 * kGateBytes;
       const int act = a.act;
 
       for (int k = T - 1; k >= 0; --k) {
-        const int it = T - 1 - k;  // iteration counter (rings advance with it)
+        const int it = T - 1 - k;
         const int buf = k & 1;
         if (threadIdx.x == 0) mbar_arrive_expect_tx(&sm.step_bar[buf], kTxBytes);
         // ---------------- phase A: pointwise backward of step k ----------------
@@ -439,21 +447,18 @@ __global__ void __launch_bounds__((kBwdComputeWarps + kBwdIoWarps) * 32, 1) ligr
         const __half2 da16 = __halves2half2(f16_sat(da[0] * s), f16_sat(da[1] * s));
         const __half2 dz16 = __halves2half2(f16_sat(dpz[0] * s), f16_sat(dpz[1] * s));
         if (warp_ok) {
-          sm.stage[warp][0][2 * q][g] = __low2half(da16);
-          sm.stage[warp][0][2 * q + 1][g] = __high2half(da16);
-          sm.stage[warp][1][2 * q][g] = __low2half(dz16);
-          sm.stage[warp][1][2 * q + 1][g] = __high2half(dz16);
+          sm.stage[buf][warp][0][2 * q][g] = __low2half(da16);
+          sm.stage[buf][warp][0][2 * q + 1][g] = __high2half(da16);
+          sm.stage[buf][warp][1][2 * q][g] = __low2half(dz16);
+          sm.stage[buf][warp][1][2 * q + 1][g] = __high2half(dz16);
+          fence_proxy_async_smem();
         }
         __syncwarp();
-        if (warp_ok) {
-          const int n = lane & 7;
-          const int gate = (lane >> 3) & 1;
-          const uint32_t laddr = smem_u32(&sm.g16[buf][n][gate * KP + cta_ubase + wslot0]);
-          const uint4 val = *reinterpret_cast<const uint4*>(&sm.stage[warp][gate][n][0]);
-          const uint32_t lbar = smem_u32(&sm.step_bar[buf]);
-#pragma unroll
-          for (int dst = (lane >> 4); dst < CL; dst += 2)
-            st_async_v4(mapa_shared(laddr, dst), val, mapa_shared(lbar, dst));
+        if (warp_ok && lane < 2 * CL) {  // one 128-byte tile per (gate, destination CTA)
+          const int gate = lane & 1, dstc = lane >> 1;
+          const uint32_t dst = smem_u32(&sm.g16[buf][gate][tg][0][0]);
+          bulk_push_128(mapa_shared(dst, dstc), smem_u32(&sm.stage[buf][warp][gate][0][0]),
+                        mapa_shared(smem_u32(&sm.step_bar[buf]), dstc));
         }
         // ---- outputs of the step (scaled fp16) to the I/O warps
         const int so = it % RO;
@@ -474,17 +479,17 @@ __global__ void __launch_bounds__((kBwdComputeWarps + kBwdIoWarps) * 32, 1) ligr
           float acc[4][4];
 #pragma unroll
           for (int c = 0; c < 4; ++c) { acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f; }
-          const uint32_t bufa = g16_base + buf * kBufBytes + half * (KP * 2);
+          const uint32_t bufa = g16_base + buf * kBufBytes + half * kGateBytes;
 #pragma unroll
           for (int kt = 0; kt + 1 < KT; kt += 2) {
             uint32_t b0, b1, b2, b3;
-            ldmatrix_x4(bufa + ldm_off + kt * 32, b0, b1, b2, b3);
+            ldmatrix_x4(bufa + ldm_off + kt * 256, b0, b1, b2, b3);
             mma_m16n8k16_f16(acc[kt & 3], A[kt], b0, b1);
             mma_m16n8k16_f16(acc[(kt + 1) & 3], A[kt + 1], b2, b3);
           }
           if (KT & 1) {
             uint32_t b0, b1;
-            ldmatrix_x2(bufa + ldm_off2 + (KT - 1) * 32, b0, b1);
+            ldmatrix_x2(bufa + ldm_off2 + (KT - 1) * 256, b0, b1);
             mma_m16n8k16_f16(acc[(KT - 1) & 3], A[KT - 1], b0, b1);
           }
           float c4[4];
@@ -503,7 +508,7 @@ __global__ void __launch_bounds__((kBwdComputeWarps + kBwdIoWarps) * 32, 1) ligr
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
     // ================= I/O warps (128 threads) =================
-    const int tid = threadIdx.x - kBwdComputeWarps * 32;
+    const int tid = threadIdx.x - kComputeWarps * 32;
     constexpr int NE = (UPC * kRows + NIO - 1) / NIO;
     int colv[NE], cstep[NE];
     long long chan[NE];
@@ -574,7 +579,7 @@ __global__ void __launch_bounds__((kBwdComputeWarps + kBwdIoWarps) * 32, 1) ligr
 }
 
 template <typename Args, void (*Kern)(const Args)>
-int launch_ws(const Args& a, int cluster, int nclusters, int threads, size_t smem, cudaStream_t stream) {
+int launch_ws(const Args& a, int cluster, int nclusters, size_t smem, cudaStream_t stream) {
   static std::once_flag once;
   static cudaError_t err = cudaSuccess;
   std::call_once(once, [&] {
@@ -585,7 +590,7 @@ int launch_ws(const Args& a, int cluster, int nclusters, int threads, size_t sme
   PK_CHECK_CUDA(err);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(nclusters * cluster, 1, 1);
-  cfg.blockDim = dim3(threads, 1, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -599,16 +604,14 @@ int launch_ws(const Args& a, int cluster, int nclusters, int threads, size_t sme
   return 0;
 }
 
-#define PK_FWD_WS(KT, MT, CL)                                                                           \
-  return launch_ws<RecFwdArgs, ligru_fwd_ws_kernel<KT, MT, CL>>(a, CL, nclusters, ((MT) + 1) * 32,        \
-                                                               sizeof(FwdWs<KT, MT, CL>), stream)
-#define PK_BWD_WS(KT, MT, CL)                                                                           \
-  return launch_ws<RecBwdArgs, ligru_bwd_ws_kernel<KT, MT, CL>>(                                        \
-      a, CL, nclusters, (kBwdComputeWarps + kBwdIoWarps) * 32, sizeof(BwdWs<KT, MT, CL>), stream)
+#define PK_FWD_WS(KT, MT, CL) \
+  return launch_ws<RecFwdArgs, ligru_fwd_ws_kernel<KT, MT, CL>>(a, CL, nclusters, sizeof(FwdWs<KT, MT, CL>) + 128, stream)
+#define PK_BWD_WS(KT, MT, CL) \
+  return launch_ws<RecBwdArgs, ligru_bwd_ws_kernel<KT, MT, CL>>(a, CL, nclusters, sizeof(BwdWs<KT, MT, CL>) + 128, stream)
 
 }  // namespace
 
-// (k-tiles, 8-unit tiles per CTA, cluster size): CL * 8 * MT >= H and 16 * KT >= H
+// (k-tiles, 8-unit tiles per CTA, cluster size): CL * 8 * MT >= 16 * KT >= H
 int ligru_fwd_ws(const RecFwdArgs& a, cudaStream_t stream) {
   const int nclusters = (a.ndir * a.B + kRows - 1) / kRows;
   const int H = a.H;
