@@ -40,6 +40,8 @@ extern "C" {
 
 const char* pk_last_error(void) { return pk::g_err; }
 int pk_version(void) { return PK_ABI_VERSION; }
+// bring-up hook (not part of the documented ABI): per-phase cycle counters of the recurrent kernels
+void pk_debug_set_clock_buffer(void* dev_ptr) { pk::set_debug_clock_buffer(static_cast<long long*>(dev_ptr)); }
 
 int pk_gemm_tn(int dtype, int M, int N, int K, const void* A, int64_t lda, int64_t a_k0, int64_t a_kext,
                const void* B, int64_t ldb, int64_t b_k0, int64_t b_kext, float* C, int64_t ldc,

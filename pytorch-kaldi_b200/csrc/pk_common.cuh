@@ -339,6 +339,34 @@ __device__ __forceinline__ float act_bwd_from_out(int act, float y) {
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
+// Fast variants for the serial critical path of the recurrent kernels: MUFU.EX2 / MUFU.RCP based
+// (~2 ulp), far inside the 1e-3 parity budget and several hundred cycles shorter per step than the
+// IEEE expf + division sequence (measured with the phase clocks, profiles/).
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float exp_approx(float x) {  // e^x = 2^(x * log2 e), one MUFU.EX2
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.f + exp_approx(-x)); }
+__device__ __forceinline__ float act_fwd_fast(int act, float x) {
+  switch (act) {
+    case ACT_RELU: return fmaxf(x, 0.f);
+    case ACT_TANH: return 1.f - 2.f * rcp_approx(1.f + exp_approx(2.f * x));
+    case ACT_SIGMOID: return sigmoid_fast(x);
+    case ACT_LEAKY_RELU: return x > 0.f ? x : 0.2f * x;
+    case ACT_ELU: return x > 0.f ? x : exp_approx(x) - 1.f;
+    default: return x;
+  }
+}
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+
 #endif  // __CUDACC__
 
 }  // namespace pk

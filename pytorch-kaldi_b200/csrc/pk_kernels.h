@@ -53,6 +53,7 @@ struct RecFwdArgs {
   long long ldt = 0;
   int cluster = 0;  // 0 = auto; > 0 selects a legacy (non-specialised) kernel with that cluster size
   int legacy = 0;   // 1 = non-specialised kernels of pk_rnn.cu
+  long long* dbg_clk = nullptr;  // bring-up: per-phase cycle sums of CTA 0 / warp 0 (8 slots)
   int sync = -1;    // -1 = default (st.async + mbarrier), 0 = barrier.cluster, 1 = st.async
   int dbg = 0;      // timing experiments only: bit0 skip global stores, bit1 skip global loads
 };
@@ -73,6 +74,7 @@ struct RecBwdArgs {
   __half* GT16 = nullptr;         // [ndir][2H][ldt] fp16, scaled by *gscale
   int cluster = 0;
   int legacy = 0;
+  long long* dbg_clk = nullptr;
   int sync = -1;
   int dbg = 0;
 };
@@ -80,6 +82,7 @@ int ligru_bwd(const RecBwdArgs& a, cudaStream_t stream);
 // warp-specialised variants (pk_rnn_ws.cu); the bwd one writes GT16 only
 int ligru_fwd_ws(const RecFwdArgs& a, cudaStream_t stream);
 int ligru_bwd_ws(const RecBwdArgs& a, cudaStream_t stream);
+void set_debug_clock_buffer(long long* dev_ptr);
 
 // ---- memory-bound helpers (pk_elementwise.cu) ----
 // out[c][r] = in[r][c]; optional fp16 copies. in is [R][ldi] fp32.

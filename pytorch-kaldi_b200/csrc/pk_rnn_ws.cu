@@ -12,11 +12,12 @@
 //                     out-ring --> global
 //     (before: HMMA ~21 % and peer-wait ~9 % of a warp's step; the rest was address arithmetic, 12 scattered
 //      stores and prefetch issue per thread per step)
-//  2. TILE-MAJOR STAGING + BULK PUSH.  The staged fp16 vector is stored as [8-unit tile][row][8 units], so
-//     (a) the 8x8 tile a warp produces is ONE contiguous 128-byte block that travels to each peer as a single
-//     cp.async.bulk (shared::cta -> shared::cluster, complete_tx on the receiver's mbarrier): 8x fewer
-//     messages / mbarrier updates than 16-byte st.async; (b) every ldmatrix 8x8 matrix is 128 contiguous
-//     bytes: conflict-free without padding.
+//  2. TILE-MAJOR STAGING.  The staged fp16 vector is stored as [8-unit tile][row][8 units]: every ldmatrix
+//     8x8 matrix is 128 contiguous bytes (conflict-free without padding) and a warp's tile rows are the
+//     16-byte st.async messages.  (One 128-byte cp.async.bulk per (warp, peer) was measured too: it needs a
+//     proxy fence and the compiler serialises the uniform-operand UBLKCPs -> 780 vs ~250 cycles per step.)
+//  3. TRANSIT SHADOW.  Ring hand-offs (this step's outputs, next step's inputs) happen after the push,
+//     while the data is in flight; gate math uses MUFU-based sigmoid/tanh (phase clocks: 668 -> ~150 cycles).
 #include "pk_common.cuh"
 #include "pk_kernels.h"
 
@@ -60,7 +61,7 @@ struct FwdWs {
   static constexpr int NT = CL * MT;  // 8-unit tiles of the whole layer
   static constexpr int UPC = 8 * MT;
   __half h16[2][NT][kRows][8];          // tile-major staged state, double buffered by step parity
-  __half stage[2][MT][kRows][8];        // per-warp source tiles of the bulk pushes
+  __half stage[MT][kRows][8];           // per-warp 8x8 tile, re-read as 16-byte rows for the push
   float inr[RI][2][UPC][kRows];         // [slot][gate h,z][unit][row]
   float outr[RO][3][UPC][kRows];        // [slot][h, z, hc][unit][row]
   uint64_t step_bar[2];
@@ -148,10 +149,21 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_fwd_ws_kernel(const RecFwdA
       const int tg = crank * MT + warp;  // global tile id of this warp's 8 units
       const int act = a.act;
 
+      const bool clk_on = a.dbg_clk != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+      long long tsum[6] = {0, 0, 0, 0, 0, 0};
+      // projections of step 0 (later steps are fetched in the shadow of the DSMEM transit)
+      mbar_wait(&sm.in_full[0], 0);
+      float2 ph = *reinterpret_cast<const float2*>(&sm.inr[0][0][ul][2 * q]);
+      float2 pz = *reinterpret_cast<const float2*>(&sm.inr[0][1][ul][2 * q]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.in_empty[0]);
       for (int k = 0; k < T; ++k) {
         const int cur = k & 1, nxt = cur ^ 1;
+        long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+        if (clk_on) t0 = clock64();
         if (k > 0) mbar_wait(&sm.step_bar[cur], ((k - 1) >> 1) & 1);
         if (threadIdx.x == 0) mbar_arrive_expect_tx(&sm.step_bar[nxt], kTxBytes);
+        if (clk_on) t1 = clock64();
         float acc[4][4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) { acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f; }
@@ -172,48 +184,63 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_fwd_ws_kernel(const RecFwdA
         const float ch1 = (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]);
         const float cz0 = (acc[0][2] + acc[1][2]) + (acc[2][2] + acc[3][2]);
         const float cz1 = (acc[0][3] + acc[1][3]) + (acc[2][3] + acc[3][3]);
+        if (clk_on) { t2 = clock64(); if (cz1 == 123.456f) t2 = 0; }
 
-        const int si = k % RI;
-        mbar_wait(&sm.in_full[si], (k / RI) & 1);
-        const float2 ph = *reinterpret_cast<const float2*>(&sm.inr[si][0][ul][2 * q]);
-        const float2 pz = *reinterpret_cast<const float2*>(&sm.inr[si][1][ul][2 * q]);
+        // ---- gates (reference :1133-1136)
         float hn[2], zz[2], hcv[2];
         {
-          const float zt = sigmoidf_(fmaf(sc_z, pz.x, sh_z) + cz0);
-          const float hc = act_fwd(act, fmaf(sc_h, ph.x, sh_h) + ch0) * msk[0];
-          float h = zt * hprev[0] + (1.f - zt) * hc;
+          const float zt = sigmoid_fast(fmaf(sc_z, pz.x, sh_z) + cz0);
+          const float hc = act_fwd_fast(act, fmaf(sc_h, ph.x, sh_h) + ch0) * msk[0];
+          float h = fmaf(zt, hprev[0] - hc, hc);
           if (!rok[0]) h = 0.f;
           hn[0] = h; zz[0] = zt; hcv[0] = hc; hprev[0] = h;
         }
         {
-          const float zt = sigmoidf_(fmaf(sc_z, pz.y, sh_z) + cz1);
-          const float hc = act_fwd(act, fmaf(sc_h, ph.y, sh_h) + ch1) * msk[1];
-          float h = zt * hprev[1] + (1.f - zt) * hc;
+          const float zt = sigmoid_fast(fmaf(sc_z, pz.y, sh_z) + cz1);
+          const float hc = act_fwd_fast(act, fmaf(sc_h, ph.y, sh_h) + ch1) * msk[1];
+          float h = fmaf(zt, hprev[1] - hc, hc);
           if (!rok[1]) h = 0.f;
           hn[1] = h; zz[1] = zt; hcv[1] = hc; hprev[1] = h;
         }
-        // ---- stage the warp's 8x8 fp16 tile (128 contiguous bytes) and push it to every CTA
-        sm.stage[nxt][warp][2 * q][g] = f16_sat(hn[0]);
-        sm.stage[nxt][warp][2 * q + 1][g] = f16_sat(hn[1]);
-        fence_proxy_async_smem();  // generic-proxy writes -> visible to the bulk-copy (async) proxy
+        if (clk_on) { t3 = clock64(); if (hn[1] == 123.456f) t3 = 0; }
+        // ---- stage the warp's 8x8 fp16 tile and push its 8 rows (16 bytes each) to every CTA: data and
+        //      completion (complete_tx on the receiver's mbarrier) travel in one st.async message
+        sm.stage[warp][2 * q][g] = f16_sat(hn[0]);
+        sm.stage[warp][2 * q + 1][g] = f16_sat(hn[1]);
         __syncwarp();
-        if (lane < CL) {
-          const uint32_t dst = smem_u32(&sm.h16[nxt][tg][0][0]);
-          bulk_push_128(mapa_shared(dst, lane), smem_u32(&sm.stage[nxt][warp][0][0]),
-                        mapa_shared(smem_u32(&sm.step_bar[nxt]), lane));
+        {
+          const int n = lane & 7;
+          const uint4 val = *reinterpret_cast<const uint4*>(&sm.stage[warp][n][0]);
+          const uint32_t laddr = smem_u32(&sm.h16[nxt][tg][n][0]);
+          const uint32_t lbar = smem_u32(&sm.step_bar[nxt]);
+#pragma unroll
+          for (int dst = (lane >> 3); dst < CL; dst += 4)
+            st_async_v4(mapa_shared(laddr, dst), val, mapa_shared(lbar, dst));
         }
-        // ---- hand the step's outputs to the I/O warps
+        if (clk_on) t4 = clock64();
+        // ---- in the shadow of the DSMEM transit: outputs -> I/O warps, next step's projections <- ring
         const int so = k % RO;
         if (k >= RO) mbar_wait(&sm.out_empty[so], ((k / RO) - 1) & 1);
         *reinterpret_cast<float2*>(&sm.outr[so][0][ul][2 * q]) = make_float2(hn[0], hn[1]);
         *reinterpret_cast<float2*>(&sm.outr[so][1][ul][2 * q]) = make_float2(zz[0], zz[1]);
         *reinterpret_cast<float2*>(&sm.outr[so][2][ul][2 * q]) = make_float2(hcv[0], hcv[1]);
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&sm.in_empty[si]);
-          mbar_arrive(&sm.out_full[so]);
+        if (lane == 0) mbar_arrive(&sm.out_full[so]);
+        if (k + 1 < T) {
+          const int si = (k + 1) % RI;
+          mbar_wait(&sm.in_full[si], ((k + 1) / RI) & 1);
+          ph = *reinterpret_cast<const float2*>(&sm.inr[si][0][ul][2 * q]);
+          pz = *reinterpret_cast<const float2*>(&sm.inr[si][1][ul][2 * q]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm.in_empty[si]);
+        }
+        if (clk_on) {
+          const long long t5 = clock64();
+          tsum[0] += t1 - t0; tsum[1] += t2 - t1; tsum[2] += t3 - t2; tsum[3] += t4 - t3; tsum[4] += t5 - t4;
         }
       }
+      if (clk_on)
+        for (int i = 0; i < 6; ++i) a.dbg_clk[i] = tsum[i];
       mbar_wait(&sm.step_bar[T & 1], ((T - 1) >> 1) & 1);  // drain the last incoming fill
     }
   } else {
@@ -243,11 +270,31 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_fwd_ws_kernel(const RecFwdA
     const long long gate_z = static_cast<long long>(H) * a.ldp;
     const bool do_store = !(a.dbg & 1);
     const bool do_load = !(a.dbg & 2);
+    // fast path: groups of 4 consecutive rows are contiguous and 16-byte aligned in every channel-major
+    // array when B % 4 == 0 -> one thread moves (unit, 4 rows) with 16-byte cp.async / float4 stores
+    const bool vec = (B % 4 == 0) && (a.ldp % 4 == 0) && (a.ldt % 4 == 0);
+    const int vul = tid >> 1, vr0 = (tid & 1) * 4;  // this thread's (unit, first row) in the fast path
+    const int vu = cta_ubase + vul;
+    const int vrr = cl * kRows + vr0;
+    const bool vok = (vul < UPC) && (vu < H) && (vrr < nrows);
+    const int vd = (vok && vrr >= B) ? 1 : 0;
+    const int vb = vrr - vd * B;
+    const int vcstep = vd ? -B : B;
+    const long long vcol0 = vd ? static_cast<long long>(T - 1) * B + vb : vb;
+    const long long vchan = static_cast<long long>(vd * H + vu) * a.ldt;
+    const long long vpch = static_cast<long long>(vu) * a.ldp;
+    float4 vhp = make_float4(0.f, 0.f, 0.f, 0.f);
 
     auto issue_load = [&](int kl) {  // projections of step kl -> in-ring
       const int s = kl % RI;
       if (kl >= RI) mbar_wait(&sm.in_empty[s], ((kl / RI) - 1) & 1);
-      if (do_load) {
+      if (do_load && vec) {
+        if (vok) {
+          const long long col = vcol0 + static_cast<long long>(kl) * vcstep;
+          cp_async_16(&sm.inr[s][0][vul][vr0], a.PT + vpch + col);
+          cp_async_16(&sm.inr[s][1][vul][vr0], a.PT + vpch + gate_z + col);
+        }
+      } else if (do_load) {
 #pragma unroll
         for (int j = 0; j < NE; ++j) {
           if (colv[j] >= 0) {
@@ -265,7 +312,37 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_fwd_ws_kernel(const RecFwdA
       if (k + RI - 1 < T) issue_load(k + RI - 1);
       const int s = k % RO;
       mbar_wait(&sm.out_full[s], (k / RO) & 1);
-      if (do_store) {
+      if (do_store && vec) {
+        if (vok) {
+          const long long idx = vchan + vcol0 + static_cast<long long>(k) * vcstep;
+          const float4 h4 = *reinterpret_cast<const float4*>(&sm.outr[s][0][vul][vr0]);
+          if (a.HT) *reinterpret_cast<float4*>(a.HT + idx) = h4;
+          if (a.ZT) *reinterpret_cast<float4*>(a.ZT + idx) = *reinterpret_cast<const float4*>(&sm.outr[s][1][vul][vr0]);
+          if (a.HCT) *reinterpret_cast<float4*>(a.HCT + idx) = *reinterpret_cast<const float4*>(&sm.outr[s][2][vul][vr0]);
+          if (a.HT16) {
+            uint2 pk16;
+            pk16.x = pack_f16x2_sat(h4.x, h4.y);
+            pk16.y = pack_f16x2_sat(h4.z, h4.w);
+            *reinterpret_cast<uint2*>(a.HT16 + idx) = pk16;
+          }
+          if (a.HP16) {
+            uint2 pk16;
+            pk16.x = pack_f16x2_sat(vhp.x, vhp.y);
+            pk16.y = pack_f16x2_sat(vhp.z, vhp.w);
+            *reinterpret_cast<uint2*>(a.HP16 + idx) = pk16;
+          }
+          vhp = h4;
+          if (a.Y32 || a.Y16) {
+            const long long col = vcol0 + static_cast<long long>(k) * vcstep;
+            const float hv[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (a.Y32) a.Y32[(col + i) * a.ldy32 + vd * H + vu] = hv[i];
+              if (a.Y16) a.Y16[(col + i) * a.ldy16 + vd * H + vu] = f16_sat(hv[i]);
+            }
+          }
+        }
+      } else if (do_store) {
 #pragma unroll
         for (int j = 0; j < NE; ++j) {
           if (colv[j] >= 0) {
@@ -316,7 +393,7 @@ struct BwdWs {
   static constexpr int NT = CL * MT;
   static constexpr int UPC = 8 * MT;
   __half g16[2][2][NT][kRows][8];          // [buffer][gate da,dpz][tile][row][8 units]
-  __half stage[2][NWC][2][kRows][8];
+  __half stage[NWC][2][kRows][8];
   float xbuf[2][MT16][2][32][2];
   float inr[RI][4][UPC][kRows];            // [slot][dy, z, hc, hprev][unit][row]
   __half outr[RO][2][UPC][kRows];          // [slot][da, dpz][unit][row]  (scaled fp16)
@@ -413,54 +490,62 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_bwd_ws_kernel(const RecBwdA
       constexpr uint32_t kBufBytes = 2 * kGateBytes;
       const int act = a.act;
 
+      const bool clk_on = a.dbg_clk != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+      long long tsum[6] = {0, 0, 0, 0, 0, 0};
+      // operands of the first processed step (later ones are fetched in the shadow of the transit)
+      mbar_wait(&sm.in_full[0], 0);
+      float2 dy = *reinterpret_cast<const float2*>(&sm.inr[0][0][sl][2 * q]);
+      float2 zz = *reinterpret_cast<const float2*>(&sm.inr[0][1][sl][2 * q]);
+      float2 hc = *reinterpret_cast<const float2*>(&sm.inr[0][2][sl][2 * q]);
+      float2 hp = *reinterpret_cast<const float2*>(&sm.inr[0][3][sl][2 * q]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.in_empty[0]);
+      // masks are 0/1 in training; eval uses the scalar (1-p): y = hc / m via one reciprocal
+      const float rm0 = (msk[0] != 0.f) ? __frcp_rn(msk[0]) : 0.f;
+      const float rm1 = (msk[1] != 0.f) ? __frcp_rn(msk[1]) : 0.f;
       for (int k = T - 1; k >= 0; --k) {
         const int it = T - 1 - k;
         const int buf = k & 1;
+        long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+        if (clk_on) t0 = clock64();
         if (threadIdx.x == 0) mbar_arrive_expect_tx(&sm.step_bar[buf], kTxBytes);
         // ---------------- phase A: pointwise backward of step k ----------------
-        const int si = it % RI;
-        mbar_wait(&sm.in_full[si], (it / RI) & 1);
-        const float2 dy = *reinterpret_cast<const float2*>(&sm.inr[si][0][sl][2 * q]);
-        const float2 zz = *reinterpret_cast<const float2*>(&sm.inr[si][1][sl][2 * q]);
-        const float2 hc = *reinterpret_cast<const float2*>(&sm.inr[si][2][sl][2 * q]);
-        float2 hp = *reinterpret_cast<const float2*>(&sm.inr[si][3][sl][2 * q]);
         if (k == 0) hp = make_float2(0.f, 0.f);
-        float da[2], dpz[2], keep[2];
+        float keep[2];
+        __half2 da16, dz16;
         {
-          const float dh = dy.x + carry[0];
-          const float m = msk[0];
-          const float y = (m != 0.f) ? hc.x / m : 0.f;
-          float dav = dh * (1.f - zz.x) * m * act_bwd_from_out(act, y);
-          float dpzv = dh * (hp.x - hc.x) * zz.x * (1.f - zz.x);
-          if (!rok[0]) { dav = 0.f; dpzv = 0.f; }
-          da[0] = dav; dpz[0] = dpzv; keep[0] = dh * zz.x;
+          const float dh0 = dy.x + carry[0], dh1 = dy.y + carry[1];
+          float da0 = dh0 * (1.f - zz.x) * msk[0] * act_bwd_from_out(act, hc.x * rm0);
+          float da1 = dh1 * (1.f - zz.y) * msk[1] * act_bwd_from_out(act, hc.y * rm1);
+          float dz0 = dh0 * (hp.x - hc.x) * zz.x * (1.f - zz.x);
+          float dz1 = dh1 * (hp.y - hc.y) * zz.y * (1.f - zz.y);
+          if (!rok[0]) { da0 = 0.f; dz0 = 0.f; }
+          if (!rok[1]) { da1 = 0.f; dz1 = 0.f; }
+          keep[0] = dh0 * zz.x;
+          keep[1] = dh1 * zz.y;
+          da16 = __halves2half2(f16_sat(da0 * s), f16_sat(da1 * s));
+          dz16 = __halves2half2(f16_sat(dz0 * s), f16_sat(dz1 * s));
         }
-        {
-          const float dh = dy.y + carry[1];
-          const float m = msk[1];
-          const float y = (m != 0.f) ? hc.y / m : 0.f;
-          float dav = dh * (1.f - zz.y) * m * act_bwd_from_out(act, y);
-          float dpzv = dh * (hp.y - hc.y) * zz.y * (1.f - zz.y);
-          if (!rok[1]) { dav = 0.f; dpzv = 0.f; }
-          da[1] = dav; dpz[1] = dpzv; keep[1] = dh * zz.y;
-        }
-        const __half2 da16 = __halves2half2(f16_sat(da[0] * s), f16_sat(da[1] * s));
-        const __half2 dz16 = __halves2half2(f16_sat(dpz[0] * s), f16_sat(dpz[1] * s));
+        if (clk_on) t1 = clock64();
         if (warp_ok) {
-          sm.stage[buf][warp][0][2 * q][g] = __low2half(da16);
-          sm.stage[buf][warp][0][2 * q + 1][g] = __high2half(da16);
-          sm.stage[buf][warp][1][2 * q][g] = __low2half(dz16);
-          sm.stage[buf][warp][1][2 * q + 1][g] = __high2half(dz16);
-          fence_proxy_async_smem();
+          sm.stage[warp][0][2 * q][g] = __low2half(da16);
+          sm.stage[warp][0][2 * q + 1][g] = __high2half(da16);
+          sm.stage[warp][1][2 * q][g] = __low2half(dz16);
+          sm.stage[warp][1][2 * q + 1][g] = __high2half(dz16);
         }
         __syncwarp();
-        if (warp_ok && lane < 2 * CL) {  // one 128-byte tile per (gate, destination CTA)
-          const int gate = lane & 1, dstc = lane >> 1;
-          const uint32_t dst = smem_u32(&sm.g16[buf][gate][tg][0][0]);
-          bulk_push_128(mapa_shared(dst, dstc), smem_u32(&sm.stage[buf][warp][gate][0][0]),
-                        mapa_shared(smem_u32(&sm.step_bar[buf]), dstc));
+        if (warp_ok) {  // 16 rows of 16 bytes (8 rows x 2 gates), each to every CTA of the cluster
+          const int n = lane & 7;
+          const int gate = (lane >> 3) & 1;
+          const uint4 val = *reinterpret_cast<const uint4*>(&sm.stage[warp][gate][n][0]);
+          const uint32_t laddr = smem_u32(&sm.g16[buf][gate][tg][n][0]);
+          const uint32_t lbar = smem_u32(&sm.step_bar[buf]);
+#pragma unroll
+          for (int dst = (lane >> 4); dst < CL; dst += 2)
+            st_async_v4(mapa_shared(laddr, dst), val, mapa_shared(lbar, dst));
         }
-        // ---- outputs of the step (scaled fp16) to the I/O warps
+        if (clk_on) t2 = clock64();
+        // ---- in the shadow of the transit: outputs -> I/O warps, next step's operands <- ring
         const int so = it % RO;
         if (it >= RO) mbar_wait(&sm.out_empty[so], ((it / RO) - 1) & 1);
         if (warp_ok) {
@@ -468,11 +553,20 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_bwd_ws_kernel(const RecBwdA
           *reinterpret_cast<__half2*>(&sm.outr[so][1][slot][2 * q]) = dz16;
         }
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&sm.in_empty[si]);
-          mbar_arrive(&sm.out_full[so]);
+        if (lane == 0) mbar_arrive(&sm.out_full[so]);
+        if (k > 0) {
+          const int si = (it + 1) % RI;
+          mbar_wait(&sm.in_full[si], ((it + 1) / RI) & 1);
+          dy = *reinterpret_cast<const float2*>(&sm.inr[si][0][sl][2 * q]);
+          zz = *reinterpret_cast<const float2*>(&sm.inr[si][1][sl][2 * q]);
+          hc = *reinterpret_cast<const float2*>(&sm.inr[si][2][sl][2 * q]);
+          hp = *reinterpret_cast<const float2*>(&sm.inr[si][3][sl][2 * q]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm.in_empty[si]);
         }
+        if (clk_on) t3 = clock64();
         mbar_wait(&sm.step_bar[buf], (it >> 1) & 1);
+        if (clk_on) t4 = clock64();
 
         // ---------------- phase B: U^T [da; dpz] for the carry into step k-1 ----------------
         if (k > 0) {
@@ -503,7 +597,13 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_bwd_ws_kernel(const RecBwdA
           carry[0] = keep[0] + ((half ? c4[2] : c4[0]) + o0) * inv_s;
           carry[1] = keep[1] + ((half ? c4[3] : c4[1]) + o1) * inv_s;
         }
+        if (clk_on && k > 0) {
+          const long long t5 = clock64();
+          tsum[0] += t1 - t0; tsum[1] += t2 - t1; tsum[2] += t3 - t2; tsum[3] += t4 - t3; tsum[4] += t5 - t4;
+        }
       }
+      if (clk_on)
+        for (int i = 0; i < 6; ++i) a.dbg_clk[i] = tsum[i];
     }
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
@@ -529,12 +629,30 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_bwd_ws_kernel(const RecBwdA
     const long long dir_stride = 2 * gate_stride;
     const bool do_store = !(a.dbg & 1);
     const bool do_load = !(a.dbg & 2);
+    const bool vec = (B % 4 == 0) && (a.ldt % 4 == 0);  // see the forward kernel
+    const int vul = tid >> 1, vr0 = (tid & 1) * 4;
+    const int vu = cta_ubase + vul;
+    const int vrr = cl * kRows + vr0;
+    const bool vok = (vul < UPC) && (vu < H) && (vrr < nrows);
+    const int vd = (vok && vrr >= B) ? 1 : 0;
+    const int vb = vrr - vd * B;
+    const int vcstep = vd ? -B : B;
+    const long long vcol0 = vd ? static_cast<long long>(T - 1) * B + vb : vb;
+    const long long vchan = static_cast<long long>(vd * H + vu) * a.ldt;
 
     auto issue_load = [&](int it) {  // operands of step k = T-1-it -> in-ring slot it % RI
       const int k = T - 1 - it;
       const int s = it % RI;
       if (it >= RI) mbar_wait(&sm.in_empty[s], ((it / RI) - 1) & 1);
-      if (do_load) {
+      if (do_load && vec) {
+        if (vok) {
+          const long long idx = vchan + vcol0 + static_cast<long long>(k) * vcstep;
+          cp_async_16(&sm.inr[s][0][vul][vr0], a.dYT + idx);
+          cp_async_16(&sm.inr[s][1][vul][vr0], a.ZT + idx);
+          cp_async_16(&sm.inr[s][2][vul][vr0], a.HCT + idx);
+          if (k > 0) cp_async_16(&sm.inr[s][3][vul][vr0], a.HT + idx - vcstep);
+        }
+      } else if (do_load) {
 #pragma unroll
         for (int j = 0; j < NE; ++j) {
           if (colv[j] >= 0) {
@@ -555,7 +673,15 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_bwd_ws_kernel(const RecBwdA
       const int k = T - 1 - it;
       const int s = it % RO;
       mbar_wait(&sm.out_full[s], (it / RO) & 1);
-      if (do_store) {
+      if (do_store && vec) {
+        if (vok) {
+          const long long idx = vd * dir_stride + static_cast<long long>(vu) * a.ldt + vcol0 +
+                                static_cast<long long>(k) * vcstep;
+          *reinterpret_cast<uint2*>(a.GT16 + idx) = *reinterpret_cast<const uint2*>(&sm.outr[s][0][vul][vr0]);
+          *reinterpret_cast<uint2*>(a.GT16 + idx + gate_stride) =
+              *reinterpret_cast<const uint2*>(&sm.outr[s][1][vul][vr0]);
+        }
+      } else if (do_store) {
 #pragma unroll
         for (int j = 0; j < NE; ++j) {
           if (colv[j] >= 0) {
@@ -609,10 +735,16 @@ int launch_ws(const Args& a, int cluster, int nclusters, size_t smem, cudaStream
 #define PK_BWD_WS(KT, MT, CL) \
   return launch_ws<RecBwdArgs, ligru_bwd_ws_kernel<KT, MT, CL>>(a, CL, nclusters, sizeof(BwdWs<KT, MT, CL>) + 128, stream)
 
+long long* g_dbg_clk = nullptr;
+
 }  // namespace
 
+void set_debug_clock_buffer(long long* dev_ptr) { g_dbg_clk = dev_ptr; }
+
 // (k-tiles, 8-unit tiles per CTA, cluster size): CL * 8 * MT >= 16 * KT >= H
-int ligru_fwd_ws(const RecFwdArgs& a, cudaStream_t stream) {
+int ligru_fwd_ws(const RecFwdArgs& a_in, cudaStream_t stream) {
+  RecFwdArgs a = a_in;
+  a.dbg_clk = g_dbg_clk;
   const int nclusters = (a.ndir * a.B + kRows - 1) / kRows;
   const int H = a.H;
   if (H <= 256) { PK_FWD_WS(16, 4, 8); }
@@ -620,7 +752,9 @@ int ligru_fwd_ws(const RecFwdArgs& a, cudaStream_t stream) {
   if (H <= 512) { PK_FWD_WS(32, 7, 10); }
   PK_FWD_WS(35, 7, 10);
 }
-int ligru_bwd_ws(const RecBwdArgs& a, cudaStream_t stream) {
+int ligru_bwd_ws(const RecBwdArgs& a_in, cudaStream_t stream) {
+  RecBwdArgs a = a_in;
+  a.dbg_clk = g_dbg_clk;
   const int nclusters = (a.ndir * a.B + kRows - 1) / kRows;
   const int H = a.H;
   if (H <= 256) { PK_BWD_WS(16, 4, 8); }

@@ -35,6 +35,7 @@
     }                                                                 \
   } while (0)
 
+extern "C" void pk_debug_set_clock_buffer(void*);  // bring-up hook, not in the public header
 static int g_fail = 0;
 static std::mt19937 rng(1234);
 
@@ -590,6 +591,23 @@ static void bench_all() {
       });
       printf("ligru_bwd %s: %.3f ms/layer  (%.3f us/step) rc=%d %s\n", v.name, ms, ms * 1000.f / T, rc,
              rc ? pk_last_error() : "");
+    }
+    {  // per-phase cycle breakdown of the critical-path warp (CTA 0, warp 0)
+      Dev<long long> dclk(8);
+      pk_debug_set_clock_buffer(dclk.p);
+      pk_rnn_layer_fwd(PK_CELL_LIGRU, T, B, H, ndir, PK_ACT_RELU, dPT.p, ld, dsc.p, dsh.p, dU.p, dmask.p, 1.f, dY.p, 1100,
+                       dY16.p, 1104, dHT.p, dHT16.p, dHP16.p, dZT.p, dHCT.p, ld, nullptr);
+      CK(cudaDeviceSynchronize());
+      auto c = dclk.down();
+      printf("fwd phases (cycles/step): wait_step %.0f | mma %.0f | gates %.0f | stage+push %.0f | rings(shadow) %.0f | - %.0f\n",
+             c[0] / (double)T, c[1] / (double)T, c[2] / (double)T, c[3] / (double)T, c[4] / (double)T, c[5] / (double)T);
+      pk_rnn_layer_bwd(PK_CELL_LIGRU, T, B, H, ndir, PK_ACT_RELU, ddY.p, dHT.p, dZT.p, dHCT.p, ld, dU.p, dmask.p, 1.f, dgs.p,
+                       dGT.p, dGT16.p, nullptr);
+      CK(cudaDeviceSynchronize());
+      c = dclk.down();
+      printf("bwd phases (cycles/step): phaseA %.0f | stage+push %.0f | rings(shadow) %.0f | wait_step %.0f | mma+xchg+carry %.0f | - %.0f\n",
+             c[0] / (double)T, c[1] / (double)T, c[2] / (double)T, c[3] / (double)T, c[4] / (double)T, c[5] / (double)T);
+      pk_debug_set_clock_buffer(nullptr);
     }
   }
   struct G { const char* name; int M, N, K, sk; };
