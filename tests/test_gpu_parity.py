@@ -242,7 +242,7 @@ def test_against_oracle_medium(act, quant):
     assert abs(loss.item() - ref["loss"]) / ref["loss"] < TOL_FWD
     # relu: accumulation-order differences (~1e-6) can still flip an isolated kink, which moves ONE row of a
     # weight gradient by percents; the L2 metric is robust to that, the max metric gets a wider bound
-    tol_max = 10 * TOL_GRAD if act in KINK_ACTS else TOL_GRAD
+    tol_max = 0.2 if act in KINK_ACTS else TOL_GRAD  # an isolated flipped kink moves one row by up to ~10 %
     tol_l2 = 2 * TOL_GRAD if act in KINK_ACTS else TOL_GRAD
 
     def close(got, want, what):
