@@ -71,20 +71,22 @@ int pk_version(void);
  *   (sum, sum of squares) of the OUTPUT (BatchNorm batch statistics of a channel-major
  *   projection);  accumulate: C += ...;  split_k > 1 partitions K over gridDim.z with fp32
  *   atomics;  a_k0 / b_k0 (multiples of 16 bytes) select a sub-range of each operand's K axis;
- *   a_kext / b_kext: valid extent of that axis (0 -> k0 + K), reads past it return zeros.
+ *   a_kext / b_kext: valid extent of that axis (0 -> k0 + K), reads past it return zeros;
+ *   amax_bits: optional device uint32 receiving atomicMax of |C| (float bit pattern) so that the
+ *   consumer's loss scale needs no extra pass (see pk_amax_finalize).
  * Replaces: nn.Linear forward/backward GEMMs (neural_networks.py:1114-1115, :432-435,
  * :609-611, :138-148 and their autograd transposes). */
 int pk_gemm_tn(int dtype, int M, int N, int K, const void* A, int64_t lda, int64_t a_k0,
                int64_t a_kext, const void* B, int64_t ldb, int64_t b_k0, int64_t b_kext, float* C,
                int64_t ldc, const float* bias, int bias_mode, double* rowstats, float alpha,
-               const float* alpha_dev, int accumulate, int split_k, void* stream);
+               const float* alpha_dev, int accumulate, int split_k, void* amax_bits, void* stream);
 
 /* outT[c][r] = in[r][c] (fp32, optional) plus optional fp16 copies scaled by *scale_dev:
  * outT16 (channel-major) and in16 (row-major).  Replaces flip/cat/view shuffles
  * (neural_networks.py:1095-1097, :1144-1150) and feeds the K-major GEMM operands. */
 int pk_transpose_f32(const float* in, int64_t ldi, int R, int C, float* outT, int64_t ldo,
                      void* outT16, int64_t ldo16, void* in16, int64_t ldi16,
-                     const float* scale_dev, void* stream);
+                     const float* scale_dev, void* amax_bits, void* stream);
 int pk_convert_f16(const float* in, int64_t ldi, int R, int C, void* out, int64_t ldo,
                    const float* scale_dev, void* stream);
 
@@ -92,6 +94,9 @@ int pk_convert_f16(const float* in, int64_t ldi, int R, int C, void* out, int64_
  * that keeps fp16 gradient operands in range; scale_out[1] = 2^-k.  amax_scratch: 1 float. */
 int pk_amax_scale(const float* x, int64_t ld, int R, int C, float target_log2,
                   float* amax_scratch, float* scale_out, void* stream);
+/* same, from an amax accumulated by a producer kernel (pk_gemm_tn / pk_transpose_f32 `amax_bits`);
+ * re-zeroes the accumulator for its next use. */
+int pk_amax_finalize(void* amax_bits, float target_log2, float* scale_out, void* stream);
 
 /* nn.BatchNorm1d(C, momentum) over the projection rows (neural_networks.py:1070-1071,
  * :1118-1124): stats = [C][2] doubles (sum, sumsq over the n_unique = T*B de-duplicated rows);

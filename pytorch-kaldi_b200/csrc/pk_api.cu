@@ -46,7 +46,7 @@ void pk_debug_set_clock_buffer(void* dev_ptr) { pk::set_debug_clock_buffer(stati
 int pk_gemm_tn(int dtype, int M, int N, int K, const void* A, int64_t lda, int64_t a_k0, int64_t a_kext,
                const void* B, int64_t ldb, int64_t b_k0, int64_t b_kext, float* C, int64_t ldc,
                const float* bias, int bias_mode, double* rowstats, float alpha, const float* alpha_dev,
-               int accumulate, int split_k, void* stream) {
+               int accumulate, int split_k, void* amax_bits, void* stream) {
   PK_REQUIRE(A && B && C, "pk_gemm_tn: null operand");
   GemmArgs a;
   a.dtype = dtype; a.M = M; a.N = N; a.K = K;
@@ -54,14 +54,17 @@ int pk_gemm_tn(int dtype, int M, int N, int K, const void* A, int64_t lda, int64
   a.a_k0 = a_k0; a.a_kext = a_kext; a.b_k0 = b_k0; a.b_kext = b_kext;
   a.bias = bias; a.bias_mode = bias_mode; a.rowstats = rowstats;
   a.alpha = alpha; a.alpha_dev = alpha_dev; a.accumulate = accumulate; a.split_k = split_k;
+  a.amax_bits = static_cast<unsigned int*>(amax_bits);
   return gemm_tn(a, static_cast<cudaStream_t>(stream));
 }
 
 int pk_transpose_f32(const float* in, int64_t ldi, int R, int C, float* outT, int64_t ldo, void* outT16,
-                     int64_t ldo16, void* in16, int64_t ldi16, const float* scale_dev, void* stream) {
+                     int64_t ldo16, void* in16, int64_t ldi16, const float* scale_dev, void* amax_bits,
+                     void* stream) {
   PK_REQUIRE(in != nullptr, "pk_transpose_f32: null input");
   return transpose_f32(in, ldi, R, C, outT, ldo, static_cast<__half*>(outT16), ldo16,
-                       static_cast<__half*>(in16), ldi16, scale_dev, static_cast<cudaStream_t>(stream));
+                       static_cast<__half*>(in16), ldi16, scale_dev, static_cast<unsigned int*>(amax_bits),
+                       static_cast<cudaStream_t>(stream));
 }
 
 int pk_convert_f16(const float* in, int64_t ldi, int R, int C, void* out, int64_t ldo, const float* scale_dev,
@@ -75,6 +78,11 @@ int pk_amax_scale(const float* x, int64_t ld, int R, int C, float target_log2, f
                   float* scale_out, void* stream) {
   PK_REQUIRE(x && amax_scratch && scale_out, "pk_amax_scale: null pointer");
   return amax_scale(x, ld, R, C, target_log2, amax_scratch, scale_out, static_cast<cudaStream_t>(stream));
+}
+
+int pk_amax_finalize(void* amax_bits, float target_log2, float* scale_out, void* stream) {
+  PK_REQUIRE(amax_bits && scale_out, "pk_amax_finalize: null pointer");
+  return amax_finalize(static_cast<unsigned int*>(amax_bits), target_log2, scale_out, static_cast<cudaStream_t>(stream));
 }
 
 int pk_bn_finalize(const double* stats, int C, int64_t n_unique, int64_t n_ref, const float* gamma,

@@ -42,8 +42,9 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 __global__ void transpose_kernel(const float* __restrict__ in, long long ldi, int R, int C,
                                  float* __restrict__ outT, long long ldo, __half* __restrict__ outT16,
                                  long long ldo16, __half* __restrict__ in16, long long ldi16,
-                                 const float* __restrict__ scale_dev) {
+                                 const float* __restrict__ scale_dev, unsigned int* amax_bits) {
   __shared__ float tile[32][33];
+  float amax = 0.f;
   const float s = scale_dev ? __ldg(scale_dev) : 1.f;
   const int tiles_c = (C + 31) / 32;
   const long long ntiles = static_cast<long long>((R + 31) / 32) * tiles_c;
@@ -55,6 +56,7 @@ __global__ void transpose_kernel(const float* __restrict__ in, long long ldi, in
       float v = 0.f;
       if (r < R && c < C) {
         v = in[static_cast<long long>(r) * ldi + c];
+        amax = fmaxf(amax, fabsf(v));
         if (in16) in16[static_cast<long long>(r) * ldi16 + c] = f16_sat(v * s);
       }
       tile[i][threadIdx.x] = v;
@@ -69,6 +71,10 @@ __global__ void transpose_kernel(const float* __restrict__ in, long long ldi, in
       }
     }
     __syncthreads();
+  }
+  if (amax_bits) {
+    amax = warp_max(amax);
+    if (threadIdx.x == 0 && amax > 0.f) atomicMax(amax_bits, __float_as_uint(fminf(amax, 3.0e38f)));
   }
 }
 
@@ -100,7 +106,7 @@ __global__ void amax_kernel(const float* __restrict__ x, long long ld, int R, in
   m = warp_max(m);
   if ((threadIdx.x & 31) == 0) atomicMax(amax_bits, __float_as_uint(fminf(m, 3.0e38f)));
 }
-__global__ void scale_from_amax_kernel(const unsigned int* amax_bits, float target_log2, float* scale_out) {
+__global__ void scale_from_amax_kernel(unsigned int* amax_bits, float target_log2, float* scale_out, int rezero) {
   const float amax = __uint_as_float(*amax_bits);
   float s = 1.f;
   if (amax > 0.f) {
@@ -112,6 +118,7 @@ __global__ void scale_from_amax_kernel(const unsigned int* amax_bits, float targ
   }
   scale_out[0] = s;
   scale_out[1] = 1.f / s;
+  if (rezero) *amax_bits = 0u;
 }
 
 // ------------------------------------------------------------------------------------
@@ -201,51 +208,94 @@ __global__ void bn_bwd_sums_kernel(const BnBwdArgs a, double* __restrict__ sums 
 }
 
 // pass 2: dP = gamma*rstd*(g - mean(g) - p_hat*mean(g*p_hat)), written as scaled fp16 in both
-// layouts (channel-major for dW = dP^T X, row-major for dX = dP W) through a 32x32 smem transpose
-__global__ void bn_bwd_apply_kernel(const BnBwdArgs a, const double* __restrict__ sums) {
-  __shared__ float tile[32][33];
+// layouts (channel-major for dW = dP^T X, row-major for dX = dP W).  64x64 tiles through shared memory,
+// every global access is a 4-byte (half2) or 8-byte (float2) vector along the contiguous axis.
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a, const double* __restrict__ sums) {
+  __shared__ float tile[64][65];
   const float s = a.gscale ? __ldg(a.gscale) : 1.f;
   const float inv_s = (a.GT16 && a.gscale) ? 1.f / s : 1.f;
-  const int tiles_i = static_cast<int>((a.n + 31) / 32);
-  const long long ntiles = static_cast<long long>((a.C + 31) / 32) * tiles_i;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // (32, 8)
+  const int tiles_i = static_cast<int>((a.n + 63) / 64);
+  const long long ntiles = static_cast<long long>((a.C + 63) / 64) * tiles_i;
   const double inv_n = 1.0 / static_cast<double>(a.n);
+  const bool vec_in = ((a.ldt & 1) == 0) && ((a.ldp & 1) == 0);
   for (long long tidx = blockIdx.x; tidx < ntiles; tidx += gridDim.x) {
-    const int c0 = static_cast<int>(tidx / tiles_i) * 32;
-    const long long i0 = static_cast<long long>(tidx % tiles_i) * 32;
-    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
-      const int c = c0 + j;
-      const long long i = i0 + threadIdx.x;
-      float v = 0.f;
+    const int c0 = static_cast<int>(tidx / tiles_i) * 64;
+    const long long i0 = static_cast<long long>(tidx % tiles_i) * 64;
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      const int cr = ty + 8 * jj;
+      const int c = c0 + cr;
+      const long long i = i0 + 2 * tx;
+      float v0 = 0.f, v1 = 0.f;
       if (c < a.C && i < a.n) {
+        const bool two = (i + 1 < a.n);
         const long long o0 = static_cast<long long>(c) * a.ldt + i;
         const long long o1 = static_cast<long long>(a.C + c) * a.ldt + i;
-        float g = a.GT ? a.GT[o0] : __half2float(a.GT16[o0]) * inv_s;
-        if (a.ndir == 2) g += a.GT ? a.GT[o1] : __half2float(a.GT16[o1]) * inv_s;
+        float g0, g1 = 0.f;
+        if (a.GT) {
+          g0 = a.GT[o0];
+          if (two) g1 = a.GT[o0 + 1];
+          if (a.ndir == 2) { g0 += a.GT[o1]; if (two) g1 += a.GT[o1 + 1]; }
+        } else if (vec_in && two) {
+          float2 f = __half22float2(*reinterpret_cast<const __half2*>(a.GT16 + o0));
+          if (a.ndir == 2) {
+            const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(a.GT16 + o1));
+            f.x += f2.x; f.y += f2.y;
+          }
+          g0 = f.x * inv_s; g1 = f.y * inv_s;
+        } else {
+          g0 = __half2float(a.GT16[o0]);
+          if (two) g1 = __half2float(a.GT16[o0 + 1]);
+          if (a.ndir == 2) { g0 += __half2float(a.GT16[o1]); if (two) g1 += __half2float(a.GT16[o1 + 1]); }
+          g0 *= inv_s; g1 *= inv_s;
+        }
         if (a.use_bn) {
           const float rstd = a.rstd[c];
           const float gam = a.gamma ? a.gamma[c] : 1.f;
           if (a.training) {
-            const float ph = (a.PT[static_cast<long long>(c) * a.ldp + i] - a.mean[c]) * rstd;
+            const long long po = static_cast<long long>(c) * a.ldp + i;
+            float p0, p1 = 0.f;
+            if (vec_in && two) { const float2 pp = *reinterpret_cast<const float2*>(a.PT + po); p0 = pp.x; p1 = pp.y; }
+            else { p0 = a.PT[po]; if (two) p1 = a.PT[po + 1]; }
+            const float mean = a.mean[c];
             const float mg = static_cast<float>(sums[c] * inv_n);
             const float mgp = static_cast<float>(sums[a.C + c] * inv_n);
-            v = gam * rstd * (g - mg - ph * mgp);
+            const float k = gam * rstd;
+            v0 = k * (g0 - mg - (p0 - mean) * rstd * mgp);
+            v1 = k * (g1 - mg - (p1 - mean) * rstd * mgp);
           } else {
-            v = gam * rstd * g;
+            v0 = gam * rstd * g0;
+            v1 = gam * rstd * g1;
           }
         } else {
-          v = g;
+          v0 = g0; v1 = g1;
         }
-        v *= s;
-        if (a.dPT16) a.dPT16[static_cast<long long>(c) * a.ld16t + i] = f16_sat(v);
+        v0 *= s; v1 *= s;
+        if (!two) v1 = 0.f;
+        if (a.dPT16) {
+          const long long oo = static_cast<long long>(c) * a.ld16t + i;
+          if (two && ((a.ld16t & 1) == 0)) *reinterpret_cast<__half2*>(a.dPT16 + oo) = __halves2half2(f16_sat(v0), f16_sat(v1));
+          else { a.dPT16[oo] = f16_sat(v0); if (two) a.dPT16[oo + 1] = f16_sat(v1); }
+        }
       }
-      tile[j][threadIdx.x] = v;
+      tile[cr][2 * tx] = v0;
+      tile[cr][2 * tx + 1] = v1;
     }
     __syncthreads();
     if (a.dP16) {
-      for (int j = threadIdx.y; j < 32; j += blockDim.y) {
-        const long long i = i0 + j;
-        const int c = c0 + threadIdx.x;
-        if (c < a.C && i < a.n) a.dP16[i * a.ld16r + c] = f16_sat(tile[threadIdx.x][j]);
+#pragma unroll
+      for (int ii = 0; ii < 8; ++ii) {
+        const int ir = ty + 8 * ii;
+        const long long i = i0 + ir;
+        const int c = c0 + 2 * tx;
+        if (i < a.n && c < a.C) {
+          const float v0 = tile[2 * tx][ir];
+          const float v1 = tile[2 * tx + 1][ir];
+          const long long oo = i * a.ld16r + c;
+          if (c + 1 < a.C && ((a.ld16r & 1) == 0)) *reinterpret_cast<__half2*>(a.dP16 + oo) = __halves2half2(f16_sat(v0), f16_sat(v1));
+          else { a.dP16[oo] = f16_sat(v0); if (c + 1 < a.C) a.dP16[oo + 1] = f16_sat(v1); }
+        }
       }
     }
     __syncthreads();
@@ -387,11 +437,12 @@ inline int grid_for(long long work_items, int per_block) {
 }  // namespace
 
 int transpose_f32(const float* in, long long ldi, int R, int C, float* outT, long long ldo, __half* outT16,
-                  long long ldo16, __half* in16, long long ldi16, const float* scale_dev, cudaStream_t stream) {
+                  long long ldo16, __half* in16, long long ldi16, const float* scale_dev, unsigned int* amax_bits,
+                  cudaStream_t stream) {
   PK_REQUIRE(R > 0 && C > 0, "transpose: empty");
   const long long ntiles = static_cast<long long>((R + 31) / 32) * ((C + 31) / 32);
   transpose_kernel<<<grid_for(ntiles, 1), dim3(32, 8), 0, stream>>>(in, ldi, R, C, outT, ldo, outT16, ldo16,
-                                                                     in16, ldi16, scale_dev);
+                                                                     in16, ldi16, scale_dev, amax_bits);
   PK_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -411,7 +462,13 @@ int amax_scale(const float* x, long long ld, int R, int C, float target_log2, fl
   amax_kernel<<<grid_for(static_cast<long long>(R) * C, 2048), 256, 0, stream>>>(
       x, ld, R, C, reinterpret_cast<unsigned int*>(amax_scratch));
   scale_from_amax_kernel<<<1, 1, 0, stream>>>(reinterpret_cast<unsigned int*>(amax_scratch), target_log2,
-                                              scale_out);
+                                              scale_out, 0);
+  PK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int amax_finalize(unsigned int* amax_bits, float target_log2, float* scale_out, cudaStream_t stream) {
+  scale_from_amax_kernel<<<1, 1, 0, stream>>>(amax_bits, target_log2, scale_out, 1);
   PK_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -439,7 +496,7 @@ int bn_bwd(const BnBwdArgs& a, cudaStream_t stream) {
   PK_REQUIRE(a.sums_scratch != nullptr, "bn_bwd: sums_scratch (2*C doubles) required");
   double* sums = a.sums_scratch;
   bn_bwd_sums_kernel<<<a.C, 256, 0, stream>>>(a, sums);
-  const long long ntiles = static_cast<long long>((a.C + 31) / 32) * ((a.n + 31) / 32);
+  const long long ntiles = static_cast<long long>((a.C + 63) / 64) * ((a.n + 63) / 64);
   bn_bwd_apply_kernel<<<grid_for(ntiles, 1), dim3(32, 8), 0, stream>>>(a, sums);
   PK_CHECK_CUDA(cudaGetLastError());
   return 0;

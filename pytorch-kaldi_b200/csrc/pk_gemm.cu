@@ -43,6 +43,7 @@ struct GemmDev {
   int kb_per_split;
   int bk_elems;
   int a_k0, b_k0;  // element offsets of the contraction range inside each operand's rows
+  unsigned int* amax_bits;  // optional: atomicMax of |C| (float bits) for the next loss scale
 };
 
 template <int DT>  // 0 = f16 operands, 2 = tf32 (fp32 operands)
@@ -134,6 +135,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float bias_m = 0.f;
     if (add_bias && p.bias_mode == 2 && gm < p.M) bias_m = __ldg(p.bias + gm);
     double s1 = 0.0, s2 = 0.0;
+    float amax = 0.f;
     float* crow = p.C + gm * p.ldc;
     const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
 #pragma unroll 1
@@ -150,6 +152,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (add_bias) x += (p.bias_mode == 1) ? ((gn0 + j < p.N) ? __ldg(p.bias + gn0 + j) : 0.f)
                                                 : bias_m;
           o[j] = x;
+        }
+        if (p.amax_bits) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (gn0 + j < p.N) amax = fmaxf(amax, fabsf(o[j]));
         }
         if (p.rowstats) {
 #pragma unroll
@@ -173,6 +180,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (gn0 + j < p.N) crow[gn0 + j] = o[j];
         }
       }
+    }
+    if (p.amax_bits) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+      if (lane == 0 && amax > 0.f) atomicMax(p.amax_bits, __float_as_uint(fminf(amax, 3.0e38f)));
     }
     if (p.rowstats && gm < p.M) {
       atomicAdd(p.rowstats + 2 * gm, s1);
@@ -265,6 +277,8 @@ int gemm_tn(const GemmArgs& a, cudaStream_t stream) {
   p.alpha = a.alpha;
   p.alpha_dev = a.alpha_dev;
   p.bk_elems = (a.dtype == PK_DT_F16) ? 64 : 32;
+  p.amax_bits = a.amax_bits;
+  PK_REQUIRE(!(a.amax_bits && (a.accumulate || a.split_k > 1)), "gemm_tn: amax needs a single-pass store epilogue");
   p.a_k0 = static_cast<int>(a.a_k0);
   p.b_k0 = static_cast<int>(a.b_k0);
   const int kb_total = (a.K + p.bk_elems - 1) / p.bk_elems;

@@ -29,6 +29,7 @@ struct GemmArgs {
   // contraction range: A[:, a_k0 : a_k0+K] . B[:, b_k0 : b_k0+K]^T; *_kext = valid extent of the
   // operand's K axis (0 -> k0 + K); reads past it return zeros
   long long a_k0 = 0, b_k0 = 0, a_kext = 0, b_kext = 0;
+  unsigned int* amax_bits = nullptr;  // optional atomicMax of |C| (float bits)
 };
 int gemm_tn(const GemmArgs& a, cudaStream_t stream);
 
@@ -88,7 +89,9 @@ void set_debug_clock_buffer(long long* dev_ptr);
 // out[c][r] = in[r][c]; optional fp16 copies. in is [R][ldi] fp32.
 int transpose_f32(const float* in, long long ldi, int R, int C, float* outT, long long ldo,
                   __half* outT16, long long ldo16, __half* in16, long long ldi16, const float* scale_dev,
-                  cudaStream_t stream);
+                  unsigned int* amax_bits, cudaStream_t stream);
+// scale_out[0] = 2^k, [1] = 2^-k from an amax accumulated by a producer; re-zeroes the accumulator
+int amax_finalize(unsigned int* amax_bits, float target_log2, float* scale_out, cudaStream_t stream);
 int convert_f16(const float* in, long long ldi, int R, int C, __half* out, long long ldo,
                 const float* scale_dev, cudaStream_t stream);
 // scale_out[0] = 2^k, scale_out[1] = 2^-k

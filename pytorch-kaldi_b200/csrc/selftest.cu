@@ -106,7 +106,7 @@ static void test_gemm(int dtype, int M, int N, int K, int bias_mode, bool stats,
   }
   const float alpha = 0.5f;
   PKC(pk_gemm_tn(dtype, M, N, K, dA, lda, 0, 0, dB, ldb, 0, 0, dC.p, ldc, bias_mode ? dbias.p : nullptr, bias_mode,
-                 stats ? dstats.p : nullptr, alpha, nullptr, accumulate, splitk, nullptr));
+                 stats ? dstats.p : nullptr, alpha, nullptr, accumulate, splitk, nullptr, nullptr));
   CK(cudaDeviceSynchronize());
   auto C = dC.down();
   auto st = dstats.down();
@@ -154,7 +154,7 @@ static void test_gemm_shift(int M, int N, int KX, int a0, int b0) {
   dA.up(hA);
   dB.up(hB);
   PKC(pk_gemm_tn(PK_F16, M, N, K, dA.p, ld, a0, KX, dB.p, ld, b0, KX, dC.p, N, nullptr, 0, nullptr, 1.f, nullptr, 0, 3,
-                 nullptr));
+                 nullptr, nullptr));
   CK(cudaDeviceSynchronize());
   auto C = dC.down();
   double e = 0;
@@ -378,7 +378,9 @@ static void test_elementwise() {
     Dev<__half> dT16((size_t)C * ldo16), d16((size_t)R * ldi16);
     din.up(in);
     dsc.up({2.f});
-    PKC(pk_transpose_f32(din.p, ldi, R, C, dout.p, ldo, dT16.p, ldo16, d16.p, ldi16, dsc.p, nullptr));
+    Dev<float> dam(1), dsc2(2);
+    PKC(pk_transpose_f32(din.p, ldi, R, C, dout.p, ldo, dT16.p, ldo16, d16.p, ldi16, dsc.p, dam.p, nullptr));
+    PKC(pk_amax_finalize(dam.p, 8.f, dsc2.p, nullptr));
     CK(cudaDeviceSynchronize());
     auto o = dout.down();
     auto t16 = dT16.down();
@@ -391,7 +393,14 @@ static void test_elementwise() {
         e = std::max(e, (double)std::fabs(__half2float(t16[(size_t)c * ldo16 + r]) - h2f(2.f * v)));
         e = std::max(e, (double)std::fabs(__half2float(r16[(size_t)r * ldi16 + c]) - h2f(2.f * v)));
       }
-    report("transpose_f32 (+fp16 copies)", e, 0);
+    {
+      float am = 0;
+      for (int r = 0; r < R; ++r)
+        for (int c = 0; c < C; ++c) am = std::max(am, std::fabs(in[(size_t)r * ldi + c]));
+      const float s2 = dsc2.down()[0];
+      if (!(am * s2 >= 128.f && am * s2 < 256.f) || dam.down()[0] != 0.f) e = 1;
+    }
+    report("transpose_f32 (+fp16 copies, fused amax)", e, 0);
   }
   // amax scale
   {
@@ -627,7 +636,7 @@ static void bench_all() {
       int rc = 0;
       float ms = time_ms(5, [&] {
         rc |= pk_gemm_tn(dtype, g.M, g.N, g.K, dA, lda, 0, 0, dB, lda, 0, 0, dC.p, g.N, nullptr, 0, nullptr, 1.f, nullptr, 0, g.sk,
-                         nullptr);
+                         nullptr, nullptr);
       });
       printf("gemm %s %-4s M=%5d N=%5d K=%5d sk=%2d : %.3f ms  %.1f TFLOP/s rc=%d\n", g.name,
              dtype == PK_F16 ? "f16" : "tf32", g.M, g.N, g.K, g.sk, ms, 2.0 * g.M * g.N * g.K / ms * 1e-9, rc);

@@ -158,7 +158,7 @@ class LiGRUStackFn(torch.autograd.Function):
         grads = []
         dYT = None
         dx = None
-        scratch = torch.empty(1, **f32)
+        amax_acc = torch.zeros(1, device=dev, dtype=torch.int32)  # |grad| max accumulated by the producers
         for li in reversed(range(len(saved))):
             S = saved[li]
             H, D = S["H"], S["D"]
@@ -169,10 +169,10 @@ class LiGRUStackFn(torch.autograd.Function):
                 if dy2.dtype != torch.float32 or not dy2.is_contiguous():
                     dy2 = dy2.float().contiguous()
                 dYT = torch.empty(F, ldt, **f32)
-                pk.transpose_f32(dy2, F, TB, F, outT=dYT, ldo=ldt)
-            # power-of-two loss scale for this layer's fp16 gradient operands
+                pk.transpose_f32(dy2, F, TB, F, outT=dYT, ldo=ldt, amax_bits=amax_acc)
+            # power-of-two loss scale for this layer's fp16 gradient operands (amax came with the producer)
             sc = torch.empty(2, **f32)
-            pk.amax_scale(dYT, ldt, F, TB, 8.0, scratch, sc)
+            pk.amax_finalize(amax_acc, 8.0, sc)
             legacy = bool(cfg.cell_flags & pk.REC_LEGACY)
             GT = torch.empty(ndir, C2, ldt, **f32) if legacy else None
             GT16 = torch.empty(ndir, C2, ldt, **f16)
@@ -205,7 +205,8 @@ class LiGRUStackFn(torch.autograd.Function):
             # gradient w.r.t. the layer input
             if li > 0:
                 dXT = torch.empty(D, ldt, **f32)
-                pk.gemm_tn(S["WT16"], dP16, dXT, D, TB, C2, lda=ld2H, ldb=ld2H, ldc=ldt, alpha_dev=inv)
+                pk.gemm_tn(S["WT16"], dP16, dXT, D, TB, C2, lda=ld2H, ldb=ld2H, ldc=ldt, alpha_dev=inv,
+                           amax_bits=amax_acc)
                 dYT = dXT
             elif ctx.x_needs_grad:
                 dx = torch.empty(T, B, D, **f32)

@@ -25,8 +25,9 @@ _c_int, _c_i64, _c_f, _c_p = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctype
 # name -> argtypes (mirrors include/pk_b200.h; tests check that every symbol resolves)
 SIGNATURES = {
     "pk_gemm_tn": [_c_int, _c_int, _c_int, _c_int, _c_p, _c_i64, _c_i64, _c_i64, _c_p, _c_i64, _c_i64, _c_i64, _c_p,
-                   _c_i64, _c_p, _c_int, _c_p, _c_f, _c_p, _c_int, _c_int, _c_p],
-    "pk_transpose_f32": [_c_p, _c_i64, _c_int, _c_int, _c_p, _c_i64, _c_p, _c_i64, _c_p, _c_i64, _c_p, _c_p],
+                   _c_i64, _c_p, _c_int, _c_p, _c_f, _c_p, _c_int, _c_int, _c_p, _c_p],
+    "pk_transpose_f32": [_c_p, _c_i64, _c_int, _c_int, _c_p, _c_i64, _c_p, _c_i64, _c_p, _c_i64, _c_p, _c_p, _c_p],
+    "pk_amax_finalize": [_c_p, _c_f, _c_p, _c_p],
     "pk_convert_f16": [_c_p, _c_i64, _c_int, _c_int, _c_p, _c_i64, _c_p, _c_p],
     "pk_amax_scale": [_c_p, _c_i64, _c_int, _c_int, _c_f, _c_p, _c_p, _c_p],
     "pk_bn_finalize": [_c_p, _c_int, _c_i64, _c_i64, _c_p, _c_p, _c_f, _c_f, _c_int, _c_p, _c_p, _c_p, _c_p, _c_p,
@@ -72,7 +73,7 @@ def lib():
 # kernels launched by this library since import (bench.py reports it as gpu_launches); the
 # numbers are the __global__ launches each C entry point performs (memsets are not counted)
 launch_count = 0
-KERNELS_PER_CALL = {"pk_gemm_tn": 1, "pk_transpose_f32": 1, "pk_convert_f16": 1, "pk_amax_scale": 2,
+KERNELS_PER_CALL = {"pk_amax_finalize": 1, "pk_gemm_tn": 1, "pk_transpose_f32": 1, "pk_convert_f16": 1, "pk_amax_scale": 2,
                     "pk_bn_finalize": 1, "pk_fill_scale_shift": 1, "pk_bn_bwd": 2, "pk_rnn_layer_fwd": 1,
                     "pk_rnn_layer_bwd": 1, "pk_logsoftmax_nll": 1, "pk_logsoftmax_bwd": 1, "pk_rmsprop_step": 1,
                     "pk_sgd_step": 1}
@@ -107,15 +108,20 @@ def pad8(n: int) -> int:
 
 
 def gemm_tn(A, B, C, M, N, K, *, lda, ldb, ldc, dtype=F16, a_k0=0, a_kext=0, b_k0=0, b_kext=0, bias=None,
-            bias_mode=0, rowstats=None, alpha=1.0, alpha_dev=None, accumulate=False, split_k=1):
+            bias_mode=0, rowstats=None, alpha=1.0, alpha_dev=None, accumulate=False, split_k=1, amax_bits=None):
     _check(lib().pk_gemm_tn(dtype, M, N, K, _ptr(A), lda, a_k0, a_kext, _ptr(B), ldb, b_k0, b_kext, _ptr(C), ldc,
                             _ptr(bias), bias_mode if bias is not None else 0, _ptr(rowstats), float(alpha),
-                            _ptr(alpha_dev), int(accumulate), int(split_k), _stream()), "pk_gemm_tn")
+                            _ptr(alpha_dev), int(accumulate), int(split_k), _ptr(amax_bits), _stream()), "pk_gemm_tn")
 
 
-def transpose_f32(inp, ldi, R, C, *, outT=None, ldo=0, outT16=None, ldo16=0, in16=None, ldi16=0, scale_dev=None):
+def transpose_f32(inp, ldi, R, C, *, outT=None, ldo=0, outT16=None, ldo16=0, in16=None, ldi16=0, scale_dev=None,
+                  amax_bits=None):
     _check(lib().pk_transpose_f32(_ptr(inp), ldi, R, C, _ptr(outT), ldo, _ptr(outT16), ldo16, _ptr(in16), ldi16,
-                                  _ptr(scale_dev), _stream()), "pk_transpose_f32")
+                                  _ptr(scale_dev), _ptr(amax_bits), _stream()), "pk_transpose_f32")
+
+
+def amax_finalize(amax_bits, target_log2, scale_out):
+    _check(lib().pk_amax_finalize(_ptr(amax_bits), float(target_log2), _ptr(scale_out), _stream()), "pk_amax_finalize")
 
 
 def convert_f16(inp, ldi, R, C, out, ldo, scale_dev=None):

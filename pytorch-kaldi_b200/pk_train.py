@@ -68,7 +68,7 @@ class FlatTrainer:
             raise NotImplementedError(self.opt)
 
 
-def chunk_step(net, head, trainer: FlatTrainer, inp: torch.Tensor, n_fea: int):
+def chunk_step(net, head, trainer: FlatTrainer, inp: torch.Tensor, n_fea: int, fused_head: bool = True):
     """One minibatch as core.run_nn + utils.forward_model run it: `inp` is the reference's chunk
     layout [T, B, n_fea + 1] with the label in the last column stored as float (data_io.py:272,
     utils.py:2305-2352).  Returns (loss, err) as device scalars."""
@@ -77,9 +77,15 @@ def chunk_step(net, head, trainer: FlatTrainer, inp: torch.Tensor, n_fea: int):
     x = inp[:, :, :n_fea]                              # utils.py:2321 (a strided view; no copy)
     trainer.zero_grad()
     out = net(x)                                       # out_dnn1 = compute(liGRU_layers, fea)
-    logp = head(out.view(T * B, -1))                   # out_dnn2 = compute(MLP_layers, out_dnn1)
-    loss = torch.nn.functional.nll_loss(logp, lab)     # loss_final = cost_nll(out_dnn2, lab_cd)
-    err = (logp.detach().max(dim=1)[1] != lab).float().mean()  # err_final = cost_err(out_dnn2, lab_cd)
+    if fused_head and head._is_plain_head():
+        # out_dnn2 = compute(MLP_layers, out_dnn1); loss = cost_nll(out_dnn2, lab); err = cost_err(out_dnn2, lab)
+        # as ONE fused op (linear + log-softmax + NLL + argmax error; utils.py:2339-2381)
+        import pk_functions as pkf
+        loss, err, _ = pkf.HeadNLLFn.apply(out.view(T * B, -1), head.wx[0].weight, head.wx[0].bias, lab)
+    else:
+        logp = head(out.view(T * B, -1))                   # out_dnn2 = compute(MLP_layers, out_dnn1)
+        loss = torch.nn.functional.nll_loss(logp, lab)     # loss_final = cost_nll(out_dnn2, lab_cd)
+        err = (logp.detach().max(dim=1)[1] != lab).float().mean()  # err_final = cost_err(out_dnn2, lab_cd)
     loss.backward()
     trainer.step()
     return loss.detach(), err
