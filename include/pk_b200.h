@@ -164,6 +164,19 @@ int pk_logsoftmax_bwd(int N, int S, const float* logp, int64_t ld, const int64_t
                       const float* scale_dev, void* d16, int64_t ld16, void* dT16, int64_t ld16t,
                       float* dbias, float* rowsum_scratch, void* stream);
 
+/* Dense (MLP hidden) layer epilogue: y = drop(act(scale * p + shift)) on the channel-major projection PT
+ * (BatchNorm folded into scale/shift by pk_bn_finalize, nn.Dropout's inverted scaling folded into the fp16
+ * keep mask keepT = 0 or 1/(1-p), channel-major, or NULL).  Writes YT16 (channel-major), Y16 (row-major) and
+ * optionally Y32 (row-major module output).  Replaces drop(act(bn(W x + b))) of neural_networks.py:138-148. */
+int pk_dense_act_fwd(int C, int64_t n, int act, const float* PT, int64_t ldp, const float* scale,
+                     const float* shift, const void* keepT, int64_t ldk, void* YT16, int64_t ld16t,
+                     void* Y16, int64_t ld16r, float* Y32, int64_t ld32, void* stream);
+/* its backward up to the BatchNorm: GT16 [C][ldg] = fp16(*gscale * dYT * keep * act'(y)), the GT16 input of
+ * pk_bn_bwd (ndir = 1); y is recovered from the saved YT16 / keepT. */
+int pk_dense_act_bwd(int C, int64_t n, int act, const float* dYT, int64_t ldy, const void* YT16,
+                     int64_t ld16t, const void* keepT, int64_t ldk, const float* gscale, void* GT16,
+                     int64_t ldg, void* stream);
+
 /* torch.optim.RMSprop (momentum 0, not centered) / SGD steps over a flat buffer
  * (utils.py:2121-2162, core.py:640-642); gscale multiplies the gradient (1/world_size). */
 int pk_rmsprop_step(float* p, const float* g, float* v, int64_t n, float lr, float alpha,

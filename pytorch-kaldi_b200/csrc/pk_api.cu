@@ -171,6 +171,28 @@ int pk_logsoftmax_bwd(int N, int S, const float* logp, int64_t ld, const int64_t
   return logsoftmax_bwd(a, static_cast<cudaStream_t>(stream));
 }
 
+int pk_dense_act_fwd(int C, int64_t n, int act, const float* PT, int64_t ldp, const float* scale, const float* shift,
+                     const void* keepT, int64_t ldk, void* YT16, int64_t ld16t, void* Y16, int64_t ld16r, float* Y32,
+                     int64_t ld32, void* stream) {
+  PK_REQUIRE(PT && scale && shift, "pk_dense_act_fwd: null input");
+  PK_REQUIRE(act >= PK_ACT_RELU && act <= PK_ACT_LINEAR, "pk_dense_act_fwd: bad activation %d", act);
+  DenseFwdArgs a;
+  a.C = C; a.n = n; a.act = act; a.PT = PT; a.ldp = ldp; a.scale = scale; a.shift = shift;
+  a.keepT = static_cast<const __half*>(keepT); a.ldk = ldk;
+  a.YT16 = static_cast<__half*>(YT16); a.ld16t = ld16t; a.Y16 = static_cast<__half*>(Y16); a.ld16r = ld16r;
+  a.Y32 = Y32; a.ld32 = ld32;
+  return dense_act_fwd(a, static_cast<cudaStream_t>(stream));
+}
+int pk_dense_act_bwd(int C, int64_t n, int act, const float* dYT, int64_t ldy, const void* YT16, int64_t ld16t,
+                     const void* keepT, int64_t ldk, const float* gscale, void* GT16, int64_t ldg, void* stream) {
+  PK_REQUIRE(dYT && YT16 && GT16, "pk_dense_act_bwd: null input");
+  DenseBwdArgs a;
+  a.C = C; a.n = n; a.act = act; a.dYT = dYT; a.ldy = ldy; a.YT16 = static_cast<const __half*>(YT16); a.ld16t = ld16t;
+  a.keepT = static_cast<const __half*>(keepT); a.ldk = ldk; a.gscale = gscale;
+  a.GT16 = static_cast<__half*>(GT16); a.ldg = ldg;
+  return dense_act_bwd(a, static_cast<cudaStream_t>(stream));
+}
+
 int pk_rmsprop_step(float* p, const float* g, float* v, int64_t n, float lr, float alpha, float eps,
                     float gscale, void* stream) {
   PK_REQUIRE(n <= 0 || (p && g && v), "pk_rmsprop_step: null pointer");

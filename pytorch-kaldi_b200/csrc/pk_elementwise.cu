@@ -303,6 +303,76 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a, co
 }
 
 // ------------------------------------------------------------------------------------
+// Dense (MLP hidden) layer epilogues: y = drop(act(scale * p + shift))  (reference neural_networks.py:138-148,
+// BatchNorm folded into scale/shift, nn.Dropout's inverted scaling folded into the keep mask)
+// ------------------------------------------------------------------------------------
+// PT [C][ldp] channel-major projections -> YT16 [C][ld16t] (operand of the next dW), Y16 [n][ld16r] (operand of
+// the next projection), optional Y32 [n][ld32] (module output).  keepT: fp16 [C][ldk] with 0 or 1/(1-p), or null.
+__global__ void __launch_bounds__(256) dense_act_fwd_kernel(const DenseFwdArgs a) {
+  __shared__ float tile[64][65];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int tiles_i = static_cast<int>((a.n + 63) / 64);
+  const long long ntiles = static_cast<long long>((a.C + 63) / 64) * tiles_i;
+  for (long long tidx = blockIdx.x; tidx < ntiles; tidx += gridDim.x) {
+    const int c0 = static_cast<int>(tidx / tiles_i) * 64;
+    const long long i0 = static_cast<long long>(tidx % tiles_i) * 64;
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      const int cr = ty + 8 * jj;
+      const int c = c0 + cr;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const long long i = i0 + 2 * tx + e;
+        float y = 0.f;
+        if (c < a.C && i < a.n) {
+          const float p = a.PT[static_cast<long long>(c) * a.ldp + i];
+          y = act_fwd(a.act, fmaf(a.scale[c], p, a.shift[c]));
+          if (a.keepT) y *= __half2float(a.keepT[static_cast<long long>(c) * a.ldk + i]);
+          if (a.YT16) a.YT16[static_cast<long long>(c) * a.ld16t + i] = f16_sat(y);
+        }
+        tile[cr][2 * tx + e] = y;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii) {
+      const int ir = ty + 8 * ii;
+      const long long i = i0 + ir;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = c0 + 2 * tx + e;
+        if (i < a.n && c < a.C) {
+          const float y = tile[2 * tx + e][ir];
+          if (a.Y16) a.Y16[i * a.ld16r + c] = f16_sat(y);
+          if (a.Y32) a.Y32[i * a.ld32 + c] = y;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// dYT [C][ldy] fp32 (gradient w.r.t. the layer output, channel-major) -> GT16 [C][ldg] = fp16(scale * dY * keep *
+// act'(y)), the input of pk_bn_bwd (ndir = 1).  y is recovered from the saved post-dropout YT16.
+__global__ void dense_act_bwd_kernel(const DenseBwdArgs a) {
+  const float s = a.gscale ? __ldg(a.gscale) : 1.f;
+  const long long total = static_cast<long long>(a.C) * a.n;
+  for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total;
+       e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long c = e / a.n;
+    const long long i = e - c * a.n;
+    const float dy = a.dYT[c * a.ldy + i];
+    const float keep = a.keepT ? __half2float(a.keepT[c * a.ldk + i]) : 1.f;
+    float g = 0.f;
+    if (keep != 0.f) {
+      const float y = __half2float(a.YT16[c * a.ld16t + i]) / keep;
+      g = dy * keep * act_bwd_from_out(a.act, y);
+    }
+    a.GT16[c * a.ldg + i] = f16_sat(g * s);
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // LogSoftmax + NLL + argmax error, one warp per row (row stays L1-resident across passes)
 // ------------------------------------------------------------------------------------
 __global__ void logsoftmax_nll_kernel(const HeadFwdArgs a, double* __restrict__ acc /* [2] */) {
@@ -522,6 +592,20 @@ int logsoftmax_bwd(const HeadBwdArgs& a, cudaStream_t stream) {
   if (a.dbias) PK_CHECK_CUDA(cudaMemsetAsync(a.dbias, 0, sizeof(float) * a.S, stream));
   const long long ntiles = static_cast<long long>((a.N + 31) / 32) * ((a.S + 31) / 32);
   logsoftmax_bwd_kernel<<<grid_for(ntiles, 1), dim3(32, 8), 0, stream>>>(a, rowsum);
+  PK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int dense_act_fwd(const DenseFwdArgs& a, cudaStream_t stream) {
+  PK_REQUIRE(a.C > 0 && a.n > 0, "dense_act_fwd: empty");
+  const long long ntiles = static_cast<long long>((a.C + 63) / 64) * ((a.n + 63) / 64);
+  dense_act_fwd_kernel<<<grid_for(ntiles, 1), dim3(32, 8), 0, stream>>>(a);
+  PK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int dense_act_bwd(const DenseBwdArgs& a, cudaStream_t stream) {
+  PK_REQUIRE(a.C > 0 && a.n > 0, "dense_act_bwd: empty");
+  dense_act_bwd_kernel<<<grid_for(static_cast<long long>(a.C) * a.n, 1024), 256, 0, stream>>>(a);
   PK_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -152,6 +152,37 @@ struct HeadBwdArgs {
   float* rowsum_scratch = nullptr;    // [N] (general mode only)
 };
 int logsoftmax_bwd(const HeadBwdArgs& a, cudaStream_t stream);
+struct DenseFwdArgs {
+  int C = 0, act = 0;
+  long long n = 0;
+  const float* PT = nullptr;  // [C][ldp]
+  long long ldp = 0;
+  const float* scale = nullptr;
+  const float* shift = nullptr;
+  const __half* keepT = nullptr;  // [C][ldk] 0 or 1/(1-p), or null
+  long long ldk = 0;
+  __half* YT16 = nullptr;  // [C][ld16t]
+  long long ld16t = 0;
+  __half* Y16 = nullptr;  // [n][ld16r]
+  long long ld16r = 0;
+  float* Y32 = nullptr;  // [n][ld32]
+  long long ld32 = 0;
+};
+int dense_act_fwd(const DenseFwdArgs& a, cudaStream_t stream);
+struct DenseBwdArgs {
+  int C = 0, act = 0;
+  long long n = 0;
+  const float* dYT = nullptr;  // [C][ldy]
+  long long ldy = 0;
+  const __half* YT16 = nullptr;
+  long long ld16t = 0;
+  const __half* keepT = nullptr;
+  long long ldk = 0;
+  const float* gscale = nullptr;
+  __half* GT16 = nullptr;  // [C][ldg]
+  long long ldg = 0;
+};
+int dense_act_bwd(const DenseBwdArgs& a, cudaStream_t stream);
 int rmsprop_step(float* p, const float* g, float* v, long long n, float lr, float alpha, float eps,
                  float gscale, cudaStream_t stream);
 int sgd_step(float* p, const float* g, long long n, float lr, float gscale, cudaStream_t stream);

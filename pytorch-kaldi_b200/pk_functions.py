@@ -333,11 +333,175 @@ class HeadNLLFn(torch.autograd.Function):
         return dx, dW, db, None
 
 
+@dataclass
+class DenseLayerCfg:
+    O: int
+    act: str                      # activation name; "softmax" only on the last layer
+    use_bn: bool
+    bn_training: bool
+    bn: Optional[torch.nn.Module] = None
+    keepT: Optional[torch.Tensor] = None   # fp16 [O, pad8(N)] with 0 or 1/(1-p) (training dropout) or None
+
+
+class MLPStackFn(torch.autograd.Function):
+    """MLP stack `drop(act(bn(W x + b)))` per layer (reference neural_networks.py:130-150); a final softmax
+    layer is the fused linear + LogSoftmax.  Hidden layers run channel-major like the recurrent projections:
+    GEMM (+bias, +BatchNorm statistics in the epilogue) -> folded scale/shift -> fused act/dropout epilogue that
+    emits the fp16 operands of the next layer; backward = act/dropout backward -> the same BatchNorm-backward
+    kernel -> dW / dX GEMMs."""
+
+    @staticmethod
+    def forward(ctx, x, layers, *params):
+        if not x.is_cuda:
+            raise RuntimeError("pytorch-kaldi_b200: MLP needs CUDA tensors (there is no CPU fallback)")
+        dev = x.device
+        N, I0 = x.shape
+        ldn = pad8(N)
+        f32 = dict(device=dev, dtype=torch.float32)
+        f16 = dict(device=dev, dtype=torch.float16)
+        need_grad = any(ctx.needs_input_grad)
+        x2 = x if (x.dtype == torch.float32 and x.stride(1) == 1) else x.float().contiguous()
+        I = I0
+        X16 = torch.empty(N, pad8(I), **f16)
+        XT16 = torch.empty(I, ldn, **f16) if need_grad else None
+        pk.transpose_f32(x2, x2.stride(0), N, I, outT16=XT16, ldo16=ldn, in16=X16, ldi16=pad8(I))
+        saved, pi, out = [], 0, None
+        for li, L in enumerate(layers):
+            O = L.O
+            W, b = params[pi], params[pi + 1]
+            pi += 2
+            if L.use_bn:
+                gam, bet = params[pi], params[pi + 1]
+                pi += 2
+            ldI, ldO = pad8(I), pad8(O)
+            W16 = torch.empty(O, ldI, **f16)
+            WT16 = torch.empty(I, ldO, **f16) if need_grad else None
+            pk.transpose_f32(W.contiguous(), I, O, I, outT16=WT16, ldo16=ldO, in16=W16, ldi16=ldI)
+            last = li == len(layers) - 1
+            if L.act == "softmax":
+                if not last or L.use_bn or L.keepT is not None:
+                    raise NotImplementedError("softmax is only supported as the plain last MLP layer")
+                logp = torch.empty(N, O, **f32)
+                pk.gemm_tn(X16, W16, logp, N, O, I, lda=ldI, ldb=ldI, ldc=O, bias=b.contiguous(), bias_mode=1)
+                pk.logsoftmax_nll(N, O, logp, O, None, None)
+                out = logp
+                if need_grad:
+                    saved.append(dict(kind="softmax", I=I, O=O, XT16=XT16, WT16=WT16, logp=logp))
+                break
+            bn_train = L.use_bn and L.bn_training
+            PT = torch.empty(O, ldn, **f32)
+            stats = torch.zeros(O, 2, device=dev, dtype=torch.float64) if bn_train else None
+            pk.gemm_tn(W16, X16, PT, O, N, I, lda=ldI, ldb=ldI, ldc=ldn, bias=b.contiguous(), bias_mode=2,
+                       rowstats=stats)
+            scale, shift = torch.empty(O, **f32), torch.empty(O, **f32)
+            mean = rstd = None
+            if L.use_bn:
+                mean, rstd = torch.empty(O, **f32), torch.empty(O, **f32)
+                bn = L.bn
+                pk.bn_finalize(stats, O, N, N, gam, bet, bn.eps, bn.momentum if bn.momentum is not None else 0.1,
+                               bn_train, bn.running_mean, bn.running_var,
+                               bn.num_batches_tracked if bn_train else None, scale, shift, mean, rstd)
+            else:
+                pk.fill_scale_shift(None, O, scale, shift)
+            YT16 = torch.empty(O, ldn, **f16) if need_grad else None
+            Y16 = None if last else torch.empty(N, ldO, **f16)
+            if last:
+                out = torch.empty(N, O, **f32)
+            pk.dense_act_fwd(O, N, pk.ACT_IDS[L.act], PT, ldn, scale, shift, L.keepT, ldn, YT16, ldn, Y16, ldO,
+                             out if last else None, O)
+            if need_grad:
+                saved.append(dict(kind="dense", I=I, O=O, XT16=XT16, WT16=WT16, PT=PT if bn_train else None, mean=mean,
+                                  rstd=rstd, gamma=gam if L.use_bn else None, YT16=YT16, keepT=L.keepT,
+                                  act=pk.ACT_IDS[L.act], use_bn=L.use_bn, bn_train=bn_train))
+            X16, XT16, I = Y16, YT16, O
+        ctx.saved = saved
+        ctx.dims = (N, I0, ldn)
+        ctx.x_needs_grad = ctx.needs_input_grad[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, dOut):
+        saved = ctx.saved
+        N, I0, ldn = ctx.dims
+        dev = dOut.device
+        f32 = dict(device=dev, dtype=torch.float32)
+        f16 = dict(device=dev, dtype=torch.float16)
+        amax_acc = torch.zeros(1, device=dev, dtype=torch.int32)
+        grads = []
+        dYT = None
+        dx = None
+        for li in reversed(range(len(saved))):
+            S = saved[li]
+            I, O = S["I"], S["O"]
+            ldO = pad8(O)
+            need_dx = li > 0 or ctx.x_needs_grad
+            sc = torch.empty(2, **f32)
+            if S["kind"] == "softmax":
+                dl = dOut if (dOut.dtype == torch.float32 and dOut.is_contiguous()) else dOut.float().contiguous()
+                pk.amax_scale(dl, O, N, O, 8.0, torch.empty(1, **f32), sc)
+                d16 = torch.empty(N, ldO, **f16)
+                dT16 = torch.empty(O, ldn, **f16)
+                db = torch.empty(O, **f32)
+                pk.logsoftmax_bwd(N, O, S["logp"], O, None, dl, O, 1.0, 1.0, sc, d16, ldO, dT16, ldn, db,
+                                  torch.empty(N, **f32))
+                dPT16, dP16 = dT16, d16
+                lg = []
+            else:
+                if dYT is None:  # this dense layer is the module output: autograd gives the row-major gradient
+                    dy2 = dOut if (dOut.dtype == torch.float32 and dOut.is_contiguous()) else dOut.float().contiguous()
+                    dYT = torch.empty(O, ldn, **f32)
+                    pk.transpose_f32(dy2, O, N, O, outT=dYT, ldo=ldn, amax_bits=amax_acc)
+                pk.amax_finalize(amax_acc, 8.0, sc)
+                GT16 = torch.empty(O, ldn, **f16)
+                pk.dense_act_bwd(O, N, S["act"], dYT, ldn, S["YT16"], ldn, S["keepT"], ldn, sc, GT16, ldn)
+                dgamma, dbeta = torch.empty(O, **f32), torch.empty(O, **f32)
+                dPT16 = torch.empty(O, ldn, **f16)
+                dP16 = torch.empty(N, ldO, **f16) if need_dx else None
+                pk.bn_bwd(O, 1, N, None, GT16, ldn, S["PT"], ldn, S["use_bn"], S["bn_train"], S["mean"], S["rstd"],
+                          S["gamma"], sc, dgamma, dbeta, dPT16, ldn, dP16, ldO,
+                          torch.empty(2 * O, device=dev, dtype=torch.float64))
+                # a bias in front of BatchNorm has a mathematically zero gradient (reference: rounding noise)
+                db = torch.zeros(O, **f32) if S["use_bn"] else dbeta
+                lg = [dgamma, dbeta] if S["use_bn"] else []
+            inv = sc[1:2]
+            dW = torch.empty(O, I, **f32)
+            pk.gemm_tn(dPT16, S["XT16"], dW, O, I, N, lda=ldn, ldb=ldn, ldc=I, alpha_dev=inv,
+                       split_k=8 if N >= 4096 else 1)
+            grads = [dW, db] + lg + grads
+            if li > 0:
+                dXT = torch.empty(I, ldn, **f32)
+                pk.gemm_tn(S["WT16"], dP16, dXT, I, N, O, lda=ldO, ldb=ldO, ldc=ldn, alpha_dev=inv, amax_bits=amax_acc)
+                dYT = dXT
+            elif ctx.x_needs_grad:
+                dx = torch.empty(N, I, **f32)
+                pk.gemm_tn(dP16, S["WT16"], dx, N, I, O, lda=ldO, ldb=ldO, ldc=I, alpha_dev=inv)
+        ctx.saved = None
+        return (dx, None, *grads)
+
+
 def mlp_forward(module, x):
-    """General MLP stack (hidden layers with BatchNorm / LayerNorm / activation / dropout,
-    reference neural_networks.py:130-150).  Dense layers share the projection GEMM + fused
-    epilogue path of the recurrent layers; until that path is wired for hidden layers this
-    raises instead of silently running eager PyTorch."""
-    raise NotImplementedError(
-        "pytorch-kaldi_b200.MLP: only the single-layer softmax head runs natively in this build "
-        "(hidden-layer stacks: next scope row); there is no eager fallback")
+    """neural_networks.MLP.forward for general stacks: builds the static layer description and calls MLPStackFn."""
+    if module.dnn_use_laynorm_inp or module.dnn_use_batchnorm_inp or any(module.dnn_use_laynorm):
+        raise NotImplementedError(
+            "pytorch-kaldi_b200.MLP: dnn_use_laynorm / *_inp normalisation are not implemented natively yet "
+            "(no shipped recipe enables them); there is no eager fallback")
+    N = x.shape[0]
+    ldn = pad8(N)
+    layers, params = [], []
+    for i, O in enumerate(module.dnn_lay):
+        p = module.dnn_drop[i]
+        keepT = None
+        if module.training and p > 0.0:
+            override = getattr(module, "_keep_override", None)
+            if override is not None and override[i] is not None:
+                keepT = torch.zeros(O, ldn, device=x.device, dtype=torch.float16)
+                keepT[:, :N] = (override[i].to(x.device).t().float() / (1.0 - p)).half()
+            else:
+                keepT = ((torch.rand(O, ldn, device=x.device) >= p).half() / (1.0 - p)).contiguous()
+        use_bn = bool(module.dnn_use_batchnorm[i])
+        layers.append(DenseLayerCfg(O=O, act=module.dnn_act[i], use_bn=use_bn, bn_training=module.training,
+                                    bn=module.bn[i] if use_bn else None, keepT=keepT))
+        params += [module.wx[i].weight, module.wx[i].bias]
+        if use_bn:
+            params += [module.bn[i].weight, module.bn[i].bias]
+    return MLPStackFn.apply(x, layers, *params)

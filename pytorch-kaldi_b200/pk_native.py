@@ -42,6 +42,9 @@ SIGNATURES = {
     "pk_logsoftmax_nll": [_c_int, _c_int, _c_p, _c_i64, _c_p, _c_p, _c_p],
     "pk_logsoftmax_bwd": [_c_int, _c_int, _c_p, _c_i64, _c_p, _c_p, _c_i64, _c_f, _c_f, _c_p, _c_p, _c_i64, _c_p,
                           _c_i64, _c_p, _c_p, _c_p],
+    "pk_dense_act_fwd": [_c_int, _c_i64, _c_int, _c_p, _c_i64, _c_p, _c_p, _c_p, _c_i64, _c_p, _c_i64, _c_p, _c_i64,
+                         _c_p, _c_i64, _c_p],
+    "pk_dense_act_bwd": [_c_int, _c_i64, _c_int, _c_p, _c_i64, _c_p, _c_i64, _c_p, _c_i64, _c_p, _c_p, _c_i64, _c_p],
     "pk_rmsprop_step": [_c_p, _c_p, _c_p, _c_i64, _c_f, _c_f, _c_f, _c_f, _c_p],
     "pk_sgd_step": [_c_p, _c_p, _c_i64, _c_f, _c_f, _c_p],
 }
@@ -73,7 +76,7 @@ def lib():
 # kernels launched by this library since import (bench.py reports it as gpu_launches); the
 # numbers are the __global__ launches each C entry point performs (memsets are not counted)
 launch_count = 0
-KERNELS_PER_CALL = {"pk_amax_finalize": 1, "pk_gemm_tn": 1, "pk_transpose_f32": 1, "pk_convert_f16": 1, "pk_amax_scale": 2,
+KERNELS_PER_CALL = {"pk_dense_act_fwd": 1, "pk_dense_act_bwd": 1, "pk_amax_finalize": 1, "pk_gemm_tn": 1, "pk_transpose_f32": 1, "pk_convert_f16": 1, "pk_amax_scale": 2,
                     "pk_bn_finalize": 1, "pk_fill_scale_shift": 1, "pk_bn_bwd": 2, "pk_rnn_layer_fwd": 1,
                     "pk_rnn_layer_bwd": 1, "pk_logsoftmax_nll": 1, "pk_logsoftmax_bwd": 1, "pk_rmsprop_step": 1,
                     "pk_sgd_step": 1}
@@ -175,6 +178,16 @@ def logsoftmax_bwd(N, S, logp, ld, labels, dlogp, lddl, gcoef, out_scale, scale_
                                    float(out_scale), _ptr(scale_dev), _ptr(d16), ld16, _ptr(dT16), ld16t,
                                    _ptr(dbias), _ptr(rowsum_scratch), _stream()), "pk_logsoftmax_bwd",
            1 if dlogp is not None else 0)
+
+
+def dense_act_fwd(C, n, act, PT, ldp, scale, shift, keepT, ldk, YT16, ld16t, Y16, ld16r, Y32, ld32):
+    _check(lib().pk_dense_act_fwd(C, n, act, _ptr(PT), ldp, _ptr(scale), _ptr(shift), _ptr(keepT), ldk, _ptr(YT16),
+                                  ld16t, _ptr(Y16), ld16r, _ptr(Y32), ld32, _stream()), "pk_dense_act_fwd")
+
+
+def dense_act_bwd(C, n, act, dYT, ldy, YT16, ld16t, keepT, ldk, gscale, GT16, ldg):
+    _check(lib().pk_dense_act_bwd(C, n, act, _ptr(dYT), ldy, _ptr(YT16), ld16t, _ptr(keepT), ldk, _ptr(gscale),
+                                  _ptr(GT16), ldg, _stream()), "pk_dense_act_bwd")
 
 
 def rmsprop_step(p, g, v, lr, alpha, eps, gscale=1.0):

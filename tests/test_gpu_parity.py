@@ -318,3 +318,50 @@ def test_full_size_training_step_runs_and_learns():
     assert all(np.isfinite(losses))
     assert abs(losses[0] - np.log(S)) < 0.5
     assert losses[-1] < losses[0]
+
+
+def mlp_opts(m):
+    return {"dnn_lay": ",".join(map(str, m["lay"])), "dnn_drop": ",".join(map(str, m["drop"])),
+            "dnn_use_laynorm_inp": "False", "dnn_use_batchnorm_inp": "False",
+            "dnn_use_batchnorm": ",".join(map(str, m["bn"])), "dnn_use_laynorm": ",".join(map(str, m["ln"])),
+            "dnn_act": ",".join(m["act"]), "use_cuda": "True", "to_do": "train"}
+
+
+def test_mlp_stack_matches_reference():
+    """BASELINE configs[0] family: MLP with BatchNorm + ReLU + dropout + softmax (neural_networks.py:60-150), SGD."""
+    pknn = _mods()
+    d = gu.load("mlp_bn_relu")
+    m = d["meta"]
+    net = pknn.MLP(mlp_opts(m), m["D"])
+    net.load_state_dict({k: torch.from_numpy(np.asarray(d["init.mlp." + k])) for k in net.state_dict()})
+    net.cuda().train()
+    net._keep_override = [torch.from_numpy(d[f"keep{i}"]) if m["drop"][i] > 0 else None for i in range(len(m["lay"]))]
+    x = torch.from_numpy(d["x"]).cuda()
+    lab = torch.from_numpy(d["lab"]).cuda().long()
+    logp = net(x)
+    loss = torch.nn.functional.nll_loss(logp, lab)
+    loss.backward()
+    assert gu.relerr(logp.detach().cpu().numpy(), d["logp"]) < TOL_FWD
+    assert abs(loss.item() - float(d["loss"])) / float(d["loss"]) < TOL_FWD
+    for k, p in net.named_parameters():
+        key = "grad.mlp." + k
+        if p.grad is None:
+            assert key not in d
+            continue
+        g = p.grad.cpu().numpy()
+        if k.startswith("wx.") and k.endswith("bias") and m["bn"][int(k.split(".")[1])]:
+            assert np.abs(g).max() < 1e-6  # bias in front of BatchNorm: zero gradient
+        else:
+            assert rel_l2(g, d[key]) < 2 * TOL_GRAD, k  # ReLU kinks: L2 metric (see TOL_GRAD_KINK_L2)
+    sd = net.state_dict()
+    for k in sd:
+        if "running" in k:
+            assert gu.relerr(sd[k].cpu().numpy(), d["bnstat.mlp." + k]) < TOL_FWD, k
+
+
+def test_mlp_unsupported_options_raise_on_gpu():
+    pknn = _mods()
+    d = gu.load("mlp_ln_tanh")
+    net = pknn.MLP(mlp_opts(d["meta"]), d["meta"]["D"]).cuda()
+    with pytest.raises(NotImplementedError):
+        net(torch.from_numpy(d["x"]).cuda())
