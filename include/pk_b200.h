@@ -121,6 +121,8 @@ int pk_bn_bwd(int C, int ndir, int64_t n, const float* GT, const void* GT16, int
               int64_t ld16t, void* dP16, int64_t ld16r, double* sums_scratch, void* stream);
 
 /* One recurrent layer, all T steps in ONE persistent cluster kernel.
+ * cell: PK_CELL_LIGRU, or PK_CELL_RNN (h = act(W x + U h) * mask, neural_networks.py:1438-1447) which runs
+ * on the same kernel with the update gate pinned to 0: pass G = 2 gate blocks with the second one zero.
  *   PT    [G*H][ldp]  channel-major projections W x (G gates: liGRU h,z), shared by both
  *                     directions (direction 1 reads time T-1-k);
  *   scale/shift [G*H] folded BatchNorm (or 1 / bias);   U [G*H][H] recurrent weights (fp32);

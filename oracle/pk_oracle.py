@@ -142,8 +142,11 @@ def batchnorm_bwd(dy, cache):
 # --------------------------------------------------------------------------------------
 
 
-def ligru_forward(x, layers, *, bidir=True, training=True, masks=None, quant=False):
+def ligru_forward(x, layers, *, bidir=True, training=True, masks=None, quant=False, cell="ligru"):
     """x [T,B,D] -> [T,B,(2)H_last].
+
+    cell="ligru": reference liGRU (:997-1155).  cell="rnn": reference RNN (:1319-1461), i.e. the same loop with
+    no update gate: h_t = act(wh_k + Uh h) * mask (:1438-1447); layer dicts then carry wh/uh/bn_wh/bh only.
 
     quant=False is the reference's fp32 algorithm.  quant=True rounds every GEMM operand (inputs,
     weights, recurrent state) to fp16 exactly where the CUDA path does, so that non-smooth points
@@ -174,25 +177,30 @@ def ligru_forward(x, layers, *, bidir=True, training=True, masks=None, quant=Fal
             mask = np.asarray(1.0 - L["drop"], dtype=x.dtype)  # :1107
         Q = q16 if quant else (lambda a: a)
         x2q = Q(x2)
-        wh_q, wz_q, uh_q, uz_q = Q(L["wh"]), Q(L["wz"]), Q(L["uh"]), Q(L["uz"])
+        rnn = cell == "rnn"
+        wh_q, uh_q = Q(L["wh"]), Q(L["uh"])
+        wz_q = np.zeros_like(wh_q) if rnn else Q(L["wz"])
+        uz_q = np.zeros_like(uh_q) if rnn else Q(L["uz"])
         wh_out = x2q @ wh_q.T  # :1114
         wz_out = x2q @ wz_q.T  # :1115
         if L.get("bh") is not None:
             wh_out = wh_out + L["bh"]
-            wz_out = wz_out + L["bz"]
+            if not rnn:
+                wz_out = wz_out + L["bz"]
         bn_cache_h = bn_cache_z = None
         if L.get("bn_wh") is not None:  # :1118-1124
             yh, bn_cache_h = batchnorm_fwd(wh_out.reshape(T * R, H), L["bn_wh"], training)
-            yz, bn_cache_z = batchnorm_fwd(wz_out.reshape(T * R, H), L["bn_wz"], training)
             wh_out = yh.reshape(T, R, H)
-            wz_out = yz.reshape(T, R, H)
+            if not rnn:
+                yz, bn_cache_z = batchnorm_fwd(wz_out.reshape(T * R, H), L["bn_wz"], training)
+                wz_out = yz.reshape(T, R, H)
         ht = np.zeros((R, H), dtype=x.dtype)  # :1096
         hs = np.zeros((T, R, H), dtype=x.dtype)
         zs = np.zeros_like(hs)
         ats = np.zeros_like(hs)
         for k in range(T):  # :1130-1141
             htq = Q(ht)
-            zt = sigmoid(wz_out[k] + htq @ uz_q.T)
+            zt = np.zeros_like(ht) if rnn else sigmoid(wz_out[k] + htq @ uz_q.T)
             at = wh_out[k] + htq @ uh_q.T
             hcand = act_fwd(L["act"], at) * mask
             ht = zt * ht + (1 - zt) * hcand
@@ -204,7 +212,7 @@ def ligru_forward(x, layers, *, bidir=True, training=True, masks=None, quant=Fal
         else:
             out = hs
         caches.append(dict(x2=x2q, hs=hs, zs=zs, ats=ats, mask=mask, bn_h=bn_cache_h, bn_z=bn_cache_z, B=B,
-                           xin_shape=xin.shape, wq=(wh_q, wz_q, uh_q, uz_q), Q=Q))
+                           xin_shape=xin.shape, wq=(wh_q, wz_q, uh_q, uz_q), Q=Q, rnn=rnn))
         x = out
     return x, caches
 
@@ -227,7 +235,7 @@ def ligru_backward(dout, layers, caches, *, bidir=True):
         da_all = np.zeros_like(hs)
         dz_all = np.zeros_like(hs)
         duh = np.zeros_like(L["uh"])
-        duz = np.zeros_like(L["uz"])
+        duz = np.zeros_like(L["uh"])
         for k in reversed(range(T)):
             hprev = hs[k - 1] if k > 0 else np.zeros((R, H), dtype=dout.dtype)
             zt, at = zs[k], ats[k]
@@ -242,18 +250,21 @@ def ligru_backward(dout, layers, caches, *, bidir=True):
             duh += da.T @ Q(hprev)
             duz += dzp.T @ Q(hprev)
             da_all[k], dz_all[k] = da, dzp
-        g = dict(uh=duh, uz=duz)
+        g = dict(uh=duh) if c["rnn"] else dict(uh=duh, uz=duz)
         dwh_pre = da_all.reshape(T * R, H)
         dwz_pre = dz_all.reshape(T * R, H)
         if c["bn_h"] is not None:
             dwh_pre, g["bn_wh_weight"], g["bn_wh_bias"] = batchnorm_bwd(dwh_pre, c["bn_h"])
-            dwz_pre, g["bn_wz_weight"], g["bn_wz_bias"] = batchnorm_bwd(dwz_pre, c["bn_z"])
+            if not c["rnn"]:
+                dwz_pre, g["bn_wz_weight"], g["bn_wz_bias"] = batchnorm_bwd(dwz_pre, c["bn_z"])
         if L.get("bh") is not None:
             g["bh"] = dwh_pre.sum(0)
-            g["bz"] = dwz_pre.sum(0)
+            if not c["rnn"]:
+                g["bz"] = dwz_pre.sum(0)
         x2f = x2.reshape(T * R, -1)
         g["wh"] = dwh_pre.T @ x2f
-        g["wz"] = dwz_pre.T @ x2f
+        if not c["rnn"]:
+            g["wz"] = dwz_pre.T @ x2f
         dx2 = (dwh_pre @ wh_q + dwz_pre @ wz_q).reshape(T, R, -1)
         if bidir:
             dout = dx2[:, :B] + flip0(dx2[:, B:])
@@ -370,10 +381,11 @@ def sgd_step(p, g, lr=0.08):
 # --------------------------------------------------------------------------------------
 
 
-def ligru_model_step(x, labels, ligru_layers, heads, *, masks, bidir=True, loss_weights=None, quant=False):
+def ligru_model_step(x, labels, ligru_layers, heads, *, masks, bidir=True, loss_weights=None, quant=False,
+                     cell="ligru"):
     """x [T,B,D], labels: list of [T*B] int arrays (one per head, t-major rows utils.py:2323).
     heads: list of single-layer softmax MLP layer dicts.  Returns dict(loss, losses, err, logp, grads)."""
-    out, caches = ligru_forward(x, ligru_layers, bidir=bidir, training=True, masks=masks, quant=quant)
+    out, caches = ligru_forward(x, ligru_layers, bidir=bidir, training=True, masks=masks, quant=quant, cell=cell)
     T, B, F = out.shape
     flat = out.reshape(T * B, F)
     dflat = np.zeros_like(flat)

@@ -122,7 +122,8 @@ int pk_rnn_layer_fwd(int cell, int T, int B, int H, int ndir, int act, const flo
                      float mask_scalar, float* Y32, int64_t ldy32, void* Y16, int64_t ldy16, float* HT,
                      void* HT16, void* HP16, float* ZT, float* HCT, int64_t ldt, void* stream) {
   const RecFlags f = parse_cell(cell);
-  PK_REQUIRE(f.cell == PK_CELL_LIGRU, "pk_rnn_layer_fwd: cell kind %d not implemented", f.cell);
+  PK_REQUIRE(f.cell == PK_CELL_LIGRU || f.cell == PK_CELL_RNN, "pk_rnn_layer_fwd: cell kind %d not implemented", f.cell);
+  PK_REQUIRE(f.cell != PK_CELL_RNN || (!f.legacy && f.cluster == 0 && f.sync != 0), "pk_rnn_layer_fwd: the RNN cell needs the default kernels");
   PK_REQUIRE(PT && scale && shift && U, "pk_rnn_layer_fwd: null input");
   PK_REQUIRE(act >= PK_ACT_RELU && act <= PK_ACT_LINEAR, "pk_rnn_layer_fwd: bad activation %d", act);
   RecFwdArgs a;
@@ -132,6 +133,7 @@ int pk_rnn_layer_fwd(int cell, int T, int B, int H, int ndir, int act, const flo
   a.HT = HT; a.HT16 = static_cast<__half*>(HT16); a.HP16 = static_cast<__half*>(HP16);
   a.ZT = ZT; a.HCT = HCT; a.ldt = ldt;
   a.cluster = f.cluster; a.sync = f.sync; a.dbg = f.dbg; a.legacy = f.legacy;
+  a.force_z0 = (f.cell == PK_CELL_RNN) ? 1 : 0;
   return ligru_fwd(a, static_cast<cudaStream_t>(stream));
 }
 
@@ -139,7 +141,7 @@ int pk_rnn_layer_bwd(int cell, int T, int B, int H, int ndir, int act, const flo
                      const float* ZT, const float* HCT, int64_t ldt, const float* U, const float* mask,
                      float mask_scalar, const float* gscale, float* GT, void* GT16, void* stream) {
   const RecFlags f = parse_cell(cell);
-  PK_REQUIRE(f.cell == PK_CELL_LIGRU, "pk_rnn_layer_bwd: cell kind %d not implemented", f.cell);
+  PK_REQUIRE(f.cell == PK_CELL_LIGRU || f.cell == PK_CELL_RNN, "pk_rnn_layer_bwd: cell kind %d not implemented", f.cell);
   PK_REQUIRE(dYT && HT && ZT && HCT && U && (GT || GT16), "pk_rnn_layer_bwd: null input");
   RecBwdArgs a;
   a.T = T; a.B = B; a.H = H; a.ndir = ndir; a.act = act;

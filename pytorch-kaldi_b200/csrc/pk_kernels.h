@@ -54,6 +54,7 @@ struct RecFwdArgs {
   long long ldt = 0;
   int cluster = 0;  // 0 = auto; > 0 selects a legacy (non-specialised) kernel with that cluster size
   int legacy = 0;   // 1 = non-specialised kernels of pk_rnn.cu
+  int force_z0 = 0; // RNN cell (reference :1438-1447): update gate pinned to 0 -> h = act(a) * mask
   long long* dbg_clk = nullptr;  // bring-up: per-phase cycle sums of CTA 0 / warp 0 (8 slots)
   int sync = -1;    // -1 = default (st.async + mbarrier), 0 = barrier.cluster, 1 = st.async
   int dbg = 0;      // timing experiments only: bit0 skip global stores, bit1 skip global loads

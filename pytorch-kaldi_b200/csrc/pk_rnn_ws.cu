@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_fwd_ws_kernel(const RecFwdA
       constexpr uint32_t kBufBytes = NT * kRows * 16;
       const int tg = crank * MT + warp;  // global tile id of this warp's 8 units
       const int act = a.act;
+      const bool z0 = a.force_z0 != 0;
 
       const bool clk_on = a.dbg_clk != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
       long long tsum[6] = {0, 0, 0, 0, 0, 0};
@@ -189,14 +190,14 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_fwd_ws_kernel(const RecFwdA
         // ---- gates (reference :1133-1136)
         float hn[2], zz[2], hcv[2];
         {
-          const float zt = sigmoid_fast(fmaf(sc_z, pz.x, sh_z) + cz0);
+          const float zt = z0 ? 0.f : sigmoid_fast(fmaf(sc_z, pz.x, sh_z) + cz0);
           const float hc = act_fwd_fast(act, fmaf(sc_h, ph.x, sh_h) + ch0) * msk[0];
           float h = fmaf(zt, hprev[0] - hc, hc);
           if (!rok[0]) h = 0.f;
           hn[0] = h; zz[0] = zt; hcv[0] = hc; hprev[0] = h;
         }
         {
-          const float zt = sigmoid_fast(fmaf(sc_z, pz.y, sh_z) + cz1);
+          const float zt = z0 ? 0.f : sigmoid_fast(fmaf(sc_z, pz.y, sh_z) + cz1);
           const float hc = act_fwd_fast(act, fmaf(sc_h, ph.y, sh_h) + ch1) * msk[1];
           float h = fmaf(zt, hprev[1] - hc, hc);
           if (!rok[1]) h = 0.f;

@@ -228,10 +228,10 @@ class _Recurrent(nn.Module):
     def forward(self, x):
         _require_cuda(x, type(self).__name__)
         self._check_supported()
-        if self._CELL != pk.CELL_LIGRU:
+        if self._CELL not in (pk.CELL_LIGRU, pk.CELL_RNN):
             raise NotImplementedError(
                 f"pytorch-kaldi_b200.{type(self).__name__}: the persistent kernel for this gate family is not "
-                "built yet (liGRU is); there is no eager fallback")
+                "built yet (liGRU and RNN are); there is no eager fallback")
         T, B, _ = x.shape
         rows = (2 if self.bidir else 1) * B
         cfg = pkf.RecStackCfg(bidir=bool(self.bidir), cell=self._CELL, cell_flags=self.cell_flags)

@@ -32,7 +32,7 @@ class RecLayerCfg:
     use_bn: bool
     bn_training: bool            # BatchNorm uses batch statistics (module.training)
     bn_h: Optional[torch.nn.Module] = None   # nn.BatchNorm1d modules (running stats are updated in place)
-    bn_z: Optional[torch.nn.Module] = None
+    bn_z: Optional[torch.nn.Module] = None   # None for single-gate cells (RNN)
     mask: Optional[torch.Tensor] = None      # [ndir*B, H] device tensor (training) or None
     mask_scalar: float = 1.0                 # eval: 1 - p
 
@@ -60,8 +60,8 @@ class LiGRUStackFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, cfg: RecStackCfg, *params):
-        # params per layer: wh, wz, uh, uz, then (bn_wh.weight, bn_wh.bias, bn_wz.weight, bn_wz.bias) if
-        # use_bn else (wh.bias, wz.bias)
+        # params per layer (NG = 2 gates for liGRU, 1 for RNN): w_g..., u_g..., then per gate (bn.weight, bn.bias)
+        # if use_bn else per gate (w.bias).  Single-gate cells are padded with a zero second gate block.
         if not x.is_cuda:
             raise RuntimeError("pytorch-kaldi_b200: liGRU needs CUDA tensors (there is no CPU fallback)")
         dev = x.device
@@ -81,14 +81,23 @@ class LiGRUStackFn(torch.autograd.Function):
         y32 = None
         for li, L in enumerate(cfg.layers):
             H = L.H
-            wh, wz, uh, uz = params[pi:pi + 4]
-            pi += 4
+            ng = 1 if cfg.cell == pk.CELL_RNN else 2
+            ws_, us_ = params[pi:pi + ng], params[pi + ng:pi + 2 * ng]
+            pi += 2 * ng
+            if ng == 2:
+                wh, wz, uh, uz = ws_[0], ws_[1], us_[0], us_[1]
+            else:  # RNN: the update-gate block is all zeros (and pinned to 0 inside the kernel)
+                wh, uh = ws_[0], us_[0]
+                wz, uz = torch.zeros_like(wh), torch.zeros_like(uh)
             if L.use_bn:
-                g_h, b_h, g_z, b_z = params[pi:pi + 4]
-                pi += 4
+                bnp = params[pi:pi + 2 * ng]
+                pi += 2 * ng
+                g_h, b_h = bnp[0], bnp[1]
+                g_z, b_z = (bnp[2], bnp[3]) if ng == 2 else (torch.ones_like(g_h), torch.zeros_like(b_h))
             else:
-                bias_h, bias_z = params[pi:pi + 2]
-                pi += 2
+                bias_h = params[pi]
+                bias_z = params[pi + 1] if ng == 2 else torch.zeros_like(bias_h)
+                pi += ng
             C2 = 2 * H
             ldD = pad8(D)
             # ---- operands: fp16 copies of the layer input and of the stacked projection weights
@@ -111,7 +120,9 @@ class LiGRUStackFn(torch.autograd.Function):
             mean = torch.empty(C2, **f32) if L.use_bn else None
             rstd = torch.empty(C2, **f32) if L.use_bn else None
             if L.use_bn:
-                for gi, (bn, gam, bet) in enumerate(((L.bn_h, g_h, b_h), (L.bn_z, g_z, b_z))):
+                if ng == 1:  # padded gate: identity "normalisation" (its projections are exactly zero)
+                    scale[H:].fill_(1.0); shift[H:].zero_(); mean[H:].zero_(); rstd[H:].fill_(1.0)
+                for gi, (bn, gam, bet) in enumerate(((L.bn_h, g_h, b_h), (L.bn_z, g_z, b_z))[:ng]):
                     sl = slice(gi * H, (gi + 1) * H)
                     pk.bn_finalize(stats[sl] if bn_train else None, H, TB, TB * ndir, gam, bet, bn.eps,
                                    bn.momentum if bn.momentum is not None else 0.1, bn_train,
@@ -138,7 +149,7 @@ class LiGRUStackFn(torch.autograd.Function):
                 saved.append(dict(D=D, H=H, XT16=XT16, WT16=WT16, PT=PT if bn_train else None, mean=mean, rstd=rstd,
                                   gamma=torch.cat([g_h, g_z]).contiguous() if L.use_bn else None,
                                   HT=HT, ZT=ZT, HCT=HCT, HP16=HP16, U=U, mask=L.mask, mask_scalar=L.mask_scalar,
-                                  act=L.act, use_bn=L.use_bn, bn_train=bn_train))
+                                  act=L.act, use_bn=L.use_bn, bn_train=bn_train, ng=ng))
             # next layer reads this layer's fp16 outputs directly
             X16, XT16, D = Y16, HT16, F
         ctx.cfg = cfg
@@ -196,11 +207,11 @@ class LiGRUStackFn(torch.autograd.Function):
             # dW = dP^T X
             dW = torch.empty(C2, D, **f32)
             pk.gemm_tn(dPT16, S["XT16"], dW, C2, D, TB, lda=ldt, ldb=ldt, ldc=D, alpha_dev=inv, split_k=8)
-            lg = [dW[:H], dW[H:], dU[:H], dU[H:]]
-            if S["use_bn"]:
-                lg += [dgamma[:H], dbeta[:H], dgamma[H:], dbeta[H:]]
+            if S["ng"] == 2:
+                lg = [dW[:H], dW[H:], dU[:H], dU[H:]]
+                lg += [dgamma[:H], dbeta[:H], dgamma[H:], dbeta[H:]] if S["use_bn"] else [dbeta[:H], dbeta[H:]]
             else:
-                lg += [dbeta[:H], dbeta[H:]]
+                lg = [dW[:H], dU[:H]] + ([dgamma[:H], dbeta[:H]] if S["use_bn"] else [dbeta[:H]])
             grads = lg + grads
             # gradient w.r.t. the layer input
             if li > 0:

@@ -89,9 +89,14 @@ def grads_np(module, prefix):
     return out
 
 
-def ligru_case(name, *, T, B, D, lay, S, S2, drop, bn, act, bidir, seed, head_scale=20.0, full=True):
+def ligru_case(name, *, T, B, D, lay, S, S2, drop, bn, act, bidir, seed, head_scale=20.0, full=True, cell="ligru"):
     torch.manual_seed(seed)
-    net = ref_nn.liGRU(ligru_opts(lay, drop, bn, act, bidir), D)
+    opts = ligru_opts(lay, drop, bn, act, bidir)
+    if cell == "rnn":  # same option names with the rnn_ prefix (proto/RNN.proto)
+        opts = {k.replace("ligru_", "rnn_"): v for k, v in opts.items()}
+        net = ref_nn.RNN(opts, D)
+    else:
+        net = ref_nn.liGRU(opts, D)
     head = ref_nn.MLP(mlp_opts([S], 0.0, False, False, "softmax"), net.out_dim)
     head2 = ref_nn.MLP(mlp_opts([S2], 0.0, False, False, "softmax"), net.out_dim) if S2 else None
     with torch.no_grad():  # give the posteriors real margins
@@ -100,14 +105,13 @@ def ligru_case(name, *, T, B, D, lay, S, S2, drop, bn, act, bidir, seed, head_sc
         if head2 is not None:
             head2.wx[0].weight.mul_(head_scale)
         for i in range(len(lay)):
-            if bn:
-                net.bn_wh[i].weight.uniform_(0.5, 1.5)
-                net.bn_wh[i].bias.normal_(0, 0.2)
-                net.bn_wz[i].weight.uniform_(0.5, 1.5)
-                net.bn_wz[i].bias.normal_(0, 0.2)
-            else:
-                net.wh[i].bias.normal_(0, 0.2)
-                net.wz[i].bias.normal_(0, 0.2)
+            gates = ("wh",) if cell == "rnn" else ("wh", "wz")
+            for gname in gates:
+                if bn:
+                    getattr(net, "bn_" + gname)[i].weight.uniform_(0.5, 1.5)
+                    getattr(net, "bn_" + gname)[i].bias.normal_(0, 0.2)
+                else:
+                    getattr(net, gname)[i].bias.normal_(0, 0.2)
     mods = [("ligru.", net), ("head.", head)] + ([("head2.", head2)] if head2 is not None else [])
     out = {}
     for pfx, m in mods:
@@ -156,7 +160,7 @@ def ligru_case(name, *, T, B, D, lay, S, S2, drop, bn, act, bidir, seed, head_sc
     net.test_flag = True
     with torch.no_grad():
         out["eval_logp"] = head(net(x).view(T * B, -1)).numpy()
-    meta = dict(T=T, B=B, D=D, lay=lay, S=S, S2=S2 or 0, drop=drop, bn=bn, act=act, bidir=bidir)
+    meta = dict(T=T, B=B, D=D, lay=lay, S=S, S2=S2 or 0, drop=drop, bn=bn, act=act, bidir=bidir, cell=cell)
     out["meta"] = np.array(repr(meta))
     if not full:  # keep the fixture small: drop the big square matrices' gradients down to samples
         rng = np.random.default_rng(0)
@@ -218,20 +222,34 @@ def mlp_case(name, *, N, D, lay, drop, bn, ln, act, seed):
 
 if __name__ == "__main__":
     torch.set_num_threads(4)
+    only = sys.argv[1:]  # optional: names of the fixtures to (re)generate
     # A: the headline recipe in miniature (2 heads like cfg/TIMIT_baselines/TIMIT_liGRU_fmllr.cfg)
-    ligru_case("ligru_small", T=12, B=4, D=10, lay=[24, 24], S=30, S2=7, drop=0.2, bn=True, act="relu", bidir=True,
+    if not only or "ligru_small" in only:
+      ligru_case("ligru_small", T=12, B=4, D=10, lay=[24, 24], S=30, S2=7, drop=0.2, bn=True, act="relu", bidir=True,
                seed=11)
     # B: no BatchNorm (biases), tanh, unidirectional, odd sizes
-    ligru_case("ligru_uni_tanh_nobn", T=9, B=3, D=7, lay=[20], S=13, S2=0, drop=0.3, bn=False, act="tanh",
+    if not only or "ligru_uni_tanh_nobn" in only:
+      ligru_case("ligru_uni_tanh_nobn", T=9, B=3, D=7, lay=[20], S=13, S2=0, drop=0.3, bn=False, act="tanh",
                bidir=False, seed=12)
     # C: ragged sizes that do not divide any tile: B not multiple of 8, H not multiple of 8
-    ligru_case("ligru_ragged", T=17, B=5, D=13, lay=[37, 29, 37], S=41, S2=0, drop=0.2, bn=True, act="leaky_relu",
+    if not only or "ligru_ragged" in only:
+      ligru_case("ligru_ragged", T=17, B=5, D=13, lay=[37, 29, 37], S=41, S2=0, drop=0.2, bn=True, act="leaky_relu",
                bidir=True, seed=13)
     # D: the real hidden size of config 2 (one layer, short chunk) — sampled gradients only
-    ligru_case("ligru_h550", T=10, B=8, D=40, lay=[550], S=100, S2=0, drop=0.2, bn=True, act="relu", bidir=True,
+    if not only or "ligru_h550" in only:
+      ligru_case("ligru_h550", T=10, B=8, D=40, lay=[550], S=100, S2=0, drop=0.2, bn=True, act="relu", bidir=True,
                seed=14, full=False)
     # E: config-1 family: MLP with BatchNorm + ReLU + dropout + softmax output
-    mlp_case("mlp_bn_relu", N=64, D=23, lay=[48, 48, 19], drop=[0.15, 0.15, 0.0], bn=[True, True, False],
+    if not only or "mlp_bn_relu" in only:
+      mlp_case("mlp_bn_relu", N=64, D=23, lay=[48, 48, 19], drop=[0.15, 0.15, 0.0], bn=[True, True, False],
              ln=[False, False, False], act=["relu", "relu", "softmax"], seed=21)
-    mlp_case("mlp_ln_tanh", N=33, D=11, lay=[20, 16, 9], drop=[0.0, 0.1, 0.0], bn=[False, True, False],
+    if not only or "mlp_ln_tanh" in only:
+      mlp_case("mlp_ln_tanh", N=33, D=11, lay=[20, 16, 9], drop=[0.0, 0.1, 0.0], bn=[False, True, False],
              ln=[True, True, False], act=["tanh", "sigmoid", "softmax"], seed=22)
+    # F: plain RNN cell (neural_networks.py:1319-1461): bidirectional BN+ReLU stack and a unidirectional tanh/bias one
+    if not only or "rnn_bidir_bn" in only:
+      ligru_case("rnn_bidir_bn", T=14, B=6, D=11, lay=[40, 40], S=23, S2=0, drop=0.2, bn=True, act="relu", bidir=True,
+                 seed=31, cell="rnn")
+    if not only or "rnn_uni_tanh" in only:
+      ligru_case("rnn_uni_tanh", T=10, B=3, D=9, lay=[33], S=12, S2=0, drop=0.1, bn=False, act="tanh", bidir=False,
+                 seed=32, cell="rnn")

@@ -30,23 +30,25 @@ def bn_dict(d, prefix, stage="init.", dtype=np.float64):
 def ligru_layers(d, dtype=np.float64, stage="init."):
     m = d["meta"]
     layers = []
+    rnn = m.get("cell", "ligru") == "rnn"  # single-gate cell: no wz / uz / bn_wz
     for i in range(len(m["lay"])):
         L = dict(
             wh=d[f"{stage}ligru.wh.{i}.weight"].astype(dtype),
-            wz=d[f"{stage}ligru.wz.{i}.weight"].astype(dtype),
             uh=d[f"{stage}ligru.uh.{i}.weight"].astype(dtype),
-            uz=d[f"{stage}ligru.uz.{i}.weight"].astype(dtype),
             act=m["act"],
             drop=m["drop"],
         )
+        if not rnn:
+            L["wz"] = d[f"{stage}ligru.wz.{i}.weight"].astype(dtype)
+            L["uz"] = d[f"{stage}ligru.uz.{i}.weight"].astype(dtype)
         if m["bn"]:
             L["bn_wh"] = bn_dict(d, f"ligru.bn_wh.{i}", "init.", dtype)
-            L["bn_wz"] = bn_dict(d, f"ligru.bn_wz.{i}", "init.", dtype)
+            L["bn_wz"] = None if rnn else bn_dict(d, f"ligru.bn_wz.{i}", "init.", dtype)
             L["bh"] = L["bz"] = None
         else:
             L["bn_wh"] = L["bn_wz"] = None
             L["bh"] = d[f"{stage}ligru.wh.{i}.bias"].astype(dtype)
-            L["bz"] = d[f"{stage}ligru.wz.{i}.bias"].astype(dtype)
+            L["bz"] = None if rnn else d[f"{stage}ligru.wz.{i}.bias"].astype(dtype)
         layers.append(L)
     return layers
 

@@ -60,7 +60,10 @@ def head_opts(S):
 def build_from_fixture(d, stage="init."):
     pknn = _mods()
     m = d["meta"]
-    net = pknn.liGRU(ligru_opts(m), m["D"])
+    if m.get("cell", "ligru") == "rnn":
+        net = pknn.RNN({k.replace("ligru_", "rnn_"): v for k, v in ligru_opts(m).items()}, m["D"])
+    else:
+        net = pknn.liGRU(ligru_opts(m), m["D"])
     head = pknn.MLP(head_opts(m["S"]), net.out_dim)
     head2 = pknn.MLP(head_opts(m["S2"]), net.out_dim) if m["S2"] else None
 
@@ -106,7 +109,8 @@ def run_step(d):
     return net, head, head2, h, logp, logp2, loss, loss_cd, err
 
 
-@pytest.mark.parametrize("name", ["ligru_small", "ligru_uni_tanh_nobn", "ligru_ragged", "ligru_h550"])
+@pytest.mark.parametrize("name", ["ligru_small", "ligru_uni_tanh_nobn", "ligru_ragged", "ligru_h550", "rnn_bidir_bn",
+                                  "rnn_uni_tanh"])
 def test_forward_matches_reference(name):
     d = gu.load(name)
     net, head, head2, h, logp, logp2, loss, loss_cd, err = run_step(d)
@@ -128,7 +132,8 @@ def test_forward_matches_reference(name):
         assert err.item() == pytest.approx(float(d["err"]), abs=1e-7)
 
 
-@pytest.mark.parametrize("name", ["ligru_small", "ligru_uni_tanh_nobn", "ligru_ragged", "ligru_h550"])
+@pytest.mark.parametrize("name", ["ligru_small", "ligru_uni_tanh_nobn", "ligru_ragged", "ligru_h550", "rnn_bidir_bn",
+                                  "rnn_uni_tanh"])
 def test_gradients_match_reference(name):
     d = gu.load(name)
     net, head, head2, h, *_ = run_step(d)

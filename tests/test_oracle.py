@@ -6,7 +6,7 @@ import pytest
 import golden_util as gu
 import pk_oracle as orc
 
-LIGRU_CASES = ["ligru_small", "ligru_uni_tanh_nobn", "ligru_ragged", "ligru_h550"]
+LIGRU_CASES = ["ligru_small", "ligru_uni_tanh_nobn", "ligru_ragged", "ligru_h550", "rnn_bidir_bn", "rnn_uni_tanh"]
 MLP_CASES = ["mlp_bn_relu", "mlp_ln_tanh"]
 TOL = 2e-4  # oracle runs in float64, the reference in float32
 
@@ -20,7 +20,8 @@ def run_ligru(name, dtype=np.float64):
     if m["S2"]:
         heads.append(gu.head_layer(d, "head2", dtype))
         labels.append(d["lab2"].astype(np.int64))
-    res = orc.ligru_model_step(d["x"].astype(dtype), labels, layers, heads, masks=gu.masks(d), bidir=m["bidir"])
+    res = orc.ligru_model_step(d["x"].astype(dtype), labels, layers, heads, masks=gu.masks(d), bidir=m["bidir"],
+                               cell=m.get("cell", "ligru"))
     return d, layers, heads, res
 
 
@@ -41,16 +42,18 @@ def test_ligru_forward_loss_err(name):
 def test_ligru_gradients(name):
     d, layers, heads, res = run_ligru(name)
     m = d["meta"]
+    rnn = m.get("cell", "ligru") == "rnn"
     for i, g in enumerate(res["ligru_grads"]):
-        for k in ("wh", "wz", "uh", "uz"):
+        for k in (("wh", "uh") if rnn else ("wh", "wz", "uh", "uz")):
             gu.check_tensor(d, f"grad.ligru.{k}.{i}.weight", g[k], 5e-4)
         if m["bn"]:
-            for gate in ("wh", "wz"):
+            for gate in (("wh",) if rnn else ("wh", "wz")):
                 gu.check_tensor(d, f"grad.ligru.bn_{gate}.{i}.weight", g[f"bn_{gate}_weight"], 5e-4)
                 gu.check_tensor(d, f"grad.ligru.bn_{gate}.{i}.bias", g[f"bn_{gate}_bias"], 5e-4)
         else:
             gu.check_tensor(d, f"grad.ligru.wh.{i}.bias", g["bh"], 5e-4)
-            gu.check_tensor(d, f"grad.ligru.wz.{i}.bias", g["bz"], 5e-4)
+            if not rnn:
+                gu.check_tensor(d, f"grad.ligru.wz.{i}.bias", g["bz"], 5e-4)
     gu.check_tensor(d, "grad.head.wx.0.weight", res["head_grads"][0]["w"], 5e-4)
     gu.check_tensor(d, "grad.head.wx.0.bias", res["head_grads"][0]["b"], 5e-4)
 
