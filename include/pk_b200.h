@@ -150,6 +150,32 @@ int pk_rnn_layer_bwd(int cell, int T, int B, int H, int ndir, int act, const flo
                      const float* U, const float* mask, float mask_scalar, const float* gscale,
                      float* GT, void* GT16, void* stream);
 
+/* Step-wise recurrent path: one fused tensor-core kernel per time step, all T launches issued inside this
+ * call.  Serves the cells / sizes the persistent kernels do not hold: PK_CELL_LSTM (neural_networks.py:
+ * 300-483), PK_CELL_GRU (:486-654) and PK_CELL_MGRU (:1158-1316) — these two need two dependent products per
+ * step and run as two launches per step — and PK_CELL_LIGRU with any H (e.g. 5x1024).  Same tensor conventions as pk_rnn_layer_fwd; gate
+ * order of PT/scale/shift/U rows and of the saved tensors sv0..sv4 ([ndir*H][ldt] fp32, may be NULL when the
+ * backward is not needed):
+ *   liGRU: gates (h, z)       saved sv0 = z, sv1 = masked candidate
+ *   LSTM : gates (f, i, o, c) saved sv0 = f, sv1 = act(c~)*mask, sv2 = i, sv3 = o, sv4 = cell state c
+ *   GRU  : gates (h, z, r)    saved sv0 = z, sv1 = masked candidate, sv2 = r;   HX16 = fp16 (r * h_{k-1})
+ *   mGRU : gates (h, z)       saved sv0 = z, sv1 = masked candidate;            HX16 = fp16 (z * h_{k-1})
+ * HX16 [ndir*H][ldt] (GRU / minimalGRU only, else NULL) is the K-major operand of dUh like HP16 is for the others.
+ * workspace: device scratch of pk_rnn_step_workspace_bytes(cell, T, B, H, ndir, backward) bytes (packed fp16
+ * weights, fp32 state, double-buffered fp16 operands). */
+int64_t pk_rnn_step_workspace_bytes(int cell, int T, int B, int H, int ndir, int backward);
+int pk_rnn_step_fwd(int cell, int T, int B, int H, int ndir, int act, const float* PT, int64_t ldp,
+                    const float* scale, const float* shift, const float* U, const float* mask,
+                    float mask_scalar, float* Y32, int64_t ldy32, void* Y16, int64_t ldy16, float* HT,
+                    void* HT16, void* HP16, void* HX16, float* sv0, float* sv1, float* sv2, float* sv3,
+                    float* sv4, int64_t ldt, void* workspace, int64_t workspace_bytes, void* stream);
+/* reverse-time counterpart: GT16 [ndir][NG*H][ldt] fp16 scaled by *gscale (gate order as above). */
+int pk_rnn_step_bwd(int cell, int T, int B, int H, int ndir, int act, const float* dYT, const float* HT,
+                    const float* sv0, const float* sv1, const float* sv2, const float* sv3,
+                    const float* sv4, int64_t ldt, const float* U, const float* mask, float mask_scalar,
+                    const float* gscale, void* GT16, void* workspace, int64_t workspace_bytes,
+                    void* stream);
+
 /* In place: logits [N][ld] -> log-posteriors (act_fun("softmax") = LogSoftmax(dim=1),
  * neural_networks.py:53-54).  With labels (int64, utils.py:2348-2352): acc[0] = sum_n
  * -logp[n,lab[n]] (nn.NLLLoss numerator, utils.py:2361), acc[1] = #(argmax != lab)

@@ -275,6 +275,153 @@ def ligru_backward(dout, layers, caches, *, bidir=True):
 
 
 # --------------------------------------------------------------------------------------
+# LSTM :300-483, GRU :486-654, minimalGRU :1158-1316 — same scaffolding as the liGRU, other step equations
+# --------------------------------------------------------------------------------------
+
+GATES = {"lstm": ("f", "i", "o", "c"), "gru": ("h", "z", "r"), "minimalgru": ("h", "z")}
+
+
+def cell_forward(x, layers, *, cell, bidir=True, training=True, masks=None, quant=False):
+    """x [T,B,D] -> [T,B,(2)H_last] for cell in {"lstm", "gru", "minimalgru"}.
+
+    layers: list of dicts with w / u (lists of [H,D] / [H,H] in the reference's registration order GATES[cell]),
+    b (list of biases or None), bn (list of BatchNorm dicts or None), act, drop.
+    Step equations: LSTM :457-469, GRU :631-637, minimalGRU :1293-1297.  quant as in ligru_forward."""
+    names = GATES[cell]
+    caches = []
+    for li, L in enumerate(layers):
+        T, B, D = x.shape
+        H = L["u"][0].shape[0]
+        x2 = np.concatenate([x, flip0(x)], axis=1) if bidir else x
+        R = x2.shape[1]
+        if training and masks is not None:
+            mask = masks[li].astype(x.dtype)
+        else:
+            mask = np.asarray(1.0 - L["drop"], dtype=x.dtype)
+        Q = q16 if quant else (lambda a: a)
+        x2q = Q(x2)
+        wq = [Q(w) for w in L["w"]]
+        uq = dict(zip(names, [Q(u) for u in L["u"]]))
+        pre, bnc = {}, {}
+        for gi, n in enumerate(names):
+            p = x2q @ wq[gi].T
+            if L.get("b") is not None:
+                p = p + L["b"][gi]
+            bnc[n] = None
+            if L.get("bn") is not None:
+                y, bnc[n] = batchnorm_fwd(p.reshape(T * R, H), L["bn"][gi], training)
+                p = y.reshape(T, R, H)
+            pre[n] = p
+        ht = np.zeros((R, H), dtype=x.dtype)
+        ct = np.zeros((R, H), dtype=x.dtype)
+        st = {k: np.zeros((T, R, H), dtype=x.dtype) for k in ("h", "c", "g0", "g1", "g2", "a")}
+        for k in range(T):
+            hq = Q(ht)
+            if cell == "lstm":
+                ft = sigmoid(pre["f"][k] + hq @ uq["f"].T)
+                it = sigmoid(pre["i"][k] + hq @ uq["i"].T)
+                ot = sigmoid(pre["o"][k] + hq @ uq["o"].T)
+                at = pre["c"][k] + hq @ uq["c"].T
+                ct = it * act_fwd(L["act"], at) * mask + ft * ct
+                ht = ot * act_fwd(L["act"], ct)
+                st["g0"][k], st["g1"][k], st["g2"][k], st["c"][k] = ft, it, ot, ct
+            else:
+                zt = sigmoid(pre["z"][k] + hq @ uq["z"].T)
+                if cell == "gru":
+                    rt = sigmoid(pre["r"][k] + hq @ uq["r"].T)
+                    st["g1"][k] = rt
+                    at = pre["h"][k] + Q(rt * ht) @ uq["h"].T
+                else:
+                    at = pre["h"][k] + Q(zt * ht) @ uq["h"].T
+                hcand = act_fwd(L["act"], at) * mask
+                ht = zt * ht + (1 - zt) * hcand
+                st["g0"][k] = zt
+            st["h"][k], st["a"][k] = ht, at
+        hs = st["h"]
+        out = np.concatenate([hs[:, :B], flip0(hs[:, B:])], axis=2) if bidir else hs
+        caches.append(dict(x2=x2q, st=st, mask=mask, bn=bnc, B=B, wq=wq, uq=uq, Q=Q))
+        x = out
+    return x, caches
+
+
+def cell_backward(dout, layers, caches, *, cell, bidir=True):
+    """Hand-derived BPTT of cell_forward.  grads[i] = dict(w=[..], u=[..], b=[..] or None, bn_weight=[..],
+    bn_bias=[..]) in GATES[cell] order."""
+    names = GATES[cell]
+    grads = [None] * len(layers)
+    for li in reversed(range(len(layers))):
+        L, c = layers[li], caches[li]
+        st, mask, B, Q, uq = c["st"], c["mask"], c["B"], c["Q"], c["uq"]
+        hs = st["h"]
+        T, R, H = hs.shape
+        dH = np.concatenate([dout[:, :, :H], flip0(dout[:, :, H:])], axis=1) if bidir else dout
+        zero = np.zeros((R, H), dtype=dout.dtype)
+        carry, ccarry = zero.copy(), zero.copy()
+        dpre = {n: np.zeros_like(hs) for n in names}
+        du = {n: np.zeros_like(L["u"][0]) for n in names}
+        for k in reversed(range(T)):
+            hp = hs[k - 1] if k > 0 else zero
+            at = st["a"][k]
+            dh = dH[k] + carry
+            if cell == "lstm":
+                ft, it, ot, ct = st["g0"][k], st["g1"][k], st["g2"][k], st["c"][k]
+                cp = st["c"][k - 1] if k > 0 else zero
+                ac = act_fwd(L["act"], ct)
+                ya = act_fwd(L["act"], at)
+                dc = dh * ot * act_bwd(L["act"], ct, ac) + ccarry
+                d = dict(f=dc * cp * ft * (1 - ft), i=dc * ya * mask * it * (1 - it), o=dh * ac * ot * (1 - ot),
+                         c=dc * it * mask * act_bwd(L["act"], at, ya))
+                ccarry = dc * ft
+                carry = sum(d[n] @ uq[n] for n in names)
+                for n in names:
+                    du[n] += d[n].T @ Q(hp)
+            else:
+                zt = st["g0"][k]
+                y = act_fwd(L["act"], at)
+                hcand = y * mask
+                da = dh * (1 - zt) * mask * act_bwd(L["act"], at, y)
+                v = da @ uq["h"]
+                dzt = dh * (hp - hcand)
+                if cell == "gru":
+                    rt = st["g1"][k]
+                    drp = v * hp * rt * (1 - rt)
+                    dzp = dzt * zt * (1 - zt)
+                    carry = dh * zt + v * rt + dzp @ uq["z"] + drp @ uq["r"]
+                    d = dict(h=da, z=dzp, r=drp)
+                    du["h"] += da.T @ Q(rt * hp)
+                    du["r"] += drp.T @ Q(hp)
+                else:
+                    dzp = (dzt + v * hp) * zt * (1 - zt)
+                    carry = dh * zt + v * zt + dzp @ uq["z"]
+                    d = dict(h=da, z=dzp)
+                    du["h"] += da.T @ Q(zt * hp)
+                du["z"] += dzp.T @ Q(hp)
+            for n in names:
+                dpre[n][k] = d[n]
+        g = dict(w=[], u=[du[n] for n in names], b=None, bn_weight=None, bn_bias=None)
+        if L.get("bn") is not None:
+            g["bn_weight"], g["bn_bias"] = [], []
+        if L.get("b") is not None:
+            g["b"] = []
+        x2f = c["x2"].reshape(T * R, -1)
+        dx2 = 0.0
+        for gi, n in enumerate(names):
+            dp = dpre[n].reshape(T * R, H)
+            if c["bn"][n] is not None:
+                dp, gw, gb = batchnorm_bwd(dp, c["bn"][n])
+                g["bn_weight"].append(gw)
+                g["bn_bias"].append(gb)
+            if L.get("b") is not None:
+                g["b"].append(dp.sum(0))
+            g["w"].append(dp.T @ x2f)
+            dx2 = dx2 + dp @ c["wq"][gi]
+        dx2 = dx2.reshape(T, R, -1)
+        dout = dx2[:, :B] + flip0(dx2[:, B:]) if bidir else dx2
+        grads[li] = g
+    return dout, grads
+
+
+# --------------------------------------------------------------------------------------
 # MLP  (neural_networks.py:60-150) — also the senone head (dnn_act = softmax)
 # --------------------------------------------------------------------------------------
 
@@ -385,7 +532,11 @@ def ligru_model_step(x, labels, ligru_layers, heads, *, masks, bidir=True, loss_
                      cell="ligru"):
     """x [T,B,D], labels: list of [T*B] int arrays (one per head, t-major rows utils.py:2323).
     heads: list of single-layer softmax MLP layer dicts.  Returns dict(loss, losses, err, logp, grads)."""
-    out, caches = ligru_forward(x, ligru_layers, bidir=bidir, training=True, masks=masks, quant=quant, cell=cell)
+    generic = cell in GATES
+    if generic:
+        out, caches = cell_forward(x, ligru_layers, cell=cell, bidir=bidir, training=True, masks=masks, quant=quant)
+    else:
+        out, caches = ligru_forward(x, ligru_layers, bidir=bidir, training=True, masks=masks, quant=quant, cell=cell)
     T, B, F = out.shape
     flat = out.reshape(T * B, F)
     dflat = np.zeros_like(flat)
@@ -399,7 +550,10 @@ def ligru_model_step(x, labels, ligru_layers, heads, *, masks, bidir=True, loss_
         dx, hg = mlp_backward(dlogp, [hd], hc)
         dflat += dx
         hgrads.append(hg[0])
-    _, lgrads = ligru_backward(dflat.reshape(T, B, F), ligru_layers, caches, bidir=bidir)
+    if generic:
+        _, lgrads = cell_backward(dflat.reshape(T, B, F), ligru_layers, caches, cell=cell, bidir=bidir)
+    else:
+        _, lgrads = ligru_backward(dflat.reshape(T, B, F), ligru_layers, caches, bidir=bidir)
     loss = sum(w * l for w, l in zip(lw, losses))
     return dict(loss=loss, losses=losses, err=cost_err(logps[0], labels[0]), logp=logps, out=out, ligru_grads=lgrads,
                 head_grads=hgrads)

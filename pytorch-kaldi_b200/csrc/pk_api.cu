@@ -151,6 +151,44 @@ int pk_rnn_layer_bwd(int cell, int T, int B, int H, int ndir, int act, const flo
   return ligru_bwd(a, static_cast<cudaStream_t>(stream));
 }
 
+int64_t pk_rnn_step_workspace_bytes(int cell, int T, int B, int H, int ndir, int backward) {
+  return cell_step_workspace_bytes(cell & PK_CELL_MASK, T, B, H, ndir, backward);
+}
+
+int pk_rnn_step_fwd(int cell, int T, int B, int H, int ndir, int act, const float* PT, int64_t ldp,
+                    const float* scale, const float* shift, const float* U, const float* mask, float mask_scalar,
+                    float* Y32, int64_t ldy32, void* Y16, int64_t ldy16, float* HT, void* HT16, void* HP16,
+                    void* HX16, float* sv0, float* sv1, float* sv2, float* sv3, float* sv4, int64_t ldt, void* workspace,
+                    int64_t workspace_bytes, void* stream) {
+  PK_REQUIRE(PT && scale && shift && U, "pk_rnn_step_fwd: null input");
+  PK_REQUIRE(act >= PK_ACT_RELU && act <= PK_ACT_LINEAR, "pk_rnn_step_fwd: bad activation %d", act);
+  PK_REQUIRE(T > 0 && B > 0 && H > 0 && (ndir == 1 || ndir == 2), "pk_rnn_step_fwd: bad shape");
+  CellStepFwdArgs a;
+  a.cell = cell & PK_CELL_MASK; a.T = T; a.B = B; a.H = H; a.ndir = ndir; a.act = act;
+  a.PT = PT; a.ldp = ldp; a.scale = scale; a.shift = shift; a.U = U; a.mask = mask; a.mask_scalar = mask_scalar;
+  a.Y32 = Y32; a.ldy32 = ldy32; a.Y16 = static_cast<__half*>(Y16); a.ldy16 = ldy16;
+  a.HT = HT; a.HT16 = static_cast<__half*>(HT16); a.HP16 = static_cast<__half*>(HP16);
+  a.HX16 = static_cast<__half*>(HX16);
+  a.SV[0] = sv0; a.SV[1] = sv1; a.SV[2] = sv2; a.SV[3] = sv3; a.SV[4] = sv4; a.ldt = ldt;
+  a.workspace = workspace; a.workspace_bytes = workspace_bytes;
+  return cell_step_fwd(a, static_cast<cudaStream_t>(stream));
+}
+
+int pk_rnn_step_bwd(int cell, int T, int B, int H, int ndir, int act, const float* dYT, const float* HT,
+                    const float* sv0, const float* sv1, const float* sv2, const float* sv3, const float* sv4,
+                    int64_t ldt, const float* U, const float* mask, float mask_scalar, const float* gscale,
+                    void* GT16, void* workspace, int64_t workspace_bytes, void* stream) {
+  PK_REQUIRE(dYT && HT && sv0 && sv1 && U && GT16, "pk_rnn_step_bwd: null input");
+  PK_REQUIRE((cell & PK_CELL_MASK) != PK_CELL_LSTM || (sv2 && sv3 && sv4), "pk_rnn_step_bwd: LSTM needs sv0..sv4");
+  PK_REQUIRE((cell & PK_CELL_MASK) != PK_CELL_GRU || sv2, "pk_rnn_step_bwd: GRU needs sv2 (reset gate)");
+  CellStepBwdArgs a;
+  a.cell = cell & PK_CELL_MASK; a.T = T; a.B = B; a.H = H; a.ndir = ndir; a.act = act;
+  a.dYT = dYT; a.HT = HT; a.SV[0] = sv0; a.SV[1] = sv1; a.SV[2] = sv2; a.SV[3] = sv3; a.SV[4] = sv4;
+  a.ldt = ldt; a.U = U; a.mask = mask; a.mask_scalar = mask_scalar; a.gscale = gscale;
+  a.GT16 = static_cast<__half*>(GT16); a.workspace = workspace; a.workspace_bytes = workspace_bytes;
+  return cell_step_bwd(a, static_cast<cudaStream_t>(stream));
+}
+
 int pk_logsoftmax_nll(int N, int S, float* logits, int64_t ld, const int64_t* labels, double* acc,
                       void* stream) {
   PK_REQUIRE(logits != nullptr, "pk_logsoftmax_nll: null logits");

@@ -86,6 +86,51 @@ int ligru_fwd_ws(const RecFwdArgs& a, cudaStream_t stream);
 int ligru_bwd_ws(const RecBwdArgs& a, cudaStream_t stream);
 void set_debug_clock_buffer(long long* dev_ptr);
 
+// ---- step-wise recurrent path (pk_cell_step.cu): one fused kernel per time step ----
+enum CellKind { CELL_LIGRU = 0, CELL_RNN = 1, CELL_GRU = 2, CELL_MGRU = 3, CELL_LSTM = 4 };
+// saved tensors SV[0..4], all [ndir*H][ldt] fp32 channel-major, natural time:
+//   liGRU: z, hcand            LSTM: f, g (= act(c~)*mask), i, o, c
+//   GRU:   z, hcand, r         minimalGRU: z, hcand
+struct CellStepFwdArgs {
+  int cell = 0, T = 0, B = 0, H = 0, ndir = 1, act = 0;
+  const float* PT = nullptr;  // [NG*H][ldp]
+  long long ldp = 0;
+  const float* scale = nullptr;
+  const float* shift = nullptr;
+  const float* U = nullptr;  // [NG*H][H] fp32, gate order of the saved-tensor list above
+  const float* mask = nullptr;
+  float mask_scalar = 1.f;
+  float* Y32 = nullptr;
+  long long ldy32 = 0;
+  __half* Y16 = nullptr;
+  long long ldy16 = 0;
+  float* HT = nullptr;
+  __half* HT16 = nullptr;
+  __half* HP16 = nullptr;
+  __half* HX16 = nullptr;  // GRU / minimalGRU: fp16 (r*h_{k-1}) / (z*h_{k-1}), the operand of dUh
+  float* SV[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  long long ldt = 0;
+  void* workspace = nullptr;
+  long long workspace_bytes = 0;
+};
+struct CellStepBwdArgs {
+  int cell = 0, T = 0, B = 0, H = 0, ndir = 1, act = 0;
+  const float* dYT = nullptr;
+  const float* HT = nullptr;
+  const float* SV[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  long long ldt = 0;
+  const float* U = nullptr;
+  const float* mask = nullptr;
+  float mask_scalar = 1.f;
+  const float* gscale = nullptr;
+  __half* GT16 = nullptr;  // [ndir][NG*H][ldt] fp16 scaled
+  void* workspace = nullptr;
+  long long workspace_bytes = 0;
+};
+long long cell_step_workspace_bytes(int cell, int T, int B, int H, int ndir, int backward);
+int cell_step_fwd(const CellStepFwdArgs& a, cudaStream_t stream);
+int cell_step_bwd(const CellStepBwdArgs& a, cudaStream_t stream);
+
 // ---- memory-bound helpers (pk_elementwise.cu) ----
 // out[c][r] = in[r][c]; optional fp16 copies. in is [R][ldi] fp32.
 int transpose_f32(const float* in, long long ldi, int R, int C, float* outT, long long ldo,

@@ -228,10 +228,6 @@ class _Recurrent(nn.Module):
     def forward(self, x):
         _require_cuda(x, type(self).__name__)
         self._check_supported()
-        if self._CELL not in (pk.CELL_LIGRU, pk.CELL_RNN):
-            raise NotImplementedError(
-                f"pytorch-kaldi_b200.{type(self).__name__}: the persistent kernel for this gate family is not "
-                "built yet (liGRU and RNN are); there is no eager fallback")
         T, B, _ = x.shape
         rows = (2 if self.bidir else 1) * B
         cfg = pkf.RecStackCfg(bidir=bool(self.bidir), cell=self._CELL, cell_flags=self.cell_flags)
@@ -243,8 +239,7 @@ class _Recurrent(nn.Module):
             bns = [getattr(self, "bn_" + w)[i] for w, _ in self._GATES]
             use_bn = bool(self.use_batchnorm[i])
             cfg.layers.append(pkf.RecLayerCfg(H=H, act=pk.ACT_IDS[self.act_names[i]], use_bn=use_bn,
-                                              bn_training=self.training, bn_h=bns[0],
-                                              bn_z=bns[1] if len(bns) > 1 else None, mask=mask, mask_scalar=mscal))
+                                              bn_training=self.training, bns=bns, mask=mask, mask_scalar=mscal))
             params += [m.weight for m in ws] + [m.weight for m in us]
             if use_bn:
                 for bn in bns:

@@ -31,8 +31,7 @@ class RecLayerCfg:
     act: int
     use_bn: bool
     bn_training: bool            # BatchNorm uses batch statistics (module.training)
-    bn_h: Optional[torch.nn.Module] = None   # nn.BatchNorm1d modules (running stats are updated in place)
-    bn_z: Optional[torch.nn.Module] = None   # None for single-gate cells (RNN)
+    bns: List[torch.nn.Module] = field(default_factory=list)  # per-gate nn.BatchNorm1d (running stats updated in place)
     mask: Optional[torch.Tensor] = None      # [ndir*B, H] device tensor (training) or None
     mask_scalar: float = 1.0                 # eval: 1 - p
 
@@ -55,15 +54,36 @@ def _rows_view(x2d_src: torch.Tensor, T: int, B: int):
     return x, x.stride(1)
 
 
+PERSISTENT_MAX_H = 560  # largest hidden size the register-resident persistent kernels hold
+
+
+def _kernel_gates(cell: int) -> int:
+    """Gate blocks the recurrent kernels see (single-gate RNN is padded with a zero update gate)."""
+    return {pk.CELL_LSTM: 4, pk.CELL_GRU: 3}.get(cell, 2)
+
+
+def _real_gates(cell: int) -> int:
+    return {pk.CELL_RNN: 1, pk.CELL_LSTM: 4, pk.CELL_GRU: 3}.get(cell, 2)
+
+
+_TWO_PHASE = (pk.CELL_GRU, pk.CELL_MGRU)  # candidate contracts (gate * h): two dependent products per step
+
+
+def _stepwise(cell: int, H: int) -> bool:
+    """LSTM, GRU, minimalGRU and large-H liGRU run on the step-wise kernels (pk_cell_step.cu)."""
+    return cell in (pk.CELL_LSTM, pk.CELL_GRU, pk.CELL_MGRU) or (cell == pk.CELL_LIGRU and H > PERSISTENT_MAX_H)
+
+
 class LiGRUStackFn(torch.autograd.Function):
-    """Whole liGRU stack: reference neural_networks.liGRU.forward (:1082-1155) and its autograd."""
+    """Whole recurrent stack (liGRU :1082-1155, RNN :1398-1461, LSTM :403-483 of the reference
+    neural_networks.py) and its autograd, as a fixed sequence of C-ABI calls per layer."""
 
     @staticmethod
     def forward(ctx, x, cfg: RecStackCfg, *params):
-        # params per layer (NG = 2 gates for liGRU, 1 for RNN): w_g..., u_g..., then per gate (bn.weight, bn.bias)
-        # if use_bn else per gate (w.bias).  Single-gate cells are padded with a zero second gate block.
+        # params per layer (ngr real gates, reference registration order): w_g..., u_g..., then per gate
+        # (bn.weight, bn.bias) if use_bn else per gate (w.bias).
         if not x.is_cuda:
-            raise RuntimeError("pytorch-kaldi_b200: liGRU needs CUDA tensors (there is no CPU fallback)")
+            raise RuntimeError("pytorch-kaldi_b200: recurrent layers need CUDA tensors (there is no CPU fallback)")
         dev = x.device
         T, B, D0 = x.shape
         TB = T * B
@@ -72,6 +92,7 @@ class LiGRUStackFn(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad)
         f32 = dict(device=dev, dtype=torch.float32)
         f16 = dict(device=dev, dtype=torch.float16)
+        ngr, ngk = _real_gates(cfg.cell), _kernel_gates(cfg.cell)
 
         saved = []  # per layer dict of tensors needed by backward
         pi = 0
@@ -81,57 +102,57 @@ class LiGRUStackFn(torch.autograd.Function):
         y32 = None
         for li, L in enumerate(cfg.layers):
             H = L.H
-            ng = 1 if cfg.cell == pk.CELL_RNN else 2
-            ws_, us_ = params[pi:pi + ng], params[pi + ng:pi + 2 * ng]
-            pi += 2 * ng
-            if ng == 2:
-                wh, wz, uh, uz = ws_[0], ws_[1], us_[0], us_[1]
-            else:  # RNN: the update-gate block is all zeros (and pinned to 0 inside the kernel)
-                wh, uh = ws_[0], us_[0]
-                wz, uz = torch.zeros_like(wh), torch.zeros_like(uh)
+            ws_, us_ = list(params[pi:pi + ngr]), list(params[pi + ngr:pi + 2 * ngr])
+            pi += 2 * ngr
+            for _ in range(ngk - ngr):  # RNN: the update-gate block is all zeros (and pinned to 0 in the kernel)
+                ws_.append(torch.zeros_like(ws_[0]))
+                us_.append(torch.zeros_like(us_[0]))
             if L.use_bn:
-                bnp = params[pi:pi + 2 * ng]
-                pi += 2 * ng
-                g_h, b_h = bnp[0], bnp[1]
-                g_z, b_z = (bnp[2], bnp[3]) if ng == 2 else (torch.ones_like(g_h), torch.zeros_like(b_h))
+                bnp = params[pi:pi + 2 * ngr]
+                pi += 2 * ngr
+                gammas = [bnp[2 * g] for g in range(ngr)]
+                betas = [bnp[2 * g + 1] for g in range(ngr)]
             else:
-                bias_h = params[pi]
-                bias_z = params[pi + 1] if ng == 2 else torch.zeros_like(bias_h)
-                pi += ng
-            C2 = 2 * H
+                biases = list(params[pi:pi + ngr])
+                pi += ngr
+                biases += [torch.zeros_like(biases[0]) for _ in range(ngk - ngr)]
+            CG = ngk * H
             ldD = pad8(D)
             # ---- operands: fp16 copies of the layer input and of the stacked projection weights
             if li == 0:
                 X16 = torch.empty(TB, ldD, **f16)
                 XT16 = torch.empty(D, ldt, **f16) if need_grad else None
                 pk.transpose_f32(xsrc, ldx, TB, D, outT16=XT16, ldo16=ldt, in16=X16, ldi16=ldD)
-            Wcat = torch.cat([wh, wz], 0).contiguous()
-            W16 = torch.empty(C2, ldD, **f16)
-            ld2H = pad8(C2)
-            WT16 = torch.empty(D, ld2H, **f16) if need_grad else None
-            pk.transpose_f32(Wcat, D, C2, D, outT16=WT16, ldo16=ld2H, in16=W16, ldi16=ldD)
-            # ---- projection PT = [Wh;Wz] X^T (channel-major) with BatchNorm statistics in the epilogue
-            PT = torch.empty(C2, ldt, **f32)
+            Wcat = torch.cat(ws_, 0).contiguous()
+            W16 = torch.empty(CG, ldD, **f16)
+            ldG = pad8(CG)
+            WT16 = torch.empty(D, ldG, **f16) if need_grad else None
+            pk.transpose_f32(Wcat, D, CG, D, outT16=WT16, ldo16=ldG, in16=W16, ldi16=ldD)
+            # ---- projection PT = [W_g] X^T (channel-major) with BatchNorm statistics in the epilogue
+            PT = torch.empty(CG, ldt, **f32)
             bn_train = L.use_bn and L.bn_training
-            stats = torch.zeros(C2, 2, device=dev, dtype=torch.float64) if bn_train else None
-            pk.gemm_tn(W16, X16, PT, C2, TB, D, lda=ldD, ldb=ldD, ldc=ldt, rowstats=stats)
-            scale = torch.empty(C2, **f32)
-            shift = torch.empty(C2, **f32)
-            mean = torch.empty(C2, **f32) if L.use_bn else None
-            rstd = torch.empty(C2, **f32) if L.use_bn else None
+            stats = torch.zeros(CG, 2, device=dev, dtype=torch.float64) if bn_train else None
+            pk.gemm_tn(W16, X16, PT, CG, TB, D, lda=ldD, ldb=ldD, ldc=ldt, rowstats=stats)
+            scale = torch.empty(CG, **f32)
+            shift = torch.empty(CG, **f32)
+            mean = torch.empty(CG, **f32) if L.use_bn else None
+            rstd = torch.empty(CG, **f32) if L.use_bn else None
+            gamma = None
             if L.use_bn:
-                if ng == 1:  # padded gate: identity "normalisation" (its projections are exactly zero)
-                    scale[H:].fill_(1.0); shift[H:].zero_(); mean[H:].zero_(); rstd[H:].fill_(1.0)
-                for gi, (bn, gam, bet) in enumerate(((L.bn_h, g_h, b_h), (L.bn_z, g_z, b_z))[:ng]):
+                if ngk > ngr:  # padded gate: identity "normalisation" (its projections are exactly zero)
+                    scale[ngr * H:].fill_(1.0); shift[ngr * H:].zero_(); mean[ngr * H:].zero_(); rstd[ngr * H:].fill_(1.0)
+                for gi in range(ngr):
+                    bn = L.bns[gi]
                     sl = slice(gi * H, (gi + 1) * H)
-                    pk.bn_finalize(stats[sl] if bn_train else None, H, TB, TB * ndir, gam, bet, bn.eps,
+                    pk.bn_finalize(stats[sl] if bn_train else None, H, TB, TB * ndir, gammas[gi], betas[gi], bn.eps,
                                    bn.momentum if bn.momentum is not None else 0.1, bn_train,
                                    bn.running_mean, bn.running_var, bn.num_batches_tracked if bn_train else None,
                                    scale[sl], shift[sl], mean[sl], rstd[sl])
+                gamma = torch.cat(gammas + [torch.ones_like(gammas[0]) for _ in range(ngk - ngr)]).contiguous()
             else:
-                pk.fill_scale_shift(torch.cat([bias_h, bias_z]).contiguous(), C2, scale, shift)
-            # ---- the recurrence: one persistent cluster kernel for all T steps
-            U = torch.cat([uh, uz], 0).contiguous()
+                pk.fill_scale_shift(torch.cat(biases).contiguous(), CG, scale, shift)
+            # ---- the recurrence
+            U = torch.cat(us_, 0).contiguous()
             F = ndir * H
             last = li == len(cfg.layers) - 1
             ldF = pad8(F)
@@ -139,17 +160,24 @@ class LiGRUStackFn(torch.autograd.Function):
             if last:
                 y32 = torch.empty(T, B, F, **f32)
             HT = torch.empty(F, ldt, **f32) if need_grad else None
-            ZT = torch.empty(F, ldt, **f32) if need_grad else None
-            HCT = torch.empty(F, ldt, **f32) if need_grad else None
             HT16 = torch.empty(F, ldt, **f16) if (need_grad and not last) else None
             HP16 = torch.empty(F, ldt, **f16) if need_grad else None
-            pk.rnn_layer_fwd(cfg.cell | cfg.cell_flags, T, B, H, ndir, L.act, PT, ldt, scale, shift, U, L.mask,
-                             L.mask_scalar, y32 if last else None, F, Y16, ldF, HT, HT16, HP16, ZT, HCT, ldt)
+            stepwise = _stepwise(cfg.cell, H)
+            nsv = {pk.CELL_LSTM: 5, pk.CELL_GRU: 3}.get(cfg.cell, 2)
+            HX16 = torch.empty(F, ldt, **f16) if (need_grad and cfg.cell in _TWO_PHASE) else None
+            SV = [torch.empty(F, ldt, **f32) if need_grad else None for _ in range(nsv)]
+            if stepwise:  # one fused kernel per time step, T launches inside this call
+                wsb = pk.rnn_step_workspace_bytes(cfg.cell, T, B, H, ndir, False)
+                wsp = torch.empty(wsb, device=dev, dtype=torch.uint8)
+                pk.rnn_step_fwd(cfg.cell, T, B, H, ndir, L.act, PT, ldt, scale, shift, U, L.mask, L.mask_scalar,
+                                y32 if last else None, F, Y16, ldF, HT, HT16, HP16, HX16, SV, ldt, wsp)
+            else:  # one persistent cluster kernel for all T steps
+                pk.rnn_layer_fwd(cfg.cell | cfg.cell_flags, T, B, H, ndir, L.act, PT, ldt, scale, shift, U, L.mask,
+                                 L.mask_scalar, y32 if last else None, F, Y16, ldF, HT, HT16, HP16, SV[0], SV[1], ldt)
             if need_grad:
                 saved.append(dict(D=D, H=H, XT16=XT16, WT16=WT16, PT=PT if bn_train else None, mean=mean, rstd=rstd,
-                                  gamma=torch.cat([g_h, g_z]).contiguous() if L.use_bn else None,
-                                  HT=HT, ZT=ZT, HCT=HCT, HP16=HP16, U=U, mask=L.mask, mask_scalar=L.mask_scalar,
-                                  act=L.act, use_bn=L.use_bn, bn_train=bn_train, ng=ng))
+                                  gamma=gamma, HT=HT, SV=SV, HP16=HP16, HX16=HX16, U=U, mask=L.mask, mask_scalar=L.mask_scalar,
+                                  act=L.act, use_bn=L.use_bn, bn_train=bn_train, stepwise=stepwise))
             # next layer reads this layer's fp16 outputs directly
             X16, XT16, D = Y16, HT16, F
         ctx.cfg = cfg
@@ -166,6 +194,7 @@ class LiGRUStackFn(torch.autograd.Function):
         dev = dY.device
         f32 = dict(device=dev, dtype=torch.float32)
         f16 = dict(device=dev, dtype=torch.float16)
+        ngr, ngk = _real_gates(cfg.cell), _kernel_gates(cfg.cell)
         grads = []
         dYT = None
         dx = None
@@ -173,8 +202,8 @@ class LiGRUStackFn(torch.autograd.Function):
         for li in reversed(range(len(saved))):
             S = saved[li]
             H, D = S["H"], S["D"]
-            F, C2 = ndir * H, 2 * H
-            ld2H = pad8(C2)
+            F, CG = ndir * H, ngk * H
+            ldG = pad8(CG)
             if dYT is None:  # top layer: autograd hands us the row-major gradient of the module output
                 dy2 = dY.reshape(TB, F)
                 if dy2.dtype != torch.float32 or not dy2.is_contiguous():
@@ -184,44 +213,60 @@ class LiGRUStackFn(torch.autograd.Function):
             # power-of-two loss scale for this layer's fp16 gradient operands (amax came with the producer)
             sc = torch.empty(2, **f32)
             pk.amax_finalize(amax_acc, 8.0, sc)
-            legacy = bool(cfg.cell_flags & pk.REC_LEGACY)
-            GT = torch.empty(ndir, C2, ldt, **f32) if legacy else None
-            GT16 = torch.empty(ndir, C2, ldt, **f16)
-            pk.rnn_layer_bwd(cfg.cell | cfg.cell_flags, T, B, H, ndir, S["act"], dYT, S["HT"], S["ZT"], S["HCT"],
-                             ldt, S["U"], S["mask"], S["mask_scalar"], sc, GT, GT16)
+            GT = None
+            GT16 = torch.empty(ndir, CG, ldt, **f16)
+            if S["stepwise"]:
+                wsb = pk.rnn_step_workspace_bytes(cfg.cell, T, B, H, ndir, True)
+                wsp = torch.empty(wsb, device=dev, dtype=torch.uint8)
+                pk.rnn_step_bwd(cfg.cell, T, B, H, ndir, S["act"], dYT, S["HT"], S["SV"], ldt, S["U"], S["mask"],
+                                S["mask_scalar"], sc, GT16, wsp)
+            else:
+                if cfg.cell_flags & pk.REC_LEGACY:
+                    GT = torch.empty(ndir, CG, ldt, **f32)
+                pk.rnn_layer_bwd(cfg.cell | cfg.cell_flags, T, B, H, ndir, S["act"], dYT, S["HT"], S["SV"][0],
+                                 S["SV"][1], ldt, S["U"], S["mask"], S["mask_scalar"], sc, GT, GT16)
             inv = sc[1:2]
             # dU = sum_t G_t^T h_{t-1}  (both directions accumulate into the shared weights)
-            dU = torch.empty(C2, H, **f32)
+            dU = torch.empty(CG, H, **f32)
             for d in range(ndir):
-                pk.gemm_tn(GT16[d], S["HP16"][d * H:(d + 1) * H], dU, C2, H, TB, lda=ldt, ldb=ldt, ldc=H,
-                           alpha_dev=inv, accumulate=(d > 0), split_k=16)
+                hp = S["HP16"][d * H:(d + 1) * H]
+                if S["HX16"] is None:
+                    pk.gemm_tn(GT16[d], hp, dU, CG, H, TB, lda=ldt, ldb=ldt, ldc=H, alpha_dev=inv, accumulate=(d > 0),
+                               split_k=16)
+                else:  # GRU / minimalGRU: the candidate block contracted (gate * h_{t-1}) (:634, :1295)
+                    pk.gemm_tn(GT16[d][:H], S["HX16"][d * H:(d + 1) * H], dU[:H], H, H, TB, lda=ldt, ldb=ldt, ldc=H,
+                               alpha_dev=inv, accumulate=(d > 0), split_k=16)
+                    pk.gemm_tn(GT16[d][H:], hp, dU[H:], CG - H, H, TB, lda=ldt, ldb=ldt, ldc=H, alpha_dev=inv,
+                               accumulate=(d > 0), split_k=16)
             # BatchNorm backward on the de-duplicated projection (both directions folded)
-            dgamma = torch.empty(C2, **f32)
-            dbeta = torch.empty(C2, **f32)
+            dgamma = torch.empty(CG, **f32)
+            dbeta = torch.empty(CG, **f32)
             need_dx = li > 0 or ctx.x_needs_grad
-            dPT16 = torch.empty(C2, ldt, **f16)
-            dP16 = torch.empty(TB, ld2H, **f16) if need_dx else None
-            sums = torch.empty(2 * C2, device=dev, dtype=torch.float64)
-            pk.bn_bwd(C2, ndir, TB, GT, GT16, ldt, S["PT"], ldt, S["use_bn"], S["bn_train"], S["mean"], S["rstd"],
-                      S["gamma"], sc, dgamma, dbeta, dPT16, ldt, dP16, ld2H, sums)
+            dPT16 = torch.empty(CG, ldt, **f16)
+            dP16 = torch.empty(TB, ldG, **f16) if need_dx else None
+            sums = torch.empty(2 * CG, device=dev, dtype=torch.float64)
+            pk.bn_bwd(CG, ndir, TB, GT, GT16, ldt, S["PT"], ldt, S["use_bn"], S["bn_train"], S["mean"], S["rstd"],
+                      S["gamma"], sc, dgamma, dbeta, dPT16, ldt, dP16, ldG, sums)
             # dW = dP^T X
-            dW = torch.empty(C2, D, **f32)
-            pk.gemm_tn(dPT16, S["XT16"], dW, C2, D, TB, lda=ldt, ldb=ldt, ldc=D, alpha_dev=inv, split_k=8)
-            if S["ng"] == 2:
-                lg = [dW[:H], dW[H:], dU[:H], dU[H:]]
-                lg += [dgamma[:H], dbeta[:H], dgamma[H:], dbeta[H:]] if S["use_bn"] else [dbeta[:H], dbeta[H:]]
+            dW = torch.empty(CG, D, **f32)
+            pk.gemm_tn(dPT16, S["XT16"], dW, CG, D, TB, lda=ldt, ldb=ldt, ldc=D, alpha_dev=inv, split_k=8)
+            sl = [slice(g * H, (g + 1) * H) for g in range(ngr)]
+            lg = [dW[s] for s in sl] + [dU[s] for s in sl]
+            if S["use_bn"]:
+                for s in sl:
+                    lg += [dgamma[s], dbeta[s]]
             else:
-                lg = [dW[:H], dU[:H]] + ([dgamma[:H], dbeta[:H]] if S["use_bn"] else [dbeta[:H]])
+                lg += [dbeta[s] for s in sl]
             grads = lg + grads
             # gradient w.r.t. the layer input
             if li > 0:
                 dXT = torch.empty(D, ldt, **f32)
-                pk.gemm_tn(S["WT16"], dP16, dXT, D, TB, C2, lda=ld2H, ldb=ld2H, ldc=ldt, alpha_dev=inv,
+                pk.gemm_tn(S["WT16"], dP16, dXT, D, TB, CG, lda=ldG, ldb=ldG, ldc=ldt, alpha_dev=inv,
                            amax_bits=amax_acc)
                 dYT = dXT
             elif ctx.x_needs_grad:
                 dx = torch.empty(T, B, D, **f32)
-                pk.gemm_tn(dP16, S["WT16"], dx, TB, D, C2, lda=ld2H, ldb=ld2H, ldc=D, alpha_dev=inv)
+                pk.gemm_tn(dP16, S["WT16"], dx, TB, D, CG, lda=ldG, ldb=ldG, ldc=D, alpha_dev=inv)
         ctx.saved = None
         return (dx, None, *grads)
 

@@ -89,14 +89,18 @@ def grads_np(module, prefix):
     return out
 
 
+CELLS = {"ligru": ("liGRU", ("wh", "wz"), "ligru."), "rnn": ("RNN", ("wh",), "ligru."),
+         "lstm": ("LSTM", ("wfx", "wix", "wox", "wcx"), "net."), "gru": ("GRU", ("wh", "wz", "wr"), "net."),
+         "minimalgru": ("minimalGRU", ("wh", "wz"), "net.")}
+
+
 def ligru_case(name, *, T, B, D, lay, S, S2, drop, bn, act, bidir, seed, head_scale=20.0, full=True, cell="ligru"):
     torch.manual_seed(seed)
     opts = ligru_opts(lay, drop, bn, act, bidir)
-    if cell == "rnn":  # same option names with the rnn_ prefix (proto/RNN.proto)
-        opts = {k.replace("ligru_", "rnn_"): v for k, v in opts.items()}
-        net = ref_nn.RNN(opts, D)
-    else:
-        net = ref_nn.liGRU(opts, D)
+    # same option names with the cell's own prefix (proto/*.proto); W-list names in registration order
+    cls_name, gates, net_pfx = CELLS[cell]
+    opts = {k.replace("ligru_", cell + "_"): v for k, v in opts.items()}
+    net = getattr(ref_nn, cls_name)(opts, D)
     head = ref_nn.MLP(mlp_opts([S], 0.0, False, False, "softmax"), net.out_dim)
     head2 = ref_nn.MLP(mlp_opts([S2], 0.0, False, False, "softmax"), net.out_dim) if S2 else None
     with torch.no_grad():  # give the posteriors real margins
@@ -105,14 +109,13 @@ def ligru_case(name, *, T, B, D, lay, S, S2, drop, bn, act, bidir, seed, head_sc
         if head2 is not None:
             head2.wx[0].weight.mul_(head_scale)
         for i in range(len(lay)):
-            gates = ("wh",) if cell == "rnn" else ("wh", "wz")
             for gname in gates:
                 if bn:
                     getattr(net, "bn_" + gname)[i].weight.uniform_(0.5, 1.5)
                     getattr(net, "bn_" + gname)[i].bias.normal_(0, 0.2)
                 else:
                     getattr(net, gname)[i].bias.normal_(0, 0.2)
-    mods = [("ligru.", net), ("head.", head)] + ([("head2.", head2)] if head2 is not None else [])
+    mods = [(net_pfx, net), ("head.", head)] + ([("head2.", head2)] if head2 is not None else [])
     out = {}
     for pfx, m in mods:
         out.update({"init." + k: v for k, v in sd_np(m, pfx).items()})
@@ -253,3 +256,11 @@ if __name__ == "__main__":
     if not only or "rnn_uni_tanh" in only:
       ligru_case("rnn_uni_tanh", T=10, B=3, D=9, lay=[33], S=12, S2=0, drop=0.1, bn=False, act="tanh", bidir=False,
                  seed=32, cell="rnn")
+    # G: LSTM :300-483, GRU :486-654, minimalGRU :1158-1316 — bidirectional BN+ReLU/tanh stacks and bias variants
+    for cell, seed in (("lstm", 41), ("gru", 51), ("minimalgru", 61)):
+        if not only or f"{cell}_bidir_bn" in only:
+            ligru_case(f"{cell}_bidir_bn", T=13, B=5, D=11, lay=[36, 28], S=19, S2=0, drop=0.2, bn=True,
+                       act="tanh" if cell == "lstm" else "relu", bidir=True, seed=seed, cell=cell)
+        if not only or f"{cell}_uni_nobn" in only:
+            ligru_case(f"{cell}_uni_nobn", T=9, B=3, D=8, lay=[21], S=11, S2=0, drop=0.1, bn=False,
+                       act="tanh", bidir=False, seed=seed + 1, cell=cell)

@@ -53,6 +53,29 @@ def ligru_layers(d, dtype=np.float64, stage="init."):
     return layers
 
 
+# reference ModuleList names per cell, registration order (= oracle GATES order)
+CELL_LISTS = {"lstm": (("wfx", "wix", "wox", "wcx"), ("ufh", "uih", "uoh", "uch")),
+              "gru": (("wh", "wz", "wr"), ("uh", "uz", "ur")),
+              "minimalgru": (("wh", "wz"), ("uh", "uz"))}
+
+
+def cell_layers(d, dtype=np.float64, stage="init."):
+    """Layer dicts for oracle.cell_forward (LSTM / GRU / minimalGRU fixtures, module prefix `net.`)."""
+    m = d["meta"]
+    wn, un = CELL_LISTS[m["cell"]]
+    layers = []
+    for i in range(len(m["lay"])):
+        L = dict(w=[d[f"{stage}net.{w}.{i}.weight"].astype(dtype) for w in wn],
+                 u=[d[f"{stage}net.{u}.{i}.weight"].astype(dtype) for u in un], act=m["act"], drop=m["drop"],
+                 b=None, bn=None)
+        if m["bn"]:
+            L["bn"] = [bn_dict(d, f"net.bn_{w}.{i}", "init.", dtype) for w in wn]
+        else:
+            L["b"] = [d[f"{stage}net.{w}.{i}.bias"].astype(dtype) for w in wn]
+        layers.append(L)
+    return layers
+
+
 def head_layer(d, prefix="head", dtype=np.float64, stage="init."):
     return dict(w=d[f"{stage}{prefix}.wx.0.weight"].astype(dtype), b=d[f"{stage}{prefix}.wx.0.bias"].astype(dtype),
                 bn=None, ln=None, act="softmax", drop=0.0)

@@ -103,6 +103,46 @@ def test_ligru_eval_mode():
     assert gu.relerr(logp, d["eval_logp"]) < TOL
 
 
+CELL_CASES = [f"{c}_{v}" for c in ("lstm", "gru", "minimalgru") for v in ("bidir_bn", "uni_nobn")]
+
+
+def run_cell(name, dtype=np.float64, quant=False):
+    d = gu.load(name)
+    m = d["meta"]
+    layers = gu.cell_layers(d, dtype)
+    heads = [gu.head_layer(d, "head", dtype)]
+    res = orc.ligru_model_step(d["x"].astype(dtype), [d["lab"].astype(np.int64)], layers, heads, masks=gu.masks(d),
+                               bidir=m["bidir"], cell=m["cell"], quant=quant)
+    return d, layers, res
+
+
+@pytest.mark.parametrize("name", CELL_CASES)
+def test_cell_forward_and_gradients(name):
+    """LSTM :300-483, GRU :486-654, minimalGRU :1158-1316 restatements against the unmodified reference."""
+    d, layers, res = run_cell(name)
+    m = d["meta"]
+    wn, un = gu.CELL_LISTS[m["cell"]]
+    assert gu.relerr(res["out"], d["out"]) < TOL
+    assert gu.relerr(res["logp"][0], d["logp"]) < TOL
+    assert abs(res["loss"] - float(d["loss"])) / abs(float(d["loss"])) < 1e-5
+    assert res["err"] == pytest.approx(float(d["err"]), abs=1e-7)
+    for i, g in enumerate(res["ligru_grads"]):
+        for gi, (w, u) in enumerate(zip(wn, un)):
+            gu.check_tensor(d, f"grad.net.{w}.{i}.weight", g["w"][gi], 5e-4)
+            gu.check_tensor(d, f"grad.net.{u}.{i}.weight", g["u"][gi], 5e-4)
+            if m["bn"]:
+                gu.check_tensor(d, f"grad.net.bn_{w}.{i}.weight", g["bn_weight"][gi], 5e-4)
+                gu.check_tensor(d, f"grad.net.bn_{w}.{i}.bias", g["bn_bias"][gi], 5e-4)
+            else:
+                gu.check_tensor(d, f"grad.net.{w}.{i}.bias", g["b"][gi], 5e-4)
+    gu.check_tensor(d, "grad.head.wx.0.weight", res["head_grads"][0]["w"], 5e-4)
+    for i, L in enumerate(layers):
+        if m["bn"]:
+            for gi, w in enumerate(wn):
+                assert gu.relerr(L["bn"][gi]["running_mean"], d[f"bnstat.net.bn_{w}.{i}.running_mean"]) < TOL
+                assert gu.relerr(L["bn"][gi]["running_var"], d[f"bnstat.net.bn_{w}.{i}.running_var"]) < TOL
+
+
 @pytest.mark.parametrize("name", MLP_CASES)
 def test_mlp(name):
     d = gu.load(name)
