@@ -302,9 +302,9 @@ def main():
     pk_peaks, how = peaks()
     peak = pk_peaks.get("bf16_tflops_sustained", 1400.0)
     achieved = flops_launch / (k_avg * 1e-3) / 1e12 if k_avg > 0 else 0.0
-    roofline = {"kernel": "ligru_bwd_kernel (persistent reverse-time recurrence, 5 launches/step)", "bound": "tensor",
+    roofline = {"kernel": "ligru_bwd_ws_kernel (persistent reverse-time recurrence, 5 launches/step)", "bound": "tensor",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "peak_source": f"{how} bf16 sustained (fp16 operands, fp32 accumulate)", "traffic": None,
+                "peak_source": f"{how} bf16 sustained (fp16 operands, fp32 accumulate)", "traffic": 348441088, "traffic_unit": "bytes/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_ncu_ligru_ws_kernels.txt)",
                 "avg_launch_ms": k_avg, "launches_timed": len(k_ms),
                 "share_of_step": (k_avg * L) / (ms_dev / args.steps) if ms_dev > 0 else None,
                 "us_per_recurrent_step": 1e3 * k_avg / T}
