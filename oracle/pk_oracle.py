@@ -485,6 +485,154 @@ def mlp_backward(dout, layers, caches):
 
 
 # --------------------------------------------------------------------------------------
+# CNN :1464-1556 / SincNet :1559-1665 / SincConv :1668-1813 — conv front-ends (non-sequential modules)
+# --------------------------------------------------------------------------------------
+
+
+def sinc_filters(low_hz_, band_hz_, k, sample_rate=16000, min_low_hz=50, min_band_hz=50):
+    """SincConv.forward filter synthesis (:1777-1803).  low_hz_/band_hz_ [C,1] (normalised by the sample rate,
+    :1743-1750).  Returns (filters [C,k], cache)."""
+    n = (k - 1) / 2
+    n_ = (np.arange(-n, n + 1) / sample_rate).reshape(1, -1)                      # :1759-1760
+    n_lin = np.linspace(0, k, k)
+    window = 0.54 - 0.46 * np.cos(2 * np.pi * n_lin / k)                          # :1755-1756
+    low = min_low_hz / sample_rate + np.abs(low_hz_)                              # :1789
+    high = low + min_band_hz / sample_rate + np.abs(band_hz_)                     # :1790
+    a = 2 * np.pi * n_ * sample_rate                                              # sinc argument = f * a
+    half = int((k - 1) / 2)
+
+    def lowpass(f):  # 2 f sinc(f a) with the reference's mirrored evaluation (:1762-1770)
+        xl = (f * a)[:, :half]
+        yl = np.sin(xl) / xl
+        s = np.concatenate([yl, np.ones((f.shape[0], 1)), yl[:, ::-1]], axis=1)
+        return 2 * f * s
+
+    bp = lowpass(high) - lowpass(low)                                             # :1798
+    m = bp.max(axis=1, keepdims=True)                                             # :1799
+    filt = bp / m * window                                                        # :1800-1803
+    return filt, dict(low=low, high=high, a=a, bp=bp, m=m, window=window, low_hz_=low_hz_, band_hz_=band_hz_,
+                      half=half)
+
+
+def sinc_filters_bwd(dfilt, c):
+    """d(filters [C,k]) -> (d low_hz_, d band_hz_) [C,1]."""
+    bp, m, win, a, half = c["bp"], c["m"], c["window"], c["a"], c["half"]
+    k = bp.shape[1]
+    g = dfilt * win
+    dbp = g / m
+    jstar = bp.argmax(axis=1)
+    corr = (g * bp).sum(axis=1) / (m[:, 0] ** 2)
+    dbp[np.arange(bp.shape[0]), jstar] -= corr
+
+    def dlowpass(f):  # d/df of 2 f sinc(f a): 2 cos(f a) off-centre (mirrored like the forward), 2 at the centre
+        dl = 2 * np.cos((f * a)[:, :half])
+        return np.concatenate([dl, 2 * np.ones((f.shape[0], 1)), dl[:, ::-1]], axis=1)
+
+    dhigh = (dbp * dlowpass(c["high"])).sum(axis=1, keepdims=True)
+    dlow = -(dbp * dlowpass(c["low"])).sum(axis=1, keepdims=True) + dhigh
+    return np.sign(c["low_hz_"]) * dlow, np.sign(c["band_hz_"]) * dhigh
+
+
+def conv1d_valid(x, w, b=None):
+    """F.conv1d, stride 1, no padding.  x [N,Ci,L], w [Co,Ci,k] -> [N,Co,L-k+1]."""
+    k = w.shape[2]
+    win = np.lib.stride_tricks.sliding_window_view(x, k, axis=2)  # [N,Ci,Lo,k]
+    y = np.einsum("nilk,oik->nol", win, w, optimize=True)
+    return y if b is None else y + b[None, :, None]
+
+
+def convnet_forward(x, layers, *, ln0=None, training=True, keeps=None, quant=False):
+    """CNN.forward :1530-1556 / SincNet.forward :1638-1665 on x [N, L0].
+
+    layers: dicts with  kind "sinc" (low_hz_, band_hz_, k, sample_rate, min_low_hz, min_band_hz) or "conv" (w [Co,Ci,k],
+    b [Co]);  pool (max_pool1d length);  ln = dict(gamma [C,Lp], beta) or None (the reference's LayerNorm over the
+    LAST axis with a [C,Lp] affine, :1505-1507);  act;  drop (nn.Dropout p, inverted scaling).
+    ln0: dict(gamma [L0], beta) input LayerNorm (:1541-1542) or None.  keeps: per-layer 0/1 keep masks [N,C,Lp].
+    quant: round conv operands to fp16 where the CUDA path does.  Returns ([N, C*Lp], caches)."""
+    Q = q16 if quant else (lambda a_: a_)
+    c0 = None
+    if ln0 is not None:
+        x, c0 = layernorm_fwd(x, ln0["gamma"], ln0["beta"])
+    h = x[:, None, :]
+    caches = []
+    for li, L in enumerate(layers):
+        fc = None
+        if L["kind"] == "sinc":
+            filt, fc = sinc_filters(L["low_hz_"], L["band_hz_"], L["k"], L.get("sample_rate", 16000),
+                                    L.get("min_low_hz", 50), L.get("min_band_hz", 50))
+            w, b = filt[:, None, :], None
+        else:
+            w, b = L["w"], L["b"]
+        hq, wq = Q(h), Q(w)
+        y = conv1d_valid(hq, wq, b)
+        p = L["pool"]
+        Lp = y.shape[2] // p
+        yw = y[:, :, :Lp * p].reshape(y.shape[0], y.shape[1], Lp, p)
+        arg = yw.argmax(axis=3)
+        pooled = np.take_along_axis(yw, arg[..., None], axis=3)[..., 0]
+        lnc = None
+        pre = pooled
+        if L.get("ln") is not None:
+            pre, lnc = layernorm_fwd(pooled, L["ln"]["gamma"], L["ln"]["beta"])
+        act = act_fwd(L["act"], pre)
+        keep = None
+        out = act
+        if training and L.get("drop", 0.0) > 0 and keeps is not None and keeps[li] is not None:
+            keep = keeps[li].astype(x.dtype) / (1.0 - L["drop"])
+            out = act * keep
+        caches.append(dict(hq=hq, wq=wq, arg=arg, ylen=y.shape[2], pre=pre, act=act, keep=keep, ln=lnc, fc=fc, p=p))
+        h = out
+    return h.reshape(h.shape[0], -1), dict(layers=caches, ln0=c0)
+
+
+def convnet_backward(dout, layers, caches):
+    """Returns (dx [N,L0] w.r.t. the (normalised) input, grads list, ln0 grads or None).  grads[i]: dict(w, b) or
+    dict(low_hz_, band_hz_), plus ln_gamma / ln_beta [C,Lp]."""
+    cs = caches["layers"]
+    last = cs[-1]
+    N = dout.shape[0]
+    d = dout.reshape(N, last["act"].shape[1], last["act"].shape[2])
+    grads = [None] * len(layers)
+    for li in reversed(range(len(layers))):
+        L, c = layers[li], cs[li]
+        g = {}
+        if c["keep"] is not None:
+            d = d * c["keep"]
+        d = d * act_bwd(L["act"], c["pre"], c["act"])
+        if c["ln"] is not None:
+            xc, std, gamma, eps = c["ln"]
+            g["ln_gamma"] = (d * xc / (std + eps)).sum(0)
+            g["ln_beta"] = d.sum(0)
+            d, _, _ = layernorm_bwd(d, c["ln"])
+        # max_pool1d backward: route to the arg-max position of each window
+        Co, Lp, p = d.shape[1], d.shape[2], c["p"]
+        dy = np.zeros((N, Co, c["ylen"]), dtype=d.dtype)
+        dyw = np.zeros((N, Co, Lp, p), dtype=d.dtype)
+        np.put_along_axis(dyw, c["arg"][..., None], d[..., None], axis=3)
+        dy[:, :, :Lp * p] = dyw.reshape(N, Co, Lp * p)
+        k = c["wq"].shape[2]
+        win = np.lib.stride_tricks.sliding_window_view(c["hq"], k, axis=2)  # [N,Ci,Lo,k]
+        dw = np.einsum("nol,nilk->oik", dy, win, optimize=True)
+        if L["kind"] == "sinc":
+            g["low_hz_"], g["band_hz_"] = sinc_filters_bwd(dw[:, 0, :], c["fc"])
+        else:
+            g["w"], g["b"] = dw, dy.sum(axis=(0, 2))
+        # dx[n,i,l+j] += dy[n,o,l] w[o,i,j]
+        dh = np.zeros_like(c["hq"])
+        for j in range(k):
+            dh[:, :, j:j + dy.shape[2]] += np.einsum("nol,oi->nil", dy, c["wq"][:, :, j], optimize=True)
+        d = dh
+        grads[li] = g
+    dx = d[:, 0, :]
+    g0 = None
+    if caches["ln0"] is not None:
+        xc, std, gamma, eps = caches["ln0"]
+        g0 = dict(gamma=(dx * xc / (std + eps)).sum(0), beta=dx.sum(0))
+        dx, _, _ = layernorm_bwd(dx, caches["ln0"])
+    return dx, grads, g0
+
+
+# --------------------------------------------------------------------------------------
 # cost ops of utils.forward_model
 # --------------------------------------------------------------------------------------
 

@@ -223,6 +223,78 @@ def mlp_case(name, *, N, D, lay, drop, bn, ln, act, seed):
     print(f"{name}: loss={loss.item():.6f} err={err.item():.4f} -> {path} ({os.path.getsize(path)/1e6:.2f} MB)")
 
 
+def conv_opts(prefix, n_filt, len_filt, pool, ln, ln_inp, act, drop):
+    n = len(n_filt)
+    j = lambda v: ",".join(map(str, v))
+    o = {f"{prefix}_N_filt": j(n_filt), f"{prefix}_len_filt": j(len_filt), f"{prefix}_max_pool_len": j(pool),
+         f"{prefix}_use_laynorm_inp": str(ln_inp), f"{prefix}_use_batchnorm_inp": "False",
+         f"{prefix}_use_laynorm": j([ln] * n), f"{prefix}_use_batchnorm": j([False] * n),
+         f"{prefix}_act": j([act] * n), f"{prefix}_drop": j([drop] * n), "use_cuda": "False", "to_do": "train"}
+    if prefix == "sinc":
+        o.update(sinc_sample_rate="16000", sinc_min_low_hz="50", sinc_min_band_hz="50")
+    return o
+
+
+def conv_case(name, *, kind, N, L0, n_filt, len_filt, pool, ln, ln_inp, act, drop, S, seed):
+    """CNN :1464-1556 / SincNet :1559-1665 followed by a softmax MLP head, one SGD step."""
+    torch.manual_seed(seed)
+    prefix = "sinc" if kind == "SincNet" else "cnn"
+    net = getattr(ref_nn, kind)(conv_opts(prefix, n_filt, len_filt, pool, ln, ln_inp, act, drop), L0)
+    head = ref_nn.MLP(mlp_opts([S], 0.0, False, False, "softmax"), net.out_dim)
+    with torch.no_grad():
+        head.wx[0].weight.mul_(10.0)
+        for i in range(len(n_filt)):
+            net.ln[i].gamma.uniform_(0.5, 1.5)
+            net.ln[i].beta.normal_(0, 0.2)
+        if ln_inp:
+            net.ln0.gamma.uniform_(0.5, 1.5)
+            net.ln0.beta.normal_(0, 0.2)
+    mods = [("net.", net), ("head.", head)]
+    out = {}
+    for pfx, m in mods:
+        out.update({"init." + k: v for k, v in sd_np(m, pfx).items()})
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(N, L0, generator=g) * (1.0 + torch.rand(N, 1, generator=g))
+    lab = torch.randint(0, S, (N,), generator=g)
+    net.train(); head.train()
+    keeps = []
+    hooks = [m.register_forward_hook(lambda mod, inp, o: keeps.append(((o != 0) | (inp[0] == 0)).numpy().copy()))
+             for m in net.drop]
+    opts = [torch.optim.SGD(m.parameters(), lr=0.08) for _, m in mods]
+    torch.manual_seed(seed + 2)
+    h = net(x)
+    for hk in hooks:
+        hk.remove()
+    h.retain_grad()
+    logp = head(h)
+    loss = torch.nn.NLLLoss()(logp, lab)
+    err = torch.mean((torch.max(logp, dim=1)[1] != lab).float())
+    for o in opts:
+        o.zero_grad()
+    loss.backward()
+    out.update(x=x.numpy(), lab=lab.numpy(), out=h.detach().numpy(), logp=logp.detach().numpy(),
+               loss=np.float64(loss.item()), err=np.float64(err.item()), dout=h.grad.numpy())
+    if kind == "SincNet":
+        out["filters"] = net.conv[0].filters.detach().numpy().reshape(n_filt[0], -1)
+    for i, k in enumerate(keeps):
+        out[f"keep{i}"] = k
+    for pfx, m in mods:
+        out.update({"grad." + k: v for k, v in grads_np(m, pfx).items()})
+    for o in opts:
+        o.step()
+    for pfx, m in mods:
+        out.update({"step1." + k: v for k, v in sd_np(m, pfx).items() if "running" not in k and "num_batches" not in k})
+    net.eval(); head.eval()
+    with torch.no_grad():
+        out["eval_logp"] = head(net(x)).numpy()
+    meta = dict(kind=kind, N=N, L0=L0, n_filt=n_filt, len_filt=len_filt, pool=pool, ln=ln, ln_inp=ln_inp, act=act,
+                drop=drop, S=S)
+    out["meta"] = np.array(repr(meta))
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: loss={loss.item():.6f} err={err.item():.4f} -> {path} ({os.path.getsize(path)/1e6:.2f} MB)")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     only = sys.argv[1:]  # optional: names of the fixtures to (re)generate
@@ -264,3 +336,13 @@ if __name__ == "__main__":
         if not only or f"{cell}_uni_nobn" in only:
             ligru_case(f"{cell}_uni_nobn", T=9, B=3, D=8, lay=[21], S=11, S2=0, drop=0.1, bn=False,
                        act="tanh", bidir=False, seed=seed + 1, cell=cell)
+    # H: conv front-ends: SincNet :1559-1813 (TIMIT_SincNet_raw.cfg in miniature) and CNN :1464-1556
+    if not only or "sincnet_ln_relu" in only:
+        conv_case("sincnet_ln_relu", kind="SincNet", N=6, L0=400, n_filt=[16, 12, 12], len_filt=[33, 5, 3],
+                  pool=[3, 3, 2], ln=True, ln_inp=True, act="relu", drop=0.15, S=9, seed=71)
+    if not only or "sincnet_tanh_noln" in only:
+        conv_case("sincnet_tanh_noln", kind="SincNet", N=5, L0=300, n_filt=[10, 8], len_filt=[21, 4],
+                  pool=[2, 3], ln=False, ln_inp=False, act="tanh", drop=0.0, S=7, seed=72)
+    if not only or "cnn_ln_relu" in only:
+        conv_case("cnn_ln_relu", kind="CNN", N=7, L0=120, n_filt=[20, 12, 12], len_filt=[10, 3, 3], pool=[3, 2, 1],
+                  ln=True, ln_inp=False, act="leaky_relu", drop=0.15, S=8, seed=73)

@@ -76,6 +76,28 @@ def cell_layers(d, dtype=np.float64, stage="init."):
     return layers
 
 
+def conv_layers(d, dtype=np.float64, stage="init."):
+    """(layers, ln0) for oracle.convnet_forward from a SincNet / CNN fixture (module prefix `net.`)."""
+    m = d["meta"]
+    layers = []
+    for i in range(len(m["n_filt"])):
+        if m["kind"] == "SincNet" and i == 0:
+            k = m["len_filt"][0] + (1 - m["len_filt"][0] % 2)  # SincConv forces odd lengths (:1722-1724)
+            L = dict(kind="sinc", low_hz_=d[f"{stage}net.conv.0.low_hz_"].astype(dtype),
+                     band_hz_=d[f"{stage}net.conv.0.band_hz_"].astype(dtype), k=k)
+        else:
+            L = dict(kind="conv", w=d[f"{stage}net.conv.{i}.weight"].astype(dtype),
+                     b=d[f"{stage}net.conv.{i}.bias"].astype(dtype))
+        L.update(pool=m["pool"][i], act=m["act"], drop=m["drop"], ln=None)
+        if m["ln"]:
+            L["ln"] = dict(gamma=d[f"{stage}net.ln.{i}.gamma"].astype(dtype), beta=d[f"{stage}net.ln.{i}.beta"].astype(dtype))
+        layers.append(L)
+    ln0 = None
+    if m["ln_inp"]:
+        ln0 = dict(gamma=d[f"{stage}net.ln0.gamma"].astype(dtype), beta=d[f"{stage}net.ln0.beta"].astype(dtype))
+    return layers, ln0
+
+
 def head_layer(d, prefix="head", dtype=np.float64, stage="init."):
     return dict(w=d[f"{stage}{prefix}.wx.0.weight"].astype(dtype), b=d[f"{stage}{prefix}.wx.0.bias"].astype(dtype),
                 bn=None, ln=None, act="softmax", drop=0.0)

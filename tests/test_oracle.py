@@ -143,6 +143,54 @@ def test_cell_forward_and_gradients(name):
                 assert gu.relerr(L["bn"][gi]["running_var"], d[f"bnstat.net.bn_{w}.{i}.running_var"]) < TOL
 
 
+CONV_CASES = ["sincnet_ln_relu", "sincnet_tanh_noln", "cnn_ln_relu"]
+
+
+@pytest.mark.parametrize("name", CONV_CASES)
+def test_conv_frontends(name):
+    """CNN :1464-1556 / SincNet :1559-1813 restatement (sinc filter synthesis, conv, max-pool, LayerNorm over the
+    length axis, activation, dropout) against the unmodified reference, incl. every parameter gradient."""
+    d = gu.load(name)
+    m = d["meta"]
+    layers, ln0 = gu.conv_layers(d)
+    keeps = [d[f"keep{i}"] for i in range(len(layers))] if m["drop"] > 0 else None
+    out, caches = orc.convnet_forward(d["x"].astype(np.float64), layers, ln0=ln0, training=True, keeps=keeps)
+    assert gu.relerr(out, d["out"]) < TOL
+    if m["kind"] == "SincNet":
+        filt, _ = orc.sinc_filters(layers[0]["low_hz_"], layers[0]["band_hz_"], layers[0]["k"])
+        assert gu.relerr(filt, d["filters"]) < TOL
+    head = gu.head_layer(d, "head")
+    logp, hc = orc.mlp_forward(out, [head], training=True)
+    lab = d["lab"].astype(np.int64)
+    assert gu.relerr(logp, d["logp"]) < TOL
+    assert abs(orc.nll_loss(logp, lab) - float(d["loss"])) / float(d["loss"]) < 1e-5
+    dx, hg = orc.mlp_backward(orc.nll_loss_bwd(logp, lab), [head], hc)
+    assert gu.relerr(dx, d["dout"]) < 5e-4
+    _, grads, g0 = orc.convnet_backward(dx, layers, caches)
+    for i, g in enumerate(grads):
+        if layers[i]["kind"] == "sinc":
+            gu.check_tensor(d, "grad.net.conv.0.low_hz_", g["low_hz_"], 5e-4)
+            gu.check_tensor(d, "grad.net.conv.0.band_hz_", g["band_hz_"], 5e-4)
+        else:
+            gu.check_tensor(d, f"grad.net.conv.{i}.weight", g["w"], 5e-4)
+            if m["ln"]:
+                # a per-channel bias in front of max-pool + LayerNorm over the length axis cancels: zero gradient
+                assert np.abs(g["b"]).max() < 1e-9 and np.abs(d[f"grad.net.conv.{i}.bias"]).max() < 1e-6
+            else:
+                gu.check_tensor(d, f"grad.net.conv.{i}.bias", g["b"], 5e-4)
+        if m["ln"]:
+            gu.check_tensor(d, f"grad.net.ln.{i}.gamma", g["ln_gamma"], 5e-4)
+            gu.check_tensor(d, f"grad.net.ln.{i}.beta", g["ln_beta"], 5e-4)
+    if m["ln_inp"]:
+        gu.check_tensor(d, "grad.net.ln0.gamma", g0["gamma"], 5e-4)
+        gu.check_tensor(d, "grad.net.ln0.beta", g0["beta"], 5e-4)
+    # eval mode: dropout off
+    layers1, ln01 = gu.conv_layers(d, stage="step1.")
+    out_e, _ = orc.convnet_forward(d["x"].astype(np.float64), layers1, ln0=ln01, training=False)
+    logp_e, _ = orc.mlp_forward(out_e, [gu.head_layer(d, "head", stage="step1.")], training=False)
+    assert gu.relerr(logp_e, d["eval_logp"]) < TOL
+
+
 @pytest.mark.parametrize("name", MLP_CASES)
 def test_mlp(name):
     d = gu.load(name)
