@@ -176,6 +176,51 @@ int pk_rnn_step_bwd(int cell, int T, int B, int H, int ndir, int act, const floa
                     const float* gscale, void* GT16, void* workspace, int64_t workspace_bytes,
                     void* stream);
 
+/* ---- conv front-ends: CNN (neural_networks.py:1464-1556), SincNet (:1559-1665), SincConv (:1668-1813) ----
+ * Activations are position-major fp16 A16[n][l][c] (channel pitch Cp = pad8(C)); a stride-1 valid convolution
+ * is pk_gemm_tn with A = the activation buffer viewed with row pitch Cp and K = k*Cp (overlapping rows), B =
+ * W16 from pk_conv_pack_weights; rows l > L-k of every frame are garbage and ignored by pk_conv_post_fwd. */
+
+/* ln0 = LayerNorm(input_dim) over the sample axis (:1541-1542, :1644-1645; unbiased std, eps added to std):
+ * y [N][L] = gamma (x - mean)/(std + eps) + beta; stats [N][2] = mean, 1/(std+eps). */
+int pk_rowln_fwd(const float* x, int64_t ldx, int N, int L, const float* gamma, const float* beta, float eps,
+                 float* y, float* stats, void* stream);
+/* gradients of ln0's gamma/beta [L] from G [N*L][ldg] = dO16 . Wflip16(viewed [k][Cop])^T (columns in the
+ * flipped tap order of that operand), raw input x and the stats of pk_rowln_fwd. */
+int pk_conv_ln0_bwd(const float* G, int64_t ldg, int N, int L, int Lout, int k, const float* x, int64_t ldx,
+                    const float* stats, float* dgamma, float* dbeta, void* stream);
+/* SincConv filter synthesis (:1777-1803): band-pass = 2 high sinc - 2 low sinc, max-normalised, Hamming
+ * windowed; low_hz_/band_hz_ [C] (the module's parameters), k odd.  filt [C][k] fp32. */
+int pk_sinc_filters_fwd(const float* low_hz_, const float* band_hz_, int C, int k, float sample_rate,
+                        float min_low_hz, float min_band_hz, float* filt, void* stream);
+int pk_sinc_filters_bwd(const float* low_hz_, const float* band_hz_, int C, int k, float sample_rate,
+                        float min_low_hz, float min_band_hz, const float* dfilt, float* dlow, float* dband,
+                        void* stream);
+/* w [Co][Ci][k] fp32 (nn.Conv1d layout) -> W16 [Co][ldw], column kk*Cip + ci (forward operand) and/or
+ * Wflip16 [Ci][ldf], column j*Cop + co holding w[co][ci][k-1-j] (operand of the input gradient).  Either may
+ * be NULL; the caller zero-fills the padding. */
+int pk_conv_pack_weights(const float* w, int Co, int Ci, int k, void* W16, int Cip, int64_t ldw, void* Wflip16,
+                         int Cop, int64_t ldf, void* stream);
+/* first layer (one input channel): explicit fp16 im2col Xcol [N*L][Kp] (rows l >= Lout zero) and its
+ * transpose XcolT [k][ldp] (operand of dW); either may be NULL. */
+int pk_conv_im2col0(const float* x, int64_t ldx, int N, int L, int k, int Lout, void* Xcol, int Kp, void* XcolT,
+                    int64_t ldp, void* stream);
+/* transposed im2col of a position-major activation for dW: XT [kk*Ci + ci][pos] = A16[pos + kk][ci]. */
+int pk_conv_im2col_t(const void* A16, int64_t rows, int Cp, int Ci, int k, void* XT, int64_t ldp, void* stream);
+/* fused layer epilogue drop(act(LN_L(max_pool1d(O)))) (:1547-1553, :1652-1661).  O [N*L][ldo] conv output,
+ * Lout = L-k+1 valid positions per frame, pool p, Lp = Lout/p; gamma/beta [C][Lp] (LayerNorm over the length
+ * axis) or NULL; keep16 [N][Lp][C] = dropout keep/(1-p) or NULL.  Saves P (pooled), arg, stats [N][C][2];
+ * writes the next layer's operand A16n [N*Lp][Cpn] and/or the module output Y32 [N][C][Lp]. */
+int pk_conv_post_fwd(const float* O, int64_t ldo, int N, int L, int Lout, int p, int Lp, int C, int act,
+                     const float* gamma, const float* beta, float eps, const void* keep16, float* P, void* arg,
+                     float* stats, void* A16n, int Cpn, float* Y32, void* stream);
+/* its backward: dY[n*sn + l*sl + c*sc] -> dO [N*L][C] fp32 (zeros outside the arg-max positions), dgamma /
+ * dbeta [C][Lp], dbias [C] (may be NULL), amax of |dO| into amax_bits (may be NULL). */
+int pk_conv_post_bwd(const float* dY, int64_t sn, int64_t sl, int64_t sc, int N, int L, int Lout, int p, int Lp,
+                     int C, int act, const float* gamma, const float* beta, float eps, const void* keep16,
+                     const float* P, const void* arg, const float* stats, float* dgamma, float* dbeta,
+                     float* dbias, float* dO, void* amax_bits, void* stream);
+
 /* In place: logits [N][ld] -> log-posteriors (act_fun("softmax") = LogSoftmax(dim=1),
  * neural_networks.py:53-54).  With labels (int64, utils.py:2348-2352): acc[0] = sum_n
  * -logp[n,lab[n]] (nn.NLLLoss numerator, utils.py:2361), acc[1] = #(argmax != lab)

@@ -189,6 +189,71 @@ int pk_rnn_step_bwd(int cell, int T, int B, int H, int ndir, int act, const floa
   return cell_step_bwd(a, static_cast<cudaStream_t>(stream));
 }
 
+int pk_rowln_fwd(const float* x, int64_t ldx, int N, int L, const float* gamma, const float* beta, float eps, float* y,
+                 float* stats, void* stream) {
+  PK_REQUIRE(x && gamma && beta && y && stats, "pk_rowln_fwd: null pointer");
+  return rowln_fwd(x, ldx, N, L, gamma, beta, eps, y, stats, static_cast<cudaStream_t>(stream));
+}
+int pk_conv_ln0_bwd(const float* G, int64_t ldg, int N, int L, int Lout, int k, const float* x, int64_t ldx,
+                    const float* stats, float* dgamma, float* dbeta, void* stream) {
+  PK_REQUIRE(G && x && stats && dgamma && dbeta, "pk_conv_ln0_bwd: null pointer");
+  return conv_ln0_bwd(G, ldg, N, L, Lout, k, x, ldx, stats, dgamma, dbeta, static_cast<cudaStream_t>(stream));
+}
+int pk_sinc_filters_fwd(const float* low_hz_, const float* band_hz_, int C, int k, float sample_rate, float min_low_hz,
+                        float min_band_hz, float* filt, void* stream) {
+  PK_REQUIRE(low_hz_ && band_hz_ && filt, "pk_sinc_filters_fwd: null pointer");
+  return sinc_filters_fwd(low_hz_, band_hz_, C, k, sample_rate, min_low_hz, min_band_hz, filt,
+                          static_cast<cudaStream_t>(stream));
+}
+int pk_sinc_filters_bwd(const float* low_hz_, const float* band_hz_, int C, int k, float sample_rate, float min_low_hz,
+                        float min_band_hz, const float* dfilt, float* dlow, float* dband, void* stream) {
+  PK_REQUIRE(low_hz_ && band_hz_ && dfilt && dlow && dband, "pk_sinc_filters_bwd: null pointer");
+  return sinc_filters_bwd(low_hz_, band_hz_, C, k, sample_rate, min_low_hz, min_band_hz, dfilt, dlow, dband,
+                          static_cast<cudaStream_t>(stream));
+}
+int pk_conv_pack_weights(const float* w, int Co, int Ci, int k, void* W16, int Cip, int64_t ldw, void* Wflip16, int Cop,
+                         int64_t ldf, void* stream) {
+  return conv_pack_weights(w, Co, Ci, k, static_cast<__half*>(W16), Cip, ldw, static_cast<__half*>(Wflip16), Cop, ldf,
+                           static_cast<cudaStream_t>(stream));
+}
+int pk_conv_im2col0(const float* x, int64_t ldx, int N, int L, int k, int Lout, void* Xcol, int Kp, void* XcolT,
+                    int64_t ldp, void* stream) {
+  PK_REQUIRE(x && (Xcol || XcolT), "pk_conv_im2col0: null pointer");
+  return conv_im2col0(x, ldx, N, L, k, Lout, static_cast<__half*>(Xcol), Kp, static_cast<__half*>(XcolT), ldp,
+                      static_cast<cudaStream_t>(stream));
+}
+int pk_conv_im2col_t(const void* A16, int64_t rows, int Cp, int Ci, int k, void* XT, int64_t ldp, void* stream) {
+  PK_REQUIRE(A16 && XT, "pk_conv_im2col_t: null pointer");
+  return conv_im2colT(static_cast<const __half*>(A16), rows, Cp, Ci, k, static_cast<__half*>(XT), ldp,
+                      static_cast<cudaStream_t>(stream));
+}
+int pk_conv_post_fwd(const float* O, int64_t ldo, int N, int L, int Lout, int p, int Lp, int C, int act,
+                     const float* gamma, const float* beta, float eps, const void* keep16, float* P, void* arg,
+                     float* stats, void* A16n, int Cpn, float* Y32, void* stream) {
+  PK_REQUIRE(O && P && arg && (gamma == nullptr || (beta && stats)), "pk_conv_post_fwd: null pointer");
+  PK_REQUIRE(act >= PK_ACT_RELU && act <= PK_ACT_LINEAR, "pk_conv_post_fwd: bad activation %d", act);
+  ConvPostFwdArgs a;
+  a.O = O; a.ldo = ldo; a.N = N; a.L = L; a.Lout = Lout; a.p = p; a.Lp = Lp; a.C = C; a.act = act;
+  a.gamma = gamma; a.beta = beta; a.eps = eps; a.keep = static_cast<const __half*>(keep16);
+  a.P = P; a.arg = static_cast<uint8_t*>(arg); a.stats = stats;
+  a.A16n = static_cast<__half*>(A16n); a.Cpn = Cpn; a.Y32 = Y32;
+  return conv_post_fwd(a, static_cast<cudaStream_t>(stream));
+}
+int pk_conv_post_bwd(const float* dY, int64_t sn, int64_t sl, int64_t sc, int N, int L, int Lout, int p, int Lp, int C,
+                     int act, const float* gamma, const float* beta, float eps, const void* keep16, const float* P,
+                     const void* arg, const float* stats, float* dgamma, float* dbeta, float* dbias, float* dO,
+                     void* amax_bits, void* stream) {
+  PK_REQUIRE(dY && P && arg && dO && (gamma == nullptr || (beta && stats && dgamma && dbeta)),
+             "pk_conv_post_bwd: null pointer");
+  ConvPostBwdArgs a;
+  a.dY = dY; a.sn = sn; a.sl = sl; a.sc = sc;
+  a.N = N; a.L = L; a.Lout = Lout; a.p = p; a.Lp = Lp; a.C = C; a.act = act;
+  a.gamma = gamma; a.beta = beta; a.eps = eps; a.keep = static_cast<const __half*>(keep16);
+  a.P = P; a.arg = static_cast<const uint8_t*>(arg); a.stats = stats;
+  a.dgamma = dgamma; a.dbeta = dbeta; a.dbias = dbias; a.dO = dO; a.amax_bits = static_cast<unsigned int*>(amax_bits);
+  return conv_post_bwd(a, static_cast<cudaStream_t>(stream));
+}
+
 int pk_logsoftmax_nll(int N, int S, float* logits, int64_t ld, const int64_t* labels, double* acc,
                       void* stream) {
   PK_REQUIRE(logits != nullptr, "pk_logsoftmax_nll: null logits");

@@ -131,6 +131,55 @@ long long cell_step_workspace_bytes(int cell, int T, int B, int H, int ndir, int
 int cell_step_fwd(const CellStepFwdArgs& a, cudaStream_t stream);
 int cell_step_bwd(const CellStepBwdArgs& a, cudaStream_t stream);
 
+// ---- conv front-ends (pk_conv.cu): CNN / SincNet companions of the tcgen05 GEMM ----
+int rowln_fwd(const float* x, long long ldx, int N, int L, const float* gamma, const float* beta, float eps, float* y,
+              float* stats, cudaStream_t stream);
+int conv_ln0_bwd(const float* G, long long ldg, int N, int L, int Lout, int k, const float* x, long long ldx,
+                 const float* stats, float* dgamma, float* dbeta, cudaStream_t stream);
+int sinc_filters_fwd(const float* low_hz_, const float* band_hz_, int C, int k, float sr, float min_low, float min_band,
+                     float* filt, cudaStream_t stream);
+int sinc_filters_bwd(const float* low_hz_, const float* band_hz_, int C, int k, float sr, float min_low, float min_band,
+                     const float* dfilt, float* dlow, float* dband, cudaStream_t stream);
+int conv_pack_weights(const float* w, int Co, int Ci, int k, __half* W16, int Cip, long long ldw, __half* Wf16, int Cop,
+                      long long ldf, cudaStream_t stream);
+int conv_im2col0(const float* x, long long ldx, int N, int L, int k, int Lout, __half* Xcol, int Kp, __half* XcolT,
+                 long long ldp, cudaStream_t stream);
+int conv_im2colT(const __half* A16, long long rows, int Cp, int Ci, int k, __half* XT, long long ldp, cudaStream_t stream);
+struct ConvPostFwdArgs {
+  const float* O = nullptr;  // [N*L][ldo] conv output (+bias), position-major
+  long long ldo = 0;
+  int N = 0, L = 0, Lout = 0, p = 1, Lp = 0, C = 0, act = 0;
+  const float* gamma = nullptr;  // [C][Lp] LayerNorm affine, or null (no normalisation)
+  const float* beta = nullptr;
+  float eps = 1e-6f;
+  const __half* keep = nullptr;  // [N][Lp][C] dropout keep * 1/(1-p), or null
+  float* P = nullptr;            // [N][Lp][C] pooled values (saved)
+  uint8_t* arg = nullptr;        // [N][Lp][C] arg-max inside the pooling window (saved)
+  float* stats = nullptr;        // [N][C][2] mean, 1/(std+eps) (saved)
+  __half* A16n = nullptr;        // [N*Lp (+tail)][Cpn] next layer's fp16 operand, or null
+  int Cpn = 0;
+  float* Y32 = nullptr;          // [N][C][Lp] module output (last layer), or null
+};
+int conv_post_fwd(const ConvPostFwdArgs& a, cudaStream_t stream);
+struct ConvPostBwdArgs {
+  const float* dY = nullptr;  // dY[n*sn + l*sl + c*sc]
+  long long sn = 0, sl = 0, sc = 0;
+  int N = 0, L = 0, Lout = 0, p = 1, Lp = 0, C = 0, act = 0;
+  const float* gamma = nullptr;
+  const float* beta = nullptr;
+  float eps = 1e-6f;
+  const __half* keep = nullptr;
+  const float* P = nullptr;
+  const uint8_t* arg = nullptr;
+  const float* stats = nullptr;
+  float* dgamma = nullptr;  // [C][Lp]
+  float* dbeta = nullptr;
+  float* dbias = nullptr;   // [C] or null
+  float* dO = nullptr;      // [N*L][C] gradient w.r.t. the conv output (zeros outside the arg-max positions)
+  unsigned int* amax_bits = nullptr;
+};
+int conv_post_bwd(const ConvPostBwdArgs& a, cudaStream_t stream);
+
 // ---- memory-bound helpers (pk_elementwise.cu) ----
 // out[c][r] = in[r][c]; optional fp16 copies. in is [R][ldi] fp32.
 int transpose_f32(const float* in, long long ldi, int R, int C, float* outT, long long ldo,

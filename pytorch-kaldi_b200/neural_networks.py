@@ -18,6 +18,8 @@ RuntimeError.
 """
 from __future__ import annotations
 
+import math
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -287,8 +289,151 @@ def _not_built(name, why):
 LSTM_cudnn = _not_built("LSTM_cudnn", "cuDNN RNNs are out of scope; use arch_class = LSTM")
 GRU_cudnn = _not_built("GRU_cudnn", "cuDNN RNNs are out of scope; use arch_class = GRU")
 RNN_cudnn = _not_built("RNN_cudnn", "cuDNN RNNs are out of scope; use arch_class = RNN")
-# convolutional front-ends (neural_networks.py:1464-1959): next rows of the scope table
-CNN = _not_built("CNN", "conv1d front-end kernels are not built yet")
-SincNet = _not_built("SincNet", "sinc-conv front-end kernels are not built yet")
-SincConv = _not_built("SincConv", "sinc-conv front-end kernels are not built yet")
-SincConv_fast = _not_built("SincConv_fast", "sinc-conv front-end kernels are not built yet")
+# ---------------------------------------------------------------------------------------------
+# convolutional front-ends: CNN :1464-1556, SincNet :1559-1665, SincConv :1668-1813
+# ---------------------------------------------------------------------------------------------
+
+
+class SincConv(nn.Module):
+    """Band-pass filterbank layer parametrised by (low_hz_, band_hz_) — reference :1668-1813.  Same constructor,
+    parameters and derived constants; the filters are synthesised and applied by the native path."""
+
+    @staticmethod
+    def to_mel(hz):
+        return 2595 * np.log10(1 + hz / 700)
+
+    @staticmethod
+    def to_hz(mel):
+        return 700 * (10 ** (mel / 2595) - 1)
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, bias=False, groups=1,
+                 sample_rate=16000, min_low_hz=50, min_band_hz=50):
+        super().__init__()
+        if in_channels != 1:
+            raise ValueError("SincConv only support one input channel (here, in_channels = {%i})" % (in_channels))
+        if bias:
+            raise ValueError("SincConv does not support bias.")
+        if groups > 1:
+            raise ValueError("SincConv does not support groups.")
+        self.out_channels = out_channels
+        self.kernel_size = kernel_size + (1 - kernel_size % 2)  # odd length -> symmetric filters (:1722-1724)
+        self.stride, self.padding, self.dilation = stride, padding, dilation
+        self.sample_rate, self.min_low_hz, self.min_band_hz = sample_rate, min_low_hz, min_band_hz
+        # mel-spaced initial band edges, normalised by the sample rate (:1740-1750)
+        hi = self.sample_rate / 2 - (self.min_low_hz + self.min_band_hz)
+        hz = self.to_hz(np.linspace(self.to_mel(30), self.to_mel(hi), self.out_channels + 1)) / self.sample_rate
+        self.low_hz_ = nn.Parameter(torch.Tensor(hz[:-1]).view(-1, 1))
+        self.band_hz_ = nn.Parameter(torch.Tensor(np.diff(hz)).view(-1, 1))
+        n_lin = torch.linspace(0, self.kernel_size, steps=self.kernel_size)
+        self.window_ = 0.54 - 0.46 * torch.cos(2 * math.pi * n_lin / self.kernel_size)
+        n = (self.kernel_size - 1) / 2
+        self.n_ = torch.arange(-n, n + 1).view(1, -1) / self.sample_rate
+
+    def forward(self, waveforms):
+        """waveforms [N, 1, n_samples] -> [N, out_channels, n_samples - kernel_size + 1]"""
+        _require_cuda(waveforms, "SincConv")
+        if (self.stride, self.padding, self.dilation) != (1, 0, 1) or waveforms.shape[1] != 1:
+            raise NotImplementedError("pytorch-kaldi_b200.SincConv: only stride 1 / no padding / no dilation (what "
+                                      "SincNet uses) is implemented natively")
+        cfg = pkf.ConvStackCfg(flat_output=False)
+        cfg.layers.append(pkf.ConvLayerCfg(kind="sinc", C=self.out_channels, k=self.kernel_size, pool=1,
+                                           act=pk.ACT_IDS["linear"], use_ln=False, sample_rate=self.sample_rate,
+                                           min_low_hz=self.min_low_hz, min_band_hz=self.min_band_hz))
+        return pkf.ConvStackFn.apply(waveforms[:, 0, :], cfg, self.low_hz_, self.band_hz_)
+
+
+class SincConv_fast(nn.Module):
+    """Reference :1816-1959 (Hz-domain parametrisation, half-window evaluation).  No module of the zoo
+    instantiates it (SincNet uses SincConv, :1619-1628); constructor parity only."""
+
+    to_mel = SincConv.to_mel
+    to_hz = SincConv.to_hz
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, bias=False, groups=1,
+                 sample_rate=16000, min_low_hz=50, min_band_hz=50):
+        super().__init__()
+        if in_channels != 1:
+            raise ValueError("SincConv only support one input channel (here, in_channels = {%i})" % (in_channels))
+        if bias:
+            raise ValueError("SincConv does not support bias.")
+        if groups > 1:
+            raise ValueError("SincConv does not support groups.")
+        self.out_channels = out_channels
+        self.kernel_size = kernel_size + (1 - kernel_size % 2)
+        self.stride, self.padding, self.dilation = stride, padding, dilation
+        self.sample_rate, self.min_low_hz, self.min_band_hz = sample_rate, min_low_hz, min_band_hz
+        hi = self.sample_rate / 2 - (self.min_low_hz + self.min_band_hz)
+        hz = self.to_hz(np.linspace(self.to_mel(30), self.to_mel(hi), self.out_channels + 1))
+        self.low_hz_ = nn.Parameter(torch.Tensor(hz[:-1]).view(-1, 1))
+        self.band_hz_ = nn.Parameter(torch.Tensor(np.diff(hz)).view(-1, 1))
+        n_lin = torch.linspace(0, (self.kernel_size / 2) - 1, steps=int((self.kernel_size / 2)))
+        self.window_ = 0.54 - 0.46 * torch.cos(2 * math.pi * n_lin / self.kernel_size)
+        n = (self.kernel_size - 1) / 2.0
+        self.n_ = 2 * math.pi * torch.arange(-n, 0).view(1, -1) / self.sample_rate
+
+    def forward(self, waveforms):
+        raise NotImplementedError("pytorch-kaldi_b200.SincConv_fast: not used by any reference module; use SincConv")
+
+
+class _ConvFrontEnd(nn.Module):
+    """Shared constructor of CNN (:1465-1528) and SincNet (:1560-1636): per layer Dropout, activation, LayerNorm
+    over [N_filt, L_pooled], BatchNorm1d (constructed exactly like the reference does — its second positional
+    argument lands in `eps`), and the convolution (a SincConv for SincNet's first layer)."""
+
+    _PREFIX = ""
+    _SINC = False
+
+    def __init__(self, options, inp_dim):
+        super().__init__()
+        p = self._PREFIX
+        self.input_dim = inp_dim
+        vals = dict(N_filt=_ints(options[p + "_N_filt"]), len_filt=_ints(options[p + "_len_filt"]),
+                    max_pool_len=_ints(options[p + "_max_pool_len"]), act=str(options[p + "_act"]).split(","),
+                    drop=_floats(options[p + "_drop"]), use_laynorm=_bools(options[p + "_use_laynorm"]),
+                    use_batchnorm=_bools(options[p + "_use_batchnorm"]),
+                    use_laynorm_inp=strtobool(options[p + "_use_laynorm_inp"]),
+                    use_batchnorm_inp=strtobool(options[p + "_use_batchnorm_inp"]))
+        for k, v in vals.items():
+            setattr(self, f"{p}_{k}", v)
+        n_lay = len(vals["N_filt"])
+        setattr(self, f"N_{p}_lay", n_lay)
+        if self._SINC:
+            self.sinc_sample_rate = int(options["sinc_sample_rate"])
+            self.sinc_min_low_hz = int(options["sinc_min_low_hz"])
+            self.sinc_min_band_hz = int(options["sinc_min_band_hz"])
+        self.conv = nn.ModuleList([])
+        self.bn = nn.ModuleList([])
+        self.ln = nn.ModuleList([])
+        self.act = nn.ModuleList([])
+        self.drop = nn.ModuleList([])
+        if vals["use_laynorm_inp"]:
+            self.ln0 = LayerNorm(self.input_dim)
+        if vals["use_batchnorm_inp"]:
+            self.bn0 = nn.BatchNorm1d([self.input_dim], momentum=0.05)
+        cur = self.input_dim
+        for i in range(n_lay):
+            n_filt, len_filt, pool = vals["N_filt"][i], vals["len_filt"][i], vals["max_pool_len"][i]
+            pooled = int((cur - len_filt + 1) / pool)
+            self.drop.append(nn.Dropout(p=vals["drop"][i]))
+            self.act.append(act_fun(vals["act"][i]))
+            self.ln.append(LayerNorm([n_filt, pooled]))
+            self.bn.append(nn.BatchNorm1d(n_filt, pooled, momentum=0.05))
+            if i == 0 and self._SINC:
+                self.conv.append(SincConv(1, n_filt, len_filt, sample_rate=self.sinc_sample_rate,
+                                          min_low_hz=self.sinc_min_low_hz, min_band_hz=self.sinc_min_band_hz))
+            else:
+                self.conv.append(nn.Conv1d(1 if i == 0 else vals["N_filt"][i - 1], n_filt, len_filt))
+            cur = pooled
+        self.out_dim = cur * n_filt
+
+    def forward(self, x):
+        _require_cuda(x, type(self).__name__)
+        return pkf.conv_forward(self, x, self._PREFIX)
+
+
+class CNN(_ConvFrontEnd):
+    _PREFIX, _SINC = "cnn", False
+
+
+class SincNet(_ConvFrontEnd):
+    _PREFIX, _SINC = "sinc", True

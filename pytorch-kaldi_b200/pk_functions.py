@@ -561,3 +561,249 @@ def mlp_forward(module, x):
         if use_bn:
             params += [module.bn[i].weight, module.bn[i].bias]
     return MLPStackFn.apply(x, layers, *params)
+
+
+# ---------------------------------------------------------------------------------------------
+# conv front-ends: CNN (neural_networks.py:1464-1556), SincNet (:1559-1665), SincConv (:1668-1813)
+# ---------------------------------------------------------------------------------------------
+
+
+@dataclass
+class ConvLayerCfg:
+    kind: str                  # "sinc" (band-pass filters synthesised from low_hz_/band_hz_) or "conv"
+    C: int                     # output channels
+    k: int                     # taps
+    pool: int                  # max_pool1d length
+    act: int
+    use_ln: bool               # LayerNorm over the length axis with a [C, Lp] affine (:1505-1507)
+    ln_eps: float = 1e-6
+    keep16: Optional[torch.Tensor] = None   # [N, Lp, C] fp16: 0 or 1/(1-p) (training dropout) or None
+    sample_rate: float = 16000.0
+    min_low_hz: float = 50.0
+    min_band_hz: float = 50.0
+
+
+@dataclass
+class ConvStackCfg:
+    layers: List[ConvLayerCfg] = field(default_factory=list)
+    ln0: bool = False
+    ln0_eps: float = 1e-6
+    flat_output: bool = True   # CNN/SincNet return x.view(batch, -1); a bare SincConv returns [N, C, Lout]
+
+
+class ConvStackFn(torch.autograd.Function):
+    """`drop(act(ln(max_pool1d(conv(x)))))` stacks.  Activations are position-major fp16 `[n][l][c]`; every
+    convolution (and its input gradient) is ONE tcgen05 GEMM over an overlapping-row view of the activation
+    buffer (csrc/pk_conv.cu), the first layer (one input channel) uses an explicit fp16 im2col."""
+
+    @staticmethod
+    def forward(ctx, x, cfg: ConvStackCfg, *params):
+        if not x.is_cuda:
+            raise RuntimeError("pytorch-kaldi_b200: CNN/SincNet need CUDA tensors (there is no CPU fallback)")
+        dev = x.device
+        N, L0 = x.shape
+        f32 = dict(device=dev, dtype=torch.float32)
+        f16 = dict(device=dev, dtype=torch.float16)
+        need_grad = any(ctx.needs_input_grad)
+        xr = x if (x.dtype == torch.float32 and x.stride(1) == 1) else x.float().contiguous()
+        pi = 0
+        ln0_saved = None
+        X0, ldx0 = xr, xr.stride(0)
+        if cfg.ln0:
+            g0, b0 = params[0], params[1]
+            pi = 2
+            X0 = torch.empty(N, L0, **f32)
+            st0 = torch.empty(N, 2, **f32)
+            pk.rowln_fwd(xr, xr.stride(0), N, L0, g0, b0, cfg.ln0_eps, X0, st0)
+            ldx0 = L0
+            ln0_saved = (xr, st0)
+        saved = []
+        L, Ci, Cp = L0, 1, 1
+        A16 = None
+        y32 = None
+        nl = len(cfg.layers)
+        for li, Lc in enumerate(cfg.layers):
+            C, k, p = Lc.C, Lc.k, Lc.pool
+            Lout = L - k + 1
+            Lp = Lout // p
+            if Lout < 1 or Lp < 1:
+                raise ValueError(f"conv layer {li}: input length {L} too short for kernel {k} / pool {p}")
+            rows = N * L
+            if Lc.kind == "sinc":
+                low, band = params[pi], params[pi + 1]
+                pi += 2
+                w = torch.empty(C, 1, k, **f32)
+                pk.sinc_filters_fwd(low, band, C, k, Lc.sample_rate, Lc.min_low_hz, Lc.min_band_hz, w)
+                bias = None
+            else:
+                w, bias = params[pi].contiguous(), params[pi + 1]
+                pi += 2
+            gamma = beta = None
+            if Lc.use_ln:
+                gamma, beta = params[pi].contiguous(), params[pi + 1].contiguous()
+                pi += 2
+            O = torch.empty(rows, C, **f32)
+            XcolT = None
+            if li == 0:
+                Kp = pad8(k)
+                Xcol = torch.empty(rows, Kp, **f16)
+                ldp = pad8(rows)
+                XcolT = torch.empty(k, ldp, **f16) if need_grad else None
+                pk.conv_im2col0(X0, ldx0, N, L, k, Lout, Xcol, Kp, XcolT, ldp)
+                W16 = torch.zeros(C, Kp, **f16)
+                pk.conv_pack_weights(w, C, 1, k, W16, 1, Kp, None, 0, 0)
+                pk.gemm_tn(Xcol, W16, O, rows, C, Kp, lda=Kp, ldb=Kp, ldc=C, bias=bias, bias_mode=1)
+            else:
+                K = k * Cp
+                W16 = torch.zeros(C, K, **f16)
+                pk.conv_pack_weights(w, C, Ci, k, W16, Cp, K, None, 0, 0)
+                pk.gemm_tn(A16, W16, O, rows, C, K, lda=Cp, ldb=K, ldc=C, bias=bias, bias_mode=1)
+            last = li == nl - 1
+            P = torch.empty(N, Lp, C, **f32)
+            arg = torch.empty(N, Lp, C, device=dev, dtype=torch.uint8)
+            stats = torch.empty(N, C, 2, **f32) if Lc.use_ln else None
+            A16n, Cpn = None, 0
+            if not last:
+                Cpn = pad8(C)
+                # tail rows: the next layer's overlapping im2col rows of the last frame read past the end
+                A16n = torch.zeros(N * Lp + cfg.layers[li + 1].k, Cpn, **f16)
+            else:
+                y32 = torch.empty(N, C, Lp, **f32)
+            pk.conv_post_fwd(O, C, N, L, Lout, p, Lp, C, Lc.act, gamma, beta, Lc.ln_eps, Lc.keep16, P, arg, stats, A16n,
+                             Cpn, y32)
+            if need_grad:
+                saved.append(dict(cfg=Lc, L=L, Lout=Lout, Lp=Lp, Ci=Ci, Cp=Cp, A16=A16, XcolT=XcolT, w=w, gamma=gamma,
+                                  beta=beta, P=P, arg=arg, stats=stats,
+                                  low=low if Lc.kind == "sinc" else None, band=band if Lc.kind == "sinc" else None))
+            A16, L, Ci, Cp = A16n, Lp, C, Cpn
+        ctx.cfg, ctx.saved, ctx.ln0_saved, ctx.N, ctx.L0 = cfg, saved, ln0_saved, N, L0
+        return y32.view(N, -1) if cfg.flat_output else y32
+
+    @staticmethod
+    def backward(ctx, dY):
+        cfg, saved, N, L0 = ctx.cfg, ctx.saved, ctx.N, ctx.L0
+        dev = dY.device
+        f32 = dict(device=dev, dtype=torch.float32)
+        f16 = dict(device=dev, dtype=torch.float16)
+        amax_acc = torch.zeros(1, device=dev, dtype=torch.int32)
+        grads_rev = []
+        g0 = []
+        dA = None
+        for li in reversed(range(len(saved))):
+            S = saved[li]
+            Lc = S["cfg"]
+            C, k, p, L, Lout, Lp, Ci = Lc.C, Lc.k, Lc.pool, S["L"], S["Lout"], S["Lp"], S["Ci"]
+            rows = N * L
+            if dA is None:  # module output gradient, [N, C, Lp] order
+                dy = dY.reshape(N, C, Lp)
+                if dy.dtype != torch.float32 or not dy.is_contiguous():
+                    dy = dy.float().contiguous()
+                sn, sl, sc_ = C * Lp, 1, Lp
+            else:           # dX of the next layer: position-major [N*Lp, C]
+                dy, sn, sl, sc_ = dA, Lp * C, C, 1
+            dO = torch.empty(rows, C, **f32)
+            dgamma = torch.empty(C, Lp, **f32) if Lc.use_ln else None
+            dbeta = torch.empty(C, Lp, **f32) if Lc.use_ln else None
+            dbias = torch.empty(C, **f32) if Lc.kind == "conv" else None
+            pk.conv_post_bwd(dy, sn, sl, sc_, N, L, Lout, p, Lp, C, Lc.act, S["gamma"], S["beta"], Lc.ln_eps, Lc.keep16,
+                             S["P"], S["arg"], S["stats"], dgamma, dbeta, dbias, dO, amax_acc)
+            sc = torch.empty(2, **f32)
+            pk.amax_finalize(amax_acc, 8.0, sc)
+            inv = sc[1:2]
+            Cop = pad8(C)
+            ldp = pad8(rows)
+            dO16 = torch.zeros(k - 1 + rows, Cop, **f16)   # k-1 zero rows in front: the dX GEMM reads positions r-k+1..r
+            dOT16 = torch.empty(C, ldp, **f16)
+            pk.transpose_f32(dO, C, rows, C, outT16=dOT16, ldo16=ldp, in16=dO16[k - 1:], ldi16=Cop, scale_dev=sc)
+            need_dx = li > 0
+            if li == 0:
+                dF = torch.empty(C, k, **f32)
+                pk.gemm_tn(dOT16, S["XcolT"], dF, C, k, rows, lda=ldp, ldb=ldp, ldc=k, alpha_dev=inv, split_k=8)
+                if Lc.kind == "sinc":
+                    dlow = torch.empty(C, 1, **f32)
+                    dband = torch.empty(C, 1, **f32)
+                    pk.sinc_filters_bwd(S["low"], S["band"], C, k, Lc.sample_rate, Lc.min_low_hz, Lc.min_band_hz, dF, dlow,
+                                        dband)
+                    lg = [dlow, dband]
+                else:
+                    lg = [dF.view(C, 1, k), dbias]
+                if cfg.ln0:
+                    Wf = torch.zeros(1, k * Cop, **f16)
+                    pk.conv_pack_weights(S["w"], C, 1, k, None, 0, 0, Wf, Cop, k * Cop)
+                    G = torch.empty(rows, k, **f32)
+                    pk.gemm_tn(dO16[k - 1:], Wf, G, rows, k, Cop, lda=Cop, ldb=Cop, ldc=k, alpha_dev=inv)
+                    xraw, st0 = ctx.ln0_saved
+                    dg0 = torch.empty(L0, **f32)
+                    db0 = torch.empty(L0, **f32)
+                    pk.conv_ln0_bwd(G, k, N, L0, Lout, k, xraw, xraw.stride(0), st0, dg0, db0)
+                    g0 = [dg0, db0]
+            else:
+                Cp = S["Cp"]
+                XT = torch.empty(k * Ci, ldp, **f16)
+                pk.conv_im2col_t(S["A16"], rows, Cp, Ci, k, XT, ldp)
+                dWk = torch.empty(C, k * Ci, **f32)
+                pk.gemm_tn(dOT16, XT, dWk, C, k * Ci, rows, lda=ldp, ldb=ldp, ldc=k * Ci, alpha_dev=inv, split_k=8)
+                lg = [dWk.view(C, k, Ci).permute(0, 2, 1).contiguous(), dbias]
+            if Lc.use_ln:
+                lg += [dgamma, dbeta]
+            grads_rev.append(lg)
+            if need_dx:
+                Wf = torch.zeros(Ci, k * Cop, **f16)
+                pk.conv_pack_weights(S["w"], C, Ci, k, None, 0, 0, Wf, Cop, k * Cop)
+                dA = torch.empty(rows, Ci, **f32)
+                pk.gemm_tn(dO16, Wf, dA, rows, Ci, k * Cop, lda=Cop, ldb=k * Cop, ldc=Ci, alpha_dev=inv)
+        grads = list(g0)
+        for lg in reversed(grads_rev):
+            grads += lg
+        ctx.saved = None
+        return (None, None, *grads)
+
+
+def conv_forward(module, x, prefix):
+    """CNN.forward / SincNet.forward (neural_networks.py:1530-1556, :1638-1665): builds the static description
+    and calls ConvStackFn.  `prefix` = "cnn" or "sinc" (option-name prefix of the reference class)."""
+    g = lambda name: getattr(module, f"{prefix}_{name}")
+    if g("use_batchnorm_inp") or any(g("use_batchnorm")):
+        raise NotImplementedError(
+            f"pytorch-kaldi_b200.{type(module).__name__}: {prefix}_use_batchnorm / {prefix}_use_batchnorm_inp are not "
+            "implemented natively yet (the shipped CNN / SincNet recipes use LayerNorm); there is no eager fallback")
+    N, L0 = x.shape
+    cfg = ConvStackCfg(ln0=bool(g("use_laynorm_inp")))
+    params = []
+    if cfg.ln0:
+        cfg.ln0_eps = module.ln0.eps
+        params += [module.ln0.gamma, module.ln0.beta]
+    L = L0
+    n_lay = len(g("N_filt"))
+    for i in range(n_lay):
+        conv = module.conv[i]
+        sinc = hasattr(conv, "low_hz_")
+        k = conv.kernel_size if sinc else conv.kernel_size[0]
+        C = conv.out_channels
+        pool = g("max_pool_len")[i]
+        Lp = (L - k + 1) // pool
+        pdrop = g("drop")[i]
+        keep16 = None
+        if module.training and pdrop > 0.0:
+            override = getattr(module, "_keep_override", None)
+            if override is not None and override[i] is not None:   # tests: the reference's own mask, [N, C, Lp]
+                keep16 = (override[i].to(x.device).permute(0, 2, 1).float() / (1.0 - pdrop)).half().contiguous()
+            else:
+                keep16 = torch.empty(N, Lp, C, device=x.device, dtype=torch.float16).bernoulli_(1.0 - pdrop)
+                keep16.mul_(1.0 / (1.0 - pdrop))
+        use_ln = bool(g("use_laynorm")[i])
+        act_name = g("act")[i]
+        if act_name not in pk.ACT_IDS:
+            raise NotImplementedError(f"activation {act_name!r} is not valid inside a conv layer")
+        lc = ConvLayerCfg(kind="sinc" if sinc else "conv", C=C, k=k, pool=pool, act=pk.ACT_IDS[act_name], use_ln=use_ln,
+                          ln_eps=module.ln[i].eps, keep16=keep16)
+        if sinc:
+            lc.sample_rate, lc.min_low_hz, lc.min_band_hz = conv.sample_rate, conv.min_low_hz, conv.min_band_hz
+            params += [conv.low_hz_, conv.band_hz_]
+        else:
+            params += [conv.weight, conv.bias]
+        if use_ln:
+            params += [module.ln[i].gamma, module.ln[i].beta]
+        cfg.layers.append(lc)
+        L = Lp
+    return ConvStackFn.apply(x, cfg, *params)

@@ -44,6 +44,15 @@ SIGNATURES = {
                                        _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_i64, _c_p, _c_i64, _c_p],
     "pk_rnn_step_bwd": [_c_int] * 6 + [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_i64, _c_p, _c_p, _c_f, _c_p, _c_p,
                                        _c_p, _c_i64, _c_p],
+    "pk_rowln_fwd": [_c_p, _c_i64, _c_int, _c_int, _c_p, _c_p, _c_f, _c_p, _c_p, _c_p],
+    "pk_conv_ln0_bwd": [_c_p, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_p, _c_i64, _c_p, _c_p, _c_p, _c_p],
+    "pk_sinc_filters_fwd": [_c_p, _c_p, _c_int, _c_int, _c_f, _c_f, _c_f, _c_p, _c_p],
+    "pk_sinc_filters_bwd": [_c_p, _c_p, _c_int, _c_int, _c_f, _c_f, _c_f, _c_p, _c_p, _c_p, _c_p],
+    "pk_conv_pack_weights": [_c_p, _c_int, _c_int, _c_int, _c_p, _c_int, _c_i64, _c_p, _c_int, _c_i64, _c_p],
+    "pk_conv_im2col0": [_c_p, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_p, _c_int, _c_p, _c_i64, _c_p],
+    "pk_conv_im2col_t": [_c_p, _c_i64, _c_int, _c_int, _c_int, _c_p, _c_i64, _c_p],
+    "pk_conv_post_fwd": [_c_p, _c_i64] + [_c_int] * 7 + [_c_p, _c_p, _c_f, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p, _c_p],
+    "pk_conv_post_bwd": [_c_p, _c_i64, _c_i64, _c_i64] + [_c_int] * 7 + [_c_p, _c_p, _c_f] + [_c_p] * 10,
     "pk_logsoftmax_nll": [_c_int, _c_int, _c_p, _c_i64, _c_p, _c_p, _c_p],
     "pk_logsoftmax_bwd": [_c_int, _c_int, _c_p, _c_i64, _c_p, _c_p, _c_i64, _c_f, _c_f, _c_p, _c_p, _c_i64, _c_p,
                           _c_i64, _c_p, _c_p, _c_p],
@@ -83,7 +92,9 @@ def lib():
 launch_count = 0
 KERNELS_PER_CALL = {"pk_dense_act_fwd": 1, "pk_dense_act_bwd": 1, "pk_amax_finalize": 1, "pk_gemm_tn": 1, "pk_transpose_f32": 1, "pk_convert_f16": 1, "pk_amax_scale": 2,
                     "pk_bn_finalize": 1, "pk_fill_scale_shift": 1, "pk_bn_bwd": 2, "pk_rnn_layer_fwd": 1,
-                    "pk_rnn_layer_bwd": 1, "pk_rnn_step_fwd": 1, "pk_rnn_step_bwd": 1, "pk_logsoftmax_nll": 1, "pk_logsoftmax_bwd": 1, "pk_rmsprop_step": 1,
+                    "pk_rnn_layer_bwd": 1, "pk_rnn_step_fwd": 1, "pk_rnn_step_bwd": 1, "pk_rowln_fwd": 1, "pk_conv_ln0_bwd": 1,
+                    "pk_sinc_filters_fwd": 1, "pk_sinc_filters_bwd": 1, "pk_conv_pack_weights": 1, "pk_conv_im2col0": 1,
+                    "pk_conv_im2col_t": 1, "pk_conv_post_fwd": 1, "pk_conv_post_bwd": 1, "pk_logsoftmax_nll": 1, "pk_logsoftmax_bwd": 1, "pk_rmsprop_step": 1,
                     "pk_sgd_step": 1}
 
 
@@ -192,6 +203,53 @@ def rnn_step_bwd(cell, T, B, H, ndir, act, dYT, HT, SV, ldt, U, mask, mask_scala
                                  _ptr(mask), float(mask_scalar), _ptr(gscale), _ptr(GT16), _ptr(workspace),
                                  workspace.numel(), _stream()), "pk_rnn_step_bwd",
            (2 * T + 1) if (cell & 0xff) in (CELL_GRU, CELL_MGRU) else T)
+
+
+def rowln_fwd(x, ldx, N, L, gamma, beta, eps, y, stats):
+    _check(lib().pk_rowln_fwd(_ptr(x), ldx, N, L, _ptr(gamma), _ptr(beta), float(eps), _ptr(y), _ptr(stats), _stream()),
+           "pk_rowln_fwd")
+
+
+def conv_ln0_bwd(G, ldg, N, L, Lout, k, x, ldx, stats, dgamma, dbeta):
+    _check(lib().pk_conv_ln0_bwd(_ptr(G), ldg, N, L, Lout, k, _ptr(x), ldx, _ptr(stats), _ptr(dgamma), _ptr(dbeta),
+                                 _stream()), "pk_conv_ln0_bwd")
+
+
+def sinc_filters_fwd(low, band, C, k, sr, min_low, min_band, filt):
+    _check(lib().pk_sinc_filters_fwd(_ptr(low), _ptr(band), C, k, float(sr), float(min_low), float(min_band), _ptr(filt),
+                                     _stream()), "pk_sinc_filters_fwd")
+
+
+def sinc_filters_bwd(low, band, C, k, sr, min_low, min_band, dfilt, dlow, dband):
+    _check(lib().pk_sinc_filters_bwd(_ptr(low), _ptr(band), C, k, float(sr), float(min_low), float(min_band), _ptr(dfilt),
+                                     _ptr(dlow), _ptr(dband), _stream()), "pk_sinc_filters_bwd")
+
+
+def conv_pack_weights(w, Co, Ci, k, W16, Cip, ldw, Wflip16, Cop, ldf):
+    _check(lib().pk_conv_pack_weights(_ptr(w), Co, Ci, k, _ptr(W16), Cip, ldw, _ptr(Wflip16), Cop, ldf, _stream()),
+           "pk_conv_pack_weights")
+
+
+def conv_im2col0(x, ldx, N, L, k, Lout, Xcol, Kp, XcolT, ldp):
+    _check(lib().pk_conv_im2col0(_ptr(x), ldx, N, L, k, Lout, _ptr(Xcol), Kp, _ptr(XcolT), ldp, _stream()),
+           "pk_conv_im2col0")
+
+
+def conv_im2col_t(A16, rows, Cp, Ci, k, XT, ldp):
+    _check(lib().pk_conv_im2col_t(_ptr(A16), rows, Cp, Ci, k, _ptr(XT), ldp, _stream()), "pk_conv_im2col_t")
+
+
+def conv_post_fwd(O, ldo, N, L, Lout, p, Lp, C, act, gamma, beta, eps, keep16, P, arg, stats, A16n, Cpn, Y32):
+    _check(lib().pk_conv_post_fwd(_ptr(O), ldo, N, L, Lout, p, Lp, C, act, _ptr(gamma), _ptr(beta), float(eps),
+                                  _ptr(keep16), _ptr(P), _ptr(arg), _ptr(stats), _ptr(A16n), Cpn, _ptr(Y32), _stream()),
+           "pk_conv_post_fwd")
+
+
+def conv_post_bwd(dY, sn, sl, sc, N, L, Lout, p, Lp, C, act, gamma, beta, eps, keep16, P, arg, stats, dgamma, dbeta, dbias,
+                  dO, amax_bits):
+    _check(lib().pk_conv_post_bwd(_ptr(dY), sn, sl, sc, N, L, Lout, p, Lp, C, act, _ptr(gamma), _ptr(beta), float(eps),
+                                  _ptr(keep16), _ptr(P), _ptr(arg), _ptr(stats), _ptr(dgamma), _ptr(dbeta), _ptr(dbias),
+                                  _ptr(dO), _ptr(amax_bits), _stream()), "pk_conv_post_bwd")
 
 
 def logsoftmax_nll(N, S, logits, ld, labels, acc):

@@ -24,6 +24,18 @@ def mlp(lay, drop, bn, ln, act, ln_inp=False, bn_inp=False):
     }
 
 
+def conv(prefix, n_filt, len_filt, pool, ln=True, ln_inp=False, act="relu", drop=0.15):
+    n = len(n_filt)
+    j = lambda v: ",".join(map(str, v))
+    o = {f"{prefix}_N_filt": j(n_filt), f"{prefix}_len_filt": j(len_filt), f"{prefix}_max_pool_len": j(pool),
+         f"{prefix}_use_laynorm_inp": str(ln_inp), f"{prefix}_use_batchnorm_inp": "False",
+         f"{prefix}_use_laynorm": j([ln] * n), f"{prefix}_use_batchnorm": j([False] * n), f"{prefix}_act": j([act] * n),
+         f"{prefix}_drop": j([drop] * n), "use_cuda": "False", "to_do": "train", "arch_name": "z"}
+    if prefix == "sinc":
+        o.update(sinc_sample_rate="16000", sinc_min_low_hz="50", sinc_min_band_hz="50")
+    return o
+
+
 CASES = {
     # the shapes of the shipped recipes (cfg/TIMIT_baselines/*.cfg, cfg/Librispeech_baselines/*.cfg), scaled down
     "ligru_timit": ("liGRU", rec("ligru", [55, 55, 55, 55, 55]), 40),
@@ -35,6 +47,9 @@ CASES = {
     "mlp_head": ("MLP", mlp([193], [0.0], [False], [False], ["softmax"]), 110),
     "mlp_timit": ("MLP", mlp([102, 102, 102, 102, 193], [0.15] * 4 + [0.0], [True] * 4 + [False], [False] * 5,
                               ["relu"] * 4 + ["softmax"]), 429),
+    # cfg/TIMIT_baselines/TIMIT_SincNet_raw.cfg / TIMIT_CNN_fbank.cfg in miniature
+    "sincnet_raw": ("SincNet", conv("sinc", [16, 12, 12, 12], [33, 5, 5, 3], [3, 3, 3, 2], ln=True, ln_inp=True), 800),
+    "cnn_fbank": ("CNN", conv("cnn", [20, 12, 12], [10, 3, 3], [3, 2, 1]), 120),
     "mlp_ln_inp": ("MLP", mlp([20, 9], [0.1, 0.0], [False, False], [True, False], ["leaky_relu", "softmax"],
                                ln_inp=True, bn_inp=True), 11),
 }
