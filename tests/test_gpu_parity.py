@@ -325,10 +325,10 @@ def test_stepwise_cells_against_oracle_medium(cell, H, act):
     assert gu.relerr(out.detach().cpu().numpy(), ref["out"]) < 2 * TOL_FWD
     assert gu.relerr(logp.detach().cpu().numpy(), ref["logp"][0]) < TOL_FWD
     assert abs(loss.item() - ref["loss"]) / ref["loss"] < TOL_FWD
-    # ReLU: isolated kink flips from accumulation-order differences (see test_against_oracle_medium); the wider
-    # the layer the more of them, so the 1024-unit case gets a proportionally wider L2 bound
+    # ReLU: isolated kink flips from accumulation-order differences (see test_against_oracle_medium); wider layers
+    # and the two-product cells (GRU: fp16 r*h operand) have more of them -> 2 % L2 bound; tanh cases stay at 0.5 %
     tol_max = 0.2 if act in KINK_ACTS else TOL_GRAD
-    tol_l2 = (4 if H > 560 else 2) * TOL_GRAD if act in KINK_ACTS else TOL_GRAD
+    tol_l2 = 4 * TOL_GRAD if act in KINK_ACTS else TOL_GRAD
 
     def close(got, want, what):
         assert rel_l2(got, want) < tol_l2, what
