@@ -14,6 +14,7 @@ power-of-two loss scale before the fp16 conversion and the GEMM epilogues undo i
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional
 
@@ -53,6 +54,20 @@ def _rows_view(x2d_src: torch.Tensor, T: int, B: int):
         x = x.contiguous()
     return x, x.stride(1)
 
+
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev):
+    """One extra stream per device for work that is off the critical path of the backward sweep (weight-gradient
+    GEMMs run next to the next layer's recurrent kernel, which occupies 80 of the 148 SMs)."""
+    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=key)
+    return _SIDE_STREAMS[key]
+
+
+OVERLAP_WGRAD = os.environ.get("PK_OVERLAP", "1") != "0"
 
 PERSISTENT_MAX_H = 560  # largest hidden size the register-resident persistent kernels hold
 
@@ -199,6 +214,8 @@ class LiGRUStackFn(torch.autograd.Function):
         dYT = None
         dx = None
         amax_acc = torch.zeros(1, device=dev, dtype=torch.int32)  # |grad| max accumulated by the producers
+        main = torch.cuda.current_stream(dev)
+        side = _side_stream(dev)
         for li in reversed(range(len(saved))):
             S = saved[li]
             H, D = S["H"], S["D"]
@@ -226,19 +243,7 @@ class LiGRUStackFn(torch.autograd.Function):
                 pk.rnn_layer_bwd(cfg.cell | cfg.cell_flags, T, B, H, ndir, S["act"], dYT, S["HT"], S["SV"][0],
                                  S["SV"][1], ldt, S["U"], S["mask"], S["mask_scalar"], sc, GT, GT16)
             inv = sc[1:2]
-            # dU = sum_t G_t^T h_{t-1}  (both directions accumulate into the shared weights)
-            dU = torch.empty(CG, H, **f32)
-            for d in range(ndir):
-                hp = S["HP16"][d * H:(d + 1) * H]
-                if S["HX16"] is None:
-                    pk.gemm_tn(GT16[d], hp, dU, CG, H, TB, lda=ldt, ldb=ldt, ldc=H, alpha_dev=inv, accumulate=(d > 0),
-                               split_k=16)
-                else:  # GRU / minimalGRU: the candidate block contracted (gate * h_{t-1}) (:634, :1295)
-                    pk.gemm_tn(GT16[d][:H], S["HX16"][d * H:(d + 1) * H], dU[:H], H, H, TB, lda=ldt, ldb=ldt, ldc=H,
-                               alpha_dev=inv, accumulate=(d > 0), split_k=16)
-                    pk.gemm_tn(GT16[d][H:], hp, dU[H:], CG - H, H, TB, lda=ldt, ldb=ldt, ldc=H, alpha_dev=inv,
-                               accumulate=(d > 0), split_k=16)
-            # BatchNorm backward on the de-duplicated projection (both directions folded)
+            # BatchNorm backward on the de-duplicated projection (both directions folded) — on the critical path
             dgamma = torch.empty(CG, **f32)
             dbeta = torch.empty(CG, **f32)
             need_dx = li > 0 or ctx.x_needs_grad
@@ -247,9 +252,28 @@ class LiGRUStackFn(torch.autograd.Function):
             sums = torch.empty(2 * CG, device=dev, dtype=torch.float64)
             pk.bn_bwd(CG, ndir, TB, GT, GT16, ldt, S["PT"], ldt, S["use_bn"], S["bn_train"], S["mean"], S["rstd"],
                       S["gamma"], sc, dgamma, dbeta, dPT16, ldt, dP16, ldG, sums)
-            # dW = dP^T X
+            # weight gradients: off the critical path -> side stream, next to the following layer's recurrence
+            dU = torch.empty(CG, H, **f32)
             dW = torch.empty(CG, D, **f32)
-            pk.gemm_tn(dPT16, S["XT16"], dW, CG, D, TB, lda=ldt, ldb=ldt, ldc=D, alpha_dev=inv, split_k=8)
+            if OVERLAP_WGRAD:
+                side.wait_stream(main)
+                for t in (GT16, S["HP16"], S["HX16"], dPT16, S["XT16"], dU, dW, sc):
+                    if t is not None:
+                        t.record_stream(side)
+            with torch.cuda.stream(side if OVERLAP_WGRAD else main):
+                # dU = sum_t G_t^T h_{t-1}  (both directions accumulate into the shared weights)
+                for d in range(ndir):
+                    hp = S["HP16"][d * H:(d + 1) * H]
+                    if S["HX16"] is None:
+                        pk.gemm_tn(GT16[d], hp, dU, CG, H, TB, lda=ldt, ldb=ldt, ldc=H, alpha_dev=inv, accumulate=(d > 0),
+                                   split_k=16)
+                    else:  # GRU / minimalGRU: the candidate block contracted (gate * h_{t-1}) (:634, :1295)
+                        pk.gemm_tn(GT16[d][:H], S["HX16"][d * H:(d + 1) * H], dU[:H], H, H, TB, lda=ldt, ldb=ldt, ldc=H,
+                                   alpha_dev=inv, accumulate=(d > 0), split_k=16)
+                        pk.gemm_tn(GT16[d][H:], hp, dU[H:], CG - H, H, TB, lda=ldt, ldb=ldt, ldc=H, alpha_dev=inv,
+                                   accumulate=(d > 0), split_k=16)
+                # dW = dP^T X
+                pk.gemm_tn(dPT16, S["XT16"], dW, CG, D, TB, lda=ldt, ldb=ldt, ldc=D, alpha_dev=inv, split_k=8)
             sl = [slice(g * H, (g + 1) * H) for g in range(ngr)]
             lg = [dW[s] for s in sl] + [dU[s] for s in sl]
             if S["use_bn"]:
@@ -267,6 +291,8 @@ class LiGRUStackFn(torch.autograd.Function):
             elif ctx.x_needs_grad:
                 dx = torch.empty(T, B, D, **f32)
                 pk.gemm_tn(dP16, S["WT16"], dx, TB, D, CG, lda=ldG, ldb=ldG, ldc=D, alpha_dev=inv)
+        if OVERLAP_WGRAD:
+            main.wait_stream(side)
         ctx.saved = None
         return (dx, None, *grads)
 
