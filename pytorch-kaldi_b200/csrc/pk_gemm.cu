@@ -25,7 +25,10 @@ namespace {
 
 constexpr int kBM = 128;
 constexpr int kBN = 128;
-constexpr int kStages = 6;
+#ifndef PK_GEMM_STAGES
+#define PK_GEMM_STAGES 3
+#endif
+constexpr int kStages = PK_GEMM_STAGES;  // 3 stages (98 KB) -> two CTAs per SM: one tile's epilogue overlaps the other's mainloop
 constexpr int kTileBytes = kBM * 128;  // 128 rows x 128 bytes
 constexpr int kGemmThreads = 192;
 constexpr int kSmemBytes = 2 * kStages * kTileBytes + 256 + 1024;  // + barriers + align slack
@@ -47,7 +50,7 @@ struct GemmDev {
 };
 
 template <int DT>  // 0 = f16 operands, 2 = tf32 (fp32 operands)
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmThreads, kStages <= 3 ? 2 : 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const GemmDev p) {
   extern __shared__ uint8_t smem_raw[];

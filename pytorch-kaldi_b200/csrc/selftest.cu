@@ -601,6 +601,20 @@ static void bench_all() {
       printf("ligru_bwd %s: %.3f ms/layer  (%.3f us/step) rc=%d %s\n", v.name, ms, ms * 1000.f / T, rc,
              rc ? pk_last_error() : "");
     }
+    {  // which of the forward kernel's output streams cost time? (null pointer = stream not written)
+      struct A { const char* name; bool y, f32, f16; };
+      const A as[] = {{"all outputs", true, true, true}, {"no Y16/Y32", false, true, true}, {"no fp32 HT/ZT/HCT", true, false, true},
+                      {"no fp16 HT16/HP16", true, true, false}, {"Y16 only", true, false, false}, {"fp32 only", false, true, false}};
+      for (const A& v : as) {
+        int rc = 0;
+        float ms = time_ms(3, [&] {
+          rc |= pk_rnn_layer_fwd(PK_CELL_LIGRU, T, B, H, ndir, PK_ACT_RELU, dPT.p, ld, dsc.p, dsh.p, dU.p, dmask.p, 1.f, nullptr, 1100,
+                                 v.y ? dY16.p : nullptr, 1104, v.f32 ? dHT.p : nullptr, v.f16 ? dHT16.p : nullptr,
+                                 v.f16 ? dHP16.p : nullptr, v.f32 ? dZT.p : nullptr, v.f32 ? dHCT.p : nullptr, ld, nullptr);
+        });
+        printf("ligru_fwd ablation %-20s: %.3f us/step rc=%d\n", v.name, ms * 1000.f / T, rc);
+      }
+    }
     {  // per-phase cycle breakdown of the critical-path warp (CTA 0, warp 0)
       Dev<long long> dclk(8);
       pk_debug_set_clock_buffer(dclk.p);
