@@ -250,6 +250,10 @@ int pk_dense_act_bwd(int C, int64_t n, int act, const float* dYT, int64_t ldy, c
                      int64_t ld16t, const void* keepT, int64_t ldk, const float* gscale, void* GT16,
                      int64_t ldg, void* stream);
 
+/* torch.optim.Adam (utils.py:2131-2145, amsgrad off): m/v = exponential averages (zero-initialised by the caller),
+ * step counts from 1, g is multiplied by gscale (1/world after the allreduce), weight_decay is the L2 term. */
+int pk_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                 float eps, float weight_decay, int64_t step, float gscale, void* stream);
 /* torch.optim.RMSprop (momentum 0, not centered) / SGD steps over a flat buffer
  * (utils.py:2121-2162, core.py:640-642); gscale multiplies the gradient (1/world_size). */
 int pk_rmsprop_step(float* p, const float* g, float* v, int64_t n, float lr, float alpha,

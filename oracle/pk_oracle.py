@@ -666,6 +666,16 @@ def rmsprop_step(p, g, v, lr=0.0004, alpha=0.95, eps=1e-8):
     return p, v
 
 
+def adam_step(p, g, m, v, step, lr=0.001, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+    """torch.optim.Adam as built by utils.optimizer_init (utils.py:2131-2145), amsgrad off.  step counts from 1."""
+    g = g + weight_decay * p
+    m = betas[0] * m + (1 - betas[0]) * g
+    v = betas[1] * v + (1 - betas[1]) * g * g
+    bc1, bc2 = 1 - betas[0] ** step, 1 - betas[1] ** step
+    p = p - (lr / bc1) * m / (np.sqrt(v) / np.sqrt(bc2) + eps)
+    return p, m, v
+
+
 def sgd_step(p, g, lr=0.08):
     return p - lr * g
 

@@ -303,6 +303,11 @@ int pk_rmsprop_step(float* p, const float* g, float* v, int64_t n, float lr, flo
   PK_REQUIRE(n <= 0 || (p && g && v), "pk_rmsprop_step: null pointer");
   return rmsprop_step(p, g, v, n, lr, alpha, eps, gscale, static_cast<cudaStream_t>(stream));
 }
+int pk_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                 float weight_decay, int64_t step, float gscale, void* stream) {
+  PK_REQUIRE(p && g && m && v, "pk_adam_step: null pointer");
+  return adam_step(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, gscale, static_cast<cudaStream_t>(stream));
+}
 int pk_sgd_step(float* p, const float* g, int64_t n, float lr, float gscale, void* stream) {
   PK_REQUIRE(n <= 0 || (p && g), "pk_sgd_step: null pointer");
   return sgd_step(p, g, n, lr, gscale, static_cast<cudaStream_t>(stream));

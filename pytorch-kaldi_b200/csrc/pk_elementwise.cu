@@ -14,6 +14,8 @@
 #include "pk_common.cuh"
 #include "pk_kernels.h"
 
+#include <cmath>
+
 namespace pk {
 
 namespace {
@@ -490,6 +492,21 @@ __global__ void rmsprop_kernel(float* __restrict__ p, const float* __restrict__ 
     p[i] -= lr * gi / (sqrtf(vi) + eps);
   }
 }
+// torch.optim.Adam (utils.py:2131-2145; amsgrad off): bias corrections bc1 = 1 - b1^t, bc2 = 1 - b2^t from the host
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float rsqrt_bc2,
+                            float gscale) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float pi = p[i];
+    const float gi = fmaf(wd, pi, g[i] * gscale);
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = pi - (lr / bc1) * mi / (sqrtf(vi) * rsqrt_bc2 + eps);
+  }
+}
 __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, long long n, float lr, float gscale) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
@@ -614,6 +631,17 @@ int rmsprop_step(float* p, const float* g, float* v, long long n, float lr, floa
                  float gscale, cudaStream_t stream) {
   if (n <= 0) return 0;
   rmsprop_kernel<<<grid_for(n, 1024), 256, 0, stream>>>(p, g, v, n, lr, alpha, eps, gscale);
+  PK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float wd,
+              long long step, float gscale, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  PK_REQUIRE(step >= 1, "adam_step: step counts from 1");
+  const double bc1 = 1.0 - pow(static_cast<double>(b1), static_cast<double>(step));
+  const double bc2 = 1.0 - pow(static_cast<double>(b2), static_cast<double>(step));
+  adam_kernel<<<grid_for(n, 1024), 256, 0, stream>>>(p, g, m, v, n, lr, b1, b2, eps, wd, static_cast<float>(bc1),
+                                                     static_cast<float>(1.0 / sqrt(bc2)), gscale);
   PK_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

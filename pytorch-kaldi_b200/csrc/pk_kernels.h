@@ -281,5 +281,7 @@ int dense_act_bwd(const DenseBwdArgs& a, cudaStream_t stream);
 int rmsprop_step(float* p, const float* g, float* v, long long n, float lr, float alpha, float eps,
                  float gscale, cudaStream_t stream);
 int sgd_step(float* p, const float* g, long long n, float lr, float gscale, cudaStream_t stream);
+int adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float wd,
+              long long step, float gscale, cudaStream_t stream);
 
 }  // namespace pk

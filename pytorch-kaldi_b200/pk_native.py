@@ -60,6 +60,7 @@ SIGNATURES = {
                          _c_p, _c_i64, _c_p],
     "pk_dense_act_bwd": [_c_int, _c_i64, _c_int, _c_p, _c_i64, _c_p, _c_i64, _c_p, _c_i64, _c_p, _c_p, _c_i64, _c_p],
     "pk_rmsprop_step": [_c_p, _c_p, _c_p, _c_i64, _c_f, _c_f, _c_f, _c_f, _c_p],
+    "pk_adam_step": [_c_p, _c_p, _c_p, _c_p, _c_i64, _c_f, _c_f, _c_f, _c_f, _c_f, _c_i64, _c_f, _c_p],
     "pk_sgd_step": [_c_p, _c_p, _c_i64, _c_f, _c_f, _c_p],
 }
 
@@ -94,8 +95,9 @@ KERNELS_PER_CALL = {"pk_dense_act_fwd": 1, "pk_dense_act_bwd": 1, "pk_amax_final
                     "pk_bn_finalize": 1, "pk_fill_scale_shift": 1, "pk_bn_bwd": 2, "pk_rnn_layer_fwd": 1,
                     "pk_rnn_layer_bwd": 1, "pk_rnn_step_fwd": 1, "pk_rnn_step_bwd": 1, "pk_rowln_fwd": 1, "pk_conv_ln0_bwd": 1,
                     "pk_sinc_filters_fwd": 1, "pk_sinc_filters_bwd": 1, "pk_conv_pack_weights": 1, "pk_conv_im2col0": 1,
-                    "pk_conv_im2col_t": 1, "pk_conv_post_fwd": 1, "pk_conv_post_bwd": 1, "pk_logsoftmax_nll": 1, "pk_logsoftmax_bwd": 1, "pk_rmsprop_step": 1,
-                    "pk_sgd_step": 1}
+                    "pk_conv_im2col_t": 1, "pk_conv_post_fwd": 1, "pk_conv_post_bwd": 1, "pk_logsoftmax_nll": 1, "pk_logsoftmax_bwd": 1, "pk_rmsprop_step": 1, "pk_adam_step": 1,
+                    "pk_adam_step": [_c_p, _c_p, _c_p, _c_p, _c_i64, _c_f, _c_f, _c_f, _c_f, _c_f, _c_i64, _c_f, _c_p],
+    "pk_sgd_step": 1}
 
 
 def _check(rc, what, extra_kernels=0):
@@ -277,6 +279,11 @@ def dense_act_bwd(C, n, act, dYT, ldy, YT16, ld16t, keepT, ldk, gscale, GT16, ld
 def rmsprop_step(p, g, v, lr, alpha, eps, gscale=1.0):
     _check(lib().pk_rmsprop_step(_ptr(p), _ptr(g), _ptr(v), p.numel(), float(lr), float(alpha), float(eps),
                                  float(gscale), _stream()), "pk_rmsprop_step")
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, gscale=1.0):
+    _check(lib().pk_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), float(lr), float(beta1), float(beta2),
+                              float(eps), float(weight_decay), int(step), float(gscale), _stream()), "pk_adam_step")
 
 
 def sgd_step(p, g, lr, gscale=1.0):

@@ -24,7 +24,7 @@ class FlatTrainer:
     working (parameters stay nn.Parameters, only their storage moves)."""
 
     def __init__(self, modules: Iterable[torch.nn.Module], opt: str = "rmsprop", lr: float = 0.0004,
-                 alpha: float = 0.95, eps: float = 1e-8, optimizer_fn=None):
+                 alpha: float = 0.95, eps: float = 1e-8, optimizer_fn=None, betas=(0.9, 0.999), weight_decay: float = 0.0):
         """optimizer_fn(flat_p, flat_g, flat_v, gscale): test hook that replaces the CUDA optimizer kernel
         (tests/test_dp_gloo.py runs the buffer / allreduce plumbing on CPU with the oracle's update rule);
         without it CPU modules are refused."""
@@ -37,7 +37,9 @@ class FlatTrainer:
         n = sum(p.numel() for p in self.params)
         self.flat_p = torch.empty(n, device=dev, dtype=torch.float32)
         self.flat_g = torch.zeros(n, device=dev, dtype=torch.float32)
-        self.flat_v = torch.zeros(n, device=dev, dtype=torch.float32) if opt == "rmsprop" else None
+        self.flat_v = torch.zeros(n, device=dev, dtype=torch.float32) if opt in ("rmsprop", "adam") else None
+        self.flat_m = torch.zeros(n, device=dev, dtype=torch.float32) if opt == "adam" else None
+        self.betas, self.weight_decay, self.steps = betas, weight_decay, 0
         off = 0
         for p in self.params:
             k = p.numel()
@@ -64,6 +66,10 @@ class FlatTrainer:
             pk.rmsprop_step(self.flat_p, self.flat_g, self.flat_v, self.lr, self.alpha, self.eps, gscale)
         elif self.opt == "sgd":
             pk.sgd_step(self.flat_p, self.flat_g, self.lr, gscale)
+        elif self.opt == "adam":
+            self.steps += 1
+            pk.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr, self.betas[0], self.betas[1], self.eps,
+                         self.weight_decay, self.steps, gscale)
         else:
             raise NotImplementedError(self.opt)
 

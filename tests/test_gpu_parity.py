@@ -614,3 +614,38 @@ def test_sinc_filter_kernels_against_oracle():
     want = orc.conv1d_valid(orc.q16(x.numpy().astype(np.float64)), orc.q16(filt_ref)[:, None, :])
     assert y.shape == (3, C, 400 - k + 1)
     assert gu.relerr(y.detach().cpu().numpy(), want) < TOL_FWD
+
+
+def test_fused_optimizer_kernels_against_oracle():
+    """pk_rmsprop_step / pk_sgd_step / pk_adam_step on a flat buffer vs the oracle's update rules (which are pinned
+    to torch.optim in tests/test_oracle.py), three steps, with the 1/world gradient scale."""
+    import pk_native as pk
+    import pk_oracle as orc
+    rng = np.random.default_rng(1)
+    n = 100_003
+    p0 = rng.standard_normal(n).astype(np.float32)
+    grads = [(rng.standard_normal(n) * s).astype(np.float32) for s in (1.0, 0.05, 2.0)]
+    gs = 0.5
+    # Adam
+    p = torch.from_numpy(p0.copy()).cuda()
+    m = torch.zeros(n, device="cuda")
+    v = torch.zeros(n, device="cuda")
+    pr, mr, vr = p0.astype(np.float64), np.zeros(n), np.zeros(n)
+    for k, g in enumerate(grads, 1):
+        pk.adam_step(p, torch.from_numpy(g).cuda(), m, v, 0.002, 0.9, 0.98, 1e-7, 0.01, k, gs)
+        pr, mr, vr = orc.adam_step(pr, g.astype(np.float64) * gs, mr, vr, k, lr=0.002, betas=(0.9, 0.98), eps=1e-7,
+                                   weight_decay=0.01)
+    assert np.max(np.abs(p.cpu().numpy() - pr)) < 2e-6
+    # RMSprop / SGD
+    p = torch.from_numpy(p0.copy()).cuda()
+    v = torch.zeros(n, device="cuda")
+    q = torch.from_numpy(p0.copy()).cuda()
+    pr, vr, qr = p0.astype(np.float64), np.zeros(n), p0.astype(np.float64)
+    for g in grads:
+        gd = torch.from_numpy(g).cuda()
+        pk.rmsprop_step(p, gd, v, 0.0004, 0.95, 1e-8, gs)
+        pk.sgd_step(q, gd, 0.08, gs)
+        pr, vr = orc.rmsprop_step(pr, g.astype(np.float64) * gs, vr, lr=0.0004, alpha=0.95, eps=1e-8)
+        qr = orc.sgd_step(qr, g.astype(np.float64) * gs, lr=0.08)
+    assert np.max(np.abs(p.cpu().numpy() - pr)) < 2e-6
+    assert np.max(np.abs(q.cpu().numpy() - qr)) < 2e-6

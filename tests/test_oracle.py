@@ -219,3 +219,21 @@ def test_mlp(name):
     # SGD step (utils.py:2129-2137, lr 0.08)
     p1 = orc.sgd_step(d["init.mlp.wx.0.weight"].astype(np.float64), grads[0]["w"], lr=0.08)
     assert gu.relerr(p1, d["step1.mlp.wx.0.weight"]) < 1e-5
+
+
+def test_adam_matches_torch_optim():
+    """utils.optimizer_init builds stock torch.optim.Adam for arch_opt=adam (utils.py:2131-2145): the restatement
+    must follow it step for step (bias corrections, eps outside the square root, L2 weight decay)."""
+    import torch
+    rng = np.random.default_rng(0)
+    p0 = rng.standard_normal(300)
+    grads = [rng.standard_normal(300) * s for s in (1.0, 0.1, 3.0, 1e-3)]
+    for wd in (0.0, 0.01):
+        t = torch.nn.Parameter(torch.from_numpy(p0.copy()))
+        opt = torch.optim.Adam([t], lr=0.002, betas=(0.9, 0.98), eps=1e-7, weight_decay=wd, amsgrad=False)
+        p, m, v = p0.copy(), np.zeros(300), np.zeros(300)
+        for k, g in enumerate(grads, 1):
+            t.grad = torch.from_numpy(g.copy())
+            opt.step()
+            p, m, v = orc.adam_step(p, g, m, v, k, lr=0.002, betas=(0.9, 0.98), eps=1e-7, weight_decay=wd)
+            assert np.max(np.abs(p - t.detach().numpy())) < 1e-12
