@@ -250,6 +250,19 @@ int pk_dense_act_bwd(int C, int64_t n, int act, const float* dYT, int64_t ldy, c
                      int64_t ld16t, const void* keepT, int64_t ldk, const float* gscale, void* GT16,
                      int64_t ldg, void* stream);
 
+/* ---- input side of the path ----
+ * Chunk preparation of data_io.load_chunk (data_io.py:255-272) on the device: context-window expansion
+ * (out column (lag+left)*F + f = fea[i+left+lag][f], data_io.py:228-241), per-column mean / population-std
+ * normalisation (:263, statistics in double), and the label column lab[i+left] - lab_min appended (:266-272; pass
+ * lab = NULL for feature-only chunks).  fea [n_in][ldf]; out [n_in-left-right][ldo]; stats: 2*(left+right+1)*F doubles. */
+int pk_chunk_prepare(const float* fea, int64_t ldf, const int64_t* lab, int64_t lab_min, int64_t n_in, int F, int left,
+                     int right, double* stats, float* out, int64_t ldo, void* stream);
+/* Minibatch assembly of core.run_nn (core.py:577-598) without the per-sentence host loop: inp [max_len][B][D];
+ * desc = int64 [3][B] on the device: first frame, length and number of leading zero frames of every sentence
+ * (the random left padding is drawn by the caller, core.py:592). */
+int pk_batch_assemble(const float* data_set, int64_t ldd, int D, const int64_t* desc, int batch_size, int max_len,
+                      float* inp, void* stream);
+
 /* torch.optim.Adam (utils.py:2131-2145, amsgrad off): m/v = exponential averages (zero-initialised by the caller),
  * step counts from 1, g is multiplied by gscale (1/world after the allreduce), weight_decay is the L2 term. */
 int pk_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,

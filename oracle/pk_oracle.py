@@ -715,3 +715,45 @@ def ligru_model_step(x, labels, ligru_layers, heads, *, masks, bidir=True, loss_
     loss = sum(w * l for w, l in zip(lw, losses))
     return dict(loss=loss, losses=losses, err=cost_err(logps[0], labels[0]), logp=logps, out=out, ligru_grads=lgrads,
                 head_grads=hgrads)
+
+
+# --------------------------------------------------------------------------------------
+# input side of the path: data_io.load_chunk array work and core.run_nn batch assembly
+# --------------------------------------------------------------------------------------
+
+
+def context_window(fea, left, right):
+    """data_io.py:228-241 (np.roll per lag, then drop the wrapped rows)."""
+    n, f = fea.shape
+    out = np.empty((n, f * (left + right + 1)))
+    for j, lag in enumerate(range(-left, right + 1)):
+        out[:, j * f:(j + 1) * f] = np.roll(fea, -lag, axis=0)
+    return out[left:n - right]
+
+
+def prepare_chunk(fea, lab, left, right):
+    """data_io.py:255-272: context window, (x - mean) / std per column (float64, population std), label column."""
+    # literal dtype behaviour: context_window allocates float64 (np.empty default); without a context window the
+    # float32 features are normalised in float32
+    data = context_window(fea, left, right) if (left or right) else fea
+    data = (data - np.mean(data, axis=0)) / np.std(data, axis=0)
+    if lab is None:
+        return data
+    lab = lab - lab.min()
+    lab = lab[left:-right] if right > 0 else lab[left:]
+    return np.column_stack((data, lab))
+
+
+def assemble_batch(data_set, data_end_index, snt_index, beg_snt, batch_size, randint):
+    """core.py:581-598, literally: zero tensor [max_len, B, D], every sentence copied behind a random number of
+    leading zero frames drawn with randint(0, N_zeros)."""
+    arr_len = [int(data_end_index[0])] + [int(data_end_index[i] - data_end_index[i - 1]) for i in range(1, len(data_end_index))]
+    max_len = int(max(arr_len[snt_index:snt_index + batch_size]))
+    inp = np.zeros((max_len, batch_size, data_set.shape[1]), dtype=data_set.dtype)
+    for k in range(batch_size):
+        snt_len = int(data_end_index[snt_index]) - beg_snt
+        n_left = randint(0, max_len - snt_len)
+        inp[n_left:n_left + snt_len, k, :] = data_set[beg_snt:beg_snt + snt_len, :]
+        beg_snt = int(data_end_index[snt_index])
+        snt_index += 1
+    return inp, snt_index, beg_snt

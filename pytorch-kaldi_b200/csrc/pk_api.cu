@@ -303,6 +303,18 @@ int pk_rmsprop_step(float* p, const float* g, float* v, int64_t n, float lr, flo
   PK_REQUIRE(n <= 0 || (p && g && v), "pk_rmsprop_step: null pointer");
   return rmsprop_step(p, g, v, n, lr, alpha, eps, gscale, static_cast<cudaStream_t>(stream));
 }
+int pk_chunk_prepare(const float* fea, int64_t ldf, const int64_t* lab, int64_t lab_min, int64_t n_in, int F, int left, int right,
+                     double* stats, float* out, int64_t ldo, void* stream) {
+  PK_REQUIRE(fea && stats && out, "pk_chunk_prepare: null pointer");
+  return chunk_prepare(fea, ldf, reinterpret_cast<const long long*>(lab), lab_min, n_in, F, left, right, stats, out, ldo,
+                       static_cast<cudaStream_t>(stream));
+}
+int pk_batch_assemble(const float* data_set, int64_t ldd, int D, const int64_t* desc, int batch_size, int max_len, float* inp,
+                      void* stream) {
+  PK_REQUIRE(data_set && desc && inp, "pk_batch_assemble: null pointer");
+  return batch_assemble(data_set, ldd, D, reinterpret_cast<const long long*>(desc), batch_size, max_len, inp,
+                        static_cast<cudaStream_t>(stream));
+}
 int pk_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                  float weight_decay, int64_t step, float gscale, void* stream) {
   PK_REQUIRE(p && g && m && v, "pk_adam_step: null pointer");

@@ -14,6 +14,7 @@
 #include "pk_common.cuh"
 #include "pk_kernels.h"
 
+#include <algorithm>
 #include <cmath>
 
 namespace pk {
@@ -513,6 +514,63 @@ __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, l
     p[i] -= lr * g[i] * gscale;
 }
 
+// ---- input side of the path: chunk preparation (data_io.py:255-272) and minibatch assembly
+// (core.py:577-598) on the device ----
+// expanded column j = (lag + left) * F + f holds fea[i + left + lag][f];  stats[j] = (sum, sumsq) in double
+__global__ void chunk_stats_kernel(const float* __restrict__ fea, long long ldf, long long n_out, int F, int left, int right,
+                                   double* __restrict__ stats) {
+  const int W = left + right + 1;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= W * F) return;
+  const int lagi = j / F, f = j - lagi * F;
+  double s = 0.0, q = 0.0;
+  for (long long i = blockIdx.y; i < n_out; i += gridDim.y) {
+    const double v = fea[(i + lagi) * ldf + f];
+    s += v;
+    q += v * v;
+  }
+  atomicAdd(stats + 2 * j, s);
+  atomicAdd(stats + 2 * j + 1, q);
+}
+__global__ void chunk_write_kernel(const float* __restrict__ fea, long long ldf, const long long* __restrict__ lab, long long lab_min,
+                                   long long n_out, int F, int left, int right, const double* __restrict__ stats,
+                                   float* __restrict__ out, long long ldo) {
+  const int W = left + right + 1;
+  const int cols = W * F + (lab ? 1 : 0);
+  const long long total = n_out * cols;
+  for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total;
+       e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long i = e / cols;
+    const int j = static_cast<int>(e - i * cols);
+    float v;
+    if (j < W * F) {
+      const int lagi = j / F, f = j - lagi * F;
+      const double mean = stats[2 * j] / n_out;
+      const double var = stats[2 * j + 1] / n_out - mean * mean;  // np.std: population variance (data_io.py:263)
+      v = static_cast<float>((static_cast<double>(fea[(i + lagi) * ldf + f]) - mean) / sqrt(var > 0.0 ? var : 0.0));
+    } else {
+      v = static_cast<float>(lab[i + left] - lab_min);               // data_io.py:266-272
+    }
+    out[i * ldo + j] = v;
+  }
+}
+// inp[t][k][:] = data_set[beg[k] + t - left[k]][:] for left[k] <= t < left[k] + len[k], else 0   (core.py:584-595)
+__global__ void batch_assemble_kernel(const float* __restrict__ data, long long ldd, int D, const long long* __restrict__ desc,
+                                      int Bsz, int max_len, float* __restrict__ inp) {
+  const long long total = static_cast<long long>(max_len) * Bsz * D;
+  for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total;
+       e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(e % D);
+    const long long tk = e / D;
+    const int k = static_cast<int>(tk % Bsz);
+    const long long t = tk / Bsz;
+    const long long beg = desc[k], len = desc[Bsz + k], lz = desc[2 * Bsz + k];
+    float v = 0.f;
+    if (t >= lz && t < lz + len) v = data[(beg + t - lz) * ldd + c];
+    inp[e] = v;
+  }
+}
+
 inline int grid_for(long long work_items, int per_block) {
   long long b = (work_items + per_block - 1) / per_block;
   const long long cap = static_cast<long long>(kSMs) * 8;
@@ -642,6 +700,27 @@ int adam_step(float* p, const float* g, float* m, float* v, long long n, float l
   const double bc2 = 1.0 - pow(static_cast<double>(b2), static_cast<double>(step));
   adam_kernel<<<grid_for(n, 1024), 256, 0, stream>>>(p, g, m, v, n, lr, b1, b2, eps, wd, static_cast<float>(bc1),
                                                      static_cast<float>(1.0 / sqrt(bc2)), gscale);
+  PK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int chunk_prepare(const float* fea, long long ldf, const long long* lab, long long lab_min, long long n_in, int F, int left,
+                  int right, double* stats, float* out, long long ldo, cudaStream_t stream) {
+  const long long n_out = n_in - left - right;
+  PK_REQUIRE(n_out > 0 && F > 0 && left >= 0 && right >= 0, "chunk_prepare: bad sizes");
+  const int W = left + right + 1;
+  PK_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * W * F, stream));
+  const dim3 g1((W * F + 127) / 128, static_cast<unsigned>(std::min<long long>(n_out, 512)));
+  chunk_stats_kernel<<<g1, 128, 0, stream>>>(fea, ldf, n_out, F, left, right, stats);
+  chunk_write_kernel<<<grid_for(n_out * (W * F + 1), 1024), 256, 0, stream>>>(fea, ldf, lab, lab_min, n_out, F, left, right, stats,
+                                                                            out, ldo);
+  PK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int batch_assemble(const float* data, long long ldd, int D, const long long* desc, int Bsz, int max_len, float* inp,
+                   cudaStream_t stream) {
+  PK_REQUIRE(Bsz > 0 && max_len > 0 && D > 0, "batch_assemble: bad sizes");
+  batch_assemble_kernel<<<grid_for(static_cast<long long>(max_len) * Bsz * D, 1024), 256, 0, stream>>>(data, ldd, D, desc, Bsz,
+                                                                                                     max_len, inp);
   PK_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

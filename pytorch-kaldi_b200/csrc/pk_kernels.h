@@ -281,6 +281,10 @@ int dense_act_bwd(const DenseBwdArgs& a, cudaStream_t stream);
 int rmsprop_step(float* p, const float* g, float* v, long long n, float lr, float alpha, float eps,
                  float gscale, cudaStream_t stream);
 int sgd_step(float* p, const float* g, long long n, float lr, float gscale, cudaStream_t stream);
+int chunk_prepare(const float* fea, long long ldf, const long long* lab, long long lab_min, long long n_in, int F, int left,
+                  int right, double* stats, float* out, long long ldo, cudaStream_t stream);
+int batch_assemble(const float* data, long long ldd, int D, const long long* desc, int Bsz, int max_len, float* inp,
+                   cudaStream_t stream);
 int adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float wd,
               long long step, float gscale, cudaStream_t stream);
 

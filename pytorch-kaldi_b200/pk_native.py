@@ -60,6 +60,8 @@ SIGNATURES = {
                          _c_p, _c_i64, _c_p],
     "pk_dense_act_bwd": [_c_int, _c_i64, _c_int, _c_p, _c_i64, _c_p, _c_i64, _c_p, _c_i64, _c_p, _c_p, _c_i64, _c_p],
     "pk_rmsprop_step": [_c_p, _c_p, _c_p, _c_i64, _c_f, _c_f, _c_f, _c_f, _c_p],
+    "pk_chunk_prepare": [_c_p, _c_i64, _c_p, _c_i64, _c_i64, _c_int, _c_int, _c_int, _c_p, _c_p, _c_i64, _c_p],
+    "pk_batch_assemble": [_c_p, _c_i64, _c_int, _c_p, _c_int, _c_int, _c_p, _c_p],
     "pk_adam_step": [_c_p, _c_p, _c_p, _c_p, _c_i64, _c_f, _c_f, _c_f, _c_f, _c_f, _c_i64, _c_f, _c_p],
     "pk_sgd_step": [_c_p, _c_p, _c_i64, _c_f, _c_f, _c_p],
 }
@@ -95,8 +97,10 @@ KERNELS_PER_CALL = {"pk_dense_act_fwd": 1, "pk_dense_act_bwd": 1, "pk_amax_final
                     "pk_bn_finalize": 1, "pk_fill_scale_shift": 1, "pk_bn_bwd": 2, "pk_rnn_layer_fwd": 1,
                     "pk_rnn_layer_bwd": 1, "pk_rnn_step_fwd": 1, "pk_rnn_step_bwd": 1, "pk_rowln_fwd": 1, "pk_conv_ln0_bwd": 1,
                     "pk_sinc_filters_fwd": 1, "pk_sinc_filters_bwd": 1, "pk_conv_pack_weights": 1, "pk_conv_im2col0": 1,
-                    "pk_conv_im2col_t": 1, "pk_conv_post_fwd": 1, "pk_conv_post_bwd": 1, "pk_logsoftmax_nll": 1, "pk_logsoftmax_bwd": 1, "pk_rmsprop_step": 1, "pk_adam_step": 1,
-                    "pk_adam_step": [_c_p, _c_p, _c_p, _c_p, _c_i64, _c_f, _c_f, _c_f, _c_f, _c_f, _c_i64, _c_f, _c_p],
+                    "pk_conv_im2col_t": 1, "pk_conv_post_fwd": 1, "pk_conv_post_bwd": 1, "pk_logsoftmax_nll": 1, "pk_logsoftmax_bwd": 1, "pk_rmsprop_step": 1, "pk_adam_step": 1, "pk_chunk_prepare": 2, "pk_batch_assemble": 1,
+                    "pk_chunk_prepare": [_c_p, _c_i64, _c_p, _c_i64, _c_i64, _c_int, _c_int, _c_int, _c_p, _c_p, _c_i64, _c_p],
+    "pk_batch_assemble": [_c_p, _c_i64, _c_int, _c_p, _c_int, _c_int, _c_p, _c_p],
+    "pk_adam_step": [_c_p, _c_p, _c_p, _c_p, _c_i64, _c_f, _c_f, _c_f, _c_f, _c_f, _c_i64, _c_f, _c_p],
     "pk_sgd_step": 1}
 
 
@@ -279,6 +283,18 @@ def dense_act_bwd(C, n, act, dYT, ldy, YT16, ld16t, keepT, ldk, gscale, GT16, ld
 def rmsprop_step(p, g, v, lr, alpha, eps, gscale=1.0):
     _check(lib().pk_rmsprop_step(_ptr(p), _ptr(g), _ptr(v), p.numel(), float(lr), float(alpha), float(eps),
                                  float(gscale), _stream()), "pk_rmsprop_step")
+
+
+def chunk_prepare(fea, lab, lab_min, left, right, out):
+    n_in, F = fea.shape
+    stats = torch.empty(2 * (left + right + 1) * F, device=fea.device, dtype=torch.float64)
+    _check(lib().pk_chunk_prepare(_ptr(fea), fea.stride(0), _ptr(lab), int(lab_min), n_in, F, left, right, _ptr(stats),
+                                  _ptr(out), out.stride(0), _stream()), "pk_chunk_prepare")
+
+
+def batch_assemble(data_set, desc, batch_size, max_len, inp):
+    _check(lib().pk_batch_assemble(_ptr(data_set), data_set.stride(0), data_set.shape[1], _ptr(desc), batch_size, max_len,
+                                   _ptr(inp), _stream()), "pk_batch_assemble")
 
 
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, gscale=1.0):

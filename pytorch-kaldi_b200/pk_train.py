@@ -95,3 +95,47 @@ def chunk_step(net, head, trainer: FlatTrainer, inp: torch.Tensor, n_fea: int, f
     loss.backward()
     trainer.step()
     return loss.detach(), err
+
+
+def prepare_chunk(fea: torch.Tensor, lab, left: int, right: int) -> torch.Tensor:
+    """data_io.load_chunk's array work (data_io.py:255-272) on the device: context window, per-column mean / std
+    normalisation, label column.  fea [N, F] fp32 CUDA, lab [N] integer CUDA tensor (or None) -> data_set
+    [N-left-right, F*(left+right+1) (+1)] fp32, the layout core.run_nn indexes."""
+    if not fea.is_cuda:
+        raise RuntimeError("pytorch-kaldi_b200: prepare_chunk needs CUDA tensors (there is no CPU fallback)")
+    fea = fea.float().contiguous()
+    n_out = fea.shape[0] - left - right
+    cols = fea.shape[1] * (left + right + 1) + (1 if lab is not None else 0)
+    out = torch.empty(n_out, cols, device=fea.device, dtype=torch.float32)
+    lab64, lab_min = None, 0
+    if lab is not None:
+        lab64 = lab.long().contiguous()
+        lab_min = int(lab64.min().item())       # data_io.py:266 (one scalar per chunk)
+    pk.chunk_prepare(fea, lab64, lab_min, left, right, out)
+    return out
+
+
+def batch_descriptors(data_end_index, snt_index: int, beg_snt: int, batch_size: int, rng):
+    """The bookkeeping of core.py:581-598 for one minibatch: returns (desc [3][B] int64 = first frame / length / left
+    zeros, max_len, next snt_index, next beg_snt).  `rng.randint` is consumed exactly like the reference does (one
+    draw per sentence, in order), so a seeded run pads identically."""
+    lens, begs = [], []
+    b, s = beg_snt, snt_index
+    for _ in range(batch_size):
+        end = int(data_end_index[s])
+        begs.append(b)
+        lens.append(end - b)
+        b, s = end, s + 1
+    max_len = max(lens)
+    lefts = [rng.randint(0, max_len - L) for L in lens]   # core.py:592
+    return torch.tensor([begs, lens, lefts], dtype=torch.int64), max_len, s, b
+
+
+def assemble_batch(data_set: torch.Tensor, desc: torch.Tensor, max_len: int) -> torch.Tensor:
+    """inp [max_len, B, D] of core.py:584-595 built by one gather kernel from the device-resident chunk."""
+    if not data_set.is_cuda:
+        raise RuntimeError("pytorch-kaldi_b200: assemble_batch needs the chunk on the device (there is no CPU fallback)")
+    B = desc.shape[1]
+    inp = torch.empty(max_len, B, data_set.shape[1], device=data_set.device, dtype=torch.float32)
+    pk.batch_assemble(data_set, desc.to(data_set.device, non_blocking=True), B, max_len, inp)
+    return inp

@@ -295,6 +295,50 @@ def conv_case(name, *, kind, N, L0, n_filt, len_filt, pool, ln, ln_inp, act, dro
     print(f"{name}: loss={loss.item():.6f} err={err.item():.4f} -> {path} ({os.path.getsize(path)/1e6:.2f} MB)")
 
 
+def input_case(name, *, N, F, left, right, n_snt, batch, seed):
+    """Input side: data_io.load_chunk's array work (data_io.py:255-272, using the reference's own
+    context_window) and the minibatch assembly loop of core.run_nn (core.py:577-598, restated here line by line
+    because it is inline code of a 150-line function) with Python's `random` seeded."""
+    import random
+    import data_io as ref_io  # noqa: E402
+    rng = np.random.default_rng(seed)
+    fea = rng.standard_normal((N, F)).astype(np.float32)
+    lab = rng.integers(3, 40, N)
+    # sentence boundaries (end indices in the un-windowed frame numbering), as load_dataset returns them
+    cuts = np.sort(rng.choice(np.arange(10, N - 10), n_snt - 1, replace=False))
+    end_index = np.concatenate([cuts, [N]]).astype(np.int64)
+    # --- data_io.py:255-272
+    data_set = ref_io.context_window(fea, left, right) if (left != 0 or right != 0) else fea
+    end_index_fea = end_index - left
+    end_index_fea[-1] = end_index_fea[-1] - right
+    data_set = (data_set - np.mean(data_set, axis=0)) / np.std(data_set, axis=0)
+    data_lab = lab - lab.min()
+    data_lab = data_lab[left:-right] if right > 0 else data_lab[left:]
+    data_set = np.column_stack((data_set, data_lab))
+    # --- core.py:560-598 (seq_model branch)
+    random.seed(seed)
+    data_end_index = end_index_fea
+    t = torch.from_numpy(data_set).float()
+    snt_index, beg_snt = 0, 0
+    out = dict(fea=fea, lab=lab, data_set=data_set, data_end_index=data_end_index)
+    for i in range(n_snt // batch):
+        arr_snt_len = np.diff(np.concatenate([[0], data_end_index]))
+        max_len = int(max(arr_snt_len[snt_index:snt_index + batch]))
+        inp = torch.zeros(max_len, batch, t.shape[1]).contiguous()
+        for k in range(batch):
+            snt_len = data_end_index[snt_index] - beg_snt
+            N_zeros = max_len - snt_len
+            N_zeros_left = random.randint(0, N_zeros)
+            inp[N_zeros_left:N_zeros_left + snt_len, k, :] = t[beg_snt:beg_snt + snt_len, :]
+            beg_snt = data_end_index[snt_index]
+            snt_index = snt_index + 1
+        out[f"inp{i}"] = inp.numpy()
+    out["meta"] = np.array(repr(dict(N=N, F=F, left=left, right=right, n_snt=n_snt, batch=batch, seed=seed)))
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: data_set {data_set.shape} -> {path} ({os.path.getsize(path)/1e6:.2f} MB)")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     only = sys.argv[1:]  # optional: names of the fixtures to (re)generate
@@ -346,3 +390,8 @@ if __name__ == "__main__":
     if not only or "cnn_ln_relu" in only:
         conv_case("cnn_ln_relu", kind="CNN", N=7, L0=120, n_filt=[20, 12, 12], len_filt=[10, 3, 3], pool=[3, 2, 1],
                   ln=True, ln_inp=False, act="leaky_relu", drop=0.15, S=8, seed=73)
+    # I: input side (context window + chunk normalisation + minibatch assembly)
+    if not only or "input_cw" in only:
+        input_case("input_cw", N=400, F=7, left=3, right=2, n_snt=8, batch=4, seed=81)
+    if not only or "input_nocw" in only:
+        input_case("input_nocw", N=300, F=5, left=0, right=0, n_snt=6, batch=3, seed=82)

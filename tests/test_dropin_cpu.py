@@ -90,3 +90,25 @@ def test_abi_library_loads_and_exports_every_declared_symbol():
     L = pk_native.lib()
     assert L.pk_version() >= 2
     assert L.pk_last_error() is not None
+
+
+def test_batch_descriptors_follow_the_reference_bookkeeping():
+    """pk_train.batch_descriptors (host logic of the device-side batch assembly): same sentence ranges, same
+    random left padding (one `randint` per sentence, in order) as core.py:581-598."""
+    import random
+    import numpy as np
+    import golden_util as gu
+    import pk_train
+    d = gu.load("input_cw")
+    m = d["meta"]
+    rng = random.Random(m["seed"])
+    snt, beg = 0, 0
+    for i in range(m["n_snt"] // m["batch"]):
+        desc, max_len, snt, beg = pk_train.batch_descriptors(d["data_end_index"], snt, beg, m["batch"], rng)
+        ref = d[f"inp{i}"]
+        assert max_len == ref.shape[0] and tuple(desc.shape) == (3, m["batch"])
+        ds = d["data_set"].astype(np.float32)
+        for k in range(m["batch"]):
+            b, L, z = (int(v) for v in desc[:, k])
+            assert np.array_equal(ref[z:z + L, k], ds[b:b + L])
+            assert not ref[:z, k].any() and not ref[z + L:, k].any()

@@ -649,3 +649,27 @@ def test_fused_optimizer_kernels_against_oracle():
         qr = orc.sgd_step(qr, g.astype(np.float64) * gs, lr=0.08)
     assert np.max(np.abs(p.cpu().numpy() - pr)) < 2e-6
     assert np.max(np.abs(q.cpu().numpy() - qr)) < 2e-6
+
+
+@pytest.mark.parametrize("name", ["input_cw", "input_nocw"])
+def test_input_side_kernels_match_reference(name):
+    """pk_chunk_prepare / pk_batch_assemble against the reference-generated fixtures."""
+    import random
+    import pk_train
+    d = gu.load(name)
+    m = d["meta"]
+    fea = torch.from_numpy(d["fea"]).cuda()
+    lab = torch.from_numpy(d["lab"]).cuda()
+    ds = pk_train.prepare_chunk(fea, lab, m["left"], m["right"])
+    ref = d["data_set"]
+    assert tuple(ds.shape) == ref.shape
+    assert np.max(np.abs(ds.cpu().numpy().astype(np.float64) - ref)) < 2e-6 * max(1.0, np.abs(ref).max())
+    assert np.array_equal(ds[:, -1].cpu().numpy(), ref[:, -1].astype(np.float32))   # labels: exact
+    # assembly from the reference's own (float32) chunk: a pure gather, bit exact
+    chunk = torch.from_numpy(ref.astype(np.float32)).cuda()
+    rng = random.Random(m["seed"])
+    snt, beg = 0, 0
+    for i in range(m["n_snt"] // m["batch"]):
+        desc, max_len, snt, beg = pk_train.batch_descriptors(d["data_end_index"], snt, beg, m["batch"], rng)
+        inp = pk_train.assemble_batch(chunk, desc, max_len)
+        assert torch.equal(inp.cpu(), torch.from_numpy(d[f"inp{i}"]))

@@ -237,3 +237,22 @@ def test_adam_matches_torch_optim():
             opt.step()
             p, m, v = orc.adam_step(p, g, m, v, k, lr=0.002, betas=(0.9, 0.98), eps=1e-7, weight_decay=wd)
             assert np.max(np.abs(p - t.detach().numpy())) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["input_cw", "input_nocw"])
+def test_input_side_chunk_and_batch_assembly(name):
+    """data_io.load_chunk array work (:255-272) and core.run_nn minibatch assembly (:577-598) against the
+    reference (its own context_window; the inline loop restated in the generator with `random` seeded)."""
+    import random
+    d = gu.load(name)
+    m = d["meta"]
+    ds = orc.prepare_chunk(d["fea"], d["lab"], m["left"], m["right"])
+    assert ds.shape == d["data_set"].shape
+    assert np.max(np.abs(ds - d["data_set"])) < 1e-12
+    rng = random.Random(m["seed"])
+    snt, beg = 0, 0
+    for i in range(m["n_snt"] // m["batch"]):
+        inp, snt, beg = orc.assemble_batch(d["data_set"].astype(np.float32), d["data_end_index"], snt, beg, m["batch"],
+                                           rng.randint)
+        assert inp.shape == d[f"inp{i}"].shape
+        assert np.array_equal(inp, d[f"inp{i}"])
