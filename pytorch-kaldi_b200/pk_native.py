@@ -98,10 +98,7 @@ KERNELS_PER_CALL = {"pk_dense_act_fwd": 1, "pk_dense_act_bwd": 1, "pk_amax_final
                     "pk_rnn_layer_bwd": 1, "pk_rnn_step_fwd": 1, "pk_rnn_step_bwd": 1, "pk_rowln_fwd": 1, "pk_conv_ln0_bwd": 1,
                     "pk_sinc_filters_fwd": 1, "pk_sinc_filters_bwd": 1, "pk_conv_pack_weights": 1, "pk_conv_im2col0": 1,
                     "pk_conv_im2col_t": 1, "pk_conv_post_fwd": 1, "pk_conv_post_bwd": 1, "pk_logsoftmax_nll": 1, "pk_logsoftmax_bwd": 1, "pk_rmsprop_step": 1, "pk_adam_step": 1, "pk_chunk_prepare": 2, "pk_batch_assemble": 1,
-                    "pk_chunk_prepare": [_c_p, _c_i64, _c_p, _c_i64, _c_i64, _c_int, _c_int, _c_int, _c_p, _c_p, _c_i64, _c_p],
-    "pk_batch_assemble": [_c_p, _c_i64, _c_int, _c_p, _c_int, _c_int, _c_p, _c_p],
-    "pk_adam_step": [_c_p, _c_p, _c_p, _c_p, _c_i64, _c_f, _c_f, _c_f, _c_f, _c_f, _c_i64, _c_f, _c_p],
-    "pk_sgd_step": 1}
+                    "pk_sgd_step": 1}
 
 
 def _check(rc, what, extra_kernels=0):

@@ -87,6 +87,9 @@ def test_abi_library_loads_and_exports_every_declared_symbol():
         assert hasattr(lib, sym), f"libpk_b200.so does not export {sym}"
     # every symbol the Python binding declares must be in the header too
     assert set(pk_native.SIGNATURES) | {"pk_last_error", "pk_version"} == declared
+    # the launch-count table behind bench.py's gpu_launches covers every compute entry point
+    assert all(isinstance(v, int) for v in pk_native.KERNELS_PER_CALL.values())
+    assert set(pk_native.SIGNATURES) - set(pk_native.KERNELS_PER_CALL) <= {"pk_rnn_step_workspace_bytes"}
     L = pk_native.lib()
     assert L.pk_version() >= 2
     assert L.pk_last_error() is not None
