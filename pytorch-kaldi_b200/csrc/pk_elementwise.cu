@@ -445,38 +445,77 @@ __global__ void rowsum_kernel(const float* __restrict__ d, long long ld, int N, 
   }
 }
 
-__global__ void logsoftmax_bwd_kernel(const HeadBwdArgs a, const float* __restrict__ rowsum) {
-  __shared__ float tile[32][33];
+// 64 x 64 tiles, block (32, 8): every global access is a 2-element vector (float2 loads of the posteriors, half2
+// stores of both fp16 layouts); the channel-major copy goes through a shared-memory transpose.
+__global__ void __launch_bounds__(256) logsoftmax_bwd_kernel(const HeadBwdArgs a, const float* __restrict__ rowsum) {
+  __shared__ float tile[64][65];
   const float oscale = a.out_scale * (a.scale_dev ? __ldg(a.scale_dev) : 1.f);
-  const int tiles_c = (a.S + 31) / 32;
-  const long long ntiles = static_cast<long long>((a.N + 31) / 32) * tiles_c;
+  const int tiles_c = (a.S + 63) / 64;
+  const long long ntiles = static_cast<long long>((a.N + 63) / 64) * tiles_c;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  // vector paths need even leading dimensions / 8-byte (4-byte) aligned bases
+  const bool vin = ((a.ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.logp) & 7) == 0) &&
+                   (!a.dlogp || (((a.lddl & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.dlogp) & 7) == 0)));
+  const bool v16 = a.d16 && ((a.ld16 & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.d16) & 3) == 0);
+  const bool vt16 = a.dT16 && ((a.ld16t & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.dT16) & 3) == 0);
   for (long long tidx = blockIdx.x; tidx < ntiles; tidx += gridDim.x) {
-    const long long r0 = (tidx / tiles_c) * 32;
-    const int c0 = static_cast<int>(tidx % tiles_c) * 32;
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const long long r0 = (tidx / tiles_c) * 64;
+    const int c0 = static_cast<int>(tidx % tiles_c) * 64;
+    const int c = c0 + 2 * tx;
+#pragma unroll 2
+    for (int i = ty; i < 64; i += 8) {
       const long long r = r0 + i;
-      const int c = c0 + threadIdx.x;
-      float d = 0.f;
+      float d0 = 0.f, d1 = 0.f;
       if (r < a.N && c < a.S) {
-        const float p = expf(a.logp[r * a.ld + c]);
-        if (a.dlogp) {
-          d = a.dlogp[r * a.lddl + c] - p * rowsum[r];
+        const bool two = c + 1 < a.S;
+        float l0, l1 = 0.f;
+        if (vin && two) {
+          const float2 l = *reinterpret_cast<const float2*>(a.logp + r * a.ld + c);
+          l0 = l.x; l1 = l.y;
         } else {
-          d = (p - ((a.labels[r] == c) ? 1.f : 0.f)) * a.gcoef;
+          l0 = a.logp[r * a.ld + c];
+          if (two) l1 = a.logp[r * a.ld + c + 1];
         }
-        if (a.d16) a.d16[r * a.ld16 + c] = f16_sat(d * oscale);
+        const float p0 = __expf(l0), p1 = __expf(l1);
+        if (a.dlogp) {
+          const float rs = rowsum[r];
+          d0 = a.dlogp[r * a.lddl + c] - p0 * rs;
+          if (two) d1 = a.dlogp[r * a.lddl + c + 1] - p1 * rs;
+        } else {
+          const long long lab = a.labels[r];
+          d0 = (p0 - ((lab == c) ? 1.f : 0.f)) * a.gcoef;
+          if (two) d1 = (p1 - ((lab == c + 1) ? 1.f : 0.f)) * a.gcoef;
+        }
+        if (a.d16) {
+          if (v16 && two) {
+            *reinterpret_cast<__half2*>(a.d16 + r * a.ld16 + c) = __halves2half2(f16_sat(d0 * oscale), f16_sat(d1 * oscale));
+          } else {
+            a.d16[r * a.ld16 + c] = f16_sat(d0 * oscale);
+            if (two) a.d16[r * a.ld16 + c + 1] = f16_sat(d1 * oscale);
+          }
+        }
       }
-      tile[i][threadIdx.x] = d;
+      tile[i][2 * tx] = d0;
+      tile[i][2 * tx + 1] = d1;
     }
     __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-      const int c = c0 + i;
-      const long long r = r0 + threadIdx.x;
-      const float d = tile[threadIdx.x][i];
-      if (a.dT16 && c < a.S && r < a.N) a.dT16[static_cast<long long>(c) * a.ld16t + r] = f16_sat(d * oscale);
+#pragma unroll 2
+    for (int i = ty; i < 64; i += 8) {
+      const int cc = c0 + i;
+      const long long r = r0 + 2 * tx;
+      const float d0 = tile[2 * tx][i], d1 = tile[2 * tx + 1][i];   // rows past N hold zeros
+      if (a.dT16 && cc < a.S && r < a.N) {
+        if (vt16 && r + 1 < a.N) {
+          *reinterpret_cast<__half2*>(a.dT16 + static_cast<long long>(cc) * a.ld16t + r) =
+              __halves2half2(f16_sat(d0 * oscale), f16_sat(d1 * oscale));
+        } else {
+          a.dT16[static_cast<long long>(cc) * a.ld16t + r] = f16_sat(d0 * oscale);
+          if (r + 1 < a.N) a.dT16[static_cast<long long>(cc) * a.ld16t + r + 1] = f16_sat(d1 * oscale);
+        }
+      }
       if (a.dbias) {
-        const float cs = warp_sum(d);  // threadIdx.x spans the 32 rows of column c (zero padded)
-        if (threadIdx.x == 0 && c < a.S) atomicAdd(a.dbias + c, cs);
+        const float cs = warp_sum(d0 + d1);  // the warp spans the 64 rows of column cc (zero padded)
+        if (tx == 0 && cc < a.S) atomicAdd(a.dbias + cc, cs);
       }
     }
     __syncthreads();
@@ -665,7 +704,7 @@ int logsoftmax_bwd(const HeadBwdArgs& a, cudaStream_t stream) {
     rowsum_kernel<<<grid_for(a.N, 8), 256, 0, stream>>>(a.dlogp, a.lddl, a.N, a.S, rowsum);
   }
   if (a.dbias) PK_CHECK_CUDA(cudaMemsetAsync(a.dbias, 0, sizeof(float) * a.S, stream));
-  const long long ntiles = static_cast<long long>((a.N + 31) / 32) * ((a.S + 31) / 32);
+  const long long ntiles = static_cast<long long>((a.N + 63) / 64) * ((a.S + 63) / 64);
   logsoftmax_bwd_kernel<<<grid_for(ntiles, 1), dim3(32, 8), 0, stream>>>(a, rowsum);
   PK_CHECK_CUDA(cudaGetLastError());
   return 0;
