@@ -675,3 +675,34 @@ def test_input_side_kernels_match_reference(name):
         desc, max_len, snt, beg = pk_train.batch_descriptors(d["data_end_index"], snt, beg, m["batch"], rng)
         inp = pk_train.assemble_batch(chunk, desc, max_len)
         assert torch.equal(inp.cpu(), torch.from_numpy(d[f"inp{i}"]))
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 1500, 200), (1100, 2048, 1100), (129, 1025, 72), (260, 700, 136)])
+def test_gemm_tn_tiles_against_fp32(M, N, K):
+    """pk_gemm_tn (tcgen05): the 128x256 tile (N >= 1024) and the 128x128 one, ragged edges, bias along N / M,
+    BatchNorm row statistics and the amax side output, against fp32 matmul of the same fp16-rounded operands."""
+    import pk_native as pk
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    ldk = pk.pad8(K)
+    A = torch.zeros(M, ldk, device="cuda", dtype=torch.float16)
+    B = torch.zeros(N, ldk, device="cuda", dtype=torch.float16)
+    A[:, :K] = torch.randn(M, K, device="cuda", generator=g).half()
+    B[:, :K] = torch.randn(N, K, device="cuda", generator=g).half()
+    ref = A[:, :K].float() @ B[:, :K].float().t()
+    for mode in (0, 1, 2):
+        bias = None if mode == 0 else torch.randn(N if mode == 1 else M, device="cuda", generator=g)
+        C = torch.full((M, N), float("nan"), device="cuda")
+        stats = torch.zeros(M, 2, device="cuda", dtype=torch.float64)
+        amax = torch.zeros(1, device="cuda", dtype=torch.int32)
+        pk.gemm_tn(A, B, C, M, N, K, lda=ldk, ldb=ldk, ldc=N, bias=bias, bias_mode=mode, rowstats=stats, alpha=0.5,
+                   amax_bits=amax)
+        want = 0.5 * ref
+        if mode == 1:
+            want = want + bias[None, :]
+        if mode == 2:
+            want = want + bias[:, None]
+        scale = want.abs().max().item()
+        assert torch.isfinite(C).all()
+        assert (C - want).abs().max().item() < 2e-5 * scale + 1e-4
+        assert (stats[:, 0].float() - want.sum(1)).abs().max().item() < 1e-3 * scale
+        assert abs(amax.view(torch.float32).item() - want.abs().max().item()) < 1e-4 * scale
