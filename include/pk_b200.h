@@ -263,6 +263,11 @@ int pk_chunk_prepare(const float* fea, int64_t ldf, const int64_t* lab, int64_t 
 int pk_batch_assemble(const float* data_set, int64_t ldd, int D, const int64_t* desc, int batch_size, int max_len,
                       float* inp, void* stream);
 
+/* ---- output side of the path: forward-phase posteriors -> scaled log-likelihoods, in place:
+ * logp[n][s] -= log_prior[s] with log_prior = log(counts / sum(counts)) (core.py:664-667); the result is what
+ * data_io.write_mat stores as a Kaldi "FM" matrix (data_io.py:1200-1239). */
+int pk_sub_log_prior(float* logp, int64_t ld, int64_t n, int S, const float* log_prior, void* stream);
+
 /* torch.optim.Adam (utils.py:2131-2145, amsgrad off): m/v = exponential averages (zero-initialised by the caller),
  * step counts from 1, g is multiplied by gscale (1/world after the allreduce), weight_decay is the L2 term. */
 int pk_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,

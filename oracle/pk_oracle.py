@@ -757,3 +757,15 @@ def assemble_batch(data_set, data_end_index, snt_index, beg_snt, batch_size, ran
         beg_snt = int(data_end_index[snt_index])
         snt_index += 1
     return inp, snt_index, beg_snt
+
+
+def posterior_ark_bytes(key, logp, counts=None):
+    """core.py:660-671 + data_io.write_mat (:1200-1239): optional `out - log(counts/sum(counts))`, then the binary
+    Kaldi matrix entry (key, "\0B", "FM "/"DM ", \4 rows, \4 cols, payload)."""
+    import struct
+    out = logp
+    if counts is not None:
+        out = out - np.log(counts / np.sum(counts))
+    tag = {"float32": b"FM ", "float64": b"DM "}[str(out.dtype)]
+    head = ((key + " ").encode("latin1") if key != "" else b"") + b"\0B" + tag
+    return head + b"\x04" + struct.pack("<I", out.shape[0]) + b"\x04" + struct.pack("<I", out.shape[1]) + out.tobytes()

@@ -315,6 +315,10 @@ int pk_batch_assemble(const float* data_set, int64_t ldd, int D, const int64_t* 
   return batch_assemble(data_set, ldd, D, reinterpret_cast<const long long*>(desc), batch_size, max_len, inp,
                         static_cast<cudaStream_t>(stream));
 }
+int pk_sub_log_prior(float* logp, int64_t ld, int64_t n, int S, const float* log_prior, void* stream) {
+  PK_REQUIRE(logp && log_prior, "pk_sub_log_prior: null pointer");
+  return rows_sub_vec(logp, ld, n, S, log_prior, static_cast<cudaStream_t>(stream));
+}
 int pk_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                  float weight_decay, int64_t step, float gscale, void* stream) {
   PK_REQUIRE(p && g && m && v, "pk_adam_step: null pointer");

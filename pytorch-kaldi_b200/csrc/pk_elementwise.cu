@@ -610,6 +610,17 @@ __global__ void batch_assemble_kernel(const float* __restrict__ data, long long 
   }
 }
 
+// output side: x[n][c] -= v[c]  (log-posteriors -> scaled log-likelihoods, core.py:664-667)
+__global__ void rows_sub_vec_kernel(float* __restrict__ x, long long ld, long long n, int C, const float* __restrict__ v) {
+  const long long total = n * C;
+  for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total;
+       e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = e / C;
+    const int c = static_cast<int>(e - r * C);
+    x[r * ld + c] -= __ldg(v + c);
+  }
+}
+
 inline int grid_for(long long work_items, int per_block) {
   long long b = (work_items + per_block - 1) / per_block;
   const long long cap = static_cast<long long>(kSMs) * 8;
@@ -760,6 +771,12 @@ int batch_assemble(const float* data, long long ldd, int D, const long long* des
   PK_REQUIRE(Bsz > 0 && max_len > 0 && D > 0, "batch_assemble: bad sizes");
   batch_assemble_kernel<<<grid_for(static_cast<long long>(max_len) * Bsz * D, 1024), 256, 0, stream>>>(data, ldd, D, desc, Bsz,
                                                                                                      max_len, inp);
+  PK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int rows_sub_vec(float* x, long long ld, long long n, int C, const float* v, cudaStream_t stream) {
+  if (n <= 0 || C <= 0) return 0;
+  rows_sub_vec_kernel<<<grid_for(n * C, 1024), 256, 0, stream>>>(x, ld, n, C, v);
   PK_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

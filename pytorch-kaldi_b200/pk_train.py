@@ -9,7 +9,10 @@ utils.optimizer_init (utils.py:2106-2164).
 """
 from __future__ import annotations
 
+import struct
 from typing import Iterable, List
+
+import numpy as np
 
 import torch
 import torch.distributed as dist
@@ -139,3 +142,45 @@ def assemble_batch(data_set: torch.Tensor, desc: torch.Tensor, max_len: int) -> 
     inp = torch.empty(max_len, B, data_set.shape[1], device=data_set.device, dtype=torch.float32)
     pk.batch_assemble(data_set, desc.to(data_set.device, non_blocking=True), B, max_len, inp)
     return inp
+
+
+# ---- output side: forward-phase posterior writer -------------------------------------------------
+
+
+def load_counts(class_counts_file: str) -> np.ndarray:
+    """The senone counts file Kaldi's analyze-counts writes: one line `[ c0 c1 ... ]` (data_io.py:277-281)."""
+    with open(class_counts_file) as f:
+        row = next(f).strip().strip("[]").strip()
+    return np.array([np.float32(v) for v in row.split()])
+
+
+def write_kaldi_matrix(fd, key: str, m: np.ndarray) -> None:
+    """One entry of a binary Kaldi matrix archive: `key ` + "\0B" + "FM "/"DM " + \4 rows + \4 cols + row-major
+    payload — the byte stream data_io.write_mat produces (data_io.py:1200-1239); fd is a binary stream."""
+    if m.dtype == np.float32:
+        tag = b"FM "
+    elif m.dtype == np.float64:
+        tag = b"DM "
+    else:
+        raise TypeError(f"'{m.dtype}', please use 'float32' or 'float64'")
+    if m.ndim != 2:
+        raise ValueError("a Kaldi matrix has two axes")
+    if key != "":
+        fd.write((key + " ").encode("latin1"))
+    fd.write(b"\0B" + tag)
+    fd.write(b"\x04" + struct.pack("<I", m.shape[0]))
+    fd.write(b"\x04" + struct.pack("<I", m.shape[1]))
+    fd.write(np.ascontiguousarray(m).tobytes())
+
+
+def write_posteriors(fd, key: str, logp: torch.Tensor, counts: np.ndarray = None) -> None:
+    """core.py:660-671 for one sentence: optional prior normalisation `out - log(counts / sum(counts))` (on the
+    device, in place on a copy), device -> host, Kaldi ark entry."""
+    if not logp.is_cuda:
+        raise RuntimeError("pytorch-kaldi_b200: write_posteriors needs the posteriors on the device (no CPU path)")
+    out = logp.detach().float().contiguous()
+    if counts is not None:
+        out = out.clone()
+        log_prior = np.log(counts / np.sum(counts)).astype(np.float32)   # core.py:666-667, float32 like the reference
+        pk.sub_log_prior(out, torch.from_numpy(log_prior).to(out.device))
+    write_kaldi_matrix(fd, key, out.cpu().numpy())

@@ -339,6 +339,29 @@ def input_case(name, *, N, F, left, right, n_snt, batch, seed):
     print(f"{name}: data_set {data_set.shape} -> {path} ({os.path.getsize(path)/1e6:.2f} MB)")
 
 
+def ark_case(name, *, rows, cols, seed):
+    """Output side: prior normalisation (core.py:664-667) + the reference's own data_io.write_mat."""
+    import tempfile
+    import data_io as ref_io  # noqa: E402
+    rng = np.random.default_rng(seed)
+    logp = np.log(rng.dirichlet(np.ones(cols), rows)).astype(np.float32)
+    counts = rng.integers(5, 5000, cols).astype(np.float32)
+    with tempfile.TemporaryDirectory() as td:
+        cf = os.path.join(td, "counts")
+        with open(cf, "w") as f:
+            f.write("[ " + " ".join(str(int(c)) for c in counts) + " ]\n")
+        c2 = ref_io.load_counts(cf)
+        out_save = logp - np.log(c2 / np.sum(c2))                     # core.py:666-667
+        path = os.path.join(td, "post.ark")
+        with open(path, "wb") as fd:
+            ref_io.write_mat(td, fd, out_save, "utt_0001")           # core.py:670
+            ref_io.write_mat(td, fd, logp[:3], "utt_0002")
+        blob = np.frombuffer(open(path, "rb").read(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), logp=logp, counts=counts, ark=blob,
+                        meta=np.array(repr(dict(rows=rows, cols=cols))))
+    print(f"{name}: {blob.size} ark bytes")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     only = sys.argv[1:]  # optional: names of the fixtures to (re)generate
@@ -395,3 +418,6 @@ if __name__ == "__main__":
         input_case("input_cw", N=400, F=7, left=3, right=2, n_snt=8, batch=4, seed=81)
     if not only or "input_nocw" in only:
         input_case("input_nocw", N=300, F=5, left=0, right=0, n_snt=6, batch=3, seed=82)
+    # J: output side (prior-normalised posteriors -> Kaldi ark)
+    if not only or "post_ark" in only:
+        ark_case("post_ark", rows=11, cols=23, seed=91)

@@ -115,3 +115,22 @@ def test_batch_descriptors_follow_the_reference_bookkeeping():
             b, L, z = (int(v) for v in desc[:, k])
             assert np.array_equal(ref[z:z + L, k], ds[b:b + L])
             assert not ref[:z, k].any() and not ref[z + L:, k].any()
+
+
+def test_kaldi_matrix_writer_and_counts_reader(tmp_path):
+    """Host half of the posterior writer: pk_train.write_kaldi_matrix / load_counts against the reference-written archive
+    (the device half, the prior subtraction kernel, is covered by the GPU test)."""
+    import io
+    import numpy as np
+    import golden_util as gu
+    import pk_train
+    d = gu.load("post_ark")
+    cf = tmp_path / "counts"
+    cf.write_text("[ " + " ".join(str(int(c)) for c in d["counts"]) + " ]\n")
+    counts = pk_train.load_counts(str(cf))
+    assert counts.dtype == np.float32 and np.array_equal(counts, d["counts"])
+    out = d["logp"] - np.log(counts / np.sum(counts))
+    buf = io.BytesIO()
+    pk_train.write_kaldi_matrix(buf, "utt_0001", out)
+    pk_train.write_kaldi_matrix(buf, "utt_0002", d["logp"][:3])
+    assert buf.getvalue() == d["ark"].tobytes()

@@ -706,3 +706,16 @@ def test_gemm_tn_tiles_against_fp32(M, N, K):
         assert (C - want).abs().max().item() < 2e-5 * scale + 1e-4
         assert (stats[:, 0].float() - want.sum(1)).abs().max().item() < 1e-3 * scale
         assert abs(amax.view(torch.float32).item() - want.abs().max().item()) < 1e-4 * scale
+
+
+def test_posterior_writer_matches_reference_bytes():
+    """pk_train.write_posteriors (device-side prior subtraction + Kaldi ark entry) reproduces the archive the
+    reference's core.py:660-671 / data_io.write_mat wrote, byte for byte."""
+    import io
+    import pk_train
+    d = gu.load("post_ark")
+    logp = torch.from_numpy(d["logp"]).cuda()
+    buf = io.BytesIO()
+    pk_train.write_posteriors(buf, "utt_0001", logp, d["counts"])
+    pk_train.write_posteriors(buf, "utt_0002", logp[:3])
+    assert buf.getvalue() == d["ark"].tobytes()

@@ -256,3 +256,11 @@ def test_input_side_chunk_and_batch_assembly(name):
                                            rng.randint)
         assert inp.shape == d[f"inp{i}"].shape
         assert np.array_equal(inp, d[f"inp{i}"])
+
+
+def test_output_side_posterior_ark_bytes():
+    """prior normalisation (core.py:664-667) + data_io.write_mat (:1200-1239), byte for byte against an
+    archive written by the reference's own functions."""
+    d = gu.load("post_ark")
+    blob = (orc.posterior_ark_bytes("utt_0001", d["logp"], d["counts"]) + orc.posterior_ark_bytes("utt_0002", d["logp"][:3]))
+    assert blob == d["ark"].tobytes()
