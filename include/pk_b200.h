@@ -263,6 +263,12 @@ int pk_chunk_prepare(const float* fea, int64_t ldf, const int64_t* lab, int64_t 
 int pk_batch_assemble(const float* data_set, int64_t ldd, int D, const int64_t* desc, int batch_size, int max_len,
                       float* inp, void* stream);
 
+/* Kaldi CompressedMatrix ("CM ") payload -> fp32 on the device (data_io.py:1150-1196): col_headers
+ * [cols][4] uint16 percentiles (0/25/75/100), data [cols][rows] uint8 column-major, global min_value / range from the
+ * archive header; out [rows][ldo].  Bit-identical to the reference's numpy evaluation. */
+int pk_cm_decode(const void* col_headers, const void* data, float min_value, float range, int rows, int cols,
+                 float* out, int64_t ldo, void* stream);
+
 /* ---- output side of the path: forward-phase posteriors -> scaled log-likelihoods, in place:
  * logp[n][s] -= log_prior[s] with log_prior = log(counts / sum(counts)) (core.py:664-667); the result is what
  * data_io.write_mat stores as a Kaldi "FM" matrix (data_io.py:1200-1239). */

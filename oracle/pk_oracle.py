@@ -769,3 +769,18 @@ def posterior_ark_bytes(key, logp, counts=None):
     tag = {"float32": b"FM ", "float64": b"DM "}[str(out.dtype)]
     head = ((key + " ").encode("latin1") if key != "" else b"") + b"\0B" + tag
     return head + b"\x04" + struct.pack("<I", out.shape[0]) + b"\x04" + struct.pack("<I", out.shape[1]) + out.tobytes()
+
+
+def cm_decode(col_headers, data, globmin, globrange):
+    """Kaldi CompressedMatrix payload -> float32 [rows, cols] (data_io.py:1150-1196): col_headers [cols,4] uint16
+    percentiles, data [cols,rows] uint8 column-major; three linear segments per column (0..64, 65..192, 193..255)."""
+    globmin, globrange = np.float32(globmin), np.float32(globrange)
+    p = (col_headers.astype(np.uint16) * globrange * 1.52590218966964e-05 + globmin).astype(np.float32)
+    p0, p25, p75, p100 = (p[:, k].reshape(-1, 1) for k in range(4))
+    lo, hi = data <= 64, data > 192
+    mid = ~(lo | hi)
+    mat = np.zeros(data.shape, dtype=np.float32)
+    mat += (p0 + (p25 - p0) / 64.0 * data) * lo.astype(np.float32)
+    mat += (p25 + (p75 - p25) / 128.0 * (data - 64)) * mid.astype(np.float32)
+    mat += (p75 + (p100 - p75) / 63.0 * (data - 192)) * hi.astype(np.float32)
+    return mat.T

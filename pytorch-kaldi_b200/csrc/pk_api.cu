@@ -315,6 +315,12 @@ int pk_batch_assemble(const float* data_set, int64_t ldd, int D, const int64_t* 
   return batch_assemble(data_set, ldd, D, reinterpret_cast<const long long*>(desc), batch_size, max_len, inp,
                         static_cast<cudaStream_t>(stream));
 }
+int pk_cm_decode(const void* col_headers, const void* data, float min_value, float range, int rows, int cols, float* out,
+                 int64_t ldo, void* stream) {
+  PK_REQUIRE(col_headers && data && out, "pk_cm_decode: null pointer");
+  return cm_decode(static_cast<const uint16_t*>(col_headers), static_cast<const uint8_t*>(data), min_value, range, rows, cols, out,
+                   ldo, static_cast<cudaStream_t>(stream));
+}
 int pk_sub_log_prior(float* logp, int64_t ld, int64_t n, int S, const float* log_prior, void* stream) {
   PK_REQUIRE(logp && log_prior, "pk_sub_log_prior: null pointer");
   return rows_sub_vec(logp, ld, n, S, log_prior, static_cast<cudaStream_t>(stream));

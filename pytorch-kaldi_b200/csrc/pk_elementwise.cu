@@ -610,6 +610,32 @@ __global__ void batch_assemble_kernel(const float* __restrict__ data, long long 
   }
 }
 
+// input side: Kaldi CompressedMatrix "CM " payload -> fp32 (data_io.py:1150-1196).  hdr [cols][4] uint16
+// percentiles (0, 25, 75, 100), data [cols][rows] uint8 (column-major); out [rows][ldo].  Every operation is a
+// separately rounded fp32 op in the reference's order, so the result is bit-identical to its numpy evaluation.
+__global__ void cm_decode_kernel(const uint16_t* __restrict__ hdr, const uint8_t* __restrict__ data, float gmin, float grange,
+                                 int rows, int cols, float* __restrict__ out, long long ldo) {
+  const long long total = static_cast<long long>(rows) * cols;
+  for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total;
+       e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(e / rows);
+    const int r = static_cast<int>(e - static_cast<long long>(c) * rows);
+    float p[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      p[k] = __fadd_rn(__fmul_rn(__fmul_rn(static_cast<float>(hdr[4 * c + k]), grange), 1.52590218966964e-05f), gmin);
+    const unsigned d = data[e];
+    float v;
+    if (d <= 64u)
+      v = __fadd_rn(p[0], __fmul_rn(__fdiv_rn(__fsub_rn(p[1], p[0]), 64.0f), static_cast<float>(d)));
+    else if (d > 192u)
+      v = __fadd_rn(p[2], __fmul_rn(__fdiv_rn(__fsub_rn(p[3], p[2]), 63.0f), static_cast<float>(d - 192u)));
+    else
+      v = __fadd_rn(p[1], __fmul_rn(__fdiv_rn(__fsub_rn(p[2], p[1]), 128.0f), static_cast<float>(d - 64u)));
+    out[static_cast<long long>(r) * ldo + c] = v;
+  }
+}
+
 // output side: x[n][c] -= v[c]  (log-posteriors -> scaled log-likelihoods, core.py:664-667)
 __global__ void rows_sub_vec_kernel(float* __restrict__ x, long long ld, long long n, int C, const float* __restrict__ v) {
   const long long total = n * C;
@@ -771,6 +797,14 @@ int batch_assemble(const float* data, long long ldd, int D, const long long* des
   PK_REQUIRE(Bsz > 0 && max_len > 0 && D > 0, "batch_assemble: bad sizes");
   batch_assemble_kernel<<<grid_for(static_cast<long long>(max_len) * Bsz * D, 1024), 256, 0, stream>>>(data, ldd, D, desc, Bsz,
                                                                                                      max_len, inp);
+  PK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int cm_decode(const uint16_t* hdr, const uint8_t* data, float gmin, float grange, int rows, int cols, float* out, long long ldo,
+              cudaStream_t stream) {
+  PK_REQUIRE(rows > 0 && cols > 0, "cm_decode: empty matrix");
+  cm_decode_kernel<<<grid_for(static_cast<long long>(rows) * cols, 1024), 256, 0, stream>>>(hdr, data, gmin, grange, rows, cols, out,
+                                                                                          ldo);
   PK_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -285,6 +285,8 @@ int chunk_prepare(const float* fea, long long ldf, const long long* lab, long lo
                   int right, double* stats, float* out, long long ldo, cudaStream_t stream);
 int batch_assemble(const float* data, long long ldd, int D, const long long* desc, int Bsz, int max_len, float* inp,
                    cudaStream_t stream);
+int cm_decode(const uint16_t* hdr, const uint8_t* data, float gmin, float grange, int rows, int cols, float* out, long long ldo,
+              cudaStream_t stream);
 int rows_sub_vec(float* x, long long ld, long long n, int C, const float* v, cudaStream_t stream);
 int adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float wd,
               long long step, float gscale, cudaStream_t stream);

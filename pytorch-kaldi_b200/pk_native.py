@@ -62,6 +62,7 @@ SIGNATURES = {
     "pk_rmsprop_step": [_c_p, _c_p, _c_p, _c_i64, _c_f, _c_f, _c_f, _c_f, _c_p],
     "pk_chunk_prepare": [_c_p, _c_i64, _c_p, _c_i64, _c_i64, _c_int, _c_int, _c_int, _c_p, _c_p, _c_i64, _c_p],
     "pk_batch_assemble": [_c_p, _c_i64, _c_int, _c_p, _c_int, _c_int, _c_p, _c_p],
+    "pk_cm_decode": [_c_p, _c_p, _c_f, _c_f, _c_int, _c_int, _c_p, _c_i64, _c_p],
     "pk_sub_log_prior": [_c_p, _c_i64, _c_i64, _c_int, _c_p, _c_p],
     "pk_adam_step": [_c_p, _c_p, _c_p, _c_p, _c_i64, _c_f, _c_f, _c_f, _c_f, _c_f, _c_i64, _c_f, _c_p],
     "pk_sgd_step": [_c_p, _c_p, _c_i64, _c_f, _c_f, _c_p],
@@ -98,7 +99,7 @@ KERNELS_PER_CALL = {"pk_dense_act_fwd": 1, "pk_dense_act_bwd": 1, "pk_amax_final
                     "pk_bn_finalize": 1, "pk_fill_scale_shift": 1, "pk_bn_bwd": 2, "pk_rnn_layer_fwd": 1,
                     "pk_rnn_layer_bwd": 1, "pk_rnn_step_fwd": 1, "pk_rnn_step_bwd": 1, "pk_rowln_fwd": 1, "pk_conv_ln0_bwd": 1,
                     "pk_sinc_filters_fwd": 1, "pk_sinc_filters_bwd": 1, "pk_conv_pack_weights": 1, "pk_conv_im2col0": 1,
-                    "pk_conv_im2col_t": 1, "pk_conv_post_fwd": 1, "pk_conv_post_bwd": 1, "pk_logsoftmax_nll": 1, "pk_logsoftmax_bwd": 1, "pk_rmsprop_step": 1, "pk_adam_step": 1, "pk_chunk_prepare": 2, "pk_batch_assemble": 1, "pk_sub_log_prior": 1,
+                    "pk_conv_im2col_t": 1, "pk_conv_post_fwd": 1, "pk_conv_post_bwd": 1, "pk_logsoftmax_nll": 1, "pk_logsoftmax_bwd": 1, "pk_rmsprop_step": 1, "pk_adam_step": 1, "pk_chunk_prepare": 2, "pk_batch_assemble": 1, "pk_sub_log_prior": 1, "pk_cm_decode": 1,
                     "pk_sgd_step": 1}
 
 
@@ -293,6 +294,11 @@ def chunk_prepare(fea, lab, lab_min, left, right, out):
 def batch_assemble(data_set, desc, batch_size, max_len, inp):
     _check(lib().pk_batch_assemble(_ptr(data_set), data_set.stride(0), data_set.shape[1], _ptr(desc), batch_size, max_len,
                                    _ptr(inp), _stream()), "pk_batch_assemble")
+
+
+def cm_decode(col_headers, data, min_value, rng, rows, cols, out):
+    _check(lib().pk_cm_decode(_ptr(col_headers), _ptr(data), float(min_value), float(rng), rows, cols, _ptr(out), out.stride(0),
+                              _stream()), "pk_cm_decode")
 
 
 def sub_log_prior(logp, log_prior):

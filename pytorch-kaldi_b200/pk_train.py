@@ -184,3 +184,72 @@ def write_posteriors(fd, key: str, logp: torch.Tensor, counts: np.ndarray = None
         log_prior = np.log(counts / np.sum(counts)).astype(np.float32)   # core.py:666-667, float32 like the reference
         pk.sub_log_prior(out, torch.from_numpy(log_prior).to(out.device))
     write_kaldi_matrix(fd, key, out.cpu().numpy())
+
+
+# ---- input side: Kaldi archive reader -------------------------------------------------------------
+
+
+def _read_key(fd):
+    """Utterance key in front of every archive entry (data_io.py:762-778); None at end of file."""
+    key = b""
+    while True:
+        ch = fd.read(1)
+        if ch == b"" or ch == b" ":
+            break
+        key += ch
+    key = key.decode("latin1").strip()
+    return key or None
+
+
+def read_mat_ark(fd, device=None):
+    """Generator of (key, matrix) over a binary Kaldi matrix archive (data_io.py:1062-1131): "FM " / "DM " payloads are
+    returned as numpy arrays (or moved to `device`); "CM " (CompressedMatrix) payloads are uploaded as bytes and decoded
+    on the GPU (`pk_cm_decode`), which needs `device`."""
+    while True:
+        key = _read_key(fd)
+        if key is None:
+            return
+        if fd.read(2) != b"\0B":
+            raise ValueError("only binary Kaldi archives are supported")
+        header = fd.read(3).decode()
+        if header == "CM ":
+            gmin, grange, rows, cols = np.frombuffer(fd.read(16), dtype="float32,float32,int32,int32", count=1)[0]
+            hdr = np.frombuffer(fd.read(int(cols) * 8), dtype=np.uint16).copy()
+            data = np.frombuffer(fd.read(int(cols) * int(rows)), dtype=np.uint8).copy()
+            if device is None:
+                raise RuntimeError("pytorch-kaldi_b200: compressed matrices are decoded on the GPU (pass device=; no CPU path)")
+            out = torch.empty(int(rows), int(cols), device=device, dtype=torch.float32)
+            pk.cm_decode(torch.from_numpy(hdr.view(np.int16)).to(device), torch.from_numpy(data).to(device), gmin, grange,
+                         int(rows), int(cols), out)
+            yield key, out
+            continue
+        if header == "FM ":
+            dt = np.float32
+        elif header == "DM ":
+            dt = np.float64
+        else:
+            raise ValueError(f"The header contained '{header}'")
+        _, rows, _, cols = np.frombuffer(fd.read(10), dtype="int8,int32,int8,int32", count=1)[0]
+        mat = np.frombuffer(fd.read(int(rows) * int(cols) * np.dtype(dt).itemsize), dtype=dt).reshape(int(rows), int(cols))
+        yield key, (torch.from_numpy(mat.copy()).to(device) if device is not None else mat)
+
+
+def read_vec_int_ark(fd):
+    """Generator of (key, int32 vector) over a binary Kaldi integer-vector archive — alignments (data_io.py:790-836):
+    "\0B", \4, int32 length, then (int8 size = 4, int32 value) pairs."""
+    while True:
+        key = _read_key(fd)
+        if key is None:
+            return
+        if fd.read(2) != b"\0B":
+            raise ValueError("only binary Kaldi archives are supported")
+        if fd.read(1) != b"\x04":
+            raise ValueError("bad integer-vector header")
+        n = int(np.frombuffer(fd.read(4), dtype="int32", count=1)[0])
+        if n == 0:
+            yield key, np.array([], dtype="int32")
+            continue
+        vec = np.frombuffer(fd.read(n * 5), dtype=[("size", "int8"), ("value", "int32")], count=n)
+        if vec[0]["size"] != 4:
+            raise ValueError("integer vector with a non-int32 element size")
+        yield key, vec["value"].copy()

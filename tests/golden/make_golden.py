@@ -362,6 +362,44 @@ def ark_case(name, *, rows, cols, seed):
     print(f"{name}: {blob.size} ark bytes")
 
 
+def ark_read_case(name, *, seed):
+    """Input side: a binary feature archive (FM, DM and CM entries; the CM bytes are laid out per
+    kaldi/src/matrix/compressed-matrix.h) and an alignment archive, decoded by the reference's own readers."""
+    import io
+    import struct
+    import data_io as ref_io  # noqa: E402
+    rng = np.random.default_rng(seed)
+    fm = rng.standard_normal((9, 6)).astype(np.float32)
+    dm = rng.standard_normal((4, 5))
+    rows, cols = 37, 13
+    gmin, grange = np.float32(-7.5), np.float32(19.25)
+    pct = np.sort(rng.integers(0, 65536, (cols, 4)), axis=1).astype(np.uint16)
+    data = rng.integers(0, 256, (cols, rows)).astype(np.uint8)
+    data[:, :6] = [0, 64, 65, 192, 193, 255]  # segment boundaries
+    import tempfile
+    alis = {"utt_a": rng.integers(0, 1936, 23).astype(np.int32), "utt_b": rng.integers(0, 1936, 1).astype(np.int32)}
+    with tempfile.TemporaryDirectory() as td:
+        fp, ap = os.path.join(td, "feats.ark"), os.path.join(td, "ali.ark")
+        with open(fp, "wb") as buf:
+            ref_io.write_mat(td, buf, fm, "utt_fm")
+            ref_io.write_mat(td, buf, dm, "utt_dm")
+            buf.write(b"utt_cm \0BCM " + struct.pack("<ffii", gmin, grange, rows, cols) + pct.tobytes() + data.tobytes())
+        with open(ap, "wb") as abuf:
+            for k, v in alis.items():
+                ref_io.write_vec_int(abuf, td, v, key=k)
+        feats, ali_bytes = open(fp, "rb").read(), open(ap, "rb").read()
+        dec = {k: np.array(m) for k, m in ref_io.read_mat_ark(fp, td)}
+        dec_ali = {k: np.array(v) for k, v in ref_io.read_vec_int_ark(ap, td)}
+    out = dict(feats=np.frombuffer(feats, dtype=np.uint8), alis=np.frombuffer(ali_bytes, dtype=np.uint8),
+               cm_pct=pct, cm_data=data, cm_min=gmin, cm_range=grange, meta=np.array(repr(dict(rows=rows, cols=cols))))
+    for k, m in dec.items():
+        out["mat." + k] = m
+    for k, v in dec_ali.items():
+        out["ali." + k] = v
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(f"{name}: {len(feats)} feature bytes, {len(ali_bytes)} alignment bytes, entries {list(dec)} {list(dec_ali)}")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     only = sys.argv[1:]  # optional: names of the fixtures to (re)generate
@@ -421,3 +459,6 @@ if __name__ == "__main__":
     # J: output side (prior-normalised posteriors -> Kaldi ark)
     if not only or "post_ark" in only:
         ark_case("post_ark", rows=11, cols=23, seed=91)
+    # K: input side (Kaldi archive reader incl. compressed matrices)
+    if not only or "ark_read" in only:
+        ark_read_case("ark_read", seed=95)

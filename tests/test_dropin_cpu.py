@@ -134,3 +134,25 @@ def test_kaldi_matrix_writer_and_counts_reader(tmp_path):
     pk_train.write_kaldi_matrix(buf, "utt_0001", out)
     pk_train.write_kaldi_matrix(buf, "utt_0002", d["logp"][:3])
     assert buf.getvalue() == d["ark"].tobytes()
+
+
+def test_kaldi_archive_readers_host_side():
+    """pk_train.read_mat_ark (FM / DM entries) and read_vec_int_ark against what the reference's readers return for
+    the same bytes; a compressed entry without a device is refused loudly (it is decoded on the GPU)."""
+    import io
+    import numpy as np
+    import pytest
+    import golden_util as gu
+    import pk_train
+    d = gu.load("ark_read")
+    it = pk_train.read_mat_ark(io.BytesIO(d["feats"].tobytes()))
+    k, m = next(it)
+    assert k == "utt_fm" and m.dtype == np.float32 and np.array_equal(m, d["mat.utt_fm"])
+    k, m = next(it)
+    assert k == "utt_dm" and m.dtype == np.float64 and np.array_equal(m, d["mat.utt_dm"])
+    with pytest.raises(RuntimeError):
+        next(it)
+    alis = dict(pk_train.read_vec_int_ark(io.BytesIO(d["alis"].tobytes())))
+    assert list(alis) == ["utt_a", "utt_b"]
+    for k, v in alis.items():
+        assert v.dtype == np.int32 and np.array_equal(v, d["ali." + k])

@@ -719,3 +719,16 @@ def test_posterior_writer_matches_reference_bytes():
     pk_train.write_posteriors(buf, "utt_0001", logp, d["counts"])
     pk_train.write_posteriors(buf, "utt_0002", logp[:3])
     assert buf.getvalue() == d["ark"].tobytes()
+
+
+def test_kaldi_archive_reader_with_device_cm_decode():
+    """pk_train.read_mat_ark with device=cuda: FM / DM entries and the CompressedMatrix entry (pk_cm_decode) equal the
+    reference reader's output bit for bit."""
+    import io
+    import pk_train
+    d = gu.load("ark_read")
+    got = dict(pk_train.read_mat_ark(io.BytesIO(d["feats"].tobytes()), device="cuda"))
+    assert list(got) == ["utt_fm", "utt_dm", "utt_cm"]
+    for k, m in got.items():
+        assert m.is_cuda
+        assert np.array_equal(m.cpu().numpy(), d["mat." + k]), k

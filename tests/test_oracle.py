@@ -264,3 +264,11 @@ def test_output_side_posterior_ark_bytes():
     d = gu.load("post_ark")
     blob = (orc.posterior_ark_bytes("utt_0001", d["logp"], d["counts"]) + orc.posterior_ark_bytes("utt_0002", d["logp"][:3]))
     assert blob == d["ark"].tobytes()
+
+
+def test_input_side_compressed_matrix_decode():
+    """Kaldi CompressedMatrix decode (data_io.py:1150-1196) against the reference's own reader, bit exact."""
+    d = gu.load("ark_read")
+    got = orc.cm_decode(d["cm_pct"], d["cm_data"], d["cm_min"], d["cm_range"])
+    assert got.dtype == np.float32 and got.shape == d["mat.utt_cm"].shape
+    assert np.array_equal(got, d["mat.utt_cm"])
