@@ -201,6 +201,32 @@ def _read_key(fd):
     return key or None
 
 
+def _read_binary_matrix(fd, device=None):
+    """One binary Kaldi matrix at the stream position (after the key): "\0B" + "FM " / "DM " / "CM " (data_io.py:1087-1196)."""
+    if fd.read(2) != b"\0B":
+        raise ValueError("only binary Kaldi matrices are supported")
+    header = fd.read(3).decode()
+    if header == "CM ":
+        gmin, grange, rows, cols = np.frombuffer(fd.read(16), dtype="float32,float32,int32,int32", count=1)[0]
+        hdr = np.frombuffer(fd.read(int(cols) * 8), dtype=np.uint16).copy()
+        data = np.frombuffer(fd.read(int(cols) * int(rows)), dtype=np.uint8).copy()
+        if device is None:
+            raise RuntimeError("pytorch-kaldi_b200: compressed matrices are decoded on the GPU (pass device=; no CPU path)")
+        out = torch.empty(int(rows), int(cols), device=device, dtype=torch.float32)
+        pk.cm_decode(torch.from_numpy(hdr.view(np.int16)).to(device), torch.from_numpy(data).to(device), gmin, grange,
+                     int(rows), int(cols), out)
+        return out
+    if header == "FM ":
+        dt = np.float32
+    elif header == "DM ":
+        dt = np.float64
+    else:
+        raise ValueError(f"The header contained '{header}'")
+    _, rows, _, cols = np.frombuffer(fd.read(10), dtype="int8,int32,int8,int32", count=1)[0]
+    mat = np.frombuffer(fd.read(int(rows) * int(cols) * np.dtype(dt).itemsize), dtype=dt).reshape(int(rows), int(cols))
+    return torch.from_numpy(mat.copy()).to(device) if device is not None else mat
+
+
 def read_mat_ark(fd, device=None):
     """Generator of (key, matrix) over a binary Kaldi matrix archive (data_io.py:1062-1131): "FM " / "DM " payloads are
     returned as numpy arrays (or moved to `device`); "CM " (CompressedMatrix) payloads are uploaded as bytes and decoded
@@ -209,29 +235,25 @@ def read_mat_ark(fd, device=None):
         key = _read_key(fd)
         if key is None:
             return
-        if fd.read(2) != b"\0B":
-            raise ValueError("only binary Kaldi archives are supported")
-        header = fd.read(3).decode()
-        if header == "CM ":
-            gmin, grange, rows, cols = np.frombuffer(fd.read(16), dtype="float32,float32,int32,int32", count=1)[0]
-            hdr = np.frombuffer(fd.read(int(cols) * 8), dtype=np.uint16).copy()
-            data = np.frombuffer(fd.read(int(cols) * int(rows)), dtype=np.uint8).copy()
-            if device is None:
-                raise RuntimeError("pytorch-kaldi_b200: compressed matrices are decoded on the GPU (pass device=; no CPU path)")
-            out = torch.empty(int(rows), int(cols), device=device, dtype=torch.float32)
-            pk.cm_decode(torch.from_numpy(hdr.view(np.int16)).to(device), torch.from_numpy(data).to(device), gmin, grange,
-                         int(rows), int(cols), out)
-            yield key, out
-            continue
-        if header == "FM ":
-            dt = np.float32
-        elif header == "DM ":
-            dt = np.float64
-        else:
-            raise ValueError(f"The header contained '{header}'")
-        _, rows, _, cols = np.frombuffer(fd.read(10), dtype="int8,int32,int8,int32", count=1)[0]
-        mat = np.frombuffer(fd.read(int(rows) * int(cols) * np.dtype(dt).itemsize), dtype=dt).reshape(int(rows), int(cols))
-        yield key, (torch.from_numpy(mat.copy()).to(device) if device is not None else mat)
+        yield key, _read_binary_matrix(fd, device)
+
+
+def read_mat_scp(scp_path, device=None):
+    """Generator of (key, matrix) over a Kaldi script file, one `key path[:offset]` per line (data_io.py:1039-1059,
+    offsets as open_or_fd handles them, :696-716)."""
+    with open(scp_path) as scp:
+        for line in scp:
+            if not line.strip():
+                continue
+            key, rx = line.strip().split(None, 1)
+            offset = None
+            if ":" in rx and rx.rsplit(":", 1)[1].isdigit():
+                rx, off = rx.rsplit(":", 1)
+                offset = int(off)
+            with open(rx, "rb") as fd:
+                if offset is not None:
+                    fd.seek(offset)
+                yield key, _read_binary_matrix(fd, device)
 
 
 def read_vec_int_ark(fd):

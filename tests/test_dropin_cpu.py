@@ -156,3 +156,24 @@ def test_kaldi_archive_readers_host_side():
     assert list(alis) == ["utt_a", "utt_b"]
     for k, v in alis.items():
         assert v.dtype == np.int32 and np.array_equal(v, d["ali." + k])
+
+
+def test_kaldi_scp_reader(tmp_path):
+    """pk_train.read_mat_scp: `key path:offset` lines (data_io.py:1039-1059 / :696-716) into the same archive bytes."""
+    import numpy as np
+    import golden_util as gu
+    import pk_train
+    d = gu.load("ark_read")
+    blob = d["feats"].tobytes()
+    ark = tmp_path / "feats.ark"
+    ark.write_bytes(blob)
+    lines = []
+    for key in ("utt_fm", "utt_dm"):
+        off = blob.index(key.encode() + b" ") + len(key) + 1
+        lines.append(f"{key} {ark}:{off}")
+    scp = tmp_path / "feats.scp"
+    scp.write_text("\n".join(reversed(lines)) + "\n")      # random access: order differs from the archive
+    got = dict(pk_train.read_mat_scp(str(scp)))
+    assert list(got) == ["utt_dm", "utt_fm"]
+    for k, m in got.items():
+        assert np.array_equal(m, d["mat." + k])
