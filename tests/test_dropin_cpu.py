@@ -177,3 +177,27 @@ def test_kaldi_scp_reader(tmp_path):
     assert list(got) == ["utt_dm", "utt_fm"]
     for k, m in got.items():
         assert np.array_equal(m, d["mat." + k])
+
+
+def test_c_abi_error_convention_without_gpu():
+    """SURVEY 8b error convention: every entry point returns an int status (0 = ok), never aborts, and leaves a
+    thread-local message for pk_last_error().  Argument validation happens before any device work, so it can be
+    exercised in this GPU-less container."""
+    import ctypes
+    L = pk_native.lib()
+    rc = L.pk_gemm_tn(0, 0, 8, 8, None, 8, 0, 0, None, 8, 0, 0, None, 8, None, 0, None, 1.0, None, 0, 1, None, None)
+    assert rc != 0 and b"null operand" in L.pk_last_error()
+    rc = L.pk_rnn_layer_fwd(7, 4, 2, 8, 1, 0, None, 8, None, None, None, None, 1.0, None, 8, None, 8, None, None, None, None,
+                            None, 8, None)
+    assert rc != 0 and b"not implemented" in L.pk_last_error()
+    rc = L.pk_rnn_step_fwd(4, 4, 2, 8, 3, 0, None, 8, None, None, None, None, 1.0, None, 8, None, 8, None, None, None, None,
+                           None, None, None, None, None, 8, None, 0, None)
+    assert rc != 0 and L.pk_last_error() != b""
+    rc = L.pk_sinc_filters_fwd(None, None, 4, 8, 16000.0, 50.0, 50.0, None, None)
+    assert rc != 0 and b"null pointer" in L.pk_last_error()
+    rc = L.pk_adam_step(None, None, None, None, 10, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1, 1.0, None)
+    assert rc != 0 and b"null pointer" in L.pk_last_error()
+    # the Python shim turns the status into RuntimeError with that message
+    with pytest.raises(RuntimeError, match="null operand"):
+        pk_native._check(L.pk_gemm_tn(0, 0, 8, 8, None, 8, 0, 0, None, 8, 0, 0, None, 8, None, 0, None, 1.0, None, 0, 1, None,
+                                      None), "pk_gemm_tn")
