@@ -110,18 +110,23 @@ class LiGRUStackFn(torch.autograd.Function):
         ngr, ngk = _real_gates(cfg.cell), _kernel_gates(cfg.cell)
 
         saved = []  # per layer dict of tensors needed by backward
-        pi = 0
         xsrc, ldx = _rows_view(x, T, B)
+        main = torch.cuda.current_stream(dev)
+        side = _side_stream(dev)
+
+        # ---- weight-only work of ALL layers up front: fp16 / transposed copies of the stacked projection weights
+        # and the stacked recurrent weights depend on parameters only, so layers 1.. are prepared on the side stream
+        # while layer 0's recurrence (80 of 148 SMs) runs; each layer waits on its own event.
+        packs = []
+        pi = 0
         D = D0
-        X16 = XT16 = None
-        y32 = None
+        if OVERLAP_WGRAD:
+            side.wait_stream(main)   # parameters were last written (optimizer) on the main stream
         for li, L in enumerate(cfg.layers):
             H = L.H
             ws_, us_ = list(params[pi:pi + ngr]), list(params[pi + ngr:pi + 2 * ngr])
             pi += 2 * ngr
-            for _ in range(ngk - ngr):  # RNN: the update-gate block is all zeros (and pinned to 0 in the kernel)
-                ws_.append(torch.zeros_like(ws_[0]))
-                us_.append(torch.zeros_like(us_[0]))
+            gammas = betas = biases = None
             if L.use_bn:
                 bnp = params[pi:pi + 2 * ngr]
                 pi += 2 * ngr
@@ -130,19 +135,48 @@ class LiGRUStackFn(torch.autograd.Function):
             else:
                 biases = list(params[pi:pi + ngr])
                 pi += ngr
-                biases += [torch.zeros_like(biases[0]) for _ in range(ngk - ngr)]
+            CG = ngk * H
+            ldD, ldG = pad8(D), pad8(CG)
+            on_side = OVERLAP_WGRAD and li > 0
+            with torch.cuda.stream(side if on_side else main):
+                for _ in range(ngk - ngr):  # RNN: the update-gate block is all zeros (and pinned to 0 in the kernel)
+                    ws_.append(torch.zeros_like(ws_[0]))
+                    us_.append(torch.zeros_like(us_[0]))
+                Wcat = torch.cat(ws_, 0).contiguous()
+                W16 = torch.empty(CG, ldD, **f16)
+                WT16 = torch.empty(D, ldG, **f16) if need_grad else None
+                pk.transpose_f32(Wcat, D, CG, D, outT16=WT16, ldo16=ldG, in16=W16, ldi16=ldD)
+                U = torch.cat(us_, 0).contiguous()
+                bias_cat = None
+                if biases is not None:
+                    bias_cat = torch.cat(biases + [torch.zeros_like(biases[0]) for _ in range(ngk - ngr)]).contiguous()
+                ev = None
+                if on_side:
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    for t in (Wcat, W16, WT16, U, bias_cat):
+                        if t is not None:
+                            t.record_stream(main)   # allocated under the side stream, consumed on the main one
+            packs.append(dict(W16=W16, WT16=WT16, U=U, gammas=gammas, betas=betas, bias_cat=bias_cat, ev=ev))
+            D = ndir * H
+
+        D = D0
+        X16 = XT16 = None
+        y32 = None
+        for li, L in enumerate(cfg.layers):
+            H = L.H
+            pkd = packs[li]
+            W16, WT16, gammas, betas = pkd["W16"], pkd["WT16"], pkd["gammas"], pkd["betas"]
+            if pkd["ev"] is not None:
+                main.wait_event(pkd["ev"])
             CG = ngk * H
             ldD = pad8(D)
-            # ---- operands: fp16 copies of the layer input and of the stacked projection weights
+            ldG = pad8(CG)
+            # ---- operands: fp16 copy of the layer input (layer 0; deeper layers read the previous layer's fp16 outputs)
             if li == 0:
                 X16 = torch.empty(TB, ldD, **f16)
                 XT16 = torch.empty(D, ldt, **f16) if need_grad else None
                 pk.transpose_f32(xsrc, ldx, TB, D, outT16=XT16, ldo16=ldt, in16=X16, ldi16=ldD)
-            Wcat = torch.cat(ws_, 0).contiguous()
-            W16 = torch.empty(CG, ldD, **f16)
-            ldG = pad8(CG)
-            WT16 = torch.empty(D, ldG, **f16) if need_grad else None
-            pk.transpose_f32(Wcat, D, CG, D, outT16=WT16, ldo16=ldG, in16=W16, ldi16=ldD)
             # ---- projection PT = [W_g] X^T (channel-major) with BatchNorm statistics in the epilogue
             PT = torch.empty(CG, ldt, **f32)
             bn_train = L.use_bn and L.bn_training
@@ -165,9 +199,9 @@ class LiGRUStackFn(torch.autograd.Function):
                                    scale[sl], shift[sl], mean[sl], rstd[sl])
                 gamma = torch.cat(gammas + [torch.ones_like(gammas[0]) for _ in range(ngk - ngr)]).contiguous()
             else:
-                pk.fill_scale_shift(torch.cat(biases).contiguous(), CG, scale, shift)
+                pk.fill_scale_shift(pkd["bias_cat"], CG, scale, shift)
             # ---- the recurrence
-            U = torch.cat(us_, 0).contiguous()
+            U = pkd["U"]
             F = ndir * H
             last = li == len(cfg.layers) - 1
             ldF = pad8(F)
