@@ -58,9 +58,12 @@ extern "C" {
 #define PK_REC_SYNC_BARRIER 0x2000
 /* use the non-warp-specialised kernels (A/B timing; they also write the fp32 GT buffer) */
 #define PK_REC_LEGACY 0x4000
+/* use the round-1 warp-specialised mma.sync kernels instead of the tcgen05 ones (A/B timing; H <= 560) */
+#define PK_REC_WS 0x8000
 /* timing experiments only (results are incomplete): skip the global stores / loads */
 #define PK_REC_DBG_NOSTORE 0x10000
 #define PK_REC_DBG_NOLOAD 0x20000
+#define PK_REC_DBG_NOPROXYFENCE 0x40000 /* tcgen05 kernels: no fence.proxy.async between chunk arrival and its MMAs */
 
 const char* pk_last_error(void);
 int pk_version(void);

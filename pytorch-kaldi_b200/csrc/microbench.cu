@@ -1,0 +1,447 @@
+// microbench.cu — design probes for the persistent recurrent kernels (GPU box only; not product code).
+//
+// Measures, on the real part, the three quantities the tcgen05 recurrent design depends on:
+//   A. all-to-all exchange inside a thread-block cluster with st.async (16-byte messages + complete_tx)
+//   B. the same exchange with one cp.async.bulk shared::cta -> shared::cluster copy per destination
+//   C. latency of a dependent tcgen05 chain: K/16 x (M=128, N, K=16) MMAs -> commit -> mbarrier ->
+//      tcgen05.ld of the accumulator -> hand the buffer back to the issuer
+// Results are printed as cycles per step; profiles/r2_microbench.txt keeps the log the design cites.
+#include "pk_common.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+using namespace pk;
+
+#define CK(x)                                                                          \
+  do {                                                                                 \
+    cudaError_t e_ = (x);                                                              \
+    if (e_ != cudaSuccess) {                                                           \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      exit(2);                                                                         \
+    }                                                                                  \
+  } while (0)
+
+__device__ __forceinline__ bool wait_bounded(uint64_t* bar, uint32_t parity, bool cluster_scope) {
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    if (cluster_scope)
+      asm volatile(
+          "{\n\t.reg .pred P;\n\t"
+          "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, P;\n\t}\n"
+          : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    else
+      ok = mbar_try_wait(bar, parity) ? 1u : 0u;
+    if (ok) return true;
+    if (clock64() - t0 > 400000000LL) return false;  // ~0.2 s: bail out instead of hanging the box
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// A / B: cluster all-to-all.  Every CTA sends `bytes` to each of the CL CTAs (itself included) per step and
+// waits until it has received CL * bytes.  mode 0: st.async 16-byte messages from 128 threads; mode 1: one
+// bulk copy per destination issued by lanes of warp 0 after a proxy fence.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxBytes = 4096;
+constexpr int kMaxCL = 16;
+
+struct XSmem {
+  uint8_t buf[2][kMaxCL][kMaxBytes];
+  uint8_t stage[kMaxBytes];
+  uint64_t bar[2];
+};
+
+__global__ void __launch_bounds__(256, 1) exchange_kernel(int CL, int bytes, int steps, int mode, long long* out,
+                                                            int* fail) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  XSmem& sm = *reinterpret_cast<XSmem*>(smem_raw);
+  const uint32_t crank = cluster_ctarank();
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(&sm.bar[0], 1);
+    mbar_init(&sm.bar[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  cluster_sync_all();
+  const int nmsg = bytes / 16;
+  long long t0 = 0;
+  bool ok = true;
+  for (int k = 0; k < steps && ok; ++k) {
+    if (k == 16 && tid == 0) t0 = clock64();
+    const int nxt = (k + 1) & 1;
+    if (tid == 0) mbar_arrive_expect_tx(&sm.bar[nxt], static_cast<uint32_t>(CL * bytes));
+    if (mode == 0) {
+      if (tid < 128) {
+        for (int m = tid; m < nmsg; m += 128) {
+          const uint4 v = make_uint4(k, m, crank, tid);
+          const uint32_t laddr = smem_u32(&sm.buf[nxt][crank][m * 16]);
+          const uint32_t lbar = smem_u32(&sm.bar[nxt]);
+          for (int dst = 0; dst < CL; ++dst) st_async_v4(mapa_shared(laddr, dst), v, mapa_shared(lbar, dst));
+        }
+      }
+    } else {
+      if (tid < 128) {
+        for (int m = tid; m < nmsg; m += 128)
+          *reinterpret_cast<uint4*>(&sm.stage[m * 16]) = make_uint4(k, m, crank, tid);
+        fence_proxy_async_smem();
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (tid < CL) {
+        const uint32_t dst_addr = mapa_shared(smem_u32(&sm.buf[nxt][crank][0]), tid);
+        const uint32_t dst_bar = mapa_shared(smem_u32(&sm.bar[nxt]), tid);
+        asm volatile(
+            "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_addr),
+            "r"(smem_u32(&sm.stage[0])), "r"(bytes), "r"(dst_bar)
+            : "memory");
+      }
+    }
+    // everyone waits for the full incoming vector of this step
+    ok = wait_bounded(&sm.bar[nxt], (k >> 1) & 1, true);
+    if (mode == 1) __syncthreads();  // staging buffer reuse
+  }
+  if (!ok && tid == 0) atomicAdd(fail, 1);
+  if (tid == 0 && blockIdx.x == 0) out[0] = clock64() - t0;
+  cluster_sync_all();
+}
+
+static void run_exchange(int CL, int bytes, int mode, int nclusters) {
+  const int steps = 2016;
+  long long* d_out;
+  int* d_fail;
+  CK(cudaMalloc(&d_out, 64));
+  CK(cudaMalloc(&d_fail, 4));
+  CK(cudaMemset(d_fail, 0, 4));
+  CK(cudaFuncSetAttribute(exchange_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(XSmem) + 1024));
+  CK(cudaFuncSetAttribute(exchange_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nclusters * CL, 1, 1);
+  cfg.blockDim = dim3(256, 1, 1);
+  cfg.dynamicSmemBytes = sizeof(XSmem) + 1024;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CK(cudaLaunchKernelEx(&cfg, exchange_kernel, CL, bytes, steps, mode, d_out, d_fail));
+  CK(cudaDeviceSynchronize());
+  long long cyc;
+  int fail;
+  CK(cudaMemcpy(&cyc, d_out, 8, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&fail, d_fail, 4, cudaMemcpyDeviceToHost));
+  const double per = double(cyc) / (steps - 16);
+  printf("exchange %-8s CL=%2d clusters=%2d bytes/src=%4d in/step=%6d B : %8.1f cyc/step  (%.1f B/cyc in)%s\n",
+         mode ? "bulk" : "st.async", CL, nclusters, bytes, CL * bytes, per, CL * bytes / per, fail ? "  TIMEOUT" : "");
+  cudaFree(d_out);
+  cudaFree(d_fail);
+}
+
+// ------------------------------------------------------------------------------------------------
+// C: dependent tcgen05 chain.  A = [128 x K] fp16 resident in shared memory (128-byte-swizzled K-major chunks of
+// 64), B = [N x K]; per iteration the issuer fires K/16 MMAs + commit, four epilogue warps wait, tcgen05.ld the
+// [128 x N] fp32 accumulator, and arrive on `done`, which the issuer waits on before the next iteration.
+// ------------------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(192, 1) umma_chain_kernel(int kchunks, int iters, long long* out, float* sink) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int sch = kchunks < 9 ? kchunks : 9;             // chunks resident in shared memory (longer chains wrap)
+  uint8_t* sA = smem;                                   // sch x 16 KB
+  uint8_t* sB = smem + sch * 16384;                     // sch x N*128 B
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + sch * N * 128);
+  uint64_t* full = bars;       // accumulator ready
+  uint64_t* done = bars + 1;   // epilogue finished (4 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < sch * (16384 + N * 128) / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;  // fp16 1.0 pairs
+  if (threadIdx.x == 0) {
+    mbar_init(full, 1);
+    mbar_init(done, 4);
+    fence_mbar_init();
+  }
+  fence_proxy_async_smem();
+  if (warp == 1) tmem_alloc<64>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  long long t0 = 0, t_issue = 0, t_wait = 0;
+  float acc = 0.f;
+  if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc(0, 128, N);
+      for (int it = 0; it < iters; ++it) {
+        if (it == 8) t0 = clock64();
+        if (it > 0) {
+          mbar_wait(done, (it - 1) & 1);
+          tc_fence_after();
+        }
+        const long long a0 = clock64();
+        for (int c = 0; c < kchunks; ++c) {
+          const uint32_t a_base = smem_u32(sA + (c % sch) * 16384);
+          const uint32_t b_base = smem_u32(sB + (c % sch) * N * 128);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tmem_base, umma_desc_k_sw128(a_base + k * 32), umma_desc_k_sw128(b_base + k * 32), idesc, (c | k) != 0);
+        }
+        umma_commit(full);
+        const long long a1 = clock64();
+        if (it >= 8) t_issue += a1 - a0;
+      }
+      mbar_wait(done, (iters - 1) & 1);
+      out[0] = clock64() - t0;
+      out[1] = t_issue;
+    }
+    __syncwarp();
+  } else if (warp >= 2) {
+    const int lg = warp & 3;
+    for (int it = 0; it < iters; ++it) {
+      const long long w0 = clock64();
+      mbar_wait(full, it & 1);
+      tc_fence_after();
+      const long long w1 = clock64();
+      uint32_t v[16];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+          : "r"(tmem_base + (static_cast<uint32_t>(lg * 32) << 16))
+          : "memory");
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc += __uint_as_float(v[j]);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(done);
+      if (it >= 8 && warp == 2 && lane == 0) t_wait += w1 - w0;
+    }
+    if (warp == 2 && lane == 0) out[2] = t_wait;
+    sink[threadIdx.x] = acc;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<64>(tmem_base);
+}
+
+template <int N>
+static void run_chain(int kchunks) {
+  const int iters = 1008;
+  long long* d_out;
+  float* d_sink;
+  CK(cudaMalloc(&d_out, 64));
+  CK(cudaMalloc(&d_sink, 4096));
+  CK(cudaMemset(d_out, 0, 64));
+  const int smem = (kchunks < 9 ? kchunks : 9) * (16384 + N * 128) + 64 + 1024;
+  CK(cudaFuncSetAttribute(umma_chain_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  umma_chain_kernel<N><<<1, 192, smem>>>(kchunks, iters, d_out, d_sink);
+  CK(cudaDeviceSynchronize());
+  long long o[3];
+  float s0;
+  CK(cudaMemcpy(o, d_out, 24, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&s0, d_sink + 64, 4, cudaMemcpyDeviceToHost));
+  const double n = iters - 8;
+  printf("umma chain M=128 N=%3d K=%4d (%2d MMAs): %7.1f cyc/iter total | issue %6.1f | epilogue-side wait %6.1f  (acc check %.0f)\n",
+         N, kchunks * 64, kchunks * 4, o[0] / n, o[1] / n, o[2] / n, s0);
+  cudaFree(d_out);
+  cudaFree(d_sink);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// D: the same chain with A resident in TENSOR MEMORY (tcgen05.mma "TS" form): lane = row m, K packed two fp16
+// per 32-bit column.  Also a numerical check of that layout and of the N=16 swizzled B layout: D = A * B^T
+// against a CPU loop.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__host__ __device__ inline float a_val(int m, int k) { return float((m * 7 + k * 3) % 11 - 5) * 0.125f; }
+__host__ __device__ inline float b_val(int n, int k) { return float((n * 5 + k * 2) % 13 - 6) * 0.25f; }
+
+template <int N>
+__global__ void __launch_bounds__(192, 1) umma_ts_kernel(int K, int iters, long long* out, float* dout) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int kchunks = (K + 63) / 64;
+  uint8_t* sB = smem;  // kchunks x N*128 B
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kchunks * N * 128);
+  uint64_t* full = bars;
+  uint64_t* done = bars + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // B[n][k] (zero beyond K) in the 128-byte-swizzled K-major layout
+  for (int i = threadIdx.x; i < kchunks * N * 64; i += blockDim.x) {
+    const int c = i / (N * 64), r = i % (N * 64), n = r / 64, kk = r % 64;
+    const int k = c * 64 + kk;
+    const uint32_t off = c * (N * 128) + (n >> 3) * 1024 + (n & 7) * 128 + (((kk >> 3) ^ (n & 7)) << 4) + (kk & 7) * 2;
+    *reinterpret_cast<__half*>(sB + off) = __float2half_rn(k < K ? b_val(n, k) : 0.f);
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(full, 1);
+    mbar_init(done, 4);
+    fence_mbar_init();
+  }
+  fence_proxy_async_smem();
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t kACol = 64;  // A operand columns start here; accumulator at column 0
+  if (warp >= 2) {  // each epilogue warp fills its 32 lanes of A
+    const int lg = warp & 3;
+    const int m = lg * 32 + lane;
+    for (int k0 = 0; k0 < kchunks * 64; k0 += 16) {
+      uint32_t v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = k0 + 2 * j;
+        const __half2 h = __floats2half2_rn(k < K ? a_val(m, k) : 0.f, k + 1 < K ? a_val(m, k + 1) : 0.f);
+        v[j] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+      tmem_st_32x8(tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + kACol + k0 / 2, v);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  long long t0 = 0, t_issue = 0, t_wait = 0;
+  if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc(0, 128, N);
+      for (int it = 0; it < iters; ++it) {
+        if (it == 8) t0 = clock64();
+        if (it > 0) {
+          mbar_wait(done, (it - 1) & 1);
+          tc_fence_after();
+        }
+        const long long a0 = clock64();
+        for (int c = 0; c < kchunks; ++c) {
+          const uint32_t b_base = smem_u32(sB + c * N * 128);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16_ts(tmem_base, tmem_base + kACol + c * 32 + k * 8, umma_desc_k_sw128(b_base + k * 32), idesc, (c | k) != 0);
+        }
+        umma_commit(full);
+        const long long a1 = clock64();
+        if (it >= 8) t_issue += a1 - a0;
+      }
+      mbar_wait(done, (iters - 1) & 1);
+      out[0] = clock64() - t0;
+      out[1] = t_issue;
+    }
+    __syncwarp();
+  } else if (warp >= 2) {
+    const int lg = warp & 3;
+    for (int it = 0; it < iters; ++it) {
+      const long long w0 = clock64();
+      mbar_wait(full, it & 1);
+      tc_fence_after();
+      const long long w1 = clock64();
+      uint32_t v[16];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+          : "r"(tmem_base + (static_cast<uint32_t>(lg * 32) << 16))
+          : "memory");
+      tmem_ld_wait();
+      if (it == iters - 1) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dout[(lg * 32 + lane) * 16 + j] = __uint_as_float(v[j]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(done);
+      if (it >= 8 && warp == 2 && lane == 0) t_wait += w1 - w0;
+    }
+    if (warp == 2 && lane == 0) out[2] = t_wait;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+static void run_ts(int K) {
+  constexpr int N = 16;
+  const int iters = 1008;
+  long long* d_out;
+  float* d_d;
+  CK(cudaMalloc(&d_out, 64));
+  CK(cudaMalloc(&d_d, 128 * 16 * 4));
+  CK(cudaMemset(d_out, 0, 64));
+  const int kchunks = (K + 63) / 64;
+  const int smem = kchunks * N * 128 + 64 + 1024;
+  CK(cudaFuncSetAttribute(umma_ts_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  umma_ts_kernel<N><<<1, 192, smem>>>(K, iters, d_out, d_d);
+  CK(cudaDeviceSynchronize());
+  long long o[3];
+  std::vector<float> D(128 * 16);
+  CK(cudaMemcpy(o, d_out, 24, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(D.data(), d_d, D.size() * 4, cudaMemcpyDeviceToHost));
+  double maxerr = 0;
+  for (int m = 0; m < 128; ++m)
+    for (int n = 0; n < 16; ++n) {
+      double ref = 0;
+      for (int k = 0; k < K; ++k) ref += double(a_val(m, k)) * b_val(n, k);
+      maxerr = std::max(maxerr, std::abs(ref - D[m * 16 + n]));
+    }
+  const double nn = iters - 8;
+  printf("umma TS    M=128 N= 16 K=%4d (%2d MMAs): %7.1f cyc/iter total | issue %6.1f | epilogue-side wait %6.1f | max |D - ref| = %.3e %s\n",
+         K, kchunks * 4, o[0] / nn, o[1] / nn, o[2] / nn, maxerr, maxerr < 1e-3 ? "OK" : "MISMATCH");
+  cudaFree(d_out);
+  cudaFree(d_d);
+}
+
+int main() {
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, 0));
+  printf("device: %s, %d SMs, clock %d MHz\n", prop.name, prop.multiProcessorCount, prop.clockRate / 1000);
+  printf("--- A: st.async all-to-all ---\n");
+  for (int bytes : {512, 1024, 2048, 4096}) run_exchange(9, bytes, 0, 8);
+  run_exchange(9, 1024, 0, 1);
+  run_exchange(9, 2048, 0, 4);
+  run_exchange(10, 896, 0, 8);
+  run_exchange(5, 2048, 0, 8);
+  run_exchange(8, 1024, 0, 16);
+  printf("--- B: cp.async.bulk smem->dsmem all-to-all ---\n");
+  for (int bytes : {512, 1024, 2048, 4096}) run_exchange(9, bytes, 1, 8);
+  run_exchange(9, 1024, 1, 1);
+  run_exchange(5, 2048, 1, 8);
+  printf("--- C: dependent tcgen05 chain ---\n");
+  run_chain<16>(9);
+  run_chain<16>(18);
+  run_chain<32>(9);
+  run_chain<64>(9);
+  run_chain<16>(1);
+  printf("--- D: A operand in tensor memory ---\n");
+  run_ts(64);
+  run_ts(560);
+  run_ts(576);
+  run_ts(896);
+  return 0;
+}

@@ -53,7 +53,7 @@ struct RecFwdArgs {
   float* HCT = nullptr;
   long long ldt = 0;
   int cluster = 0;  // 0 = auto; > 0 selects a legacy (non-specialised) kernel with that cluster size
-  int legacy = 0;   // 1 = non-specialised kernels of pk_rnn.cu
+  int legacy = 0;   // 0 = tcgen05 kernels (pk_rnn_tc.cu), 2 = warp-specialised mma.sync (pk_rnn_ws.cu), 1 = pk_rnn.cu
   int force_z0 = 0; // RNN cell (reference :1438-1447): update gate pinned to 0 -> h = act(a) * mask
   long long* dbg_clk = nullptr;  // bring-up: per-phase cycle sums of CTA 0 / warp 0 (8 slots)
   int sync = -1;    // -1 = default (st.async + mbarrier), 0 = barrier.cluster, 1 = st.async
@@ -84,6 +84,11 @@ int ligru_bwd(const RecBwdArgs& a, cudaStream_t stream);
 // warp-specialised variants (pk_rnn_ws.cu); the bwd one writes GT16 only
 int ligru_fwd_ws(const RecFwdArgs& a, cudaStream_t stream);
 int ligru_bwd_ws(const RecBwdArgs& a, cudaStream_t stream);
+// tcgen05 variants (pk_rnn_tc.cu): weights stationary in tensor memory, H <= ligru_tc_max_hidden()
+int ligru_fwd_tc(const RecFwdArgs& a, cudaStream_t stream);
+int ligru_bwd_tc(const RecBwdArgs& a, cudaStream_t stream);
+int ligru_tc_max_hidden();
+void set_debug_clock_buffer_tc(long long* dev_ptr);
 void set_debug_clock_buffer(long long* dev_ptr);
 
 // ---- step-wise recurrent path (pk_cell_step.cu): one fused kernel per time step ----

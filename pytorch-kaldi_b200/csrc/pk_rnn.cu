@@ -601,8 +601,11 @@ int bwd_dispatch(const RecBwdArgs& a, int cl, int sy, int nclusters, cudaStream_
 int ligru_fwd(const RecFwdArgs& a, cudaStream_t stream) {
   PK_REQUIRE(a.T > 0 && a.B > 0 && a.H > 0, "ligru_fwd: empty problem");
   PK_REQUIRE(a.ndir == 1 || a.ndir == 2, "ligru_fwd: ndir must be 1 or 2");
+  static const int env_mode = env_int("PK_REC_MODE", 0);  // 0 = tcgen05, 2 = warp-specialised mma.sync, 1 = legacy
+  const int mode = a.legacy ? a.legacy : env_mode;
+  if (mode == 0 && a.cluster == 0 && a.sync != 0) return ligru_fwd_tc(a, stream);
   PK_REQUIRE(a.H <= 560, "ligru_fwd: hidden size %d > 560 not supported by the register-resident kernel", a.H);
-  if (!a.legacy && a.cluster == 0 && a.sync != 0 && !env_int("PK_REC_LEGACY", 0)) return ligru_fwd_ws(a, stream);
+  if (mode != 1 && a.cluster == 0 && a.sync != 0) return ligru_fwd_ws(a, stream);
   const int nclusters = (a.ndir * a.B + kRows - 1) / kRows;
   return fwd_dispatch(a, pick_cluster(a.cluster, a.H), pick_sync(a.sync), nclusters, stream);
 }
@@ -610,8 +613,11 @@ int ligru_fwd(const RecFwdArgs& a, cudaStream_t stream) {
 int ligru_bwd(const RecBwdArgs& a, cudaStream_t stream) {
   PK_REQUIRE(a.T > 0 && a.B > 0 && a.H > 0, "ligru_bwd: empty problem");
   PK_REQUIRE(a.ndir == 1 || a.ndir == 2, "ligru_bwd: ndir must be 1 or 2");
+  static const int env_mode = env_int("PK_REC_MODE", 0);
+  const int mode = a.legacy ? a.legacy : env_mode;
+  if (mode == 0 && a.cluster == 0 && a.sync != 0) return ligru_bwd_tc(a, stream);
   PK_REQUIRE(a.H <= 560, "ligru_bwd: hidden size %d > 560 not supported by the register-resident kernel", a.H);
-  if (!a.legacy && a.cluster == 0 && a.sync != 0 && !env_int("PK_REC_LEGACY", 0)) {
+  if (mode != 1 && a.cluster == 0 && a.sync != 0) {
     PK_REQUIRE(a.GT16 != nullptr, "ligru_bwd: the warp-specialised kernel writes GT16 (required)");
     return ligru_bwd_ws(a, stream);
   }

@@ -1,0 +1,824 @@
+// pk_rnn_tc.cu — persistent liGRU / RNN recurrence on tcgen05 tensor cores (round-2 default).
+//
+// Replaces the `for k in range(T)` loop of the reference (neural_networks.py:1130-1141 liGRU, :1438-1447 RNN), its
+// flip / stack / cat shuffles (:1095-1097, :1144-1150) and, in reverse time, the autograd tape behind it.
+//
+// Decomposition (measured numbers: profiles/r2_microbench.txt):
+//   * a thread-block CLUSTER owns 8 of the 2B independent batch rows; CTA c of the cluster owns hidden units
+//     [64c, 64c+64) for both gates -> M = 128 gate rows per CTA, CL = ceil(H / 64) CTAs (9 for H = 550);
+//   * WEIGHTS STATIONARY IN TENSOR MEMORY: the CTA's [128 x K] fp16 slice of U = [Uh; Uz] is written once into
+//     TMEM (lane = gate row, two K-elements per 32-bit column, 32 columns per 64-unit chunk) and is the A operand
+//     of `tcgen05.mma.cta_group::1.kind::f16` (TS form) for all T steps.  With A in shared memory every MMA
+//     re-reads 4 KB of weights (57 cycles per instruction at N = 16, measured); from TMEM the same instruction
+//     costs ~17 cycles;
+//   * the fp16 state is the B operand: [16 rows x 64 units] per source CTA in the 128-byte-swizzled K-major
+//     layout (rows 8..15 are zero padding: M = 128 needs N >= 16), double buffered by step parity.  After its gate
+//     math each CTA st.async-pushes its 8 x 64 block (16-byte messages, complete_tx on the RECEIVER's per-source
+//     mbarrier) to every CTA of the cluster;
+//   * the MMA-issuing thread waits per SOURCE chunk (its own chunk first) and fires that chunk's 4 MMAs as soon
+//     as it has landed, so the tensor work runs inside the DSMEM transit (the exchange is bandwidth-bound:
+//     ~400 + bytes / 20.5 cycles per step, measured) and only the last chunk's MMAs are exposed;
+//   * the fp32 accumulator [128 x 16] lives in TMEM (double buffered); four epilogue warps read it with
+//     tcgen05.ld, swap half of their rows through shared memory so that every thread has BOTH gates of one unit
+//     for 4 rows, and do sigmoid / activation / mask / convex update on fp32 state kept in registers;
+//   * global memory is touched only by four I/O warps: projections (forward) or saved tensors (backward) are
+//     prefetched into a shared-memory ring with 16-byte cp.async, outputs are drained from a ring in the
+//     consumer layouts (channel-major fp32 saved tensors, fp16 operand copies, row-major module output).
+//
+// Backward (reverse time) keeps U^T stationary the same way: lanes 0..63 hold Uh[:, unit]^T, lanes 64..127
+// Uz[:, unit]^T; the exchanged operand is [da; dpz] (rows 0..7 = da, rows 8..15 = dpz of the same 8 batch rows,
+// so N = 16 carries no padding), and dh_{t-1} = keep + (lanes 0..63, columns 0..7) + (lanes 64..127, columns 8..15).
+#include "pk_common.cuh"
+#include "pk_kernels.h"
+
+#include <cstdlib>
+#include <mutex>
+
+namespace pk {
+
+namespace {
+
+constexpr int kRows = 8;    // real batch rows per cluster
+constexpr int kUPC = 64;    // hidden units per CTA
+constexpr int kMaxCL = 15;  // 32 accumulator columns + 32 * CL weight columns <= 512 TMEM columns
+constexpr int RI = 4;       // input ring depth (prefetch distance + 1)
+constexpr int RO = 4;       // output ring depth
+constexpr int kIoWarps = 4;
+constexpr int NIO = kIoWarps * 32;
+constexpr int kEpiWarp0 = 2;  // warps 2..5: epilogue (TMEM lane group = warp % 4)
+constexpr int kIoWarp0 = 6;   // warps 6..9: global-memory I/O
+constexpr int kThreads = 320;
+constexpr uint32_t kACol = 32;          // first TMEM column of the stationary weights
+constexpr uint32_t kChunkBytes = 2048;  // 16 rows x 128 bytes: one source CTA's 64 units
+constexpr uint32_t kIdesc = umma_idesc(0, 128, 16);
+constexpr uint32_t kFwdTx = kRows * 128;      // bytes one source CTA delivers per step (8 rows x 64 units fp16)
+constexpr uint32_t kBwdTx = 2 * kRows * 128;  // backward: two gates
+
+__device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+
+// bounded waits: a protocol bug must trap (the launch fails with an error) instead of hanging the device
+__device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t polls = 0;
+  long long t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++polls & 0x3ffu) == 0) {
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > 4000000000LL) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tc_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t polls = 0;
+  long long t0 = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((++polls & 0x3ffu) == 0) {
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > 4000000000LL) __trap();
+    }
+  }
+}
+
+// ---- the MMA-issuing thread: per step, per source chunk: wait -> 4 MMAs; then commit to acc_full[buf]
+// src_bar[buf][c] completes when source CTA c's block of this step has landed in opnd[buf][c]
+__device__ __forceinline__ void mma_step(uint8_t* opnd_buf, uint64_t* src_bar_buf, uint64_t* acc_full, uint32_t tmem_base,
+                                         uint32_t acc_col, int CL, uint32_t crank, bool wait_data, uint32_t parity,
+                                         uint32_t tx_bytes, bool proxy_fence) {
+  for (int i = 0; i < CL; ++i) {
+    int c = static_cast<int>(crank) + i;
+    if (c >= CL) c -= CL;  // own chunk first: it also proves that the local epilogue has released the accumulator
+    if (wait_data) {
+      tc_wait_cluster(&src_bar_buf[c], parity);
+      mbar_arrive_expect_tx(&src_bar_buf[c], tx_bytes);  // re-arm for this buffer's next use (two steps on)
+      if (proxy_fence) fence_proxy_async_smem();
+      tc_fence_after();
+    }
+    const uint32_t b_base = smem_u32(opnd_buf + c * kChunkBytes);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+      umma_f16_ts(tmem_base + acc_col, tmem_base + kACol + static_cast<uint32_t>(c * 32 + kk * 8),
+                  umma_desc_k_sw128(b_base + kk * 32), kIdesc, (i | kk) != 0);
+  }
+  umma_commit(acc_full);
+}
+
+// =====================================================================================
+// forward
+// =====================================================================================
+struct FwdTc {
+  uint8_t hbuf[2][kMaxCL][kChunkBytes];  // B operand: [buffer][source CTA][16 rows x 128 B, 128B-swizzled]
+  float inr[RI][2][kUPC][kRows];         // [slot][gate h,z][unit][row]
+  float outr[RO][3][kUPC][kRows];        // [slot][h, z, hc][unit][row]
+  float xbuf[2][kUPC][4];                // accumulator rows handed to the other lane half
+  __half stage[kRows][kUPC];             // new state, [row][unit]: 16-byte messages of 8 units
+  uint64_t src_bar[2][kMaxCL];
+  uint64_t acc_full[2];
+  uint64_t in_full[RI], in_empty[RI], out_full[RO], out_empty[RO];
+  uint32_t tmem_slot;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) ligru_fwd_tc_kernel(const RecFwdArgs a, const int CL) {
+  extern __shared__ uint8_t smem_raw[];
+  FwdTc& sm = *reinterpret_cast<FwdTc*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const int cl = blockIdx.x / CL;
+  const int H = a.H, B = a.B, T = a.T;
+  const int nrows = a.ndir * B;
+  const int cta_ubase = crank * kUPC;
+
+  for (int i = threadIdx.x; i < static_cast<int>(sizeof(sm.hbuf) / 16); i += blockDim.x)
+    reinterpret_cast<uint4*>(&sm.hbuf[0][0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = threadIdx.x; i < RI * 2 * kUPC * kRows; i += blockDim.x) (&sm.inr[0][0][0][0])[i] = 0.f;
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < 2; ++b) {
+      for (int c = 0; c < CL; ++c) mbar_init(&sm.src_bar[b][c], 1);
+      mbar_init(&sm.acc_full[b], 1);
+    }
+    for (int s = 0; s < RI; ++s) { mbar_init(&sm.in_full[s], NIO); mbar_init(&sm.in_empty[s], 4); }
+    for (int s = 0; s < RO; ++s) { mbar_init(&sm.out_full[s], 4); mbar_init(&sm.out_empty[s], kIoWarps); }
+    fence_mbar_init();
+    // arm every per-source barrier for its first use (buffer 1: step 1, buffer 0: step 2)
+    for (int b = 0; b < 2; ++b)
+      for (int c = 0; c < CL; ++c) mbar_arrive_expect_tx(&sm.src_bar[b][c], kFwdTx);
+  }
+  fence_proxy_async_smem();  // the zero-filled operand buffers are read by the tensor core (async proxy) at step 0
+  if (warp == 1) tmem_alloc<512>(&sm.tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sm.tmem_slot;
+
+  // ---- stationary weights -> tensor memory (epilogue warps; lane m < 64: Uh[unit m], lane 64 + m: Uz[unit m])
+  if (warp >= kEpiWarp0 && warp < kIoWarp0) {
+    const int lg = warp & 3;
+    const int m = lg * 32 + lane;
+    const int u = cta_ubase + (m & 63);
+    const bool u_ok = u < H;
+    const float* Urow = a.U + (static_cast<long long>(m >> 6) * H + (u_ok ? u : 0)) * H;
+    const int KP = CL * kUPC;
+    for (int k0 = 0; k0 < KP; k0 += 16) {
+      uint32_t v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = k0 + 2 * j;
+        const float x0 = (u_ok && k < H) ? __ldg(Urow + k) : 0.f;
+        const float x1 = (u_ok && k + 1 < H) ? __ldg(Urow + k + 1) : 0.f;
+        v[j] = pack_f16x2_sat(x0, x1);
+      }
+      tmem_st_32x8(tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + kACol + static_cast<uint32_t>(k0 >> 1), v);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // every CTA's barriers and buffers are initialised before any peer pushes
+  tc_fence_after();
+
+  if (warp == 0) {
+    // ================= MMA issuer =================
+    if (elect_one()) {
+      const bool pf = !(a.dbg & 4);
+      for (int k = 0; k < T; ++k) {
+        const int cur = k & 1;
+        mma_step(&sm.hbuf[cur][0][0], &sm.src_bar[cur][0], &sm.acc_full[cur], tmem_base, static_cast<uint32_t>(cur * 16), CL,
+                 crank, k > 0, static_cast<uint32_t>(((k - 1) >> 1) & 1), kFwdTx, pf);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= kEpiWarp0 && warp < kIoWarp0) {
+    // ================= epilogue warps: gates =================
+    const int lg = warp & 3;
+    const int m = lg * 32 + lane;      // TMEM lane = gate row of this CTA
+    const int half = m >> 6;           // 0: lanes hold the candidate gate, 1: the update gate
+    const int ul = m & 63;             // local unit
+    const int u = cta_ubase + ul;
+    const bool u_ok = u < H;
+    const int r0 = half * 4;           // this thread finishes rows r0 .. r0+3 of its unit
+    const int et = (warp - kEpiWarp0) * 32 + lane;  // 0..127
+    float msk[4];
+    bool rok[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = cl * kRows + r0 + i;
+      rok[i] = (r < nrows) && u_ok;
+      msk[i] = a.mask ? (rok[i] ? __ldg(a.mask + static_cast<long long>(r) * H + u) : 0.f) : a.mask_scalar;
+    }
+    float sc_h = 0.f, sh_h = 0.f, sc_z = 0.f, sh_z = 0.f;
+    if (u_ok) {
+      sc_h = __ldg(a.scale + u); sh_h = __ldg(a.shift + u);
+      sc_z = __ldg(a.scale + H + u); sh_z = __ldg(a.shift + H + u);
+    }
+    float hprev[4] = {0.f, 0.f, 0.f, 0.f};
+    const int act = a.act;
+    const bool z0 = a.force_z0 != 0;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(lg * 32) << 16);
+    // push bookkeeping: message (row, 8-unit group j) of this CTA's block, destinations et>>6, +2, ...
+    const int prow = (et & 63) >> 3, pj = et & 7;
+    const uint32_t msg_off = static_cast<uint32_t>(crank * kChunkBytes + prow * 128 + ((pj ^ prow) << 4));
+
+    const bool clk_on = a.dbg_clk != nullptr && blockIdx.x == 0 && et == 0;
+    long long tsum[6] = {0, 0, 0, 0, 0, 0};
+    tc_wait(&sm.in_full[0], 0);
+    float4 ph = *reinterpret_cast<const float4*>(&sm.inr[0][0][ul][r0]);
+    float4 pz = *reinterpret_cast<const float4*>(&sm.inr[0][1][ul][r0]);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.in_empty[0]);
+    for (int k = 0; k < T; ++k) {
+      const int cur = k & 1, nxt = cur ^ 1;
+      long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+      if (clk_on) t0 = clock64();
+      tc_wait(&sm.acc_full[cur], static_cast<uint32_t>((k >> 1) & 1));
+      tc_fence_after();
+      if (clk_on) t1 = clock64();
+      uint32_t v[8];
+      tmem_ld_32x8(lane_addr + static_cast<uint32_t>(cur * 16), v);
+      tmem_ld_wait();
+      tc_fence_before();
+      // hand the rows the OTHER half finishes to it: half 0 gives rows 4..7, half 1 gives rows 0..3
+      *reinterpret_cast<float4*>(&sm.xbuf[half][ul][0]) =
+          half ? make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]))
+               : make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
+      epi_bar(1);
+      const float4 xo = *reinterpret_cast<const float4*>(&sm.xbuf[half ^ 1][ul][0]);
+      float ah[4], az[4];
+      if (half == 0) {
+        ah[0] = __uint_as_float(v[0]); ah[1] = __uint_as_float(v[1]); ah[2] = __uint_as_float(v[2]); ah[3] = __uint_as_float(v[3]);
+        az[0] = xo.x; az[1] = xo.y; az[2] = xo.z; az[3] = xo.w;
+      } else {
+        az[0] = __uint_as_float(v[4]); az[1] = __uint_as_float(v[5]); az[2] = __uint_as_float(v[6]); az[3] = __uint_as_float(v[7]);
+        ah[0] = xo.x; ah[1] = xo.y; ah[2] = xo.z; ah[3] = xo.w;
+      }
+      if (clk_on) t2 = clock64();
+      // ---- gates (reference :1133-1136)
+      const float phv[4] = {ph.x, ph.y, ph.z, ph.w}, pzv[4] = {pz.x, pz.y, pz.z, pz.w};
+      float hn[4], zz[4], hcv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float zt = z0 ? 0.f : sigmoid_fast(fmaf(sc_z, pzv[i], sh_z) + az[i]);
+        const float hc = act_fwd_fast(act, fmaf(sc_h, phv[i], sh_h) + ah[i]) * msk[i];
+        float h = fmaf(zt, hprev[i] - hc, hc);
+        if (!rok[i]) h = 0.f;
+        hn[i] = h; zz[i] = zt; hcv[i] = hc; hprev[i] = h;
+        sm.stage[r0 + i][ul] = f16_sat(h);
+      }
+      epi_bar(2);
+      if (clk_on) t3 = clock64();
+      // ---- push this CTA's 8 x 64 block to every CTA of the cluster (data + complete_tx in one message)
+      if (k + 1 < T) {
+        const uint4 val = *reinterpret_cast<const uint4*>(&sm.stage[prow][pj * 8]);
+        const uint32_t laddr = smem_u32(&sm.hbuf[nxt][0][0]) + msg_off;
+        const uint32_t lbar = smem_u32(&sm.src_bar[nxt][crank]);
+        for (int dst = et >> 6; dst < CL; dst += 2) st_async_v4(mapa_shared(laddr, dst), val, mapa_shared(lbar, dst));
+      }
+      if (clk_on) t4 = clock64();
+      // ---- in the shadow of the transit: outputs -> I/O warps, next step's projections <- ring
+      const int so = k % RO;
+      if (k >= RO) tc_wait(&sm.out_empty[so], static_cast<uint32_t>(((k / RO) - 1) & 1));
+      *reinterpret_cast<float4*>(&sm.outr[so][0][ul][r0]) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+      *reinterpret_cast<float4*>(&sm.outr[so][1][ul][r0]) = make_float4(zz[0], zz[1], zz[2], zz[3]);
+      *reinterpret_cast<float4*>(&sm.outr[so][2][ul][r0]) = make_float4(hcv[0], hcv[1], hcv[2], hcv[3]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.out_full[so]);
+      if (k + 1 < T) {
+        const int si = (k + 1) % RI;
+        tc_wait(&sm.in_full[si], static_cast<uint32_t>(((k + 1) / RI) & 1));
+        ph = *reinterpret_cast<const float4*>(&sm.inr[si][0][ul][r0]);
+        pz = *reinterpret_cast<const float4*>(&sm.inr[si][1][ul][r0]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.in_empty[si]);
+      }
+      if (clk_on) {
+        const long long t5 = clock64();
+        tsum[0] += t1 - t0; tsum[1] += t2 - t1; tsum[2] += t3 - t2; tsum[3] += t4 - t3; tsum[4] += t5 - t4;
+      }
+    }
+    if (clk_on)
+      for (int i = 0; i < 6; ++i) a.dbg_clk[i] = tsum[i];
+  } else if (warp >= kIoWarp0) {
+    // ================= I/O warps (128 threads) =================
+    const int tid = threadIdx.x - kIoWarp0 * 32;
+    constexpr int NE = (kUPC * kRows + NIO - 1) / NIO;
+    int colv[NE], cstep[NE];
+    long long chan[NE], pch[NE];
+    float hp[NE];
+#pragma unroll
+    for (int j = 0; j < NE; ++j) {
+      const int e = tid + NIO * j;
+      const int ul = e >> 3, r = e & 7;
+      const int u = cta_ubase + ul;
+      const int rr = cl * kRows + r;
+      const bool ok = (u < H) && (rr < nrows);
+      const int d = (ok && rr >= B) ? 1 : 0;
+      const int b = rr - d * B;
+      colv[j] = ok ? (d ? (T - 1) * B + b : b) : -1;  // column at step 0
+      cstep[j] = d ? -B : B;
+      chan[j] = static_cast<long long>(d * H + u) * a.ldt;
+      pch[j] = static_cast<long long>(u) * a.ldp;
+      hp[j] = 0.f;
+    }
+    const long long gate_z = static_cast<long long>(H) * a.ldp;
+    const bool do_store = !(a.dbg & 1);
+    const bool do_load = !(a.dbg & 2);
+    // fast path: groups of 4 consecutive rows are contiguous and 16-byte aligned in every channel-major
+    // array when B % 4 == 0 -> one thread moves (unit, 4 rows) with 16-byte cp.async / float4 stores
+    const bool vec = (B % 4 == 0) && (a.ldp % 4 == 0) && (a.ldt % 4 == 0);
+    const int vul = tid >> 1, vr0 = (tid & 1) * 4;
+    const int vu = cta_ubase + vul;
+    const int vrr = cl * kRows + vr0;
+    const bool vok = (vu < H) && (vrr < nrows);
+    const int vd = (vok && vrr >= B) ? 1 : 0;
+    const int vb = vrr - vd * B;
+    const int vcstep = vd ? -B : B;
+    const long long vcol0 = vd ? static_cast<long long>(T - 1) * B + vb : vb;
+    const long long vchan = static_cast<long long>(vd * H + vu) * a.ldt;
+    const long long vpch = static_cast<long long>(vu) * a.ldp;
+    float4 vhp = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    auto issue_load = [&](int kl) {  // projections of step kl -> in-ring
+      const int s = kl % RI;
+      if (kl >= RI) tc_wait(&sm.in_empty[s], static_cast<uint32_t>(((kl / RI) - 1) & 1));
+      if (do_load && vec) {
+        if (vok) {
+          const long long col = vcol0 + static_cast<long long>(kl) * vcstep;
+          cp_async_16(&sm.inr[s][0][vul][vr0], a.PT + vpch + col);
+          cp_async_16(&sm.inr[s][1][vul][vr0], a.PT + vpch + gate_z + col);
+        }
+      } else if (do_load) {
+#pragma unroll
+        for (int j = 0; j < NE; ++j) {
+          if (colv[j] >= 0) {
+            const int e = tid + NIO * j;
+            const long long col = colv[j] + static_cast<long long>(kl) * cstep[j];
+            cp_async_f32(&sm.inr[s][0][e >> 3][e & 7], a.PT + pch[j] + col);
+            cp_async_f32(&sm.inr[s][1][e >> 3][e & 7], a.PT + pch[j] + gate_z + col);
+          }
+        }
+      }
+      cp_async_arrive_noinc(&sm.in_full[s]);
+    };
+    for (int kl = 0; kl < RI - 1 && kl < T; ++kl) issue_load(kl);
+    for (int k = 0; k < T; ++k) {
+      if (k + RI - 1 < T) issue_load(k + RI - 1);
+      const int s = k % RO;
+      tc_wait(&sm.out_full[s], static_cast<uint32_t>((k / RO) & 1));
+      if (do_store && vec) {
+        if (vok) {
+          const long long idx = vchan + vcol0 + static_cast<long long>(k) * vcstep;
+          const float4 h4 = *reinterpret_cast<const float4*>(&sm.outr[s][0][vul][vr0]);
+          if (a.HT) *reinterpret_cast<float4*>(a.HT + idx) = h4;
+          if (a.ZT) *reinterpret_cast<float4*>(a.ZT + idx) = *reinterpret_cast<const float4*>(&sm.outr[s][1][vul][vr0]);
+          if (a.HCT) *reinterpret_cast<float4*>(a.HCT + idx) = *reinterpret_cast<const float4*>(&sm.outr[s][2][vul][vr0]);
+          if (a.HT16) {
+            uint2 pk16;
+            pk16.x = pack_f16x2_sat(h4.x, h4.y);
+            pk16.y = pack_f16x2_sat(h4.z, h4.w);
+            *reinterpret_cast<uint2*>(a.HT16 + idx) = pk16;
+          }
+          if (a.HP16) {
+            uint2 pk16;
+            pk16.x = pack_f16x2_sat(vhp.x, vhp.y);
+            pk16.y = pack_f16x2_sat(vhp.z, vhp.w);
+            *reinterpret_cast<uint2*>(a.HP16 + idx) = pk16;
+          }
+          vhp = h4;
+          if (a.Y32 || a.Y16) {
+            const long long col = vcol0 + static_cast<long long>(k) * vcstep;
+            const float hv[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (a.Y32) a.Y32[(col + i) * a.ldy32 + vd * H + vu] = hv[i];
+              if (a.Y16) a.Y16[(col + i) * a.ldy16 + vd * H + vu] = f16_sat(hv[i]);
+            }
+          }
+        }
+      } else if (do_store) {
+#pragma unroll
+        for (int j = 0; j < NE; ++j) {
+          if (colv[j] >= 0) {
+            const int e = tid + NIO * j;
+            const float h = sm.outr[s][0][e >> 3][e & 7];
+            const long long idx = chan[j] + colv[j] + static_cast<long long>(k) * cstep[j];
+            if (a.HT) a.HT[idx] = h;
+            if (a.ZT) a.ZT[idx] = sm.outr[s][1][e >> 3][e & 7];
+            if (a.HCT) a.HCT[idx] = sm.outr[s][2][e >> 3][e & 7];
+            if (a.HT16) a.HT16[idx] = f16_sat(h);
+            if (a.HP16) a.HP16[idx] = f16_sat(hp[j]);
+            hp[j] = h;
+          }
+        }
+        // row-major module output: for a fixed row the CTA's units are contiguous -> threads run along units
+        if (a.Y32 || a.Y16) {
+          for (int f = tid; f < kUPC * kRows; f += NIO) {
+            const int r = f / kUPC, ul = f - r * kUPC;
+            const int rr = cl * kRows + r;
+            const int u = cta_ubase + ul;
+            if (rr < nrows && u < H) {
+              const int d = rr >= B ? 1 : 0;
+              const int b = rr - d * B;
+              const long long col = static_cast<long long>(d ? T - 1 - k : k) * B + b;
+              const float h = sm.outr[s][0][ul][r];
+              if (a.Y32) a.Y32[col * a.ldy32 + d * H + u] = h;
+              if (a.Y16) a.Y16[col * a.ldy16 + d * H + u] = f16_sat(h);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.out_empty[s]);
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  }
+  // no CTA may exit (or free its tensor memory) while peers can still write into its shared memory
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// =====================================================================================
+// backward
+// =====================================================================================
+struct BwdTc {
+  uint8_t gbuf[2][kMaxCL][kChunkBytes];  // B operand: rows 0..7 = da, rows 8..15 = dpz of the cluster's 8 batch rows
+  float inr[RI][4][kUPC][kRows];         // [slot][dy, z, hc, hprev][unit][row]
+  __half outr[RO][2][kUPC][kRows];       // [slot][da, dpz][unit][row]  (scaled fp16)
+  float xbuf[2][kUPC][4];
+  __half stage[2][kRows][kUPC];          // [gate][row][unit]
+  uint64_t src_bar[2][kMaxCL];
+  uint64_t acc_full[2];
+  uint64_t in_full[RI], in_empty[RI], out_full[RO], out_empty[RO];
+  uint32_t tmem_slot;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) ligru_bwd_tc_kernel(const RecBwdArgs a, const int CL) {
+  extern __shared__ uint8_t smem_raw[];
+  BwdTc& sm = *reinterpret_cast<BwdTc*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const int cl = blockIdx.x / CL;
+  const int H = a.H, B = a.B, T = a.T;
+  const int nrows = a.ndir * B;
+  const int cta_ubase = crank * kUPC;
+
+  for (int i = threadIdx.x; i < static_cast<int>(sizeof(sm.gbuf) / 16); i += blockDim.x)
+    reinterpret_cast<uint4*>(&sm.gbuf[0][0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = threadIdx.x; i < RI * 4 * kUPC * kRows; i += blockDim.x) (&sm.inr[0][0][0][0])[i] = 0.f;
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < 2; ++b) {
+      for (int c = 0; c < CL; ++c) mbar_init(&sm.src_bar[b][c], 1);
+      mbar_init(&sm.acc_full[b], 1);
+    }
+    for (int s = 0; s < RI; ++s) { mbar_init(&sm.in_full[s], NIO); mbar_init(&sm.in_empty[s], 4); }
+    for (int s = 0; s < RO; ++s) { mbar_init(&sm.out_full[s], 4); mbar_init(&sm.out_empty[s], kIoWarps); }
+    fence_mbar_init();
+    for (int b = 0; b < 2; ++b)
+      for (int c = 0; c < CL; ++c) mbar_arrive_expect_tx(&sm.src_bar[b][c], kBwdTx);
+  }
+  fence_proxy_async_smem();
+  if (warp == 1) tmem_alloc<512>(&sm.tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sm.tmem_slot;
+
+  // ---- stationary U^T -> tensor memory: lane m < 64: A[m][j] = Uh[j][unit m]; lane 64 + m: Uz[j][unit m]
+  if (warp >= kEpiWarp0 && warp < kIoWarp0) {
+    const int lg = warp & 3;
+    const int m = lg * 32 + lane;
+    const int u = cta_ubase + (m & 63);
+    const bool u_ok = u < H;
+    const float* Ucol = a.U + static_cast<long long>(m >> 6) * H * H + (u_ok ? u : 0);
+    const int KP = CL * kUPC;
+    for (int k0 = 0; k0 < KP; k0 += 16) {
+      uint32_t v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = k0 + 2 * j;
+        const float x0 = (u_ok && k < H) ? __ldg(Ucol + static_cast<long long>(k) * H) : 0.f;
+        const float x1 = (u_ok && k + 1 < H) ? __ldg(Ucol + static_cast<long long>(k + 1) * H) : 0.f;
+        v[j] = pack_f16x2_sat(x0, x1);
+      }
+      tmem_st_32x8(tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + kACol + static_cast<uint32_t>(k0 >> 1), v);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+
+  if (warp == 0) {
+    // ================= MMA issuer: one product per step k = T-1 .. 1 (the carry into step k-1) =================
+    if (elect_one()) {
+      const bool pf = !(a.dbg & 4);
+      for (int k = T - 1; k > 0; --k) {
+        const int it = T - 1 - k;
+        const int buf = k & 1;
+        mma_step(&sm.gbuf[buf][0][0], &sm.src_bar[buf][0], &sm.acc_full[buf], tmem_base, static_cast<uint32_t>(buf * 16), CL,
+                 crank, true, static_cast<uint32_t>((it >> 1) & 1), kBwdTx, pf);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= kEpiWarp0 && warp < kIoWarp0) {
+    // ================= epilogue warps: pointwise backward =================
+    const int lg = warp & 3;
+    const int m = lg * 32 + lane;
+    const int half = m >> 6;
+    const int ul = m & 63;
+    const int u = cta_ubase + ul;
+    const bool u_ok = u < H;
+    const int r0 = half * 4;
+    const int et = (warp - kEpiWarp0) * 32 + lane;
+    float msk[4], rmk[4];
+    bool rok[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = cl * kRows + r0 + i;
+      rok[i] = (r < nrows) && u_ok;
+      msk[i] = a.mask ? (rok[i] ? __ldg(a.mask + static_cast<long long>(r) * H + u) : 0.f) : a.mask_scalar;
+      rmk[i] = (msk[i] != 0.f) ? __frcp_rn(msk[i]) : 0.f;  // masks are 0/1 in training; eval: scalar (1-p)
+    }
+    const float s = a.gscale ? __ldg(a.gscale) : 1.f;
+    const float inv_s = 1.f / s;
+    float carry[4] = {0.f, 0.f, 0.f, 0.f};
+    const int act = a.act;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + static_cast<uint32_t>(half * 8);
+    // push bookkeeping: 128 messages (gate, row, 8-unit group) -> one per epilogue thread, every destination
+    const int pg = et >> 6, prow = (et & 63) >> 3, pj = et & 7;
+    const uint32_t msg_off = static_cast<uint32_t>(crank * kChunkBytes + pg * 1024 + prow * 128 + ((pj ^ prow) << 4));
+
+    const bool clk_on = a.dbg_clk != nullptr && blockIdx.x == 0 && et == 0;
+    long long tsum[6] = {0, 0, 0, 0, 0, 0};
+    tc_wait(&sm.in_full[0], 0);
+    float4 dy = *reinterpret_cast<const float4*>(&sm.inr[0][0][ul][r0]);
+    float4 zz = *reinterpret_cast<const float4*>(&sm.inr[0][1][ul][r0]);
+    float4 hc = *reinterpret_cast<const float4*>(&sm.inr[0][2][ul][r0]);
+    float4 hp = *reinterpret_cast<const float4*>(&sm.inr[0][3][ul][r0]);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.in_empty[0]);
+    for (int k = T - 1; k >= 0; --k) {
+      const int it = T - 1 - k;
+      const int buf = k & 1;
+      long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+      if (clk_on) t0 = clock64();
+      // ---------------- phase A: pointwise backward of step k ----------------
+      if (k == 0) hp = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float dyv[4] = {dy.x, dy.y, dy.z, dy.w}, zv[4] = {zz.x, zz.y, zz.z, zz.w};
+      const float hcv[4] = {hc.x, hc.y, hc.z, hc.w}, hpv[4] = {hp.x, hp.y, hp.z, hp.w};
+      float keep[4];
+      __half da16[4], dz16[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float dh = dyv[i] + carry[i];
+        float da = dh * (1.f - zv[i]) * msk[i] * act_bwd_from_out(act, hcv[i] * rmk[i]);
+        float dz = dh * (hpv[i] - hcv[i]) * zv[i] * (1.f - zv[i]);
+        if (!rok[i]) { da = 0.f; dz = 0.f; }
+        keep[i] = dh * zv[i];
+        da16[i] = f16_sat(da * s);
+        dz16[i] = f16_sat(dz * s);
+        sm.stage[0][r0 + i][ul] = da16[i];
+        sm.stage[1][r0 + i][ul] = dz16[i];
+      }
+      epi_bar(2);
+      if (clk_on) t1 = clock64();
+      if (k > 0) {
+        const uint4 val = *reinterpret_cast<const uint4*>(&sm.stage[pg][prow][pj * 8]);
+        const uint32_t laddr = smem_u32(&sm.gbuf[buf][0][0]) + msg_off;
+        const uint32_t lbar = smem_u32(&sm.src_bar[buf][crank]);
+        for (int dst = 0; dst < CL; ++dst) st_async_v4(mapa_shared(laddr, dst), val, mapa_shared(lbar, dst));
+      }
+      if (clk_on) t2 = clock64();
+      // ---- in the shadow of the transit: outputs -> I/O warps, next step's operands <- ring
+      const int so = it % RO;
+      if (it >= RO) tc_wait(&sm.out_empty[so], static_cast<uint32_t>(((it / RO) - 1) & 1));
+      {
+        uint2 p0, p1;
+        p0.x = (static_cast<uint32_t>(__half_as_ushort(da16[1])) << 16) | __half_as_ushort(da16[0]);
+        p0.y = (static_cast<uint32_t>(__half_as_ushort(da16[3])) << 16) | __half_as_ushort(da16[2]);
+        p1.x = (static_cast<uint32_t>(__half_as_ushort(dz16[1])) << 16) | __half_as_ushort(dz16[0]);
+        p1.y = (static_cast<uint32_t>(__half_as_ushort(dz16[3])) << 16) | __half_as_ushort(dz16[2]);
+        *reinterpret_cast<uint2*>(&sm.outr[so][0][ul][r0]) = p0;
+        *reinterpret_cast<uint2*>(&sm.outr[so][1][ul][r0]) = p1;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.out_full[so]);
+      if (k > 0) {
+        const int si = (it + 1) % RI;
+        tc_wait(&sm.in_full[si], static_cast<uint32_t>(((it + 1) / RI) & 1));
+        dy = *reinterpret_cast<const float4*>(&sm.inr[si][0][ul][r0]);
+        zz = *reinterpret_cast<const float4*>(&sm.inr[si][1][ul][r0]);
+        hc = *reinterpret_cast<const float4*>(&sm.inr[si][2][ul][r0]);
+        hp = *reinterpret_cast<const float4*>(&sm.inr[si][3][ul][r0]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.in_empty[si]);
+      }
+      if (clk_on) t3 = clock64();
+      // ---------------- phase B: carry into step k-1 = keep + U^T [da; dpz] / s ----------------
+      if (k > 0) {
+        tc_wait(&sm.acc_full[buf], static_cast<uint32_t>((it >> 1) & 1));
+        tc_fence_after();
+        if (clk_on) t4 = clock64();
+        uint32_t v[8];
+        tmem_ld_32x8(lane_addr + static_cast<uint32_t>(buf * 16), v);
+        tmem_ld_wait();
+        tc_fence_before();
+        *reinterpret_cast<float4*>(&sm.xbuf[half][ul][0]) =
+            half ? make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]))
+                 : make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
+        epi_bar(1);
+        const float4 xo = *reinterpret_cast<const float4*>(&sm.xbuf[half ^ 1][ul][0]);
+        const float xv[4] = {xo.x, xo.y, xo.z, xo.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) carry[i] = keep[i] + (__uint_as_float(half ? v[4 + i] : v[i]) + xv[i]) * inv_s;
+      }
+      if (clk_on && k > 0) {
+        const long long t5 = clock64();
+        tsum[0] += t1 - t0; tsum[1] += t2 - t1; tsum[2] += t3 - t2; tsum[3] += t4 - t3; tsum[4] += t5 - t4;
+      }
+    }
+    if (clk_on)
+      for (int i = 0; i < 6; ++i) a.dbg_clk[i] = tsum[i];
+  } else if (warp >= kIoWarp0) {
+    // ================= I/O warps (128 threads) =================
+    const int tid = threadIdx.x - kIoWarp0 * 32;
+    constexpr int NE = (kUPC * kRows + NIO - 1) / NIO;
+    int colv[NE], cstep[NE];
+    long long chan[NE];
+#pragma unroll
+    for (int j = 0; j < NE; ++j) {
+      const int e = tid + NIO * j;
+      const int ul = e >> 3, r = e & 7;
+      const int u = cta_ubase + ul;
+      const int rr = cl * kRows + r;
+      const bool ok = (u < H) && (rr < nrows);
+      const int d = (ok && rr >= B) ? 1 : 0;
+      const int b = rr - d * B;
+      colv[j] = ok ? (d ? (T - 1) * B + b : b) : -1;
+      cstep[j] = d ? -B : B;
+      chan[j] = static_cast<long long>(d * H + u) * a.ldt;
+    }
+    const long long gate_stride = static_cast<long long>(H) * a.ldt;
+    const long long dir_stride = 2 * gate_stride;
+    const bool do_store = !(a.dbg & 1);
+    const bool do_load = !(a.dbg & 2);
+    const bool vec = (B % 4 == 0) && (a.ldt % 4 == 0);
+    const int vul = tid >> 1, vr0 = (tid & 1) * 4;
+    const int vu = cta_ubase + vul;
+    const int vrr = cl * kRows + vr0;
+    const bool vok = (vu < H) && (vrr < nrows);
+    const int vd = (vok && vrr >= B) ? 1 : 0;
+    const int vb = vrr - vd * B;
+    const int vcstep = vd ? -B : B;
+    const long long vcol0 = vd ? static_cast<long long>(T - 1) * B + vb : vb;
+    const long long vchan = static_cast<long long>(vd * H + vu) * a.ldt;
+
+    auto issue_load = [&](int it) {  // operands of step k = T-1-it -> in-ring slot it % RI
+      const int k = T - 1 - it;
+      const int s = it % RI;
+      if (it >= RI) tc_wait(&sm.in_empty[s], static_cast<uint32_t>(((it / RI) - 1) & 1));
+      if (do_load && vec) {
+        if (vok) {
+          const long long idx = vchan + vcol0 + static_cast<long long>(k) * vcstep;
+          cp_async_16(&sm.inr[s][0][vul][vr0], a.dYT + idx);
+          cp_async_16(&sm.inr[s][1][vul][vr0], a.ZT + idx);
+          cp_async_16(&sm.inr[s][2][vul][vr0], a.HCT + idx);
+          if (k > 0) cp_async_16(&sm.inr[s][3][vul][vr0], a.HT + idx - vcstep);
+        }
+      } else if (do_load) {
+#pragma unroll
+        for (int j = 0; j < NE; ++j) {
+          if (colv[j] >= 0) {
+            const int e = tid + NIO * j;
+            const long long idx = chan[j] + colv[j] + static_cast<long long>(k) * cstep[j];
+            cp_async_f32(&sm.inr[s][0][e >> 3][e & 7], a.dYT + idx);
+            cp_async_f32(&sm.inr[s][1][e >> 3][e & 7], a.ZT + idx);
+            cp_async_f32(&sm.inr[s][2][e >> 3][e & 7], a.HCT + idx);
+            if (k > 0) cp_async_f32(&sm.inr[s][3][e >> 3][e & 7], a.HT + idx - cstep[j]);
+          }
+        }
+      }
+      cp_async_arrive_noinc(&sm.in_full[s]);
+    };
+    for (int it = 0; it < RI - 1 && it < T; ++it) issue_load(it);
+    for (int it = 0; it < T; ++it) {
+      if (it + RI - 1 < T) issue_load(it + RI - 1);
+      const int k = T - 1 - it;
+      const int s = it % RO;
+      tc_wait(&sm.out_full[s], static_cast<uint32_t>((it / RO) & 1));
+      if (do_store && vec) {
+        if (vok) {
+          const long long idx = vd * dir_stride + static_cast<long long>(vu) * a.ldt + vcol0 + static_cast<long long>(k) * vcstep;
+          *reinterpret_cast<uint2*>(a.GT16 + idx) = *reinterpret_cast<const uint2*>(&sm.outr[s][0][vul][vr0]);
+          *reinterpret_cast<uint2*>(a.GT16 + idx + gate_stride) = *reinterpret_cast<const uint2*>(&sm.outr[s][1][vul][vr0]);
+        }
+      } else if (do_store) {
+#pragma unroll
+        for (int j = 0; j < NE; ++j) {
+          if (colv[j] >= 0) {
+            const int e = tid + NIO * j;
+            const int ul = e >> 3, r = e & 7;
+            const int u = cta_ubase + ul;
+            const int d = cstep[j] < 0 ? 1 : 0;
+            const long long col = colv[j] + static_cast<long long>(k) * cstep[j];
+            const long long idx = d * dir_stride + static_cast<long long>(u) * a.ldt + col;
+            a.GT16[idx] = sm.outr[s][0][ul][r];
+            a.GT16[idx + gate_stride] = sm.outr[s][1][ul][r];
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.out_empty[s]);
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+template <typename Args, typename Kern>
+int launch_tc(Kern kern, const Args& a, int CL, int nclusters, size_t smem, cudaStream_t stream) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nclusters * CL, 1, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, a, CL));
+  return 0;
+}
+
+long long* g_dbg_clk_tc = nullptr;
+
+int tc_attrs() {
+  static std::once_flag once;
+  static cudaError_t err = cudaSuccess;
+  std::call_once(once, [] {
+    err = cudaFuncSetAttribute(ligru_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(FwdTc) + 1024));
+    if (err == cudaSuccess)
+      err = cudaFuncSetAttribute(ligru_fwd_tc_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (err == cudaSuccess)
+      err = cudaFuncSetAttribute(ligru_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(BwdTc) + 1024));
+    if (err == cudaSuccess)
+      err = cudaFuncSetAttribute(ligru_bwd_tc_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  });
+  PK_CHECK_CUDA(err);
+  return 0;
+}
+
+}  // namespace
+
+void set_debug_clock_buffer_tc(long long* dev_ptr) { g_dbg_clk_tc = dev_ptr; }
+
+int ligru_tc_max_hidden() { return kMaxCL * kUPC; }
+
+int ligru_fwd_tc(const RecFwdArgs& a_in, cudaStream_t stream) {
+  RecFwdArgs a = a_in;
+  a.dbg_clk = g_dbg_clk_tc;
+  const int CL = (a.H + kUPC - 1) / kUPC;
+  PK_REQUIRE(CL <= kMaxCL, "ligru_fwd_tc: hidden size %d > %d", a.H, kMaxCL * kUPC);
+  if (int rc = tc_attrs()) return rc;
+  const int nclusters = (a.ndir * a.B + kRows - 1) / kRows;
+  return launch_tc(ligru_fwd_tc_kernel, a, CL, nclusters, sizeof(FwdTc) + 1024, stream);
+}
+
+int ligru_bwd_tc(const RecBwdArgs& a_in, cudaStream_t stream) {
+  RecBwdArgs a = a_in;
+  a.dbg_clk = g_dbg_clk_tc;
+  const int CL = (a.H + kUPC - 1) / kUPC;
+  PK_REQUIRE(CL <= kMaxCL, "ligru_bwd_tc: hidden size %d > %d", a.H, kMaxCL * kUPC);
+  PK_REQUIRE(a.GT16 != nullptr, "ligru_bwd_tc: writes GT16 (required)");
+  if (int rc = tc_attrs()) return rc;
+  const int nclusters = (a.ndir * a.B + kRows - 1) / kRows;
+  return launch_tc(ligru_bwd_tc_kernel, a, CL, nclusters, sizeof(BwdTc) + 1024, stream);
+}
+
+}  // namespace pk

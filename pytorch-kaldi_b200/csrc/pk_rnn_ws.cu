@@ -740,7 +740,10 @@ long long* g_dbg_clk = nullptr;
 
 }  // namespace
 
-void set_debug_clock_buffer(long long* dev_ptr) { g_dbg_clk = dev_ptr; }
+void set_debug_clock_buffer(long long* dev_ptr) {
+  g_dbg_clk = dev_ptr;
+  set_debug_clock_buffer_tc(dev_ptr);
+}
 
 // (k-tiles, 8-unit tiles per CTA, cluster size): CL * 8 * MT >= 16 * KT >= H
 int ligru_fwd_ws(const RecFwdArgs& a_in, cudaStream_t stream) {

@@ -302,9 +302,9 @@ static void test_ligru(int T, int B, int H, int ndir, int act) {
   dPT.up(c.PT); dsc.up(c.scale); dsh.up(c.shift); dU.up(c.U); dmask.up(c.mask);
   const long long ldy = (long long)ndir * H + 2;
   const long long ldy16 = ((long long)ndir * H + 7) / 8 * 8;
-  const char* names[] = {"ws", "8", "8b", "10"};
-  const int vflags[] = {0, PK_REC_CLUSTER(8), PK_REC_CLUSTER(8) | PK_REC_SYNC_BARRIER, PK_REC_CLUSTER(10)};
-  const int npass = H > 512 ? 4 : 3;
+  const char* names[] = {"tc", "tc-nofence", "ws", "8", "8b", "10"};
+  const int vflags[] = {0, PK_REC_DBG_NOPROXYFENCE, PK_REC_WS, PK_REC_CLUSTER(8), PK_REC_CLUSTER(8) | PK_REC_SYNC_BARRIER, PK_REC_CLUSTER(10)};
+  const int npass = H > 560 ? 2 : (H > 512 ? 6 : 5);
   for (int pass = 0; pass < npass; ++pass) {
     const char* cl = names[pass];
     const int vflag = vflags[pass];
@@ -361,7 +361,7 @@ static void test_ligru(int T, int B, int H, int ndir, int act) {
     for (auto x : GT) gmax = std::max(gmax, (double)std::fabs(x));
     for (size_t i = 0; i < GT.size(); ++i)
       e16 = std::max(e16, std::fabs((double)__half2float(gGT16[i]) / s - GT[i]) / std::max(gmax, 1e-30));
-    const bool ws = pass == 0;  // the warp-specialised kernel writes GT16 only
+    const bool ws = pass <= 2;  // the tcgen05 / warp-specialised kernels write GT16 only
     snprintf(name, sizeof(name), "ligru_bwd cl%s T%d B%d H%d nd%d act%d", cl, T, B, H, ndir, act);
     report(name, std::max(ws ? 0.0 : maxrel(gGT, GT, 1e-30), e16), 3e-3);
   }
@@ -579,9 +579,11 @@ static void bench_all() {
     dgs.up({1024.f});
     ddY.up(randn(nch, 1e-3f));
     struct V { const char* name; int flags; };
-    const V vs[] = {{"ws (default)            ", 0},
-                    {"ws nostore              ", PK_REC_DBG_NOSTORE},
-                    {"ws noload/nostore       ", PK_REC_DBG_NOSTORE | PK_REC_DBG_NOLOAD},
+    const V vs[] = {{"tc (default)            ", 0},
+                    {"tc no proxy fence       ", PK_REC_DBG_NOPROXYFENCE},
+                    {"tc nostore              ", PK_REC_DBG_NOSTORE},
+                    {"tc noload/nostore       ", PK_REC_DBG_NOSTORE | PK_REC_DBG_NOLOAD},
+                    {"ws (round 1)            ", PK_REC_WS},
                     {"legacy cl10 st.async    ", PK_REC_CLUSTER(10)},
                     {"legacy cl8  st.async    ", PK_REC_CLUSTER(8)},
                     {"legacy cl8  barrier     ", PK_REC_CLUSTER(8) | PK_REC_SYNC_BARRIER}};
@@ -622,13 +624,13 @@ static void bench_all() {
                        dY16.p, 1104, dHT.p, dHT16.p, dHP16.p, dZT.p, dHCT.p, ld, nullptr);
       CK(cudaDeviceSynchronize());
       auto c = dclk.down();
-      printf("fwd phases (cycles/step): wait_step %.0f | mma %.0f | gates %.0f | stage+push %.0f | rings(shadow) %.0f | - %.0f\n",
+      printf("fwd phases (cycles/step): wait_acc %.0f | ld+xchg %.0f | gates+stage %.0f | push %.0f | rings(shadow) %.0f | - %.0f\n",
              c[0] / (double)T, c[1] / (double)T, c[2] / (double)T, c[3] / (double)T, c[4] / (double)T, c[5] / (double)T);
       pk_rnn_layer_bwd(PK_CELL_LIGRU, T, B, H, ndir, PK_ACT_RELU, ddY.p, dHT.p, dZT.p, dHCT.p, ld, dU.p, dmask.p, 1.f, dgs.p,
                        dGT.p, dGT16.p, nullptr);
       CK(cudaDeviceSynchronize());
       c = dclk.down();
-      printf("bwd phases (cycles/step): phaseA %.0f | stage+push %.0f | rings(shadow) %.0f | wait_step %.0f | mma+xchg+carry %.0f | - %.0f\n",
+      printf("bwd phases (cycles/step): pointwise+stage %.0f | push %.0f | rings(shadow) %.0f | wait_acc %.0f | ld+xchg+carry %.0f | - %.0f\n",
              c[0] / (double)T, c[1] / (double)T, c[2] / (double)T, c[3] / (double)T, c[4] / (double)T, c[5] / (double)T);
       pk_debug_set_clock_buffer(nullptr);
     }
@@ -692,6 +694,8 @@ int main(int argc, char** argv) {
     test_ligru(40, 32, 550, 2, PK_ACT_RELU);
     test_ligru(9, 3, 512, 2, PK_ACT_LEAKY_RELU);
     test_ligru(9, 11, 300, 1, PK_ACT_SIGMOID);
+    test_ligru(6, 8, 900, 2, PK_ACT_RELU);
+    test_ligru(5, 4, 64, 1, PK_ACT_TANH);
   }
   bench_all();
   printf("SELFTEST %s (%d failures)\n", g_fail ? "FAILED" : "PASSED", g_fail);
