@@ -63,7 +63,9 @@ extern "C" {
 /* timing experiments only (results are incomplete): skip the global stores / loads */
 #define PK_REC_DBG_NOSTORE 0x10000
 #define PK_REC_DBG_NOLOAD 0x20000
-#define PK_REC_DBG_NOPROXYFENCE 0x40000 /* tcgen05 kernels: no fence.proxy.async between chunk arrival and its MMAs */
+#define PK_REC_GROUPS(n) ((n) << 19) /* tcgen05 kernels: n in 1..3 arrival-group barriers per step (default 1) */
+#define PK_REC_DBG_NOPROXYFENCE 0x40000
+#define PK_REC_DBG_BLOCKINGWAIT 0x200000 /* tcgen05 kernels: MMA issuer suspends in try_wait instead of spinning on test_wait */ /* tcgen05 kernels: no fence.proxy.async between chunk arrival and its MMAs */
 
 const char* pk_last_error(void);
 int pk_version(void);

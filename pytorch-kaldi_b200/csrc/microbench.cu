@@ -144,6 +144,117 @@ static void run_exchange(int CL, int bytes, int mode, int nclusters) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// A2: the same 1 KB-per-source exchange with the knobs of the recurrent kernel: destination order (all CTAs walk
+// 0..CL-1 / staggered crank+i), number of receiver barriers (1, 3 arrival groups, one per source), and the
+// half-warp split (64 messages; lanes 0..15 take even slots, lanes 16..31 odd slots).
+// ------------------------------------------------------------------------------------------------
+struct X2Smem {
+  uint8_t buf[2][kMaxCL][1024];
+  uint64_t bar[2][kMaxCL];
+};
+__global__ void __launch_bounds__(256, 1) exchange2_kernel(int CL, int steps, int stagger, int nbar, int split, long long* out,
+                                                             int* fail) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  X2Smem& sm = *reinterpret_cast<X2Smem*>(smem_raw);
+  const uint32_t crank = cluster_ctarank();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gsz = (CL + 2) / 3;
+  // bytes each barrier expects per step
+  auto bar_of = [&](int slot, int src) { return nbar == 1 ? 0 : (nbar == 3 ? slot / gsz : src); };
+  if (tid == 0) {
+    for (int b = 0; b < 2; ++b)
+      for (int j = 0; j < kMaxCL; ++j) mbar_init(&sm.bar[b][j], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  cluster_sync_all();
+  long long t0 = 0;
+  bool ok = true;
+  __shared__ int s_ok;
+  if (tid == 0) s_ok = 1;
+  __syncthreads();
+  for (int k = 0; k < steps && ok; ++k) {
+    if (k == 16 && tid == 0) t0 = clock64();
+    const int nxt = (k + 1) & 1;
+    if (tid == 0) {
+      // arm: count the bytes every barrier will receive this step
+      int cnt[kMaxCL];
+      for (int j = 0; j < kMaxCL; ++j) cnt[j] = 0;
+      for (int src = 0; src < CL; ++src) {
+        const int slot = stagger ? (static_cast<int>(crank) - src + CL) % CL : static_cast<int>(crank);
+        cnt[bar_of(slot, src)] += 1024;
+      }
+      for (int j = 0; j < kMaxCL; ++j)
+        if (cnt[j]) mbar_arrive_expect_tx(&sm.bar[nxt][j], cnt[j]);
+    }
+    if (warp < 4) {
+      const int msg = split ? (warp * 16 + (lane & 15)) : tid;  // 64 messages of 16 B (split) or 128 of 8... (1 KB total)
+      const int nmsg_bytes = 16;
+      if (split || tid < 64) {
+        const uint4 v = make_uint4(k, msg, crank, tid);
+        const uint32_t laddr = smem_u32(&sm.buf[nxt][crank][(split ? msg : tid) * nmsg_bytes]);
+        const int i0 = split ? (lane >> 4) : 0, istep = split ? 2 : 1;
+        for (int i = i0; i < CL; i += istep) {
+          int dst = stagger ? static_cast<int>(crank) + i : i;
+          if (dst >= CL) dst -= CL;
+          const int slot = stagger ? i : dst;
+          const uint32_t lbar = smem_u32(&sm.bar[nxt][bar_of(slot, crank)]);
+          st_async_v4(mapa_shared(laddr, dst), v, mapa_shared(lbar, dst));
+        }
+      }
+    }
+    // consumer: one thread walks the barriers in order (like the MMA issuer), everyone then syncs
+    if (tid == 32) {
+      const int nb = nbar == 1 ? 1 : (nbar == 3 ? (CL + gsz - 1) / gsz : CL);
+      for (int j = 0; j < nb && ok; ++j) {
+        int bj = j;
+        if (nbar > 3) { bj = static_cast<int>(crank) - j; if (bj < 0) bj += CL; }
+        if (nbar == 3 && !stagger && bj != static_cast<int>(crank) / gsz) continue;  // unstaggered: one group barrier is used
+        ok = wait_bounded(&sm.bar[nxt][bj], (k >> 1) & 1, true);
+      }
+      if (!ok) s_ok = 0;
+    }
+    __syncthreads();
+    ok = s_ok != 0;
+  }
+  if (!ok && tid == 32) atomicAdd(fail, 1);
+  if (tid == 0 && blockIdx.x == 0) out[0] = clock64() - t0;
+  cluster_sync_all();
+}
+
+static void run_exchange2(int CL, int stagger, int nbar, int split) {
+  const int steps = 2016, nclusters = 8;
+  long long* d_out;
+  int* d_fail;
+  CK(cudaMalloc(&d_out, 64));
+  CK(cudaMalloc(&d_fail, 4));
+  CK(cudaMemset(d_fail, 0, 4));
+  CK(cudaFuncSetAttribute(exchange2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(X2Smem) + 1024));
+  CK(cudaFuncSetAttribute(exchange2_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nclusters * CL, 1, 1);
+  cfg.blockDim = dim3(256, 1, 1);
+  cfg.dynamicSmemBytes = sizeof(X2Smem) + 1024;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CK(cudaLaunchKernelEx(&cfg, exchange2_kernel, CL, steps, stagger, nbar, split, d_out, d_fail));
+  CK(cudaDeviceSynchronize());
+  long long cyc;
+  int fail;
+  CK(cudaMemcpy(&cyc, d_out, 8, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&fail, d_fail, 4, cudaMemcpyDeviceToHost));
+  printf("exchange2 CL=%2d 1 KB/src stagger=%d barriers=%d split=%d : %8.1f cyc/step%s\n", CL, stagger, nbar, split,
+         double(cyc) / (steps - 16), fail ? "  TIMEOUT" : "");
+  cudaFree(d_out);
+  cudaFree(d_fail);
+}
+
+// ------------------------------------------------------------------------------------------------
 // C: dependent tcgen05 chain.  A = [128 x K] fp16 resident in shared memory (128-byte-swizzled K-major chunks of
 // 64), B = [N x K]; per iteration the issuer fires K/16 MMAs + commit, four epilogue warps wait, tcgen05.ld the
 // [128 x N] fp32 accumulator, and arrive on `done`, which the issuer waits on before the next iteration.
@@ -261,27 +372,11 @@ static void run_chain(int kchunks) {
 // per 32-bit column.  Also a numerical check of that layout and of the N=16 swizzled B layout: D = A * B^T
 // against a CPU loop.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
-      "}\n" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&v)[8]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
-               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
-               : "memory");
-}
 __host__ __device__ inline float a_val(int m, int k) { return float((m * 7 + k * 3) % 11 - 5) * 0.125f; }
 __host__ __device__ inline float b_val(int n, int k) { return float((n * 5 + k * 2) % 13 - 6) * 0.25f; }
 
 template <int N>
-__global__ void __launch_bounds__(192, 1) umma_ts_kernel(int K, int iters, long long* out, float* dout) {
+__global__ void __launch_bounds__(320, 1) umma_ts_kernel(int K, int iters, long long* out, float* dout, int acol, int accol, int noise) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const int kchunks = (K + 63) / 64;
@@ -301,6 +396,8 @@ __global__ void __launch_bounds__(192, 1) umma_ts_kernel(int K, int iters, long 
   if (threadIdx.x == 0) {
     mbar_init(full, 1);
     mbar_init(done, 4);
+    mbar_init(done + 1, 1);
+    tmem_slot[1] = 0u;
     fence_mbar_init();
   }
   fence_proxy_async_smem();
@@ -309,7 +406,8 @@ __global__ void __launch_bounds__(192, 1) umma_ts_kernel(int K, int iters, long 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  constexpr uint32_t kACol = 64;  // A operand columns start here; accumulator at column 0
+  const uint32_t kACol = acol;  // A operand columns start here
+  const uint32_t tmem_acc = tmem_base + accol;
   if (warp >= 2) {  // each epilogue warp fills its 32 lanes of A
     const int lg = warp & 3;
     const int m = lg * 32 + lane;
@@ -343,17 +441,31 @@ __global__ void __launch_bounds__(192, 1) umma_ts_kernel(int K, int iters, long 
           const uint32_t b_base = smem_u32(sB + c * N * 128);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_f16_ts(tmem_base, tmem_base + kACol + c * 32 + k * 8, umma_desc_k_sw128(b_base + k * 32), idesc, (c | k) != 0);
+            umma_f16_ts(tmem_acc, tmem_base + kACol + c * 32 + k * 8, umma_desc_k_sw128(b_base + k * 32), idesc, (c | k) != 0);
         }
         umma_commit(full);
         const long long a1 = clock64();
         if (it >= 8) t_issue += a1 - a0;
       }
       mbar_wait(done, (iters - 1) & 1);
-      out[0] = clock64() - t0;
-      out[1] = t_issue;
+      if (blockIdx.x == 0) {
+        out[0] = clock64() - t0;
+        out[1] = t_issue;
+      }
+      *reinterpret_cast<volatile uint32_t*>(tmem_slot + 1) = 1u;  // stop the noise warps
     }
     __syncwarp();
+  } else if (warp >= 6) {
+    // noise warps: what the recurrent kernel's I/O warps do while the MMAs run (barrier spins + smem traffic)
+    volatile uint32_t* stop = reinterpret_cast<volatile uint32_t*>(tmem_slot + 1);
+    float* scratch = reinterpret_cast<float*>(sB);  // harmless: rows beyond the operand are not used
+    (void)scratch;
+    uint32_t spins = 0;
+    while (noise && *stop == 0u) {
+      if (noise & 1) (void)mbar_try_wait(done + 1, 1);  // never-completing barrier: a pure spin
+      if (noise & 2) { float x = reinterpret_cast<volatile float*>(bars + 8)[threadIdx.x & 63]; reinterpret_cast<volatile float*>(bars + 8)[threadIdx.x & 63] = x + 1.f; }
+      if (++spins > 400000000u) break;
+    }
   } else if (warp >= 2) {
     const int lg = warp & 3;
     for (int it = 0; it < iters; ++it) {
@@ -367,10 +479,10 @@ __global__ void __launch_bounds__(192, 1) umma_ts_kernel(int K, int iters, long 
           "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
           : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
             "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-          : "r"(tmem_base + (static_cast<uint32_t>(lg * 32) << 16))
+          : "r"(tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + accol)
           : "memory");
       tmem_ld_wait();
-      if (it == iters - 1) {
+      if (it == iters - 1 && blockIdx.x == 0) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) dout[(lg * 32 + lane) * 16 + j] = __uint_as_float(v[j]);
       }
@@ -379,14 +491,14 @@ __global__ void __launch_bounds__(192, 1) umma_ts_kernel(int K, int iters, long 
       if (lane == 0) mbar_arrive(done);
       if (it >= 8 && warp == 2 && lane == 0) t_wait += w1 - w0;
     }
-    if (warp == 2 && lane == 0) out[2] = t_wait;
+    if (warp == 2 && lane == 0 && blockIdx.x == 0) out[2] = t_wait;
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
-static void run_ts(int K) {
+static void run_ts(int K, int grid = 1, int cluster = 1, int acol = 64, int accol = 0, int noise = 0) {
   constexpr int N = 16;
   const int iters = 1008;
   long long* d_out;
@@ -395,9 +507,23 @@ static void run_ts(int K) {
   CK(cudaMalloc(&d_d, 128 * 16 * 4));
   CK(cudaMemset(d_out, 0, 64));
   const int kchunks = (K + 63) / 64;
-  const int smem = kchunks * N * 128 + 64 + 1024;
+  const int smem = kchunks * N * 128 + 1024 + 1024;
   CK(cudaFuncSetAttribute(umma_ts_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  umma_ts_kernel<N><<<1, 192, smem>>>(K, iters, d_out, d_d);
+  CK(cudaFuncSetAttribute(umma_ts_kernel<N>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(320, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, umma_ts_kernel<N>, K, iters, d_out, d_d, acol, accol, noise));
+  }
   CK(cudaDeviceSynchronize());
   long long o[3];
   std::vector<float> D(128 * 16);
@@ -411,16 +537,18 @@ static void run_ts(int K) {
       maxerr = std::max(maxerr, std::abs(ref - D[m * 16 + n]));
     }
   const double nn = iters - 8;
-  printf("umma TS    M=128 N= 16 K=%4d (%2d MMAs): %7.1f cyc/iter total | issue %6.1f | epilogue-side wait %6.1f | max |D - ref| = %.3e %s\n",
-         K, kchunks * 4, o[0] / nn, o[1] / nn, o[2] / nn, maxerr, maxerr < 1e-3 ? "OK" : "MISMATCH");
+  printf("umma TS grid=%3d cl=%d acol=%2d acc=%2d noise=%d K=%4d (%2d MMAs): %7.1f cyc/iter total | issue %6.1f | epilogue-side wait %6.1f | max |D - ref| = %.3e %s\n",
+         grid, cluster, acol, accol, noise, K, kchunks * 4, o[0] / nn, o[1] / nn, o[2] / nn, maxerr, maxerr < 1e-3 ? "OK" : "MISMATCH");
   cudaFree(d_out);
   cudaFree(d_d);
 }
 
 int main() {
+  setvbuf(stdout, nullptr, _IONBF, 0);
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
   printf("device: %s, %d SMs, clock %d MHz\n", prop.name, prop.multiProcessorCount, prop.clockRate / 1000);
+  if (getenv("PK_MB_ONLY_TS") == nullptr) {
   printf("--- A: st.async all-to-all ---\n");
   for (int bytes : {512, 1024, 2048, 4096}) run_exchange(9, bytes, 0, 8);
   run_exchange(9, 1024, 0, 1);
@@ -428,6 +556,10 @@ int main() {
   run_exchange(10, 896, 0, 8);
   run_exchange(5, 2048, 0, 8);
   run_exchange(8, 1024, 0, 16);
+  printf("--- A2: exchange knobs (1 KB per source, 9 CTAs) ---\n");
+  for (int split : {0, 1})
+    for (int stagger : {0, 1})
+      for (int nbar : {1, 3, 9}) run_exchange2(9, stagger, nbar, split);
   printf("--- B: cp.async.bulk smem->dsmem all-to-all ---\n");
   for (int bytes : {512, 1024, 2048, 4096}) run_exchange(9, bytes, 1, 8);
   run_exchange(9, 1024, 1, 1);
@@ -438,10 +570,16 @@ int main() {
   run_chain<32>(9);
   run_chain<64>(9);
   run_chain<16>(1);
+  }
   printf("--- D: A operand in tensor memory ---\n");
-  run_ts(64);
-  run_ts(560);
   run_ts(576);
-  run_ts(896);
+  run_ts(576, 72, 1);
+  run_ts(576, 72, 9);
+  run_ts(576, 144, 1);
+  run_ts(576, 1, 1, 32, 16);
+  run_ts(576, 1, 1, 64, 0, 1);
+  run_ts(576, 1, 1, 64, 0, 2);
+  run_ts(576, 1, 1, 64, 0, 3);
+  run_ts(576, 72, 9, 32, 16, 3);
   return 0;
 }

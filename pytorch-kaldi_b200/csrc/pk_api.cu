@@ -23,14 +23,16 @@ using namespace pk;
 
 namespace {
 struct RecFlags {
-  int cell, cluster, sync, dbg, legacy;
+  int cell, cluster, sync, dbg, legacy, groups;
 };
 RecFlags parse_cell(int cell) {
   RecFlags f;
   f.cluster = (cell >> 8) & 0x1f;  // PK_REC_CLUSTER(n)
   f.sync = (cell & PK_REC_SYNC_BARRIER) ? 0 : -1;
-  f.dbg = ((cell & PK_REC_DBG_NOSTORE) ? 1 : 0) | ((cell & PK_REC_DBG_NOLOAD) ? 2 : 0) | ((cell & PK_REC_DBG_NOPROXYFENCE) ? 4 : 0);
+  f.dbg = ((cell & PK_REC_DBG_NOSTORE) ? 1 : 0) | ((cell & PK_REC_DBG_NOLOAD) ? 2 : 0) | ((cell & PK_REC_DBG_NOPROXYFENCE) ? 4 : 0) |
+          ((cell & PK_REC_DBG_BLOCKINGWAIT) ? 8 : 0);
   f.legacy = (cell & PK_REC_LEGACY) ? 1 : ((cell & PK_REC_WS) ? 2 : 0);
+  f.groups = (cell >> 19) & 3;
   f.cell = cell & PK_CELL_MASK;
   return f;
 }
@@ -132,7 +134,7 @@ int pk_rnn_layer_fwd(int cell, int T, int B, int H, int ndir, int act, const flo
   a.Y32 = Y32; a.ldy32 = ldy32; a.Y16 = static_cast<__half*>(Y16); a.ldy16 = ldy16;
   a.HT = HT; a.HT16 = static_cast<__half*>(HT16); a.HP16 = static_cast<__half*>(HP16);
   a.ZT = ZT; a.HCT = HCT; a.ldt = ldt;
-  a.cluster = f.cluster; a.sync = f.sync; a.dbg = f.dbg; a.legacy = f.legacy;
+  a.cluster = f.cluster; a.sync = f.sync; a.dbg = f.dbg; a.legacy = f.legacy; a.groups = f.groups;
   a.force_z0 = (f.cell == PK_CELL_RNN) ? 1 : 0;
   return ligru_fwd(a, static_cast<cudaStream_t>(stream));
 }
@@ -147,7 +149,7 @@ int pk_rnn_layer_bwd(int cell, int T, int B, int H, int ndir, int act, const flo
   a.T = T; a.B = B; a.H = H; a.ndir = ndir; a.act = act;
   a.dYT = dYT; a.HT = HT; a.ZT = ZT; a.HCT = HCT; a.ldt = ldt; a.U = U; a.mask = mask;
   a.mask_scalar = mask_scalar; a.gscale = gscale; a.GT = GT; a.GT16 = static_cast<__half*>(GT16);
-  a.cluster = f.cluster; a.sync = f.sync; a.dbg = f.dbg; a.legacy = f.legacy;
+  a.cluster = f.cluster; a.sync = f.sync; a.dbg = f.dbg; a.legacy = f.legacy; a.groups = f.groups;
   return ligru_bwd(a, static_cast<cudaStream_t>(stream));
 }
 

@@ -58,6 +58,7 @@ struct RecFwdArgs {
   long long* dbg_clk = nullptr;  // bring-up: per-phase cycle sums of CTA 0 / warp 0 (8 slots)
   int sync = -1;    // -1 = default (st.async + mbarrier), 0 = barrier.cluster, 1 = st.async
   int dbg = 0;      // timing experiments only: bit0 skip global stores, bit1 skip global loads
+  int groups = 0;   // tcgen05 kernels: arrival-group barriers per buffer (1..3), 0 = default
 };
 int ligru_fwd(const RecFwdArgs& a, cudaStream_t stream);
 
@@ -79,6 +80,7 @@ struct RecBwdArgs {
   long long* dbg_clk = nullptr;
   int sync = -1;
   int dbg = 0;
+  int groups = 0;
 };
 int ligru_bwd(const RecBwdArgs& a, cudaStream_t stream);
 // warp-specialised variants (pk_rnn_ws.cu); the bwd one writes GT16 only

@@ -51,6 +51,7 @@ constexpr int kThreads = 320;
 constexpr uint32_t kACol = 32;          // first TMEM column of the stationary weights
 constexpr uint32_t kChunkBytes = 2048;  // 16 rows x 128 bytes: one source CTA's 64 units
 constexpr uint32_t kIdesc = umma_idesc(0, 128, 16);
+constexpr int kTrace0 = 200;  // bring-up: steps [kTrace0, kTrace0 + 8) of CTA 0 are time-stamped into dbg_clk[8..]
 constexpr uint32_t kFwdTx = kRows * 128;      // bytes one source CTA delivers per step (8 rows x 64 units fp16)
 constexpr uint32_t kBwdTx = 2 * kRows * 128;  // backward: two gates
 
@@ -60,7 +61,6 @@ __device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gsrc)
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
 // bounded waits: a protocol bug must trap (the launch fails with an error) instead of hanging the device
 __device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t parity) {
@@ -95,27 +95,84 @@ __device__ __forceinline__ void tc_wait_cluster(uint64_t* bar, uint32_t parity) 
   }
 }
 
-// ---- the MMA-issuing thread: per step, per source chunk: wait -> 4 MMAs; then commit to acc_full[buf]
-// src_bar[buf][c] completes when source CTA c's block of this step has landed in opnd[buf][c]
-__device__ __forceinline__ void mma_step(uint8_t* opnd_buf, uint64_t* src_bar_buf, uint64_t* acc_full, uint32_t tmem_base,
-                                         uint32_t acc_col, int CL, uint32_t crank, bool wait_data, uint32_t parity,
-                                         uint32_t tx_bytes, bool proxy_fence) {
-  for (int i = 0; i < CL; ++i) {
-    int c = static_cast<int>(crank) + i;
-    if (c >= CL) c -= CL;  // own chunk first: it also proves that the local epilogue has released the accumulator
+// spinning variant (mbarrier.test_wait never suspends the thread): used by the MMA issuer, whose wake-up latency
+// is on the serial critical path of every step
+__device__ __forceinline__ void tc_spin_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t polls = 0;
+  long long t0 = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((++polls & 0xfffu) == 0) {
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > 4000000000LL) __trap();
+    }
+  }
+}
+
+// Source chunks are grouped by ARRIVAL ORDER.  Every CTA pushes to destinations crank, crank+1, ... (mod CL), so
+// the block of source s reaches destination d in slot i = (d - s) mod CL; slots [g * gsz, (g+1) * gsz) share one
+// mbarrier (kGroups barriers per buffer instead of one per source: a barrier hand-off costs ~100 cycles, a chunk's
+// MMAs ~70).
+constexpr int kDefaultGroups = 1;
+constexpr int kGroups = 3;  // at most; the launch picks 1..3 (RecArgs::groups)
+__device__ __forceinline__ int group_size(int CL, int ng) { return (CL + ng - 1) / ng; }
+
+// ---- the MMA-issuing thread, one step: per arrival group: wait -> re-arm -> that group's MMAs (chunk order =
+// arrival order); finally commit to acc_full.
+__device__ __forceinline__ void mma_step(uint32_t opnd_addr, uint64_t* grp_bar_buf, uint64_t* acc_full, uint32_t tmem_base,
+                                         uint32_t acc_col, int CL, int gsz, uint32_t crank, bool wait_data, uint32_t parity,
+                                         uint32_t tx_bytes, bool proxy_fence, bool spin, long long* trace) {
+  if (trace) trace[0] = clock64();
+  // Running operand addresses (chunk c = crank, crank-1, ... with wrap-around): per MMA only two uniform adds remain.
+  // Shared-memory descriptor: low word = (address >> 4) | LBO field, high word constant (SBO 1024 B, version 1,
+  // 128-byte swizzle) — advancing the address by x bytes adds x >> 4 to the low word.
+  constexpr uint32_t kDescHi = static_cast<uint32_t>((1024u >> 4) | (1u << 14) | (2u << 29));
+  const uint32_t d_tmem = tmem_base + acc_col;
+  int c = static_cast<int>(crank);
+  uint32_t a_addr = tmem_base + kACol + crank * 32u;
+  uint32_t b_lo = (((opnd_addr + crank * kChunkBytes) & 0x3FFFFu) >> 4) | (1u << 16);
+  uint32_t first = 0;  // the very first MMA of the step overwrites the accumulator
+  int i = 0;
+  for (int g = 0; i < CL; ++g) {
+    const int i_end = min(CL, i + gsz);
     if (wait_data) {
-      tc_wait_cluster(&src_bar_buf[c], parity);
-      mbar_arrive_expect_tx(&src_bar_buf[c], tx_bytes);  // re-arm for this buffer's next use (two steps on)
+      if (spin) tc_spin_cluster(&grp_bar_buf[g], parity); else tc_wait_cluster(&grp_bar_buf[g], parity);
+      mbar_arrive_expect_tx(&grp_bar_buf[g], tx_bytes * static_cast<uint32_t>(i_end - i));  // re-arm (use after next)
       if (proxy_fence) fence_proxy_async_smem();
       tc_fence_after();
     }
-    const uint32_t b_base = smem_u32(opnd_buf + c * kChunkBytes);
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk)
-      umma_f16_ts(tmem_base + acc_col, tmem_base + kACol + static_cast<uint32_t>(c * 32 + kk * 8),
-                  umma_desc_k_sw128(b_base + kk * 32), kIdesc, (i | kk) != 0);
+    if (trace) trace[g == 0 ? 1 : 2] = clock64();
+    for (; i < i_end; ++i) {
+      const uint64_t hi = static_cast<uint64_t>(kDescHi) << 32;
+      // branch-free body (a branch per MMA serialises the descriptor chains); k-steps beyond H multiply zero weights
+      umma_f16_ts(d_tmem, a_addr, hi | b_lo, kIdesc, first);
+      umma_f16_ts(d_tmem, a_addr + 8, hi | (b_lo + 2), kIdesc, 1u);
+      umma_f16_ts(d_tmem, a_addr + 16, hi | (b_lo + 4), kIdesc, 1u);
+      umma_f16_ts(d_tmem, a_addr + 24, hi | (b_lo + 6), kIdesc, 1u);
+      first = 1u;
+      if (c == 0) {
+        c = CL - 1;
+        a_addr += static_cast<uint32_t>(CL - 1) * 32u;
+        b_lo += static_cast<uint32_t>(CL - 1) * (kChunkBytes >> 4);
+      } else {
+        --c;
+        a_addr -= 32u;
+        b_lo -= (kChunkBytes >> 4);
+      }
+    }
   }
   umma_commit(acc_full);
+  if (trace) trace[3] = clock64();
 }
 
 // =====================================================================================
@@ -125,14 +182,14 @@ struct FwdTc {
   uint8_t hbuf[2][kMaxCL][kChunkBytes];  // B operand: [buffer][source CTA][16 rows x 128 B, 128B-swizzled]
   float inr[RI][2][kUPC][kRows];         // [slot][gate h,z][unit][row]
   float outr[RO][3][kUPC][kRows];        // [slot][h, z, hc][unit][row]
-  float xbuf[2][kUPC][4];                // accumulator rows handed to the other lane half
-  __half stage[kRows][kUPC];             // new state, [row][unit]: 16-byte messages of 8 units
-  uint64_t src_bar[2][kMaxCL];
+  __half stage[4][kRows][16];            // per epilogue warp: new state [row][16 units] -> 16-byte messages of 8 units
+  uint64_t src_bar[2][kGroups];          // [buffer][arrival group]
   uint64_t acc_full[2];
   uint64_t in_full[RI], in_empty[RI], out_full[RO], out_empty[RO];
   uint32_t tmem_slot;
 };
 
+template <int ACT>  // activation id: the per-element switch would be an indirect branch (BRX) on the serial path
 __global__ void __launch_bounds__(kThreads, 1) ligru_fwd_tc_kernel(const RecFwdArgs a, const int CL) {
   extern __shared__ uint8_t smem_raw[];
   FwdTc& sm = *reinterpret_cast<FwdTc*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -144,13 +201,14 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_fwd_tc_kernel(const RecFwdA
   const int H = a.H, B = a.B, T = a.T;
   const int nrows = a.ndir * B;
   const int cta_ubase = crank * kUPC;
+  const int gsz = group_size(CL, a.groups);  // source chunks per arrival-group barrier
 
   for (int i = threadIdx.x; i < static_cast<int>(sizeof(sm.hbuf) / 16); i += blockDim.x)
     reinterpret_cast<uint4*>(&sm.hbuf[0][0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
   for (int i = threadIdx.x; i < RI * 2 * kUPC * kRows; i += blockDim.x) (&sm.inr[0][0][0][0])[i] = 0.f;
   if (threadIdx.x == 0) {
     for (int b = 0; b < 2; ++b) {
-      for (int c = 0; c < CL; ++c) mbar_init(&sm.src_bar[b][c], 1);
+      for (int g = 0; g < kGroups; ++g) mbar_init(&sm.src_bar[b][g], 1);
       mbar_init(&sm.acc_full[b], 1);
     }
     for (int s = 0; s < RI; ++s) { mbar_init(&sm.in_full[s], NIO); mbar_init(&sm.in_empty[s], 4); }
@@ -158,7 +216,8 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_fwd_tc_kernel(const RecFwdA
     fence_mbar_init();
     // arm every per-source barrier for its first use (buffer 1: step 1, buffer 0: step 2)
     for (int b = 0; b < 2; ++b)
-      for (int c = 0; c < CL; ++c) mbar_arrive_expect_tx(&sm.src_bar[b][c], kFwdTx);
+      for (int g = 0; g * gsz < CL; ++g)
+        mbar_arrive_expect_tx(&sm.src_bar[b][g], kFwdTx * static_cast<uint32_t>(min(CL, (g + 1) * gsz) - g * gsz));
   }
   fence_proxy_async_smem();  // the zero-filled operand buffers are read by the tensor core (async proxy) at step 0
   if (warp == 1) tmem_alloc<512>(&sm.tmem_slot);
@@ -167,13 +226,13 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_fwd_tc_kernel(const RecFwdA
   tc_fence_after();
   const uint32_t tmem_base = sm.tmem_slot;
 
-  // ---- stationary weights -> tensor memory (epilogue warps; lane m < 64: Uh[unit m], lane 64 + m: Uz[unit m])
+  // ---- stationary weights -> tensor memory (epilogue warps).  Gate rows are interleaved per 32-lane group so that
+  //      both gates of a unit live in ONE warp: lane 32g + l holds gate (l >> 4) of local unit 16g + (l & 15)
   if (warp >= kEpiWarp0 && warp < kIoWarp0) {
     const int lg = warp & 3;
-    const int m = lg * 32 + lane;
-    const int u = cta_ubase + (m & 63);
+    const int u = cta_ubase + lg * 16 + (lane & 15);
     const bool u_ok = u < H;
-    const float* Urow = a.U + (static_cast<long long>(m >> 6) * H + (u_ok ? u : 0)) * H;
+    const float* Urow = a.U + (static_cast<long long>(lane >> 4) * H + (u_ok ? u : 0)) * H;
     const int KP = CL * kUPC;
     for (int k0 = 0; k0 < KP; k0 += 16) {
       uint32_t v[8];
@@ -199,21 +258,21 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_fwd_tc_kernel(const RecFwdA
       const bool pf = !(a.dbg & 4);
       for (int k = 0; k < T; ++k) {
         const int cur = k & 1;
-        mma_step(&sm.hbuf[cur][0][0], &sm.src_bar[cur][0], &sm.acc_full[cur], tmem_base, static_cast<uint32_t>(cur * 16), CL,
-                 crank, k > 0, static_cast<uint32_t>(((k - 1) >> 1) & 1), kFwdTx, pf);
+        long long* tr = (a.dbg_clk && blockIdx.x == 0 && k >= kTrace0 && k < kTrace0 + 8) ? a.dbg_clk + 8 + (k - kTrace0) * 16 : nullptr;
+        mma_step(smem_u32(&sm.hbuf[cur][0][0]), &sm.src_bar[cur][0], &sm.acc_full[cur], tmem_base, static_cast<uint32_t>(cur * 16), CL,
+                 gsz, crank, k > 0, static_cast<uint32_t>(((k - 1) >> 1) & 1), kFwdTx, pf, !(a.dbg & 8), tr);
       }
     }
     __syncwarp();
   } else if (warp >= kEpiWarp0 && warp < kIoWarp0) {
-    // ================= epilogue warps: gates =================
-    const int lg = warp & 3;
-    const int m = lg * 32 + lane;      // TMEM lane = gate row of this CTA
-    const int half = m >> 6;           // 0: lanes hold the candidate gate, 1: the update gate
-    const int ul = m & 63;             // local unit
+    // ================= epilogue warps: gates (each warp is self-contained: no block-level barrier) =================
+    const int lg = warp & 3;           // TMEM lane group this warp may read
+    const int ew = warp - kEpiWarp0;   // staging buffer of this warp
+    const int half = lane >> 4;        // 0: this lane's TMEM row is the candidate gate, 1: the update gate
+    const int ul = lg * 16 + (lane & 15);  // local unit
     const int u = cta_ubase + ul;
     const bool u_ok = u < H;
     const int r0 = half * 4;           // this thread finishes rows r0 .. r0+3 of its unit
-    const int et = (warp - kEpiWarp0) * 32 + lane;  // 0..127
     float msk[4];
     bool rok[4];
 #pragma unroll
@@ -228,14 +287,18 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_fwd_tc_kernel(const RecFwdA
       sc_z = __ldg(a.scale + H + u); sh_z = __ldg(a.shift + H + u);
     }
     float hprev[4] = {0.f, 0.f, 0.f, 0.f};
-    const int act = a.act;
     const bool z0 = a.force_z0 != 0;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(lg * 32) << 16);
-    // push bookkeeping: message (row, 8-unit group j) of this CTA's block, destinations et>>6, +2, ...
-    const int prow = (et & 63) >> 3, pj = et & 7;
+    // push bookkeeping: the warp owns 16 messages (row, 8-unit group); lane -> message lane & 15, destinations
+    // lane >> 4, +2, ...
+    const int prow = (lane & 15) >> 1, pjl = lane & 1;
+    const int pj = lg * 2 + pjl;  // 8-unit group inside the CTA's 64 units
     const uint32_t msg_off = static_cast<uint32_t>(crank * kChunkBytes + prow * 128 + ((pj ^ prow) << 4));
 
-    const bool clk_on = a.dbg_clk != nullptr && blockIdx.x == 0 && et == 0;
+    uint32_t gtab = 0;  // arrival group of slot i, 2 bits each (no division on the per-step path)
+    for (int i = 0; i < CL; ++i) gtab |= static_cast<uint32_t>(i / gsz) << (2 * i);
+    const bool clk_on = a.dbg_clk != nullptr && blockIdx.x == 0 && ew == 0 && lane == 0;
+    const bool clk3 = a.dbg_clk != nullptr && blockIdx.x == 0 && ew == 3 && lane == 0;
     long long tsum[6] = {0, 0, 0, 0, 0, 0};
     tc_wait(&sm.in_full[0], 0);
     float4 ph = *reinterpret_cast<const float4*>(&sm.inr[0][0][ul][r0]);
@@ -249,23 +312,20 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_fwd_tc_kernel(const RecFwdA
       tc_wait(&sm.acc_full[cur], static_cast<uint32_t>((k >> 1) & 1));
       tc_fence_after();
       if (clk_on) t1 = clock64();
+      if (clk3 && k >= kTrace0 && k < kTrace0 + 8) a.dbg_clk[8 + (k - kTrace0) * 16 + 9] = clock64();
       uint32_t v[8];
       tmem_ld_32x8(lane_addr + static_cast<uint32_t>(cur * 16), v);
       tmem_ld_wait();
       tc_fence_before();
-      // hand the rows the OTHER half finishes to it: half 0 gives rows 4..7, half 1 gives rows 0..3
-      *reinterpret_cast<float4*>(&sm.xbuf[half][ul][0]) =
-          half ? make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]))
-               : make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
-      epi_bar(1);
-      const float4 xo = *reinterpret_cast<const float4*>(&sm.xbuf[half ^ 1][ul][0]);
+      // lane l and lane l ^ 16 hold the two gates of one unit: swap the rows the partner finishes
       float ah[4], az[4];
-      if (half == 0) {
-        ah[0] = __uint_as_float(v[0]); ah[1] = __uint_as_float(v[1]); ah[2] = __uint_as_float(v[2]); ah[3] = __uint_as_float(v[3]);
-        az[0] = xo.x; az[1] = xo.y; az[2] = xo.z; az[3] = xo.w;
-      } else {
-        az[0] = __uint_as_float(v[4]); az[1] = __uint_as_float(v[5]); az[2] = __uint_as_float(v[6]); az[3] = __uint_as_float(v[7]);
-        ah[0] = xo.x; ah[1] = xo.y; ah[2] = xo.z; ah[3] = xo.w;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float mine = __uint_as_float(half ? v[4 + i] : v[i]);      // own gate, own rows
+        const float give = __uint_as_float(half ? v[i] : v[4 + i]);      // own gate, partner's rows
+        const float got = __shfl_xor_sync(0xffffffffu, give, 16);        // partner's gate, own rows
+        ah[i] = half ? got : mine;
+        az[i] = half ? mine : got;
       }
       if (clk_on) t2 = clock64();
       // ---- gates (reference :1133-1136)
@@ -274,20 +334,24 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_fwd_tc_kernel(const RecFwdA
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float zt = z0 ? 0.f : sigmoid_fast(fmaf(sc_z, pzv[i], sh_z) + az[i]);
-        const float hc = act_fwd_fast(act, fmaf(sc_h, phv[i], sh_h) + ah[i]) * msk[i];
+        const float hc = act_fwd_fast(ACT, fmaf(sc_h, phv[i], sh_h) + ah[i]) * msk[i];
         float h = fmaf(zt, hprev[i] - hc, hc);
         if (!rok[i]) h = 0.f;
         hn[i] = h; zz[i] = zt; hcv[i] = hc; hprev[i] = h;
-        sm.stage[r0 + i][ul] = f16_sat(h);
+        sm.stage[ew][r0 + i][lane & 15] = f16_sat(h);
       }
-      epi_bar(2);
+      __syncwarp();
       if (clk_on) t3 = clock64();
-      // ---- push this CTA's 8 x 64 block to every CTA of the cluster (data + complete_tx in one message)
+      // ---- push the warp's 8 x 16 block to every CTA of the cluster (data + complete_tx in one message)
       if (k + 1 < T) {
-        const uint4 val = *reinterpret_cast<const uint4*>(&sm.stage[prow][pj * 8]);
+        const uint4 val = *reinterpret_cast<const uint4*>(&sm.stage[ew][prow][pjl * 8]);
         const uint32_t laddr = smem_u32(&sm.hbuf[nxt][0][0]) + msg_off;
-        const uint32_t lbar = smem_u32(&sm.src_bar[nxt][crank]);
-        for (int dst = et >> 6; dst < CL; dst += 2) st_async_v4(mapa_shared(laddr, dst), val, mapa_shared(lbar, dst));
+        const uint32_t lbar0 = smem_u32(&sm.src_bar[nxt][0]);
+        int dst = static_cast<int>(crank) + (lane >> 4);
+        for (int i = lane >> 4; i < CL; i += 2, dst += 2) {  // slot i: destination crank + i -> its arrival group i / gsz
+          if (dst >= CL) dst -= CL;
+          st_async_v4(mapa_shared(laddr, dst), val, mapa_shared(lbar0 + ((gtab >> (2 * i)) & 3u) * 8u, dst));
+        }
       }
       if (clk_on) t4 = clock64();
       // ---- in the shadow of the transit: outputs -> I/O warps, next step's projections <- ring
@@ -309,7 +373,12 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_fwd_tc_kernel(const RecFwdA
       if (clk_on) {
         const long long t5 = clock64();
         tsum[0] += t1 - t0; tsum[1] += t2 - t1; tsum[2] += t3 - t2; tsum[3] += t4 - t3; tsum[4] += t5 - t4;
+        if (k >= kTrace0 && k < kTrace0 + 8) {
+          long long* tr = a.dbg_clk + 8 + (k - kTrace0) * 16;
+          tr[4] = t1; tr[5] = t2; tr[6] = t3; tr[7] = t4; tr[8] = t5;
+        }
       }
+      if (clk3 && k >= kTrace0 && k < kTrace0 + 8) a.dbg_clk[8 + (k - kTrace0) * 16 + 10] = clock64();
     }
     if (clk_on)
       for (int i = 0; i < 6; ++i) a.dbg_clk[i] = tsum[i];
@@ -461,14 +530,14 @@ struct BwdTc {
   uint8_t gbuf[2][kMaxCL][kChunkBytes];  // B operand: rows 0..7 = da, rows 8..15 = dpz of the cluster's 8 batch rows
   float inr[RI][4][kUPC][kRows];         // [slot][dy, z, hc, hprev][unit][row]
   __half outr[RO][2][kUPC][kRows];       // [slot][da, dpz][unit][row]  (scaled fp16)
-  float xbuf[2][kUPC][4];
-  __half stage[2][kRows][kUPC];          // [gate][row][unit]
-  uint64_t src_bar[2][kMaxCL];
+  __half stage[4][2][kRows][16];         // per epilogue warp: [gate][row][16 units]
+  uint64_t src_bar[2][kGroups];          // [buffer][arrival group]
   uint64_t acc_full[2];
   uint64_t in_full[RI], in_empty[RI], out_full[RO], out_empty[RO];
   uint32_t tmem_slot;
 };
 
+template <int ACT>
 __global__ void __launch_bounds__(kThreads, 1) ligru_bwd_tc_kernel(const RecBwdArgs a, const int CL) {
   extern __shared__ uint8_t smem_raw[];
   BwdTc& sm = *reinterpret_cast<BwdTc*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -480,20 +549,22 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_bwd_tc_kernel(const RecBwdA
   const int H = a.H, B = a.B, T = a.T;
   const int nrows = a.ndir * B;
   const int cta_ubase = crank * kUPC;
+  const int gsz = group_size(CL, a.groups);  // source chunks per arrival-group barrier
 
   for (int i = threadIdx.x; i < static_cast<int>(sizeof(sm.gbuf) / 16); i += blockDim.x)
     reinterpret_cast<uint4*>(&sm.gbuf[0][0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
   for (int i = threadIdx.x; i < RI * 4 * kUPC * kRows; i += blockDim.x) (&sm.inr[0][0][0][0])[i] = 0.f;
   if (threadIdx.x == 0) {
     for (int b = 0; b < 2; ++b) {
-      for (int c = 0; c < CL; ++c) mbar_init(&sm.src_bar[b][c], 1);
+      for (int g = 0; g < kGroups; ++g) mbar_init(&sm.src_bar[b][g], 1);
       mbar_init(&sm.acc_full[b], 1);
     }
     for (int s = 0; s < RI; ++s) { mbar_init(&sm.in_full[s], NIO); mbar_init(&sm.in_empty[s], 4); }
     for (int s = 0; s < RO; ++s) { mbar_init(&sm.out_full[s], 4); mbar_init(&sm.out_empty[s], kIoWarps); }
     fence_mbar_init();
     for (int b = 0; b < 2; ++b)
-      for (int c = 0; c < CL; ++c) mbar_arrive_expect_tx(&sm.src_bar[b][c], kBwdTx);
+      for (int g = 0; g * gsz < CL; ++g)
+        mbar_arrive_expect_tx(&sm.src_bar[b][g], kBwdTx * static_cast<uint32_t>(min(CL, (g + 1) * gsz) - g * gsz));
   }
   fence_proxy_async_smem();
   if (warp == 1) tmem_alloc<512>(&sm.tmem_slot);
@@ -502,13 +573,13 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_bwd_tc_kernel(const RecBwdA
   tc_fence_after();
   const uint32_t tmem_base = sm.tmem_slot;
 
-  // ---- stationary U^T -> tensor memory: lane m < 64: A[m][j] = Uh[j][unit m]; lane 64 + m: Uz[j][unit m]
+  // ---- stationary U^T -> tensor memory: lane 32g + l, unit = 16g + (l & 15): A[.][j] = Uh[j][unit] (l < 16) or
+  //      Uz[j][unit] (l >= 16) — both halves of a unit's sum live in one warp
   if (warp >= kEpiWarp0 && warp < kIoWarp0) {
     const int lg = warp & 3;
-    const int m = lg * 32 + lane;
-    const int u = cta_ubase + (m & 63);
+    const int u = cta_ubase + lg * 16 + (lane & 15);
     const bool u_ok = u < H;
-    const float* Ucol = a.U + static_cast<long long>(m >> 6) * H * H + (u_ok ? u : 0);
+    const float* Ucol = a.U + static_cast<long long>(lane >> 4) * H * H + (u_ok ? u : 0);
     const int KP = CL * kUPC;
     for (int k0 = 0; k0 < KP; k0 += 16) {
       uint32_t v[8];
@@ -535,21 +606,20 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_bwd_tc_kernel(const RecBwdA
       for (int k = T - 1; k > 0; --k) {
         const int it = T - 1 - k;
         const int buf = k & 1;
-        mma_step(&sm.gbuf[buf][0][0], &sm.src_bar[buf][0], &sm.acc_full[buf], tmem_base, static_cast<uint32_t>(buf * 16), CL,
-                 crank, true, static_cast<uint32_t>((it >> 1) & 1), kBwdTx, pf);
+        mma_step(smem_u32(&sm.gbuf[buf][0][0]), &sm.src_bar[buf][0], &sm.acc_full[buf], tmem_base, static_cast<uint32_t>(buf * 16), CL,
+                 gsz, crank, true, static_cast<uint32_t>((it >> 1) & 1), kBwdTx, pf, !(a.dbg & 8), nullptr);
       }
     }
     __syncwarp();
   } else if (warp >= kEpiWarp0 && warp < kIoWarp0) {
-    // ================= epilogue warps: pointwise backward =================
+    // ================= epilogue warps: pointwise backward (self-contained warps) =================
     const int lg = warp & 3;
-    const int m = lg * 32 + lane;
-    const int half = m >> 6;
-    const int ul = m & 63;
+    const int ew = warp - kEpiWarp0;
+    const int half = lane >> 4;
+    const int ul = lg * 16 + (lane & 15);
     const int u = cta_ubase + ul;
     const bool u_ok = u < H;
     const int r0 = half * 4;
-    const int et = (warp - kEpiWarp0) * 32 + lane;
     float msk[4], rmk[4];
     bool rok[4];
 #pragma unroll
@@ -562,13 +632,16 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_bwd_tc_kernel(const RecBwdA
     const float s = a.gscale ? __ldg(a.gscale) : 1.f;
     const float inv_s = 1.f / s;
     float carry[4] = {0.f, 0.f, 0.f, 0.f};
-    const int act = a.act;
-    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + static_cast<uint32_t>(half * 8);
-    // push bookkeeping: 128 messages (gate, row, 8-unit group) -> one per epilogue thread, every destination
-    const int pg = et >> 6, prow = (et & 63) >> 3, pj = et & 7;
+    // lanes < 16 own the Uh^T partial sums (valid in accumulator columns 0..7), lanes >= 16 the Uz^T ones (8..15)
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(lg * 32) << 16);
+    // push bookkeeping: the warp owns 32 messages (gate, row, 8-unit group) -> one per lane, every destination
+    const int pg = lane >> 4, prow = (lane & 15) >> 1, pjl = lane & 1;
+    const int pj = lg * 2 + pjl;
     const uint32_t msg_off = static_cast<uint32_t>(crank * kChunkBytes + pg * 1024 + prow * 128 + ((pj ^ prow) << 4));
 
-    const bool clk_on = a.dbg_clk != nullptr && blockIdx.x == 0 && et == 0;
+    uint32_t gtab = 0;  // arrival group of slot i, 2 bits each (no division on the per-step path)
+    for (int i = 0; i < CL; ++i) gtab |= static_cast<uint32_t>(i / gsz) << (2 * i);
+    const bool clk_on = a.dbg_clk != nullptr && blockIdx.x == 0 && ew == 0 && lane == 0;
     long long tsum[6] = {0, 0, 0, 0, 0, 0};
     tc_wait(&sm.in_full[0], 0);
     float4 dy = *reinterpret_cast<const float4*>(&sm.inr[0][0][ul][r0]);
@@ -591,22 +664,26 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_bwd_tc_kernel(const RecBwdA
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float dh = dyv[i] + carry[i];
-        float da = dh * (1.f - zv[i]) * msk[i] * act_bwd_from_out(act, hcv[i] * rmk[i]);
+        float da = dh * (1.f - zv[i]) * msk[i] * act_bwd_from_out(ACT, hcv[i] * rmk[i]);
         float dz = dh * (hpv[i] - hcv[i]) * zv[i] * (1.f - zv[i]);
         if (!rok[i]) { da = 0.f; dz = 0.f; }
         keep[i] = dh * zv[i];
         da16[i] = f16_sat(da * s);
         dz16[i] = f16_sat(dz * s);
-        sm.stage[0][r0 + i][ul] = da16[i];
-        sm.stage[1][r0 + i][ul] = dz16[i];
+        sm.stage[ew][0][r0 + i][lane & 15] = da16[i];
+        sm.stage[ew][1][r0 + i][lane & 15] = dz16[i];
       }
-      epi_bar(2);
+      __syncwarp();
       if (clk_on) t1 = clock64();
       if (k > 0) {
-        const uint4 val = *reinterpret_cast<const uint4*>(&sm.stage[pg][prow][pj * 8]);
+        const uint4 val = *reinterpret_cast<const uint4*>(&sm.stage[ew][pg][prow][pjl * 8]);
         const uint32_t laddr = smem_u32(&sm.gbuf[buf][0][0]) + msg_off;
-        const uint32_t lbar = smem_u32(&sm.src_bar[buf][crank]);
-        for (int dst = 0; dst < CL; ++dst) st_async_v4(mapa_shared(laddr, dst), val, mapa_shared(lbar, dst));
+        const uint32_t lbar0 = smem_u32(&sm.src_bar[buf][0]);
+        int dst = static_cast<int>(crank);
+        for (int i = 0; i < CL; ++i, ++dst) {
+          if (dst >= CL) dst -= CL;
+          st_async_v4(mapa_shared(laddr, dst), val, mapa_shared(lbar0 + ((gtab >> (2 * i)) & 3u) * 8u, dst));
+        }
       }
       if (clk_on) t2 = clock64();
       // ---- in the shadow of the transit: outputs -> I/O warps, next step's operands <- ring
@@ -639,18 +716,18 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_bwd_tc_kernel(const RecBwdA
         tc_wait(&sm.acc_full[buf], static_cast<uint32_t>((it >> 1) & 1));
         tc_fence_after();
         if (clk_on) t4 = clock64();
-        uint32_t v[8];
-        tmem_ld_32x8(lane_addr + static_cast<uint32_t>(buf * 16), v);
+        // tcgen05.ld is warp-collective (one address for the warp): fetch all 16 columns, each half keeps its 8
+        uint32_t w[16];
+        tmem_ld_32x16(lane_addr + static_cast<uint32_t>(buf * 16), w);
         tmem_ld_wait();
         tc_fence_before();
-        *reinterpret_cast<float4*>(&sm.xbuf[half][ul][0]) =
-            half ? make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]))
-                 : make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
-        epi_bar(1);
-        const float4 xo = *reinterpret_cast<const float4*>(&sm.xbuf[half ^ 1][ul][0]);
-        const float xv[4] = {xo.x, xo.y, xo.z, xo.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) carry[i] = keep[i] + (__uint_as_float(half ? v[4 + i] : v[i]) + xv[i]) * inv_s;
+        for (int i = 0; i < 4; ++i) {
+          const float mine = __uint_as_float(half ? w[12 + i] : w[i]);  // own partial sum, own rows
+          const float give = __uint_as_float(half ? w[8 + i] : w[4 + i]);  // own partial sum, partner's rows
+          const float got = __shfl_xor_sync(0xffffffffu, give, 16);     // partner's partial sum, own rows
+          carry[i] = keep[i] + (mine + got) * inv_s;
+        }
       }
       if (clk_on && k > 0) {
         const long long t5 = clock64();
@@ -778,20 +855,46 @@ int launch_tc(Kern kern, const Args& a, int CL, int nclusters, size_t smem, cuda
 
 long long* g_dbg_clk_tc = nullptr;
 
-int tc_attrs() {
-  static std::once_flag once;
-  static cudaError_t err = cudaSuccess;
-  std::call_once(once, [] {
-    err = cudaFuncSetAttribute(ligru_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(FwdTc) + 1024));
-    if (err == cudaSuccess)
-      err = cudaFuncSetAttribute(ligru_fwd_tc_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    if (err == cudaSuccess)
-      err = cudaFuncSetAttribute(ligru_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(BwdTc) + 1024));
-    if (err == cudaSuccess)
-      err = cudaFuncSetAttribute(ligru_bwd_tc_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-  });
+template <int ACT>
+int tc_attrs_one() {
+  cudaError_t err = cudaFuncSetAttribute(ligru_fwd_tc_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(FwdTc) + 1024));
+  if (err == cudaSuccess) err = cudaFuncSetAttribute(ligru_fwd_tc_kernel<ACT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  if (err == cudaSuccess)
+    err = cudaFuncSetAttribute(ligru_bwd_tc_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(BwdTc) + 1024));
+  if (err == cudaSuccess) err = cudaFuncSetAttribute(ligru_bwd_tc_kernel<ACT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   PK_CHECK_CUDA(err);
   return 0;
+}
+
+int tc_attrs() {
+  static std::once_flag once;
+  static int rc = 0;
+  std::call_once(once, [] {
+    rc = tc_attrs_one<ACT_RELU>();
+    if (!rc) rc = tc_attrs_one<ACT_TANH>();
+    if (!rc) rc = tc_attrs_one<ACT_SIGMOID>();
+    if (!rc) rc = tc_attrs_one<ACT_LEAKY_RELU>();
+    if (!rc) rc = tc_attrs_one<ACT_ELU>();
+    if (!rc) rc = tc_attrs_one<ACT_LINEAR>();
+  });
+  return rc;
+}
+
+#define PK_TC_DISPATCH(KERN, ARGS, SMEM)                                                          \
+  switch (ARGS.act) {                                                                             \
+    case ACT_RELU: return launch_tc(KERN<ACT_RELU>, ARGS, CL, nclusters, SMEM, stream);           \
+    case ACT_TANH: return launch_tc(KERN<ACT_TANH>, ARGS, CL, nclusters, SMEM, stream);           \
+    case ACT_SIGMOID: return launch_tc(KERN<ACT_SIGMOID>, ARGS, CL, nclusters, SMEM, stream);     \
+    case ACT_LEAKY_RELU: return launch_tc(KERN<ACT_LEAKY_RELU>, ARGS, CL, nclusters, SMEM, stream); \
+    case ACT_ELU: return launch_tc(KERN<ACT_ELU>, ARGS, CL, nclusters, SMEM, stream);             \
+    case ACT_LINEAR: return launch_tc(KERN<ACT_LINEAR>, ARGS, CL, nclusters, SMEM, stream);       \
+    default: PK_REQUIRE(false, "recurrent kernel: bad activation %d", ARGS.act);                  \
+  }
+
+int pick_groups(int requested) {
+  static const int env = [] { const char* e = getenv("PK_TC_GROUPS"); return e ? atoi(e) : 0; }();
+  int g = requested > 0 ? requested : (env > 0 ? env : kDefaultGroups);
+  return g < 1 ? 1 : (g > kGroups ? kGroups : g);
 }
 
 }  // namespace
@@ -803,22 +906,26 @@ int ligru_tc_max_hidden() { return kMaxCL * kUPC; }
 int ligru_fwd_tc(const RecFwdArgs& a_in, cudaStream_t stream) {
   RecFwdArgs a = a_in;
   a.dbg_clk = g_dbg_clk_tc;
+  a.groups = pick_groups(a.groups);
   const int CL = (a.H + kUPC - 1) / kUPC;
   PK_REQUIRE(CL <= kMaxCL, "ligru_fwd_tc: hidden size %d > %d", a.H, kMaxCL * kUPC);
   if (int rc = tc_attrs()) return rc;
   const int nclusters = (a.ndir * a.B + kRows - 1) / kRows;
-  return launch_tc(ligru_fwd_tc_kernel, a, CL, nclusters, sizeof(FwdTc) + 1024, stream);
+  PK_TC_DISPATCH(ligru_fwd_tc_kernel, a, sizeof(FwdTc) + 1024)
+  return 0;
 }
 
 int ligru_bwd_tc(const RecBwdArgs& a_in, cudaStream_t stream) {
   RecBwdArgs a = a_in;
   a.dbg_clk = g_dbg_clk_tc;
+  a.groups = pick_groups(a.groups);
   const int CL = (a.H + kUPC - 1) / kUPC;
   PK_REQUIRE(CL <= kMaxCL, "ligru_bwd_tc: hidden size %d > %d", a.H, kMaxCL * kUPC);
   PK_REQUIRE(a.GT16 != nullptr, "ligru_bwd_tc: writes GT16 (required)");
   if (int rc = tc_attrs()) return rc;
   const int nclusters = (a.ndir * a.B + kRows - 1) / kRows;
-  return launch_tc(ligru_bwd_tc_kernel, a, CL, nclusters, sizeof(BwdTc) + 1024, stream);
+  PK_TC_DISPATCH(ligru_bwd_tc_kernel, a, sizeof(BwdTc) + 1024)
+  return 0;
 }
 
 }  // namespace pk

@@ -302,8 +302,8 @@ static void test_ligru(int T, int B, int H, int ndir, int act) {
   dPT.up(c.PT); dsc.up(c.scale); dsh.up(c.shift); dU.up(c.U); dmask.up(c.mask);
   const long long ldy = (long long)ndir * H + 2;
   const long long ldy16 = ((long long)ndir * H + 7) / 8 * 8;
-  const char* names[] = {"tc", "tc-nofence", "ws", "8", "8b", "10"};
-  const int vflags[] = {0, PK_REC_DBG_NOPROXYFENCE, PK_REC_WS, PK_REC_CLUSTER(8), PK_REC_CLUSTER(8) | PK_REC_SYNC_BARRIER, PK_REC_CLUSTER(10)};
+  const char* names[] = {"tc", "tc-3groups", "ws", "8", "8b", "10"};
+  const int vflags[] = {0, PK_REC_GROUPS(3), PK_REC_WS, PK_REC_CLUSTER(8), PK_REC_CLUSTER(8) | PK_REC_SYNC_BARRIER, PK_REC_CLUSTER(10)};
   const int npass = H > 560 ? 2 : (H > 512 ? 6 : 5);
   for (int pass = 0; pass < npass; ++pass) {
     const char* cl = names[pass];
@@ -580,6 +580,12 @@ static void bench_all() {
     ddY.up(randn(nch, 1e-3f));
     struct V { const char* name; int flags; };
     const V vs[] = {{"tc (default)            ", 0},
+                    {"tc 1 group              ", PK_REC_GROUPS(1)},
+                    {"tc 2 groups             ", PK_REC_GROUPS(2)},
+                    {"tc 3 groups             ", PK_REC_GROUPS(3)},
+                    {"tc 1 group no pfence    ", PK_REC_GROUPS(1) | PK_REC_DBG_NOPROXYFENCE},
+                    {"tc 1 group blocking wait", PK_REC_GROUPS(1) | PK_REC_DBG_BLOCKINGWAIT},
+                    {"tc 2 groups nopf        ", PK_REC_GROUPS(2) | PK_REC_DBG_NOPROXYFENCE},
                     {"tc no proxy fence       ", PK_REC_DBG_NOPROXYFENCE},
                     {"tc nostore              ", PK_REC_DBG_NOSTORE},
                     {"tc noload/nostore       ", PK_REC_DBG_NOSTORE | PK_REC_DBG_NOLOAD},
@@ -618,7 +624,7 @@ static void bench_all() {
       }
     }
     {  // per-phase cycle breakdown of the critical-path warp (CTA 0, warp 0)
-      Dev<long long> dclk(8);
+      Dev<long long> dclk(8 + 8 * 16);
       pk_debug_set_clock_buffer(dclk.p);
       pk_rnn_layer_fwd(PK_CELL_LIGRU, T, B, H, ndir, PK_ACT_RELU, dPT.p, ld, dsc.p, dsh.p, dU.p, dmask.p, 1.f, dY.p, 1100,
                        dY16.p, 1104, dHT.p, dHT16.p, dHP16.p, dZT.p, dHCT.p, ld, nullptr);
@@ -626,6 +632,16 @@ static void bench_all() {
       auto c = dclk.down();
       printf("fwd phases (cycles/step): wait_acc %.0f | ld+xchg %.0f | gates+stage %.0f | push %.0f | rings(shadow) %.0f | - %.0f\n",
              c[0] / (double)T, c[1] / (double)T, c[2] / (double)T, c[3] / (double)T, c[4] / (double)T, c[5] / (double)T);
+      {
+        const long long base = c[8 + 4];
+        printf("fwd trace (cycles rel. to acc wake of step 200): issuer[top first_ready last_ready commit] epi0[wake ld gates push rings] epi3[wake end]\n");
+        for (int st = 0; st < 8; ++st) {
+          const long long* t = &c[8 + st * 16];
+          printf("  step %d: issuer %6lld %6lld %6lld %6lld | epi0 %6lld %6lld %6lld %6lld %6lld | epi3 %6lld %6lld\n", 200 + st, t[0] - base,
+                 t[1] - base, t[2] - base, t[3] - base, t[4] - base, t[5] - base, t[6] - base, t[7] - base, t[8] - base, t[9] - base,
+                 t[10] - base);
+        }
+      }
       pk_rnn_layer_bwd(PK_CELL_LIGRU, T, B, H, ndir, PK_ACT_RELU, ddY.p, dHT.p, dZT.p, dHCT.p, ld, dU.p, dmask.p, 1.f, dgs.p,
                        dGT.p, dGT16.p, nullptr);
       CK(cudaDeviceSynchronize());
