@@ -58,8 +58,11 @@ extern "C" {
 #define PK_REC_SYNC_BARRIER 0x2000
 /* use the non-warp-specialised kernels (A/B timing; they also write the fp32 GT buffer) */
 #define PK_REC_LEGACY 0x4000
-/* use the round-1 warp-specialised mma.sync kernels instead of the tcgen05 ones (A/B timing; H <= 560) */
-#define PK_REC_WS 0x8000
+/* kernel choice for the persistent liGRU / RNN recurrence.  Default (no flag): the faster of the two on this
+ * part as measured (profiles/r2_selftest_tc_vs_ws.log) — the warp-specialised register-stationary mma.sync
+ * kernels for H <= 560, the tcgen05 kernels (weights stationary in tensor memory) for 560 < H <= 1024. */
+#define PK_REC_WS 0x8000   /* force the warp-specialised mma.sync kernels (H <= 560) */
+#define PK_REC_TC 0x400000 /* force the tcgen05 kernels (H <= 1024) */
 /* timing experiments only (results are incomplete): skip the global stores / loads */
 #define PK_REC_DBG_NOSTORE 0x10000
 #define PK_REC_DBG_NOLOAD 0x20000

@@ -31,7 +31,7 @@ RecFlags parse_cell(int cell) {
   f.sync = (cell & PK_REC_SYNC_BARRIER) ? 0 : -1;
   f.dbg = ((cell & PK_REC_DBG_NOSTORE) ? 1 : 0) | ((cell & PK_REC_DBG_NOLOAD) ? 2 : 0) | ((cell & PK_REC_DBG_NOPROXYFENCE) ? 4 : 0) |
           ((cell & PK_REC_DBG_BLOCKINGWAIT) ? 8 : 0);
-  f.legacy = (cell & PK_REC_LEGACY) ? 1 : ((cell & PK_REC_WS) ? 2 : 0);
+  f.legacy = (cell & PK_REC_LEGACY) ? 1 : ((cell & PK_REC_WS) ? 2 : ((cell & PK_REC_TC) ? 3 : 0));
   f.groups = (cell >> 19) & 3;
   f.cell = cell & PK_CELL_MASK;
   return f;

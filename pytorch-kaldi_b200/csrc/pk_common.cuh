@@ -11,6 +11,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+
 namespace pk {
 
 // ----------------------------------------------------------------------------
@@ -35,6 +37,28 @@ void set_last_error(const char* fmt, ...);
       return 2;                                                                     \
     }                                                                               \
   } while (0)
+
+// One-time set-up PER DEVICE (cudaFuncSetAttribute is per context: a process that drives several GPUs, like the
+// reference's DataParallel mode, must opt every device in): run(f) executes f once for the calling thread's
+// current device and returns its (cached) result.
+struct PerDeviceOnce {
+  std::mutex m;
+  bool done[64] = {};
+  cudaError_t err[64] = {};
+  template <typename F>
+  cudaError_t run(F f) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lock(m);
+    if (!done[dev]) {
+      err[dev] = f();
+      done[dev] = true;
+    }
+    return err[dev];
+  }
+};
 
 // activation ids shared by host and device (neural_networks.act_fun, reference
 // neural_networks.py:36-57)
@@ -351,14 +375,15 @@ __device__ __forceinline__ void ldmatrix_x2(uint32_t saddr, uint32_t& r0, uint32
 }
 
 // fp32 pair -> packed fp16x2 (round to nearest, saturating to the finite range)
+// (NaN propagates: fminf / fmaxf would silently turn it into -65504 and hide a diverged run)
 __device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
-  lo = fminf(fmaxf(lo, -65504.f), 65504.f);
-  hi = fminf(fmaxf(hi, -65504.f), 65504.f);
+  lo = (lo != lo) ? lo : fminf(fmaxf(lo, -65504.f), 65504.f);
+  hi = (hi != hi) ? hi : fminf(fmaxf(hi, -65504.f), 65504.f);
   __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
 __device__ __forceinline__ __half f16_sat(float x) {
-  x = fminf(fmaxf(x, -65504.f), 65504.f);
+  x = (x != x) ? x : fminf(fmaxf(x, -65504.f), 65504.f);
   return __float2half_rn(x);
 }
 

@@ -449,16 +449,13 @@ int gemm_tn(const GemmArgs& a, cudaStream_t stream) {
   PK_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "gemm_tn: empty problem M=%d N=%d K=%d", a.M, a.N, a.K);
   PK_REQUIRE(a.dtype == PK_DT_F16 || a.dtype == PK_DT_TF32, "gemm_tn: bad dtype %d", a.dtype);
   PK_REQUIRE(a.bias_mode >= 0 && a.bias_mode <= 2, "gemm_tn: bad bias mode");
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_tn_kernel<0, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(128));
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(gemm_tn_kernel<2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(128));
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(gemm_tn_kernel<0, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(256));
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(gemm_tn_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes);
+  static PerDeviceOnce attr_once;
+  const cudaError_t attr_err = attr_once.run([] {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel<0, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(128));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tn_kernel<2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(128));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tn_kernel<0, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(256));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tn_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes);
+    return e;
   });
   PK_CHECK_CUDA(attr_err);
 

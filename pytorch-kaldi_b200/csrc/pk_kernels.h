@@ -53,7 +53,8 @@ struct RecFwdArgs {
   float* HCT = nullptr;
   long long ldt = 0;
   int cluster = 0;  // 0 = auto; > 0 selects a legacy (non-specialised) kernel with that cluster size
-  int legacy = 0;   // 0 = tcgen05 kernels (pk_rnn_tc.cu), 2 = warp-specialised mma.sync (pk_rnn_ws.cu), 1 = pk_rnn.cu
+  int legacy = 0;   // 0 = auto (faster kernel for this H), 3 = tcgen05 (pk_rnn_tc.cu), 2 = warp-specialised mma.sync
+                    // (pk_rnn_ws.cu), 1 = pk_rnn.cu
   int force_z0 = 0; // RNN cell (reference :1438-1447): update gate pinned to 0 -> h = act(a) * mask
   long long* dbg_clk = nullptr;  // bring-up: per-phase cycle sums of CTA 0 / warp 0 (8 slots)
   int sync = -1;    // -1 = default (st.async + mbarrier), 0 = barrier.cluster, 1 = st.async

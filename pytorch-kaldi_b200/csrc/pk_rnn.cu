@@ -601,9 +601,12 @@ int bwd_dispatch(const RecBwdArgs& a, int cl, int sy, int nclusters, cudaStream_
 int ligru_fwd(const RecFwdArgs& a, cudaStream_t stream) {
   PK_REQUIRE(a.T > 0 && a.B > 0 && a.H > 0, "ligru_fwd: empty problem");
   PK_REQUIRE(a.ndir == 1 || a.ndir == 2, "ligru_fwd: ndir must be 1 or 2");
-  static const int env_mode = env_int("PK_REC_MODE", 0);  // 0 = tcgen05, 2 = warp-specialised mma.sync, 1 = legacy
-  const int mode = a.legacy ? a.legacy : env_mode;
-  if (mode == 0 && a.cluster == 0 && a.sync != 0) return ligru_fwd_tc(a, stream);
+  // 0 = auto: the faster kernel for this hidden size as measured on B200 (profiles/): register-stationary mma.sync
+  // (ws) up to H = 560, tcgen05 with TMEM-stationary weights beyond; 3 = tcgen05, 2 = ws, 1 = legacy (pk_rnn.cu)
+  static const int env_mode = env_int("PK_REC_MODE", 0);
+  int mode = a.legacy ? a.legacy : env_mode;
+  if (mode == 0) mode = a.H <= 560 ? 2 : 3;
+  if (mode == 3 && a.cluster == 0 && a.sync != 0) return ligru_fwd_tc(a, stream);
   PK_REQUIRE(a.H <= 560, "ligru_fwd: hidden size %d > 560 not supported by the register-resident kernel", a.H);
   if (mode != 1 && a.cluster == 0 && a.sync != 0) return ligru_fwd_ws(a, stream);
   const int nclusters = (a.ndir * a.B + kRows - 1) / kRows;
@@ -614,8 +617,9 @@ int ligru_bwd(const RecBwdArgs& a, cudaStream_t stream) {
   PK_REQUIRE(a.T > 0 && a.B > 0 && a.H > 0, "ligru_bwd: empty problem");
   PK_REQUIRE(a.ndir == 1 || a.ndir == 2, "ligru_bwd: ndir must be 1 or 2");
   static const int env_mode = env_int("PK_REC_MODE", 0);
-  const int mode = a.legacy ? a.legacy : env_mode;
-  if (mode == 0 && a.cluster == 0 && a.sync != 0) return ligru_bwd_tc(a, stream);
+  int mode = a.legacy ? a.legacy : env_mode;
+  if (mode == 0) mode = a.H <= 560 ? 2 : 3;
+  if (mode == 3 && a.cluster == 0 && a.sync != 0) return ligru_bwd_tc(a, stream);
   PK_REQUIRE(a.H <= 560, "ligru_bwd: hidden size %d > 560 not supported by the register-resident kernel", a.H);
   if (mode != 1 && a.cluster == 0 && a.sync != 0) {
     PK_REQUIRE(a.GT16 != nullptr, "ligru_bwd: the warp-specialised kernel writes GT16 (required)");

@@ -40,7 +40,9 @@ namespace {
 
 constexpr int kRows = 8;    // real batch rows per cluster
 constexpr int kUPC = 64;    // hidden units per CTA
-constexpr int kMaxCL = 15;  // 32 accumulator columns + 32 * CL weight columns <= 512 TMEM columns
+constexpr int kMaxCL = 16;  // H <= 1024
+constexpr int kTmemCL = 15; // chunks whose weights fit tensor memory: 32 accumulator columns + 32 * 15 = 512; the
+                            // 16th chunk (units 960..1023 as K) stays in shared memory and is multiplied in SS form
 constexpr int RI = 4;       // input ring depth (prefetch distance + 1)
 constexpr int RO = 4;       // output ring depth
 constexpr int kIoWarps = 4;
@@ -125,13 +127,19 @@ __device__ __forceinline__ void tc_spin_cluster(uint64_t* bar, uint32_t parity) 
 // MMAs ~70).
 constexpr int kDefaultGroups = 1;
 constexpr int kGroups = 3;  // at most; the launch picks 1..3 (RecArgs::groups)
+__device__ __forceinline__ long long gtime_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ int group_size(int CL, int ng) { return (CL + ng - 1) / ng; }
 
 // ---- the MMA-issuing thread, one step: per arrival group: wait -> re-arm -> that group's MMAs (chunk order =
 // arrival order); finally commit to acc_full.
+template <bool TAIL>  // TAIL: H > 960, chunk 15's weights are multiplied from shared memory
 __device__ __forceinline__ void mma_step(uint32_t opnd_addr, uint64_t* grp_bar_buf, uint64_t* acc_full, uint32_t tmem_base,
-                                         uint32_t acc_col, int CL, int gsz, uint32_t crank, bool wait_data, uint32_t parity,
-                                         uint32_t tx_bytes, bool proxy_fence, bool spin, long long* trace) {
+                                         uint32_t acc_col, int CL, int gsz, bool tail4, uint32_t crank, bool wait_data, uint32_t parity,
+                                         uint32_t tx_bytes, bool proxy_fence, bool spin, uint32_t wtail_addr, long long* trace, long long* gt = nullptr) {
   if (trace) trace[0] = clock64();
   // Running operand addresses (chunk c = crank, crank-1, ... with wrap-around): per MMA only two uniform adds remain.
   // Shared-memory descriptor: low word = (address >> 4) | LBO field, high word constant (SBO 1024 B, version 1,
@@ -147,18 +155,31 @@ __device__ __forceinline__ void mma_step(uint32_t opnd_addr, uint64_t* grp_bar_b
     const int i_end = min(CL, i + gsz);
     if (wait_data) {
       if (spin) tc_spin_cluster(&grp_bar_buf[g], parity); else tc_wait_cluster(&grp_bar_buf[g], parity);
-      mbar_arrive_expect_tx(&grp_bar_buf[g], tx_bytes * static_cast<uint32_t>(i_end - i));  // re-arm (use after next)
       if (proxy_fence) fence_proxy_async_smem();
       tc_fence_after();
     }
+    const uint32_t rearm = tx_bytes * static_cast<uint32_t>(i_end - i);
     if (trace) trace[g == 0 ? 1 : 2] = clock64();
+    if (gt) gt[2] = gtime_ns();
     for (; i < i_end; ++i) {
       const uint64_t hi = static_cast<uint64_t>(kDescHi) << 32;
+      if (TAIL && c == kTmemCL) {  // H > 960: this chunk's weights live in shared memory (SS form, ~57 cycles per MMA)
+        const uint32_t w_lo = ((wtail_addr & 0x3FFFFu) >> 4) | (1u << 16);
+        umma_f16(d_tmem, hi | w_lo, hi | b_lo, kIdesc, first);
+        umma_f16(d_tmem, hi | (w_lo + 2), hi | (b_lo + 2), kIdesc, 1u);
+        umma_f16(d_tmem, hi | (w_lo + 4), hi | (b_lo + 4), kIdesc, 1u);
+        umma_f16(d_tmem, hi | (w_lo + 6), hi | (b_lo + 6), kIdesc, 1u);
+        first = 1u;
+        --c;
+        a_addr -= 32u;
+        b_lo -= (kChunkBytes >> 4);
+        continue;
+      }
       // branch-free body (a branch per MMA serialises the descriptor chains); k-steps beyond H multiply zero weights
       umma_f16_ts(d_tmem, a_addr, hi | b_lo, kIdesc, first);
       umma_f16_ts(d_tmem, a_addr + 8, hi | (b_lo + 2), kIdesc, 1u);
       umma_f16_ts(d_tmem, a_addr + 16, hi | (b_lo + 4), kIdesc, 1u);
-      umma_f16_ts(d_tmem, a_addr + 24, hi | (b_lo + 6), kIdesc, 1u);
+      if (c != CL - 1 || tail4) umma_f16_ts(d_tmem, a_addr + 24, hi | (b_lo + 6), kIdesc, 1u);  // last chunk: k-steps beyond H are zero
       first = 1u;
       if (c == 0) {
         c = CL - 1;
@@ -170,6 +191,7 @@ __device__ __forceinline__ void mma_step(uint32_t opnd_addr, uint64_t* grp_bar_b
         b_lo -= (kChunkBytes >> 4);
       }
     }
+    if (wait_data) mbar_arrive_expect_tx(&grp_bar_buf[g], rearm);  // re-arm for this buffer's next use (two steps on)
   }
   umma_commit(acc_full);
   if (trace) trace[3] = clock64();
@@ -180,16 +202,17 @@ __device__ __forceinline__ void mma_step(uint32_t opnd_addr, uint64_t* grp_bar_b
 // =====================================================================================
 struct FwdTc {
   uint8_t hbuf[2][kMaxCL][kChunkBytes];  // B operand: [buffer][source CTA][16 rows x 128 B, 128B-swizzled]
+  uint8_t wtail[128 * 128];              // A tile of chunk 15 (H > 960 only): [128 gate rows x 64 K] fp16, 128B-swizzled
   float inr[RI][2][kUPC][kRows];         // [slot][gate h,z][unit][row]
   float outr[RO][3][kUPC][kRows];        // [slot][h, z, hc][unit][row]
-  __half stage[4][kRows][16];            // per epilogue warp: new state [row][16 units] -> 16-byte messages of 8 units
+  uint8_t stage[kRows * 128];            // image of this CTA's block of the operand (8 swizzled rows of 128 B)
   uint64_t src_bar[2][kGroups];          // [buffer][arrival group]
   uint64_t acc_full[2];
   uint64_t in_full[RI], in_empty[RI], out_full[RO], out_empty[RO];
   uint32_t tmem_slot;
 };
 
-template <int ACT>  // activation id: the per-element switch would be an indirect branch (BRX) on the serial path
+template <int ACT, bool TAIL>  // activation id: the per-element switch would be an indirect branch (BRX) on the serial path
 __global__ void __launch_bounds__(kThreads, 1) ligru_fwd_tc_kernel(const RecFwdArgs a, const int CL) {
   extern __shared__ uint8_t smem_raw[];
   FwdTc& sm = *reinterpret_cast<FwdTc*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -233,7 +256,21 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_fwd_tc_kernel(const RecFwdA
     const int u = cta_ubase + lg * 16 + (lane & 15);
     const bool u_ok = u < H;
     const float* Urow = a.U + (static_cast<long long>(lane >> 4) * H + (u_ok ? u : 0)) * H;
-    const int KP = CL * kUPC;
+    const int KP = min(CL, kTmemCL) * kUPC;
+    if (TAIL) {  // K = 960..1023 of this thread's gate row -> the shared-memory A tile (row = TMEM lane)
+      const int m = lg * 32 + lane;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int k = kTmemCL * kUPC + j * 8 + 2 * e;
+          w[e] = pack_f16x2_sat((u_ok && k < H) ? __ldg(Urow + k) : 0.f, (u_ok && k + 1 < H) ? __ldg(Urow + k + 1) : 0.f);
+        }
+        *reinterpret_cast<uint4*>(&sm.wtail[(m >> 3) * 1024 + (m & 7) * 128 + ((j ^ (m & 7)) << 4)]) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      fence_proxy_async_smem();
+    }
     for (int k0 = 0; k0 < KP; k0 += 16) {
       uint32_t v[8];
 #pragma unroll
@@ -259,8 +296,10 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_fwd_tc_kernel(const RecFwdA
       for (int k = 0; k < T; ++k) {
         const int cur = k & 1;
         long long* tr = (a.dbg_clk && blockIdx.x == 0 && k >= kTrace0 && k < kTrace0 + 8) ? a.dbg_clk + 8 + (k - kTrace0) * 16 : nullptr;
-        mma_step(smem_u32(&sm.hbuf[cur][0][0]), &sm.src_bar[cur][0], &sm.acc_full[cur], tmem_base, static_cast<uint32_t>(cur * 16), CL,
-                 gsz, crank, k > 0, static_cast<uint32_t>(((k - 1) >> 1) & 1), kFwdTx, pf, !(a.dbg & 8), tr);
+        long long* gt = (a.dbg_clk && blockIdx.x < CL && k >= kTrace0 && k < kTrace0 + 8) ? a.dbg_clk + 136 + blockIdx.x * 64 + (k - kTrace0) * 8 : nullptr;
+        mma_step<TAIL>(smem_u32(&sm.hbuf[cur][0][0]), &sm.src_bar[cur][0], &sm.acc_full[cur], tmem_base, static_cast<uint32_t>(cur * 16), CL,
+                 gsz, (H - (CL - 1) * kUPC) > 48, crank, k > 0, static_cast<uint32_t>(((k - 1) >> 1) & 1), kFwdTx, pf, !(a.dbg & 8), smem_u32(&sm.wtail[0]), tr, gt);
+        if (gt) gt[3] = gtime_ns();
       }
     }
     __syncwarp();
@@ -289,11 +328,14 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_fwd_tc_kernel(const RecFwdA
     float hprev[4] = {0.f, 0.f, 0.f, 0.f};
     const bool z0 = a.force_z0 != 0;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(lg * 32) << 16);
-    // push bookkeeping: the warp owns 16 messages (row, 8-unit group); lane -> message lane & 15, destinations
-    // lane >> 4, +2, ...
-    const int prow = (lane & 15) >> 1, pjl = lane & 1;
-    const int pj = lg * 2 + pjl;  // 8-unit group inside the CTA's 64 units
-    const uint32_t msg_off = static_cast<uint32_t>(crank * kChunkBytes + prow * 128 + ((pj ^ prow) << 4));
+    // The block is staged as its final shared-memory image and pushed as WHOLE 128-byte rows: one st.async
+    // instruction = 32 lanes x 16 B = 4 complete rows for one destination (scattered 16-byte pieces reach only
+    // ~1/3 of the DSMEM bandwidth, measured).  Instruction q of the CTA (q < 2 CL): slot q >> 1, rows 4 (q & 1) ..;
+    // warp ew issues q = ew, ew + 4, ...
+    const uint32_t stage_off[4] = {static_cast<uint32_t>((r0 + 0) * 128 + ((((ul >> 3) ^ (r0 + 0)) & 7) << 4) + (ul & 7) * 2),
+                                   static_cast<uint32_t>((r0 + 1) * 128 + ((((ul >> 3) ^ (r0 + 1)) & 7) << 4) + (ul & 7) * 2),
+                                   static_cast<uint32_t>((r0 + 2) * 128 + ((((ul >> 3) ^ (r0 + 2)) & 7) << 4) + (ul & 7) * 2),
+                                   static_cast<uint32_t>((r0 + 3) * 128 + ((((ul >> 3) ^ (r0 + 3)) & 7) << 4) + (ul & 7) * 2)};
 
     uint32_t gtab = 0;  // arrival group of slot i, 2 bits each (no division on the per-step path)
     for (int i = 0; i < CL; ++i) gtab |= static_cast<uint32_t>(i / gsz) << (2 * i);
@@ -338,22 +380,28 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_fwd_tc_kernel(const RecFwdA
         float h = fmaf(zt, hprev[i] - hc, hc);
         if (!rok[i]) h = 0.f;
         hn[i] = h; zz[i] = zt; hcv[i] = hc; hprev[i] = h;
-        sm.stage[ew][r0 + i][lane & 15] = f16_sat(h);
+        *reinterpret_cast<__half*>(&sm.stage[stage_off[i]]) = f16_sat(h);
       }
-      __syncwarp();
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps: the block image is complete
       if (clk_on) t3 = clock64();
+      long long* gt = (a.dbg_clk && blockIdx.x < CL && ew == 0 && lane == 0 && k >= kTrace0 && k < kTrace0 + 8) ? a.dbg_clk + 136 + blockIdx.x * 64 + (k - kTrace0) * 8 : nullptr;
+      if (gt) gt[0] = gtime_ns();
       // ---- push the warp's 8 x 16 block to every CTA of the cluster (data + complete_tx in one message)
       if (k + 1 < T) {
-        const uint4 val = *reinterpret_cast<const uint4*>(&sm.stage[ew][prow][pjl * 8]);
-        const uint32_t laddr = smem_u32(&sm.hbuf[nxt][0][0]) + msg_off;
+        const uint4 v0 = *reinterpret_cast<const uint4*>(&sm.stage[lane * 16]);        // rows 0..3
+        const uint4 v1 = *reinterpret_cast<const uint4*>(&sm.stage[512 + lane * 16]);  // rows 4..7
+        const uint32_t laddr = smem_u32(&sm.hbuf[nxt][0][0]) + crank * kChunkBytes + static_cast<uint32_t>(lane * 16);
         const uint32_t lbar0 = smem_u32(&sm.src_bar[nxt][0]);
-        int dst = static_cast<int>(crank) + (lane >> 4);
-        for (int i = lane >> 4; i < CL; i += 2, dst += 2) {  // slot i: destination crank + i -> its arrival group i / gsz
+        for (int q = ew; q < 2 * CL; q += 4) {
+          const int i = q >> 1;  // slot i: destination crank + i -> lands in its arrival group
+          int dst = static_cast<int>(crank) + i;
           if (dst >= CL) dst -= CL;
-          st_async_v4(mapa_shared(laddr, dst), val, mapa_shared(lbar0 + ((gtab >> (2 * i)) & 3u) * 8u, dst));
+          st_async_v4(mapa_shared(laddr + static_cast<uint32_t>((q & 1) * 512), dst), (q & 1) ? v1 : v0,
+                      mapa_shared(lbar0 + ((gtab >> (2 * i)) & 3u) * 8u, dst));
         }
       }
       if (clk_on) t4 = clock64();
+      if (gt) gt[1] = gtime_ns();
       // ---- in the shadow of the transit: outputs -> I/O warps, next step's projections <- ring
       const int so = k % RO;
       if (k >= RO) tc_wait(&sm.out_empty[so], static_cast<uint32_t>(((k / RO) - 1) & 1));
@@ -528,16 +576,17 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_fwd_tc_kernel(const RecFwdA
 // =====================================================================================
 struct BwdTc {
   uint8_t gbuf[2][kMaxCL][kChunkBytes];  // B operand: rows 0..7 = da, rows 8..15 = dpz of the cluster's 8 batch rows
+  uint8_t wtail[128 * 128];              // A tile of chunk 15 (H > 960 only)
   float inr[RI][4][kUPC][kRows];         // [slot][dy, z, hc, hprev][unit][row]
   __half outr[RO][2][kUPC][kRows];       // [slot][da, dpz][unit][row]  (scaled fp16)
-  __half stage[4][2][kRows][16];         // per epilogue warp: [gate][row][16 units]
+  uint8_t stage[2 * kRows * 128];        // image of this CTA's block: rows 0..7 = da, rows 8..15 = dpz (swizzled)
   uint64_t src_bar[2][kGroups];          // [buffer][arrival group]
   uint64_t acc_full[2];
   uint64_t in_full[RI], in_empty[RI], out_full[RO], out_empty[RO];
   uint32_t tmem_slot;
 };
 
-template <int ACT>
+template <int ACT, bool TAIL>
 __global__ void __launch_bounds__(kThreads, 1) ligru_bwd_tc_kernel(const RecBwdArgs a, const int CL) {
   extern __shared__ uint8_t smem_raw[];
   BwdTc& sm = *reinterpret_cast<BwdTc*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -580,7 +629,22 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_bwd_tc_kernel(const RecBwdA
     const int u = cta_ubase + lg * 16 + (lane & 15);
     const bool u_ok = u < H;
     const float* Ucol = a.U + static_cast<long long>(lane >> 4) * H * H + (u_ok ? u : 0);
-    const int KP = CL * kUPC;
+    const int KP = min(CL, kTmemCL) * kUPC;
+    if (TAIL) {
+      const int m = lg * 32 + lane;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int k = kTmemCL * kUPC + j * 8 + 2 * e;
+          w[e] = pack_f16x2_sat((u_ok && k < H) ? __ldg(Ucol + static_cast<long long>(k) * H) : 0.f,
+                                (u_ok && k + 1 < H) ? __ldg(Ucol + static_cast<long long>(k + 1) * H) : 0.f);
+        }
+        *reinterpret_cast<uint4*>(&sm.wtail[(m >> 3) * 1024 + (m & 7) * 128 + ((j ^ (m & 7)) << 4)]) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      fence_proxy_async_smem();
+    }
     for (int k0 = 0; k0 < KP; k0 += 16) {
       uint32_t v[8];
 #pragma unroll
@@ -606,8 +670,8 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_bwd_tc_kernel(const RecBwdA
       for (int k = T - 1; k > 0; --k) {
         const int it = T - 1 - k;
         const int buf = k & 1;
-        mma_step(smem_u32(&sm.gbuf[buf][0][0]), &sm.src_bar[buf][0], &sm.acc_full[buf], tmem_base, static_cast<uint32_t>(buf * 16), CL,
-                 gsz, crank, true, static_cast<uint32_t>((it >> 1) & 1), kBwdTx, pf, !(a.dbg & 8), nullptr);
+        mma_step<TAIL>(smem_u32(&sm.gbuf[buf][0][0]), &sm.src_bar[buf][0], &sm.acc_full[buf], tmem_base, static_cast<uint32_t>(buf * 16), CL,
+                 gsz, (H - (CL - 1) * kUPC) > 48, crank, true, static_cast<uint32_t>((it >> 1) & 1), kBwdTx, pf, !(a.dbg & 8), smem_u32(&sm.wtail[0]), nullptr);
       }
     }
     __syncwarp();
@@ -634,10 +698,12 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_bwd_tc_kernel(const RecBwdA
     float carry[4] = {0.f, 0.f, 0.f, 0.f};
     // lanes < 16 own the Uh^T partial sums (valid in accumulator columns 0..7), lanes >= 16 the Uz^T ones (8..15)
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(lg * 32) << 16);
-    // push bookkeeping: the warp owns 32 messages (gate, row, 8-unit group) -> one per lane, every destination
-    const int pg = lane >> 4, prow = (lane & 15) >> 1, pjl = lane & 1;
-    const int pj = lg * 2 + pjl;
-    const uint32_t msg_off = static_cast<uint32_t>(crank * kChunkBytes + pg * 1024 + prow * 128 + ((pj ^ prow) << 4));
+    // staged block image + whole-row pushes as in the forward kernel: instruction q (q < 4 CL): slot q >> 2,
+    // 512-byte quarter q & 3; warp ew issues q = ew, ew + 4, ... i.e. quarter ew of every slot
+    const uint32_t stage_off[4] = {static_cast<uint32_t>((r0 + 0) * 128 + ((((ul >> 3) ^ (r0 + 0)) & 7) << 4) + (ul & 7) * 2),
+                                   static_cast<uint32_t>((r0 + 1) * 128 + ((((ul >> 3) ^ (r0 + 1)) & 7) << 4) + (ul & 7) * 2),
+                                   static_cast<uint32_t>((r0 + 2) * 128 + ((((ul >> 3) ^ (r0 + 2)) & 7) << 4) + (ul & 7) * 2),
+                                   static_cast<uint32_t>((r0 + 3) * 128 + ((((ul >> 3) ^ (r0 + 3)) & 7) << 4) + (ul & 7) * 2)};
 
     uint32_t gtab = 0;  // arrival group of slot i, 2 bits each (no division on the per-step path)
     for (int i = 0; i < CL; ++i) gtab |= static_cast<uint32_t>(i / gsz) << (2 * i);
@@ -670,14 +736,14 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_bwd_tc_kernel(const RecBwdA
         keep[i] = dh * zv[i];
         da16[i] = f16_sat(da * s);
         dz16[i] = f16_sat(dz * s);
-        sm.stage[ew][0][r0 + i][lane & 15] = da16[i];
-        sm.stage[ew][1][r0 + i][lane & 15] = dz16[i];
+        *reinterpret_cast<__half*>(&sm.stage[stage_off[i]]) = da16[i];
+        *reinterpret_cast<__half*>(&sm.stage[1024 + stage_off[i]]) = dz16[i];
       }
-      __syncwarp();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
       if (clk_on) t1 = clock64();
       if (k > 0) {
-        const uint4 val = *reinterpret_cast<const uint4*>(&sm.stage[ew][pg][prow][pjl * 8]);
-        const uint32_t laddr = smem_u32(&sm.gbuf[buf][0][0]) + msg_off;
+        const uint4 val = *reinterpret_cast<const uint4*>(&sm.stage[ew * 512 + lane * 16]);
+        const uint32_t laddr = smem_u32(&sm.gbuf[buf][0][0]) + crank * kChunkBytes + static_cast<uint32_t>(ew * 512 + lane * 16);
         const uint32_t lbar0 = smem_u32(&sm.src_bar[buf][0]);
         int dst = static_cast<int>(crank);
         for (int i = 0; i < CL; ++i, ++dst) {
@@ -855,40 +921,47 @@ int launch_tc(Kern kern, const Args& a, int CL, int nclusters, size_t smem, cuda
 
 long long* g_dbg_clk_tc = nullptr;
 
-template <int ACT>
-int tc_attrs_one() {
-  cudaError_t err = cudaFuncSetAttribute(ligru_fwd_tc_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(FwdTc) + 1024));
-  if (err == cudaSuccess) err = cudaFuncSetAttribute(ligru_fwd_tc_kernel<ACT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+template <int ACT, bool TAIL>
+cudaError_t tc_attrs_one() {
+  cudaError_t err = cudaFuncSetAttribute(ligru_fwd_tc_kernel<ACT, TAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(FwdTc) + 1024));
+  if (err == cudaSuccess) err = cudaFuncSetAttribute(ligru_fwd_tc_kernel<ACT, TAIL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   if (err == cudaSuccess)
-    err = cudaFuncSetAttribute(ligru_bwd_tc_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(BwdTc) + 1024));
-  if (err == cudaSuccess) err = cudaFuncSetAttribute(ligru_bwd_tc_kernel<ACT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    err = cudaFuncSetAttribute(ligru_bwd_tc_kernel<ACT, TAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(BwdTc) + 1024));
+  if (err == cudaSuccess) err = cudaFuncSetAttribute(ligru_bwd_tc_kernel<ACT, TAIL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  return err;
+}
+template <int ACT>
+cudaError_t tc_attrs_act() {
+  cudaError_t e = tc_attrs_one<ACT, false>();
+  return e == cudaSuccess ? tc_attrs_one<ACT, true>() : e;
+}
+
+int tc_attrs() {
+  static PerDeviceOnce once;
+  const cudaError_t err = once.run([] {
+    cudaError_t e = tc_attrs_act<ACT_RELU>();
+    if (e == cudaSuccess) e = tc_attrs_act<ACT_TANH>();
+    if (e == cudaSuccess) e = tc_attrs_act<ACT_SIGMOID>();
+    if (e == cudaSuccess) e = tc_attrs_act<ACT_LEAKY_RELU>();
+    if (e == cudaSuccess) e = tc_attrs_act<ACT_ELU>();
+    if (e == cudaSuccess) e = tc_attrs_act<ACT_LINEAR>();
+    return e;
+  });
   PK_CHECK_CUDA(err);
   return 0;
 }
 
-int tc_attrs() {
-  static std::once_flag once;
-  static int rc = 0;
-  std::call_once(once, [] {
-    rc = tc_attrs_one<ACT_RELU>();
-    if (!rc) rc = tc_attrs_one<ACT_TANH>();
-    if (!rc) rc = tc_attrs_one<ACT_SIGMOID>();
-    if (!rc) rc = tc_attrs_one<ACT_LEAKY_RELU>();
-    if (!rc) rc = tc_attrs_one<ACT_ELU>();
-    if (!rc) rc = tc_attrs_one<ACT_LINEAR>();
-  });
-  return rc;
-}
-
-#define PK_TC_DISPATCH(KERN, ARGS, SMEM)                                                          \
-  switch (ARGS.act) {                                                                             \
-    case ACT_RELU: return launch_tc(KERN<ACT_RELU>, ARGS, CL, nclusters, SMEM, stream);           \
-    case ACT_TANH: return launch_tc(KERN<ACT_TANH>, ARGS, CL, nclusters, SMEM, stream);           \
-    case ACT_SIGMOID: return launch_tc(KERN<ACT_SIGMOID>, ARGS, CL, nclusters, SMEM, stream);     \
-    case ACT_LEAKY_RELU: return launch_tc(KERN<ACT_LEAKY_RELU>, ARGS, CL, nclusters, SMEM, stream); \
-    case ACT_ELU: return launch_tc(KERN<ACT_ELU>, ARGS, CL, nclusters, SMEM, stream);             \
-    case ACT_LINEAR: return launch_tc(KERN<ACT_LINEAR>, ARGS, CL, nclusters, SMEM, stream);       \
-    default: PK_REQUIRE(false, "recurrent kernel: bad activation %d", ARGS.act);                  \
+#define PK_TC_LAUNCH(KERN, A, ARGS, SMEM) \
+  return (CL > kTmemCL) ? launch_tc(KERN<A, true>, ARGS, CL, nclusters, SMEM, stream) : launch_tc(KERN<A, false>, ARGS, CL, nclusters, SMEM, stream)
+#define PK_TC_DISPATCH(KERN, ARGS, SMEM)                                             \
+  switch (ARGS.act) {                                                                \
+    case ACT_RELU: PK_TC_LAUNCH(KERN, ACT_RELU, ARGS, SMEM);                         \
+    case ACT_TANH: PK_TC_LAUNCH(KERN, ACT_TANH, ARGS, SMEM);                         \
+    case ACT_SIGMOID: PK_TC_LAUNCH(KERN, ACT_SIGMOID, ARGS, SMEM);                   \
+    case ACT_LEAKY_RELU: PK_TC_LAUNCH(KERN, ACT_LEAKY_RELU, ARGS, SMEM);             \
+    case ACT_ELU: PK_TC_LAUNCH(KERN, ACT_ELU, ARGS, SMEM);                           \
+    case ACT_LINEAR: PK_TC_LAUNCH(KERN, ACT_LINEAR, ARGS, SMEM);                     \
+    default: PK_REQUIRE(false, "recurrent kernel: bad activation %d", ARGS.act);     \
   }
 
 int pick_groups(int requested) {

@@ -707,12 +707,11 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_bwd_ws_kernel(const RecBwdA
 
 template <typename Args, void (*Kern)(const Args)>
 int launch_ws(const Args& a, int cluster, int nclusters, size_t smem, cudaStream_t stream) {
-  static std::once_flag once;
-  static cudaError_t err = cudaSuccess;
-  std::call_once(once, [&] {
-    err = cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (err == cudaSuccess && cluster > 8)
-      err = cudaFuncSetAttribute(Kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  static PerDeviceOnce once;
+  const cudaError_t err = once.run([&] {
+    cudaError_t e = cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e == cudaSuccess && cluster > 8) e = cudaFuncSetAttribute(Kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    return e;
   });
   PK_CHECK_CUDA(err);
   cudaLaunchConfig_t cfg = {};

@@ -303,7 +303,7 @@ static void test_ligru(int T, int B, int H, int ndir, int act) {
   const long long ldy = (long long)ndir * H + 2;
   const long long ldy16 = ((long long)ndir * H + 7) / 8 * 8;
   const char* names[] = {"tc", "tc-3groups", "ws", "8", "8b", "10"};
-  const int vflags[] = {0, PK_REC_GROUPS(3), PK_REC_WS, PK_REC_CLUSTER(8), PK_REC_CLUSTER(8) | PK_REC_SYNC_BARRIER, PK_REC_CLUSTER(10)};
+  const int vflags[] = {PK_REC_TC, PK_REC_TC | PK_REC_GROUPS(3), PK_REC_WS, PK_REC_CLUSTER(8), PK_REC_CLUSTER(8) | PK_REC_SYNC_BARRIER, PK_REC_CLUSTER(10)};
   const int npass = H > 560 ? 2 : (H > 512 ? 6 : 5);
   for (int pass = 0; pass < npass; ++pass) {
     const char* cl = names[pass];
@@ -579,17 +579,15 @@ static void bench_all() {
     dgs.up({1024.f});
     ddY.up(randn(nch, 1e-3f));
     struct V { const char* name; int flags; };
-    const V vs[] = {{"tc (default)            ", 0},
-                    {"tc 1 group              ", PK_REC_GROUPS(1)},
-                    {"tc 2 groups             ", PK_REC_GROUPS(2)},
-                    {"tc 3 groups             ", PK_REC_GROUPS(3)},
-                    {"tc 1 group no pfence    ", PK_REC_GROUPS(1) | PK_REC_DBG_NOPROXYFENCE},
-                    {"tc 1 group blocking wait", PK_REC_GROUPS(1) | PK_REC_DBG_BLOCKINGWAIT},
-                    {"tc 2 groups nopf        ", PK_REC_GROUPS(2) | PK_REC_DBG_NOPROXYFENCE},
-                    {"tc no proxy fence       ", PK_REC_DBG_NOPROXYFENCE},
-                    {"tc nostore              ", PK_REC_DBG_NOSTORE},
-                    {"tc noload/nostore       ", PK_REC_DBG_NOSTORE | PK_REC_DBG_NOLOAD},
-                    {"ws (round 1)            ", PK_REC_WS},
+    const V vs[] = {{"default (auto)          ", 0},
+                    {"tc tcgen05, 1 group     ", PK_REC_TC},
+                    {"tc 2 groups             ", PK_REC_TC | PK_REC_GROUPS(2)},
+                    {"tc 3 groups             ", PK_REC_TC | PK_REC_GROUPS(3)},
+                    {"tc no proxy fence       ", PK_REC_TC | PK_REC_DBG_NOPROXYFENCE},
+                    {"tc blocking wait        ", PK_REC_TC | PK_REC_DBG_BLOCKINGWAIT},
+                    {"tc nostore              ", PK_REC_TC | PK_REC_DBG_NOSTORE},
+                    {"tc noload/nostore       ", PK_REC_TC | PK_REC_DBG_NOSTORE | PK_REC_DBG_NOLOAD},
+                    {"ws mma.sync (round 1)   ", PK_REC_WS},
                     {"legacy cl10 st.async    ", PK_REC_CLUSTER(10)},
                     {"legacy cl8  st.async    ", PK_REC_CLUSTER(8)},
                     {"legacy cl8  barrier     ", PK_REC_CLUSTER(8) | PK_REC_SYNC_BARRIER}};
@@ -624,9 +622,9 @@ static void bench_all() {
       }
     }
     {  // per-phase cycle breakdown of the critical-path warp (CTA 0, warp 0)
-      Dev<long long> dclk(8 + 8 * 16);
+      Dev<long long> dclk(8 + 8 * 16 + 16 * 64);
       pk_debug_set_clock_buffer(dclk.p);
-      pk_rnn_layer_fwd(PK_CELL_LIGRU, T, B, H, ndir, PK_ACT_RELU, dPT.p, ld, dsc.p, dsh.p, dU.p, dmask.p, 1.f, dY.p, 1100,
+      pk_rnn_layer_fwd(PK_CELL_LIGRU | PK_REC_TC, T, B, H, ndir, PK_ACT_RELU, dPT.p, ld, dsc.p, dsh.p, dU.p, dmask.p, 1.f, dY.p, 1100,
                        dY16.p, 1104, dHT.p, dHT16.p, dHP16.p, dZT.p, dHCT.p, ld, nullptr);
       CK(cudaDeviceSynchronize());
       auto c = dclk.down();
@@ -642,7 +640,16 @@ static void bench_all() {
                  t[10] - base);
         }
       }
-      pk_rnn_layer_bwd(PK_CELL_LIGRU, T, B, H, ndir, PK_ACT_RELU, ddY.p, dHT.p, dZT.p, dHCT.p, ld, dU.p, dmask.p, 1.f, dgs.p,
+      {
+        printf("fwd per-CTA global-time trace of cluster 0 (ns rel. to CTA 0 push start of step 202): [push_start push_end all_ready commit]\n");
+        const long long base = c[136 + 2 * 8 + 0];
+        for (int st = 2; st < 5; ++st)
+          for (int cta = 0; cta < 9; ++cta) {
+            const long long* t = &c[136 + cta * 64 + st * 8];
+            printf("  step %d cta %d: %6lld %6lld %6lld %6lld\n", 200 + st, cta, t[0] - base, t[1] - base, t[2] - base, t[3] - base);
+          }
+      }
+      pk_rnn_layer_bwd(PK_CELL_LIGRU | PK_REC_TC, T, B, H, ndir, PK_ACT_RELU, ddY.p, dHT.p, dZT.p, dHCT.p, ld, dU.p, dmask.p, 1.f, dgs.p,
                        dGT.p, dGT16.p, nullptr);
       CK(cudaDeviceSynchronize());
       c = dclk.down();
@@ -650,6 +657,31 @@ static void bench_all() {
              c[0] / (double)T, c[1] / (double)T, c[2] / (double)T, c[3] / (double)T, c[4] / (double)T, c[5] / (double)T);
       pk_debug_set_clock_buffer(nullptr);
     }
+  }
+  {  // config-4 layer shape: H = 1024 (15 chunks of weights in tensor memory + 1 in shared memory)
+    const int T = 500, B = 32, H = 1024, ndir = 2;
+    const long long ld = (long long)T * B;
+    const size_t nch = (size_t)ndir * H * ld;
+    Dev<float> dPT((size_t)2 * H * ld), dsc(2 * H), dsh(2 * H), dU((size_t)2 * H * H), dmask((size_t)ndir * B * H);
+    dPT.up(randn((size_t)2 * H * ld));
+    dsc.up(std::vector<float>(2 * H, 1.f));
+    dU.up(randn((size_t)2 * H * H, 1.f / 32.f));
+    dmask.up(std::vector<float>((size_t)ndir * B * H, 1.f));
+    Dev<float> dHT(nch), dZT(nch), dHCT(nch), dgs(1), ddY(nch);
+    Dev<__half> dY16((size_t)T * B * 2048), dHT16(nch), dHP16(nch), dGT16(2 * nch);
+    dgs.up({1024.f});
+    ddY.up(randn(nch, 1e-3f));
+    int rc = 0;
+    float ms = time_ms(3, [&] {
+      rc |= pk_rnn_layer_fwd(PK_CELL_LIGRU, T, B, H, ndir, PK_ACT_RELU, dPT.p, ld, dsc.p, dsh.p, dU.p, dmask.p, 1.f, nullptr, 2048,
+                             dY16.p, 2048, dHT.p, dHT16.p, dHP16.p, dZT.p, dHCT.p, ld, nullptr);
+    });
+    printf("ligru_fwd H=1024 tcgen05: %.3f ms/layer  (%.3f us/step) rc=%d %s\n", ms, ms * 1000.f / T, rc, rc ? pk_last_error() : "");
+    ms = time_ms(3, [&] {
+      rc |= pk_rnn_layer_bwd(PK_CELL_LIGRU, T, B, H, ndir, PK_ACT_RELU, ddY.p, dHT.p, dZT.p, dHCT.p, ld, dU.p, dmask.p, 1.f, dgs.p,
+                             nullptr, dGT16.p, nullptr);
+    });
+    printf("ligru_bwd H=1024 tcgen05: %.3f ms/layer  (%.3f us/step) rc=%d %s\n", ms, ms * 1000.f / T, rc, rc ? pk_last_error() : "");
   }
   struct G { const char* name; int M, N, K, sk; };
   const G gs[] = {{"proj  PT=W.X^T  ", 1100, 16000, 1100, 1}, {"head  logits    ", 16000, 1936, 1100, 1},
@@ -711,6 +743,8 @@ int main(int argc, char** argv) {
     test_ligru(9, 3, 512, 2, PK_ACT_LEAKY_RELU);
     test_ligru(9, 11, 300, 1, PK_ACT_SIGMOID);
     test_ligru(6, 8, 900, 2, PK_ACT_RELU);
+    test_ligru(5, 8, 1024, 2, PK_ACT_RELU);
+    test_ligru(4, 3, 1000, 1, PK_ACT_TANH);
     test_ligru(5, 4, 64, 1, PK_ACT_TANH);
   }
   bench_all();

@@ -136,8 +136,12 @@ class MLP(nn.Module):
 
     def forward(self, x):
         _require_cuda(x, "MLP")
+        with torch.cuda.device(x.device):  # kernels launch on the tensor's device, not the thread's current one
+            return self._forward_on_device(x)
+
+    def _forward_on_device(self, x):
         if self._is_plain_head():
-            return pkf.LinearLogSoftmaxFn.apply(x, self.wx[0].weight, self.wx[0].bias)
+            return pkf.LinearLogSoftmaxFn.apply(x, self.wx[0].weight, self.wx[0].bias, torch.is_grad_enabled())
         return pkf.mlp_forward(self, x)
 
 
@@ -226,13 +230,17 @@ class _Recurrent(nn.Module):
         for a in self.act_names:
             if a not in pk.ACT_IDS:
                 raise NotImplementedError(f"activation {a!r} is not valid inside a recurrent layer")
+        if self._CELL == pk.CELL_RNN and max(self.lay) > pkf.PERSISTENT_MAX_H:
+            raise NotImplementedError(f"pytorch-kaldi_b200.RNN: rnn_lay > {pkf.PERSISTENT_MAX_H} is not supported (the plain RNN cell "
+                                      "runs on the persistent kernels only); there is no fallback")
 
     def forward(self, x):
         _require_cuda(x, type(self).__name__)
         self._check_supported()
         T, B, _ = x.shape
         rows = (2 if self.bidir else 1) * B
-        cfg = pkf.RecStackCfg(bidir=bool(self.bidir), cell=self._CELL, cell_flags=self.cell_flags)
+        cfg = pkf.RecStackCfg(bidir=bool(self.bidir), cell=self._CELL, cell_flags=self.cell_flags,
+                              grad_enabled=torch.is_grad_enabled())
         params = []
         for i, H in enumerate(self.lay):
             mask, mscal = self._mask(i, rows, H, x.device)
@@ -248,7 +256,8 @@ class _Recurrent(nn.Module):
                     params += [bn.weight, bn.bias]
             else:
                 params += [m.bias for m in ws]
-        return pkf.LiGRUStackFn.apply(x, cfg, *params)
+        with torch.cuda.device(x.device):
+            return pkf.LiGRUStackFn.apply(x, cfg, *params)
 
 
 class liGRU(_Recurrent):
@@ -335,11 +344,12 @@ class SincConv(nn.Module):
         if (self.stride, self.padding, self.dilation) != (1, 0, 1) or waveforms.shape[1] != 1:
             raise NotImplementedError("pytorch-kaldi_b200.SincConv: only stride 1 / no padding / no dilation (what "
                                       "SincNet uses) is implemented natively")
-        cfg = pkf.ConvStackCfg(flat_output=False)
+        cfg = pkf.ConvStackCfg(flat_output=False, grad_enabled=torch.is_grad_enabled())
         cfg.layers.append(pkf.ConvLayerCfg(kind="sinc", C=self.out_channels, k=self.kernel_size, pool=1,
                                            act=pk.ACT_IDS["linear"], use_ln=False, sample_rate=self.sample_rate,
                                            min_low_hz=self.min_low_hz, min_band_hz=self.min_band_hz))
-        return pkf.ConvStackFn.apply(waveforms[:, 0, :], cfg, self.low_hz_, self.band_hz_)
+        with torch.cuda.device(waveforms.device):
+            return pkf.ConvStackFn.apply(waveforms[:, 0, :], cfg, self.low_hz_, self.band_hz_)
 
 
 class SincConv_fast(nn.Module):
@@ -428,7 +438,8 @@ class _ConvFrontEnd(nn.Module):
 
     def forward(self, x):
         _require_cuda(x, type(self).__name__)
-        return pkf.conv_forward(self, x, self._PREFIX)
+        with torch.cuda.device(x.device):
+            return pkf.conv_forward(self, x, self._PREFIX)
 
 
 class CNN(_ConvFrontEnd):

@@ -43,6 +43,7 @@ class RecStackCfg:
     layers: List[RecLayerCfg] = field(default_factory=list)
     cell: int = pk.CELL_LIGRU
     cell_flags: int = 0  # tuning flags OR-ed into the cell id (cluster size, ...)
+    grad_enabled: bool = True  # torch.is_grad_enabled() at call time (inside Function.forward it is always off)
 
 
 def _rows_view(x2d_src: torch.Tensor, T: int, B: int):
@@ -69,7 +70,7 @@ def _side_stream(dev):
 
 OVERLAP_WGRAD = os.environ.get("PK_OVERLAP", "1") != "0"
 
-PERSISTENT_MAX_H = 560  # largest hidden size the register-resident persistent kernels hold
+PERSISTENT_MAX_H = 1024  # largest hidden size the persistent tcgen05 kernels hold (16 CTAs x 64 units; csrc/pk_rnn_tc.cu)
 
 
 def _kernel_gates(cell: int) -> int:
@@ -104,7 +105,9 @@ class LiGRUStackFn(torch.autograd.Function):
         TB = T * B
         ldt = pad8(TB)
         ndir = 2 if cfg.bidir else 1
-        need_grad = any(ctx.needs_input_grad)
+        # needs_input_grad reflects requires_grad of the inputs, not the grad mode: under torch.no_grad() (the valid /
+        # forward phases) nothing is saved for backward and none of the training-only buffers is allocated or written
+        need_grad = cfg.grad_enabled and any(ctx.needs_input_grad)
         f32 = dict(device=dev, dtype=torch.float32)
         f16 = dict(device=dev, dtype=torch.float16)
         ngr, ngk = _real_gates(cfg.cell), _kernel_gates(cfg.cell)
@@ -336,7 +339,7 @@ class LinearLogSoftmaxFn(torch.autograd.Function):
     dnn_act=softmax, :53-54).  Input [N,F] row-major fp32, output log-posteriors [N,S]."""
 
     @staticmethod
-    def forward(ctx, x, W, b):
+    def forward(ctx, x, W, b, grad_enabled=True):
         if not x.is_cuda:
             raise RuntimeError("pytorch-kaldi_b200: MLP needs CUDA tensors (there is no CPU fallback)")
         dev = x.device
@@ -344,15 +347,15 @@ class LinearLogSoftmaxFn(torch.autograd.Function):
         S = W.shape[0]
         f32 = dict(device=dev, dtype=torch.float32)
         f16 = dict(device=dev, dtype=torch.float16)
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = grad_enabled and any(ctx.needs_input_grad)
         ldF, ldn, ldS = pad8(F), pad8(N), pad8(S)
         x2 = x if (x.dtype == torch.float32 and x.stride(1) == 1) else x.float().contiguous()
         X16 = torch.empty(N, ldF, **f16)
-        XT16 = torch.empty(F, ldn, **f16) if ctx.needs_input_grad[1] else None
+        XT16 = torch.empty(F, ldn, **f16) if (need_grad and ctx.needs_input_grad[1]) else None
         pk.transpose_f32(x2, x2.stride(0), N, F, outT16=XT16, ldo16=ldn, in16=X16, ldi16=ldF)
         Wc = W.contiguous()
         W16 = torch.empty(S, ldF, **f16)
-        WT16 = torch.empty(F, ldS, **f16) if ctx.needs_input_grad[0] else None
+        WT16 = torch.empty(F, ldS, **f16) if (need_grad and ctx.needs_input_grad[0]) else None
         pk.transpose_f32(Wc, F, S, F, outT16=WT16, ldo16=ldS, in16=W16, ldi16=ldF)
         logp = torch.empty(N, S, **f32)
         pk.gemm_tn(X16, W16, logp, N, S, F, lda=ldF, ldb=ldF, ldc=S, bias=b.contiguous() if b is not None else None,
@@ -387,7 +390,7 @@ class LinearLogSoftmaxFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dW = torch.empty(S, F, **f32)
             pk.gemm_tn(dT16, XT16, dW, S, F, N, lda=ldn, ldb=ldn, ldc=F, alpha_dev=inv, split_k=8)
-        return dx, dW, db
+        return dx, dW, db, None
 
 
 class HeadNLLFn(torch.autograd.Function):
@@ -457,6 +460,7 @@ class DenseLayerCfg:
     bn_training: bool
     bn: Optional[torch.nn.Module] = None
     keepT: Optional[torch.Tensor] = None   # fp16 [O, pad8(N)] with 0 or 1/(1-p) (training dropout) or None
+    grad_enabled: bool = True              # torch.is_grad_enabled() at call time
 
 
 class MLPStackFn(torch.autograd.Function):
@@ -475,7 +479,7 @@ class MLPStackFn(torch.autograd.Function):
         ldn = pad8(N)
         f32 = dict(device=dev, dtype=torch.float32)
         f16 = dict(device=dev, dtype=torch.float16)
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = layers[0].grad_enabled and any(ctx.needs_input_grad)
         x2 = x if (x.dtype == torch.float32 and x.stride(1) == 1) else x.float().contiguous()
         I = I0
         X16 = torch.empty(N, pad8(I), **f16)
@@ -616,7 +620,8 @@ def mlp_forward(module, x):
                 keepT = ((torch.rand(O, ldn, device=x.device) >= p).half() / (1.0 - p)).contiguous()
         use_bn = bool(module.dnn_use_batchnorm[i])
         layers.append(DenseLayerCfg(O=O, act=module.dnn_act[i], use_bn=use_bn, bn_training=module.training,
-                                    bn=module.bn[i] if use_bn else None, keepT=keepT))
+                                    bn=module.bn[i] if use_bn else None, keepT=keepT,
+                                    grad_enabled=torch.is_grad_enabled()))
         params += [module.wx[i].weight, module.wx[i].bias]
         if use_bn:
             params += [module.bn[i].weight, module.bn[i].bias]
@@ -649,6 +654,7 @@ class ConvStackCfg:
     ln0: bool = False
     ln0_eps: float = 1e-6
     flat_output: bool = True   # CNN/SincNet return x.view(batch, -1); a bare SincConv returns [N, C, Lout]
+    grad_enabled: bool = True  # torch.is_grad_enabled() at call time
 
 
 class ConvStackFn(torch.autograd.Function):
@@ -664,7 +670,13 @@ class ConvStackFn(torch.autograd.Function):
         N, L0 = x.shape
         f32 = dict(device=dev, dtype=torch.float32)
         f16 = dict(device=dev, dtype=torch.float16)
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = cfg.grad_enabled and any(ctx.needs_input_grad)
+        if need_grad and ctx.needs_input_grad[0]:
+            # the gradient w.r.t. the waveform (a trainable module IN FRONT of the CNN / SincNet / SincConv, e.g. a
+            # joint-training enhancement front-end) is not implemented: fail loudly instead of handing autograd a
+            # silent zero
+            raise NotImplementedError("pytorch-kaldi_b200: CNN / SincNet / SincConv do not produce the gradient w.r.t. their "
+                                      "input yet; detach the input or keep trainable modules behind the front-end")
         xr = x if (x.dtype == torch.float32 and x.stride(1) == 1) else x.float().contiguous()
         pi = 0
         ln0_saved = None
@@ -828,7 +840,7 @@ def conv_forward(module, x, prefix):
             f"pytorch-kaldi_b200.{type(module).__name__}: {prefix}_use_batchnorm / {prefix}_use_batchnorm_inp are not "
             "implemented natively yet (the shipped CNN / SincNet recipes use LayerNorm); there is no eager fallback")
     N, L0 = x.shape
-    cfg = ConvStackCfg(ln0=bool(g("use_laynorm_inp")))
+    cfg = ConvStackCfg(ln0=bool(g("use_laynorm_inp")), grad_enabled=torch.is_grad_enabled())
     params = []
     if cfg.ln0:
         cfg.ln0_eps = module.ln0.eps

@@ -23,19 +23,36 @@ import pk_native as pk
 class FlatTrainer:
     """Re-homes the parameters of `modules` into one contiguous fp32 buffer (and their gradients
     into another), so that a step is: backward -> (allreduce of the flat gradient) -> one
-    rmsprop/sgd kernel over the flat buffers.  state_dict()/load_state_dict() of the modules keep
-    working (parameters stay nn.Parameters, only their storage moves)."""
+    rmsprop/sgd/adam kernel over the flat buffers.  state_dict()/load_state_dict() of the modules keep
+    working (parameters stay nn.Parameters, only their storage moves).
+
+    Optimizer semantics are torch.optim's as configured by utils.optimizer_init (utils.py:2106-2164); options the
+    fused kernels do not implement are REFUSED (never silently ignored).  optimizer_state_dicts() /
+    load_optimizer_state_dicts() emit / accept the torch.optim state_dict layout per architecture, i.e. what the
+    reference stores as `optimizer_par` and reloads for every chunk (core.py:523-535, :713-722)."""
 
     def __init__(self, modules: Iterable[torch.nn.Module], opt: str = "rmsprop", lr: float = 0.0004,
-                 alpha: float = 0.95, eps: float = 1e-8, optimizer_fn=None, betas=(0.9, 0.999), weight_decay: float = 0.0):
-        """optimizer_fn(flat_p, flat_g, flat_v, gscale): test hook that replaces the CUDA optimizer kernel
-        (tests/test_dp_gloo.py runs the buffer / allreduce plumbing on CPU with the oracle's update rule);
-        without it CPU modules are refused."""
+                 alpha: float = 0.95, eps: float = 1e-8, betas=(0.9, 0.999), weight_decay: float = 0.0,
+                 momentum: float = 0.0, centered: bool = False, nesterov: bool = False, dampening: float = 0.0,
+                 amsgrad: bool = False):
+        if opt not in ("rmsprop", "sgd", "adam"):
+            raise NotImplementedError(f"FlatTrainer: optimizer {opt!r} (reference offers sgd / adam / rmsprop)")
+        unsupported = []
+        if opt == "rmsprop":
+            unsupported = [n for n, v in (("momentum", momentum), ("centered", centered), ("weight_decay", weight_decay)) if v]
+        elif opt == "sgd":
+            unsupported = [n for n, v in (("momentum", momentum), ("weight_decay", weight_decay), ("nesterov", nesterov),
+                                          ("dampening", dampening)) if v]
+        elif amsgrad:
+            unsupported = ["amsgrad"]
+        if unsupported:
+            raise NotImplementedError(f"FlatTrainer({opt}): option(s) {unsupported} are not implemented by the fused optimizer "
+                                      "kernel; refusing instead of silently ignoring them")
         self.modules: List[torch.nn.Module] = list(modules)
         self.params = [p for m in self.modules for p in m.parameters()]
-        self.optimizer_fn = optimizer_fn
-        if not self.params or (not self.params[0].is_cuda and optimizer_fn is None):
-            raise RuntimeError("FlatTrainer needs CUDA modules (no CPU path)")
+        if not self.params:
+            raise RuntimeError("FlatTrainer: no parameters")
+        self._require_device(self.params[0])
         dev = self.params[0].device
         n = sum(p.numel() for p in self.params)
         self.flat_p = torch.empty(n, device=dev, dtype=torch.float32)
@@ -43,38 +60,148 @@ class FlatTrainer:
         self.flat_v = torch.zeros(n, device=dev, dtype=torch.float32) if opt in ("rmsprop", "adam") else None
         self.flat_m = torch.zeros(n, device=dev, dtype=torch.float32) if opt == "adam" else None
         self.betas, self.weight_decay, self.steps = betas, weight_decay, 0
+        self.offsets = []
         off = 0
         for p in self.params:
             k = p.numel()
             self.flat_p[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat_p[off:off + k].view_as(p)
             p.grad = self.flat_g[off:off + k].view_as(p)
+            self.offsets.append((off, k))
             off += k
         self.n = n
         self.opt, self.lr, self.alpha, self.eps = opt, lr, alpha, eps
+        self.used = None  # per parameter: does it ever receive a gradient? (decided at the first step)
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    @classmethod
+    def from_options(cls, modules, options, lr):
+        """Build from an [architecture] cfg section the way utils.optimizer_init does (utils.py:2106-2164): arch_opt
+        and the opt_* keys (strings)."""
+        sb = lambda v: str(v).lower() in ("true", "1", "yes")
+        kind = options["arch_opt"]
+        if kind == "sgd":
+            return cls(modules, "sgd", lr, momentum=float(options["opt_momentum"]), weight_decay=float(options["opt_weight_decay"]),
+                       nesterov=sb(options["opt_nesterov"]), dampening=float(options["opt_dampening"]))
+        if kind == "adam":
+            return cls(modules, "adam", lr, betas=tuple(map(float, str(options["opt_betas"]).split(","))),
+                       eps=float(options["opt_eps"]), weight_decay=float(options["opt_weight_decay"]),
+                       amsgrad=sb(options["opt_amsgrad"]))
+        if kind == "rmsprop":
+            return cls(modules, "rmsprop", lr, alpha=float(options["opt_alpha"]), eps=float(options["opt_eps"]),
+                       momentum=float(options["opt_momentum"]), centered=sb(options["opt_centered"]),
+                       weight_decay=float(options["opt_weight_decay"]))
+        raise NotImplementedError(f"arch_opt = {kind!r}")
+
+    def _require_device(self, p):
+        if not p.is_cuda:
+            raise RuntimeError("FlatTrainer needs CUDA modules (no CPU path)")
 
     def zero_grad(self):
         self.flat_g.zero_()
+
+    def _mark_used(self):
+        """torch.optim skips parameters whose .grad is None (the reference's unused ln.* / disabled bn.* modules).  The
+        flat buffer always holds a tensor, so 'never written by backward' is detected once, after the first backward:
+        an all-zero gradient range of a parameter means autograd never touched it."""
+        nz = torch.stack([self.flat_g[o:o + k].abs().max() if k else self.flat_g.new_zeros(()) for o, k in self.offsets])
+        self.used = (nz > 0).cpu().tolist()
+
+    def _ranges(self):
+        """Contiguous [offset, length) ranges of the parameters that receive gradients."""
+        out = []
+        for (o, k), u in zip(self.offsets, self.used):
+            if not u or k == 0:
+                continue
+            if out and out[-1][0] + out[-1][1] == o:
+                out[-1][1] += k
+            else:
+                out.append([o, k])
+        return out
+
+    def _apply_update(self, gscale):
+        """The fused optimizer kernel(s) over the flat buffers."""
+        if self.opt == "rmsprop":
+            pk.rmsprop_step(self.flat_p, self.flat_g, self.flat_v, self.lr, self.alpha, self.eps, gscale)
+        elif self.opt == "sgd":
+            pk.sgd_step(self.flat_p, self.flat_g, self.lr, gscale)
+        else:
+            self.steps += 1
+            if self.weight_decay == 0.0:
+                pk.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr, self.betas[0], self.betas[1], self.eps,
+                             0.0, self.steps, gscale)
+            else:
+                # weight decay moves parameters even where the gradient is zero: parameters that never receive a
+                # gradient must be skipped like torch.optim does -> one launch per contiguous used range
+                for o, k in self._ranges():
+                    pk.adam_step(self.flat_p[o:o + k], self.flat_g[o:o + k], self.flat_m[o:o + k], self.flat_v[o:o + k], self.lr,
+                                 self.betas[0], self.betas[1], self.eps, self.weight_decay, self.steps, gscale)
 
     def step(self):
         """(allreduce) + optimizer.  Gradients are summed across ranks and scaled by 1/world inside the
         optimizer kernel, i.e. the loss is the mean over the global batch (equal shard sizes)."""
         if self.world > 1:
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)
-        gscale = 1.0 / self.world
-        if self.optimizer_fn is not None:
-            self.optimizer_fn(self.flat_p, self.flat_g, self.flat_v, gscale)
-        elif self.opt == "rmsprop":
-            pk.rmsprop_step(self.flat_p, self.flat_g, self.flat_v, self.lr, self.alpha, self.eps, gscale)
-        elif self.opt == "sgd":
-            pk.sgd_step(self.flat_p, self.flat_g, self.lr, gscale)
-        elif self.opt == "adam":
+        if self.used is None and (self.opt == "adam" and self.weight_decay != 0.0):
+            self._mark_used()
+        if self.opt != "adam":
             self.steps += 1
-            pk.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr, self.betas[0], self.betas[1], self.eps,
-                         self.weight_decay, self.steps, gscale)
-        else:
-            raise NotImplementedError(self.opt)
+        self._apply_update(1.0 / self.world)
+
+    # ---- optimizer state in the torch.optim layout, one dict per architecture (module) -------------------------
+    def _group(self):
+        if self.opt == "rmsprop":
+            return dict(lr=self.lr, momentum=0, alpha=self.alpha, eps=self.eps, centered=False, weight_decay=0)
+        if self.opt == "sgd":
+            return dict(lr=self.lr, momentum=0, dampening=0, weight_decay=0, nesterov=False)
+        return dict(lr=self.lr, betas=tuple(self.betas), eps=self.eps, weight_decay=self.weight_decay, amsgrad=False)
+
+    def optimizer_state_dicts(self):
+        """[{'state': {i: {...}}, 'param_groups': [{..., 'params': [0..n-1]}]} per module] — the layout of
+        torch.optim.{RMSprop,SGD,Adam}.state_dict() (RMSprop: step, square_avg; Adam: step, exp_avg, exp_avg_sq; SGD
+        without momentum: empty), parameters indexed in registration order like the reference's per-architecture
+        optimizers.  Parameters that never received a gradient carry no state, as in torch.optim."""
+        if self.used is None and self.steps > 0:
+            self._mark_used()
+        out, pi = [], 0
+        for m in self.modules:
+            ps = list(m.parameters())
+            state = {}
+            for j, p in enumerate(ps):
+                o, k = self.offsets[pi + j]
+                if self.steps == 0 or self.opt == "sgd" or (self.used is not None and not self.used[pi + j]):
+                    continue
+                st = {"step": torch.tensor(float(self.steps))}
+                if self.opt == "rmsprop":
+                    st["square_avg"] = self.flat_v[o:o + k].view_as(p).clone()
+                else:
+                    st["exp_avg"] = self.flat_m[o:o + k].view_as(p).clone()
+                    st["exp_avg_sq"] = self.flat_v[o:o + k].view_as(p).clone()
+                state[j] = st
+            g = self._group()
+            g["params"] = list(range(len(ps)))
+            out.append({"state": state, "param_groups": [g]})
+            pi += len(ps)
+        return out
+
+    def load_optimizer_state_dicts(self, dicts):
+        """Inverse of optimizer_state_dicts(); accepts dictionaries written by the reference's own torch.optim
+        optimizers (core.py:531-535: `optimizer_par`)."""
+        pi, steps = 0, 0
+        for m, d in zip(self.modules, dicts):
+            ps = list(m.parameters())
+            for j, st in d.get("state", {}).items():
+                o, k = self.offsets[pi + int(j)]
+                steps = max(steps, int(float(st.get("step", 0))))
+                if self.opt == "rmsprop" and "square_avg" in st:
+                    self.flat_v[o:o + k].copy_(st["square_avg"].reshape(-1))
+                if self.opt == "adam":
+                    self.flat_m[o:o + k].copy_(st["exp_avg"].reshape(-1))
+                    self.flat_v[o:o + k].copy_(st["exp_avg_sq"].reshape(-1))
+            g = d.get("param_groups", [{}])[0]
+            self.lr = float(g.get("lr", self.lr))
+            pi += len(ps)
+        self.steps = steps
 
 
 def chunk_step(net, head, trainer: FlatTrainer, inp: torch.Tensor, n_fea: int, fused_head: bool = True):

@@ -23,12 +23,23 @@ def _setup_paths():
             sys.path.insert(0, p)
 
 
-def _oracle_rmsprop(flat_p, flat_g, flat_v, gscale):
+def _cpu_trainer(modules):
+    """FlatTrainer with its two device-specific hooks overridden IN THE TEST (the product class has no test hook):
+    CPU modules are accepted and the fused CUDA optimizer kernel is replaced by the oracle's RMSprop rule."""
     import pk_oracle as orc
-    p, v = orc.rmsprop_step(flat_p.numpy().astype(np.float64), flat_g.numpy().astype(np.float64) * gscale,
-                            flat_v.numpy().astype(np.float64), lr=0.0004, alpha=0.95, eps=1e-8)
-    flat_p.copy_(torch.from_numpy(p).float())
-    flat_v.copy_(torch.from_numpy(v).float())
+    import pk_train
+
+    class CpuTrainer(pk_train.FlatTrainer):
+        def _require_device(self, p):
+            pass
+
+        def _apply_update(self, gscale):
+            p, v = orc.rmsprop_step(self.flat_p.numpy().astype(np.float64), self.flat_g.numpy().astype(np.float64) * gscale,
+                                    self.flat_v.numpy().astype(np.float64), lr=self.lr, alpha=self.alpha, eps=self.eps)
+            self.flat_p.copy_(torch.from_numpy(p).float())
+            self.flat_v.copy_(torch.from_numpy(v).float())
+
+    return CpuTrainer(modules)
 
 
 def _model():
@@ -55,7 +66,7 @@ def _worker(rank, world, port, out):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     net = _model()
-    tr = pk_train.FlatTrainer([net], optimizer_fn=_oracle_rmsprop)
+    tr = _cpu_trainer([net])
     assert tr.world == world
     data = torch.arange(2 * 6 * 5, dtype=torch.float32).reshape(2, 6, 5) / 7.0
     for step in range(3):
@@ -79,7 +90,7 @@ def test_two_rank_data_parallel_matches_single_process():
     _setup_paths()
     import pk_train
     net = _model()
-    tr = pk_train.FlatTrainer([net], optimizer_fn=_oracle_rmsprop)
+    tr = _cpu_trainer([net])
     data = torch.arange(2 * 6 * 5, dtype=torch.float32).reshape(2, 6, 5) / 7.0
     for step in range(3):
         tr.zero_grad()
@@ -94,10 +105,52 @@ def test_flat_trainer_keeps_state_dict_api():
     import pk_train
     net = _model()
     before = {k: v.clone() for k, v in net.state_dict().items()}
-    tr = pk_train.FlatTrainer([net], optimizer_fn=_oracle_rmsprop)
+    tr = _cpu_trainer([net])
     after = net.state_dict()
     assert list(before) == list(after)
     assert all(torch.equal(before[k], after[k]) for k in before)
     assert tr.n == sum(p.numel() for p in net.parameters())
     with pytest.raises(RuntimeError):
-        pk_train.FlatTrainer([_model()])  # CPU modules without the test hook are refused
+        pk_train.FlatTrainer([_model()])  # the product class refuses CPU modules
+    for kw in (dict(opt="rmsprop", momentum=0.9), dict(opt="rmsprop", centered=True), dict(opt="sgd", nesterov=True),
+               dict(opt="sgd", weight_decay=1e-4), dict(opt="adam", amsgrad=True), dict(opt="adagrad")):
+        with pytest.raises(NotImplementedError):   # unsupported optimizer options are refused, never ignored
+            pk_train.FlatTrainer([_model()], **kw)
+
+
+def test_optimizer_state_round_trips_in_torch_optim_layout():
+    """The reference reloads `optimizer_par` for every chunk (core.py:523-535): the flat optimizer state must export
+    to / import from the torch.optim.RMSprop state_dict layout, parameter-indexed per architecture."""
+    _setup_paths()
+    net = _model()
+    ref = _model()
+    ref.load_state_dict(net.state_dict())
+    tr = _cpu_trainer([net])
+    opt = torch.optim.RMSprop(ref.parameters(), lr=0.0004, alpha=0.95, eps=1e-8)
+    data = torch.arange(6 * 5, dtype=torch.float32).reshape(6, 5) / 7.0
+    for step in range(2):
+        tr.zero_grad()
+        _surrogate_loss(net, data + step).backward()
+        tr.step()
+        opt.zero_grad()
+        _surrogate_loss(ref, data + step).backward()
+        opt.step()
+    sd = tr.optimizer_state_dicts()[0]
+    rsd = opt.state_dict()
+    assert sd["param_groups"][0]["params"] == rsd["param_groups"][0]["params"]
+    for j, st in rsd["state"].items():  # every state the reference holds exists here with the same values
+        assert float(sd["state"][j]["step"]) == float(st["step"])
+        assert torch.allclose(sd["state"][j]["square_avg"], st["square_avg"], rtol=1e-5, atol=1e-12)
+    # a fresh trainer resumes from the reference's own optimizer state and then tracks the reference
+    net2 = _model()
+    net2.load_state_dict(ref.state_dict())
+    tr2 = _cpu_trainer([net2])
+    tr2.load_optimizer_state_dicts([rsd])
+    tr2.zero_grad()
+    _surrogate_loss(net2, data + 2).backward()
+    tr2.step()
+    opt.zero_grad()
+    _surrogate_loss(ref, data + 2).backward()
+    opt.step()
+    for a, b in zip(net2.parameters(), ref.parameters()):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-7)
