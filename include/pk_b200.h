@@ -292,6 +292,20 @@ int pk_rmsprop_step(float* p, const float* g, float* v, int64_t n, float lr, flo
                     float eps, float gscale, void* stream);
 int pk_sgd_step(float* p, const float* g, int64_t n, float lr, float gscale, void* stream);
 
+/* ---- the reference's custom LayerNorm (neural_networks.py:23-33: unbiased std, eps added to the std, over the
+ * feature axis) as used by MLP layers (`dnn_use_laynorm`, :129-145), on channel-major activations PT[C][ld]
+ * (one column per frame).  Forward: in place, XH (optional) receives x_hat, stats[n][2] = (mean, std + eps).
+ * Backward: dT16 (fp16, loss-scaled gradient w.r.t. the LayerNorm output) is replaced by the gradient w.r.t. its
+ * input, dR16 (optional) receives the row-major copy, dgamma / dbeta are un-scaled with scale[1]. */
+int pk_ln_cm_fwd(float* PT, int C, int64_t n, int64_t ld, const float* gamma, const float* beta, float eps, float* XH,
+                 float* stats, void* stream);
+int pk_ln_cm_bwd(void* dT16, int64_t ld16t, void* dR16, int64_t ld16r, const float* XH, int64_t ld, int C, int64_t n,
+                 const float* gamma, const float* stats, float eps, const float* scale, float* dgamma, float* dbeta,
+                 float* dbias /* optional: gradient of a bias added in front of the norm */, void* stream);
+/* per-channel (sum, sum of squares) over n frames of PT[C][ld]: BatchNorm batch statistics when the GEMM epilogue
+ * cannot provide them (BatchNorm applied to a LayerNorm output, :142-143) */
+int pk_row_stats(const float* PT, int C, int64_t n, int64_t ld, double* stats, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

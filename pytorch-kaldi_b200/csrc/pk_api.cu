@@ -337,4 +337,21 @@ int pk_sgd_step(float* p, const float* g, int64_t n, float lr, float gscale, voi
   return sgd_step(p, g, n, lr, gscale, static_cast<cudaStream_t>(stream));
 }
 
+int pk_ln_cm_fwd(float* PT, int C, int64_t n, int64_t ld, const float* gamma, const float* beta, float eps, float* XH,
+                 float* stats, void* stream) {
+  PK_REQUIRE(PT && gamma && beta, "pk_ln_cm_fwd: null input");
+  return ln_cm_fwd(PT, C, n, ld, gamma, beta, eps, XH, stats, static_cast<cudaStream_t>(stream));
+}
+int pk_ln_cm_bwd(void* dT16, int64_t ld16t, void* dR16, int64_t ld16r, const float* XH, int64_t ld, int C, int64_t n,
+                 const float* gamma, const float* stats, float eps, const float* scale, float* dgamma, float* dbeta,
+                 float* dbias, void* stream) {
+  PK_REQUIRE(dT16 && XH && gamma && stats && scale && dgamma && dbeta, "pk_ln_cm_bwd: null input");
+  return ln_cm_bwd(static_cast<__half*>(dT16), ld16t, static_cast<__half*>(dR16), ld16r, XH, ld, C, n, gamma, stats, eps, scale,
+                   dgamma, dbeta, dbias, static_cast<cudaStream_t>(stream));
+}
+int pk_row_stats(const float* PT, int C, int64_t n, int64_t ld, double* stats, void* stream) {
+  PK_REQUIRE(PT && stats, "pk_row_stats: null input");
+  return row_stats(PT, C, n, ld, stats, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

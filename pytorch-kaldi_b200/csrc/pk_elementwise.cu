@@ -655,6 +655,110 @@ inline int grid_for(long long work_items, int per_block) {
   return static_cast<int>(b);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Reference LayerNorm (neural_networks.py:23-33: y = gamma (x - mean) / (std_unbiased + eps) + beta over the
+// FEATURE axis) on channel-major activations PT[C][ld]: one thread per frame (column), fully coalesced along n.
+// Forward normalises in place, keeps x_hat for the backward and (mean, std + eps) per frame.
+// ---------------------------------------------------------------------------------------------
+__global__ void ln_cm_fwd_kernel(float* __restrict__ PT, int C, long long n, long long ld, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, float eps, float* __restrict__ XH, float* __restrict__ stats) {
+  const long long col = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (col >= n) return;
+  float s = 0.f;
+  for (int c = 0; c < C; ++c) s += PT[c * ld + col];
+  const float mean = s / C;
+  float ss = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float d = PT[c * ld + col] - mean;
+    ss = fmaf(d, d, ss);
+  }
+  const float sd = sqrtf(ss / (C - 1)) + eps;  // torch.std: unbiased; eps is added to the std
+  const float r = 1.f / sd;
+  for (int c = 0; c < C; ++c) {
+    const float xh = (PT[c * ld + col] - mean) * r;
+    if (XH) XH[c * ld + col] = xh;
+    PT[c * ld + col] = fmaf(__ldg(gamma + c), xh, __ldg(beta + c));
+  }
+  if (stats) {
+    stats[2 * col] = mean;
+    stats[2 * col + 1] = sd;
+  }
+}
+
+// Backward of the same: dY16 (fp16, loss-scaled, gradient w.r.t. the LayerNorm output, channel-major) -> gradient
+// w.r.t. its input in both operand layouts (same scale), dgamma / dbeta un-scaled.
+//   dxh = dy * gamma;  dx = (dxh - mean_c(dxh)) / sd - xh * sum_c(dxh * xh) / ((C - 1) * (sd - eps))
+__global__ void ln_cm_bwd_kernel(__half* __restrict__ dT16, long long ld16t, __half* __restrict__ dR16, long long ld16r,
+                                 const float* __restrict__ XH, long long ld, int C, long long n,
+                                 const float* __restrict__ gamma, const float* __restrict__ stats, float eps,
+                                 const float* __restrict__ scale /* [2]: loss scale, 1 / loss scale */,
+                                 float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias) {
+  const long long col = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool ok = col < n;
+  const float inv_scale = __ldg(scale + 1);
+  float s1 = 0.f, q = 0.f;
+  if (ok)
+    for (int c = 0; c < C; ++c) {
+      const float dxh = __half2float(dT16[c * ld16t + col]) * __ldg(gamma + c);
+      s1 += dxh;
+      q = fmaf(dxh, XH[c * ld + col], q);
+    }
+  const float sd = ok ? stats[2 * col + 1] : 1.f;
+  const float r = 1.f / sd;
+  const float m1 = s1 / C;
+  const float k2 = q / ((C - 1) * fmaxf(sd - eps, 1e-30f));
+  for (int c = 0; c < C; ++c) {
+    float dy = 0.f, xh = 0.f, dx = 0.f;
+    if (ok) {
+      dy = __half2float(dT16[c * ld16t + col]);
+      xh = XH[c * ld + col];
+      dx = (dy * __ldg(gamma + c) - m1) * r - xh * k2;
+      const __half h = f16_sat(dx);
+      dT16[c * ld16t + col] = h;
+      if (dR16) dR16[col * ld16r + c] = h;
+    }
+    // per-channel sums over this block's frames -> one atomic per warp (dbias: the Linear bias in front of the norm)
+    float a = dy * xh, b = dy, e = dx;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+      e += __shfl_xor_sync(0xffffffffu, e, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(dgamma + c, a * inv_scale);
+      atomicAdd(dbeta + c, b * inv_scale);
+      if (dbias) atomicAdd(dbias + c, e * inv_scale);
+    }
+  }
+}
+
+// per-channel (sum, sum of squares) of PT[C][ld] over n frames: BatchNorm batch statistics of a LayerNorm output
+__global__ void row_stats_kernel(const float* __restrict__ PT, long long ld, long long n, double* __restrict__ stats) {
+  const float* row = PT + static_cast<long long>(blockIdx.x) * ld;
+  double s = 0.0, ss = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const double v = row[i];
+    s += v;
+    ss += v * v;
+  }
+  __shared__ double sh[2][32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = ss; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) { a += sh[0][w]; b += sh[1][w]; }
+    stats[2 * blockIdx.x] = a;
+    stats[2 * blockIdx.x + 1] = b;
+  }
+}
+
 }  // namespace
 
 int transpose_f32(const float* in, long long ldi, int R, int C, float* outT, long long ldo, __half* outT16,
@@ -817,6 +921,32 @@ int rows_sub_vec(float* x, long long ld, long long n, int C, const float* v, cud
 int sgd_step(float* p, const float* g, long long n, float lr, float gscale, cudaStream_t stream) {
   if (n <= 0) return 0;
   sgd_kernel<<<grid_for(n, 1024), 256, 0, stream>>>(p, g, n, lr, gscale);
+  PK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+
+int ln_cm_fwd(float* PT, int C, long long n, long long ld, const float* gamma, const float* beta, float eps, float* XH,
+              float* stats, cudaStream_t stream) {
+  PK_REQUIRE(C > 1 && n > 0, "ln_cm_fwd: need C > 1 features and n > 0 frames");
+  ln_cm_fwd_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, stream>>>(PT, C, n, ld, gamma, beta, eps, XH, stats);
+  PK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int ln_cm_bwd(__half* dT16, long long ld16t, __half* dR16, long long ld16r, const float* XH, long long ld, int C, long long n,
+              const float* gamma, const float* stats, float eps, const float* scale, float* dgamma, float* dbeta,
+              float* dbias, cudaStream_t stream) {
+  PK_REQUIRE(C > 1 && n > 0, "ln_cm_bwd: need C > 1 features and n > 0 frames");
+  PK_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, sizeof(float) * C, stream));
+  PK_CHECK_CUDA(cudaMemsetAsync(dbeta, 0, sizeof(float) * C, stream));
+  if (dbias) PK_CHECK_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * C, stream));
+  ln_cm_bwd_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, stream>>>(dT16, ld16t, dR16, ld16r, XH, ld, C, n, gamma, stats,
+                                                                               eps, scale, dgamma, dbeta, dbias);
+  PK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int row_stats(const float* PT, int C, long long n, long long ld, double* stats, cudaStream_t stream) {
+  row_stats_kernel<<<C, 256, 0, stream>>>(PT, ld, n, stats);
   PK_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -299,4 +299,12 @@ int rows_sub_vec(float* x, long long ld, long long n, int C, const float* v, cud
 int adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float wd,
               long long step, float gscale, cudaStream_t stream);
 
+// reference LayerNorm (unbiased std, eps added to the std) over the feature axis of channel-major activations
+int ln_cm_fwd(float* PT, int C, long long n, long long ld, const float* gamma, const float* beta, float eps, float* XH,
+              float* stats, cudaStream_t stream);
+int ln_cm_bwd(__half* dT16, long long ld16t, __half* dR16, long long ld16r, const float* XH, long long ld, int C, long long n,
+              const float* gamma, const float* stats, float eps, const float* scale, float* dgamma, float* dbeta,
+              float* dbias, cudaStream_t stream);
+int row_stats(const float* PT, int C, long long n, long long ld, double* stats, cudaStream_t stream);
+
 }  // namespace pk

@@ -68,7 +68,7 @@ struct FwdWs {
   uint64_t in_full[RI], in_empty[RI], out_full[RO], out_empty[RO];
 };
 
-template <int KT, int MT, int CL>
+template <int KT, int MT, int CL, int ACT>  // ACT: a per-element activation switch is an indirect branch (BRX) on the serial path
 __global__ void __launch_bounds__(kThreads, 1) ligru_fwd_ws_kernel(const RecFwdArgs a) {
   using S = FwdWs<KT, MT, CL>;
   constexpr int NT = S::NT, UPC = S::UPC;
@@ -147,7 +147,6 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_fwd_ws_kernel(const RecFwdA
       const uint32_t h16_base = smem_u32(&sm.h16[0][0][0][0]);
       constexpr uint32_t kBufBytes = NT * kRows * 16;
       const int tg = crank * MT + warp;  // global tile id of this warp's 8 units
-      const int act = a.act;
       const bool z0 = a.force_z0 != 0;
 
       const bool clk_on = a.dbg_clk != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
@@ -191,14 +190,14 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_fwd_ws_kernel(const RecFwdA
         float hn[2], zz[2], hcv[2];
         {
           const float zt = z0 ? 0.f : sigmoid_fast(fmaf(sc_z, pz.x, sh_z) + cz0);
-          const float hc = act_fwd_fast(act, fmaf(sc_h, ph.x, sh_h) + ch0) * msk[0];
+          const float hc = act_fwd_fast(ACT, fmaf(sc_h, ph.x, sh_h) + ch0) * msk[0];
           float h = fmaf(zt, hprev[0] - hc, hc);
           if (!rok[0]) h = 0.f;
           hn[0] = h; zz[0] = zt; hcv[0] = hc; hprev[0] = h;
         }
         {
           const float zt = z0 ? 0.f : sigmoid_fast(fmaf(sc_z, pz.y, sh_z) + cz1);
-          const float hc = act_fwd_fast(act, fmaf(sc_h, ph.y, sh_h) + ch1) * msk[1];
+          const float hc = act_fwd_fast(ACT, fmaf(sc_h, ph.y, sh_h) + ch1) * msk[1];
           float h = fmaf(zt, hprev[1] - hc, hc);
           if (!rok[1]) h = 0.f;
           hn[1] = h; zz[1] = zt; hcv[1] = hc; hprev[1] = h;
@@ -402,7 +401,7 @@ struct BwdWs {
   uint64_t in_full[RI], in_empty[RI], out_full[RO], out_empty[RO];
 };
 
-template <int KT, int MT, int CL>
+template <int KT, int MT, int CL, int ACT>
 __global__ void __launch_bounds__(kThreads, 1) ligru_bwd_ws_kernel(const RecBwdArgs a) {
   using S = BwdWs<KT, MT, CL>;
   constexpr int MT16 = S::MT16, NWC = S::NWC, NT = S::NT, UPC = S::UPC;
@@ -489,7 +488,6 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_bwd_ws_kernel(const RecBwdA
       const uint32_t g16_base = smem_u32(&sm.g16[0][0][0][0][0]);
       constexpr uint32_t kGateBytes = NT * kRows * 16;
       constexpr uint32_t kBufBytes = 2 * kGateBytes;
-      const int act = a.act;
 
       const bool clk_on = a.dbg_clk != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
       long long tsum[6] = {0, 0, 0, 0, 0, 0};
@@ -516,8 +514,8 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_bwd_ws_kernel(const RecBwdA
         __half2 da16, dz16;
         {
           const float dh0 = dy.x + carry[0], dh1 = dy.y + carry[1];
-          float da0 = dh0 * (1.f - zz.x) * msk[0] * act_bwd_from_out(act, hc.x * rm0);
-          float da1 = dh1 * (1.f - zz.y) * msk[1] * act_bwd_from_out(act, hc.y * rm1);
+          float da0 = dh0 * (1.f - zz.x) * msk[0] * act_bwd_from_out(ACT, hc.x * rm0);
+          float da1 = dh1 * (1.f - zz.y) * msk[1] * act_bwd_from_out(ACT, hc.y * rm1);
           float dz0 = dh0 * (hp.x - hc.x) * zz.x * (1.f - zz.x);
           float dz1 = dh1 * (hp.y - hc.y) * zz.y * (1.f - zz.y);
           if (!rok[0]) { da0 = 0.f; dz0 = 0.f; }
@@ -730,10 +728,17 @@ int launch_ws(const Args& a, int cluster, int nclusters, size_t smem, cudaStream
   return 0;
 }
 
-#define PK_FWD_WS(KT, MT, CL) \
-  return launch_ws<RecFwdArgs, ligru_fwd_ws_kernel<KT, MT, CL>>(a, CL, nclusters, sizeof(FwdWs<KT, MT, CL>) + 128, stream)
-#define PK_BWD_WS(KT, MT, CL) \
-  return launch_ws<RecBwdArgs, ligru_bwd_ws_kernel<KT, MT, CL>>(a, CL, nclusters, sizeof(BwdWs<KT, MT, CL>) + 128, stream)
+#define PK_WS_ACT(ARGS, KERN, SMEM, KT, MT, CL)                                                              \
+  switch (a.act) {                                                                                         \
+    case ACT_RELU: return launch_ws<ARGS, KERN<KT, MT, CL, ACT_RELU>>(a, CL, nclusters, SMEM, stream);     \
+    case ACT_TANH: return launch_ws<ARGS, KERN<KT, MT, CL, ACT_TANH>>(a, CL, nclusters, SMEM, stream);     \
+    case ACT_SIGMOID: return launch_ws<ARGS, KERN<KT, MT, CL, ACT_SIGMOID>>(a, CL, nclusters, SMEM, stream); \
+    case ACT_LEAKY_RELU: return launch_ws<ARGS, KERN<KT, MT, CL, ACT_LEAKY_RELU>>(a, CL, nclusters, SMEM, stream); \
+    case ACT_ELU: return launch_ws<ARGS, KERN<KT, MT, CL, ACT_ELU>>(a, CL, nclusters, SMEM, stream);       \
+    default: return launch_ws<ARGS, KERN<KT, MT, CL, ACT_LINEAR>>(a, CL, nclusters, SMEM, stream);         \
+  }
+#define PK_FWD_WS(KT, MT, CL) PK_WS_ACT(RecFwdArgs, ligru_fwd_ws_kernel, sizeof(FwdWs<KT, MT, CL>) + 128, KT, MT, CL)
+#define PK_BWD_WS(KT, MT, CL) PK_WS_ACT(RecBwdArgs, ligru_bwd_ws_kernel, sizeof(BwdWs<KT, MT, CL>) + 128, KT, MT, CL)
 
 long long* g_dbg_clk = nullptr;
 

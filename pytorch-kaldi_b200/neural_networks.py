@@ -285,19 +285,117 @@ class LSTM(_Recurrent):
     _GATES = (("wfx", "ufh"), ("wix", "uih"), ("wox", "uoh"), ("wcx", "uch"))
 
 
-def _not_built(name, why):
-    class _Stub(nn.Module):
-        def __init__(self, *a, **k):
-            raise NotImplementedError(f"pytorch-kaldi_b200.{name}: {why}")
-    _Stub.__name__ = name
-    return _Stub
+class _CudnnLayout(nn.Module):
+    """LSTM_cudnn / GRU_cudnn / RNN_cudnn (reference neural_networks.py:153-297): thin wrappers over torch.nn.LSTM /
+    GRU / RNN (per-direction weights, two biases, no BatchNorm, zero initial state, inter-layer nn.Dropout).  The
+    constructor is the reference's (same sub-module, same init calls -> identical state_dict keys / shapes /
+    generator consumption, so `cfg/TIMIT_baselines/TIMIT_LSTM_fmllr_cudnn.cfg` and its checkpoints drop in), but the
+    forward never calls cuDNN: every (layer, direction) runs on this library's own recurrent kernels as a
+    unidirectional, bias-only layer (pk_functions.LiGRUStackFn), the reverse direction on the time-flipped input."""
+
+    _ATTR = ""      # ModuleList attribute name of the reference class
+    _TORCH = None   # torch.nn class
+    _CELL = -1
+    _ORDER = ()     # torch's row-block order -> this library's gate order (blocks of H rows)
+
+    def __init__(self, options, inp_dim):
+        super().__init__()
+        self.input_dim = inp_dim
+        self.hidden_size = int(options["hidden_size"])
+        self.num_layers = int(options["num_layers"])
+        if self._TORCH is nn.RNN:
+            self.nonlinearity = options["nonlinearity"]
+        self.bias = bool(strtobool(options["bias"]))
+        self.batch_first = bool(strtobool(options["batch_first"]))
+        self.dropout = float(options["dropout"])
+        self.bidirectional = bool(strtobool(options["bidirectional"]))
+        kw = dict(bias=self.bias, dropout=self.dropout, bidirectional=self.bidirectional)
+        if self._TORCH is nn.RNN:
+            kw["nonlinearity"] = self.nonlinearity
+        setattr(self, self._ATTR, nn.ModuleList([self._TORCH(self.input_dim, self.hidden_size, self.num_layers, **kw)]))
+        self._init_like_reference()
+        self.out_dim = self.hidden_size + self.bidirectional * self.hidden_size
+        self.cell_flags = 0
+
+    def _init_like_reference(self):
+        pass
+
+    def _act(self):
+        return pk.ACT_IDS["tanh"]
+
+    def forward(self, x):
+        _require_cuda(x, type(self).__name__)
+        rnn = getattr(self, self._ATTR)[0]
+        H, G = self.hidden_size, len(self._ORDER)
+        out = x
+        with torch.cuda.device(x.device):
+            for layer in range(self.num_layers):
+                ys = []
+                for d in range(2 if self.bidirectional else 1):
+                    sfx = f"_l{layer}" + ("_reverse" if d else "")
+                    w_ih, w_hh = getattr(rnn, "weight_ih" + sfx), getattr(rnn, "weight_hh" + sfx)
+                    ws = [w_ih[g * H:(g + 1) * H] for g in self._ORDER]
+                    us = [w_hh[g * H:(g + 1) * H] for g in self._ORDER]
+                    if self.bias:
+                        b = getattr(rnn, "bias_ih" + sfx) + getattr(rnn, "bias_hh" + sfx)
+                        bs = [b[g * H:(g + 1) * H] for g in self._ORDER]
+                    else:
+                        bs = [torch.zeros(H, device=x.device) for _ in range(G)]
+                    cfg = pkf.RecStackCfg(bidir=False, cell=self._CELL, cell_flags=self.cell_flags,
+                                          grad_enabled=torch.is_grad_enabled())
+                    cfg.layers.append(pkf.RecLayerCfg(H=H, act=self._act(), use_bn=False, bn_training=False, bns=[],
+                                                      mask=None, mask_scalar=1.0))
+                    xin = torch.flip(out, dims=[0]) if d else out       # reverse direction: time-flipped input ...
+                    y = pkf.LiGRUStackFn.apply(xin, cfg, *ws, *us, *bs)
+                    ys.append(torch.flip(y, dims=[0]) if d else y)      # ... and output
+                out = torch.cat(ys, dim=2) if len(ys) > 1 else ys[0]
+                if self.dropout > 0.0 and self.training and layer < self.num_layers - 1:
+                    out = torch.nn.functional.dropout(out, self.dropout, True)  # nn.LSTM's inter-layer dropout
+        return out
 
 
-# cuDNN wrappers of the reference (neural_networks.py:153-297) are deliberately not provided:
-# the north star of this library forbids routing the recurrence through cuDNN.
-LSTM_cudnn = _not_built("LSTM_cudnn", "cuDNN RNNs are out of scope; use arch_class = LSTM")
-GRU_cudnn = _not_built("GRU_cudnn", "cuDNN RNNs are out of scope; use arch_class = GRU")
-RNN_cudnn = _not_built("RNN_cudnn", "cuDNN RNNs are out of scope; use arch_class = RNN")
+class LSTM_cudnn(_CudnnLayout):
+    """nn.LSTM gate algebra (i, f, g, o row blocks; c = f c + i tanh(g); h = o tanh(c)) = this library's LSTM cell with
+    act = tanh and no mask; gate order of the kernels: f, i, o, c."""
+    _ATTR, _TORCH, _CELL, _ORDER = "lstm", nn.LSTM, pk.CELL_LSTM, (1, 0, 3, 2)
+
+    def _init_like_reference(self):
+        for name, param in self.lstm[0].named_parameters():  # reference :178-184
+            if "weight_hh" in name:
+                if self.batch_first:
+                    nn.init.orthogonal_(param)
+            elif "bias" in name:
+                nn.init.zeros_(param)
+
+
+class RNN_cudnn(_CudnnLayout):
+    """nn.RNN: h = act(W x + b_ih + U h + b_hh), act in {tanh, relu}."""
+    _ATTR, _TORCH, _CELL, _ORDER = "rnn", nn.RNN, pk.CELL_RNN, (0,)
+
+    def _act(self):
+        return pk.ACT_IDS[self.nonlinearity]
+
+
+class GRU_cudnn(_CudnnLayout):
+    """nn.GRU computes the candidate as tanh(W x + b + r * (U h + b_hn)); the reference's own GRU class — and this
+    library's GRU kernels — contract U with (r * h) instead (neural_networks.py:634).  The constructor (state_dict
+    layout, init) is provided; the forward is refused rather than silently computing different math."""
+    _ATTR, _TORCH, _CELL, _ORDER = "gru", nn.GRU, pk.CELL_GRU, (2, 1, 0)
+
+    def _init_like_reference(self):
+        for name, param in self.gru[0].named_parameters():  # reference :229-235
+            if "weight_hh" in name:
+                nn.init.orthogonal_(param)
+            elif "weight_ih" in name:
+                nn.init.xavier_uniform_(param)
+            elif "bias" in name:
+                nn.init.zeros_(param)
+
+    def forward(self, x):  # noqa: D401
+        raise NotImplementedError("pytorch-kaldi_b200.GRU_cudnn: nn.GRU's candidate gate r * (U h + b) is not what the native "
+                                  "GRU kernels compute (U (r * h), the reference's own GRU class); use arch_class = GRU")
+
+
 # ---------------------------------------------------------------------------------------------
 # convolutional front-ends: CNN :1464-1556, SincNet :1559-1665, SincConv :1668-1813
 # ---------------------------------------------------------------------------------------------

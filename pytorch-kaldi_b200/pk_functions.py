@@ -70,6 +70,44 @@ def _side_stream(dev):
 
 OVERLAP_WGRAD = os.environ.get("PK_OVERLAP", "1") != "0"
 
+# Set by pk_train.FlatTrainer: parameters live in ONE flat buffer whose gradient buffer is zeroed / consumed once per
+# step, every parameter is used once per step -> backward may write a weight gradient straight into `param.grad`
+# (a view of the flat gradient buffer) and hand autograd `None`, which removes the AccumulateGrad read-modify-write
+# (one eager `add` per parameter per step) from the hot path.
+DIRECT_GRAD = False
+_DIRECT_STORAGES = set()   # data_ptr of the flat gradient storages that opted in (FlatTrainer(direct_grad=True))
+
+
+def register_direct_grad_buffer(flat_g):
+    global DIRECT_GRAD
+    _DIRECT_STORAGES.add(flat_g.untyped_storage().data_ptr())
+    DIRECT_GRAD = True
+
+
+def _stacked(ts):
+    """[t0; t1; ...] as ONE matrix without a copy when the tensors are adjacent rows of the same storage (FlatTrainer
+    lays the gates of a layer out back to back), else None."""
+    t0 = ts[0]
+    if t0.dim() != 2 or not all(t.is_contiguous() and t.dtype == t0.dtype and t.shape[1] == t0.shape[1] for t in ts):
+        return None
+    off = t0.storage_offset()
+    for t in ts:
+        if t.untyped_storage().data_ptr() != t0.untyped_storage().data_ptr() or t.storage_offset() != off:
+            return None
+        off += t.numel()
+    rows = sum(t.shape[0] for t in ts)
+    return t0.as_strided((rows, t0.shape[1]), (t0.shape[1], 1))
+
+
+def _direct_grad_target(params):
+    """The stacked `.grad` view of `params` if gradients may be written in place (see DIRECT_GRAD), else None."""
+    if not DIRECT_GRAD:
+        return None
+    gs = [p.grad for p in params]
+    if any(g is None or g.untyped_storage().data_ptr() not in _DIRECT_STORAGES for g in gs):
+        return None
+    return _stacked(gs)
+
 PERSISTENT_MAX_H = 1024  # largest hidden size the persistent tcgen05 kernels hold (16 CTAs x 64 units; csrc/pk_rnn_tc.cu)
 
 
@@ -142,14 +180,19 @@ class LiGRUStackFn(torch.autograd.Function):
             ldD, ldG = pad8(D), pad8(CG)
             on_side = OVERLAP_WGRAD and li > 0
             with torch.cuda.stream(side if on_side else main):
+                wparams, uparams = list(ws_), list(us_)   # the nn.Parameters themselves (targets of direct gradients)
                 for _ in range(ngk - ngr):  # RNN: the update-gate block is all zeros (and pinned to 0 in the kernel)
                     ws_.append(torch.zeros_like(ws_[0]))
                     us_.append(torch.zeros_like(us_[0]))
-                Wcat = torch.cat(ws_, 0).contiguous()
+                Wcat = _stacked(ws_)       # zero-copy when the gates are adjacent in the flat parameter buffer
+                if Wcat is None:
+                    Wcat = torch.cat(ws_, 0).contiguous()
                 W16 = torch.empty(CG, ldD, **f16)
                 WT16 = torch.empty(D, ldG, **f16) if need_grad else None
                 pk.transpose_f32(Wcat, D, CG, D, outT16=WT16, ldo16=ldG, in16=W16, ldi16=ldD)
-                U = torch.cat(us_, 0).contiguous()
+                U = _stacked(us_)
+                if U is None:
+                    U = torch.cat(us_, 0).contiguous()
                 bias_cat = None
                 if biases is not None:
                     bias_cat = torch.cat(biases + [torch.zeros_like(biases[0]) for _ in range(ngk - ngr)]).contiguous()
@@ -160,7 +203,8 @@ class LiGRUStackFn(torch.autograd.Function):
                     for t in (Wcat, W16, WT16, U, bias_cat):
                         if t is not None:
                             t.record_stream(main)   # allocated under the side stream, consumed on the main one
-            packs.append(dict(W16=W16, WT16=WT16, U=U, gammas=gammas, betas=betas, bias_cat=bias_cat, ev=ev))
+            packs.append(dict(W16=W16, WT16=WT16, U=U, gammas=gammas, betas=betas, bias_cat=bias_cat, ev=ev,
+                              wparams=wparams, uparams=uparams))
             D = ndir * H
 
         D = D0
@@ -229,7 +273,8 @@ class LiGRUStackFn(torch.autograd.Function):
             if need_grad:
                 saved.append(dict(D=D, H=H, XT16=XT16, WT16=WT16, PT=PT if bn_train else None, mean=mean, rstd=rstd,
                                   gamma=gamma, HT=HT, SV=SV, HP16=HP16, HX16=HX16, U=U, mask=L.mask, mask_scalar=L.mask_scalar,
-                                  act=L.act, use_bn=L.use_bn, bn_train=bn_train, stepwise=stepwise))
+                                  act=L.act, use_bn=L.use_bn, bn_train=bn_train, stepwise=stepwise,
+                                  wparams=pkd["wparams"], uparams=pkd["uparams"]))
             # next layer reads this layer's fp16 outputs directly
             X16, XT16, D = Y16, HT16, F
         ctx.cfg = cfg
@@ -290,8 +335,10 @@ class LiGRUStackFn(torch.autograd.Function):
             pk.bn_bwd(CG, ndir, TB, GT, GT16, ldt, S["PT"], ldt, S["use_bn"], S["bn_train"], S["mean"], S["rstd"],
                       S["gamma"], sc, dgamma, dbeta, dPT16, ldt, dP16, ldG, sums)
             # weight gradients: off the critical path -> side stream, next to the following layer's recurrence
-            dU = torch.empty(CG, H, **f32)
-            dW = torch.empty(CG, D, **f32)
+            dU_direct = _direct_grad_target(S["uparams"]) if ngk == ngr else None
+            dW_direct = _direct_grad_target(S["wparams"]) if ngk == ngr else None
+            dU = dU_direct if dU_direct is not None else torch.empty(CG, H, **f32)
+            dW = dW_direct if dW_direct is not None else torch.empty(CG, D, **f32)
             if OVERLAP_WGRAD:
                 side.wait_stream(main)
                 for t in (GT16, S["HP16"], S["HX16"], dPT16, S["XT16"], dU, dW, sc):
@@ -312,7 +359,9 @@ class LiGRUStackFn(torch.autograd.Function):
                 # dW = dP^T X
                 pk.gemm_tn(dPT16, S["XT16"], dW, CG, D, TB, lda=ldt, ldb=ldt, ldc=D, alpha_dev=inv, split_k=8)
             sl = [slice(g * H, (g + 1) * H) for g in range(ngr)]
-            lg = [dW[s] for s in sl] + [dU[s] for s in sl]
+            # gradients written in place into param.grad are reported to autograd as None (nothing left to accumulate)
+            lg = ([None] * ngr if dW_direct is not None else [dW[s] for s in sl]) + \
+                 ([None] * ngr if dU_direct is not None else [dU[s] for s in sl])
             if S["use_bn"]:
                 for s in sl:
                     lg += [dgamma[s], dbeta[s]]
@@ -424,6 +473,7 @@ class HeadNLLFn(torch.autograd.Function):
         err = (acc[1] / N).float()
         ctx.save_for_backward(logp, lab)
         ctx.aux = (XT16, WT16, N, F, S)
+        ctx.wparam = W
         ctx.mark_non_differentiable(err, logp)
         return loss, err, logp
 
@@ -447,9 +497,11 @@ class HeadNLLFn(torch.autograd.Function):
         db = db * dl  # the kernel's bias gradient excludes the device-side factor
         dx = torch.empty(N, F, **f32)
         pk.gemm_tn(d16, WT16, dx, N, F, S, lda=ldS, ldb=ldS, ldc=F, alpha=1.0 / out_scale)
-        dW = torch.empty(S, F, **f32)
+        dW_direct = _direct_grad_target([ctx.wparam])
+        dW = dW_direct if dW_direct is not None else torch.empty(S, F, **f32)
         pk.gemm_tn(dT16, XT16, dW, S, F, N, lda=ldn, ldb=ldn, ldc=F, alpha=1.0 / out_scale, split_k=8)
-        return dx, dW, db, None
+        ctx.wparam = None
+        return dx, (None if dW_direct is not None else dW), db, None
 
 
 @dataclass
@@ -461,6 +513,8 @@ class DenseLayerCfg:
     bn: Optional[torch.nn.Module] = None
     keepT: Optional[torch.Tensor] = None   # fp16 [O, pad8(N)] with 0 or 1/(1-p) (training dropout) or None
     grad_enabled: bool = True              # torch.is_grad_enabled() at call time
+    use_ln: bool = False                   # reference LayerNorm between the Linear and BatchNorm / act (:129-145)
+    ln_eps: float = 1e-6
 
 
 class MLPStackFn(torch.autograd.Function):
@@ -493,13 +547,16 @@ class MLPStackFn(torch.autograd.Function):
             if L.use_bn:
                 gam, bet = params[pi], params[pi + 1]
                 pi += 2
+            if L.use_ln:
+                lgam, lbet = params[pi], params[pi + 1]
+                pi += 2
             ldI, ldO = pad8(I), pad8(O)
             W16 = torch.empty(O, ldI, **f16)
             WT16 = torch.empty(I, ldO, **f16) if need_grad else None
             pk.transpose_f32(W.contiguous(), I, O, I, outT16=WT16, ldo16=ldO, in16=W16, ldi16=ldI)
             last = li == len(layers) - 1
             if L.act == "softmax":
-                if not last or L.use_bn or L.keepT is not None:
+                if not last or L.use_bn or L.use_ln or L.keepT is not None:
                     raise NotImplementedError("softmax is only supported as the plain last MLP layer")
                 logp = torch.empty(N, O, **f32)
                 pk.gemm_tn(X16, W16, logp, N, O, I, lda=ldI, ldb=ldI, ldc=O, bias=b.contiguous(), bias_mode=1)
@@ -512,7 +569,14 @@ class MLPStackFn(torch.autograd.Function):
             PT = torch.empty(O, ldn, **f32)
             stats = torch.zeros(O, 2, device=dev, dtype=torch.float64) if bn_train else None
             pk.gemm_tn(W16, X16, PT, O, N, I, lda=ldI, ldb=ldI, ldc=ldn, bias=b.contiguous(), bias_mode=2,
-                       rowstats=stats)
+                       rowstats=None if L.use_ln else stats)
+            XH = lnstats = None
+            if L.use_ln:  # y = gamma (x - mean_features) / (std + eps) + beta per frame, in place (:23-33)
+                XH = torch.empty(O, ldn, **f32) if need_grad else None
+                lnstats = torch.empty(N, 2, **f32)
+                pk.ln_cm_fwd(PT, O, N, ldn, lgam.contiguous(), lbet.contiguous(), L.ln_eps, XH, lnstats)
+                if bn_train:   # BatchNorm over the LayerNorm output: its batch statistics need their own pass
+                    pk.row_stats(PT, O, N, ldn, stats)
             scale, shift = torch.empty(O, **f32), torch.empty(O, **f32)
             mean = rstd = None
             if L.use_bn:
@@ -532,7 +596,8 @@ class MLPStackFn(torch.autograd.Function):
             if need_grad:
                 saved.append(dict(kind="dense", I=I, O=O, XT16=XT16, WT16=WT16, PT=PT if bn_train else None, mean=mean,
                                   rstd=rstd, gamma=gam if L.use_bn else None, YT16=YT16, keepT=L.keepT,
-                                  act=pk.ACT_IDS[L.act], use_bn=L.use_bn, bn_train=bn_train))
+                                  act=pk.ACT_IDS[L.act], use_bn=L.use_bn, bn_train=bn_train, use_ln=L.use_ln,
+                                  XH=XH, lnstats=lnstats, lgam=lgam.contiguous() if L.use_ln else None, ln_eps=L.ln_eps))
             X16, XT16, I = Y16, YT16, O
         ctx.saved = saved
         ctx.dims = (N, I0, ldn)
@@ -583,6 +648,11 @@ class MLPStackFn(torch.autograd.Function):
                 # a bias in front of BatchNorm has a mathematically zero gradient (reference: rounding noise)
                 db = torch.zeros(O, **f32) if S["use_bn"] else dbeta
                 lg = [dgamma, dbeta] if S["use_bn"] else []
+                if S["use_ln"]:  # LayerNorm backward turns the gradient w.r.t. its output into that w.r.t. the Linear output
+                    dlg, dlb, db = torch.empty(O, **f32), torch.empty(O, **f32), torch.empty(O, **f32)
+                    pk.ln_cm_bwd(dPT16, ldn, dP16, ldO, S["XH"], ldn, O, N, S["lgam"], S["lnstats"], S["ln_eps"], sc,
+                                 dlg, dlb, db)
+                    lg = lg + [dlg, dlb]
             inv = sc[1:2]
             dW = torch.empty(O, I, **f32)
             pk.gemm_tn(dPT16, S["XT16"], dW, O, I, N, lda=ldn, ldb=ldn, ldc=I, alpha_dev=inv,
@@ -601,10 +671,10 @@ class MLPStackFn(torch.autograd.Function):
 
 def mlp_forward(module, x):
     """neural_networks.MLP.forward for general stacks: builds the static layer description and calls MLPStackFn."""
-    if module.dnn_use_laynorm_inp or module.dnn_use_batchnorm_inp or any(module.dnn_use_laynorm):
+    if module.dnn_use_laynorm_inp or module.dnn_use_batchnorm_inp:
         raise NotImplementedError(
-            "pytorch-kaldi_b200.MLP: dnn_use_laynorm / *_inp normalisation are not implemented natively yet "
-            "(no shipped recipe enables them); there is no eager fallback")
+            "pytorch-kaldi_b200.MLP: dnn_use_laynorm_inp / dnn_use_batchnorm_inp (normalisation of the INPUT) are not "
+            "implemented natively yet (no shipped recipe enables them); there is no eager fallback")
     N = x.shape[0]
     ldn = pad8(N)
     layers, params = [], []
@@ -619,12 +689,15 @@ def mlp_forward(module, x):
             else:
                 keepT = ((torch.rand(O, ldn, device=x.device) >= p).half() / (1.0 - p)).contiguous()
         use_bn = bool(module.dnn_use_batchnorm[i])
+        use_ln = bool(module.dnn_use_laynorm[i])
         layers.append(DenseLayerCfg(O=O, act=module.dnn_act[i], use_bn=use_bn, bn_training=module.training,
                                     bn=module.bn[i] if use_bn else None, keepT=keepT,
-                                    grad_enabled=torch.is_grad_enabled()))
+                                    grad_enabled=torch.is_grad_enabled(), use_ln=use_ln, ln_eps=module.ln[i].eps))
         params += [module.wx[i].weight, module.wx[i].bias]
         if use_bn:
             params += [module.bn[i].weight, module.bn[i].bias]
+        if use_ln:
+            params += [module.ln[i].gamma, module.ln[i].beta]
     return MLPStackFn.apply(x, layers, *params)
 
 

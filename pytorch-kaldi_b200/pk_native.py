@@ -67,6 +67,9 @@ SIGNATURES = {
     "pk_sub_log_prior": [_c_p, _c_i64, _c_i64, _c_int, _c_p, _c_p],
     "pk_adam_step": [_c_p, _c_p, _c_p, _c_p, _c_i64, _c_f, _c_f, _c_f, _c_f, _c_f, _c_i64, _c_f, _c_p],
     "pk_sgd_step": [_c_p, _c_p, _c_i64, _c_f, _c_f, _c_p],
+    "pk_ln_cm_fwd": [_c_p, _c_int, _c_i64, _c_i64, _c_p, _c_p, _c_f, _c_p, _c_p, _c_p],
+    "pk_ln_cm_bwd": [_c_p, _c_i64, _c_p, _c_i64, _c_p, _c_i64, _c_int, _c_i64, _c_p, _c_p, _c_f, _c_p, _c_p, _c_p, _c_p, _c_p],
+    "pk_row_stats": [_c_p, _c_int, _c_i64, _c_i64, _c_p, _c_p],
 }
 
 _lib = None
@@ -101,7 +104,7 @@ KERNELS_PER_CALL = {"pk_dense_act_fwd": 1, "pk_dense_act_bwd": 1, "pk_amax_final
                     "pk_rnn_layer_bwd": 1, "pk_rnn_step_fwd": 1, "pk_rnn_step_bwd": 1, "pk_rowln_fwd": 1, "pk_conv_ln0_bwd": 1,
                     "pk_sinc_filters_fwd": 1, "pk_sinc_filters_bwd": 1, "pk_conv_pack_weights": 1, "pk_conv_im2col0": 1,
                     "pk_conv_im2col_t": 1, "pk_conv_post_fwd": 1, "pk_conv_post_bwd": 1, "pk_logsoftmax_nll": 1, "pk_logsoftmax_bwd": 1, "pk_rmsprop_step": 1, "pk_adam_step": 1, "pk_chunk_prepare": 2, "pk_batch_assemble": 1, "pk_sub_log_prior": 1, "pk_cm_decode": 1,
-                    "pk_sgd_step": 1}
+                    "pk_sgd_step": 1, "pk_ln_cm_fwd": 1, "pk_ln_cm_bwd": 1, "pk_row_stats": 1}
 
 
 def _check(rc, what, extra_kernels=0):
@@ -314,3 +317,16 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, gscale=1.0)
 
 def sgd_step(p, g, lr, gscale=1.0):
     _check(lib().pk_sgd_step(_ptr(p), _ptr(g), p.numel(), float(lr), float(gscale), _stream()), "pk_sgd_step")
+
+
+def ln_cm_fwd(PT, C, n, ld, gamma, beta, eps, XH, stats):
+    _check(lib().pk_ln_cm_fwd(_ptr(PT), C, n, ld, _ptr(gamma), _ptr(beta), eps, _ptr(XH), _ptr(stats), _stream()), "pk_ln_cm_fwd")
+
+
+def ln_cm_bwd(dT16, ld16t, dR16, ld16r, XH, ld, C, n, gamma, stats, eps, scale, dgamma, dbeta, dbias=None):
+    _check(lib().pk_ln_cm_bwd(_ptr(dT16), ld16t, _ptr(dR16), ld16r, _ptr(XH), ld, C, n, _ptr(gamma), _ptr(stats), eps,
+                              _ptr(scale), _ptr(dgamma), _ptr(dbeta), _ptr(dbias), _stream()), "pk_ln_cm_bwd", 2)
+
+
+def row_stats(PT, C, n, ld, stats):
+    _check(lib().pk_row_stats(_ptr(PT), C, n, ld, _ptr(stats), _stream()), "pk_row_stats")

@@ -34,7 +34,7 @@ class FlatTrainer:
     def __init__(self, modules: Iterable[torch.nn.Module], opt: str = "rmsprop", lr: float = 0.0004,
                  alpha: float = 0.95, eps: float = 1e-8, betas=(0.9, 0.999), weight_decay: float = 0.0,
                  momentum: float = 0.0, centered: bool = False, nesterov: bool = False, dampening: float = 0.0,
-                 amsgrad: bool = False):
+                 amsgrad: bool = False, direct_grad: bool = True):
         if opt not in ("rmsprop", "sgd", "adam"):
             raise NotImplementedError(f"FlatTrainer: optimizer {opt!r} (reference offers sgd / adam / rmsprop)")
         unsupported = []
@@ -49,7 +49,7 @@ class FlatTrainer:
             raise NotImplementedError(f"FlatTrainer({opt}): option(s) {unsupported} are not implemented by the fused optimizer "
                                       "kernel; refusing instead of silently ignoring them")
         self.modules: List[torch.nn.Module] = list(modules)
-        self.params = [p for m in self.modules for p in m.parameters()]
+        self.params = [p for m in self.modules for p in m.parameters()]   # registration order = optimizer index order
         if not self.params:
             raise RuntimeError("FlatTrainer: no parameters")
         self._require_device(self.params[0])
@@ -60,15 +60,40 @@ class FlatTrainer:
         self.flat_v = torch.zeros(n, device=dev, dtype=torch.float32) if opt in ("rmsprop", "adam") else None
         self.flat_m = torch.zeros(n, device=dev, dtype=torch.float32) if opt == "adam" else None
         self.betas, self.weight_decay, self.steps = betas, weight_decay, 0
-        self.offsets = []
+        # Placement inside the flat buffer: the gate matrices of one recurrent layer go back to back ([wh_i; wz_i],
+        # [uh_i; uz_i], ...) so that the stacked operands the kernels want are zero-copy views and their gradients are
+        # written in place (pk_functions._stacked / DIRECT_GRAD); everything else follows in registration order.  The
+        # optimizer-state indices (self.params order) are not affected.
+        placed, order = set(), []
+        for m in self.modules:
+            for sub in m.modules():
+                gates = getattr(sub, "_GATES", None)
+                if not gates or not hasattr(sub, "lay"):
+                    continue
+                for i in range(len(sub.lay)):
+                    for col in (0, 1):
+                        for pair in gates:
+                            p = getattr(sub, pair[col])[i].weight
+                            if id(p) not in placed:
+                                placed.add(id(p))
+                                order.append(p)
+        order += [p for p in self.params if id(p) not in placed]
+        where = {}
         off = 0
-        for p in self.params:
+        for p in order:
             k = p.numel()
             self.flat_p[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat_p[off:off + k].view_as(p)
             p.grad = self.flat_g[off:off + k].view_as(p)
-            self.offsets.append((off, k))
+            where[id(p)] = (off, k)
             off += k
+        self.offsets = [where[id(p)] for p in self.params]
+        if direct_grad:
+            # one backward per step(): weight gradients are WRITTEN into the flat buffer by the GEMM epilogues instead of
+            # being accumulated by autograd (no AccumulateGrad adds); pass direct_grad=False to accumulate several
+            # backward passes before a step
+            import pk_functions
+            pk_functions.register_direct_grad_buffer(self.flat_g)
         self.n = n
         self.opt, self.lr, self.alpha, self.eps = opt, lr, alpha, eps
         self.used = None  # per parameter: does it ever receive a gradient? (decided at the first step)

@@ -70,10 +70,39 @@ def test_cpu_tensors_are_refused_loudly():
         h(torch.zeros(3, 110))
 
 
-def test_unsupported_options_raise():
-    for name in ("LSTM_cudnn", "GRU_cudnn", "RNN_cudnn"):
-        with pytest.raises(NotImplementedError):
-            getattr(pknn, name)({}, 3)
+CUDNN_OPTS = dict(hidden_size="24", num_layers="2", bias="True", batch_first="True", dropout="0.2", bidirectional="True",
+                  nonlinearity="tanh", use_cuda="False", to_do="train")
+
+
+def test_cudnn_layout_classes_construct_like_the_reference():
+    """LSTM_cudnn / GRU_cudnn / RNN_cudnn (reference :153-297): same sub-module, state_dict keys / shapes / values and
+    generator consumption as the reference constructors (cfg/TIMIT_baselines/TIMIT_LSTM_fmllr_cudnn.cfg drops in);
+    CPU tensors are refused, nn.GRU's different gate algebra is refused instead of silently mis-computed."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    ref = None
+    if os.path.exists(os.path.join(ref_dir, "neural_networks.py")):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("ref_nn_for_cudnn", os.path.join(ref_dir, "neural_networks.py"))
+        ref = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref)
+    for name, attr in (("LSTM_cudnn", "lstm"), ("GRU_cudnn", "gru"), ("RNN_cudnn", "rnn")):
+        torch.manual_seed(5)
+        m = getattr(pknn, name)(dict(CUDNN_OPTS), 10)
+        after = torch.rand(1).item()
+        assert m.out_dim == 48
+        keys = list(m.state_dict().keys())
+        assert keys[0] == f"{attr}.0.weight_ih_l0" and f"{attr}.0.weight_hh_l1_reverse" in keys
+        if ref is not None:
+            torch.manual_seed(5)
+            r = getattr(ref, name)(dict(CUDNN_OPTS), 10)
+            assert torch.rand(1).item() == after, "constructor consumed the generator differently"
+            assert list(r.state_dict().keys()) == keys
+            for k, v in r.state_dict().items():
+                assert torch.equal(v, m.state_dict()[k]), (name, k)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        pknn.LSTM_cudnn(dict(CUDNN_OPTS), 10)(torch.zeros(5, 2, 10))
+    with pytest.raises(NotImplementedError):
+        pknn.GRU_cudnn(dict(CUDNN_OPTS), 10)(torch.zeros(5, 2, 10))
 
 
 def test_abi_library_loads_and_exports_every_declared_symbol():

@@ -416,10 +416,12 @@ def mlp_opts(m):
             "dnn_act": ",".join(m["act"]), "use_cuda": "True", "to_do": "train"}
 
 
-def test_mlp_stack_matches_reference():
-    """BASELINE configs[0] family: MLP with BatchNorm + ReLU + dropout + softmax (neural_networks.py:60-150), SGD."""
+@pytest.mark.parametrize("name", ["mlp_bn_relu", "mlp_ln_tanh"])
+def test_mlp_stack_matches_reference(name):
+    """BASELINE configs[0] family (neural_networks.py:60-150), SGD.  mlp_bn_relu: BatchNorm + ReLU + dropout + softmax;
+    mlp_ln_tanh: the reference's custom LayerNorm (:23-33) alone (tanh) and under BatchNorm (sigmoid, dropout)."""
     pknn = _mods()
-    d = gu.load("mlp_bn_relu")
+    d = gu.load(name)
     m = d["meta"]
     net = pknn.MLP(mlp_opts(m), m["D"])
     net.load_state_dict({k: torch.from_numpy(np.asarray(d["init.mlp." + k])) for k in net.state_dict()})
@@ -438,22 +440,26 @@ def test_mlp_stack_matches_reference():
             assert key not in d
             continue
         g = p.grad.cpu().numpy()
-        if k.startswith("wx.") and k.endswith("bias") and m["bn"][int(k.split(".")[1])]:
-            assert np.abs(g).max() < 1e-6  # bias in front of BatchNorm: zero gradient
+        if k.startswith("wx.") and k.endswith("bias") and m["bn"][int(k.split(".")[1])] and not m["ln"][int(k.split(".")[1])]:
+            assert np.abs(g).max() < 1e-6  # bias directly in front of BatchNorm: zero gradient
         else:
             assert rel_l2(g, d[key]) < 2 * TOL_GRAD, k  # ReLU kinks: L2 metric (see TOL_GRAD_KINK_L2)
     sd = net.state_dict()
     for k in sd:
-        if "running" in k:
+        if "running" in k and ("bnstat.mlp." + k) in d:
             assert gu.relerr(sd[k].cpu().numpy(), d["bnstat.mlp." + k]) < TOL_FWD, k
 
 
 def test_mlp_unsupported_options_raise_on_gpu():
+    """Input normalisation of the MLP (dnn_use_laynorm_inp / dnn_use_batchnorm_inp) is not built: loud, no fallback."""
     pknn = _mods()
     d = gu.load("mlp_ln_tanh")
-    net = pknn.MLP(mlp_opts(d["meta"]), d["meta"]["D"]).cuda()
-    with pytest.raises(NotImplementedError):
-        net(torch.from_numpy(d["x"]).cuda())
+    for opt in ("dnn_use_laynorm_inp", "dnn_use_batchnorm_inp"):
+        o = mlp_opts(d["meta"])
+        o[opt] = "True"
+        net = pknn.MLP(o, d["meta"]["D"]).cuda()
+        with pytest.raises(NotImplementedError):
+            net(torch.from_numpy(d["x"]).cuda())
 
 
 def conv_opts(m):
