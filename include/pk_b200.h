@@ -48,16 +48,7 @@ extern "C" {
 #define PK_CELL_MGRU 3
 #define PK_CELL_LSTM 4
 #define PK_CELL_MASK 0xff
-/* optional tuning flags OR-ed into `cell`: CTAs per cluster of the persistent kernel
- * (default: chosen from H) */
-#define PK_REC_CLUSTER(n) ((n) << 8) /* n in {8, 9, 10, 12, 16}; bits 8..12 */
-#define PK_REC_CLUSTER8 PK_REC_CLUSTER(8)
-#define PK_REC_CLUSTER16 PK_REC_CLUSTER(16)
-/* step synchronisation: default = st.async + mbarrier; this flag selects the
- * barrier.cluster variant (kept for A/B timing) */
-#define PK_REC_SYNC_BARRIER 0x2000
-/* use the non-warp-specialised kernels (A/B timing; they also write the fp32 GT buffer) */
-#define PK_REC_LEGACY 0x4000
+/* optional flags OR-ed into `cell` */
 /* kernel choice for the persistent liGRU / RNN recurrence.  Default (no flag): the faster of the two on this
  * part as measured (profiles/r2_selftest_tc_vs_ws.log) — the warp-specialised register-stationary mma.sync
  * kernels for H <= 560, the tcgen05 kernels (weights stationary in tensor memory) for 560 < H <= 1024. */
@@ -67,8 +58,8 @@ extern "C" {
 #define PK_REC_DBG_NOSTORE 0x10000
 #define PK_REC_DBG_NOLOAD 0x20000
 #define PK_REC_GROUPS(n) ((n) << 19) /* tcgen05 kernels: n in 1..3 arrival-group barriers per step (default 1) */
-#define PK_REC_DBG_NOPROXYFENCE 0x40000
-#define PK_REC_DBG_BLOCKINGWAIT 0x200000 /* tcgen05 kernels: MMA issuer suspends in try_wait instead of spinning on test_wait */ /* tcgen05 kernels: no fence.proxy.async between chunk arrival and its MMAs */
+#define PK_REC_DBG_NOPROXYFENCE 0x40000 /* tcgen05 kernels: no fence.proxy.async between chunk arrival and its MMAs */
+#define PK_REC_DBG_BLOCKINGWAIT 0x200000 /* tcgen05 kernels: MMA issuer suspends in try_wait instead of spinning on test_wait */
 
 const char* pk_last_error(void);
 int pk_version(void);

@@ -27,11 +27,11 @@ struct RecFlags {
 };
 RecFlags parse_cell(int cell) {
   RecFlags f;
-  f.cluster = (cell >> 8) & 0x1f;  // PK_REC_CLUSTER(n)
-  f.sync = (cell & PK_REC_SYNC_BARRIER) ? 0 : -1;
+  f.cluster = 0;
+  f.sync = -1;
   f.dbg = ((cell & PK_REC_DBG_NOSTORE) ? 1 : 0) | ((cell & PK_REC_DBG_NOLOAD) ? 2 : 0) | ((cell & PK_REC_DBG_NOPROXYFENCE) ? 4 : 0) |
           ((cell & PK_REC_DBG_BLOCKINGWAIT) ? 8 : 0);
-  f.legacy = (cell & PK_REC_LEGACY) ? 1 : ((cell & PK_REC_WS) ? 2 : ((cell & PK_REC_TC) ? 3 : 0));
+  f.legacy = (cell & PK_REC_WS) ? 2 : ((cell & PK_REC_TC) ? 3 : 0);
   f.groups = (cell >> 19) & 3;
   f.cell = cell & PK_CELL_MASK;
   return f;
@@ -125,7 +125,6 @@ int pk_rnn_layer_fwd(int cell, int T, int B, int H, int ndir, int act, const flo
                      void* HT16, void* HP16, float* ZT, float* HCT, int64_t ldt, void* stream) {
   const RecFlags f = parse_cell(cell);
   PK_REQUIRE(f.cell == PK_CELL_LIGRU || f.cell == PK_CELL_RNN, "pk_rnn_layer_fwd: cell kind %d not implemented", f.cell);
-  PK_REQUIRE(f.cell != PK_CELL_RNN || (f.legacy != 1 && f.cluster == 0 && f.sync != 0), "pk_rnn_layer_fwd: the RNN cell needs the default kernels");
   PK_REQUIRE(PT && scale && shift && U, "pk_rnn_layer_fwd: null input");
   PK_REQUIRE(act >= PK_ACT_RELU && act <= PK_ACT_LINEAR, "pk_rnn_layer_fwd: bad activation %d", act);
   RecFwdArgs a;

@@ -1001,4 +1001,37 @@ int ligru_bwd_tc(const RecBwdArgs& a_in, cudaStream_t stream) {
   return 0;
 }
 
+// ---- dispatch of the persistent liGRU / RNN recurrence (C ABI: pk_rnn_layer_fwd / pk_rnn_layer_bwd)
+// mode 0 = auto: the faster kernel for this hidden size as measured on B200 (profiles/r2_selftest_tc_vs_ws.log):
+// register-stationary mma.sync (pk_rnn_ws.cu) up to H = 560, tcgen05 with TMEM-stationary weights beyond.
+namespace {
+int rec_mode(int requested, int H) {
+  static const int env_mode = [] { const char* e = getenv("PK_REC_MODE"); return e ? atoi(e) : 0; }();
+  int mode = requested ? requested : env_mode;
+  if (mode == 0) mode = H <= 560 ? 2 : 3;
+  return mode;
+}
+}  // namespace
+
+int ligru_fwd(const RecFwdArgs& a, cudaStream_t stream) {
+  PK_REQUIRE(a.T > 0 && a.B > 0 && a.H > 0, "ligru_fwd: empty problem");
+  PK_REQUIRE(a.ndir == 1 || a.ndir == 2, "ligru_fwd: ndir must be 1 or 2");
+  const int mode = rec_mode(a.legacy, a.H);
+  PK_REQUIRE(mode == 2 || mode == 3, "ligru_fwd: kernel variant %d was removed (PK_REC_WS / PK_REC_TC select the two that exist)", mode);
+  if (mode == 3) return ligru_fwd_tc(a, stream);
+  PK_REQUIRE(a.H <= 560, "ligru_fwd: hidden size %d > 560 not supported by the register-stationary kernels", a.H);
+  return ligru_fwd_ws(a, stream);
+}
+
+int ligru_bwd(const RecBwdArgs& a, cudaStream_t stream) {
+  PK_REQUIRE(a.T > 0 && a.B > 0 && a.H > 0, "ligru_bwd: empty problem");
+  PK_REQUIRE(a.ndir == 1 || a.ndir == 2, "ligru_bwd: ndir must be 1 or 2");
+  PK_REQUIRE(a.GT16 != nullptr, "ligru_bwd: the kernels write GT16 (required)");
+  const int mode = rec_mode(a.legacy, a.H);
+  PK_REQUIRE(mode == 2 || mode == 3, "ligru_bwd: kernel variant %d was removed (PK_REC_WS / PK_REC_TC select the two that exist)", mode);
+  if (mode == 3) return ligru_bwd_tc(a, stream);
+  PK_REQUIRE(a.H <= 560, "ligru_bwd: hidden size %d > 560 not supported by the register-stationary kernels", a.H);
+  return ligru_bwd_ws(a, stream);
+}
+
 }  // namespace pk

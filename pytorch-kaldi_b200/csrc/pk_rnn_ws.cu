@@ -1,8 +1,8 @@
-// pk_rnn_ws.cu — warp-specialised persistent liGRU kernels (round-1 default).
+// pk_rnn_ws.cu — warp-specialised persistent liGRU kernels on mma.sync (default for H <= 560).
 //
-// Same decomposition as pk_rnn.cu (cluster of CL CTAs x 8 batch rows, recurrent weights stationary in
-// registers as mma.sync fragments, asynchronous DSMEM exchange completed on the receiver's mbarrier), with
-// two changes driven by the ncu profiles under profiles/:
+// Cluster of CL CTAs x 8 batch rows, recurrent weights stationary in registers as mma.sync fragments, asynchronous
+// DSMEM exchange completed on the receiver's mbarrier (the non-specialised first version, pk_rnn.cu, was removed in
+// round 2), with the refinements driven by the ncu profiles under profiles/:
 //
 //  1. WARP SPECIALISATION.  The per-step global-memory work no longer runs on the warps that sit on the
 //     serial critical path:

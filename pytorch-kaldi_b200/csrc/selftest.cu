@@ -302,9 +302,9 @@ static void test_ligru(int T, int B, int H, int ndir, int act) {
   dPT.up(c.PT); dsc.up(c.scale); dsh.up(c.shift); dU.up(c.U); dmask.up(c.mask);
   const long long ldy = (long long)ndir * H + 2;
   const long long ldy16 = ((long long)ndir * H + 7) / 8 * 8;
-  const char* names[] = {"tc", "tc-3groups", "ws", "8", "8b", "10"};
-  const int vflags[] = {PK_REC_TC, PK_REC_TC | PK_REC_GROUPS(3), PK_REC_WS, PK_REC_CLUSTER(8), PK_REC_CLUSTER(8) | PK_REC_SYNC_BARRIER, PK_REC_CLUSTER(10)};
-  const int npass = H > 560 ? 2 : (H > 512 ? 6 : 5);
+  const char* names[] = {"tc", "tc-3groups", "ws"};
+  const int vflags[] = {PK_REC_TC, PK_REC_TC | PK_REC_GROUPS(3), PK_REC_WS};
+  const int npass = H > 560 ? 2 : 3;
   for (int pass = 0; pass < npass; ++pass) {
     const char* cl = names[pass];
     const int vflag = vflags[pass];
@@ -361,7 +361,7 @@ static void test_ligru(int T, int B, int H, int ndir, int act) {
     for (auto x : GT) gmax = std::max(gmax, (double)std::fabs(x));
     for (size_t i = 0; i < GT.size(); ++i)
       e16 = std::max(e16, std::fabs((double)__half2float(gGT16[i]) / s - GT[i]) / std::max(gmax, 1e-30));
-    const bool ws = pass <= 2;  // the tcgen05 / warp-specialised kernels write GT16 only
+    const bool ws = true;  // the kernels write GT16 only
     snprintf(name, sizeof(name), "ligru_bwd cl%s T%d B%d H%d nd%d act%d", cl, T, B, H, ndir, act);
     report(name, std::max(ws ? 0.0 : maxrel(gGT, GT, 1e-30), e16), 3e-3);
   }
@@ -587,10 +587,7 @@ static void bench_all() {
                     {"tc blocking wait        ", PK_REC_TC | PK_REC_DBG_BLOCKINGWAIT},
                     {"tc nostore              ", PK_REC_TC | PK_REC_DBG_NOSTORE},
                     {"tc noload/nostore       ", PK_REC_TC | PK_REC_DBG_NOSTORE | PK_REC_DBG_NOLOAD},
-                    {"ws mma.sync (round 1)   ", PK_REC_WS},
-                    {"legacy cl10 st.async    ", PK_REC_CLUSTER(10)},
-                    {"legacy cl8  st.async    ", PK_REC_CLUSTER(8)},
-                    {"legacy cl8  barrier     ", PK_REC_CLUSTER(8) | PK_REC_SYNC_BARRIER}};
+                    {"ws mma.sync             ", PK_REC_WS}};
     for (const V& v : vs) {
       const int flag = v.flags;
       int rc = 0;

@@ -320,8 +320,6 @@ class LiGRUStackFn(torch.autograd.Function):
                 pk.rnn_step_bwd(cfg.cell, T, B, H, ndir, S["act"], dYT, S["HT"], S["SV"], ldt, S["U"], S["mask"],
                                 S["mask_scalar"], sc, GT16, wsp)
             else:
-                if cfg.cell_flags & pk.REC_LEGACY:
-                    GT = torch.empty(ndir, CG, ldt, **f32)
                 pk.rnn_layer_bwd(cfg.cell | cfg.cell_flags, T, B, H, ndir, S["act"], dYT, S["HT"], S["SV"][0],
                                  S["SV"][1], ldt, S["U"], S["mask"], S["mask_scalar"], sc, GT, GT16)
             inv = sc[1:2]

@@ -55,5 +55,8 @@ def test_cudnn_layout_matches_torch_rnn(name, attr, nonlin):
     # the gradient w.r.t. the input flows too (a module in front of the RNN trains through it)
     xr = x.clone().requires_grad_(True)
     (oracle(xr)[0] * wgt).sum().backward()
-    tol = 0.05 if nonlin == "relu" else 5e-3
-    assert gu.relerr(xg.grad.cpu().numpy(), xr.grad.numpy()) < tol
+    if nonlin == "relu":  # kinks: relative L2 (tests/test_gpu_parity.py TOL_GRAD_KINK_L2)
+        got, ref = xg.grad.cpu().numpy(), xr.grad.numpy()
+        assert float(np.linalg.norm(got - ref) / np.linalg.norm(ref)) < 0.05
+    else:
+        assert gu.relerr(xg.grad.cpu().numpy(), xr.grad.numpy()) < 5e-3

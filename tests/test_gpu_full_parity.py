@@ -28,7 +28,7 @@ TOL = 1e-3  # north star: per-frame senone log-posteriors and the training loss 
 # Gradient bounds vs the fp32 reference at FULL size (relative L2 over 8192 sampled entries per tensor).  fp16
 # tensor-core operands + the ReLU kinks of a 500-step recurrence set these; they are measured
 # values with ~2x head-room, not wishes (profiles/r2_full_parity.txt keeps the per-tensor numbers).
-GRAD_L2 = {"full_ligru5x550": 0.05, "full_lstm4x550": 0.02}
+GRAD_L2 = {"full_ligru5x550": 0.06, "full_lstm4x550": 0.005}   # measured: 3.4e-2 (ReLU kinks, layer 0) / 1.9e-3 (tanh)
 # Hidden-state bound (max abs error / max abs value, last layer): liGRU states are convex combinations (bounded error);
 # the LSTM cell accumulates c over 500 steps before tanh, measured 3.8e-3 at this size
 H_TOL = {"full_ligru5x550": 2e-3, "full_lstm4x550": 6e-3, "full_ligru5x1024": 2e-3}

@@ -133,7 +133,10 @@ def test_unmodified_run_nn_drives_the_dropin(tmp_path):
         for k in r:
             assert r[k].shape == g[k].shape, k
             if "running" in k:
-                assert torch.allclose(r[k], g[k].float(), rtol=2e-3, atol=1e-5), k
+                # error relative to the statistic's scale (entries near zero carry no relative meaning); after the first
+                # optimizer step the two runs no longer hold identical weights (sign-SGD-like RMSprop steps, see below),
+                # so the later minibatches' statistics may differ at the 1e-2 level
+                assert float((r[k] - g[k].float()).abs().max()) <= 1e-2 * max(float(r[k].abs().max()), 1e-3), k
         # parameters after 4 RMSprop steps (each step moves an entry by ~lr/sqrt(1-alpha) = 1.8e-3 in the direction
         # of its gradient's sign): entries stay within a few steps of the reference everywhere and on the same side
         # for the overwhelming majority

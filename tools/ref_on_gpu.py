@@ -94,6 +94,12 @@ def main():
     head = ref.MLP(bench.head_opts(S, "True"), net.out_dim)
     row("reference LSTM_cudnn (nn.LSTM 4x550 bidir, cuDNN fp32, no BN, per-direction weights) + head on B200 — "
         "config 3's speed bar, not a parity oracle", [net, head], 3, 10, 0.0016)
+    # the same with PyTorch's DEFAULT flags (torch.backends.cudnn.allow_tf32 = True: what the unmodified reference runs)
+    torch.backends.cudnn.allow_tf32 = True
+    net = ref.LSTM_cudnn(copts, F)
+    head = ref.MLP(bench.head_opts(S, "True"), net.out_dim)
+    row("reference LSTM_cudnn as above with PyTorch's default torch.backends.cudnn.allow_tf32=True (TF32 recurrent GEMMs)",
+        [net, head], 3, 10, 0.0016)
     print(json.dumps(out, indent=1))
 
 
