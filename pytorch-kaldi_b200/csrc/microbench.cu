@@ -556,6 +556,27 @@ int main() {
   run_exchange(10, 896, 0, 8);
   run_exchange(5, 2048, 0, 8);
   run_exchange(8, 1024, 0, 16);
+  run_exchange(16, 1024, 0, 8);
+  run_exchange(16, 1024, 0, 4);
+  run_exchange(16, 1024, 0, 1);
+  run_exchange(12, 1024, 0, 8);
+  for (int cl : {9, 10, 12, 16}) {  // how many clusters of this size are co-resident?
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(8 * cl, 1, 1);
+    cfg.blockDim = dim3(256, 1, 1);
+    cfg.dynamicSmemBytes = 120 * 1024;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = -1;
+    CK(cudaFuncSetAttribute(exchange_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, exchange_kernel, &cfg);
+    printf("cudaOccupancyMaxActiveClusters(cluster %2d, 256 threads, 120 KB smem) = %d (%s)\n", cl, n, cudaGetErrorString(e));
+  }
   printf("--- A2: exchange knobs (1 KB per source, 9 CTAs) ---\n");
   for (int split : {0, 1})
     for (int stagger : {0, 1})

@@ -758,6 +758,8 @@ int ligru_fwd_ws(const RecFwdArgs& a_in, cudaStream_t stream) {
   if (H <= 256) { PK_FWD_WS(16, 4, 8); }
   if (H <= 384) { PK_FWD_WS(24, 6, 8); }
   if (H <= 512) { PK_FWD_WS(32, 7, 10); }
+  static const int wide = [] { const char* e = getenv("PK_WS_CL14"); return e ? atoi(e) : 0; }();
+  if (wide) { PK_FWD_WS(35, 5, 14); }   // experiment: 14 CTAs x 40 units (5 compute warps): shorter HMMA chain per SM
   PK_FWD_WS(35, 7, 10);
 }
 int ligru_bwd_ws(const RecBwdArgs& a_in, cudaStream_t stream) {
@@ -768,6 +770,8 @@ int ligru_bwd_ws(const RecBwdArgs& a_in, cudaStream_t stream) {
   if (H <= 256) { PK_BWD_WS(16, 4, 8); }
   if (H <= 384) { PK_BWD_WS(24, 6, 8); }
   if (H <= 512) { PK_BWD_WS(32, 7, 10); }
+  static const int wide = [] { const char* e = getenv("PK_WS_CL14"); return e ? atoi(e) : 0; }();
+  if (wide) { PK_BWD_WS(35, 5, 14); }
   PK_BWD_WS(35, 7, 10);
 }
 

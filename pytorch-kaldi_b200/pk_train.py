@@ -229,6 +229,35 @@ class FlatTrainer:
         self.steps = steps
 
 
+class GraphedStep:
+    """A whole training step (forward_model -> zero_grad -> backward -> optimizer) captured ONCE into a CUDA graph and
+    replayed per minibatch: for launch-bound recipes (the MLP of cfg/TIMIT_baselines/TIMIT_MLP_mfcc_basic.cfg trains on
+    128-frame minibatches: ~45 kernels of a few microseconds each) the host launch cost disappears.  `step_fn(inp)`
+    must be free of host synchronisation (device-side dropout masks: `fast_dropout` / nn.Dropout-style device RNG) and
+    return device tensors; inputs are copied into a static buffer, outputs are read from static tensors.  Shapes are
+    fixed at capture (one graph per minibatch shape)."""
+
+    def __init__(self, step_fn, example_inp: torch.Tensor, warmup: int = 3):
+        if not example_inp.is_cuda:
+            raise RuntimeError("GraphedStep needs CUDA tensors (no CPU path)")
+        self.static_inp = example_inp.clone()
+        s = torch.cuda.Stream(device=example_inp.device)
+        s.wait_stream(torch.cuda.current_stream(example_inp.device))
+        with torch.cuda.stream(s):   # warm-up outside the capture: one-time attribute set-up, allocator pools
+            for _ in range(warmup):
+                step_fn(self.static_inp)
+        torch.cuda.current_stream(example_inp.device).wait_stream(s)
+        torch.cuda.synchronize(example_inp.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_out = step_fn(self.static_inp)
+
+    def __call__(self, inp: torch.Tensor):
+        self.static_inp.copy_(inp, non_blocking=True)
+        self.graph.replay()
+        return self.static_out
+
+
 def chunk_step(net, head, trainer: FlatTrainer, inp: torch.Tensor, n_fea: int, fused_head: bool = True):
     """One minibatch as core.run_nn + utils.forward_model run it: `inp` is the reference's chunk
     layout [T, B, n_fea + 1] with the label in the last column stored as float (data_io.py:272,
@@ -353,10 +382,61 @@ def _read_key(fd):
     return key or None
 
 
+def open_rx(rxspec, mode="rb"):
+    """Kaldi rxfilename / rspecifier -> (binary stream, close?) the way data_io.open_or_fd does (data_io.py:685-718):
+    optional `ark:` / `scp:` prefix with modifiers, optional `:offset` suffix, `cmd |` input pipes (run through the
+    shell, as the reference does — e.g. `copy-feats ... |` when the Kaldi binaries are installed), `.gz` files, plain
+    files; an already opened stream is passed through."""
+    import gzip
+    import re
+    import subprocess
+    if not isinstance(rxspec, str):
+        return rxspec, False
+    f, offset = rxspec, None
+    if re.search(r"^(ark|scp)(,scp|,b|,t|,n?f|,n?p|,b?o|,n?s|,n?cs)*:", f):
+        f = f.split(":", 1)[1]
+    if re.search(r":[0-9]+$", f):
+        f, off = f.rsplit(":", 1)
+        offset = int(off)
+    f = f.strip()
+    if f.endswith("|"):
+        proc = subprocess.Popen(f[:-1], shell=True, stdout=subprocess.PIPE)
+        fd = proc.stdout
+    elif f.split(".")[-1] == "gz":
+        fd = gzip.open(f, mode)
+    else:
+        fd = open(f, mode)
+    if offset is not None:
+        fd.seek(offset)
+    return fd, True
+
+
+def _read_ascii_matrix(fd):
+    """Text-mode Kaldi matrix after the opening " [" (data_io.py:1133-1147): rows of numbers, the last one ends in "]"."""
+    rows = []
+    while True:
+        line = fd.readline().decode()
+        if len(line) == 0:
+            raise ValueError("unexpected end of file inside an ascii matrix")
+        arr = line.strip().split()
+        if not arr:
+            continue
+        if arr[-1] != "]":
+            rows.append(np.array(arr, dtype="float32"))
+        else:
+            rows.append(np.array(arr[:-1], dtype="float32"))
+            return np.vstack(rows)
+
+
 def _read_binary_matrix(fd, device=None):
-    """One binary Kaldi matrix at the stream position (after the key): "\0B" + "FM " / "DM " / "CM " (data_io.py:1087-1196)."""
-    if fd.read(2) != b"\0B":
-        raise ValueError("only binary Kaldi matrices are supported")
+    """One Kaldi matrix at the stream position (after the key): "\0B" + "FM " / "DM " / "CM " (data_io.py:1087-1196), or
+    the text form " [ ... ]" (data_io.py:1133-1147)."""
+    flag = fd.read(2)
+    if flag == b" [":
+        mat = _read_ascii_matrix(fd)
+        return torch.from_numpy(mat).to(device) if device is not None else mat
+    if flag != b"\0B":
+        raise ValueError("neither a binary nor a text Kaldi matrix")
     header = fd.read(3).decode()
     if header == "CM ":
         gmin, grange, rows, cols = np.frombuffer(fd.read(16), dtype="float32,float32,int32,int32", count=1)[0]
@@ -398,14 +478,41 @@ def read_mat_scp(scp_path, device=None):
             if not line.strip():
                 continue
             key, rx = line.strip().split(None, 1)
-            offset = None
-            if ":" in rx and rx.rsplit(":", 1)[1].isdigit():
-                rx, off = rx.rsplit(":", 1)
-                offset = int(off)
-            with open(rx, "rb") as fd:
-                if offset is not None:
-                    fd.seek(offset)
+            fd, close = open_rx(rx)   # plain / gzipped file, `cmd |` pipe, optional :offset
+            try:
                 yield key, _read_binary_matrix(fd, device)
+            finally:
+                if close:
+                    fd.close()
+
+
+def read_vec_flt(fd):
+    """One Kaldi float vector at the stream position (data_io.py:922-990): binary "\0B" + "FV " / "DV " + \4 + int32
+    length + payload, or the text form "[ a b c ]"."""
+    flag = fd.read(2)
+    if flag == b"\0B":
+        header = fd.read(3).decode()
+        if header not in ("FV ", "DV "):
+            raise ValueError(f"The header contained '{header}'")
+        dt = np.float32 if header == "FV " else np.float64
+        if fd.read(1) != b"\x04":
+            raise ValueError("bad float-vector header")
+        n = int(np.frombuffer(fd.read(4), dtype="int32", count=1)[0])
+        if n == 0:
+            return np.array([], dtype="float32")
+        return np.frombuffer(fd.read(n * np.dtype(dt).itemsize), dtype=dt).copy()
+    arr = (flag + fd.readline()).decode().strip().split()
+    arr = [a for a in arr if a not in ("[", "]")]
+    return np.array(arr, dtype=float)
+
+
+def read_vec_flt_ark(fd):
+    """Generator of (key, float vector) over a Kaldi float-vector archive (data_io.py:901-920), binary or text."""
+    while True:
+        key = _read_key(fd)
+        if key is None:
+            return
+        yield key, read_vec_flt(fd)
 
 
 def read_vec_int_ark(fd):

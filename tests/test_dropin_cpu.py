@@ -6,8 +6,10 @@ import ctypes
 import hashlib
 import json
 import os
+import sys
 import re
 
+import numpy as np
 import pytest
 import torch
 
@@ -230,3 +232,82 @@ def test_c_abi_error_convention_without_gpu():
     with pytest.raises(RuntimeError, match="null operand"):
         pk_native._check(L.pk_gemm_tn(0, 0, 8, 8, None, 8, 0, 0, None, 8, 0, 0, None, 8, None, 0, None, 1.0, None, 0, 1, None,
                                       None), "pk_gemm_tn")
+
+
+def _ref_data_io():
+    """The reference's own data_io.py (baseline/_ref, git-ignored copy made by build()) or None."""
+    p = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.exists(os.path.join(p, "data_io.py")):
+        return None
+    import importlib
+    sys.path.insert(0, p)
+    try:
+        for m in ("data_io", "utils"):
+            sys.modules.pop(m, None)
+        return importlib.import_module("data_io")
+    finally:
+        sys.path.remove(p)
+        sys.modules.pop("utils", None)
+
+
+def test_text_archives_float_vectors_and_rxspecs_match_the_reference_readers(tmp_path):
+    """SURVEY 8f-3 leftovers: ascii matrices (data_io.py:1133-1147), float vectors binary / ascii (:879-990), gzipped files,
+    `cmd |` input pipes and :offset suffixes (open_or_fd, :685-718) — against the reference's own readers when available."""
+    import gzip
+    import pk_train
+    rng = np.random.default_rng(3)
+    mats = {"utt_a": rng.standard_normal((5, 7)).astype(np.float32), "utt_b": rng.standard_normal((1, 3)).astype(np.float32)}
+    txt = tmp_path / "feats.txt.ark"
+    with open(txt, "wb") as f:
+        for k, m in mats.items():
+            f.write((k + "  [\n").encode())
+            for i, r in enumerate(m):
+                f.write(("  " + " ".join(repr(float(v)) for v in r) + (" ]\n" if i == len(m) - 1 else "\n")).encode())
+    got = dict(pk_train.read_mat_ark(open(txt, "rb")))
+    assert list(got) == list(mats)
+    for k in mats:
+        assert np.array_equal(got[k], mats[k])
+    vecs = {"v1": rng.standard_normal(6).astype(np.float32), "v2": np.array([], dtype=np.float32), "v3": rng.standard_normal(4)}
+    vark = tmp_path / "vec.ark"
+    with open(vark, "wb") as f:
+        for k, v in vecs.items():
+            f.write((k + " ").encode() + b"\0B" + (b"FV " if v.dtype == np.float32 else b"DV ") + b"\x04" +
+                    np.int32(v.size).tobytes() + v.tobytes())
+        f.write(b"v4 [ 1.25 -2 3e-3 ]\n")
+    gv = dict(pk_train.read_vec_flt_ark(open(vark, "rb")))
+    for k, v in vecs.items():
+        assert np.array_equal(gv[k], v), k
+    assert np.allclose(gv["v4"], [1.25, -2.0, 3e-3])
+    # binary matrix archive through a gzip file, an input pipe and an scp with byte offsets
+    bark = tmp_path / "feats.ark"
+    offs = {}
+    with open(bark, "wb") as f:
+        for k, m in mats.items():
+            f.write((k + " ").encode())
+            offs[k] = f.tell()
+            f.write(b"\0BFM " + b"\x04" + np.int32(m.shape[0]).tobytes() + b"\x04" + np.int32(m.shape[1]).tobytes() + m.tobytes())
+    gz = tmp_path / "feats.ark.gz"
+    with gzip.open(gz, "wb") as f:
+        f.write(open(bark, "rb").read())
+    for spec in (f"ark:{gz}", f"ark:cat {bark} |"):
+        fd, close = pk_train.open_rx(spec)
+        got = dict(pk_train.read_mat_ark(fd))
+        if close:
+            fd.close()
+        assert all(np.array_equal(got[k], mats[k]) for k in mats), spec
+    scp = tmp_path / "feats.scp"
+    with open(scp, "w") as f:
+        for k in mats:
+            f.write(f"{k} {bark}:{offs[k]}\n")
+    got = dict(pk_train.read_mat_scp(str(scp)))
+    assert all(np.array_equal(got[k], mats[k]) for k in mats)
+    ref = _ref_data_io()
+    if ref is not None:  # the reference's own readers give the same arrays
+        out = str(tmp_path)
+        rm = {k: np.array(v) for k, v in ref.read_mat_ark(str(txt), out)}
+        assert all(np.array_equal(rm[k], mats[k]) for k in mats)
+        rv = {k: np.array(v) for k, v in ref.read_vec_flt_ark(str(vark), out)}
+        for k in gv:
+            assert np.allclose(rv[k], gv[k]), k
+        rs = {k: np.array(v) for k, v in ref.read_mat_scp(str(scp), out)}
+        assert all(np.array_equal(rs[k], mats[k]) for k in mats)
