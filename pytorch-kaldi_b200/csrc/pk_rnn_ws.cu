@@ -749,7 +749,9 @@ void set_debug_clock_buffer(long long* dev_ptr) {
   set_debug_clock_buffer_tc(dev_ptr);
 }
 
-// (k-tiles, 8-unit tiles per CTA, cluster size): CL * 8 * MT >= 16 * KT >= H
+// (k-tiles, 8-unit tiles per CTA, cluster size): CL * 8 * MT >= 16 * KT >= H.  Measured (round 2): a 14-CTA cluster with 5
+// tiles per CTA (shorter HMMA chain per SM) is 1.8x SLOWER (1.89 vs 1.04 us per step) — large clusters lose on the
+// DSMEM exchange / placement, so 10 x 7 tiles stays.
 int ligru_fwd_ws(const RecFwdArgs& a_in, cudaStream_t stream) {
   RecFwdArgs a = a_in;
   a.dbg_clk = g_dbg_clk;
@@ -758,8 +760,6 @@ int ligru_fwd_ws(const RecFwdArgs& a_in, cudaStream_t stream) {
   if (H <= 256) { PK_FWD_WS(16, 4, 8); }
   if (H <= 384) { PK_FWD_WS(24, 6, 8); }
   if (H <= 512) { PK_FWD_WS(32, 7, 10); }
-  static const int wide = [] { const char* e = getenv("PK_WS_CL14"); return e ? atoi(e) : 0; }();
-  if (wide) { PK_FWD_WS(35, 5, 14); }   // experiment: 14 CTAs x 40 units (5 compute warps): shorter HMMA chain per SM
   PK_FWD_WS(35, 7, 10);
 }
 int ligru_bwd_ws(const RecBwdArgs& a_in, cudaStream_t stream) {
@@ -770,8 +770,6 @@ int ligru_bwd_ws(const RecBwdArgs& a_in, cudaStream_t stream) {
   if (H <= 256) { PK_BWD_WS(16, 4, 8); }
   if (H <= 384) { PK_BWD_WS(24, 6, 8); }
   if (H <= 512) { PK_BWD_WS(32, 7, 10); }
-  static const int wide = [] { const char* e = getenv("PK_WS_CL14"); return e ? atoi(e) : 0; }();
-  if (wide) { PK_BWD_WS(35, 5, 14); }
   PK_BWD_WS(35, 7, 10);
 }
 

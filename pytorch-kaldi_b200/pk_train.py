@@ -249,8 +249,10 @@ class GraphedStep:
         torch.cuda.current_stream(example_inp.device).wait_stream(s)
         torch.cuda.synchronize(example_inp.device)
         self.graph = torch.cuda.CUDAGraph()
+        n0 = pk.launch_count
         with torch.cuda.graph(self.graph):
             self.static_out = step_fn(self.static_inp)
+        self.launches_per_replay = pk.launch_count - n0   # library kernels recorded into the graph (one step)
 
     def __call__(self, inp: torch.Tensor):
         self.static_inp.copy_(inp, non_blocking=True)
