@@ -211,38 +211,15 @@ def load_reference_lib():
     return mod
 
 
-_THREADS = {}
-
-
 def pick_threads(c):
-    """Thread count for the CPU arm: every host thread the path can USE.  The reference's per-step GEMMs are small
-    ([64 x 550] x [550 x 1100]): on a many-core host all-cores intra-op threading can be slower than a subset
-    (round 1 measured 64 threads slower than 1), so a two-step probe on a 12-frame sub-chunk picks the fastest of
-    {8, 16, 32, 64, all}; the chosen count is what `cores` reports.  Set regardless of OMP_NUM_THREADS (torchrun
-    exports OMP_NUM_THREADS=1)."""
-    import torch
-    key = c["workload"]
-    if key in _THREADS:
-        return _THREADS[key]
+    """Thread count for the CPU arm.  The reference's per-step GEMMs are small ([64 x 550] x [550 x 1100] inside a Python
+    time loop), so intra-op threading stops paying early: measured on this pool's 128-thread hosts (gpurun_out /
+    profiles/r2_bench_reference.json) 16 threads is the fastest of {8, 16, 32, 64, 128} and 128 threads is 20x SLOWER
+    (8 frames/s vs 182) — the arm therefore uses min(host threads, 16) and reports that as `cores`.  PK_REF_THREADS
+    overrides.  Set regardless of OMP_NUM_THREADS (torchrun exports OMP_NUM_THREADS=1)."""
     ncpu = os.cpu_count() or 1
     forced = os.environ.get("PK_REF_THREADS")
-    if forced:
-        _THREADS[key] = max(1, min(int(forced), ncpu))
-        return _THREADS[key]
-    cands = sorted({t for t in (8, 16, 32, 64, ncpu) if t <= ncpu})
-    best, best_t = cands[-1], float("inf")
-    if len(cands) > 1 and load_reference_lib() is not None:
-        for t in cands:
-            torch.set_num_threads(t)
-            step = _reference_step(c, None if c["kind"] == "mlp" else 12)[0]
-            step()
-            t0 = time.perf_counter()
-            step()
-            dt = time.perf_counter() - t0
-            if dt < best_t:
-                best, best_t = t, dt
-    _THREADS[key] = best
-    return best
+    return max(1, min(int(forced), ncpu)) if forced else min(ncpu, 16)
 
 
 def reference_step_factory(c, Ts=None):
@@ -303,7 +280,7 @@ def _reference_step(c, Ts):
         return float(loss.item()), float(err.item())
 
     desc = (f"the reference's own modules (baseline/_ref/neural_networks.py, torch {torch.__version__} CPU fp32, "
-            f"@THREADS@ of {os.cpu_count()} host threads: fastest of a probe): fwd + NLLLoss + cost_err + backward + {c['opt']}")
+            f"@THREADS@ of {os.cpu_count()} host threads, see pick_threads): fwd + NLLLoss + cost_err + backward + {c['opt']}")
     return step, frames, desc, "reference"
 
 
@@ -386,6 +363,8 @@ def run_reference_arm(args, c, rank):
            "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "last_loss": loss}
     print(json.dumps(out), flush=True)
+    sys.stdout.flush()
+    os._exit(0)   # do not wait for intra-op thread pools / allocator teardown of a 100-second CPU job
 
 
 # ---------------------------------------------------------------------------------------------
