@@ -54,6 +54,10 @@ extern "C" {
  * kernels for H <= 560, the tcgen05 kernels (weights stationary in tensor memory) for 560 < H <= 1024. */
 #define PK_REC_WS 0x8000   /* force the warp-specialised mma.sync kernels (H <= 560) */
 #define PK_REC_TC 0x400000 /* force the tcgen05 kernels (H <= 1024) */
+/* backward mma.sync kernel, formulation of the per-step exchange: all-gather of (da, dpz) blocks, or K-split with a
+ * reduce-scatter of fp16 partial sums (half the DSMEM bytes per step).  Default: the measured-faster one. */
+#define PK_REC_BWD_ALLGATHER 0x800000
+#define PK_REC_BWD_KSPLIT 0x1000000
 /* timing experiments only (results are incomplete): skip the global stores / loads */
 #define PK_REC_DBG_NOSTORE 0x10000
 #define PK_REC_DBG_NOLOAD 0x20000

@@ -30,7 +30,8 @@ RecFlags parse_cell(int cell) {
   f.cluster = 0;
   f.sync = -1;
   f.dbg = ((cell & PK_REC_DBG_NOSTORE) ? 1 : 0) | ((cell & PK_REC_DBG_NOLOAD) ? 2 : 0) | ((cell & PK_REC_DBG_NOPROXYFENCE) ? 4 : 0) |
-          ((cell & PK_REC_DBG_BLOCKINGWAIT) ? 8 : 0);
+          ((cell & PK_REC_DBG_BLOCKINGWAIT) ? 8 : 0) | ((cell & PK_REC_BWD_ALLGATHER) ? 16 : 0) |
+          ((cell & PK_REC_BWD_KSPLIT) ? 32 : 0);
   f.legacy = (cell & PK_REC_WS) ? 2 : ((cell & PK_REC_TC) ? 3 : 0);
   f.groups = (cell >> 19) & 3;
   f.cell = cell & PK_CELL_MASK;

@@ -386,6 +386,106 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_fwd_ws_kernel(const RecFwdA
 // =====================================================================================
 // backward
 // =====================================================================================
+// I/O warps of the backward kernels (128 threads): global --cp.async--> in-ring (RI-1 steps ahead), out-ring --> global.
+template <class S, int UPC>
+__device__ __forceinline__ void bwd_io_warps(S& sm, const RecBwdArgs& a, int cta_ubase, int cl, int lane) {
+  const int H = a.H, B = a.B, T = a.T;
+  const int nrows = a.ndir * B;
+  // ================= I/O warps (128 threads) =================
+  const int tid = threadIdx.x - kComputeWarps * 32;
+  constexpr int NE = (UPC * kRows + NIO - 1) / NIO;
+  int colv[NE], cstep[NE];
+  long long chan[NE];
+#pragma unroll
+  for (int j = 0; j < NE; ++j) {
+    const int e = tid + NIO * j;
+    const int ul = e >> 3, r = e & 7;
+    const int u = cta_ubase + ul;
+    const int rr = cl * kRows + r;
+    const bool ok = (e < UPC * kRows) && (u < H) && (rr < nrows);
+    const int d = (ok && rr >= B) ? 1 : 0;
+    const int b = rr - d * B;
+    colv[j] = ok ? (d ? (T - 1) * B + b : b) : -1;  // column at step index 0
+    cstep[j] = d ? -B : B;
+    chan[j] = static_cast<long long>(d * H + u) * a.ldt;
+  }
+  const long long gate_stride = static_cast<long long>(H) * a.ldt;
+  const long long dir_stride = 2 * gate_stride;
+  const bool do_store = !(a.dbg & 1);
+  const bool do_load = !(a.dbg & 2);
+  const bool vec = (B % 4 == 0) && (a.ldt % 4 == 0);  // see the forward kernel
+  const int vul = tid >> 1, vr0 = (tid & 1) * 4;
+  const int vu = cta_ubase + vul;
+  const int vrr = cl * kRows + vr0;
+  const bool vok = (vul < UPC) && (vu < H) && (vrr < nrows);
+  const int vd = (vok && vrr >= B) ? 1 : 0;
+  const int vb = vrr - vd * B;
+  const int vcstep = vd ? -B : B;
+  const long long vcol0 = vd ? static_cast<long long>(T - 1) * B + vb : vb;
+  const long long vchan = static_cast<long long>(vd * H + vu) * a.ldt;
+
+  auto issue_load = [&](int it) {  // operands of step k = T-1-it -> in-ring slot it % RI
+    const int k = T - 1 - it;
+    const int s = it % RI;
+    if (it >= RI) mbar_wait(&sm.in_empty[s], ((it / RI) - 1) & 1);
+    if (do_load && vec) {
+      if (vok) {
+        const long long idx = vchan + vcol0 + static_cast<long long>(k) * vcstep;
+        cp_async_16(&sm.inr[s][0][vul][vr0], a.dYT + idx);
+        cp_async_16(&sm.inr[s][1][vul][vr0], a.ZT + idx);
+        cp_async_16(&sm.inr[s][2][vul][vr0], a.HCT + idx);
+        if (k > 0) cp_async_16(&sm.inr[s][3][vul][vr0], a.HT + idx - vcstep);
+      }
+    } else if (do_load) {
+#pragma unroll
+      for (int j = 0; j < NE; ++j) {
+        if (colv[j] >= 0) {
+          const int e = tid + NIO * j;
+          const long long idx = chan[j] + colv[j] + static_cast<long long>(k) * cstep[j];
+          cp_async_f32(&sm.inr[s][0][e >> 3][e & 7], a.dYT + idx);
+          cp_async_f32(&sm.inr[s][1][e >> 3][e & 7], a.ZT + idx);
+          cp_async_f32(&sm.inr[s][2][e >> 3][e & 7], a.HCT + idx);
+          if (k > 0) cp_async_f32(&sm.inr[s][3][e >> 3][e & 7], a.HT + idx - cstep[j]);
+        }
+      }
+    }
+    cp_async_arrive_noinc(&sm.in_full[s]);
+  };
+  for (int it = 0; it < RI - 1 && it < T; ++it) issue_load(it);
+  for (int it = 0; it < T; ++it) {
+    if (it + RI - 1 < T) issue_load(it + RI - 1);
+    const int k = T - 1 - it;
+    const int s = it % RO;
+    mbar_wait(&sm.out_full[s], (it / RO) & 1);
+    if (do_store && vec) {
+      if (vok) {
+        const long long idx = vd * dir_stride + static_cast<long long>(vu) * a.ldt + vcol0 +
+                              static_cast<long long>(k) * vcstep;
+        *reinterpret_cast<uint2*>(a.GT16 + idx) = *reinterpret_cast<const uint2*>(&sm.outr[s][0][vul][vr0]);
+        *reinterpret_cast<uint2*>(a.GT16 + idx + gate_stride) =
+            *reinterpret_cast<const uint2*>(&sm.outr[s][1][vul][vr0]);
+      }
+    } else if (do_store) {
+#pragma unroll
+      for (int j = 0; j < NE; ++j) {
+        if (colv[j] >= 0) {
+          const int e = tid + NIO * j;
+          const int ul = e >> 3, r = e & 7;
+          const int u = cta_ubase + ul;
+          const int d = cstep[j] < 0 ? 1 : 0;
+          const long long col = colv[j] + static_cast<long long>(k) * cstep[j];
+          const long long idx = d * dir_stride + static_cast<long long>(u) * a.ldt + col;
+          a.GT16[idx] = sm.outr[s][0][ul][r];
+          a.GT16[idx + gate_stride] = sm.outr[s][1][ul][r];
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.out_empty[s]);
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
 template <int KT, int MT, int CL>
 struct BwdWs {
   static constexpr int MT16 = (MT + 1) / 2;
@@ -606,102 +706,12 @@ __global__ void __launch_bounds__(kThreads, 1) ligru_bwd_ws_kernel(const RecBwdA
     }
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
-    // ================= I/O warps (128 threads) =================
-    const int tid = threadIdx.x - kComputeWarps * 32;
-    constexpr int NE = (UPC * kRows + NIO - 1) / NIO;
-    int colv[NE], cstep[NE];
-    long long chan[NE];
-#pragma unroll
-    for (int j = 0; j < NE; ++j) {
-      const int e = tid + NIO * j;
-      const int ul = e >> 3, r = e & 7;
-      const int u = cta_ubase + ul;
-      const int rr = cl * kRows + r;
-      const bool ok = (e < UPC * kRows) && (u < H) && (rr < nrows);
-      const int d = (ok && rr >= B) ? 1 : 0;
-      const int b = rr - d * B;
-      colv[j] = ok ? (d ? (T - 1) * B + b : b) : -1;  // column at step index 0
-      cstep[j] = d ? -B : B;
-      chan[j] = static_cast<long long>(d * H + u) * a.ldt;
-    }
-    const long long gate_stride = static_cast<long long>(H) * a.ldt;
-    const long long dir_stride = 2 * gate_stride;
-    const bool do_store = !(a.dbg & 1);
-    const bool do_load = !(a.dbg & 2);
-    const bool vec = (B % 4 == 0) && (a.ldt % 4 == 0);  // see the forward kernel
-    const int vul = tid >> 1, vr0 = (tid & 1) * 4;
-    const int vu = cta_ubase + vul;
-    const int vrr = cl * kRows + vr0;
-    const bool vok = (vul < UPC) && (vu < H) && (vrr < nrows);
-    const int vd = (vok && vrr >= B) ? 1 : 0;
-    const int vb = vrr - vd * B;
-    const int vcstep = vd ? -B : B;
-    const long long vcol0 = vd ? static_cast<long long>(T - 1) * B + vb : vb;
-    const long long vchan = static_cast<long long>(vd * H + vu) * a.ldt;
-
-    auto issue_load = [&](int it) {  // operands of step k = T-1-it -> in-ring slot it % RI
-      const int k = T - 1 - it;
-      const int s = it % RI;
-      if (it >= RI) mbar_wait(&sm.in_empty[s], ((it / RI) - 1) & 1);
-      if (do_load && vec) {
-        if (vok) {
-          const long long idx = vchan + vcol0 + static_cast<long long>(k) * vcstep;
-          cp_async_16(&sm.inr[s][0][vul][vr0], a.dYT + idx);
-          cp_async_16(&sm.inr[s][1][vul][vr0], a.ZT + idx);
-          cp_async_16(&sm.inr[s][2][vul][vr0], a.HCT + idx);
-          if (k > 0) cp_async_16(&sm.inr[s][3][vul][vr0], a.HT + idx - vcstep);
-        }
-      } else if (do_load) {
-#pragma unroll
-        for (int j = 0; j < NE; ++j) {
-          if (colv[j] >= 0) {
-            const int e = tid + NIO * j;
-            const long long idx = chan[j] + colv[j] + static_cast<long long>(k) * cstep[j];
-            cp_async_f32(&sm.inr[s][0][e >> 3][e & 7], a.dYT + idx);
-            cp_async_f32(&sm.inr[s][1][e >> 3][e & 7], a.ZT + idx);
-            cp_async_f32(&sm.inr[s][2][e >> 3][e & 7], a.HCT + idx);
-            if (k > 0) cp_async_f32(&sm.inr[s][3][e >> 3][e & 7], a.HT + idx - cstep[j]);
-          }
-        }
-      }
-      cp_async_arrive_noinc(&sm.in_full[s]);
-    };
-    for (int it = 0; it < RI - 1 && it < T; ++it) issue_load(it);
-    for (int it = 0; it < T; ++it) {
-      if (it + RI - 1 < T) issue_load(it + RI - 1);
-      const int k = T - 1 - it;
-      const int s = it % RO;
-      mbar_wait(&sm.out_full[s], (it / RO) & 1);
-      if (do_store && vec) {
-        if (vok) {
-          const long long idx = vd * dir_stride + static_cast<long long>(vu) * a.ldt + vcol0 +
-                                static_cast<long long>(k) * vcstep;
-          *reinterpret_cast<uint2*>(a.GT16 + idx) = *reinterpret_cast<const uint2*>(&sm.outr[s][0][vul][vr0]);
-          *reinterpret_cast<uint2*>(a.GT16 + idx + gate_stride) =
-              *reinterpret_cast<const uint2*>(&sm.outr[s][1][vul][vr0]);
-        }
-      } else if (do_store) {
-#pragma unroll
-        for (int j = 0; j < NE; ++j) {
-          if (colv[j] >= 0) {
-            const int e = tid + NIO * j;
-            const int ul = e >> 3, r = e & 7;
-            const int u = cta_ubase + ul;
-            const int d = cstep[j] < 0 ? 1 : 0;
-            const long long col = colv[j] + static_cast<long long>(k) * cstep[j];
-            const long long idx = d * dir_stride + static_cast<long long>(u) * a.ldt + col;
-            a.GT16[idx] = sm.outr[s][0][ul][r];
-            a.GT16[idx + gate_stride] = sm.outr[s][1][ul][r];
-          }
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.out_empty[s]);
-    }
-    asm volatile("cp.async.wait_all;" ::: "memory");
+    bwd_io_warps<S, UPC>(sm, a, cta_ubase, cl, lane);
   }
   cluster_sync_all();
 }
+
+#include "pk_rnn_ks.inc"
 
 template <typename Args, void (*Kern)(const Args)>
 int launch_ws(const Args& a, int cluster, int nclusters, size_t smem, cudaStream_t stream) {
@@ -740,6 +750,19 @@ int launch_ws(const Args& a, int cluster, int nclusters, size_t smem, cudaStream
 #define PK_FWD_WS(KT, MT, CL) PK_WS_ACT(RecFwdArgs, ligru_fwd_ws_kernel, sizeof(FwdWs<KT, MT, CL>) + 128, KT, MT, CL)
 #define PK_BWD_WS(KT, MT, CL) PK_WS_ACT(RecBwdArgs, ligru_bwd_ws_kernel, sizeof(BwdWs<KT, MT, CL>) + 128, KT, MT, CL)
 
+#define PK_KS_ACT(MT, CL)                                                                                    \
+  {                                                                                                          \
+    constexpr size_t smem = sizeof(BwdKs<MT, CL>) + 128;                                                       \
+    switch (a.act) {                                                                                         \
+      case ACT_RELU: return launch_ws<RecBwdArgs, ligru_bwd_ks_kernel<MT, CL, ACT_RELU>>(a, CL, nclusters, smem, stream); \
+      case ACT_TANH: return launch_ws<RecBwdArgs, ligru_bwd_ks_kernel<MT, CL, ACT_TANH>>(a, CL, nclusters, smem, stream); \
+      case ACT_SIGMOID: return launch_ws<RecBwdArgs, ligru_bwd_ks_kernel<MT, CL, ACT_SIGMOID>>(a, CL, nclusters, smem, stream); \
+      case ACT_LEAKY_RELU: return launch_ws<RecBwdArgs, ligru_bwd_ks_kernel<MT, CL, ACT_LEAKY_RELU>>(a, CL, nclusters, smem, stream); \
+      case ACT_ELU: return launch_ws<RecBwdArgs, ligru_bwd_ks_kernel<MT, CL, ACT_ELU>>(a, CL, nclusters, smem, stream); \
+      default: return launch_ws<RecBwdArgs, ligru_bwd_ks_kernel<MT, CL, ACT_LINEAR>>(a, CL, nclusters, smem, stream); \
+    }                                                                                                        \
+  }
+
 long long* g_dbg_clk = nullptr;
 
 }  // namespace
@@ -767,6 +790,14 @@ int ligru_bwd_ws(const RecBwdArgs& a_in, cudaStream_t stream) {
   a.dbg_clk = g_dbg_clk;
   const int nclusters = (a.ndir * a.B + kRows - 1) / kRows;
   const int H = a.H;
+  // formulation of the exchange: dbg bit 4 forces the all-gather kernel, bit 5 the K-split one; default PK_BWD_KS (env)
+  static const int env_ks = [] { const char* e = getenv("PK_BWD_KS"); return e ? atoi(e) : 0; }();
+  const bool ksplit = (a.dbg & 32) ? true : ((a.dbg & 16) ? false : env_ks != 0);
+  if (ksplit) {
+    if (H <= 256) PK_KS_ACT(4, 8)
+    if (H <= 384) PK_KS_ACT(6, 8)
+    PK_KS_ACT(7, 10)
+  }
   if (H <= 256) { PK_BWD_WS(16, 4, 8); }
   if (H <= 384) { PK_BWD_WS(24, 6, 8); }
   if (H <= 512) { PK_BWD_WS(32, 7, 10); }

@@ -302,9 +302,9 @@ static void test_ligru(int T, int B, int H, int ndir, int act) {
   dPT.up(c.PT); dsc.up(c.scale); dsh.up(c.shift); dU.up(c.U); dmask.up(c.mask);
   const long long ldy = (long long)ndir * H + 2;
   const long long ldy16 = ((long long)ndir * H + 7) / 8 * 8;
-  const char* names[] = {"tc", "tc-3groups", "ws"};
-  const int vflags[] = {PK_REC_TC, PK_REC_TC | PK_REC_GROUPS(3), PK_REC_WS};
-  const int npass = H > 560 ? 2 : 3;
+  const char* names[] = {"tc", "tc-3groups", "ws-allgather", "ws-ksplit"};
+  const int vflags[] = {PK_REC_TC, PK_REC_TC | PK_REC_GROUPS(3), PK_REC_WS | PK_REC_BWD_ALLGATHER, PK_REC_WS | PK_REC_BWD_KSPLIT};
+  const int npass = H > 560 ? 2 : 4;
   for (int pass = 0; pass < npass; ++pass) {
     const char* cl = names[pass];
     const int vflag = vflags[pass];
@@ -587,7 +587,8 @@ static void bench_all() {
                     {"tc blocking wait        ", PK_REC_TC | PK_REC_DBG_BLOCKINGWAIT},
                     {"tc nostore              ", PK_REC_TC | PK_REC_DBG_NOSTORE},
                     {"tc noload/nostore       ", PK_REC_TC | PK_REC_DBG_NOSTORE | PK_REC_DBG_NOLOAD},
-                    {"ws mma.sync             ", PK_REC_WS}};
+                    {"ws mma.sync all-gather  ", PK_REC_WS | PK_REC_BWD_ALLGATHER},
+                    {"ws mma.sync bwd K-split ", PK_REC_WS | PK_REC_BWD_KSPLIT}};
     for (const V& v : vs) {
       const int flag = v.flags;
       int rc = 0;
@@ -652,6 +653,15 @@ static void bench_all() {
       c = dclk.down();
       printf("bwd phases (cycles/step): pointwise+stage %.0f | push %.0f | rings(shadow) %.0f | wait_acc %.0f | ld+xchg+carry %.0f | - %.0f\n",
              c[0] / (double)T, c[1] / (double)T, c[2] / (double)T, c[3] / (double)T, c[4] / (double)T, c[5] / (double)T);
+      for (int v = 0; v < 2; ++v) {
+        pk_rnn_layer_bwd(PK_CELL_LIGRU | PK_REC_WS | (v ? PK_REC_BWD_KSPLIT : PK_REC_BWD_ALLGATHER), T, B, H, ndir, PK_ACT_RELU, ddY.p,
+                         dHT.p, dZT.p, dHCT.p, ld, dU.p, dmask.p, 1.f, dgs.p, dGT.p, dGT16.p, nullptr);
+        CK(cudaDeviceSynchronize());
+        c = dclk.down();
+        printf(v ? "bwd ws K-split phases (cycles/step): pointwise+local stage+bar %.0f | HMMA+stage+push %.0f | rings(shadow) %.0f | wait %.0f | reduce %.0f\n"
+                 : "bwd ws all-gather phases (cycles/step): pointwise %.0f | stage+push %.0f | rings(shadow) %.0f | wait %.0f | HMMA+pair exchange %.0f\n",
+               c[0] / (double)T, c[1] / (double)T, c[2] / (double)T, c[3] / (double)T, c[4] / (double)T);
+      }
       pk_debug_set_clock_buffer(nullptr);
     }
   }

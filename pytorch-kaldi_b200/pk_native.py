@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libpk_b200.so")
 F16, TF32 = 0, 2
 ACT_IDS = {"relu": 0, "tanh": 1, "sigmoid": 2, "leaky_relu": 3, "elu": 4, "linear": 5}
 CELL_LIGRU, CELL_RNN, CELL_GRU, CELL_MGRU, CELL_LSTM = 0, 1, 2, 3, 4
+REC_BWD_ALLGATHER, REC_BWD_KSPLIT = 0x800000, 0x1000000  # backward mma.sync kernel: exchange formulation
 REC_WS, REC_TC = 0x8000, 0x400000  # force the mma.sync / tcgen05 persistent kernels (default: faster one for this H)
 
 _c_int, _c_i64, _c_f, _c_p = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
