@@ -790,8 +790,9 @@ int ligru_bwd_ws(const RecBwdArgs& a_in, cudaStream_t stream) {
   a.dbg_clk = g_dbg_clk;
   const int nclusters = (a.ndir * a.B + kRows - 1) / kRows;
   const int H = a.H;
-  // formulation of the exchange: dbg bit 4 forces the all-gather kernel, bit 5 the K-split one; default PK_BWD_KS (env)
-  static const int env_ks = [] { const char* e = getenv("PK_BWD_KS"); return e ? atoi(e) : 0; }();
+  // formulation of the exchange: dbg bit 4 forces the all-gather kernel, bit 5 the K-split one; default K-split
+  // (1.20 vs 1.33 us per step at H = 550, profiles/r2_selftest_ksplit.log), PK_BWD_KS=0 in the environment flips it
+  static const int env_ks = [] { const char* e = getenv("PK_BWD_KS"); return e ? atoi(e) : 1; }();
   const bool ksplit = (a.dbg & 32) ? true : ((a.dbg & 16) ? false : env_ks != 0);
   if (ksplit) {
     if (H <= 256) PK_KS_ACT(4, 8)

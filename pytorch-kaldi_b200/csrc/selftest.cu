@@ -653,6 +653,12 @@ static void bench_all() {
       c = dclk.down();
       printf("bwd phases (cycles/step): pointwise+stage %.0f | push %.0f | rings(shadow) %.0f | wait_acc %.0f | ld+xchg+carry %.0f | - %.0f\n",
              c[0] / (double)T, c[1] / (double)T, c[2] / (double)T, c[3] / (double)T, c[4] / (double)T, c[5] / (double)T);
+      pk_rnn_layer_fwd(PK_CELL_LIGRU | PK_REC_WS, T, B, H, ndir, PK_ACT_RELU, dPT.p, ld, dsc.p, dsh.p, dU.p, dmask.p, 1.f, dY.p, 1100,
+                       dY16.p, 1104, dHT.p, dHT16.p, dHP16.p, dZT.p, dHCT.p, ld, nullptr);
+      CK(cudaDeviceSynchronize());
+      c = dclk.down();
+      printf("fwd ws phases (cycles/step): wait %.0f | ldmatrix+HMMA %.0f | gates %.0f | stage+push %.0f | rings(shadow) %.0f\n",
+             c[0] / (double)T, c[1] / (double)T, c[2] / (double)T, c[3] / (double)T, c[4] / (double)T);
       for (int v = 0; v < 2; ++v) {
         pk_rnn_layer_bwd(PK_CELL_LIGRU | PK_REC_WS | (v ? PK_REC_BWD_KSPLIT : PK_REC_BWD_ALLGATHER), T, B, H, ndir, PK_ACT_RELU, ddY.p,
                          dHT.p, dZT.p, dHCT.p, ld, dU.p, dmask.p, 1.f, dgs.p, dGT.p, dGT16.p, nullptr);
