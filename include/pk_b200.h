@@ -167,6 +167,11 @@ int pk_rnn_layer_bwd(int cell, int T, int B, int H, int ndir, int act, const flo
  * workspace: device scratch of pk_rnn_step_workspace_bytes(cell, T, B, H, ndir, backward) bytes (packed fp16
  * weights, fp32 state, double-buffered fp16 operands). */
 int64_t pk_rnn_step_workspace_bytes(int cell, int T, int B, int H, int ndir, int backward);
+/* number of __global__ launches one pk_rnn_step_fwd / _bwd call performs for this shape (weight packing + the
+ * recurrent kernel(s): 2 for the cluster-persistent LSTM kernels (csrc/pk_cell_cluster.cu, H <= 560: 16 batch rows
+ * per thread-block cluster, weights stationary in shared memory, state exchanged over distributed shared memory),
+ * 2-3 for the cooperative step-wise kernels, T (2T for GRU / minimalGRU) + packs for per-step launches). */
+int pk_rnn_step_launches(int cell, int T, int B, int H, int ndir, int backward);
 int pk_rnn_step_fwd(int cell, int T, int B, int H, int ndir, int act, const float* PT, int64_t ldp,
                     const float* scale, const float* shift, const float* U, const float* mask,
                     float mask_scalar, float* Y32, int64_t ldy32, void* Y16, int64_t ldy16, float* HT,

@@ -157,6 +157,10 @@ int64_t pk_rnn_step_workspace_bytes(int cell, int T, int B, int H, int ndir, int
   return cell_step_workspace_bytes(cell & PK_CELL_MASK, T, B, H, ndir, backward);
 }
 
+int pk_rnn_step_launches(int cell, int T, int B, int H, int ndir, int backward) {
+  return cell_step_launches(cell & PK_CELL_MASK, T, B, H, ndir, backward);
+}
+
 int pk_rnn_step_fwd(int cell, int T, int B, int H, int ndir, int act, const float* PT, int64_t ldp,
                     const float* scale, const float* shift, const float* U, const float* mask, float mask_scalar,
                     float* Y32, int64_t ldy32, void* Y16, int64_t ldy16, float* HT, void* HT16, void* HP16,

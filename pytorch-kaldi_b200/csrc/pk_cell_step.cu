@@ -628,7 +628,10 @@ Layout make_layout(int cell, int B, int H, int ndir, bool bwd) {
   L.NU = (H + 7) / 8;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) / 256 * 256; return r; };
-  L.off_wp = take(static_cast<size_t>(L.NU) * L.NG * 8 * L.KPs * 2);
+  size_t wp_bytes = static_cast<size_t>(L.NU) * L.NG * 8 * L.KPs * 2;
+  if (cell == CELL_LSTM)  // the cluster-persistent kernels pack one image per CTA (pk_cell_cluster.cu)
+    wp_bytes = std::max(wp_bytes, static_cast<size_t>(lstm_cluster_pack_bytes(H)));
+  L.off_wp = take(wp_bytes);
   L.off_h = take(static_cast<size_t>(ndir) * B * H * 4);
   L.off_c = take(static_cast<size_t>(ndir) * B * H * 4);
   const size_t op = static_cast<size_t>(L.Rp) * L.KPs * 2;
@@ -695,6 +698,18 @@ long long cell_step_workspace_bytes(int cell, int T, int B, int H, int ndir, int
   return static_cast<long long>(make_layout(cell, B, H, ndir, backward != 0).total);
 }
 
+int cell_step_launches(int cell, int T, int B, int H, int ndir, int backward) {
+  if (lstm_cluster_usable(cell, H)) return 2;  // pack + one cluster-persistent kernel
+  const Layout L = make_layout(cell, B, H, ndir, backward != 0);
+  const bool tp = two_phase(cell);
+  const int packs = tp ? 2 : 1;
+  if (persist_enabled()) {  // the cooperative variant is used whenever the grid fits one wave (148 SMs x >= 1 CTA)
+    const int ctas = L.NU * ((L.Rp + kRowsPerCta - 1) / kRowsPerCta);
+    if (ctas <= 148) return packs + 1;
+  }
+  return packs + (tp ? 2 : 1) * T;
+}
+
 static bool cell_supported(int cell) {
   return cell == CELL_LIGRU || cell == CELL_LSTM || cell == CELL_GRU || cell == CELL_MGRU;
 }
@@ -706,6 +721,7 @@ int cell_step_fwd(const CellStepFwdArgs& a, cudaStream_t stream) {
              "cell_step_fwd: workspace too small (%lld < %zu)", a.workspace_bytes, L.total);
   char* ws = static_cast<char*>(a.workspace);
   __half* Wp = reinterpret_cast<__half*>(ws + L.off_wp);
+  if (lstm_cluster_usable(a.cell, a.H)) return lstm_cluster_fwd(a, Wp, stream);
   __half* S[2] = {reinterpret_cast<__half*>(ws + L.off_a), reinterpret_cast<__half*>(ws + L.off_b)};
   unsigned* counter = reinterpret_cast<unsigned*>(ws + L.off_bar);
   const size_t op = static_cast<size_t>(L.Rp) * L.KPs * 2;
@@ -783,6 +799,7 @@ int cell_step_bwd(const CellStepBwdArgs& a, cudaStream_t stream) {
              "cell_step_bwd: workspace too small (%lld < %zu)", a.workspace_bytes, L.total);
   char* ws = static_cast<char*>(a.workspace);
   __half* UTp = reinterpret_cast<__half*>(ws + L.off_wp);
+  if (lstm_cluster_usable(a.cell, a.H)) return lstm_cluster_bwd(a, UTp, stream);
   const size_t op = static_cast<size_t>(L.Rp) * L.KPs * 2;
   __half* Ga = reinterpret_cast<__half*>(ws + L.off_a);
   __half* Gb = reinterpret_cast<__half*>(ws + L.off_b);

@@ -324,6 +324,14 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, uint4 v) {
                : "memory");
 }
 
+__device__ __forceinline__ void st_cluster_v4_f32(uint32_t cluster_addr, float x, float y, float z, float w) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "f"(x), "f"(y), "f"(z), "f"(w)
+               : "memory");
+}
+__device__ __forceinline__ void st_cluster_v2_f32(uint32_t cluster_addr, float x, float y) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(x), "f"(y) : "memory");
+}
+
 // remote (or local) 16-byte store that signals `bytes` on an mbarrier living in the SAME target
 // CTA: data and completion travel together, so the consumer needs no fence and no barrier.
 __device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, uint4 v, uint32_t cluster_mbar) {
@@ -369,6 +377,15 @@ __device__ __forceinline__ void ldmatrix_x4(uint32_t saddr, uint32_t& r0, uint32
 }
 __device__ __forceinline__ void ldmatrix_x2(uint32_t saddr, uint32_t& r0, uint32_t& r1) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];"
+               : "=r"(r0), "=r"(r1)
+               : "r"(saddr)
+               : "memory");
+}
+
+// two 8x8 b16 matrices, transposed on the way: shared-memory rows are the K index (8 consecutive N per 16-byte row),
+// the result is the col-major B fragment of mma.m16n8k16 (lanes 0-7: rows k0..k0+7, lanes 8-15: rows k0+8..k0+15)
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t saddr, uint32_t& r0, uint32_t& r1) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];"
                : "=r"(r0), "=r"(r1)
                : "r"(saddr)
                : "memory");

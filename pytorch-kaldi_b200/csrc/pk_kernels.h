@@ -136,6 +136,13 @@ struct CellStepBwdArgs {
   long long workspace_bytes = 0;
 };
 long long cell_step_workspace_bytes(int cell, int T, int B, int H, int ndir, int backward);
+// kernel launches one cell_step_fwd / cell_step_bwd call performs for this shape (bench.py's gpu_launches claim)
+int cell_step_launches(int cell, int T, int B, int H, int ndir, int backward);
+// cluster-persistent LSTM kernels (pk_cell_cluster.cu): DSMEM state exchange instead of L2 + grid barrier, H <= 560
+bool lstm_cluster_usable(int cell, int H);
+long long lstm_cluster_pack_bytes(int H);
+int lstm_cluster_fwd(const CellStepFwdArgs& a, __half* Wc, cudaStream_t stream);
+int lstm_cluster_bwd(const CellStepBwdArgs& a, __half* Wc, cudaStream_t stream);
 int cell_step_fwd(const CellStepFwdArgs& a, cudaStream_t stream);
 int cell_step_bwd(const CellStepBwdArgs& a, cudaStream_t stream);
 

@@ -41,6 +41,7 @@ SIGNATURES = {
     "pk_rnn_layer_bwd": [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_p, _c_p, _c_p, _c_p, _c_i64, _c_p, _c_p,
                          _c_f, _c_p, _c_p, _c_p, _c_p],
     "pk_rnn_step_workspace_bytes": [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int],
+    "pk_rnn_step_launches": [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int],
     "pk_rnn_step_fwd": [_c_int] * 6 + [_c_p, _c_i64, _c_p, _c_p, _c_p, _c_p, _c_f, _c_p, _c_i64, _c_p, _c_i64, _c_p, _c_p,
                                        _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_i64, _c_p, _c_i64, _c_p],
     "pk_rnn_step_bwd": [_c_int] * 6 + [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_i64, _c_p, _c_p, _c_f, _c_p, _c_p,
@@ -101,7 +102,7 @@ def lib():
 launch_count = 0
 KERNELS_PER_CALL = {"pk_dense_act_fwd": 1, "pk_dense_act_bwd": 1, "pk_amax_finalize": 1, "pk_gemm_tn": 1, "pk_transpose_f32": 1, "pk_convert_f16": 1, "pk_amax_scale": 2,
                     "pk_bn_finalize": 1, "pk_fill_scale_shift": 1, "pk_bn_bwd": 2, "pk_rnn_layer_fwd": 1,
-                    "pk_rnn_layer_bwd": 1, "pk_rnn_step_fwd": 1, "pk_rnn_step_bwd": 1, "pk_rowln_fwd": 1, "pk_conv_ln0_bwd": 1,
+                    "pk_rnn_layer_bwd": 1, "pk_rnn_step_fwd": 0, "pk_rnn_step_bwd": 0, "pk_rowln_fwd": 1, "pk_conv_ln0_bwd": 1,
                     "pk_sinc_filters_fwd": 1, "pk_sinc_filters_bwd": 1, "pk_conv_pack_weights": 1, "pk_conv_im2col0": 1,
                     "pk_conv_im2col_t": 1, "pk_conv_post_fwd": 1, "pk_conv_post_bwd": 1, "pk_logsoftmax_nll": 1, "pk_logsoftmax_bwd": 1, "pk_rmsprop_step": 1, "pk_adam_step": 1, "pk_chunk_prepare": 2, "pk_batch_assemble": 1, "pk_sub_log_prior": 1, "pk_cm_decode": 1,
                     "pk_sgd_step": 1, "pk_ln_cm_fwd": 1, "pk_ln_cm_bwd": 1, "pk_row_stats": 1}
@@ -197,13 +198,18 @@ def rnn_step_workspace_bytes(cell, T, B, H, ndir, backward):
     return int(lib().pk_rnn_step_workspace_bytes(cell, T, B, H, ndir, 1 if backward else 0))
 
 
+def rnn_step_launches(cell, T, B, H, ndir, backward):
+    """__global__ launches of one rnn_step_fwd / rnn_step_bwd call (depends on which kernel family takes the shape)."""
+    return int(lib().pk_rnn_step_launches(cell, T, B, H, ndir, 1 if backward else 0))
+
+
 def rnn_step_fwd(cell, T, B, H, ndir, act, PT, ldp, scale, shift, U, mask, mask_scalar, Y32, ldy32, Y16, ldy16, HT, HT16,
                  HP16, HX16, SV, ldt, workspace):
     sv = list(SV) + [None] * (5 - len(SV))
     _check(lib().pk_rnn_step_fwd(cell, T, B, H, ndir, act, _ptr(PT), ldp, _ptr(scale), _ptr(shift), _ptr(U), _ptr(mask),
                                  float(mask_scalar), _ptr(Y32), ldy32, _ptr(Y16), ldy16, _ptr(HT), _ptr(HT16),
                                  _ptr(HP16), _ptr(HX16), *[_ptr(s) for s in sv], ldt, _ptr(workspace), workspace.numel(), _stream()),
-           "pk_rnn_step_fwd", (2 * T + 1) if (cell & 0xff) in (CELL_GRU, CELL_MGRU) else T)  # pack + T step kernels
+           "pk_rnn_step_fwd", rnn_step_launches(cell, T, B, H, ndir, False))
 
 
 def rnn_step_bwd(cell, T, B, H, ndir, act, dYT, HT, SV, ldt, U, mask, mask_scalar, gscale, GT16, workspace):
@@ -211,7 +217,7 @@ def rnn_step_bwd(cell, T, B, H, ndir, act, dYT, HT, SV, ldt, U, mask, mask_scala
     _check(lib().pk_rnn_step_bwd(cell, T, B, H, ndir, act, _ptr(dYT), _ptr(HT), *[_ptr(s) for s in sv], ldt, _ptr(U),
                                  _ptr(mask), float(mask_scalar), _ptr(gscale), _ptr(GT16), _ptr(workspace),
                                  workspace.numel(), _stream()), "pk_rnn_step_bwd",
-           (2 * T + 1) if (cell & 0xff) in (CELL_GRU, CELL_MGRU) else T)
+           rnn_step_launches(cell, T, B, H, ndir, True))
 
 
 def rowln_fwd(x, ldx, N, L, gamma, beta, eps, y, stats):
