@@ -536,3 +536,89 @@ def read_vec_int_ark(fd):
         if vec[0]["size"] != 4:
             raise ValueError("integer vector with a non-int32 element size")
         yield key, vec["value"].copy()
+
+
+def read_post(fd):
+    """One Kaldi `Posterior` (vector<vector<pair<int32, float>>>: frames x (index, value) records) at the stream position
+    (data_io.py:1314-1348): "\0B", then \4 + int32 frame count, per frame \4 + int32 record count and 10-byte records
+    (int8 4, int32 index, int8 4, float32 value).  Returns a list (frames) of lists of (index, value) tuples like the
+    reference; an empty frame is an empty list (the reference asserts on it)."""
+    if fd.read(2) != b"\0B":
+        raise ValueError("only binary Kaldi posteriors are supported")
+    if fd.read(1) != b"\x04":
+        raise ValueError("bad posterior header")
+    n_frames = int(np.frombuffer(fd.read(4), dtype="int32", count=1)[0])
+    rec = np.dtype([("size_idx", "int8"), ("idx", "int32"), ("size_post", "int8"), ("post", "float32")])
+    out = []
+    for _ in range(n_frames):
+        if fd.read(1) != b"\x04":
+            raise ValueError("bad posterior frame header")
+        n = int(np.frombuffer(fd.read(4), dtype="int32", count=1)[0])
+        data = np.frombuffer(fd.read(n * 10), dtype=rec, count=n)
+        if n and (data[0]["size_idx"] != 4 or data[0]["size_post"] != 4):
+            raise ValueError("posterior record with a non-4-byte field")
+        out.append(data[["idx", "post"]].tolist())
+    return out
+
+
+def read_post_ark(fd):
+    """Generator of (key, posterior) over a binary Kaldi posterior archive (data_io.py:1291-1311)."""
+    while True:
+        key = _read_key(fd)
+        if key is None:
+            return
+        yield key, read_post(fd)
+
+
+def read_post_scp(scp_path):
+    """Generator of (key, posterior) over a Kaldi script file of posteriors (data_io.py:1270-1288)."""
+    with open(scp_path) as scp:
+        for line in scp:
+            if not line.strip():
+                continue
+            key, rx = line.strip().split(None, 1)
+            fd, close = open_rx(rx)
+            try:
+                yield key, read_post(fd)
+            finally:
+                if close:
+                    fd.close()
+
+
+def read_post_rxspec(spec):
+    """`ark:...` / `scp:...` adaptor (data_io.py:1256-1267)."""
+    if spec.startswith("ark:"):
+        fd, close = open_rx(spec)
+        try:
+            yield from read_post_ark(fd)
+        finally:
+            if close:
+                fd.close()
+    elif spec.startswith("scp:"):
+        yield from read_post_scp(spec.split(":", 1)[1])
+    else:
+        raise ValueError(f"unsupported input type {spec!r}: it should begin with 'ark:' or 'scp:'")
+
+
+def read_cntime(fd):
+    """Kaldi confusion-network bin times, vector<pair<float, float>> (data_io.py:1384-1416): "\0B", \4 + int32 count, then
+    10-byte records (int8 4, float32 begin, int8 4, float32 end).  Returns a list of (begin, end) tuples."""
+    if fd.read(2) != b"\0B":
+        raise ValueError("only binary Kaldi confusion-network times are supported")
+    if fd.read(1) != b"\x04":
+        raise ValueError("bad cntime header")
+    n = int(np.frombuffer(fd.read(4), dtype="int32", count=1)[0])
+    rec = np.dtype([("size_beg", "int8"), ("t_beg", "float32"), ("size_end", "int8"), ("t_end", "float32")])
+    data = np.frombuffer(fd.read(n * 10), dtype=rec, count=n)
+    if n and (data[0]["size_beg"] != 4 or data[0]["size_end"] != 4):
+        raise ValueError("cntime record with a non-4-byte field")
+    return data[["t_beg", "t_end"]].tolist()
+
+
+def read_cntime_ark(fd):
+    """Generator of (key, bin times) over a Kaldi confusion-network time archive (data_io.py:1360-1381)."""
+    while True:
+        key = _read_key(fd)
+        if key is None:
+            return
+        yield key, read_cntime(fd)

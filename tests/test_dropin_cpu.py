@@ -311,3 +311,59 @@ def test_text_archives_float_vectors_and_rxspecs_match_the_reference_readers(tmp
             assert np.allclose(rv[k], gv[k]), k
         rs = {k: np.array(v) for k, v in ref.read_mat_scp(str(scp), out)}
         assert all(np.array_equal(rs[k], mats[k]) for k in mats)
+
+
+def test_posterior_and_cntime_readers(tmp_path):
+    """SURVEY 8f-3 leftovers: Kaldi `Posterior` archives / scripts and confusion-network bin times
+    (data_io.py:1256-1416) against hand-built archives and — when the reference is present — its own readers."""
+    import pk_train
+    rng = np.random.RandomState(7)
+    posts, times = {}, {}
+    ark = tmp_path / "post.ark"
+    offs = {}
+    with open(ark, "wb") as f:
+        for k, nfr in (("utt_a", 5), ("utt_b", 1), ("utt_c", 9)):
+            frames = []
+            f.write((k + " ").encode())
+            offs[k] = f.tell()
+            f.write(b"\0B\x04" + np.int32(nfr).tobytes())
+            for _ in range(nfr):
+                n = int(rng.randint(1, 4))
+                recs = [(int(rng.randint(0, 1936)), float(np.float32(rng.rand()))) for _ in range(n)]
+                f.write(b"\x04" + np.int32(n).tobytes())
+                for idx, p in recs:
+                    f.write(b"\x04" + np.int32(idx).tobytes() + b"\x04" + np.float32(p).tobytes())
+                frames.append(recs)
+            posts[k] = frames
+    got = dict(pk_train.read_post_ark(open(ark, "rb")))
+    assert got == posts
+    assert dict(pk_train.read_post_rxspec(f"ark:{ark}")) == posts
+    scp = tmp_path / "post.scp"
+    with open(scp, "w") as f:
+        for k in posts:
+            f.write(f"{k} {ark}:{offs[k]}\n")
+    assert dict(pk_train.read_post_rxspec(f"scp:{scp}")) == posts
+    cark = tmp_path / "cn.ark"
+    with open(cark, "wb") as f:
+        for k, n in (("utt_a", 4), ("utt_b", 2)):
+            t = [(float(np.float32(i * 0.1)), float(np.float32(i * 0.1 + 0.07))) for i in range(n)]
+            f.write((k + " ").encode() + b"\0B\x04" + np.int32(n).tobytes())
+            for b, e in t:
+                f.write(b"\x04" + np.float32(b).tobytes() + b"\x04" + np.float32(e).tobytes())
+            times[k] = t
+    assert dict(pk_train.read_cntime_ark(open(cark, "rb"))) == times
+    with pytest.raises(ValueError):
+        list(pk_train.read_post_rxspec("file.ark"))
+    ref = _ref_data_io()
+    if ref is not None:
+        # the reference's archive generators call read_post(fd) / read_cntime(fd) without their second argument
+        # (TypeError, data_io.py:1308 / :1377), so its single-entry readers are driven over the archive directly
+        out = str(tmp_path)
+        for path, one, want in ((ark, ref.read_post, posts), (cark, ref.read_cntime, times)):
+            with open(path, "rb") as fd:
+                seen = {}
+                key = ref.read_key(fd)
+                while key:
+                    seen[key] = one(fd, out)
+                    key = ref.read_key(fd)
+            assert seen == want
