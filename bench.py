@@ -590,7 +590,10 @@ def main():
         H = c["lay"][0]
         ng = {"ligru": 2, "lstm": 4, "gru": 3, "minimalgru": 2, "rnn": 1}[c["cell"]]
         flops_launch = 2.0 * c["T"] * (2 * c["B"]) * (ng * H) * H  # U^T [gate gradients] for every row of the direction-stacked batch
-        kname = ("cell_bwd_persist_kernel (step-wise reverse-time recurrence)" if stepwise else
+        cluster = stepwise and c["cell"] == "lstm" and pk.rnn_step_is_cluster(pk.CELL_LSTM, H)
+        kname = ("lstm_cluster_bwd_kernel (cluster-persistent reverse-time recurrence: weights stationary in shared memory, "
+                 "K-split reduce-scatter over distributed shared memory) + weight packing" if cluster else
+                 "cell_bwd_persist_kernel (step-wise reverse-time recurrence)" if stepwise else
                  "ligru_bwd_ws_kernel (persistent reverse-time recurrence, register-stationary mma.sync; the faster of the "
                  "two kernel families at this H)" if H <= 560 else
                  "ligru_bwd_tc_kernel (persistent reverse-time recurrence on tcgen05, weights stationary in TMEM)")

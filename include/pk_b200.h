@@ -172,6 +172,8 @@ int64_t pk_rnn_step_workspace_bytes(int cell, int T, int B, int H, int ndir, int
  * per thread-block cluster, weights stationary in shared memory, state exchanged over distributed shared memory),
  * 2-3 for the cooperative step-wise kernels, T (2T for GRU / minimalGRU) + packs for per-step launches). */
 int pk_rnn_step_launches(int cell, int T, int B, int H, int ndir, int backward);
+/* 1 if pk_rnn_step_fwd / _bwd run this (cell, H) on the cluster-persistent kernels, 0 for the step-wise family */
+int pk_rnn_step_is_cluster(int cell, int H);
 int pk_rnn_step_fwd(int cell, int T, int B, int H, int ndir, int act, const float* PT, int64_t ldp,
                     const float* scale, const float* shift, const float* U, const float* mask,
                     float mask_scalar, float* Y32, int64_t ldy32, void* Y16, int64_t ldy16, float* HT,
@@ -183,6 +185,21 @@ int pk_rnn_step_bwd(int cell, int T, int B, int H, int ndir, int act, const floa
                     const float* sv4, int64_t ldt, const float* U, const float* mask, float mask_scalar,
                     const float* gscale, void* GT16, void* workspace, int64_t workspace_bytes,
                     void* stream);
+
+/* ---- FusionLinearConv (neural_networks.py:2057-2099, used by liGRU_layer :795-995 / fusionRNN_jit :719-793) ----
+ * The shared per-microphone affine map Conv1d(1, C, kernel = d, stride = d) is pk_gemm_tn over the zero-copy view
+ * [N*M][d] of the input (row n*M + m = channel m of frame n) -> O [N*M][ldo] fp32 (+ bias).  These two calls do the
+ * rest.  Columns are G gate blocks of Hh (e.g. wh | wz of a liGRU_layer), each with its own slope:
+ *   fwd: P[n][c] = red * sum_m act(O[n*M+m][c]);  mode 0: act(x) = x > 0 ? x : slopes[c / Hh] * x (relu 0, leaky_relu
+ *        0.01, prelu = the learnt parameter, read on the device), mode 1: tanh;  red = 1 ("sum") or 1/M ("mean")
+ *   bwd: dO[n*M+m][c] = red * dP[n][c] * act'(O[n*M+m][c]);  dbias[c] += column sums of dO (conv bias gradient);
+ *        dslope[c / Hh] += sum over O <= 0 of red * dP * O (PReLU gradient; may be NULL).  dbias / dslope must be
+ *        zeroed by the caller (atomics). */
+int pk_fusion_reduce_fwd(const float* O, int64_t ldo, int64_t N, int M, int C, int Hh, int mode, const float* slopes,
+                         float red, float* P, int64_t ldp, void* stream);
+int pk_fusion_reduce_bwd(const float* dP, int64_t lddp, const float* O, int64_t ldo, int64_t N, int M, int C, int Hh,
+                         int mode, const float* slopes, float red, float* dO, int64_t lddo, float* dbias, float* dslope,
+                         void* stream);
 
 /* ---- conv front-ends: CNN (neural_networks.py:1464-1556), SincNet (:1559-1665), SincConv (:1668-1813) ----
  * Activations are position-major fp16 A16[n][l][c] (channel pitch Cp = pad8(C)); a stride-1 valid convolution

@@ -161,6 +161,8 @@ int pk_rnn_step_launches(int cell, int T, int B, int H, int ndir, int backward) 
   return cell_step_launches(cell & PK_CELL_MASK, T, B, H, ndir, backward);
 }
 
+int pk_rnn_step_is_cluster(int cell, int H) { return lstm_cluster_usable(cell & PK_CELL_MASK, H) ? 1 : 0; }
+
 int pk_rnn_step_fwd(int cell, int T, int B, int H, int ndir, int act, const float* PT, int64_t ldp,
                     const float* scale, const float* shift, const float* U, const float* mask, float mask_scalar,
                     float* Y32, int64_t ldy32, void* Y16, int64_t ldy16, float* HT, void* HT16, void* HP16,
@@ -193,6 +195,21 @@ int pk_rnn_step_bwd(int cell, int T, int B, int H, int ndir, int act, const floa
   a.ldt = ldt; a.U = U; a.mask = mask; a.mask_scalar = mask_scalar; a.gscale = gscale;
   a.GT16 = static_cast<__half*>(GT16); a.workspace = workspace; a.workspace_bytes = workspace_bytes;
   return cell_step_bwd(a, static_cast<cudaStream_t>(stream));
+}
+
+int pk_fusion_reduce_fwd(const float* O, int64_t ldo, int64_t N, int M, int C, int Hh, int mode, const float* slopes,
+                         float red, float* P, int64_t ldp, void* stream) {
+  PK_REQUIRE(O && P && N > 0 && M > 0 && C > 0 && Hh > 0 && C % Hh == 0, "pk_fusion_reduce_fwd: bad arguments");
+  PK_REQUIRE(mode == 1 || (mode == 0 && slopes), "pk_fusion_reduce_fwd: mode 0 (piecewise linear) needs the slopes, mode 1 = tanh");
+  return fusion_reduce_fwd(O, ldo, N, M, C, Hh, mode, slopes, red, P, ldp, static_cast<cudaStream_t>(stream));
+}
+int pk_fusion_reduce_bwd(const float* dP, int64_t lddp, const float* O, int64_t ldo, int64_t N, int M, int C, int Hh,
+                         int mode, const float* slopes, float red, float* dO, int64_t lddo, float* dbias, float* dslope,
+                         void* stream) {
+  PK_REQUIRE(dP && O && dO && dbias && N > 0 && M > 0 && C > 0 && Hh > 0 && C % Hh == 0, "pk_fusion_reduce_bwd: bad arguments");
+  PK_REQUIRE(mode == 1 || (mode == 0 && slopes), "pk_fusion_reduce_bwd: mode 0 (piecewise linear) needs the slopes, mode 1 = tanh");
+  return fusion_reduce_bwd(dP, lddp, O, ldo, N, M, C, Hh, mode, slopes, red, dO, lddo, dbias, dslope,
+                           static_cast<cudaStream_t>(stream));
 }
 
 int pk_rowln_fwd(const float* x, int64_t ldx, int N, int L, const float* gamma, const float* beta, float eps, float* y,

@@ -195,6 +195,13 @@ struct ConvPostBwdArgs {
 };
 int conv_post_bwd(const ConvPostBwdArgs& a, cudaStream_t stream);
 
+// ---- FusionLinearConv companions (pk_fusion.cu): activation + reduction over the microphone channels ----
+int fusion_reduce_fwd(const float* O, long long ldo, long long N, int M, int C, int Hh, int mode, const float* slopes,
+                      float red, float* P, long long ldp, cudaStream_t stream);
+int fusion_reduce_bwd(const float* dP, long long lddp, const float* O, long long ldo, long long N, int M, int C, int Hh,
+                      int mode, const float* slopes, float red, float* dO, long long lddo, float* dbias, float* dslope,
+                      cudaStream_t stream);
+
 // ---- memory-bound helpers (pk_elementwise.cu) ----
 // out[c][r] = in[r][c]; optional fp16 copies. in is [R][ldi] fp32.
 int transpose_f32(const float* in, long long ldi, int R, int C, float* outT, long long ldo,

@@ -397,6 +397,185 @@ class GRU_cudnn(_CudnnLayout):
 
 
 # ---------------------------------------------------------------------------------------------
+# FusionRNN: FusionLinearConv :2057-2099, liGRU_layer :795-995, fusionRNN_jit :719-793
+# ---------------------------------------------------------------------------------------------
+
+
+class FusionLinearConv(nn.Module):
+    """Reference :2057-2099 — one affine map shared by the `number_of_mic` channels that are concatenated along the last
+    dimension (Conv1d(1, out, kernel = in/mic, stride = in/mic)), an activation, and a sum / mean over the channels.
+    Same constructor, parameters and init; the forward is the native GEMM + reduction (pk_functions.FusionProjFn)."""
+
+    def __init__(self, in_features, out_features, number_of_mic=1, bias=True, seed=None, act="leaky", reduce="sum"):
+        super().__init__()
+        self.in_features = in_features // number_of_mic
+        self.out_features = out_features
+        self.number_of_mic = number_of_mic
+        self.reduce = reduce
+        if act == "leaky_relu":
+            self.act_function = nn.LeakyReLU()
+        elif act == "prelu":
+            self.act_function = nn.PReLU()
+        elif act == "relu":
+            self.act_function = nn.ReLU()
+        else:
+            self.act_function = nn.Tanh()
+        self.conv = nn.Conv1d(1, self.out_features, kernel_size=self.in_features, stride=self.in_features, bias=True, padding=0)
+        self.conv.bias.data.fill_(0)
+        torch.nn.init.xavier_normal_(self.conv.weight.data)
+
+    def _fusion_cfg(self):
+        a = self.act_function
+        if isinstance(a, nn.PReLU):
+            mode, prelu, slope = 0, True, 0.0
+        elif isinstance(a, nn.LeakyReLU):
+            mode, prelu, slope = 0, False, float(a.negative_slope)
+        elif isinstance(a, nn.ReLU):
+            mode, prelu, slope = 0, False, 0.0
+        else:
+            mode, prelu, slope = 1, False, 0.0
+        red = 1.0 / self.number_of_mic if self.reduce == "mean" else 1.0
+        return pkf.FusionCfg(M=self.number_of_mic, mode=mode, red=red, prelu=prelu, slope=slope,
+                             grad_enabled=torch.is_grad_enabled())
+
+    def _fusion_params(self):
+        p = [self.conv.weight, self.conv.bias]
+        if isinstance(self.act_function, nn.PReLU):
+            p.append(self.act_function.weight)
+        return p
+
+    def forward(self, input):
+        _require_cuda(input, "FusionLinearConv")
+        with torch.cuda.device(input.device):
+            return pkf.FusionProjFn.apply(input, self._fusion_cfg(), *self._fusion_params())
+
+
+class liGRU_layer(nn.Module):
+    """Reference :795-995 (a torch.jit.ScriptModule there): one bidirectional liGRU layer with the two input
+    projections `wz`, `wh` (nn.Linear with bias, or FusionLinearConv when `do_fusion`), BatchNorm on both, ONE stacked
+    recurrent matrix `u` = [Uz; Uh] (:866-868, chunked as (uz, uh) at :975), ReLU candidate and an nn.Dropout-style
+    mask (kept entries scaled by 1/(1-p)) that is constant over time (:935-970).  Same constructor (sub-module names,
+    creation order, init) -> identical state_dict and generator consumption; the forward runs the persistent liGRU
+    kernels: gate blocks re-ordered to this library's (h, z), the Linear biases cancel against BatchNorm."""
+
+    def __init__(self, input_size, hidden_size, num_layers, batch_size, dropout=0.0, nonlinearity="relu", bidirectional=True,
+                 device="cuda", do_fusion=False, fusion_layer_size=64, number_of_mic=1, act="relu", reduce="mean"):
+        super().__init__()
+        self.hidden_size = int(hidden_size)
+        self.input_size = int(input_size)
+        self.batch_size = batch_size
+        self.bidirectional = bidirectional
+        self.dropout = dropout
+        self.device = device
+        self.do_fusion = bool(do_fusion)
+        self.fusion_layer_size = fusion_layer_size
+        self.number_of_mic = number_of_mic
+        self.reduce = reduce
+        if self.do_fusion:
+            self.hidden_size = self.fusion_layer_size // self.number_of_mic
+            self.wz = FusionLinearConv(self.input_size, self.hidden_size, bias=True, number_of_mic=self.number_of_mic, act=act,
+                                       reduce=self.reduce)
+            self.wh = FusionLinearConv(self.input_size, self.hidden_size, bias=True, number_of_mic=self.number_of_mic, act=act,
+                                       reduce=self.reduce)
+        else:
+            self.wz = nn.Linear(self.input_size, self.hidden_size, bias=True)
+            self.wh = nn.Linear(self.input_size, self.hidden_size, bias=True)
+            self.wz.bias.data.fill_(0)
+            torch.nn.init.xavier_normal_(self.wz.weight.data)
+            self.wh.bias.data.fill_(0)
+            torch.nn.init.xavier_normal_(self.wh.weight.data)
+        self.u = nn.Linear(self.hidden_size, 2 * self.hidden_size, bias=False)
+        nn.init.orthogonal_(self.u.weight)
+        self.bn_wh = nn.BatchNorm1d(self.hidden_size, momentum=0.05)
+        self.bn_wz = nn.BatchNorm1d(self.hidden_size, momentum=0.05)
+        self.drop = torch.nn.Dropout(p=self.dropout, inplace=False)
+        self.N_drop_masks = 100
+        self.drop_mask_cnt = 0
+        self.act = torch.nn.ReLU()
+        self.cell_flags = 0
+        self._mask_override = None  # tests: a [ndir*B, H] mask (already scaled) instead of a fresh draw
+
+    def _mask(self, rows, device):
+        if not self.training:
+            return None, 1.0          # drop_mask_te = 1.0 (:875)
+        if self._mask_override is not None:
+            return self._mask_override.to(device), 1.0
+        if self.dropout <= 0.0:
+            return None, 1.0
+        keep = 1.0 - self.dropout
+        return torch.empty(rows, self.hidden_size, device=device).bernoulli_(keep).mul_(1.0 / keep), 1.0
+
+    def forward(self, x):
+        _require_cuda(x, "liGRU_layer")
+        T, B, _ = x.shape
+        H = self.hidden_size
+        rows = (2 if self.bidirectional else 1) * B
+        with torch.cuda.device(x.device):
+            if self.do_fusion:
+                # both fused projections in one GEMM: [T, B, 2H] = [P_h | P_z]; the recurrent stack then sees them
+                # through identity "weights" (exact in the fp32-accumulating GEMM, one fp16 rounding of P)
+                cfgf = self.wh._fusion_cfg()
+                x = pkf.FusionProjFn.apply(x, cfgf, *self.wh._fusion_params(), *self.wz._fusion_params())
+                eye = torch.eye(2 * H, device=x.device)
+                ws, bias = [eye[:H], eye[H:]], None
+            else:
+                ws, bias = [self.wh.weight, self.wz.weight], [self.wh.bias, self.wz.bias]
+            mask, mscal = self._mask(rows, x.device)
+            cfg = pkf.RecStackCfg(bidir=bool(self.bidirectional), cell=pk.CELL_LIGRU, cell_flags=self.cell_flags,
+                                  grad_enabled=torch.is_grad_enabled())
+            cfg.layers.append(pkf.RecLayerCfg(H=H, act=pk.ACT_IDS["relu"], use_bn=True, bn_training=self.training,
+                                              bns=[self.bn_wh, self.bn_wz], mask=mask, mask_scalar=mscal, proj_bias=bias))
+            us = [self.u.weight[H:], self.u.weight[:H]]   # (uz, uh) = u(h).chunk(2, 1)  ->  this library's (h, z)
+            return pkf.LiGRUStackFn.apply(x, cfg, *ws, *us, self.bn_wh.weight, self.bn_wh.bias, self.bn_wz.weight,
+                                          self.bn_wz.bias)
+
+
+class fusionRNN_jit(nn.Module):
+    """Reference :719-793 (cfg/DIRHA_baselines/DIRHA_fusionRNN_MFCC_6ch.cfg): a stack of liGRU_layer, the first one
+    with FusionLinearConv input projections over the microphone channels.  The reference stores
+    `map(strtobool, options["fusionRNN_do_fusion"])` — a map object, always truthy — so the FIRST layer always fuses and
+    the others never do; kept.  `options["batches"]` (the reference's fixed batch size, :727) is optional here: the
+    kernels take the batch size from the input."""
+
+    def __init__(self, options, inp_dim):
+        super().__init__()
+        input_size = inp_dim
+        lay = _ints(options["fusionRNN_lay"])
+        hidden_size = lay[0]
+        dropout = _floats(options["fusionRNN_drop"])[0]
+        num_layers = len(lay)
+        batch_size = int(options["batches"]) if "batches" in options else 0
+        self.do_fusion = True
+        self.act = str(options["fusionRNN_fusion_act"])
+        self.reduce = str(options["fusionRNN_fusion_reduce"])
+        self.fusion_layer_size = int(options["fusionRNN_fusion_layer_size"])
+        self.to_do = options["to_do"]
+        self.number_of_mic = int(options["fusionRNN_number_of_mic"])
+        self.save_mic = self.number_of_mic
+        bidirectional = True
+        self.out_dim = 2 * hidden_size
+        current_dim = int(input_size)
+        self.model = torch.nn.ModuleList([])
+        self.training = self.to_do == "train"
+        for i in range(num_layers):
+            rnn_lay = liGRU_layer(current_dim, hidden_size, num_layers, batch_size, dropout=dropout, bidirectional=bidirectional,
+                                  device="cuda", do_fusion=self.do_fusion, fusion_layer_size=self.fusion_layer_size,
+                                  number_of_mic=self.number_of_mic, act=self.act, reduce=self.reduce)
+            if i == 0:
+                current_dim = (self.fusion_layer_size // self.save_mic) * 2
+                self.number_of_mic = 1
+                self.do_fusion = False
+            else:
+                current_dim = hidden_size * 2
+            self.model.append(rnn_lay)
+
+    def forward(self, x):
+        for ligru_lay in self.model:
+            x = ligru_lay(x)
+        return x
+
+
+# ---------------------------------------------------------------------------------------------
 # convolutional front-ends: CNN :1464-1556, SincNet :1559-1665, SincConv :1668-1813
 # ---------------------------------------------------------------------------------------------
 

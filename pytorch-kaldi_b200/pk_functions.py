@@ -35,6 +35,9 @@ class RecLayerCfg:
     bns: List[torch.nn.Module] = field(default_factory=list)  # per-gate nn.BatchNorm1d (running stats updated in place)
     mask: Optional[torch.Tensor] = None      # [ndir*B, H] device tensor (training) or None
     mask_scalar: float = 1.0                 # eval: 1 - p
+    # liGRU_layer (:861-870) keeps a bias on the Linear IN FRONT of BatchNorm: it cancels against the batch statistics
+    # (training) and is folded into the shift (eval); per real gate, or None
+    proj_bias: Optional[List[torch.Tensor]] = None
 
 
 @dataclass
@@ -101,7 +104,7 @@ def _stacked(ts):
 
 def _direct_grad_target(params):
     """The stacked `.grad` view of `params` if gradients may be written in place (see DIRECT_GRAD), else None."""
-    if not DIRECT_GRAD:
+    if not DIRECT_GRAD or any(not p.is_leaf for p in params):   # views (e.g. slices of a stacked matrix) have no .grad
         return None
     gs = [p.grad for p in params]
     if any(g is None or g.untyped_storage().data_ptr() not in _DIRECT_STORAGES for g in gs):
@@ -244,6 +247,11 @@ class LiGRUStackFn(torch.autograd.Function):
                                    bn.momentum if bn.momentum is not None else 0.1, bn_train,
                                    bn.running_mean, bn.running_var, bn.num_batches_tracked if bn_train else None,
                                    scale[sl], shift[sl], mean[sl], rstd[sl])
+                    if L.proj_bias is not None:
+                        if bn_train:   # the statistics came from W x; the module normalises W x + b
+                            bn.running_mean.add_(L.proj_bias[gi].detach(), alpha=bn.momentum if bn.momentum is not None else 0.1)
+                        else:
+                            shift[sl].addcmul_(scale[sl], L.proj_bias[gi].detach())
                 gamma = torch.cat(gammas + [torch.ones_like(gammas[0]) for _ in range(ngk - ngr)]).contiguous()
             else:
                 pk.fill_scale_shift(pkd["bias_cat"], CG, scale, shift)
@@ -500,6 +508,108 @@ class HeadNLLFn(torch.autograd.Function):
         pk.gemm_tn(dT16, XT16, dW, S, F, N, lda=ldn, ldb=ldn, ldc=F, alpha=1.0 / out_scale, split_k=8)
         ctx.wparam = None
         return dx, (None if dW_direct is not None else dW), db, None
+
+
+@dataclass
+class FusionCfg:
+    """Static description of a FusionLinearConv group (reference neural_networks.py:2057-2099)."""
+    M: int                    # microphone channels concatenated along the feature axis
+    mode: int                 # 0: act(x) = x > 0 ? x : slope * x (relu / leaky_relu / prelu), 1: tanh
+    red: float                # 1 ("sum") or 1 / M ("mean")
+    prelu: bool               # the slope is the nn.PReLU parameter of each gate (trained)
+    slope: float = 0.0        # fixed slope otherwise (relu 0, nn.LeakyReLU() 0.01)
+    grad_enabled: bool = True
+
+
+class FusionProjFn(torch.autograd.Function):
+    """`reduce_m act(Conv1d(1, H, kernel = d, stride = d)(x))` for G FusionLinearConv modules that read the same input
+    (wh and wz of a liGRU_layer, :817-825): ONE tcgen05 GEMM over the zero-copy view [N*M, d] of the input against the
+    stacked filters [G*H, d] (+ bias), then the activation + channel reduction kernel; backward = its pointwise
+    backward (dO, bias and PReLU-slope gradients) -> the weight-gradient GEMM (and dX when the input needs one).
+    Returns [..., G*H] fp32 (gate blocks side by side)."""
+
+    @staticmethod
+    def forward(ctx, x, cfg: FusionCfg, *params):
+        if not x.is_cuda:
+            raise RuntimeError("pytorch-kaldi_b200: FusionLinearConv needs CUDA tensors (there is no CPU fallback)")
+        per = 3 if cfg.prelu else 2          # per gate: conv.weight [H,1,d], conv.bias [H] (, prelu.weight [1])
+        G = len(params) // per
+        ws = [params[per * g] for g in range(G)]
+        bs = [params[per * g + 1] for g in range(G)]
+        H, d = ws[0].shape[0], ws[0].shape[-1]
+        M = cfg.M
+        if x.shape[-1] != M * d:
+            raise ValueError(f"FusionLinearConv: last dimension {x.shape[-1]} != number_of_mic * in_features = {M} * {d}")
+        dev = x.device
+        f32 = dict(device=dev, dtype=torch.float32)
+        f16 = dict(device=dev, dtype=torch.float16)
+        need_grad = cfg.grad_enabled and any(ctx.needs_input_grad)
+        lead = x.shape[:-1]
+        N = int(math.prod(lead))
+        rows, C = N * M, G * H
+        xr = x.reshape(rows, d)
+        if xr.dtype != torch.float32 or not xr.is_contiguous():
+            xr = xr.float().contiguous()
+        ldd, ldr, ldC = pad8(d), pad8(rows), pad8(C)
+        X16 = torch.empty(rows, ldd, **f16)
+        XT16 = torch.empty(d, ldr, **f16) if need_grad else None
+        pk.transpose_f32(xr, d, rows, d, outT16=XT16, ldo16=ldr, in16=X16, ldi16=ldd)
+        Wcat = torch.cat([w.reshape(H, d) for w in ws]).contiguous()
+        W16 = torch.empty(C, ldd, **f16)
+        WT16 = torch.empty(d, ldC, **f16) if (need_grad and ctx.needs_input_grad[0]) else None
+        pk.transpose_f32(Wcat, d, C, d, outT16=WT16, ldo16=ldC, in16=W16, ldi16=ldd)
+        if cfg.prelu:
+            slopes = torch.cat([params[per * g + 2].reshape(1) for g in range(G)]).float().contiguous()
+        else:
+            slopes = torch.full((G,), float(cfg.slope), **f32)
+        O = torch.empty(rows, C, **f32)
+        pk.gemm_tn(X16, W16, O, rows, C, d, lda=ldd, ldb=ldd, ldc=C, bias=torch.cat(bs).contiguous(), bias_mode=1)
+        P = torch.empty(N, C, **f32)
+        pk.fusion_reduce_fwd(O, C, N, M, C, H, cfg.mode, slopes, cfg.red, P, C)
+        if need_grad:
+            ctx.saved = (O, XT16, WT16, slopes)
+            ctx.dims = (N, M, d, H, G, per, tuple(x.shape), [tuple(w.shape) for w in ws])
+            ctx.cfg = cfg
+        return P.view(*lead, C)
+
+    @staticmethod
+    def backward(ctx, dP):
+        O, XT16, WT16, slopes = ctx.saved
+        N, M, d, H, G, per, xshape, wshapes = ctx.dims
+        cfg = ctx.cfg
+        dev = dP.device
+        f32 = dict(device=dev, dtype=torch.float32)
+        f16 = dict(device=dev, dtype=torch.float16)
+        rows, C = N * M, G * H
+        ldr, ldC = pad8(rows), pad8(C)
+        dp2 = dP.reshape(N, C)
+        if dp2.dtype != torch.float32 or not dp2.is_contiguous():
+            dp2 = dp2.float().contiguous()
+        dO = torch.empty(rows, C, **f32)
+        dbias = torch.zeros(C, **f32)
+        dsl = torch.zeros(G, **f32)
+        pk.fusion_reduce_bwd(dp2, C, O, C, N, M, C, H, cfg.mode, slopes, cfg.red, dO, C, dbias, dsl)
+        sc = torch.empty(2, **f32)
+        pk.amax_scale(dO, C, rows, C, 8.0, torch.empty(1, **f32), sc)
+        inv = sc[1:2]
+        need_dx = ctx.needs_input_grad[0]
+        dOT16 = torch.empty(C, ldr, **f16)
+        d16 = torch.empty(rows, ldC, **f16) if need_dx else None
+        pk.transpose_f32(dO, C, rows, C, outT16=dOT16, ldo16=ldr, in16=d16, ldi16=ldC, scale_dev=sc)
+        dW = torch.empty(C, d, **f32)
+        pk.gemm_tn(dOT16, XT16, dW, C, d, rows, lda=ldr, ldb=ldr, ldc=d, alpha_dev=inv, split_k=8 if rows >= 4096 else 1)
+        dx = None
+        if need_dx:
+            dxr = torch.empty(rows, d, **f32)
+            pk.gemm_tn(d16, WT16, dxr, rows, d, C, lda=ldC, ldb=ldC, ldc=d, alpha_dev=inv)
+            dx = dxr.view(xshape)
+        grads = []
+        for g in range(G):
+            grads += [dW[g * H:(g + 1) * H].reshape(wshapes[g]), dbias[g * H:(g + 1) * H]]
+            if cfg.prelu:
+                grads.append(dsl[g:g + 1])
+        ctx.saved = None
+        return (dx, None, *grads)
 
 
 @dataclass

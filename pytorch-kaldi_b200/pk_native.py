@@ -42,10 +42,14 @@ SIGNATURES = {
                          _c_f, _c_p, _c_p, _c_p, _c_p],
     "pk_rnn_step_workspace_bytes": [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int],
     "pk_rnn_step_launches": [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int],
+    "pk_rnn_step_is_cluster": [_c_int, _c_int],
     "pk_rnn_step_fwd": [_c_int] * 6 + [_c_p, _c_i64, _c_p, _c_p, _c_p, _c_p, _c_f, _c_p, _c_i64, _c_p, _c_i64, _c_p, _c_p,
                                        _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_i64, _c_p, _c_i64, _c_p],
     "pk_rnn_step_bwd": [_c_int] * 6 + [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_i64, _c_p, _c_p, _c_f, _c_p, _c_p,
                                        _c_p, _c_i64, _c_p],
+    "pk_fusion_reduce_fwd": [_c_p, _c_i64, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_p, _c_f, _c_p, _c_i64, _c_p],
+    "pk_fusion_reduce_bwd": [_c_p, _c_i64, _c_p, _c_i64, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_p, _c_f, _c_p, _c_i64,
+                             _c_p, _c_p, _c_p],
     "pk_rowln_fwd": [_c_p, _c_i64, _c_int, _c_int, _c_p, _c_p, _c_f, _c_p, _c_p, _c_p],
     "pk_conv_ln0_bwd": [_c_p, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_p, _c_i64, _c_p, _c_p, _c_p, _c_p],
     "pk_sinc_filters_fwd": [_c_p, _c_p, _c_int, _c_int, _c_f, _c_f, _c_f, _c_p, _c_p],
@@ -102,7 +106,7 @@ def lib():
 launch_count = 0
 KERNELS_PER_CALL = {"pk_dense_act_fwd": 1, "pk_dense_act_bwd": 1, "pk_amax_finalize": 1, "pk_gemm_tn": 1, "pk_transpose_f32": 1, "pk_convert_f16": 1, "pk_amax_scale": 2,
                     "pk_bn_finalize": 1, "pk_fill_scale_shift": 1, "pk_bn_bwd": 2, "pk_rnn_layer_fwd": 1,
-                    "pk_rnn_layer_bwd": 1, "pk_rnn_step_fwd": 0, "pk_rnn_step_bwd": 0, "pk_rowln_fwd": 1, "pk_conv_ln0_bwd": 1,
+                    "pk_rnn_layer_bwd": 1, "pk_rnn_step_fwd": 0, "pk_rnn_step_bwd": 0, "pk_rowln_fwd": 1, "pk_conv_ln0_bwd": 1, "pk_fusion_reduce_fwd": 1, "pk_fusion_reduce_bwd": 1,
                     "pk_sinc_filters_fwd": 1, "pk_sinc_filters_bwd": 1, "pk_conv_pack_weights": 1, "pk_conv_im2col0": 1,
                     "pk_conv_im2col_t": 1, "pk_conv_post_fwd": 1, "pk_conv_post_bwd": 1, "pk_logsoftmax_nll": 1, "pk_logsoftmax_bwd": 1, "pk_rmsprop_step": 1, "pk_adam_step": 1, "pk_chunk_prepare": 2, "pk_batch_assemble": 1, "pk_sub_log_prior": 1, "pk_cm_decode": 1,
                     "pk_sgd_step": 1, "pk_ln_cm_fwd": 1, "pk_ln_cm_bwd": 1, "pk_row_stats": 1}
@@ -203,6 +207,11 @@ def rnn_step_launches(cell, T, B, H, ndir, backward):
     return int(lib().pk_rnn_step_launches(cell, T, B, H, ndir, 1 if backward else 0))
 
 
+def rnn_step_is_cluster(cell, H):
+    """True when the step entry points run this (cell, H) on the cluster-persistent kernels (csrc/pk_cell_cluster.cu)."""
+    return bool(lib().pk_rnn_step_is_cluster(cell, H))
+
+
 def rnn_step_fwd(cell, T, B, H, ndir, act, PT, ldp, scale, shift, U, mask, mask_scalar, Y32, ldy32, Y16, ldy16, HT, HT16,
                  HP16, HX16, SV, ldt, workspace):
     sv = list(SV) + [None] * (5 - len(SV))
@@ -218,6 +227,16 @@ def rnn_step_bwd(cell, T, B, H, ndir, act, dYT, HT, SV, ldt, U, mask, mask_scala
                                  _ptr(mask), float(mask_scalar), _ptr(gscale), _ptr(GT16), _ptr(workspace),
                                  workspace.numel(), _stream()), "pk_rnn_step_bwd",
            rnn_step_launches(cell, T, B, H, ndir, True))
+
+
+def fusion_reduce_fwd(O, ldo, N, M, C, Hh, mode, slopes, red, P, ldp):
+    _check(lib().pk_fusion_reduce_fwd(_ptr(O), ldo, N, M, C, Hh, mode, _ptr(slopes), float(red), _ptr(P), ldp, _stream()),
+           "pk_fusion_reduce_fwd")
+
+
+def fusion_reduce_bwd(dP, lddp, O, ldo, N, M, C, Hh, mode, slopes, red, dO, lddo, dbias, dslope):
+    _check(lib().pk_fusion_reduce_bwd(_ptr(dP), lddp, _ptr(O), ldo, N, M, C, Hh, mode, _ptr(slopes), float(red), _ptr(dO),
+                                      lddo, _ptr(dbias), _ptr(dslope), _stream()), "pk_fusion_reduce_bwd")
 
 
 def rowln_fwd(x, ldx, N, L, gamma, beta, eps, y, stats):

@@ -120,7 +120,7 @@ def test_abi_library_loads_and_exports_every_declared_symbol():
     assert set(pk_native.SIGNATURES) | {"pk_last_error", "pk_version"} == declared
     # the launch-count table behind bench.py's gpu_launches covers every compute entry point
     assert all(isinstance(v, int) for v in pk_native.KERNELS_PER_CALL.values())
-    assert set(pk_native.SIGNATURES) - set(pk_native.KERNELS_PER_CALL) <= {"pk_rnn_step_workspace_bytes", "pk_rnn_step_launches"}
+    assert set(pk_native.SIGNATURES) - set(pk_native.KERNELS_PER_CALL) <= {"pk_rnn_step_workspace_bytes", "pk_rnn_step_launches", "pk_rnn_step_is_cluster"}
     L = pk_native.lib()
     assert L.pk_version() >= 2
     assert L.pk_last_error() is not None
