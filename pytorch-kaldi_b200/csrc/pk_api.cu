@@ -161,7 +161,9 @@ int pk_rnn_step_launches(int cell, int T, int B, int H, int ndir, int backward) 
   return cell_step_launches(cell & PK_CELL_MASK, T, B, H, ndir, backward);
 }
 
-int pk_rnn_step_is_cluster(int cell, int H) { return lstm_cluster_usable(cell & PK_CELL_MASK, H) ? 1 : 0; }
+int pk_rnn_step_is_cluster(int cell, int H) {
+  return (lstm_cluster_usable(cell & PK_CELL_MASK, H) || gru_cluster_usable(cell & PK_CELL_MASK, H)) ? 1 : 0;
+}
 
 int pk_rnn_step_fwd(int cell, int T, int B, int H, int ndir, int act, const float* PT, int64_t ldp,
                     const float* scale, const float* shift, const float* U, const float* mask, float mask_scalar,

@@ -564,7 +564,7 @@ int launch_cluster(const Args& a, int cluster, int nclusters, int threads, size_
   (p.act == ACT_TANH ? launch_cluster<ARGS, KERN<MT, ACT_TANH>>(p, G.CL, nclusters, MT * 32, SMEM, stream)  \
                      : launch_cluster<ARGS, KERN<MT, -1>>(p, G.CL, nclusters, MT * 32, SMEM, stream))
 
-constexpr int kDefaultOn = 0;  // flipped to 1 once this version has been verified on the GPU against the step-wise path
+constexpr int kDefaultOn = 1;  // verified on B200 against the step-wise family and the full-size reference fixture (profiles/r2_lstm_cluster.txt)
 
 }  // namespace
 

@@ -631,6 +631,8 @@ Layout make_layout(int cell, int B, int H, int ndir, bool bwd) {
   size_t wp_bytes = static_cast<size_t>(L.NU) * L.NG * 8 * L.KPs * 2;
   if (cell == CELL_LSTM)  // the cluster-persistent kernels pack one image per CTA (pk_cell_cluster.cu)
     wp_bytes = std::max(wp_bytes, static_cast<size_t>(lstm_cluster_pack_bytes(H)));
+  if (cell == CELL_GRU || cell == CELL_MGRU)  // pk_cell_cluster2.cu
+    wp_bytes = std::max(wp_bytes, static_cast<size_t>(gru_cluster_pack_bytes(cell, H)));
   L.off_wp = take(wp_bytes);
   L.off_h = take(static_cast<size_t>(ndir) * B * H * 4);
   L.off_c = take(static_cast<size_t>(ndir) * B * H * 4);
@@ -699,7 +701,7 @@ long long cell_step_workspace_bytes(int cell, int T, int B, int H, int ndir, int
 }
 
 int cell_step_launches(int cell, int T, int B, int H, int ndir, int backward) {
-  if (lstm_cluster_usable(cell, H)) return 2;  // pack + one cluster-persistent kernel
+  if (lstm_cluster_usable(cell, H) || gru_cluster_usable(cell, H)) return 2;  // pack + one cluster-persistent kernel
   const Layout L = make_layout(cell, B, H, ndir, backward != 0);
   const bool tp = two_phase(cell);
   const int packs = tp ? 2 : 1;
@@ -722,6 +724,7 @@ int cell_step_fwd(const CellStepFwdArgs& a, cudaStream_t stream) {
   char* ws = static_cast<char*>(a.workspace);
   __half* Wp = reinterpret_cast<__half*>(ws + L.off_wp);
   if (lstm_cluster_usable(a.cell, a.H)) return lstm_cluster_fwd(a, Wp, stream);
+  if (gru_cluster_usable(a.cell, a.H)) return gru_cluster_fwd(a, Wp, stream);
   __half* S[2] = {reinterpret_cast<__half*>(ws + L.off_a), reinterpret_cast<__half*>(ws + L.off_b)};
   unsigned* counter = reinterpret_cast<unsigned*>(ws + L.off_bar);
   const size_t op = static_cast<size_t>(L.Rp) * L.KPs * 2;
@@ -800,6 +803,7 @@ int cell_step_bwd(const CellStepBwdArgs& a, cudaStream_t stream) {
   char* ws = static_cast<char*>(a.workspace);
   __half* UTp = reinterpret_cast<__half*>(ws + L.off_wp);
   if (lstm_cluster_usable(a.cell, a.H)) return lstm_cluster_bwd(a, UTp, stream);
+  if (gru_cluster_usable(a.cell, a.H)) return gru_cluster_bwd(a, UTp, stream);
   const size_t op = static_cast<size_t>(L.Rp) * L.KPs * 2;
   __half* Ga = reinterpret_cast<__half*>(ws + L.off_a);
   __half* Gb = reinterpret_cast<__half*>(ws + L.off_b);

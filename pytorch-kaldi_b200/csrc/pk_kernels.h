@@ -143,6 +143,11 @@ bool lstm_cluster_usable(int cell, int H);
 long long lstm_cluster_pack_bytes(int H);
 int lstm_cluster_fwd(const CellStepFwdArgs& a, __half* Wc, cudaStream_t stream);
 int lstm_cluster_bwd(const CellStepBwdArgs& a, __half* Wc, cudaStream_t stream);
+// cluster-persistent GRU / minimalGRU kernels (pk_cell_cluster2.cu): two exchanges per step
+bool gru_cluster_usable(int cell, int H);
+long long gru_cluster_pack_bytes(int cell, int H);
+int gru_cluster_fwd(const CellStepFwdArgs& a, __half* Wc, cudaStream_t stream);
+int gru_cluster_bwd(const CellStepBwdArgs& a, __half* Wc, cudaStream_t stream);
 int cell_step_fwd(const CellStepFwdArgs& a, cudaStream_t stream);
 int cell_step_bwd(const CellStepBwdArgs& a, cudaStream_t stream);
 
