@@ -36,6 +36,9 @@ namespace {
 
 constexpr int kRB = 16;  // batch rows per cluster
 constexpr int kNG = 4;   // f, i, o, c~
+constexpr int kIoS = 20;                 // floats per (tensor, unit) row of the I/O staging: 16 batch rows + 4 (bank spread)
+constexpr int kIoFloats = 3 * 8 * kIoS;  // per warp: three [8 units][16 rows] fp32 tensors at a time
+constexpr int kBwdStageMin = 2 * 8 * kIoS * 4;  // backward: the per-warp push stage doubles as I/O staging (two fp32 tensors)
 constexpr int kMaxSmem = 232448 - 1024;  // 227 KB opt-in limit per CTA on sm_100, minus the static part (mbarriers)
 
 struct Geom {
@@ -52,9 +55,10 @@ inline Geom make_geom(int H) {
   g.KPs = 16 * g.KT + 8;                // row pitch in halves (+8: conflict-free ldmatrix)
   g.GLS = kNG * g.UPC + 8;              // row pitch of the local gate-gradient operand
   g.w_cta_bytes = static_cast<size_t>(kNG) * g.UPC * g.KPs * 2;
-  g.smem_fwd = g.w_cta_bytes + static_cast<size_t>(2) * kRB * g.KPs * 2 + static_cast<size_t>(g.MT) * kRB * 8 * 2;
+  g.smem_fwd = g.w_cta_bytes + static_cast<size_t>(2) * kRB * g.KPs * 2 + static_cast<size_t>(g.MT) * kRB * 8 * 2 +
+               static_cast<size_t>(g.MT) * kIoFloats * 4;
   g.smem_bwd = g.w_cta_bytes + static_cast<size_t>(2) * g.CL * kRB * g.UPC * 2 + static_cast<size_t>(kRB) * g.GLS * 2 +
-               static_cast<size_t>(g.MT) * kRB * g.UPC * 2;
+               static_cast<size_t>(g.MT) * std::max(kRB * g.UPC * 2, kBwdStageMin);
   return g;
 }
 
@@ -114,6 +118,7 @@ __global__ void __launch_bounds__(MT * 32, 1) lstm_cluster_fwd_kernel(const CFwd
   __half* Wsm = reinterpret_cast<__half*>(smem);                    // [4][UPC][KPs]
   __half* Ssm = Wsm + static_cast<size_t>(kNG) * UPC * KPs;         // [2][16][KPs] state, double buffered
   __half* stage = Ssm + static_cast<size_t>(2) * kRB * KPs;         // [MT][16][8]
+  float* iobuf = reinterpret_cast<float*>(stage + static_cast<size_t>(MT) * kRB * 8);  // [MT][kIoFloats] I/O staging
   __shared__ __align__(8) uint64_t step_bar[2];                     // one per state buffer: CL * MT * 256 bytes per fill
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, q = lane & 3;
@@ -174,6 +179,32 @@ __global__ void __launch_bounds__(MT * 32, 1) lstm_cluster_fwd_kernel(const CFwd
       mk[i][e] = a.mask ? ((rok[i] && uok[e]) ? __ldg(a.mask + static_cast<long long>(rr) * H + u0 + e) : 0.f)
                         : a.mask_scalar;
     }
+  // Global I/O runs in a second, row-vectorised view of the warp's [8 units][16 rows] tile: lane -> (unit lane / 4, rows
+  // 4 (lane % 4) .. + 3).  In every channel-major tensor these four rows are 16 contiguous, 16-byte aligned bytes when
+  // B % 4 == 0 (and the pitches are multiples of 4), so one LDG.128 / STG.128 moves what the MMA-fragment view needs four
+  // scattered 4-byte accesses for (16 loads + 40 stores per thread and step were ~4000 of the ~7400 cycles of a
+  // step); the two views are exchanged through a per-warp shared-memory tile.
+  const bool vec = (B % 4 == 0) && (a.ldp % 4 == 0) && (a.ldt % 4 == 0);
+  const int io_ul = lane >> 2, io_rg = lane & 3;
+  const int io_u = static_cast<int>(crank) * UPC + warp * 8 + io_ul;
+  const int io_r = cl * kRB + 4 * io_rg;
+  const bool io_ok = vec && (io_u < H) && (io_r < nrows);
+  const int io_d = (io_ok && io_r >= B) ? 1 : 0;
+  const long long io_col0 = io_d ? static_cast<long long>(T - 1) * B + (io_r - B) : io_r;
+  const int io_cstep = io_d ? -B : B;
+  const long long io_chan = static_cast<long long>(io_d * H + io_u) * a.ldt;
+  float* my_io = iobuf + warp * kIoFloats;
+  float* io_w = my_io + io_ul * kIoS + 4 * io_rg;   // this lane's float4 in tensor slot 0 (row-vectorised view)
+  float4 pv[kNG], vhp4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto load_pre_vec = [&](int k) {
+#pragma unroll
+    for (int gg = 0; gg < kNG; ++gg) {
+      pv[gg] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (io_ok)
+        pv[gg] = __ldg(reinterpret_cast<const float4*>(a.PT + static_cast<long long>(gg * H + io_u) * a.ldp + io_col0 +
+                                                       static_cast<long long>(k) * io_cstep));
+    }
+  };
   float pre[kNG][2][2], pnx[kNG][2][2];
   auto load_pre = [&](int k, float (&dst)[kNG][2][2]) {
 #pragma unroll
@@ -188,7 +219,7 @@ __global__ void __launch_bounds__(MT * 32, 1) lstm_cluster_fwd_kernel(const CFwd
                                   static_cast<long long>(k) * cstep[i]);
         }
   };
-  load_pre(0, pre);
+  if (vec) load_pre_vec(0); else load_pre(0, pre);
 
   const uint32_t a_off = static_cast<uint32_t>((((lane & 7) + 8 * ((lane >> 3) & 1)) * KPs + 8 * (lane >> 4)) * 2);
   const uint32_t b_base = smem_u32(Wsm) + static_cast<uint32_t>(((warp * 8 + (lane & 7)) * KPs + 8 * ((lane >> 3) & 1)) * 2);
@@ -201,7 +232,25 @@ __global__ void __launch_bounds__(MT * 32, 1) lstm_cluster_fwd_kernel(const CFwd
   long long tclk = clock64();
   for (int k = 0; k < T; ++k) {
     const int cur = k & 1, nxt = cur ^ 1;
-    if (k + 1 < T) load_pre(k + 1, pnx);     // lands behind the barrier wait and the MMAs
+    if (vec) {
+      // projections of THIS step: row-vectorised registers -> fragment view (two gate blocks per round)
+#pragma unroll
+      for (int r2 = 0; r2 < 2; ++r2) {
+        *reinterpret_cast<float4*>(io_w) = pv[2 * r2];
+        *reinterpret_cast<float4*>(io_w + 8 * kIoS) = pv[2 * r2 + 1];
+        __syncwarp();
+#pragma unroll
+        for (int gl = 0; gl < 2; ++gl)
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) pre[2 * r2 + gl][i][e] = my_io[(gl * 8 + 2 * q + e) * kIoS + g + 8 * i];
+        __syncwarp();
+      }
+      if (k + 1 < T) load_pre_vec(k + 1);    // lands behind the barrier wait and the MMAs
+    } else if (k + 1 < T) {
+      load_pre(k + 1, pnx);
+    }
     CL_CLK(0)
     if (k > 0) mbar_wait(&step_bar[cur], ((k - 1) >> 1) & 1);  // h_{k-1} of every CTA has landed in buffer `cur`
     if (threadIdx.x == 0) mbar_arrive_expect_tx(&step_bar[nxt], tx_bytes);
@@ -273,7 +322,50 @@ __global__ void __launch_bounds__(MT * 32, 1) lstm_cluster_fwd_kernel(const CFwd
       for (int dst = (lane >> 4); dst < a.CL; dst += 2) st_async_v4(mapa_shared(laddr, dst), val, mapa_shared(lbar, dst));
     }
     CL_CLK(4)
-    // ---- saved tensors / outputs (channel-major, natural time), in the shadow of the barrier
+    // ---- saved tensors / outputs (channel-major, natural time), in the shadow of the exchange
+    if (vec) {
+      const long long idx = io_chan + io_col0 + static_cast<long long>(k) * io_cstep;
+      auto put3 = [&](const float (&t0)[2][2], const float (&t1)[2][2], const float (&t2)[2][2]) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            float* w = my_io + (2 * q + e) * kIoS + g + 8 * i;
+            w[0] = t0[i][e];
+            w[8 * kIoS] = t1[i][e];
+            w[16 * kIoS] = t2[i][e];
+          }
+        __syncwarp();
+      };
+      put3(vf, vg, vi);
+      if (io_ok) {
+        if (a.SV0) *reinterpret_cast<float4*>(a.SV0 + idx) = *reinterpret_cast<const float4*>(io_w);
+        if (a.SV1) *reinterpret_cast<float4*>(a.SV1 + idx) = *reinterpret_cast<const float4*>(io_w + 8 * kIoS);
+        if (a.SV2) *reinterpret_cast<float4*>(a.SV2 + idx) = *reinterpret_cast<const float4*>(io_w + 16 * kIoS);
+      }
+      __syncwarp();
+      put3(vo, vc, hn);
+      if (io_ok) {
+        if (a.SV3) *reinterpret_cast<float4*>(a.SV3 + idx) = *reinterpret_cast<const float4*>(io_w);
+        if (a.SV4) *reinterpret_cast<float4*>(a.SV4 + idx) = *reinterpret_cast<const float4*>(io_w + 8 * kIoS);
+        const float4 h4 = *reinterpret_cast<const float4*>(io_w + 16 * kIoS);
+        if (a.HT) *reinterpret_cast<float4*>(a.HT + idx) = h4;
+        if (a.HT16) {
+          uint2 p16;
+          p16.x = pack_f16x2_sat(h4.x, h4.y);
+          p16.y = pack_f16x2_sat(h4.z, h4.w);
+          *reinterpret_cast<uint2*>(a.HT16 + idx) = p16;
+        }
+        if (a.HP16) {
+          uint2 p16;
+          p16.x = pack_f16x2_sat(vhp4.x, vhp4.y);
+          p16.y = pack_f16x2_sat(vhp4.z, vhp4.w);
+          *reinterpret_cast<uint2*>(a.HP16 + idx) = p16;
+        }
+        vhp4 = h4;
+      }
+      __syncwarp();
+    }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const long long col = col0[i] + static_cast<long long>(k) * cstep[i];
@@ -281,27 +373,32 @@ __global__ void __launch_bounds__(MT * 32, 1) lstm_cluster_fwd_kernel(const CFwd
       for (int e = 0; e < 2; ++e) {
         if (rok[i] && uok[e]) {
           const int u = u0 + e;
-          const long long cidx = static_cast<long long>(rd[i] * H + u) * a.ldt + col;
-          if (a.SV0) a.SV0[cidx] = vf[i][e];
-          if (a.SV1) a.SV1[cidx] = vg[i][e];
-          if (a.SV2) a.SV2[cidx] = vi[i][e];
-          if (a.SV3) a.SV3[cidx] = vo[i][e];
-          if (a.SV4) a.SV4[cidx] = vc[i][e];
-          if (a.HT) a.HT[cidx] = hn[i][e];
-          if (a.HT16) a.HT16[cidx] = f16_sat(hn[i][e]);
-          if (a.HP16) a.HP16[cidx] = f16_sat(hp[i][e]);
+          if (!vec) {
+            const long long cidx = static_cast<long long>(rd[i] * H + u) * a.ldt + col;
+            if (a.SV0) a.SV0[cidx] = vf[i][e];
+            if (a.SV1) a.SV1[cidx] = vg[i][e];
+            if (a.SV2) a.SV2[cidx] = vi[i][e];
+            if (a.SV3) a.SV3[cidx] = vo[i][e];
+            if (a.SV4) a.SV4[cidx] = vc[i][e];
+            if (a.HT) a.HT[cidx] = hn[i][e];
+            if (a.HT16) a.HT16[cidx] = f16_sat(hn[i][e]);
+            if (a.HP16) a.HP16[cidx] = f16_sat(hp[i][e]);
+          }
+          // row-major module output / next layer's operand: for a fixed row the tile's units are contiguous
           if (a.Y32) a.Y32[col * a.ldy32 + rd[i] * H + u] = hn[i][e];
           if (a.Y16) a.Y16[col * a.ldy16 + rd[i] * H + u] = f16_sat(hn[i][e]);
         }
         hp[i][e] = hn[i][e];
       }
     }
+    if (!vec) {
 #pragma unroll
-    for (int gg = 0; gg < kNG; ++gg)
+      for (int gg = 0; gg < kNG; ++gg)
 #pragma unroll
-      for (int i = 0; i < 2; ++i)
+        for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int e = 0; e < 2; ++e) pre[gg][i][e] = pnx[gg][i][e];
+          for (int e = 0; e < 2; ++e) pre[gg][i][e] = pnx[gg][i][e];
+    }
     CL_CLK(5)
   }
   mbar_wait(&step_bar[T & 1], ((T - 1) >> 1) & 1);  // drain the last incoming fill
@@ -336,7 +433,8 @@ __global__ void __launch_bounds__(MT * 32, 1) lstm_cluster_bwd_kernel(const CBwd
   __half* Wsm = reinterpret_cast<__half*>(smem);                              // [4][UPC][KPs]
   __half* recv = Wsm + static_cast<size_t>(kNG) * UPC * KPs;                  // [2][CL][16][UPC] partial dh (scaled fp16)
   __half* Gl = recv + static_cast<size_t>(2) * a.CL * BLK;                    // [16][GLS] own gate gradients (A operand)
-  __half* stage = Gl + static_cast<size_t>(kRB) * GLS;                        // [MT][16][UPC] per warp: one partial block
+  __half* stage = Gl + static_cast<size_t>(kRB) * GLS;                        // [MT][STG] per warp: one partial block / I/O staging
+  constexpr int STG = (BLK * 2 > kBwdStageMin ? BLK * 2 : kBwdStageMin) / 2;  // halves per warp
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, q = lane & 3;
   const uint32_t crank = cluster_ctarank();
@@ -414,20 +512,66 @@ __global__ void __launch_bounds__(MT * 32, 1) lstm_cluster_bwd_kernel(const CBwd
         }
       }
   };
-  load_ops(T - 1, op);
-
   const uint32_t w_base = smem_u32(Wsm);
   const uint32_t gl_a = smem_u32(Gl) + static_cast<uint32_t>((((lane & 7) + 8 * ((lane >> 3) & 1)) * GLS + 8 * (lane >> 4)) * 2);
-  __half* my_stage = stage + warp * BLK;
+  __half* my_stage = stage + warp * STG;
   const long long gate_stride = static_cast<long long>(H) * a.ldt;
+  // row-vectorised I/O view (see the forward kernel): lane -> (unit lane / 4, rows 4 (lane % 4) .. + 3)
+  const bool vec = (B % 4 == 0) && (a.ldt % 4 == 0);
+  const int io_ul = lane >> 2, io_rg = lane & 3;
+  const int io_u = static_cast<int>(crank) * UPC + warp * 8 + io_ul;
+  const int io_r = cl * kRB + 4 * io_rg;
+  const bool io_ok = vec && (io_u < H) && (io_r < nrows);
+  const int io_d = (io_ok && io_r >= B) ? 1 : 0;
+  const long long io_col0 = io_d ? static_cast<long long>(T - 1) * B + (io_r - B) : io_r;
+  const int io_cstep = io_d ? -B : B;
+  const long long io_chan = static_cast<long long>(io_d * H + io_u) * a.ldt;
+  float* my_io = reinterpret_cast<float*>(my_stage);
+  float* io_w = my_io + io_ul * kIoS + 4 * io_rg;
+  float4 pv[7];
+  auto load_ops_vec = [&](int k) {
+#pragma unroll
+    for (int j = 0; j < 7; ++j) pv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (io_ok) {
+      const long long idx = io_chan + io_col0 + static_cast<long long>(k) * io_cstep;
+      pv[0] = __ldg(reinterpret_cast<const float4*>(a.dYT + idx));
+      pv[1] = __ldg(reinterpret_cast<const float4*>(a.SV0 + idx));
+      pv[2] = __ldg(reinterpret_cast<const float4*>(a.SV1 + idx));
+      pv[3] = __ldg(reinterpret_cast<const float4*>(a.SV2 + idx));
+      pv[4] = __ldg(reinterpret_cast<const float4*>(a.SV3 + idx));
+      pv[5] = __ldg(reinterpret_cast<const float4*>(a.SV4 + idx));
+      if (k > 0) pv[6] = __ldg(reinterpret_cast<const float4*>(a.SV4 + idx - io_cstep));
+    }
+  };
 
+  if (vec) load_ops_vec(T - 1); else load_ops(T - 1, op);
   const bool clk_on = g_cl_clk[15] != 0 && blockIdx.x == 0 && threadIdx.x == 0;
   long long tclk = clock64();
   for (int it = 0; it < T; ++it) {
     const int k = T - 1 - it;
     const int buf = it & 1;
     if (threadIdx.x == 0 && k > 0) mbar_arrive_expect_tx(&step_bar[buf], tx_bytes);
-    if (k > 0) load_ops(k - 1, opn);
+    if (vec) {
+      // operands of THIS step: row-vectorised registers -> fragment view, two tensors per round
+#pragma unroll
+      for (int r2 = 0; r2 < 4; ++r2) {
+        *reinterpret_cast<float4*>(io_w) = pv[2 * r2];
+        if (2 * r2 + 1 < 7) *reinterpret_cast<float4*>(io_w + 8 * kIoS) = pv[2 * r2 + 1];
+        __syncwarp();
+#pragma unroll
+        for (int jl = 0; jl < 2; ++jl)
+          if (2 * r2 + jl < 7) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) op[2 * r2 + jl][i][e] = my_io[(jl * 8 + 2 * q + e) * kIoS + g + 8 * i];
+          }
+        __syncwarp();
+      }
+      if (k > 0) load_ops_vec(k - 1);
+    } else if (k > 0) {
+      load_ops(k - 1, opn);
+    }
     CL_CLK(8)
     // ---- B: pointwise backward of step k (same algebra as pk_cell_step.cu, M_LSTM); `carry` = U^T dpre of step k+1
 #pragma unroll
@@ -455,10 +599,23 @@ __global__ void __launch_bounds__(MT * 32, 1) lstm_cluster_bwd_kernel(const CBwd
         for (int gg = 0; gg < kNG; ++gg) {
           const __half hv = f16_sat(gq[gg] * s);
           Gl[(g + 8 * i) * GLS + gg * UPC + ul0 + e] = hv;
-          if (ok)
+          if (vec)
+            my_stage[(gg * 8 + 2 * q + e) * kIoS + g + 8 * i] = hv;
+          else if (ok)
             a.GT16[(static_cast<long long>(rd[i]) * kNG + gg) * gate_stride + static_cast<long long>(u0 + e) * a.ldt + col] = hv;
         }
       }
+    }
+    if (vec) {  // gate gradients of the step: 4 rows x 2 bytes per (gate, unit) = one 8-byte store
+      __syncwarp();
+      if (io_ok) {
+        const long long cidx = static_cast<long long>(io_u) * a.ldt + io_col0 + static_cast<long long>(k) * io_cstep;
+#pragma unroll
+        for (int gg = 0; gg < kNG; ++gg)
+          *reinterpret_cast<uint2*>(a.GT16 + (static_cast<long long>(io_d) * kNG + gg) * gate_stride + cidx) =
+              *reinterpret_cast<const uint2*>(my_stage + (gg * 8 + io_ul) * kIoS + 4 * io_rg);
+      }
+      __syncwarp();
     }
     CL_CLK(9)
     // ---- C / D: partial dh_{k-1} for every owner CTA (K-split over this CTA's gate rows), reduce-scatter
@@ -522,12 +679,14 @@ __global__ void __launch_bounds__(MT * 32, 1) lstm_cluster_bwd_kernel(const CBwd
       }
       CL_CLK(12)
     }
+    if (!vec) {
 #pragma unroll
-    for (int j = 0; j < 7; ++j)
+      for (int j = 0; j < 7; ++j)
 #pragma unroll
-      for (int i = 0; i < 2; ++i)
+        for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int e = 0; e < 2; ++e) op[j][i][e] = opn[j][i][e];
+          for (int e = 0; e < 2; ++e) op[j][i][e] = opn[j][i][e];
+    }
   }
   cluster_sync_all();  // no CTA exits while peers may still address its shared memory
 }

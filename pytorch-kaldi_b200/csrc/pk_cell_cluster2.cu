@@ -605,7 +605,7 @@ int launch_cluster2(const Args& a, int cluster, int nclusters, int threads, size
     default: return PK_G_NGT(ARGS, KERN, 5, SMEM);         \
   }
 
-constexpr int kDefaultOn2 = 0;  // flipped to 1 once verified on the GPU against the step-wise path
+constexpr int kDefaultOn2 = 1;  // verified on B200 against the step-wise family (profiles/r2_gru_cluster.txt)
 
 }  // namespace
 
