@@ -55,7 +55,7 @@ inline Geom make_geom(int H) {
   g.KPs = 16 * g.KT + 8;                // row pitch in halves (+8: conflict-free ldmatrix)
   g.GLS = kNG * g.UPC + 8;              // row pitch of the local gate-gradient operand
   g.w_cta_bytes = static_cast<size_t>(kNG) * g.UPC * g.KPs * 2;
-  g.smem_fwd = g.w_cta_bytes + static_cast<size_t>(2) * kRB * g.KPs * 2 + static_cast<size_t>(g.MT) * kRB * 8 * 2 +
+  g.smem_fwd = g.w_cta_bytes + static_cast<size_t>(2) * (2 * g.KT) * 256 + static_cast<size_t>(g.MT) * kRB * 8 * 2 +
                static_cast<size_t>(g.MT) * kIoFloats * 4;
   g.smem_bwd = g.w_cta_bytes + static_cast<size_t>(2) * g.CL * kRB * g.UPC * 2 + static_cast<size_t>(kRB) * g.GLS * 2 +
                static_cast<size_t>(g.MT) * std::max(kRB * g.UPC * 2, kBwdStageMin);
@@ -116,8 +116,12 @@ __global__ void __launch_bounds__(MT * 32, 1) lstm_cluster_fwd_kernel(const CFwd
   extern __shared__ __align__(128) uint8_t smem[];
   const int KPs = a.KPs;
   __half* Wsm = reinterpret_cast<__half*>(smem);                    // [4][UPC][KPs]
-  __half* Ssm = Wsm + static_cast<size_t>(kNG) * UPC * KPs;         // [2][16][KPs] state, double buffered
-  __half* stage = Ssm + static_cast<size_t>(2) * kRB * KPs;         // [MT][16][8]
+  // fp16 state, TILE-MAJOR [2 buffers][2 KT tiles of 8 units][16 rows][8 units]: every ldmatrix 8x8 matrix is 128
+  // contiguous bytes (conflict-free without padding) and a warp's tile is ONE contiguous 256-byte run at the receiver
+  // (16-byte pieces scattered over 16 rows of a row-major buffer reached a third of the DSMEM bandwidth: 2800 cycles
+  // of LSU back-pressure per step in the first version)
+  __half* Ssm = Wsm + static_cast<size_t>(kNG) * UPC * KPs;
+  __half* stage = Ssm + static_cast<size_t>(2) * (2 * a.KT) * 128;  // [MT][16][8]
   float* iobuf = reinterpret_cast<float*>(stage + static_cast<size_t>(MT) * kRB * 8);  // [MT][kIoFloats] I/O staging
   __shared__ __align__(8) uint64_t step_bar[2];                     // one per state buffer: CL * MT * 256 bytes per fill
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -139,7 +143,7 @@ __global__ void __launch_bounds__(MT * 32, 1) lstm_cluster_fwd_kernel(const CFwd
     for (int o = threadIdx.x * 16; o < bytes; o += NTHR * 16) cp_async_16(smem + o, src + o);
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < kRB * KPs; i += NTHR) reinterpret_cast<uint32_t*>(Ssm)[i] = 0u;  // h_{-1} = 0, both buffers
+  for (int i = threadIdx.x; i < 2 * (2 * a.KT) * 64; i += NTHR) reinterpret_cast<uint32_t*>(Ssm)[i] = 0u;  // h_{-1} = 0, both buffers
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   cluster_sync_all();  // nobody pushes into a buffer that is still being zeroed
@@ -221,11 +225,13 @@ __global__ void __launch_bounds__(MT * 32, 1) lstm_cluster_fwd_kernel(const CFwd
   };
   if (vec) load_pre_vec(0); else load_pre(0, pre);
 
-  const uint32_t a_off = static_cast<uint32_t>((((lane & 7) + 8 * ((lane >> 3) & 1)) * KPs + 8 * (lane >> 4)) * 2);
-  const uint32_t b_base = smem_u32(Wsm) + static_cast<uint32_t>(((warp * 8 + (lane & 7)) * KPs + 8 * ((lane >> 3) & 1)) * 2);
+  // A fragment of k-step kt: matrices (rows 0-7 | 8-15) x (tile 2kt | 2kt+1); 512 bytes per k-step
+  const uint32_t a_off = static_cast<uint32_t>(((lane >> 4) * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * 16);
+  // B fragments of TWO k-steps of one gate in one ldmatrix.x4: matrices = k offsets 0, 8, 16, 24 of the warp's 8 weight rows
+  const uint32_t b_base = smem_u32(Wsm) + static_cast<uint32_t>(((warp * 8 + (lane & 7)) * KPs + 8 * (lane >> 3)) * 2);
   const uint32_t gate_bytes = static_cast<uint32_t>(UPC * KPs * 2);
   const uint32_t s_base = smem_u32(Ssm);
-  const uint32_t buf_bytes = static_cast<uint32_t>(kRB * KPs * 2);
+  const uint32_t buf_bytes = static_cast<uint32_t>(2 * a.KT * 256);
   __half* my_stage = stage + warp * kRB * 8;
 
   const bool clk_on = g_cl_clk[15] != 0 && blockIdx.x == 0 && threadIdx.x == 0;
@@ -259,30 +265,48 @@ __global__ void __launch_bounds__(MT * 32, 1) lstm_cluster_fwd_kernel(const CFwd
 #pragma unroll
     for (int gg = 0; gg < kNG; ++gg) acc[gg][0] = acc[gg][1] = acc[gg][2] = acc[gg][3] = 0.f;
     const uint32_t a_base = s_base + cur * buf_bytes + a_off;
-    // fragment loads of k-step kt+1 are issued before the MMAs of kt (the asm statements keep program order, so a
-    // load -> MMA -> load -> MMA sequence would expose the full ldmatrix latency 4 x KT times per step)
+    // fragment loads of the NEXT pair of k-steps are issued before the MMAs of this pair (the asm statements keep
+    // program order, so a load -> MMA -> load -> MMA sequence would expose the ldmatrix latency 4 x KT times per step);
+    // one ldmatrix.x4 per gate brings the B fragments of both k-steps (x2 loads moved half the bytes per instruction)
     {
-      uint32_t fa0[4], fb0[kNG][2], fa1[4], fb1[kNG][2];
-      auto ldk = [&](int kt, uint32_t (&fa)[4], uint32_t (&fb)[kNG][2]) {
-        ldmatrix_x4(a_base + kt * 32, fa[0], fa[1], fa[2], fa[3]);
+      struct Frag { uint32_t a0[4], a1[4], b[kNG][4]; };
+      Frag f0, f1;
+      auto ld2 = [&](int kt, Frag& f) {
+        ldmatrix_x4(a_base + kt * 512, f.a0[0], f.a0[1], f.a0[2], f.a0[3]);
+        ldmatrix_x4(a_base + kt * 512 + 512, f.a1[0], f.a1[1], f.a1[2], f.a1[3]);
 #pragma unroll
-        for (int gg = 0; gg < kNG; ++gg) ldmatrix_x2(b_base + gg * gate_bytes + kt * 32, fb[gg][0], fb[gg][1]);
+        for (int gg = 0; gg < kNG; ++gg)
+          ldmatrix_x4(b_base + gg * gate_bytes + kt * 32, f.b[gg][0], f.b[gg][1], f.b[gg][2], f.b[gg][3]);
       };
-      auto mmk = [&](const uint32_t (&fa)[4], const uint32_t (&fb)[kNG][2]) {
+      auto mm2 = [&](const Frag& f) {
 #pragma unroll
-        for (int gg = 0; gg < kNG; ++gg) mma_m16n8k16_f16(acc[gg], fa, fb[gg][0], fb[gg][1]);
+        for (int gg = 0; gg < kNG; ++gg) mma_m16n8k16_f16(acc[gg], f.a0, f.b[gg][0], f.b[gg][1]);
+#pragma unroll
+        for (int gg = 0; gg < kNG; ++gg) mma_m16n8k16_f16(acc[gg], f.a1, f.b[gg][2], f.b[gg][3]);
       };
       const int KT = a.KT;
-      ldk(0, fa0, fb0);
-      int kt = 0;
-#pragma unroll 2
-      for (; kt + 2 <= KT; kt += 2) {
-        ldk(kt + 1, fa1, fb1);
-        mmk(fa0, fb0);
-        if (kt + 2 < KT) ldk(kt + 2, fa0, fb0);
-        mmk(fa1, fb1);
+      const int KP = KT >> 1;        // pairs of k-steps
+      if (KP > 0) ld2(0, f0);
+      int p2 = 0;
+#pragma unroll 1
+      for (; p2 + 2 <= KP; p2 += 2) {
+        ld2(2 * (p2 + 1), f1);
+        mm2(f0);
+        if (p2 + 2 < KP) ld2(2 * (p2 + 2), f0);
+        mm2(f1);
       }
-      if (kt < KT) mmk(fa0, fb0);
+      if (p2 < KP) mm2(f0);
+      if (KT & 1) {                  // odd tail: one k-step with x2 loads of the B fragments
+        const int kt = KT - 1;
+        uint32_t fa[4];
+        ldmatrix_x4(a_base + kt * 512, fa[0], fa[1], fa[2], fa[3]);
+#pragma unroll
+        for (int gg = 0; gg < kNG; ++gg) {
+          uint32_t b0, b1;
+          ldmatrix_x2(b_base + gg * gate_bytes + kt * 32, b0, b1);
+          mma_m16n8k16_f16(acc[gg], fa, b0, b1);
+        }
+      }
     }
     CL_CLK(2)
     // ---- gates and state update (reference :457-469; gate blocks f, i, o, c~)
@@ -314,7 +338,7 @@ __global__ void __launch_bounds__(MT * 32, 1) lstm_cluster_fwd_kernel(const CFwd
       const int row = lane & 15;
       const uint4 val = *reinterpret_cast<const uint4*>(my_stage + row * 8);
       const uint32_t laddr = s_base + nxt * buf_bytes +
-                             static_cast<uint32_t>((row * KPs + static_cast<int>(crank) * UPC + warp * 8) * 2);
+                             static_cast<uint32_t>(((static_cast<int>(crank) * MT + warp) * kRB + row) * 16);
       const uint32_t lbar = smem_u32(&step_bar[nxt]);
       // data and completion (complete_tx on the receiver's mbarrier) travel in one st.async message: no fence, no
       // cluster barrier on the serial path (barrier.cluster.arrive.release compiles to MEMBAR.ALL.GPU + CGA barrier:
@@ -633,10 +657,13 @@ __global__ void __launch_bounds__(MT * 32, 1) lstm_cluster_bwd_kernel(const CBwd
         const uint32_t b_base = w_base + static_cast<uint32_t>(((lane & 15) * KPs + d * UPC) * 2);
         {  // B fragments of k-step ks+1 are loaded before the MMAs of ks (see the forward kernel)
           uint32_t f0[MT][2], f1[MT][2];
-          auto ldb = [&](int ks, uint32_t (&f)[MT][2]) {
+          auto ldb = [&](int ks, uint32_t (&f)[MT][2]) {  // one x4 per pair of n-tiles (lanes 16-31: the second tile)
 #pragma unroll
-            for (int t = 0; t < MT; ++t)
-              ldmatrix_x2_trans(b_base + static_cast<uint32_t>((ks * 16 * KPs + 8 * t) * 2), f[t][0], f[t][1]);
+            for (int t = 0; t + 1 < MT; t += 2)
+              ldmatrix_x4_trans(b_base + static_cast<uint32_t>((ks * 16 * KPs + 8 * t) * 2) + (lane >> 4) * 16, f[t][0], f[t][1],
+                                f[t + 1][0], f[t + 1][1]);
+            if (MT & 1)
+              ldmatrix_x2_trans(b_base + static_cast<uint32_t>((ks * 16 * KPs + 8 * (MT - 1)) * 2), f[MT - 1][0], f[MT - 1][1]);
           };
           ldb(0, f0);
 #pragma unroll

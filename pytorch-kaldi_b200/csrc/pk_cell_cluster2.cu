@@ -47,7 +47,7 @@ inline Geom2 make_geom2(int cell, int H) {
   g.GAS = 16 * g.KA + 8;
   g.GBS = 16 * g.KB + 8;
   g.w_cta_bytes = static_cast<size_t>(g.NGT) * g.UPC * g.KPs * 2;
-  g.smem_fwd = g.w_cta_bytes + static_cast<size_t>(3) * kRB * g.KPs * 2 + static_cast<size_t>(g.MT) * kRB * 8 * 2;
+  g.smem_fwd = g.w_cta_bytes + static_cast<size_t>(3) * (2 * g.KT) * 256 + static_cast<size_t>(g.MT) * kRB * 8 * 2;
   g.smem_bwd = g.w_cta_bytes + static_cast<size_t>(2) * g.CL * kRB * g.UPC * 2 + static_cast<size_t>(kRB) * (g.GAS + g.GBS) * 2 +
                static_cast<size_t>(g.MT) * kRB * g.UPC * 2;
   return g;
@@ -101,9 +101,12 @@ __global__ void __launch_bounds__(MT * 32, 1) gru_cluster_fwd_kernel(const GFwd 
   __shared__ __align__(8) uint64_t bars[3];  // [0], [1]: the two h buffers; [2]: the x buffer
   const int KPs = a.KPs;
   __half* Wsm = reinterpret_cast<__half*>(smem);                    // [NGT][UPC][KPs]
-  __half* Ssm = Wsm + static_cast<size_t>(NGT) * UPC * KPs;         // [2][16][KPs] h, double buffered
-  __half* Xsm = Ssm + static_cast<size_t>(2) * kRB * KPs;           // [16][KPs] x = gate * h
-  __half* stage = Xsm + static_cast<size_t>(kRB) * KPs;             // [MT][16][8]
+  // operand buffers are TILE-MAJOR [2 KT tiles of 8 units][16 rows][8 units] (see pk_cell_cluster.cu): conflict-free
+  // ldmatrix without padding, and a warp's tile lands as one contiguous 256-byte run at every receiver
+  const int TB = 2 * a.KT * 128;                                    // halves per buffer
+  __half* Ssm = Wsm + static_cast<size_t>(NGT) * UPC * KPs;         // [2] h, double buffered
+  __half* Xsm = Ssm + static_cast<size_t>(2) * TB;                  // x = gate * h
+  __half* stage = Xsm + static_cast<size_t>(TB);                    // [MT][16][8]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, q = lane & 3;
   const uint32_t crank = cluster_ctarank();
@@ -124,7 +127,7 @@ __global__ void __launch_bounds__(MT * 32, 1) gru_cluster_fwd_kernel(const GFwd 
     for (int o = threadIdx.x * 16; o < bytes; o += NTHR * 16) cp_async_16(smem + o, src + o);
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < 3 * kRB * KPs / 2; i += NTHR) reinterpret_cast<uint32_t*>(Ssm)[i] = 0u;  // h_{-1} = 0, x = 0
+  for (int i = threadIdx.x; i < 3 * TB / 2; i += NTHR) reinterpret_cast<uint32_t*>(Ssm)[i] = 0u;  // h_{-1} = 0, x = 0
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   cluster_sync_all();
@@ -178,22 +181,22 @@ __global__ void __launch_bounds__(MT * 32, 1) gru_cluster_fwd_kernel(const GFwd 
   };
   load_pre(0, pre);
 
-  const uint32_t a_off = static_cast<uint32_t>((((lane & 7) + 8 * ((lane >> 3) & 1)) * KPs + 8 * (lane >> 4)) * 2);
+  const uint32_t a_off = static_cast<uint32_t>(((lane >> 4) * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * 16);
   const uint32_t b_base = smem_u32(Wsm) + static_cast<uint32_t>(((warp * 8 + (lane & 7)) * KPs + 8 * ((lane >> 3) & 1)) * 2);
   const uint32_t gate_bytes = static_cast<uint32_t>(UPC * KPs * 2);
   const uint32_t s_base = smem_u32(Ssm), x_base = smem_u32(Xsm);
-  const uint32_t buf_bytes = static_cast<uint32_t>(kRB * KPs * 2);
+  const uint32_t buf_bytes = static_cast<uint32_t>(TB * 2);
   __half* my_stage = stage + warp * kRB * 8;
   const int KT = a.KT;
   const int prow = lane & 15;
-  const uint32_t tile_off = static_cast<uint32_t>((prow * KPs + static_cast<int>(crank) * UPC + warp * 8) * 2);
+  const uint32_t tile_off = static_cast<uint32_t>(((static_cast<int>(crank) * MT + warp) * kRB + prow) * 16);
 
   // NB gate blocks starting at block b0 times the [16 x K] operand at a_base (fragment loads one k-step ahead)
   auto product = [&](uint32_t a_base, int b0, auto& acc, auto nb_tag) {
     constexpr int NB = decltype(nb_tag)::value;
     uint32_t fa0[4], fb0[NB][2], fa1[4], fb1[NB][2];
     auto ldk = [&](int kt, uint32_t (&fa)[4], uint32_t (&fb)[NB][2]) {
-      ldmatrix_x4(a_base + kt * 32, fa[0], fa[1], fa[2], fa[3]);
+      ldmatrix_x4(a_base + kt * 512, fa[0], fa[1], fa[2], fa[3]);
 #pragma unroll
       for (int gg = 0; gg < NB; ++gg) ldmatrix_x2(b_base + (b0 + gg) * gate_bytes + kt * 32, fb[gg][0], fb[gg][1]);
     };
@@ -449,7 +452,9 @@ __global__ void __launch_bounds__(MT * 32, 1) gru_cluster_bwd_kernel(const GBwd 
         const uint32_t b_row = w_base + static_cast<uint32_t>(((row0 + kr) * KPs + d * UPC) * 2);
         uint32_t f[MT][2];
 #pragma unroll
-        for (int t = 0; t < MT; ++t) ldmatrix_x2_trans(b_row + 16 * t, f[t][0], f[t][1]);
+        for (int t = 0; t + 1 < MT; t += 2)  // one x4 per pair of n-tiles (lanes 16-31: the second tile)
+          ldmatrix_x4_trans(b_row + 16 * t + (lane >> 4) * 16, f[t][0], f[t][1], f[t + 1][0], f[t + 1][1]);
+        if (MT & 1) ldmatrix_x2_trans(b_row + 16 * (MT - 1), f[MT - 1][0], f[MT - 1][1]);
 #pragma unroll
         for (int t = 0; t < MT; ++t) mma_m16n8k16_f16(acc[t], af[ks], f[t][0], f[t][1]);
       }

@@ -391,6 +391,14 @@ __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t saddr, uint32_t& r0, 
                : "memory");
 }
 
+// four transposed 8x8 b16 matrices: lanes 0-7 / 8-15 / 16-23 / 24-31 supply the row addresses of matrices 0..3
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t saddr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(saddr)
+               : "memory");
+}
+
 // fp32 pair -> packed fp16x2 (round to nearest, saturating to the finite range)
 // (NaN propagates: fminf / fmaxf would silently turn it into -65504 and hide a diverged run)
 __device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
