@@ -168,9 +168,11 @@ int pk_rnn_layer_bwd(int cell, int T, int B, int H, int ndir, int act, const flo
  * weights, fp32 state, double-buffered fp16 operands). */
 int64_t pk_rnn_step_workspace_bytes(int cell, int T, int B, int H, int ndir, int backward);
 /* number of __global__ launches one pk_rnn_step_fwd / _bwd call performs for this shape (weight packing + the
- * recurrent kernel(s): 2 for the cluster-persistent LSTM kernels (csrc/pk_cell_cluster.cu, H <= 560: 16 batch rows
- * per thread-block cluster, weights stationary in shared memory, state exchanged over distributed shared memory),
- * 2-3 for the cooperative step-wise kernels, T (2T for GRU / minimalGRU) + packs for per-step launches). */
+ * recurrent kernel(s)): 2 for the cluster-persistent kernels (csrc/pk_cell_cluster.cu LSTM, pk_cell_cluster2.cu GRU /
+ * minimalGRU, H <= 560: 16 batch rows per thread-block cluster, the CTA's slice of the recurrent weights stationary in
+ * shared memory, state / partial sums exchanged over distributed shared memory with st.async + mbarrier),
+ * 2-3 for the cooperative step-wise kernels, T (2T for GRU / minimalGRU) + packs for per-step launches.
+ * Environment: PK_LSTM_CLUSTER=0 / PK_GRU_CLUSTER=0 select the step-wise family for A/B runs. */
 int pk_rnn_step_launches(int cell, int T, int B, int H, int ndir, int backward);
 /* 1 if pk_rnn_step_fwd / _bwd run this (cell, H) on the cluster-persistent kernels, 0 for the step-wise family */
 int pk_rnn_step_is_cluster(int cell, int H);

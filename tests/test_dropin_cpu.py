@@ -367,3 +367,50 @@ def test_posterior_and_cntime_readers(tmp_path):
                     seen[key] = one(fd, out)
                     key = ref.read_key(fd)
             assert seen == want
+
+
+def test_fusion_rnn_constructor_surface_matches_the_reference():
+    """fusionRNN_jit / liGRU_layer / FusionLinearConv (reference :719-995, :2057-2099): same parameter / buffer names,
+    shapes and registration order as the reference classes (checkpoints load either way).  The reference hard-codes
+    device="cuda" in its constructors; on a CPU-only host `.to("cuda")` and `torch.tensor(..., device="cuda")` are
+    patched to no-ops for the duration of ITS construction only.  Values are not compared: the reference moves `u` to
+    the GPU before `orthogonal_`, i.e. it draws from the CUDA generator."""
+    p = os.path.join(ROOT, "baseline", "_ref", "neural_networks.py")
+    if not os.path.exists(p):
+        pytest.skip("baseline/_ref missing (python -c 'import __graft_entry__ as g; g.build()')")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_nn_fusion_cpu", p)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    opts = {"fusionRNN_lay": "16,16,16", "fusionRNN_drop": "0.1,0.1,0.1", "batches": "3", "fusionRNN_do_fusion": "True",
+            "fusionRNN_fusion_act": "prelu", "fusionRNN_fusion_reduce": "sum", "fusionRNN_fusion_layer_size": "32",
+            "fusionRNN_number_of_mic": "2", "fusionRNN_bidir": "True", "fusionRNN_act": "prelu,prelu,prelu",
+            "use_cuda": "True", "to_do": "train"}
+    orig_to, orig_tensor = torch.nn.Module.to, torch.tensor
+
+    def to_nocuda(self, *a, **k):
+        a = tuple(x for x in a if x != "cuda")
+        k = {kk: v for kk, v in k.items() if v != "cuda"}
+        return orig_to(self, *a, **k) if (a or k) else self
+
+    def tensor_nocuda(*a, **k):
+        if k.get("device") == "cuda":
+            k.pop("device")
+        return orig_tensor(*a, **k)
+
+    torch.nn.Module.to, torch.tensor = to_nocuda, tensor_nocuda
+    try:
+        r = ref.fusionRNN_jit(dict(opts), 10)
+    finally:
+        torch.nn.Module.to, torch.tensor = orig_to, orig_tensor
+    m = pknn.fusionRNN_jit(dict(opts), 10)
+    assert r.out_dim == m.out_dim == 32
+    rs, ms = r.state_dict(), m.state_dict()
+    assert list(rs.keys()) == list(ms.keys())
+    assert all(rs[k].shape == ms[k].shape and rs[k].dtype == ms[k].dtype for k in rs)
+    assert [n for n, _ in r.named_parameters()] == [n for n, _ in m.named_parameters()]
+    m.load_state_dict(rs)           # a reference checkpoint loads
+    assert m.model[0].do_fusion and not m.model[1].do_fusion and m.model[0].hidden_size == 16
+    assert m.model[1].input_size == 32 and m.model[0].wz.in_features == 5 and m.model[0].wz.number_of_mic == 2
+    with pytest.raises(RuntimeError):   # no CPU path
+        m(torch.zeros(4, 3, 10))
