@@ -414,3 +414,42 @@ def test_fusion_rnn_constructor_surface_matches_the_reference():
     assert m.model[1].input_size == 32 and m.model[0].wz.in_features == 5 and m.model[0].wz.number_of_mic == 2
     with pytest.raises(RuntimeError):   # no CPU path
         m(torch.zeros(4, 3, 10))
+
+
+def test_qlstm_constructor_and_weight_assembly_match_the_reference():
+    """quaternion_neural_networks.QLSTM / QuaternionLinear(Autograd): same numpy / scipy draws -> identical state_dict; the
+    assembled dense matrix equals the reference's Hamilton-product kernel (quaternion_neural_networks.py:375-395)."""
+    p = os.path.join(ROOT, "baseline", "_ref", "quaternion_neural_networks.py")
+    if not os.path.exists(p):
+        pytest.skip("baseline/_ref missing (python -c 'import __graft_entry__ as g; g.build()')")
+    import importlib.util
+    import quaternion_neural_networks as pkq
+    spec = importlib.util.spec_from_file_location("ref_qnn_cpu", p)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    opts = {"lstm_lay": "16,16", "lstm_drop": "0.2,0.2", "lstm_bidir": "True", "lstm_act": "tanh,tanh",
+            "quaternion_init": "quaternion", "use_cuda": "False", "to_do": "train"}
+    for autograd in ("True", "False"):
+        np.random.seed(11)
+        torch.manual_seed(11)
+        r = ref.QLSTM(dict(opts, autograd=autograd), 12)
+        np.random.seed(11)
+        torch.manual_seed(11)
+        m = pkq.QLSTM(dict(opts, autograd=autograd, use_cuda="True"), 12)
+        rs, ms = r.state_dict(), m.state_dict()
+        assert list(rs.keys()) == list(ms.keys()) and r.out_dim == m.out_dim == 32
+        assert all(torch.equal(rs[k], ms[k]) for k in rs), autograd
+        assert [n for n, _ in r.named_parameters()] == [n for n, _ in m.named_parameters()]
+        lay_r, lay_m = r.wix[1], m.wix[1]
+        x = torch.randn(5, 32)
+        want = ref.quaternion_linear(x, lay_r.r_weight, lay_r.i_weight, lay_r.j_weight, lay_r.k_weight, lay_r.bias)
+        got = torch.nn.functional.linear(x, lay_m.dense_weight(), lay_m.dense_bias(x.device))
+        assert torch.allclose(want, got, rtol=1e-6, atol=1e-6)
+    for init in ("unitary", "random"):                       # the other two initialisers, same draws
+        np.random.seed(5)
+        a = ref.QuaternionLinearAutograd(8, 12, weight_init=init)
+        np.random.seed(5)
+        b = pkq.QuaternionLinearAutograd(8, 12, weight_init=init)
+        assert all(torch.equal(x, y) for x, y in zip(a.state_dict().values(), b.state_dict().values())), init
+    with pytest.raises(RuntimeError):                        # no CPU path
+        m(torch.zeros(3, 2, 12))
