@@ -591,7 +591,14 @@ int launch_cluster2(const Args& a, int cluster, int nclusters, int threads, size
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  PK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, Kern, a));
+  // a cluster of this size with this much shared memory per CTA may not be schedulable on every part (GPC sizes,
+  // MIG slices): report -1 and let the caller run the step-wise family instead of failing the layer
+  const cudaError_t le = cudaLaunchKernelEx(&cfg, Kern, a);
+  if (le != cudaSuccess) {
+    cudaGetLastError();
+    set_last_error("cluster-persistent kernel launch failed (%s): falling back to the step-wise kernels", cudaGetErrorString(le));
+    return -1;
+  }
   return 0;
 }
 

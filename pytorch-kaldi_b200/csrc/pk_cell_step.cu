@@ -723,8 +723,9 @@ int cell_step_fwd(const CellStepFwdArgs& a, cudaStream_t stream) {
              "cell_step_fwd: workspace too small (%lld < %zu)", a.workspace_bytes, L.total);
   char* ws = static_cast<char*>(a.workspace);
   __half* Wp = reinterpret_cast<__half*>(ws + L.off_wp);
-  if (lstm_cluster_usable(a.cell, a.H)) return lstm_cluster_fwd(a, Wp, stream);
-  if (gru_cluster_usable(a.cell, a.H)) return gru_cluster_fwd(a, Wp, stream);
+  // cluster-persistent families first; -1 = "cannot launch here" -> the step-wise kernels below (same interface)
+  if (lstm_cluster_usable(a.cell, a.H)) { const int rc = lstm_cluster_fwd(a, Wp, stream); if (rc != -1) return rc; }
+  if (gru_cluster_usable(a.cell, a.H)) { const int rc = gru_cluster_fwd(a, Wp, stream); if (rc != -1) return rc; }
   __half* S[2] = {reinterpret_cast<__half*>(ws + L.off_a), reinterpret_cast<__half*>(ws + L.off_b)};
   unsigned* counter = reinterpret_cast<unsigned*>(ws + L.off_bar);
   const size_t op = static_cast<size_t>(L.Rp) * L.KPs * 2;
@@ -802,8 +803,8 @@ int cell_step_bwd(const CellStepBwdArgs& a, cudaStream_t stream) {
              "cell_step_bwd: workspace too small (%lld < %zu)", a.workspace_bytes, L.total);
   char* ws = static_cast<char*>(a.workspace);
   __half* UTp = reinterpret_cast<__half*>(ws + L.off_wp);
-  if (lstm_cluster_usable(a.cell, a.H)) return lstm_cluster_bwd(a, UTp, stream);
-  if (gru_cluster_usable(a.cell, a.H)) return gru_cluster_bwd(a, UTp, stream);
+  if (lstm_cluster_usable(a.cell, a.H)) { const int rc = lstm_cluster_bwd(a, UTp, stream); if (rc != -1) return rc; }
+  if (gru_cluster_usable(a.cell, a.H)) { const int rc = gru_cluster_bwd(a, UTp, stream); if (rc != -1) return rc; }
   const size_t op = static_cast<size_t>(L.Rp) * L.KPs * 2;
   __half* Ga = reinterpret_cast<__half*>(ws + L.off_a);
   __half* Gb = reinterpret_cast<__half*>(ws + L.off_b);
