@@ -453,3 +453,28 @@ def test_qlstm_constructor_and_weight_assembly_match_the_reference():
         assert all(torch.equal(x, y) for x, y in zip(a.state_dict().values(), b.state_dict().values())), init
     with pytest.raises(RuntimeError):                        # no CPU path
         m(torch.zeros(3, 2, 12))
+
+
+def test_step_entry_point_host_logic(monkeypatch):
+    """Host-side mirrors behind pk_rnn_step_* (no kernel runs): which kernel family takes a (cell, H), how many launches a
+    call makes, and that the workspace covers the cluster kernels' per-CTA weight images (csrc/pk_cell_cluster*.cu)."""
+    pk = pk_native
+    monkeypatch.delenv("PK_LSTM_CLUSTER", raising=False)
+    monkeypatch.delenv("PK_GRU_CLUSTER", raising=False)
+    # defaults: LSTM / GRU / minimalGRU of the shipped recipes run cluster-persistent, one pack + one kernel per call
+    for cell in (pk.CELL_LSTM, pk.CELL_GRU, pk.CELL_MGRU):
+        assert pk.rnn_step_is_cluster(cell, 550)
+        assert pk.rnn_step_launches(cell, 500, 32, 550, 2, False) == pk.rnn_step_launches(cell, 500, 32, 550, 2, True) == 2
+    # what they cannot hold falls to the step-wise family
+    assert not pk.rnn_step_is_cluster(pk.CELL_LSTM, 600) and not pk.rnn_step_is_cluster(pk.CELL_LIGRU, 2048)
+    assert pk.rnn_step_is_cluster(pk.CELL_GRU, 640) and not pk.rnn_step_is_cluster(pk.CELL_GRU, 700)
+    assert pk.rnn_step_launches(pk.CELL_LIGRU, 50, 8, 2048, 2, False) == 51        # pack + one launch per step
+    # per-CTA images: CL * gates * UPC * (16 KT + 8) halves must fit the workspace (H = 550: 14 x 4 x 40 x 568 x 2 bytes)
+    assert pk.rnn_step_workspace_bytes(pk.CELL_LSTM, 500, 32, 550, 2, False) >= 14 * 4 * 40 * 568 * 2
+    assert pk.rnn_step_workspace_bytes(pk.CELL_GRU, 500, 32, 550, 2, True) >= 14 * 3 * 40 * 568 * 2
+    # the A/B switches
+    monkeypatch.setenv("PK_LSTM_CLUSTER", "0")
+    monkeypatch.setenv("PK_GRU_CLUSTER", "0")
+    assert not pk.rnn_step_is_cluster(pk.CELL_LSTM, 550) and not pk.rnn_step_is_cluster(pk.CELL_MGRU, 550)
+    assert pk.rnn_step_launches(pk.CELL_LSTM, 500, 32, 550, 2, True) == 2           # cooperative step-wise kernel + pack
+    assert pk.rnn_step_launches(pk.CELL_GRU, 500, 32, 550, 2, True) == 3            # two packs + cooperative kernel
